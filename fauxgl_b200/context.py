@@ -1,0 +1,392 @@
+"""Python mirror of the reference's ``Context`` (context.go:40-145, 351-439) over
+the C ABI of ``include/fauxgl_b200.h``.
+
+This is the host-side stand-in for the Go package (go/fauxgl is the cgo shim a
+Go program would import; the build image has no Go toolchain).  Names, argument
+meaning and defaults follow the reference so parity tests read like its
+examples.  Every call goes to ``libfauxgl_b200.so`` (hand-written sm_100a CUDA
+kernels); there is no CPU fallback: if the library or a CUDA device is
+missing, construction raises ``FauxglError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import weakref
+from typing import NamedTuple, Optional
+
+import numpy as np
+
+from .color import Color, Transparent
+from .matrix import Identity, Matrix
+from .mesh import Mesh
+from .shader import (SHADER_PHONG, SHADER_SOLID, SHADER_TEXTURE, ImageTexture, PhongShader,
+                     SolidColorShader, TextureShader)
+
+FaceCW, FaceCCW = 1, 2
+CullNone, CullFront, CullBack = 1, 2, 3
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfauxgl_b200.so")
+
+
+class FauxglError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__("fauxgl_b200 error %d: %s" % (status, message))
+        self.status = status
+
+
+class RasterizeInfo(NamedTuple):
+    """context.go:28-38"""
+    TotalPixels: int
+    UpdatedPixels: int
+
+    def Add(self, other):
+        return RasterizeInfo(self.TotalPixels + other.TotalPixels, self.UpdatedPixels + other.UpdatedPixels)
+
+
+class _State(C.Structure):
+    _fields_ = [("read_depth", C.c_int32), ("write_depth", C.c_int32), ("write_color", C.c_int32),
+                ("alpha_blend", C.c_int32), ("wireframe", C.c_int32), ("front_face", C.c_int32),
+                ("cull", C.c_int32), ("_pad", C.c_int32), ("line_width", C.c_double), ("depth_bias", C.c_double)]
+
+
+class _Shader(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("matrix", C.c_double * 16),
+                ("light", C.c_double * 3), ("camera", C.c_double * 3), ("object", C.c_double * 4),
+                ("ambient", C.c_double * 4), ("diffuse", C.c_double * 4), ("specular", C.c_double * 4),
+                ("specular_power", C.c_double), ("color", C.c_double * 4), ("texture", C.c_void_p)]
+
+
+class _MeshDesc(C.Structure):
+    _fields_ = [("ntriangles", C.c_uint64), ("position", C.c_void_p), ("normal", C.c_void_p),
+                ("texture", C.c_void_p), ("color", C.c_void_p), ("nlines", C.c_uint64),
+                ("lposition", C.c_void_p), ("lnormal", C.c_void_p), ("ltexture", C.c_void_p),
+                ("lcolor", C.c_void_p)]
+
+
+class _Info(C.Structure):
+    _fields_ = [("total_pixels", C.c_uint64), ("updated_pixels", C.c_uint64)]
+
+
+class DrawStats(C.Structure):
+    _fields_ = [("prims_in", C.c_uint64), ("records", C.c_uint64), ("pairs", C.c_uint64),
+                ("clip_triangles", C.c_uint64), ("tiles_x", C.c_uint32), ("tiles_y", C.c_uint32),
+                ("tile_w", C.c_uint32), ("tile_h", C.c_uint32), ("kernel_launches", C.c_uint32),
+                ("retries", C.c_uint32)]
+
+
+# every symbol include/fauxgl_b200.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+ABI = [
+    ("fgl_abi_version", C.c_int, []),
+    ("fgl_last_error", C.c_char_p, [_P]),
+    ("fgl_device_count", C.c_int, []),
+    ("fgl_context_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    ("fgl_context_destroy", C.c_int, [_P]),
+    ("fgl_context_size", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("fgl_clear_color", C.c_int, [_P, C.POINTER(C.c_uint8)]),
+    ("fgl_clear_depth", C.c_int, [_P, C.c_double]),
+    ("fgl_mesh_create", C.c_int, [_P, C.POINTER(_MeshDesc), C.POINTER(_P)]),
+    ("fgl_mesh_destroy", C.c_int, [_P]),
+    ("fgl_mesh_counts", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("fgl_mesh_transform", C.c_int, [_P, _P, C.POINTER(C.c_double)]),
+    ("fgl_mesh_read", C.c_int, [_P, _P, _P, _P, _P, _P]),
+    ("fgl_texture_create", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    ("fgl_texture_destroy", C.c_int, [_P]),
+    ("fgl_draw_triangles", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64, C.POINTER(_Info)]),
+    ("fgl_draw_lines", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64, C.POINTER(_Info)]),
+    ("fgl_draw_triangles_async", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64]),
+    ("fgl_draw_lines_async", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64]),
+    ("fgl_sync", C.c_int, [_P, C.POINTER(_Info)]),
+    ("fgl_get_draw_stats", C.c_int, [_P, C.POINTER(DrawStats)]),
+    ("fgl_read_color", C.c_int, [_P, _P, C.c_size_t]),
+    ("fgl_read_depth", C.c_int, [_P, _P]),
+    ("fgl_write_color", C.c_int, [_P, _P, C.c_size_t]),
+    ("fgl_write_depth", C.c_int, [_P, _P]),
+    ("fgl_resolve", C.c_int, [_P, C.c_int, _P]),
+    ("fgl_resolve_device", C.c_int, [_P, C.c_int]),
+    ("fgl_read_resolved", C.c_int, [_P, _P]),
+    ("fgl_composite_pack", C.c_int, [_P, _P]),
+    ("fgl_composite_unpack", C.c_int, [_P, _P]),
+    ("fgl_composite_min", C.c_int, [_P, _P, _P, C.c_uint64]),
+    ("fgl_stream", _P, [_P]),
+    ("fgl_color_device_ptr", _P, [_P]),
+    ("fgl_depth_device_ptr", _P, [_P]),
+]
+
+_lib = None
+
+
+def capi():
+    """Load libfauxgl_b200.so (built by fauxgl_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FauxglError(-3, "libfauxgl_b200.so has not been built (python -m fauxgl_b200.build); "
+                                  "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in ABI:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, ctx=None):
+    if rc != 0:
+        msg = capi().fgl_last_error(ctx)
+        raise FauxglError(rc, msg.decode() if msg else "?")
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+class DeviceTexture:
+    def __init__(self, ctx: "Context", tex: ImageTexture):
+        self.handle = _P()
+        px = np.ascontiguousarray(tex.pixels, dtype=np.uint8)
+        _check(capi().fgl_texture_create(ctx._h, px.ctypes.data, tex.Width, tex.Height, tex.format,
+                                         C.byref(self.handle)), ctx._h)
+        self._fin = weakref.finalize(self, capi().fgl_texture_destroy, self.handle)
+
+
+class DeviceMesh:
+    """Device-resident copy of a Mesh (fgl_mesh_create)."""
+
+    def __init__(self, ctx: "Context", mesh: Mesh, attributes=("position", "normal", "texture", "color")):
+        self.ctx = ctx
+        self.generation = mesh.generation
+        self.num_triangles, self.num_lines = mesh.num_triangles, mesh.num_lines
+        d = _MeshDesc()
+        keep = []
+
+        def arr(a, want):
+            if not want or a is None or len(a) == 0:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            keep.append(a)
+            return a.ctypes.data
+        d.ntriangles = mesh.num_triangles
+        d.position = arr(mesh.position, True)
+        d.normal = arr(mesh.normal, "normal" in attributes)
+        d.texture = arr(mesh.texture, "texture" in attributes)
+        d.color = arr(mesh.color, "color" in attributes)
+        d.nlines = mesh.num_lines
+        d.lposition = arr(mesh.lposition, True)
+        d.lnormal = arr(mesh.lnormal, "normal" in attributes)
+        d.ltexture = arr(mesh.ltexture, "texture" in attributes)
+        d.lcolor = arr(mesh.lcolor, "color" in attributes)
+        self.handle = _P()
+        _check(capi().fgl_mesh_create(ctx._h, C.byref(d), C.byref(self.handle)), ctx._h)
+        self._fin = weakref.finalize(self, capi().fgl_mesh_destroy, self.handle)
+
+    def Transform(self, matrix: Matrix):
+        """Mesh.Transform on the device (mesh.go:167-175)."""
+        m = (C.c_double * 16)(*matrix)
+        _check(capi().fgl_mesh_transform(self.ctx._h, self.handle, m), self.ctx._h)
+
+    def read(self):
+        pos = np.empty((self.num_triangles, 3, 3)); nrm = np.empty((self.num_triangles, 3, 3))
+        lpos = np.empty((self.num_lines, 2, 3)); lnrm = np.empty((self.num_lines, 2, 3))
+        _check(capi().fgl_mesh_read(self.ctx._h, self.handle, _ptr(pos), _ptr(nrm), _ptr(lpos), _ptr(lnrm)), self.ctx._h)
+        return pos, nrm, lpos, lnrm
+
+    def Close(self):
+        self._fin()
+
+
+class Context:
+    """context.go:40-58.  Exported fields keep the reference's names and
+    defaults (NewContext, context.go:60-81).  The device owns the colour and
+    depth buffers between draws; ``Image()`` / ``DepthBuffer`` read them back."""
+
+    def __init__(self, width: int, height: int, device: int = 0):
+        self._h = _P()
+        _check(capi().fgl_context_create(int(width), int(height), int(device), C.byref(self._h)))
+        self._fin = weakref.finalize(self, capi().fgl_context_destroy, self._h)
+        self.Width, self.Height = int(width), int(height)
+        self.ClearColor = Transparent
+        self.Shader = SolidColorShader(Identity(), Color(1.0, 0.0, 1.0, 1.0))
+        self.ReadDepth = True
+        self.WriteDepth = True
+        self.WriteColor = True
+        self.AlphaBlend = True
+        self.Wireframe = False
+        self.FrontFace = FaceCCW
+        self.Cull = CullBack
+        self.LineWidth = 2.0
+        self.DepthBias = 0.0
+        self._meshes = weakref.WeakKeyDictionary()   # Mesh -> DeviceMesh
+        self._textures = weakref.WeakKeyDictionary()  # ImageTexture -> DeviceTexture
+        self._keep = None
+
+    # -- lifetime ------------------------------------------------------------------
+    def Close(self):
+        self._meshes.clear()
+        self._textures.clear()
+        self._fin()
+
+    # -- buffers -------------------------------------------------------------------
+    def Image(self) -> np.ndarray:
+        """context.go:83: ColorBuffer as (H,W,4) uint8, NRGBA."""
+        out = np.empty((self.Height, self.Width, 4), dtype=np.uint8)
+        _check(capi().fgl_read_color(self._h, out.ctypes.data, 0), self._h)
+        return out
+
+    @property
+    def ColorBuffer(self) -> np.ndarray:
+        return self.Image()
+
+    @property
+    def DepthBuffer(self) -> np.ndarray:
+        out = np.empty((self.Height, self.Width), dtype=np.float64)
+        _check(capi().fgl_read_depth(self._h, out.ctypes.data), self._h)
+        return out
+
+    def UploadColorBuffer(self, pix: np.ndarray):
+        pix = np.ascontiguousarray(pix, dtype=np.uint8)
+        assert pix.shape == (self.Height, self.Width, 4)
+        _check(capi().fgl_write_color(self._h, pix.ctypes.data, 0), self._h)
+
+    def UploadDepthBuffer(self, depth: np.ndarray):
+        depth = np.ascontiguousarray(depth, dtype=np.float64)
+        assert depth.shape == (self.Height, self.Width)
+        _check(capi().fgl_write_depth(self._h, depth.ctypes.data), self._h)
+
+    def ClearColorBufferWith(self, color: Color):  # context.go:119
+        c = (C.c_uint8 * 4)(*Color(*color).NRGBA())
+        _check(capi().fgl_clear_color(self._h, c), self._h)
+
+    def ClearColorBuffer(self):  # context.go:133
+        self.ClearColorBufferWith(self.ClearColor)
+
+    def ClearDepthBufferWith(self, value: float):  # context.go:137
+        _check(capi().fgl_clear_depth(self._h, float(value)), self._h)
+
+    def ClearDepthBuffer(self):  # context.go:143
+        self.ClearDepthBufferWith(np.finfo(np.float64).max)
+
+    # -- draw ---------------------------------------------------------------------------
+    def _state(self) -> _State:
+        s = _State()
+        s.read_depth, s.write_depth, s.write_color = int(self.ReadDepth), int(self.WriteDepth), int(self.WriteColor)
+        s.alpha_blend, s.wireframe = int(self.AlphaBlend), int(self.Wireframe)
+        s.front_face, s.cull = int(self.FrontFace), int(self.Cull)
+        s.line_width, s.depth_bias = float(self.LineWidth), float(self.DepthBias)
+        return s
+
+    def _shader(self) -> _Shader:
+        sh = self.Shader
+        # the closed set the Go shim resolves by type switch; anything else has no device
+        # equivalent and is an error, never a CPU fallback
+        if not isinstance(sh, (SolidColorShader, TextureShader, PhongShader)):
+            raise FauxglError(-4, "Shader %r has no device implementation (only SolidColorShader, "
+                                  "TextureShader and PhongShader do); there is no CPU fallback" % type(sh).__name__)
+        d = sh.describe()
+        s = _Shader()
+        s.kind = d["kind"]
+        s.matrix[:] = d["matrix"]
+        for key in ("light", "camera", "object", "ambient", "diffuse", "specular", "color"):
+            if key in d:
+                getattr(s, key)[:] = d[key]
+        s.specular_power = d.get("specular_power", 0.0)
+        tex = d.get("texture")
+        if tex is not None:
+            if not isinstance(tex, ImageTexture):
+                raise FauxglError(-4, "Texture %r has no device implementation" % type(tex).__name__)
+            dt = self._textures.get(tex)
+            if dt is None:
+                dt = DeviceTexture(self, tex)
+                self._textures[tex] = dt
+            s.texture = dt.handle
+            self._keep = dt
+        return s
+
+    def device_mesh(self, mesh) -> DeviceMesh:
+        if isinstance(mesh, DeviceMesh):
+            return mesh
+        dm = self._meshes.get(mesh)
+        if dm is None or dm.generation != mesh.generation:
+            dm = DeviceMesh(self, mesh)
+            self._meshes[mesh] = dm
+        return dm
+
+    def DrawTriangles(self, mesh, first: int = 0, count: Optional[int] = None) -> RasterizeInfo:  # context.go:413
+        dm = self.device_mesh(mesh)
+        count = dm.num_triangles - first if count is None else count
+        info = _Info()
+        st, sh = self._state(), self._shader()
+        _check(capi().fgl_draw_triangles(self._h, C.byref(st), C.byref(sh), dm.handle, first, count, C.byref(info)), self._h)
+        return RasterizeInfo(info.total_pixels, info.updated_pixels)
+
+    def DrawLines(self, mesh, first: int = 0, count: Optional[int] = None) -> RasterizeInfo:  # context.go:391
+        dm = self.device_mesh(mesh)
+        count = dm.num_lines - first if count is None else count
+        info = _Info()
+        st, sh = self._state(), self._shader()
+        _check(capi().fgl_draw_lines(self._h, C.byref(st), C.byref(sh), dm.handle, first, count, C.byref(info)), self._h)
+        return RasterizeInfo(info.total_pixels, info.updated_pixels)
+
+    def DrawMesh(self, mesh) -> RasterizeInfo:  # context.go:435
+        info1 = self.DrawTriangles(mesh)
+        info2 = self.DrawLines(mesh)
+        return info1.Add(info2)
+
+    def DrawMeshAsync(self, mesh, first: int = 0, count: Optional[int] = None):
+        """Enqueue DrawTriangles + DrawLines without waiting (Sync() returns the summed info)."""
+        dm = self.device_mesh(mesh)
+        st, sh = self._state(), self._shader()
+        tcount = dm.num_triangles - first if count is None else count
+        _check(capi().fgl_draw_triangles_async(self._h, C.byref(st), C.byref(sh), dm.handle, first, tcount), self._h)
+        if dm.num_lines and count is None:
+            _check(capi().fgl_draw_lines_async(self._h, C.byref(st), C.byref(sh), dm.handle, 0, dm.num_lines), self._h)
+
+    def Sync(self) -> RasterizeInfo:
+        info = _Info()
+        _check(capi().fgl_sync(self._h, C.byref(info)), self._h)
+        return RasterizeInfo(info.total_pixels, info.updated_pixels)
+
+    def DrawStats(self) -> DrawStats:
+        s = DrawStats()
+        _check(capi().fgl_get_draw_stats(self._h, C.byref(s)), self._h)
+        return s
+
+    # -- SSAA resolve (resize.Resize(..., resize.Bilinear) in the examples) -------------
+    def Resolve(self, factor: int) -> np.ndarray:
+        out = np.empty((self.Height // factor, self.Width // factor, 4), dtype=np.uint8)
+        _check(capi().fgl_resolve(self._h, int(factor), out.ctypes.data), self._h)
+        return out
+
+    def ResolveDevice(self, factor: int):
+        _check(capi().fgl_resolve_device(self._h, int(factor)), self._h)
+
+    # -- sort-last composite -----------------------------------------------------------------
+    def CompositePack(self, keys_dev_ptr: int):
+        _check(capi().fgl_composite_pack(self._h, keys_dev_ptr), self._h)
+
+    def CompositeUnpack(self, keys_dev_ptr: int):
+        _check(capi().fgl_composite_unpack(self._h, keys_dev_ptr), self._h)
+
+    def CompositeMin(self, inout_ptr: int, other_ptr: int, count: int):
+        _check(capi().fgl_composite_min(self._h, inout_ptr, other_ptr, count), self._h)
+
+    # -- interop ---------------------------------------------------------------------------------
+    @property
+    def stream_ptr(self) -> int:
+        return capi().fgl_stream(self._h) or 0
+
+    @property
+    def color_ptr(self) -> int:
+        return capi().fgl_color_device_ptr(self._h) or 0
+
+    @property
+    def depth_ptr(self) -> int:
+        return capi().fgl_depth_device_ptr(self._h) or 0
+
+
+def NewContext(width: int, height: int, device: int = 0) -> Context:
+    """context.go:60"""
+    return Context(width, height, device)

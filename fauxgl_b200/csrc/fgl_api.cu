@@ -1,0 +1,696 @@
+// fgl_api.cu -- the C ABI of include/fauxgl_b200.h: contexts, meshes, textures,
+// draw calls, read-back.  Host-side only; the kernels live in the other
+// translation units.  There is no CPU rendering path in this library: every
+// entry point either runs CUDA kernels or fails with an fgl_status.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "fgl_internal.h"
+
+using namespace fgl;
+
+namespace {
+
+thread_local std::string t_last_error;
+
+int fail(fgl_ctx *ctx, int code, const char *fmt, ...);
+
+#define CK(ctx, expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            cudaGetLastError();                                                                    \
+            return fail(ctx, _e == cudaErrorMemoryAllocation ? FGL_E_OOM : FGL_E_CUDA, "%s: %s", #expr, \
+                        cudaGetErrorString(_e));                                                   \
+        }                                                                                          \
+    } while (0)
+
+}  // namespace
+
+struct fgl_tex {
+    int device;
+    uint8_t *pixels;
+    int w, h, format;
+};
+
+struct fgl_mesh {
+    int device;
+    uint64_t nt, nl;
+    double *tpos, *tnrm, *ttex, *tcol;  // planar, triangles
+    double *lpos, *lnrm, *ltex, *lcol;  // planar, lines
+};
+
+struct fgl_ctx {
+    int device;
+    int w, h;
+    cudaStream_t stream;
+    std::mutex mu;
+    std::string err;
+    uint32_t *color;
+    double *depth;
+    uint32_t *resolved;
+    int rw, rh;
+    WorkBuffers wb;
+    DrawCounters *host_counters;       // pinned
+    DrawCounters *acc_dev;             // async accumulation (total/updated/overflow)
+    bool async_pending;
+    fgl_draw_stats stats;
+};
+
+namespace {
+
+int fail(fgl_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+template <class T>
+cudaError_t dev_alloc(T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    return cudaMalloc(reinterpret_cast<void **>(p), n * sizeof(T));
+}
+template <class T>
+void dev_free(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void free_work(WorkBuffers &wb) {
+    dev_free(wb.prim_nrec); dev_free(wb.prim_rec_off); dev_free(wb.recs); dev_free(wb.rec_tiles);
+    dev_free(wb.rec_npairs); dev_free(wb.rec_pair_off); dev_free(wb.clip_pool);
+    dev_free(wb.pair_key[0]); dev_free(wb.pair_key[1]); dev_free(wb.pair_val[0]); dev_free(wb.pair_val[1]);
+    dev_free(wb.scan_tmp);
+    wb.cap_prims = wb.cap_records = wb.cap_pairs = wb.cap_clip = 0;
+}
+
+// (Re)allocate work buffers so that they hold at least the given capacities.
+int ensure_work(fgl_ctx *c, uint64_t prims, uint64_t records, uint64_t pairs, uint64_t clip) {
+    WorkBuffers &wb = c->wb;
+    const uint64_t LIM = 0xfffffff0ull;
+    if (prims > LIM || records > LIM || pairs > LIM || clip > LIM)
+        return fail(c, FGL_E_INVALID, "draw too large for 32-bit work indices");
+    bool scan_dirty = false;
+    if (prims > wb.cap_prims) {
+        dev_free(wb.prim_nrec); dev_free(wb.prim_rec_off);
+        CK(c, dev_alloc(&wb.prim_nrec, prims));
+        CK(c, dev_alloc(&wb.prim_rec_off, prims + 1));
+        wb.cap_prims = (uint32_t)prims;
+        scan_dirty = true;
+    }
+    if (records > wb.cap_records) {
+        dev_free(wb.recs); dev_free(wb.rec_tiles); dev_free(wb.rec_npairs); dev_free(wb.rec_pair_off);
+        CK(c, dev_alloc(&wb.recs, records));
+        CK(c, dev_alloc(&wb.rec_tiles, records));
+        CK(c, dev_alloc(&wb.rec_npairs, records));
+        CK(c, dev_alloc(&wb.rec_pair_off, records + 1));
+        wb.cap_records = (uint32_t)records;
+        scan_dirty = true;
+    }
+    if (pairs > wb.cap_pairs) {
+        for (int k = 0; k < 2; k++) {
+            dev_free(wb.pair_key[k]); dev_free(wb.pair_val[k]);
+            CK(c, dev_alloc(&wb.pair_key[k], pairs));
+            CK(c, dev_alloc(&wb.pair_val[k], pairs));
+        }
+        wb.cap_pairs = (uint32_t)pairs;
+    }
+    if (clip > wb.cap_clip) {
+        dev_free(wb.clip_pool);
+        CK(c, dev_alloc(&wb.clip_pool, clip));
+        wb.cap_clip = (uint32_t)clip;
+    }
+    if (scan_dirty || !wb.scan_tmp) {
+        const size_t words = std::max(scan_tmp_words(wb.cap_prims), scan_tmp_words(wb.cap_records));
+        if (words > wb.scan_tmp_words) {
+            dev_free(wb.scan_tmp);
+            CK(c, dev_alloc(&wb.scan_tmp, words));
+            wb.scan_tmp_words = (uint32_t)words;
+        }
+    }
+    return FGL_OK;
+}
+
+int check_ctx(fgl_ctx *c) {
+    if (!c) return fail(nullptr, FGL_E_INVALID, "null context");
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, FGL_E_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e));
+    return FGL_OK;
+}
+
+__global__ void k_accumulate(const DrawCounters *cur, DrawCounters *acc) {
+    acc->total_pixels += cur->total_pixels;
+    acc->updated_pixels += cur->updated_pixels;
+    acc->overflow |= cur->overflow;
+    acc->need_records = max(acc->need_records, cur->need_records);
+    acc->need_pairs = max(acc->need_pairs, cur->need_pairs);
+    acc->need_clip = max(acc->need_clip, cur->need_clip);
+}
+
+int build_params(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const fgl_mesh *mesh, uint64_t first,
+                 uint64_t count, bool lines, DrawParams *p) {
+    if (!state || !sh || !mesh) return fail(c, FGL_E_INVALID, "null state/shader/mesh");
+    if (mesh->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on device %d, context on %d", mesh->device, c->device);
+    const uint64_t n = lines ? mesh->nl : mesh->nt;
+    if (first > n || count > n - first) return fail(c, FGL_E_INVALID, "primitive range [%llu,+%llu) outside mesh of %llu",
+                                                    (unsigned long long)first, (unsigned long long)count, (unsigned long long)n);
+    if (sh->kind != FGL_SHADER_SOLID && sh->kind != FGL_SHADER_TEXTURE && sh->kind != FGL_SHADER_PHONG)
+        return fail(c, FGL_E_UNSUPPORTED, "shader kind %d has no device implementation (no CPU fallback)", sh->kind);
+    if (sh->kind == FGL_SHADER_TEXTURE && !sh->texture)
+        return fail(c, FGL_E_INVALID, "TextureShader without a texture");
+    if (sh->texture && sh->texture->device != c->device) return fail(c, FGL_E_INVALID, "texture lives on another device");
+    if (state->cull < FGL_CULL_NONE || state->cull > FGL_CULL_BACK || state->front_face < FGL_FACE_CW ||
+        state->front_face > FGL_FACE_CCW)
+        return fail(c, FGL_E_INVALID, "bad cull/front_face");
+    memset(p, 0, sizeof *p);
+    p->state = *state;
+    p->kind = sh->kind;
+    memcpy(p->matrix, sh->matrix, sizeof p->matrix);
+    memcpy(p->light, sh->light, sizeof p->light);
+    memcpy(p->camera, sh->camera, sizeof p->camera);
+    memcpy(p->object, sh->object, sizeof p->object);
+    memcpy(p->ambient, sh->ambient, sizeof p->ambient);
+    memcpy(p->diffuse, sh->diffuse, sizeof p->diffuse);
+    memcpy(p->specular, sh->specular, sizeof p->specular);
+    p->specular_power = sh->specular_power;
+    memcpy(p->color, sh->color, sizeof p->color);
+    p->object_is_discard = (sh->object[0] == 0 && sh->object[1] == 0 && sh->object[2] == 0 && sh->object[3] == 0);
+    const bool uses_tex = sh->kind == FGL_SHADER_TEXTURE || (sh->kind == FGL_SHADER_PHONG && sh->texture);
+    if (uses_tex) {
+        p->has_texture = 1;
+        p->tex = sh->texture->pixels;
+        p->tex_w = sh->texture->w; p->tex_h = sh->texture->h; p->tex_format = sh->texture->format;
+    }
+    p->width = c->w; p->height = c->h;
+    p->tiles_x = (c->w + TILE_W - 1) / TILE_W;
+    p->tiles_y = (c->h + TILE_H - 1) / TILE_H;
+    // Screen(w, h), matrix.go:119-128
+    const double w2 = (double)c->w / 2, h2 = (double)c->h / 2;
+    const double scr[16] = {w2, 0, 0, w2, 0, -h2, 0, h2, 0, 0, 0.5, 0.5, 0, 0, 0, 1};
+    memcpy(p->screen, scr, sizeof scr);
+    if (lines) {
+        p->mesh.pos = mesh->lpos; p->mesh.nrm = mesh->lnrm; p->mesh.tex = mesh->ltex; p->mesh.col = mesh->lcol;
+        p->mesh.n = (uint32_t)mesh->nl; p->mesh.nverts = 2;
+    } else {
+        p->mesh.pos = mesh->tpos; p->mesh.nrm = mesh->tnrm; p->mesh.tex = mesh->ttex; p->mesh.col = mesh->tcol;
+        p->mesh.n = (uint32_t)mesh->nt; p->mesh.nverts = 3;
+    }
+    p->first = (uint32_t)first; p->count = (uint32_t)count;
+    p->is_lines = lines ? 1 : 0;
+    return FGL_OK;
+}
+
+int enqueue_draw(fgl_ctx *c, const DrawParams &p) {
+    int launches = 0;
+    launches += launch_geometry(p, c->wb, c->stream);
+    int sorted = 0;
+    launches += launch_binning(p, c->wb, &sorted, c->stream);
+    launches += launch_raster(p, c->wb, sorted, c->color, c->depth, c->stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(c, FGL_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+    c->stats.kernel_launches = (uint32_t)launches;
+    return FGL_OK;
+}
+
+int initial_capacity(fgl_ctx *c, const DrawParams &p) {
+    const uint64_t n = p.count;
+    // a primitive normally yields <= 1 record (2 for a line, 6 in wireframe); clipping may add a few
+    const uint64_t per = p.is_lines ? 2 : (p.state.wireframe ? 6 : 1);
+    const uint64_t rec = n * per + n / 8 + 1024;
+    const uint64_t pairs = std::max<uint64_t>(rec * 2, 1u << 16);
+    const uint64_t clip = std::max<uint64_t>(n / 16, 4096);
+    return ensure_work(c, n, std::max<uint64_t>(rec, c->wb.cap_records), std::max<uint64_t>(pairs, c->wb.cap_pairs),
+                       std::max<uint64_t>(clip, c->wb.cap_clip));
+}
+
+int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const fgl_mesh *mesh, uint64_t first,
+                uint64_t count, bool lines, bool async, fgl_raster_info *info) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (info) { info->total_pixels = 0; info->updated_pixels = 0; }
+    DrawParams p;
+    rc = build_params(c, state, sh, mesh, first, count, lines, &p);
+    if (rc) return rc;
+    c->stats.prims_in = count;
+    c->stats.retries = 0;
+    if (count == 0) return FGL_OK;
+    rc = initial_capacity(c, p);
+    if (rc) return rc;
+    if (async) {
+        rc = enqueue_draw(c, p);
+        if (rc) return rc;
+        k_accumulate<<<1, 1, 0, c->stream>>>(c->wb.counters, c->acc_dev);
+        c->async_pending = true;
+        return FGL_OK;
+    }
+    for (int attempt = 0; attempt < 6; attempt++) {
+        rc = enqueue_draw(c, p);
+        if (rc) return rc;
+        CK(c, cudaMemcpyAsync(c->host_counters, c->wb.counters, sizeof(DrawCounters), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        const DrawCounters &hc = *c->host_counters;
+        if (!hc.overflow) {
+            if (info) { info->total_pixels = hc.total_pixels; info->updated_pixels = hc.updated_pixels; }
+            c->stats.records = hc.n_records; c->stats.pairs = hc.n_pairs; c->stats.clip_triangles = hc.n_clip;
+            return FGL_OK;
+        }
+        // the raster kernel did not run (it checks the flag): grow and re-issue
+        c->stats.retries++;
+        const uint64_t rec = std::max<uint64_t>(c->wb.cap_records, (uint64_t)hc.need_records + hc.need_records / 4 + 1024);
+        const uint64_t pairs = std::max<uint64_t>(c->wb.cap_pairs, (uint64_t)hc.need_pairs + hc.need_pairs / 4 + 1024);
+        const uint64_t clip = std::max<uint64_t>(c->wb.cap_clip, (uint64_t)hc.need_clip + hc.need_clip / 4 + 1024);
+        rc = ensure_work(c, p.count, rec, pairs, clip);
+        if (rc) return rc;
+    }
+    return fail(c, FGL_E_OVERFLOW, "work buffers still too small after regrowing");
+}
+
+}  // namespace
+
+extern "C" {
+
+int fgl_abi_version(void) { return FGL_ABI_VERSION; }
+
+const char *fgl_last_error(const fgl_ctx *ctx) {
+    if (ctx && !ctx->err.empty()) return ctx->err.c_str();
+    return t_last_error.c_str();
+}
+
+int fgl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
+    if (!out) return fail(nullptr, FGL_E_INVALID, "null out pointer");
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || width > 65535 * TILE_W / 4 || height > 65535 * TILE_H / 4 ||
+        (uint64_t)width * (uint64_t)height > (1ull << 31))
+        return fail(nullptr, FGL_E_INVALID, "bad framebuffer size %dx%d", width, height);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, FGL_E_NO_DEVICE, "no CUDA device available (%s); fauxgl_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, FGL_E_INVALID, "device %d out of range [0,%d)", device, ndev);
+    CK(nullptr, cudaSetDevice(device));
+    fgl_ctx *c = new (std::nothrow) fgl_ctx();
+    if (!c) return fail(nullptr, FGL_E_OOM, "host allocation failed");
+    c->device = device; c->w = width; c->h = height;
+    c->color = nullptr; c->depth = nullptr; c->resolved = nullptr; c->rw = c->rh = 0;
+    memset(&c->wb, 0, sizeof c->wb);
+    memset(&c->stats, 0, sizeof c->stats);
+    c->host_counters = nullptr; c->acc_dev = nullptr; c->async_pending = false;
+    const size_t npix = (size_t)width * height;
+    cudaError_t err = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = dev_alloc(&c->color, npix);
+    if (err == cudaSuccess) err = dev_alloc(&c->depth, npix);
+    if (err == cudaSuccess) err = dev_alloc(&c->wb.counters, 1);
+    if (err == cudaSuccess) err = dev_alloc(&c->acc_dev, 1);
+    if (err == cudaSuccess) err = cudaMallocHost(reinterpret_cast<void **>(&c->host_counters), sizeof(DrawCounters));
+    c->wb.ntiles = (uint32_t)(((width + TILE_W - 1) / TILE_W) * ((height + TILE_H - 1) / TILE_H));
+    if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_start, c->wb.ntiles);
+    if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_end, c->wb.ntiles);
+    if (err == cudaSuccess) err = cudaMemsetAsync(c->acc_dev, 0, sizeof(DrawCounters), c->stream);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        int rc = fail(nullptr, err == cudaErrorMemoryAllocation ? FGL_E_OOM : FGL_E_CUDA, "context allocation: %s",
+                      cudaGetErrorString(err));
+        fgl_context_destroy(c);
+        return rc;
+    }
+    c->stats.tiles_x = (uint32_t)((width + TILE_W - 1) / TILE_W);
+    c->stats.tiles_y = (uint32_t)((height + TILE_H - 1) / TILE_H);
+    c->stats.tile_w = TILE_W; c->stats.tile_h = TILE_H;
+    // NewContext: image.NewNRGBA is zeroed; ClearDepthBuffer() -> math.MaxFloat64 (context.go:64,79)
+    launch_clear_color(c->color, npix, 0u, c->stream);
+    launch_clear_depth(c->depth, npix, 1.7976931348623157e308, c->stream);
+    err = cudaStreamSynchronize(c->stream);
+    if (err != cudaSuccess) {
+        int rc = fail(nullptr, FGL_E_CUDA, "context init: %s", cudaGetErrorString(err));
+        fgl_context_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return FGL_OK;
+}
+
+int fgl_context_destroy(fgl_ctx *c) {
+    if (!c) return FGL_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_work(c->wb);
+    dev_free(c->wb.tile_start); dev_free(c->wb.tile_end); dev_free(c->wb.counters);
+    dev_free(c->acc_dev); dev_free(c->color); dev_free(c->depth); dev_free(c->resolved);
+    if (c->host_counters) cudaFreeHost(c->host_counters);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return FGL_OK;
+}
+
+int fgl_context_size(const fgl_ctx *c, int *width, int *height) {
+    if (!c) return fail(nullptr, FGL_E_INVALID, "null context");
+    if (width) *width = c->w;
+    if (height) *height = c->h;
+    return FGL_OK;
+}
+
+int fgl_clear_color(fgl_ctx *c, const uint8_t rgba[4]) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!rgba) return fail(c, FGL_E_INVALID, "null colour");
+    std::lock_guard<std::mutex> lock(c->mu);
+    const uint32_t v = (uint32_t)rgba[0] | ((uint32_t)rgba[1] << 8) | ((uint32_t)rgba[2] << 16) | ((uint32_t)rgba[3] << 24);
+    launch_clear_color(c->color, (size_t)c->w * c->h, v, c->stream);
+    CK(c, cudaGetLastError());
+    return FGL_OK;
+}
+
+int fgl_clear_depth(fgl_ctx *c, double value) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(c->mu);
+    launch_clear_depth(c->depth, (size_t)c->w * c->h, value, c->stream);
+    CK(c, cudaGetLastError());
+    return FGL_OK;
+}
+
+// ---- meshes ---------------------------------------------------------------------------------
+
+static int upload_attr(fgl_ctx *c, const double *host, double **planes, uint64_t n, int nverts, int ncomp_in,
+                       int ncomp_out, double *staging) {
+    CK(c, dev_alloc(planes, (size_t)n * nverts * ncomp_out));
+    if (n == 0) return FGL_OK;
+    if (!host) {
+        CK(c, cudaMemsetAsync(*planes, 0, sizeof(double) * n * nverts * ncomp_out, c->stream));
+        return FGL_OK;
+    }
+    CK(c, cudaMemcpyAsync(staging, host, sizeof(double) * n * nverts * ncomp_in, cudaMemcpyHostToDevice, c->stream));
+    launch_mesh_ingest(staging, *planes, (uint32_t)n, nverts, ncomp_in, ncomp_out, c->stream);
+    CK(c, cudaGetLastError());
+    return FGL_OK;
+}
+
+int fgl_mesh_create(fgl_ctx *c, const fgl_mesh_desc *d, fgl_mesh **out) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!d || !out) return fail(c, FGL_E_INVALID, "null mesh description/out pointer");
+    *out = nullptr;
+    if (d->ntriangles > 0xfffffff0ull || d->nlines > 0xfffffff0ull) return fail(c, FGL_E_INVALID, "mesh too large");
+    if ((d->ntriangles && !d->position) || (d->nlines && !d->lposition))
+        return fail(c, FGL_E_INVALID, "position array missing");
+    std::lock_guard<std::mutex> lock(c->mu);
+    fgl_mesh *m = new (std::nothrow) fgl_mesh();
+    if (!m) return fail(c, FGL_E_OOM, "host allocation failed");
+    memset(m, 0, sizeof *m);
+    m->device = c->device; m->nt = d->ntriangles; m->nl = d->nlines;
+    // one staging buffer, reused attribute by attribute (stream order keeps it safe)
+    const size_t stage_elems = std::max<size_t>((size_t)m->nt * 3 * 4, (size_t)m->nl * 2 * 4);
+    double *staging = nullptr;
+    cudaError_t e = dev_alloc(&staging, stage_elems);
+    if (e != cudaSuccess) { delete m; cudaGetLastError(); return fail(c, FGL_E_OOM, "staging: %s", cudaGetErrorString(e)); }
+    rc = upload_attr(c, d->position, &m->tpos, m->nt, 3, 3, 3, staging);
+    if (!rc) rc = upload_attr(c, d->normal, &m->tnrm, m->nt, 3, 3, 3, staging);
+    if (!rc) rc = upload_attr(c, d->texture, &m->ttex, m->nt, 3, 3, 2, staging);
+    if (!rc) rc = upload_attr(c, d->color, &m->tcol, m->nt, 3, 4, 4, staging);
+    if (!rc) rc = upload_attr(c, d->lposition, &m->lpos, m->nl, 2, 3, 3, staging);
+    if (!rc) rc = upload_attr(c, d->lnormal, &m->lnrm, m->nl, 2, 3, 3, staging);
+    if (!rc) rc = upload_attr(c, d->ltexture, &m->ltex, m->nl, 2, 3, 2, staging);
+    if (!rc) rc = upload_attr(c, d->lcolor, &m->lcol, m->nl, 2, 4, 4, staging);
+    cudaError_t se = cudaStreamSynchronize(c->stream);
+    cudaFree(staging);
+    if (!rc && se != cudaSuccess) rc = fail(c, FGL_E_CUDA, "mesh upload: %s", cudaGetErrorString(se));
+    if (rc) { fgl_mesh_destroy(m); return rc; }
+    *out = m;
+    return FGL_OK;
+}
+
+int fgl_mesh_destroy(fgl_mesh *m) {
+    if (!m) return FGL_OK;
+    cudaSetDevice(m->device);
+    dev_free(m->tpos); dev_free(m->tnrm); dev_free(m->ttex); dev_free(m->tcol);
+    dev_free(m->lpos); dev_free(m->lnrm); dev_free(m->ltex); dev_free(m->lcol);
+    delete m;
+    return FGL_OK;
+}
+
+int fgl_mesh_counts(const fgl_mesh *m, uint64_t *nt, uint64_t *nl) {
+    if (!m) return fail(nullptr, FGL_E_INVALID, "null mesh");
+    if (nt) *nt = m->nt;
+    if (nl) *nl = m->nl;
+    return FGL_OK;
+}
+
+int fgl_mesh_transform(fgl_ctx *c, fgl_mesh *m, const double matrix[16]) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!m || !matrix) return fail(c, FGL_E_INVALID, "null mesh/matrix");
+    if (m->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on another device");
+    std::lock_guard<std::mutex> lock(c->mu);
+    launch_mesh_transform(m->tpos, m->tnrm, (uint32_t)m->nt, 3, matrix, c->stream);
+    launch_mesh_transform(m->lpos, m->lnrm, (uint32_t)m->nl, 2, matrix, c->stream);
+    CK(c, cudaGetLastError());
+    return FGL_OK;
+}
+
+static int read_attr(fgl_ctx *c, const double *planes, double *host, uint64_t n, int nverts, int ncomp) {
+    if (!host || n == 0) return FGL_OK;
+    double *staging = nullptr;
+    CK(c, dev_alloc(&staging, (size_t)n * nverts * ncomp));
+    launch_mesh_export(planes, staging, (uint32_t)n, nverts, ncomp, c->stream);
+    cudaError_t e = cudaMemcpyAsync(host, staging, sizeof(double) * n * nverts * ncomp, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(staging);
+    if (e != cudaSuccess) return fail(c, FGL_E_CUDA, "mesh read: %s", cudaGetErrorString(e));
+    return FGL_OK;
+}
+
+int fgl_mesh_read(fgl_ctx *c, const fgl_mesh *m, double *position, double *normal, double *lposition, double *lnormal) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!m) return fail(c, FGL_E_INVALID, "null mesh");
+    std::lock_guard<std::mutex> lock(c->mu);
+    rc = read_attr(c, m->tpos, position, m->nt, 3, 3);
+    if (!rc) rc = read_attr(c, m->tnrm, normal, m->nt, 3, 3);
+    if (!rc) rc = read_attr(c, m->lpos, lposition, m->nl, 2, 3);
+    if (!rc) rc = read_attr(c, m->lnrm, lnormal, m->nl, 2, 3);
+    return rc;
+}
+
+// ---- textures ---------------------------------------------------------------------------------
+
+int fgl_texture_create(fgl_ctx *c, const uint8_t *rgba8, int width, int height, int format, fgl_tex **out) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!rgba8 || !out || width <= 0 || height <= 0) return fail(c, FGL_E_INVALID, "bad texture arguments");
+    if (format != FGL_TEX_RGBA && format != FGL_TEX_NRGBA) return fail(c, FGL_E_INVALID, "bad texture format %d", format);
+    *out = nullptr;
+    std::lock_guard<std::mutex> lock(c->mu);
+    fgl_tex *t = new (std::nothrow) fgl_tex();
+    if (!t) return fail(c, FGL_E_OOM, "host allocation failed");
+    t->device = c->device; t->w = width; t->h = height; t->format = format; t->pixels = nullptr;
+    const size_t bytes = (size_t)width * height * 4;
+    cudaError_t e = dev_alloc(&t->pixels, bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->pixels, rgba8, bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        dev_free(t->pixels);
+        delete t;
+        return fail(c, FGL_E_CUDA, "texture upload: %s", cudaGetErrorString(e));
+    }
+    *out = t;
+    return FGL_OK;
+}
+
+int fgl_texture_destroy(fgl_tex *t) {
+    if (!t) return FGL_OK;
+    cudaSetDevice(t->device);
+    dev_free(t->pixels);
+    delete t;
+    return FGL_OK;
+}
+
+// ---- draws ----------------------------------------------------------------------------------------
+
+int fgl_draw_triangles(fgl_ctx *c, const fgl_state *s, const fgl_shader *sh, const fgl_mesh *m, uint64_t first,
+                       uint64_t count, fgl_raster_info *info) {
+    return draw_common(c, s, sh, m, first, count, false, false, info);
+}
+int fgl_draw_lines(fgl_ctx *c, const fgl_state *s, const fgl_shader *sh, const fgl_mesh *m, uint64_t first,
+                   uint64_t count, fgl_raster_info *info) {
+    return draw_common(c, s, sh, m, first, count, true, false, info);
+}
+int fgl_draw_triangles_async(fgl_ctx *c, const fgl_state *s, const fgl_shader *sh, const fgl_mesh *m, uint64_t first,
+                             uint64_t count) {
+    return draw_common(c, s, sh, m, first, count, false, true, nullptr);
+}
+int fgl_draw_lines_async(fgl_ctx *c, const fgl_state *s, const fgl_shader *sh, const fgl_mesh *m, uint64_t first,
+                         uint64_t count) {
+    return draw_common(c, s, sh, m, first, count, true, true, nullptr);
+}
+
+int fgl_sync(fgl_ctx *c, fgl_raster_info *info) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (info) { info->total_pixels = 0; info->updated_pixels = 0; }
+    if (c->async_pending) {
+        CK(c, cudaMemcpyAsync(c->host_counters, c->acc_dev, sizeof(DrawCounters), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaMemsetAsync(c->acc_dev, 0, sizeof(DrawCounters), c->stream));
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (c->async_pending) {
+        c->async_pending = false;
+        const DrawCounters hc = *c->host_counters;
+        if (hc.overflow) {
+            // grow so that re-issuing the frame succeeds
+            ensure_work(c, c->wb.cap_prims,
+                        std::max<uint64_t>(c->wb.cap_records, (uint64_t)hc.need_records + hc.need_records / 4 + 1024),
+                        std::max<uint64_t>(c->wb.cap_pairs, (uint64_t)hc.need_pairs + hc.need_pairs / 4 + 1024),
+                        std::max<uint64_t>(c->wb.cap_clip, (uint64_t)hc.need_clip + hc.need_clip / 4 + 1024));
+            return fail(c, FGL_E_OVERFLOW, "an async draw outgrew its work buffers (now regrown): re-issue the frame");
+        }
+        if (info) { info->total_pixels = hc.total_pixels; info->updated_pixels = hc.updated_pixels; }
+    }
+    return FGL_OK;
+}
+
+int fgl_get_draw_stats(const fgl_ctx *c, fgl_draw_stats *out) {
+    if (!c || !out) return fail(nullptr, FGL_E_INVALID, "null argument");
+    *out = c->stats;
+    return FGL_OK;
+}
+
+// ---- read-back / upload ---------------------------------------------------------------------------
+
+int fgl_read_color(fgl_ctx *c, uint8_t *dst, size_t stride) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!dst) return fail(c, FGL_E_INVALID, "null destination");
+    if (stride == 0) stride = (size_t)c->w * 4;
+    if (stride < (size_t)c->w * 4) return fail(c, FGL_E_INVALID, "stride too small");
+    std::lock_guard<std::mutex> lock(c->mu);
+    CK(c, cudaMemcpy2DAsync(dst, stride, c->color, (size_t)c->w * 4, (size_t)c->w * 4, c->h, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return FGL_OK;
+}
+int fgl_read_depth(fgl_ctx *c, double *dst) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!dst) return fail(c, FGL_E_INVALID, "null destination");
+    std::lock_guard<std::mutex> lock(c->mu);
+    CK(c, cudaMemcpyAsync(dst, c->depth, sizeof(double) * c->w * c->h, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return FGL_OK;
+}
+int fgl_write_color(fgl_ctx *c, const uint8_t *src, size_t stride) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!src) return fail(c, FGL_E_INVALID, "null source");
+    if (stride == 0) stride = (size_t)c->w * 4;
+    if (stride < (size_t)c->w * 4) return fail(c, FGL_E_INVALID, "stride too small");
+    std::lock_guard<std::mutex> lock(c->mu);
+    CK(c, cudaMemcpy2DAsync(c->color, (size_t)c->w * 4, src, stride, (size_t)c->w * 4, c->h, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return FGL_OK;
+}
+int fgl_write_depth(fgl_ctx *c, const double *src) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!src) return fail(c, FGL_E_INVALID, "null source");
+    std::lock_guard<std::mutex> lock(c->mu);
+    CK(c, cudaMemcpyAsync(c->depth, src, sizeof(double) * c->w * c->h, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return FGL_OK;
+}
+
+// ---- SSAA resolve --------------------------------------------------------------------------------
+
+int fgl_resolve_device(fgl_ctx *c, int factor) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (factor < 1 || factor > 16 || c->w % factor || c->h % factor)
+        return fail(c, FGL_E_INVALID, "resolve factor %d must be in [1,16] and divide %dx%d", factor, c->w, c->h);
+    std::lock_guard<std::mutex> lock(c->mu);
+    const int dw = c->w / factor, dh = c->h / factor;
+    if (dw != c->rw || dh != c->rh) {
+        dev_free(c->resolved);
+        CK(c, dev_alloc(&c->resolved, (size_t)dw * dh));
+        c->rw = dw; c->rh = dh;
+    }
+    if (factor == 1) {
+        // resize.Resize returns its input unchanged when the size already matches
+        CK(c, cudaMemcpyAsync(c->resolved, c->color, (size_t)dw * dh * 4, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        launch_resolve(c->color, c->w, c->h, c->resolved, factor, c->stream);
+        CK(c, cudaGetLastError());
+    }
+    return FGL_OK;
+}
+int fgl_read_resolved(fgl_ctx *c, uint8_t *dst) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!dst) return fail(c, FGL_E_INVALID, "null destination");
+    if (!c->resolved) return fail(c, FGL_E_INVALID, "nothing resolved yet");
+    std::lock_guard<std::mutex> lock(c->mu);
+    CK(c, cudaMemcpyAsync(dst, c->resolved, (size_t)c->rw * c->rh * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return FGL_OK;
+}
+int fgl_resolve(fgl_ctx *c, int factor, uint8_t *dst) {
+    int rc = fgl_resolve_device(c, factor);
+    if (rc) return rc;
+    return fgl_read_resolved(c, dst);
+}
+
+// ---- composite -----------------------------------------------------------------------------------------
+
+int fgl_composite_pack(fgl_ctx *c, void *keys_dev) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!keys_dev) return fail(c, FGL_E_INVALID, "null key buffer");
+    std::lock_guard<std::mutex> lock(c->mu);
+    launch_composite_pack(c->color, c->depth, static_cast<unsigned long long *>(keys_dev), (size_t)c->w * c->h, c->stream);
+    CK(c, cudaGetLastError());
+    return FGL_OK;
+}
+int fgl_composite_unpack(fgl_ctx *c, const void *keys_dev) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!keys_dev) return fail(c, FGL_E_INVALID, "null key buffer");
+    std::lock_guard<std::mutex> lock(c->mu);
+    launch_composite_unpack(c->color, c->depth, static_cast<const unsigned long long *>(keys_dev), (size_t)c->w * c->h, c->stream);
+    CK(c, cudaGetLastError());
+    return FGL_OK;
+}
+int fgl_composite_min(fgl_ctx *c, void *inout, const void *other, uint64_t count) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!inout || !other) return fail(c, FGL_E_INVALID, "null key buffer");
+    std::lock_guard<std::mutex> lock(c->mu);
+    launch_composite_min(static_cast<unsigned long long *>(inout), static_cast<const unsigned long long *>(other), count, c->stream);
+    CK(c, cudaGetLastError());
+    return FGL_OK;
+}
+
+void *fgl_stream(const fgl_ctx *c) { return c ? (void *)c->stream : nullptr; }
+void *fgl_color_device_ptr(const fgl_ctx *c) { return c ? (void *)c->color : nullptr; }
+void *fgl_depth_device_ptr(const fgl_ctx *c) { return c ? (void *)c->depth : nullptr; }
+
+}  // extern "C"

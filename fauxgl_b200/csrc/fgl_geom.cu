@@ -1,0 +1,446 @@
+// fgl_geom.cu -- primitive-parallel front end: mesh ingest (AoS -> planar SoA),
+// Mesh.Transform, and the geometry stage of a draw (Shader.Vertex, outcodes,
+// ClipTriangle/ClipLine, NDC divide, cull, screen transform, wireframe/fat-line
+// expansion, integer bounding box) with order-preserving compaction.
+//
+// Replaces Context.DrawTriangle / DrawLine / drawClippedTriangle /
+// drawClippedLine / line / wireframe (context.go:283-389) and clipping.go.
+// One thread per input primitive; coalesced f64 loads from the position planes.
+// Compaction keeps primitive order: a count pass, an exclusive
+// scan, and an emit pass that re-runs the same arithmetic (deterministic, so
+// both passes agree) and writes each record at its ordered slot.
+#include "fgl_internal.h"
+#include "fgl_math.cuh"
+
+namespace fgl {
+
+// ---- mesh ingest / export / transform ---------------------------------------------------
+
+// aos: [n][nverts][ncomp_in] -> planes[(v*ncomp_out + c)*n + i], c < ncomp_out <= ncomp_in.
+__global__ void k_mesh_ingest(const double *__restrict__ aos, double *__restrict__ planes, uint32_t n, int nverts,
+                              int ncomp_in, int ncomp_out) {
+    const size_t total = (size_t)n * nverts * ncomp_out;
+    for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)(o % n);
+        const uint32_t vc = (uint32_t)(o / n);
+        const uint32_t v = vc / ncomp_out, c = vc % ncomp_out;
+        planes[o] = aos[((size_t)i * nverts + v) * ncomp_in + c];
+    }
+}
+__global__ void k_mesh_export(const double *__restrict__ planes, double *__restrict__ aos, uint32_t n, int nverts,
+                              int ncomp) {
+    const size_t total = (size_t)n * nverts * ncomp;
+    for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)(o % n);
+        const uint32_t vc = (uint32_t)(o / n);
+        const uint32_t v = vc / ncomp, c = vc % ncomp;
+        aos[((size_t)i * nverts + v) * ncomp + c] = planes[o];
+    }
+}
+struct Mat16 { double m[16]; };
+// Mesh.Transform: mesh.go:167-175, triangle.go:66-73, line.go:23-28.
+__global__ void k_mesh_transform(double *__restrict__ pos, double *__restrict__ nrm, uint32_t n, int nverts,
+                                 const Mat16 M) {
+    const size_t total = (size_t)n * nverts;
+    for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)(o % n), v = (uint32_t)(o / n);
+        double *px = pos + (size_t)(v * 3 + 0) * n + i, *py = pos + (size_t)(v * 3 + 1) * n + i,
+               *pz = pos + (size_t)(v * 3 + 2) * n + i;
+        V3 p = m_mul_position(M.m, v3(*px, *py, *pz));
+        *px = p.x; *py = p.y; *pz = p.z;
+        double *nx = nrm + (size_t)(v * 3 + 0) * n + i, *ny = nrm + (size_t)(v * 3 + 1) * n + i,
+               *nz = nrm + (size_t)(v * 3 + 2) * n + i;
+        V3 d = m_mul_direction(M.m, v3(*nx, *ny, *nz));
+        *nx = d.x; *ny = d.y; *nz = d.z;
+    }
+}
+
+static int grid_for(size_t total, int threads) {
+    size_t b = (total + threads - 1) / threads;
+    size_t cap = 148 * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+int launch_mesh_ingest(const double *aos, double *planes, uint32_t n, int nverts, int ncomp_in, int ncomp_out,
+                       cudaStream_t st) {
+    if (n == 0) return 0;
+    k_mesh_ingest<<<grid_for((size_t)n * nverts * ncomp_out, 256), 256, 0, st>>>(aos, planes, n, nverts, ncomp_in,
+                                                                                ncomp_out);
+    return 1;
+}
+int launch_mesh_export(const double *planes, double *aos, uint32_t n, int nverts, int ncomp, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_mesh_export<<<grid_for((size_t)n * nverts * ncomp, 256), 256, 0, st>>>(planes, aos, n, nverts, ncomp);
+    return 1;
+}
+int launch_mesh_transform(double *pos, double *nrm, uint32_t n, int nverts, const double m[16], cudaStream_t st) {
+    if (n == 0) return 0;
+    Mat16 M;
+    for (int i = 0; i < 16; i++) M.m[i] = m[i];
+    k_mesh_transform<<<grid_for((size_t)n * nverts, 256), 256, 0, st>>>(pos, nrm, n, nverts, M);
+    return 1;
+}
+
+// ---- geometry stage -----------------------------------------------------------------------
+
+struct FullVertex {  // vertex.go:3-12 without Texture.Z
+    V3 pos, nrm;
+    double tu, tv;
+    C4 col;
+    V4 out;
+};
+
+FGL_DI int32_t sat_i32(long long v) {
+    const long long L = 1LL << 30;
+    return (int32_t)(v < -L ? -L : (v > L ? L : v));
+}
+
+// Integer bounding box of a screen triangle, context.go:155-160, and its on-screen tile range.
+struct BBox { int32_t x0, x1, y0, y1; bool visible; RecTiles tiles; uint32_t npairs; };
+FGL_DI BBox compute_bbox(const DrawParams &p, V3 s0, V3 s1, V3 s2) {
+    BBox b;
+    const double mnx = go_min(s0.x, go_min(s1.x, s2.x)), mny = go_min(s0.y, go_min(s1.y, s2.y));
+    const double mxx = go_max(s0.x, go_max(s1.x, s2.x)), mxy = go_max(s0.y, go_max(s1.y, s2.y));
+    b.x0 = sat_i32(go_int(floor(mnx)));
+    b.x1 = sat_i32(go_int(ceil(mxx)));
+    b.y0 = sat_i32(go_int(floor(mny)));
+    b.y1 = sat_i32(go_int(ceil(mxy)));
+    // pixels outside the framebuffer are dropped (x-guard rule), so only the
+    // on-screen part of the box is binned
+    const int32_t cx0 = max(b.x0, 0), cx1 = min(b.x1, p.width - 1);
+    const int32_t cy0 = max(b.y0, 0), cy1 = min(b.y1, p.height - 1);
+    b.visible = cx0 <= cx1 && cy0 <= cy1;
+    // The forward-differencing chains are replayed from (x0, y0); a box that starts
+    // millions of pixels off screen (infinite/overflowing coordinates -- the reference
+    // itself would spin for 2^63 iterations on those) is dropped instead of walked.
+    constexpr int32_t FAR = 1 << 22;
+    if (b.x0 < -FAR || b.y0 < -FAR || b.x1 > FAR || b.y1 > FAR) b.visible = false;
+    if (b.visible) {
+        b.tiles.tx0 = (uint16_t)(cx0 / TILE_W); b.tiles.tx1 = (uint16_t)(cx1 / TILE_W);
+        b.tiles.ty0 = (uint16_t)(cy0 / TILE_H); b.tiles.ty1 = (uint16_t)(cy1 / TILE_H);
+        b.npairs = (uint32_t)(b.tiles.tx1 - b.tiles.tx0 + 1) * (uint32_t)(b.tiles.ty1 - b.tiles.ty0 + 1);
+    } else {
+        b.tiles.tx0 = b.tiles.tx1 = b.tiles.ty0 = b.tiles.ty1 = 0;
+        b.npairs = 0;
+    }
+    return b;
+}
+
+struct CountEmit {
+    uint32_t n;
+    static constexpr bool kWrite = false;
+    FGL_DI void record(const DrawParams &p, V3 s0, V3 s1, V3 s2, double w0, double w1, double w2, uint32_t,
+                       uint32_t) {
+        (void)w0; (void)w1; (void)w2;
+        if (compute_bbox(p, s0, s1, s2).visible) n++;
+    }
+    FGL_DI uint32_t pool_alloc(const FullVertex *) { return 0; }
+};
+struct WriteEmit {
+    uint32_t next;
+    const WorkBuffers *wb;
+    static constexpr bool kWrite = true;
+    FGL_DI void record(const DrawParams &p, V3 s0, V3 s1, V3 s2, double w0, double w1, double w2, uint32_t src,
+                       uint32_t flags) {
+        const BBox b = compute_bbox(p, s0, s1, s2);
+        if (!b.visible) return;
+        const uint32_t r = next++;
+        if (r >= wb->cap_records) return;
+        Rec rec;
+        rec.s[0] = s0.x; rec.s[1] = s0.y; rec.s[2] = s0.z;
+        rec.s[3] = s1.x; rec.s[4] = s1.y; rec.s[5] = s1.z;
+        rec.s[6] = s2.x; rec.s[7] = s2.y; rec.s[8] = s2.z;
+        rec.w[0] = w0; rec.w[1] = w1; rec.w[2] = w2;
+        rec.src = src; rec.flags = flags;
+        rec.x0 = b.x0; rec.x1 = b.x1; rec.y0 = b.y0; rec.y1 = b.y1;
+        wb->recs[r] = rec;
+        wb->rec_tiles[r] = b.tiles;
+        wb->rec_npairs[r] = b.npairs;
+    }
+    FGL_DI uint32_t pool_alloc(const FullVertex *v) {
+        const uint32_t slot = atomicAdd(&wb->counters->n_clip, 1u);
+        if (slot >= wb->cap_clip) { atomicOr(&wb->counters->overflow, 4u); return 0; }
+        ClipTri t;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            t.v[k].pos[0] = v[k].pos.x; t.v[k].pos[1] = v[k].pos.y; t.v[k].pos[2] = v[k].pos.z;
+            t.v[k].nrm[0] = v[k].nrm.x; t.v[k].nrm[1] = v[k].nrm.y; t.v[k].nrm[2] = v[k].nrm.z;
+            t.v[k].tex[0] = v[k].tu; t.v[k].tex[1] = v[k].tv;
+            t.v[k].col[0] = v[k].col.r; t.v[k].col[1] = v[k].col.g; t.v[k].col[2] = v[k].col.b; t.v[k].col[3] = v[k].col.a;
+        }
+        wb->clip_pool[slot] = t;
+        return slot;
+    }
+};
+
+FGL_DI uint32_t vmap3(uint32_t a, uint32_t b, uint32_t c) { return a | (b << 2) | (c << 4); }
+
+// Context.line, context.go:283-294: fat line -> two triangles (v1,v0,v0; s11,s01,s00), (v1,v1,v0; s10,s11,s00).
+template <class Emit>
+FGL_DI void emit_line(const DrawParams &p, Emit &e, V3 s0, V3 s1, uint32_t i0, uint32_t i1, double w0, double w1,
+                      uint32_t src, uint32_t srcflags) {
+    const double half = p.state.line_width / 2;
+    const V3 n = v_muls(v_perpendicular(v_sub(s1, s0)), half);
+    s0 = v_add(s0, v_muls(v_normalize(v_sub(s0, s1)), half));
+    s1 = v_add(s1, v_muls(v_normalize(v_sub(s1, s0)), half));
+    const V3 s00 = v_add(s0, n), s01 = v_sub(s0, n), s10 = v_add(s1, n), s11 = v_sub(s1, n);
+    e.record(p, s11, s01, s00, w1, w0, w0, src, srcflags | vmap3(i1, i0, i0));
+    e.record(p, s10, s11, s00, w1, w1, w0, src, srcflags | vmap3(i1, i1, i0));
+}
+
+// drawClippedTriangle, context.go:316-349.  o[] = Output of the three vertices.
+template <class Emit>
+FGL_DI void emit_clipped_triangle(const DrawParams &p, Emit &e, const V4 o[3], uint32_t src, uint32_t srcflags) {
+    V3 ndc0 = v3(o[0].x / o[0].w, o[0].y / o[0].w, o[0].z / o[0].w);
+    V3 ndc1 = v3(o[1].x / o[1].w, o[1].y / o[1].w, o[1].z / o[1].w);
+    V3 ndc2 = v3(o[2].x / o[2].w, o[2].y / o[2].w, o[2].z / o[2].w);
+    double a = (ndc1.x - ndc0.x) * (ndc2.y - ndc0.y) - (ndc2.x - ndc0.x) * (ndc1.y - ndc0.y);
+    uint32_t i0 = 0, i2 = 2;
+    if (a < 0) {
+        V3 t = ndc0; ndc0 = ndc2; ndc2 = t;
+        i0 = 2; i2 = 0;
+    }
+    if (p.state.cull == FGL_CULL_FRONT) a = -a;
+    if (p.state.front_face == FGL_FACE_CW) a = -a;
+    if (p.state.cull != FGL_CULL_NONE && a <= 0) return;
+    const V3 s0 = m_mul_position(p.screen, ndc0), s1 = m_mul_position(p.screen, ndc1),
+             s2 = m_mul_position(p.screen, ndc2);
+    const double w0 = o[i0].w, w1 = o[1].w, w2 = o[i2].w;
+    if (p.state.wireframe) {  // context.go:296-301
+        emit_line(p, e, s0, s1, i0, 1, w0, w1, src, srcflags);
+        emit_line(p, e, s1, s2, 1, i2, w1, w2, src, srcflags);
+        emit_line(p, e, s2, s0, i2, i0, w2, w0, src, srcflags);
+    } else {
+        e.record(p, s0, s1, s2, w0, w1, w2, src, srcflags | vmap3(i0, 1, i2));
+    }
+}
+
+// ---- clipping.go ------------------------------------------------------------------------------
+struct ClipPlane { double px, py, pz, pw, nx, ny, nz, nw; };
+__constant__ ClipPlane c_clip_planes[6] = {  // clipping.go:3-10
+    {1, 0, 0, 1, -1, 0, 0, 1}, {-1, 0, 0, 1, 1, 0, 0, 1}, {0, 1, 0, 1, 0, -1, 0, 1},
+    {0, -1, 0, 1, 0, 1, 0, 1}, {0, 0, 1, 1, 0, 0, -1, 1}, {0, 0, -1, 1, 0, 0, 1, 1},
+};
+FGL_DI bool point_in_front(const ClipPlane &pl, V4 v) {  // clipping.go:16-18
+    return w_dot(w_sub(v, v4(pl.px, pl.py, pl.pz, pl.pw)), v4(pl.nx, pl.ny, pl.nz, pl.nw)) > 0;
+}
+FGL_DI V4 intersect_segment(const ClipPlane &pl, V4 v0, V4 v1) {  // clipping.go:20-26
+    const V4 N = v4(pl.nx, pl.ny, pl.nz, pl.nw);
+    const V4 u = w_sub(v1, v0);
+    const V4 w = w_sub(v0, v4(pl.px, pl.py, pl.pz, pl.pw));
+    const double d = w_dot(N, u);
+    const double n = -w_dot(N, w);
+    return w_add(v0, w_muls(u, n / d));
+}
+constexpr int MAX_POLY = 12;
+// sutherlandHodgman, clipping.go:28-52.  pts holds the input and receives the output.
+__device__ __noinline__ int sutherland_hodgman(V4 *pts, int n) {
+    V4 tmp[MAX_POLY];
+    V4 *in = tmp, *out = pts;
+    for (int pi = 0; pi < 6; pi++) {
+        const ClipPlane pl = c_clip_planes[pi];
+        V4 *t = in; in = out; out = t;
+        const int nin = n;
+        n = 0;
+        if (nin == 0) return 0;
+        V4 s = in[nin - 1];
+        for (int k = 0; k < nin; k++) {
+            const V4 e = in[k];
+            if (point_in_front(pl, e)) {
+                if (!point_in_front(pl, s)) { if (n < MAX_POLY) out[n++] = intersect_segment(pl, s, e); }
+                if (n < MAX_POLY) out[n++] = e;
+            } else if (point_in_front(pl, s)) {
+                if (n < MAX_POLY) out[n++] = intersect_segment(pl, s, e);
+            }
+            s = e;
+        }
+    }
+    if (out != pts)
+        for (int k = 0; k < n; k++) pts[k] = out[k];
+    return n;
+}
+FGL_DI V4 barycentric(V3 p1, V3 p2, V3 p3, V3 p) {  // vertex.go:81-95
+    const V3 v0 = v_sub(p2, p1), v1 = v_sub(p3, p1), v2 = v_sub(p, p1);
+    const double d00 = v_dot(v0, v0), d01 = v_dot(v0, v1), d11 = v_dot(v1, v1);
+    const double d20 = v_dot(v2, v0), d21 = v_dot(v2, v1);
+    const double d = d00 * d11 - d01 * d01;
+    const double v = (d11 * d20 - d01 * d21) / d;
+    const double w = (d00 * d21 - d01 * d20) / d;
+    const double u = 1 - v - w;
+    return v4(u, v, w, 1);
+}
+FGL_DI double interp1(double a, double b, double c, V4 B) {  // vertex.go:49-79 per component
+    double n = 0;
+    n = n + a * B.x;
+    n = n + b * B.y;
+    n = n + c * B.z;
+    return n * B.w;
+}
+__device__ __noinline__ FullVertex interpolate_vertexes(const FullVertex *t, V4 B) {  // vertex.go:18-47
+    FullVertex v;
+    v.pos = v3(interp1(t[0].pos.x, t[1].pos.x, t[2].pos.x, B), interp1(t[0].pos.y, t[1].pos.y, t[2].pos.y, B),
+               interp1(t[0].pos.z, t[1].pos.z, t[2].pos.z, B));
+    v.nrm = v_normalize(v3(interp1(t[0].nrm.x, t[1].nrm.x, t[2].nrm.x, B),
+                           interp1(t[0].nrm.y, t[1].nrm.y, t[2].nrm.y, B),
+                           interp1(t[0].nrm.z, t[1].nrm.z, t[2].nrm.z, B)));
+    v.tu = interp1(t[0].tu, t[1].tu, t[2].tu, B);
+    v.tv = interp1(t[0].tv, t[1].tv, t[2].tv, B);
+    v.col = c4(interp1(t[0].col.r, t[1].col.r, t[2].col.r, B), interp1(t[0].col.g, t[1].col.g, t[2].col.g, B),
+               interp1(t[0].col.b, t[1].col.b, t[2].col.b, B), interp1(t[0].col.a, t[1].col.a, t[2].col.a, B));
+    v.out = v4(interp1(t[0].out.x, t[1].out.x, t[2].out.x, B), interp1(t[0].out.y, t[1].out.y, t[2].out.y, B),
+               interp1(t[0].out.z, t[1].out.z, t[2].out.z, B), interp1(t[0].out.w, t[1].out.w, t[2].out.w, B));
+    return v;
+}
+FGL_DI void fix_normals(FullVertex *t) {  // triangle.go:33-58
+    const V3 e1 = v_sub(t[1].pos, t[0].pos), e2 = v_sub(t[2].pos, t[0].pos);
+    const V3 n = v_normalize(v_cross(e1, e2));
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (v_is_zero(t[k].nrm)) t[k].nrm = n;
+}
+
+FGL_DI double plane_at(const double *base, uint32_t n, uint32_t v, uint32_t ncomp, uint32_t c, uint32_t i) {
+    return __ldg(base + (size_t)(v * ncomp + c) * n + i);
+}
+
+// DrawTriangle's clip branch, context.go:376-384 + ClipTriangle, clipping.go:54-74.
+template <class Emit>
+__device__ __noinline__ void clip_and_emit(const DrawParams &p, Emit &e, uint32_t prim, const V4 o[3]) {
+    const MeshPlanes &m = p.mesh;
+    FullVertex t[3];
+#pragma unroll
+    for (uint32_t v = 0; v < 3; v++) {
+        t[v].pos = v3(plane_at(m.pos, m.n, v, 3, 0, prim), plane_at(m.pos, m.n, v, 3, 1, prim),
+                      plane_at(m.pos, m.n, v, 3, 2, prim));
+        t[v].nrm = v3(plane_at(m.nrm, m.n, v, 3, 0, prim), plane_at(m.nrm, m.n, v, 3, 1, prim),
+                      plane_at(m.nrm, m.n, v, 3, 2, prim));
+        t[v].tu = plane_at(m.tex, m.n, v, 2, 0, prim);
+        t[v].tv = plane_at(m.tex, m.n, v, 2, 1, prim);
+        t[v].col = c4(plane_at(m.col, m.n, v, 4, 0, prim), plane_at(m.col, m.n, v, 4, 1, prim),
+                      plane_at(m.col, m.n, v, 4, 2, prim), plane_at(m.col, m.n, v, 4, 3, prim));
+        t[v].out = o[v];
+    }
+    fix_normals(t);  // NewTriangle(v1, v2, v3), context.go:378
+    const V3 p1 = w_xyz(o[0]), p2 = w_xyz(o[1]), p3 = w_xyz(o[2]);
+    V4 np[MAX_POLY];
+    np[0] = o[0]; np[1] = o[1]; np[2] = o[2];
+    const int n = sutherland_hodgman(np, 3);
+    for (int i = 2; i < n; i++) {
+        FullVertex nv[3];
+        nv[0] = interpolate_vertexes(t, barycentric(p1, p2, p3, w_xyz(np[0])));
+        nv[1] = interpolate_vertexes(t, barycentric(p1, p2, p3, w_xyz(np[i - 1])));
+        nv[2] = interpolate_vertexes(t, barycentric(p1, p2, p3, w_xyz(np[i])));
+        fix_normals(nv);  // NewTriangle, clipping.go:71
+        const V4 oo[3] = {nv[0].out, nv[1].out, nv[2].out};
+        if (Emit::kWrite) {
+            // only allocate a pool slot if the fan triangle survives culling: probe with a counter
+            CountEmit probe{0};
+            emit_clipped_triangle(p, probe, oo, 0, 0);
+            if (probe.n == 0) continue;
+            const uint32_t slot = e.pool_alloc(nv);
+            emit_clipped_triangle(p, e, oo, slot, REC_SRC_POOL);
+        } else {
+            emit_clipped_triangle(p, e, oo, 0, REC_SRC_POOL);
+        }
+    }
+}
+
+template <class Emit>
+FGL_DI void process_triangle(const DrawParams &p, Emit &e, uint32_t prim) {
+    const MeshPlanes &m = p.mesh;
+    V4 o[3];
+    bool outside = false;
+#pragma unroll
+    for (uint32_t v = 0; v < 3; v++) {
+        const V3 pos = v3(plane_at(m.pos, m.n, v, 3, 0, prim), plane_at(m.pos, m.n, v, 3, 1, prim),
+                          plane_at(m.pos, m.n, v, 3, 2, prim));
+        o[v] = m_mul_position_w(p.matrix, pos);  // Shader.Vertex, shader.go:20,39,70
+        outside = outside || w_outside(o[v]);
+    }
+    if (outside) clip_and_emit(p, e, prim, o);
+    else emit_clipped_triangle(p, e, o, prim, 0);
+}
+
+// DrawLine, context.go:351-368 + ClipLine, clipping.go:76-98 + drawClippedLine, context.go:303-314.
+template <class Emit>
+FGL_DI void process_line(const DrawParams &p, Emit &e, uint32_t prim) {
+    const MeshPlanes &m = p.mesh;
+    V4 w1, w2;
+    {
+        const V3 a = v3(plane_at(m.pos, m.n, 0, 3, 0, prim), plane_at(m.pos, m.n, 0, 3, 1, prim),
+                        plane_at(m.pos, m.n, 0, 3, 2, prim));
+        const V3 b = v3(plane_at(m.pos, m.n, 1, 3, 0, prim), plane_at(m.pos, m.n, 1, 3, 1, prim),
+                        plane_at(m.pos, m.n, 1, 3, 2, prim));
+        w1 = m_mul_position_w(p.matrix, a);
+        w2 = m_mul_position_w(p.matrix, b);
+    }
+    if (w_outside(w1) || w_outside(w2)) {
+        for (int pi = 0; pi < 6; pi++) {
+            const ClipPlane pl = c_clip_planes[pi];
+            const bool f1 = point_in_front(pl, w1), f2 = point_in_front(pl, w2);
+            if (f1 && f2) continue;
+            else if (f1) w2 = intersect_segment(pl, w1, w2);
+            else if (f2) w1 = intersect_segment(pl, w2, w1);
+            else return;
+        }
+    }
+    const V3 ndc0 = v3(w1.x / w1.w, w1.y / w1.w, w1.z / w1.w);
+    const V3 ndc1 = v3(w2.x / w2.w, w2.y / w2.w, w2.z / w2.w);
+    const V3 s0 = m_mul_position(p.screen, ndc0), s1 = m_mul_position(p.screen, ndc1);
+    emit_line(p, e, s0, s1, 0, 1, w1.w, w2.w, prim, 0);
+}
+
+__global__ void k_draw_begin(DrawCounters *ctr) {
+    ctr->total_pixels = 0; ctr->updated_pixels = 0;
+    ctr->n_records = 0; ctr->n_pairs = 0; ctr->n_clip = 0; ctr->overflow = 0;
+    ctr->need_records = 0; ctr->need_pairs = 0; ctr->need_clip = 0; ctr->_pad = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_geom_count(const __grid_constant__ DrawParams p, uint32_t *__restrict__ prim_nrec) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.count) return;
+    CountEmit e{0};
+    if (p.is_lines) process_line(p, e, p.first + i);
+    else process_triangle(p, e, p.first + i);
+    prim_nrec[i] = e.n;
+}
+
+__global__ void k_set_nrecords(DrawCounters *ctr, const uint32_t *__restrict__ prim_rec_off, uint32_t count,
+                               uint32_t cap_records) {
+    const uint32_t total = prim_rec_off[count];
+    ctr->n_records = total;
+    ctr->need_records = total;
+    if (total > cap_records) ctr->overflow |= 1u;
+}
+
+__global__ void __launch_bounds__(256)
+k_geom_emit(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.count) return;
+    if (wb.prim_nrec[i] == 0) return;
+    WriteEmit e{wb.prim_rec_off[i], &wb};
+    if (p.is_lines) process_line(p, e, p.first + i);
+    else process_triangle(p, e, p.first + i);
+}
+
+__global__ void k_finish_geom(DrawCounters *ctr, uint32_t cap_clip) {
+    ctr->need_clip = ctr->n_clip;
+    if (ctr->n_clip > cap_clip) ctr->overflow |= 4u;
+}
+
+int launch_geometry(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {
+    int launches = 0;
+    k_draw_begin<<<1, 1, 0, st>>>(wb.counters);
+    launches++;
+    const uint32_t blocks = (p.count + 255) / 256;
+    k_geom_count<<<blocks, 256, 0, st>>>(p, wb.prim_nrec);
+    launches++;
+    launches += launch_exclusive_scan(wb.prim_nrec, wb.prim_rec_off, p.count, nullptr, wb.scan_tmp, st);
+    k_set_nrecords<<<1, 1, 0, st>>>(wb.counters, wb.prim_rec_off, p.count, wb.cap_records);
+    k_geom_emit<<<blocks, 256, 0, st>>>(p, wb);
+    k_finish_geom<<<1, 1, 0, st>>>(wb.counters, wb.cap_clip);
+    launches += 3;
+    return launches;
+}
+
+}  // namespace fgl

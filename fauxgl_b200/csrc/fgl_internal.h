@@ -1,0 +1,128 @@
+// fgl_internal.h -- device-side data layout and kernel launch interfaces shared
+// by the translation units of libfauxgl_b200.so.  Not part of the C ABI.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/fauxgl_b200.h"
+
+namespace fgl {
+
+// ---- screen tiles -------------------------------------------------------------
+// Wide, short tiles: the reference walks each scanline left to right with
+// forward differencing (context.go:207-213), so a span that crosses a tile
+// boundary has to replay the chain from its start; wide tiles keep that rare.
+constexpr int TILE_W = 64;
+constexpr int TILE_H = 16;
+constexpr int TILE_PIX = TILE_W * TILE_H;
+
+// ---- device mesh: planar SoA ----------------------------------------------------
+// plane(attr, v, c)[i] = attr_base[(v * ncomp + c) * n + i]; a warp reading one
+// component of 32 consecutive primitives touches 256 contiguous bytes.
+struct MeshPlanes {
+    const double *pos;  // 3 comps
+    const double *nrm;  // 3 comps
+    const double *tex;  // 2 comps (Texture.X, Texture.Y; .Z is never read by a built-in shader)
+    const double *col;  // 4 comps
+    uint32_t n;         // primitives in the mesh (plane stride)
+    uint32_t nverts;    // 3 for triangles, 2 for lines
+};
+
+// ---- raster record: one screen-space triangle handed to the tile rasteriser ----
+// (the arguments of Context.rasterize, context.go:151, minus the attributes,
+// which stay in the mesh planes / clip pool and are fetched on demand).
+struct __align__(16) Rec {
+    double s[9];     // s0.xyz s1.xyz s2.xyz (screen space)
+    double w[3];     // Output.W of v0 v1 v2
+    uint32_t src;    // primitive index in the mesh planes, or clip-pool triangle index
+    uint32_t flags;  // REC_* below
+    int32_t x0, x1;  // integer bounding box, context.go:155-160 (saturated to int32)
+    int32_t y0, y1;
+};
+static_assert(sizeof(Rec) == 128, "Rec layout");
+
+constexpr uint32_t REC_VMAP_MASK = 0x3f;  // 3 x 2 bits: source vertex of v0,v1,v2
+constexpr uint32_t REC_SRC_POOL = 1u << 6;  // src indexes the clip pool
+
+// Clip pool: vertices produced by ClipTriangle (clipping.go:54-74), AoS.
+struct ClipVertex {
+    double pos[3], nrm[3], tex[2], col[4];
+};
+struct ClipTri { ClipVertex v[3]; };
+
+// Tile bounding box of a record (inclusive), for pair generation.
+struct RecTiles { uint16_t tx0, tx1, ty0, ty1; };
+
+// ---- per-draw device constants ------------------------------------------------------
+struct DrawParams {
+    fgl_state state;
+    // shader (fgl_shader with the texture resolved)
+    int32_t kind, has_texture;
+    double matrix[16], light[3], camera[3], object[4], ambient[4], diffuse[4], specular[4];
+    double specular_power, color[4];
+    const uint8_t *tex;
+    int32_t tex_w, tex_h, tex_format, object_is_discard;
+    // framebuffer
+    int32_t width, height, tiles_x, tiles_y;
+    double screen[16];  // Screen(w,h), matrix.go:119-128
+    // input
+    MeshPlanes mesh;
+    uint32_t first, count;  // primitive range
+    int32_t is_lines;
+};
+
+// Device-side counters/results of one draw (also copied to pinned host memory).
+struct DrawCounters {
+    unsigned long long total_pixels, updated_pixels;
+    unsigned int n_records, n_pairs, n_clip, overflow;  // overflow: bit0 records, bit1 pairs, bit2 clip pool
+    unsigned int need_records, need_pairs, need_clip, _pad;
+};
+
+struct WorkBuffers {
+    // geometry
+    uint32_t *prim_nrec;      // [count]   records emitted per primitive
+    uint32_t *prim_rec_off;   // [count+1] exclusive scan
+    Rec *recs;                // [cap_records]
+    RecTiles *rec_tiles;      // [cap_records]
+    uint32_t *rec_npairs;     // [cap_records]
+    uint32_t *rec_pair_off;   // [cap_records+1]
+    ClipTri *clip_pool;       // [cap_clip]
+    // binning
+    uint32_t *pair_key[2];    // [cap_pairs] tile id (ping-pong for the radix sort)
+    uint32_t *pair_val[2];    // [cap_pairs] record id
+    uint32_t *tile_start;     // [ntiles]
+    uint32_t *tile_end;       // [ntiles]
+    uint32_t *scan_tmp;       // block sums for scans / radix histograms
+    DrawCounters *counters;   // device
+    uint32_t cap_prims, cap_records, cap_pairs, cap_clip, ntiles, scan_tmp_words;
+};
+
+// ---- kernel launchers (each returns the number of kernels it launched) --------------
+int launch_mesh_ingest(const double *aos, double *planes, uint32_t n, int nverts, int ncomp_in, int ncomp_out,
+                       cudaStream_t st);
+int launch_mesh_export(const double *planes, double *aos, uint32_t n, int nverts, int ncomp, cudaStream_t st);
+int launch_mesh_transform(double *pos, double *nrm, uint32_t n, int nverts, const double m[16], cudaStream_t st);
+
+int launch_clear_color(uint32_t *color, size_t npix, uint32_t rgba, cudaStream_t st);
+int launch_clear_depth(double *depth, size_t npix, double v, cudaStream_t st);
+
+// exclusive scan of in[0..n) into out[0..n], out[n] = total; n read from *n_dev if n_dev != nullptr
+// (bounded by n_max).  tmp needs >= scan_tmp_words(n_max) words.
+size_t scan_tmp_words(uint32_t n_max);
+int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n_max, const unsigned int *n_dev,
+                          uint32_t *tmp, cudaStream_t st);
+
+int launch_geometry(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
+int launch_binning(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
+int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,
+                  cudaStream_t st);
+
+int launch_resolve(const uint32_t *src, int sw, int sh, uint32_t *dst, int factor, cudaStream_t st);
+int launch_composite_pack(const uint32_t *color, const double *depth, unsigned long long *keys, size_t npix,
+                          cudaStream_t st);
+int launch_composite_unpack(uint32_t *color, double *depth, const unsigned long long *keys, size_t npix,
+                            cudaStream_t st);
+int launch_composite_min(unsigned long long *inout, const unsigned long long *other, size_t n, cudaStream_t st);
+
+}  // namespace fgl

@@ -1,0 +1,178 @@
+// fgl_post.cu -- framebuffer kernels around the draw: clears, the SSAA resolve
+// and the pack/unpack/min kernels of the sort-last depth composite.
+#include "fgl_internal.h"
+
+namespace fgl {
+
+// ---- clears: ClearColorBufferWith / ClearDepthBufferWith, context.go:119-141 --------------
+__global__ void k_clear_color(uint4 *__restrict__ color4, uint32_t *__restrict__ color, size_t npix, uint32_t rgba) {
+    const size_t n4 = npix / 4;
+    const uint4 v = make_uint4(rgba, rgba, rgba, rgba);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+        color4[i] = v;
+    if (blockIdx.x == 0 && threadIdx.x < (npix & 3)) color[n4 * 4 + threadIdx.x] = rgba;
+}
+__global__ void k_clear_depth(double2 *__restrict__ depth2, double *__restrict__ depth, size_t npix, double value) {
+    const size_t n2 = npix / 2;
+    const double2 v = make_double2(value, value);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
+        depth2[i] = v;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (npix & 1)) depth[npix - 1] = value;
+}
+int launch_clear_color(uint32_t *color, size_t npix, uint32_t rgba, cudaStream_t st) {
+    k_clear_color<<<148 * 8, 256, 0, st>>>(reinterpret_cast<uint4 *>(color), color, npix, rgba);
+    return 1;
+}
+int launch_clear_depth(double *depth, size_t npix, double v, cudaStream_t st) {
+    k_clear_depth<<<148 * 8, 256, 0, st>>>(reinterpret_cast<double2 *>(depth), depth, npix, v);
+    return 1;
+}
+
+// ---- SSAA resolve -------------------------------------------------------------------------------
+// resize.Resize(w/f, h/f, img, resize.Bilinear) of github.com/nfnt/resize on an
+// *image.NRGBA (the call every reference example makes, e.g. examples/teapot.go:60;
+// the library is external and unpinned -- restated from its published algorithm:
+// createWeights8 + resizeNRGBA + resizeRGBA).  Two separable passes of a 2f-tap tent
+// with int16 weights round(tent*256), int32 accumulation, truncating division by the
+// weight sum and clamping after each pass; the first pass premultiplies by alpha.
+// For an integer factor the weights are the same for every output pixel.
+constexpr int RES_OX = 32, RES_OY = 8;  // output tile per CTA
+constexpr int RES_MAX_TAPS = 32;        // factor <= 16
+
+struct ResolveWeights {
+    int16_t coeff[RES_MAX_TAPS];
+    int flen;    // 2 * factor
+    int start0;  // start(y) = factor * y + start0
+    int sum;
+};
+
+__device__ __forceinline__ uint32_t clamp_u8(int v) { return v < 0 ? 0u : (v > 255 ? 255u : (uint32_t)v); }
+
+__global__ void __launch_bounds__(RES_OX *RES_OY)
+k_resolve(const uint32_t *__restrict__ src, int sw, int sh, uint32_t *__restrict__ dst, int dw, int dh, int factor,
+          const ResolveWeights W) {
+    extern __shared__ uint32_t s_temp[];  // [rows][RES_OX] horizontally filtered, premultiplied
+    const int ox0 = blockIdx.x * RES_OX, oy0 = blockIdx.y * RES_OY;
+    const int rows = (RES_OY - 1) * factor + W.flen;  // source rows this tile needs
+    const int row_start = factor * oy0 + W.start0;
+    const int tid = threadIdx.y * RES_OX + threadIdx.x;
+    // pass 1: horizontal (resizeNRGBA)
+    for (int idx = tid; idx < rows * RES_OX; idx += RES_OX * RES_OY) {
+        const int r = idx / RES_OX, c = idx % RES_OX;
+        const int ox = ox0 + c;
+        int sy = row_start + r;
+        uint32_t out = 0;
+        if (ox < dw) {
+            sy = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy);  // pass 2 clamps its (row) index the same way
+            const uint32_t *row = src + (size_t)sy * sw;
+            const int start = factor * ox + W.start0;
+            int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+            for (int i = 0; i < W.flen; i++) {
+                const int coeff = W.coeff[i];
+                if (coeff == 0) continue;
+                int xi = start + i;
+                xi = xi < 0 ? 0 : (xi >= sw - 1 ? sw - 1 : xi);
+                const uint32_t px = __ldg(row + xi);
+                const int a = (int)(px >> 24);
+                const int r8 = (int)(px & 0xff) * a / 0xff;
+                const int g8 = (int)((px >> 8) & 0xff) * a / 0xff;
+                const int b8 = (int)((px >> 16) & 0xff) * a / 0xff;
+                acc0 += coeff * r8; acc1 += coeff * g8; acc2 += coeff * b8; acc3 += coeff * a;
+            }
+            out = clamp_u8(acc0 / W.sum) | (clamp_u8(acc1 / W.sum) << 8) | (clamp_u8(acc2 / W.sum) << 16) |
+                  (clamp_u8(acc3 / W.sum) << 24);
+        }
+        s_temp[idx] = out;
+    }
+    __syncthreads();
+    // pass 2: vertical (resizeRGBA on the transposed temporary)
+    const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
+    if (ox < dw && oy < dh) {
+        int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+        for (int i = 0; i < W.flen; i++) {
+            const int coeff = W.coeff[i];
+            if (coeff == 0) continue;
+            const uint32_t px = s_temp[(threadIdx.y * factor + i) * RES_OX + threadIdx.x];
+            acc0 += coeff * (int)(px & 0xff); acc1 += coeff * (int)((px >> 8) & 0xff);
+            acc2 += coeff * (int)((px >> 16) & 0xff); acc3 += coeff * (int)(px >> 24);
+        }
+        dst[(size_t)oy * dw + ox] = clamp_u8(acc0 / W.sum) | (clamp_u8(acc1 / W.sum) << 8) |
+                                    (clamp_u8(acc2 / W.sum) << 16) | (clamp_u8(acc3 / W.sum) << 24);
+    }
+}
+
+int launch_resolve(const uint32_t *src, int sw, int sh, uint32_t *dst, int factor, cudaStream_t st) {
+    const int dw = sw / factor, dh = sh / factor;
+    // createWeights8 with scale == factor, blur == 1, taps == 2 (Bilinear)
+    ResolveWeights W;
+    const double scale = (double)factor;
+    W.flen = 2 * factor;
+    const double ff = 1.0 / scale;
+    double ix = scale * 0.5 - 0.5;  // y == 0
+    const int start = (int)ix - W.flen / 2 + 1;
+    W.start0 = start;
+    ix -= (double)start;
+    W.sum = 0;
+    for (int i = 0; i < W.flen; i++) {
+        double in = (ix - (double)i) * ff;
+        if (in < 0) in = -in;
+        const double k = in <= 1 ? 1 - in : 0;
+        W.coeff[i] = (int16_t)(k * 256);
+        W.sum += W.coeff[i];
+    }
+    dim3 grid((dw + RES_OX - 1) / RES_OX, (dh + RES_OY - 1) / RES_OY), block(RES_OX, RES_OY);
+    const size_t smem = sizeof(uint32_t) * (size_t)((RES_OY - 1) * factor + W.flen) * RES_OX;
+    k_resolve<<<grid, block, smem, st>>>(src, sw, sh, dst, dw, dh, factor, W);
+    return 1;
+}
+
+// ---- sort-last composite keys -----------------------------------------------------------
+// key = (depth32 << 32 | R<<24 | G<<16 | B<<8 | A) ^ 2^63, stored as int64: the bias makes
+// *signed* 64-bit min (ncclInt64 / torch int64, which every collective library has)
+// order keys by depth first, then colour.
+__device__ __forceinline__ uint32_t depth32(double z) {
+    if (!(z >= 0)) return 0u;          // NaN / negative roundoff
+    if (z > 1) return 0xFFFFFFFFu;     // cleared (MaxFloat64) or beyond the far plane
+    if (z == 1) return 0xFFFFFFFEu;
+    return (uint32_t)(z * 4294967295.0);
+}
+__global__ void k_composite_pack(const uint32_t *__restrict__ color, const double *__restrict__ depth,
+                                 unsigned long long *__restrict__ keys, size_t npix) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t c = color[i];
+        const uint32_t be = ((c & 0xff) << 24) | (((c >> 8) & 0xff) << 16) | (((c >> 16) & 0xff) << 8) | (c >> 24);
+        keys[i] = (((unsigned long long)depth32(depth[i]) << 32) | be) ^ 0x8000000000000000ull;
+    }
+}
+__global__ void k_composite_unpack(uint32_t *__restrict__ color, double *__restrict__ depth,
+                                   const unsigned long long *__restrict__ keys, size_t npix) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[i] ^ 0x8000000000000000ull;
+        const uint32_t be = (uint32_t)k, d32 = (uint32_t)(k >> 32);
+        color[i] = (be >> 24) | (((be >> 16) & 0xff) << 8) | (((be >> 8) & 0xff) << 16) | ((be & 0xff) << 24);
+        depth[i] = d32 == 0xFFFFFFFFu ? 1.7976931348623157e308 : (double)d32 / 4294967295.0;
+    }
+}
+__global__ void k_composite_min(long long *__restrict__ inout, const long long *__restrict__ other, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const long long a = inout[i], b = other[i];
+        inout[i] = b < a ? b : a;
+    }
+}
+int launch_composite_pack(const uint32_t *color, const double *depth, unsigned long long *keys, size_t npix,
+                          cudaStream_t st) {
+    k_composite_pack<<<148 * 8, 256, 0, st>>>(color, depth, keys, npix);
+    return 1;
+}
+int launch_composite_unpack(uint32_t *color, double *depth, const unsigned long long *keys, size_t npix,
+                            cudaStream_t st) {
+    k_composite_unpack<<<148 * 8, 256, 0, st>>>(color, depth, keys, npix);
+    return 1;
+}
+int launch_composite_min(unsigned long long *inout, const unsigned long long *other, size_t n, cudaStream_t st) {
+    k_composite_min<<<148 * 8, 256, 0, st>>>(reinterpret_cast<long long *>(inout),
+                                            reinterpret_cast<const long long *>(other), n);
+    return 1;
+}
+
+}  // namespace fgl

@@ -1,0 +1,197 @@
+/*
+ * fauxgl_b200.h -- C ABI of the B200-native rasterisation back end for
+ * fogleman/fauxgl's DrawMesh path.
+ *
+ * The reference is pure Go and has no FFI seam; the drop-in boundary is its
+ * exported Context method set.  Each entry point below replaces
+ * the reference function cited beside it (file:line into the reference tree)
+ * and is what the cgo shim in go/fauxgl binds.
+ *
+ * Conventions: plain C, no exceptions cross the boundary.  Every function
+ * returns 0 on success or a negative fgl_status; fgl_last_error() gives the
+ * message.  Handles are opaque.  The caller owns host buffers, the library
+ * owns device buffers.  All entry points are thread-safe per context (calls on
+ * one context are serialised by a mutex, matching the reference's contract
+ * that concurrent DrawTriangle calls on one Context are legal) and may be
+ * called from any OS thread (goroutines migrate): each call selects the
+ * context's device itself.  There is no CPU fallback anywhere behind this
+ * interface: without a CUDA device fgl_context_create fails.
+ */
+#ifndef FAUXGL_B200_H
+#define FAUXGL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGL_ABI_VERSION 1
+
+typedef enum {
+    FGL_OK = 0,
+    FGL_E_INVALID = -1,      /* bad argument */
+    FGL_E_CUDA = -2,         /* CUDA runtime error (message has the detail) */
+    FGL_E_NO_DEVICE = -3,    /* no usable CUDA device: there is no CPU fallback */
+    FGL_E_UNSUPPORTED = -4,  /* e.g. a Shader kind with no device implementation */
+    FGL_E_OOM = -5,
+    FGL_E_OVERFLOW = -6      /* async draw outgrew its work buffers; re-issue the frame */
+} fgl_status;
+
+typedef struct fgl_ctx fgl_ctx;    /* context.go:40-58  Context            */
+typedef struct fgl_mesh fgl_mesh;  /* mesh.go:9-13      Mesh (device copy) */
+typedef struct fgl_tex fgl_tex;    /* texture.go:21-25  ImageTexture       */
+
+/* context.go:11-26 */
+enum { FGL_FACE_CW = 1, FGL_FACE_CCW = 2 };
+enum { FGL_CULL_NONE = 1, FGL_CULL_FRONT = 2, FGL_CULL_BACK = 3 };
+/* shader.go:11,30,49 -- the closed set of built-in shaders */
+enum { FGL_SHADER_SOLID = 1, FGL_SHADER_TEXTURE = 2, FGL_SHADER_PHONG = 3 };
+/* Which Go image type the texture decoded to; decides the RGBA() conversion
+ * MakeColor applies (color.go:25-29): *image.RGBA or *image.NRGBA. */
+enum { FGL_TEX_RGBA = 0, FGL_TEX_NRGBA = 1 };
+
+/* The render state fields of Context, context.go:47-55. */
+typedef struct {
+    int32_t read_depth, write_depth, write_color, alpha_blend, wireframe;
+    int32_t front_face;   /* FGL_FACE_*  */
+    int32_t cull;         /* FGL_CULL_*  */
+    int32_t _pad;
+    double line_width;
+    double depth_bias;
+} fgl_state;
+
+/* SolidColorShader / TextureShader / PhongShader, shader.go:11-14,30-33,49-59. */
+typedef struct {
+    int32_t kind;         /* FGL_SHADER_* */
+    int32_t _pad;
+    double matrix[16];    /* row-major X00..X33, matrix.go:5-10 */
+    double light[3];      /* PhongShader.LightDirection (used as given) */
+    double camera[3];     /* PhongShader.CameraPosition */
+    double object[4];     /* ObjectColor; all zero == Discard => use vertex colour (shader.go:78) */
+    double ambient[4];
+    double diffuse[4];
+    double specular[4];
+    double specular_power;
+    double color[4];      /* SolidColorShader.Color */
+    const fgl_tex *texture; /* NULL == nil */
+} fgl_shader;
+
+/* Host-side mesh description.  Attribute arrays are float64,
+ * [nprims][verts_per_prim][k] with k = 3 (position, normal, texture) or 4
+ * (color) -- i.e. the fields of the reference's Vertex (vertex.go:3-12)
+ * gathered per attribute.  NULL means all-zero.  position is required when the
+ * matching count is non-zero. */
+typedef struct {
+    uint64_t ntriangles;
+    const double *position, *normal, *texture, *color;     /* [T][3][k] */
+    uint64_t nlines;
+    const double *lposition, *lnormal, *ltexture, *lcolor; /* [L][2][k] */
+} fgl_mesh_desc;
+
+/* context.go:28-31 */
+typedef struct { uint64_t total_pixels, updated_pixels; } fgl_raster_info;
+
+/* Device-side statistics of the most recent draw call on the context. */
+typedef struct {
+    uint64_t prims_in;       /* primitives submitted                       */
+    uint64_t records;        /* raster triangles after clip/cull/expansion */
+    uint64_t pairs;          /* (tile, triangle) pairs binned              */
+    uint64_t clip_triangles; /* triangles produced by the clipper          */
+    uint32_t tiles_x, tiles_y, tile_w, tile_h;
+    uint32_t kernel_launches; /* kernels launched by that draw             */
+    uint32_t retries;         /* work-buffer regrows (sync draws only)     */
+} fgl_draw_stats;
+
+int fgl_abi_version(void);
+/* Thread-local message of the last failing call (ctx may be NULL). */
+const char *fgl_last_error(const fgl_ctx *ctx);
+int fgl_device_count(void);
+
+/* NewContext, context.go:60-81: colour buffer zeroed (transparent), depth
+ * buffer cleared to math.MaxFloat64. */
+int fgl_context_create(int width, int height, int device, fgl_ctx **out);
+int fgl_context_destroy(fgl_ctx *ctx);
+int fgl_context_size(const fgl_ctx *ctx, int *width, int *height);
+
+/* ClearColorBufferWith, context.go:119-131 (rgba = Color.NRGBA(), color.go:56). */
+int fgl_clear_color(fgl_ctx *ctx, const uint8_t rgba[4]);
+/* ClearDepthBufferWith, context.go:137-141. */
+int fgl_clear_depth(fgl_ctx *ctx, double value);
+
+/* Upload a mesh once; draws reference it by handle (the reference walks
+ * []*Triangle on every DrawTriangles call, context.go:413-433). */
+int fgl_mesh_create(fgl_ctx *ctx, const fgl_mesh_desc *desc, fgl_mesh **out);
+int fgl_mesh_destroy(fgl_mesh *mesh);
+int fgl_mesh_counts(const fgl_mesh *mesh, uint64_t *ntriangles, uint64_t *nlines);
+/* Mesh.Transform, mesh.go:167-175 (+ triangle.go:66-73, line.go:23-28): positions
+ * by MulPosition, normals by MulDirection (normalised), on the device. */
+int fgl_mesh_transform(fgl_ctx *ctx, fgl_mesh *mesh, const double matrix[16]);
+/* Read the device copy back (same layout as fgl_mesh_desc; any pointer may be NULL). */
+int fgl_mesh_read(fgl_ctx *ctx, const fgl_mesh *mesh, double *position, double *normal,
+                  double *lposition, double *lnormal);
+
+/* NewImageTexture, texture.go:27-30.  rgba8: h rows of w RGBA8 texels. */
+int fgl_texture_create(fgl_ctx *ctx, const uint8_t *rgba8, int width, int height, int format, fgl_tex **out);
+int fgl_texture_destroy(fgl_tex *tex);
+
+/* DrawTriangles, context.go:413-433, over triangles [first, first+count) of
+ * the mesh, in triangle-index order.  Blocks until the
+ * RasterizeInfo is known (the reference returns it by value). */
+int fgl_draw_triangles(fgl_ctx *ctx, const fgl_state *state, const fgl_shader *shader,
+                       const fgl_mesh *mesh, uint64_t first, uint64_t count, fgl_raster_info *info);
+/* DrawLines, context.go:391-411. */
+int fgl_draw_lines(fgl_ctx *ctx, const fgl_state *state, const fgl_shader *shader,
+                   const fgl_mesh *mesh, uint64_t first, uint64_t count, fgl_raster_info *info);
+/* Same draws, enqueued without waiting; the RasterizeInfo of all draws since
+ * the last fgl_sync is accumulated and returned by fgl_sync. */
+int fgl_draw_triangles_async(fgl_ctx *ctx, const fgl_state *state, const fgl_shader *shader,
+                             const fgl_mesh *mesh, uint64_t first, uint64_t count);
+int fgl_draw_lines_async(fgl_ctx *ctx, const fgl_state *state, const fgl_shader *shader,
+                         const fgl_mesh *mesh, uint64_t first, uint64_t count);
+/* Wait for everything enqueued on the context; info (may be NULL) receives the
+ * sum over the async draws since the previous fgl_sync. */
+int fgl_sync(fgl_ctx *ctx, fgl_raster_info *info);
+int fgl_get_draw_stats(const fgl_ctx *ctx, fgl_draw_stats *out);
+
+/* Image(), context.go:83-85: ColorBuffer.Pix (NRGBA8, non-premultiplied). */
+int fgl_read_color(fgl_ctx *ctx, uint8_t *dst, size_t stride_bytes);
+/* DepthBuffer, context.go:44. */
+int fgl_read_depth(fgl_ctx *ctx, double *dst);
+/* The reference exposes both buffers as writable fields; these upload them. */
+int fgl_write_color(fgl_ctx *ctx, const uint8_t *src, size_t stride_bytes);
+int fgl_write_depth(fgl_ctx *ctx, const double *src);
+
+/* SSAA resolve: resize.Resize(w/factor, h/factor, Image(), resize.Bilinear) as
+ * called by every example (examples/teapot.go:60, dragon.go:82, ...).  dst
+ * receives (h/factor) rows of (w/factor) RGBA8 (premultiplied, as
+ * *image.RGBA).  fgl_resolve_device leaves the result on the device only. */
+int fgl_resolve(fgl_ctx *ctx, int factor, uint8_t *dst_rgba8);
+int fgl_resolve_device(fgl_ctx *ctx, int factor);
+int fgl_read_resolved(fgl_ctx *ctx, uint8_t *dst_rgba8);
+
+/* Sort-last multi-GPU composite (not in the reference).
+ * fgl_composite_pack writes one uint64 key per pixel,
+ * (depth32 << 32 | R<<24 | G<<16 | B<<8 | A) with depth32 a monotone map of the
+ * float64 depth, into device memory `keys_dev` (width*height uint64).  The
+ * caller min-reduces the key buffers across ranks (NCCL ncclMin on
+ * ncclUint64 / torch.distributed) and hands the result to
+ * fgl_composite_unpack, which rewrites this context's colour buffer (and, as
+ * float32-quantised values, its depth buffer).  fgl_composite_min merges a
+ * second key buffer on the same device (used by the single-GPU test of the
+ * composite and by the peer-memory path). */
+int fgl_composite_pack(fgl_ctx *ctx, void *keys_dev);
+int fgl_composite_unpack(fgl_ctx *ctx, const void *keys_dev);
+int fgl_composite_min(fgl_ctx *ctx, void *keys_dev_inout, const void *keys_dev_other, uint64_t count);
+
+/* Interop for the host harness (timing with CUDA events on the launching
+ * stream; zero-copy views of the buffers). */
+void *fgl_stream(const fgl_ctx *ctx);            /* cudaStream_t */
+void *fgl_color_device_ptr(const fgl_ctx *ctx);  /* width*height*4 bytes */
+void *fgl_depth_device_ptr(const fgl_ctx *ctx);  /* width*height doubles */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAUXGL_B200_H */

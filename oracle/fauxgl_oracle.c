@@ -792,5 +792,6 @@ uint64_t oracle_pack_key(double depth, const uint8_t rgba[4]) {
     else if (depth == 1) d32 = 0xFFFFFFFEu;
     else d32 = (uint32_t)(depth * 4294967295.0);
     uint32_t c = ((uint32_t)rgba[0] << 24) | ((uint32_t)rgba[1] << 16) | ((uint32_t)rgba[2] << 8) | rgba[3];
-    return ((uint64_t)d32 << 32) | c;
+    /* biased by 2^63 so that a signed 64-bit min (ncclInt64) orders by depth, then colour */
+    return (((uint64_t)d32 << 32) | c) ^ 0x8000000000000000ull;
 }

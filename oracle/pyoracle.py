@@ -163,11 +163,15 @@ class OracleContext:
         del keep
         return (info.total_pixels, info.updated_pixels)
 
-    def DrawTriangles(self, mesh):
-        return self._draw(lib().oracle_draw_triangles, mesh.triangle_vertices())
+    def DrawTriangles(self, mesh, first=0, count=None):
+        v = mesh.triangle_vertices()
+        count = len(v) - first if count is None else count
+        return self._draw(lib().oracle_draw_triangles, v[first:first + count])
 
-    def DrawLines(self, mesh):
-        return self._draw(lib().oracle_draw_lines, mesh.line_vertices())
+    def DrawLines(self, mesh, first=0, count=None):
+        v = mesh.line_vertices()
+        count = len(v) - first if count is None else count
+        return self._draw(lib().oracle_draw_lines, v[first:first + count])
 
     def DrawMesh(self, mesh):
         a = self.DrawTriangles(mesh)
