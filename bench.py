@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of fogleman/fauxgl's DrawMesh path
+(README.md:36: 871 306-triangle Phong render at 1920x1080; and 16x SSAA) on
+N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+A "step" is one frame: ClearDepthBuffer + ClearColorBufferWith + DrawMesh of the
+synthetic 871 306-triangle mesh (SURVEY.md 8d "M871k"; the dragon itself is not
+in the reference repository).  `value` is device-timed with the mesh resident in
+HBM; `e2e` goes through the public Context API with host (pinned) mesh arrays
+uploaded and the image read back inside the timed region.  With N > 1 every
+rank renders its own frames of the batch (frame sharding, no collective: weak
+scaling); the sort-last composite is timed separately in `sort_last`.
+
+--impl reference times the reference's own CPU algorithm (goroutine striding +
+256 mutexes restated with pthreads, oracle/fauxgl_oracle.c -- the Go toolchain is
+absent) on the host cores, same scene, same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+T_TRIANGLES = 871306
+W1, H1 = 1920, 1080
+SSAA = 4
+ALGO_BYTES_C1 = T_TRIANGLES * 144 + W1 * H1 * 12                     # 150 351 264
+ALGO_BYTES_C2 = (T_TRIANGLES * 144 + (W1 * SSAA) * (H1 * SSAA) * 12
+                 + (W1 * SSAA) * (H1 * SSAA) * 4 + W1 * H1 * 4)      # 664 604 064
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def scene_setup():
+    """README.md:53-114 'Complete Example'."""
+    from fauxgl_b200 import HexColor, LookAt, NewPhongShader, V
+    eye, center, up = V(-3, 1, -0.75), V(0, -0.07, 0), V(0, 1, 0)
+    matrix = LookAt(eye, center, up).Perspective(30, 1920 / 1080, 1, 10)
+    shader = NewPhongShader(matrix, V(-0.75, 1, 0.25).Normalize(), eye)
+    shader.ObjectColor = HexColor("#468966")
+    return shader, HexColor("#FFF8E3")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_frames(mesh, frames: int, warmup: int, threads: int):
+    """The reference's CPU schedule (context.go:413-433: worker wi takes i%wn==wi, 256
+    mutexes, unlocked early-Z) restated in oracle/fauxgl_oracle.c, timed per frame."""
+    from oracle import pyoracle
+    shader, bg = scene_setup()
+    octx = pyoracle.OracleContext(W1, H1, x_guard=True, threads=threads)
+    octx.Shader = shader
+    verts = np.ascontiguousarray(mesh.triangle_vertices())  # flattening is mesh prep, not DrawMesh
+    times = []
+    for i in range(warmup + frames):
+        t0 = time.perf_counter()
+        octx.ClearDepthBuffer()
+        octx.ClearColorBufferWith(bg)
+        octx._draw(pyoracle.lib().oracle_draw_triangles, verts)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from fauxgl_b200 import synth
+    mesh = synth.bumpy_surface()
+    cores = os.cpu_count() or 1
+    times = cpu_reference_frames(mesh, args.steps, min(args.warmup, 1), cores)
+    ms = 1e3 * sum(times) / len(times)
+    value = T_TRIANGLES / (ms / 1e3) / 1e6
+    line = {
+        "impl": "reference", "metric": "Mtri/s, 871k-tri Phong 1080p DrawMesh", "value": value, "unit": "Mtri/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": value / (T_TRIANGLES / 0.150 / 1e6), "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "M871k: synthetic 871306-triangle bumpy closed surface, smoothed normals, Phong, 1920x1080, README camera",
+                   "frames_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": "Mtri/s", "cores": cores, "kind": "port",
+                         "sample": "%d full frames (clear + DrawMesh) of the same scene, pthread restatement of the reference's "
+                                   "goroutine schedule (no Go toolchain)" % len(times)},
+        "e2e": {"value": value, "unit": "Mtri/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-ssaa", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from fauxgl_b200 import synth
+    from fauxgl_b200.context import Context, DeviceMesh
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    use_dist = world > 1
+    if use_dist:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if not use_dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    mesh = synth.bumpy_surface()
+    shader, bg = scene_setup()
+    hbm_peak, peak_src = load_peaks()
+
+    # ---------------- device-resident throughput (value) ----------------
+    def timed_frames(width, height, resolve, steps, warmup, profile):
+        ctx = Context(width, height, local_rank)
+        ctx.Shader = shader
+        dm = DeviceMesh(ctx, mesh, ("position", "normal"))
+        ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+        def frame():
+            ctx.ClearDepthBuffer()
+            ctx.ClearColorBufferWith(bg)
+            ctx.DrawMeshAsync(dm)
+            if resolve:
+                ctx.ResolveDevice(resolve)
+        ctx.DrawMesh(dm)          # one synchronous draw sizes the work buffers (async draws cannot regrow)
+        for _ in range(warmup):
+            frame()
+        info = ctx.Sync()
+        stats = ctx.DrawStats()
+        launches_per_frame = 2 + stats.kernel_launches + 1 + (1 if resolve else 0)
+        if profile:
+            ctx.SetProfiling(True)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        with torch.cuda.stream(ext):
+            for i in range(steps):
+                flush.zero_()                       # L2 flush between timed frames (256 MiB > 126 MB L2)
+                starts[i].record(ext)
+                frame()
+                ends[i].record(ext)
+        info = ctx.Sync()
+        barrier()
+        clocks = sampler.stop()
+        ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+        st = ctx.StageTimes() if profile else None
+        if profile:
+            ctx.SetProfiling(False)
+        out = {"ms": ms, "info": info, "records": int(stats.records), "pairs": int(stats.pairs),
+               "launches_per_frame": int(launches_per_frame), "clocks": clocks, "stage": st}
+        del dm
+        ctx.Close()
+        return out
+
+    r1 = timed_frames(W1, H1, 0, K, Wm, True)
+    ms1 = max_over_ranks(sum(r1["ms"]) / K)
+    value = world * T_TRIANGLES / (ms1 / 1e3) / 1e6
+
+    st = r1["stage"]
+    stages = {"geometry_ms": st.geometry_ms / st.draws, "binning_ms": st.binning_ms / st.draws,
+              "raster_ms": st.raster_ms / st.draws}
+    dom = max(stages, key=stages.get)
+    # algorithmic bytes per launch of each stage (DESIGN.md "Roofline"): geometry reads the position
+    # planes twice (count + emit pass) = T*72*2; raster consumes the normal planes of the surviving
+    # triangles' vertices and owns the framebuffer traffic (12 B/px, load + store of touched tiles is
+    # implementation, not algorithm): T*72 + W*H*12; binning moves no algorithmic bytes at all.
+    algo = {"geometry_ms": T_TRIANGLES * 72, "raster_ms": T_TRIANGLES * 72 + W1 * H1 * 12, "binning_ms": 0}
+    dom_bytes = algo[dom] if algo[dom] else ALGO_BYTES_C1
+    roofline = {
+        "bound": "hbm", "kernel": {"geometry_ms": "k_geom_count+k_geom_emit", "binning_ms": "pair sort",
+                                   "raster_ms": "k_raster"}[dom],
+        "achieved": dom_bytes / (stages[dom] / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": dom_bytes / (stages[dom] / 1e3) / 1e9 / hbm_peak, "traffic": None,
+        "peak_source": peak_src, "algorithmic_bytes": dom_bytes,
+        "frame": {"algorithmic_bytes": ALGO_BYTES_C1, "achieved": ALGO_BYTES_C1 / (ms1 / 1e3) / 1e9,
+                  "frac": ALGO_BYTES_C1 / (ms1 / 1e3) / 1e9 / hbm_peak},
+        "stages_ms": stages,
+    }
+
+    # ---------------- 16x SSAA (7680x4320 + resolve) ----------------
+    ssaa = None
+    if not args.no_ssaa:
+        K2 = max(3, min(K, 10))
+        r2 = timed_frames(W1 * SSAA, H1 * SSAA, SSAA, K2, 3, True)
+        ms2 = max_over_ranks(sum(r2["ms"]) / K2)
+        s2 = r2["stage"]
+        ssaa = {"ms_per_frame": ms2, "mtri_s": world * T_TRIANGLES / (ms2 / 1e3) / 1e6, "steps": K2,
+                "total_pixels": int(r2["info"].TotalPixels / (3 + K2)),
+                "roofline_frac_frame": ALGO_BYTES_C2 / (ms2 / 1e3) / 1e9 / hbm_peak,
+                "stages_ms": {"geometry_ms": s2.geometry_ms / s2.draws, "binning_ms": s2.binning_ms / s2.draws,
+                              "raster_ms": s2.raster_ms / s2.draws},
+                "workload": "same mesh at 7680x4320 + 4x4 nfnt-bilinear resolve to 1920x1080"}
+
+    # ---------------- end to end through the public API with host buffers ----------------
+    Ke = max(3, min(K, 10))
+    ctx = Context(W1, H1, local_rank)
+    ctx.Shader = shader
+    ctx.upload_attributes = ("position", "normal")
+    pin_pos = torch.empty(mesh.position.shape, dtype=torch.float64, pin_memory=True)
+    pin_nrm = torch.empty(mesh.normal.shape, dtype=torch.float64, pin_memory=True)
+    pin_img = torch.empty((H1, W1, 4), dtype=torch.uint8, pin_memory=True)
+    pin_pos.numpy()[...] = mesh.position
+    pin_nrm.numpy()[...] = mesh.normal
+    hmesh = type(mesh)(pin_pos.numpy(), pin_nrm.numpy())
+    img = pin_img.numpy()
+
+    def e2e_frame():
+        hmesh.Invalidate()                 # host mesh changed (animate.go:66): positions+normals are re-uploaded
+        ctx.ClearDepthBuffer()
+        ctx.ClearColorBufferWith(bg)
+        info = ctx.DrawMesh(hmesh)         # synchronous, returns RasterizeInfo like the reference
+        ctx.Image(out=img)                 # read the frame back
+        return info
+    for _ in range(3):
+        e2e_frame()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        einfo = e2e_frame()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / Ke)
+    barrier()
+    e2e = {"value": world * T_TRIANGLES / (e2e_ms / 1e3) / 1e6, "unit": "Mtri/s", "ms_per_step": e2e_ms, "steps": Ke,
+           "h2d_bytes_per_step": int(pin_pos.numel() * 8 + pin_nrm.numel() * 8),
+           "d2h_bytes_per_step": int(W1 * H1 * 4 + 16),
+           "what": "mesh (position+normal, pinned host) upload + clears + DrawMesh (sync) + Image() read-back"}
+    checksum = int(img.astype(np.uint64).sum())
+    ctx.Close()
+
+    # ---------------- CPU baseline beside it (rank 0, N == 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        times = cpu_reference_frames(mesh, 5, 1, cores)
+        cms = 1e3 * float(np.median(times))
+        cpu = {"value": T_TRIANGLES / (cms / 1e3) / 1e6, "unit": "Mtri/s", "cores": cores, "kind": "port",
+               "ms_per_frame_median": cms, "ms_per_frame_best": 1e3 * min(times),
+               "sample": "5 full frames (clear + DrawMesh) of the same 871306-triangle scene; pthread restatement of "
+                         "the reference's goroutine schedule (context.go:413-433), the Go toolchain being absent"}
+
+    if rank == 0:
+        line = {
+            "metric": "Mtri/s, 871k-tri Phong 1080p DrawMesh", "value": value, "unit": "Mtri/s", "n_gpus": world,
+            "steps": K, "warmup": Wm, "ms_per_step": ms1, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": value / (T_TRIANGLES / 0.150 / 1e6),   # README.md:36: ~150 ms/frame on the author's (unspecified) CPU
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "M871k: synthetic 871306-triangle bumpy closed surface, smoothed normals, Phong, "
+                                   "1920x1080, README camera; one frame = ClearDepth + ClearColor + DrawMesh",
+                       "frames_per_step": 1, "sharding": "frames per GPU, no collective" if world > 1 else "single GPU",
+                       "l2": "flushed between timed frames (256 MiB memset outside the event pair)",
+                       "timing": "CUDA events on the library's stream, per frame, summed; max over ranks"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(r1["launches_per_frame"] * K),
+            "clocks": r1["clocks"], "ssaa16": ssaa,
+            "raster_info": {"total_pixels": int(einfo.TotalPixels), "updated_pixels": int(einfo.UpdatedPixels),
+                            "records": r1["records"], "pairs": r1["pairs"], "image_checksum": checksum},
+        }
+        print(json.dumps(line))
+    if use_dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

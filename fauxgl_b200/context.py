@@ -76,6 +76,11 @@ class DrawStats(C.Structure):
                 ("retries", C.c_uint32)]
 
 
+class StageTimes(C.Structure):
+    _fields_ = [("geometry_ms", C.c_float), ("binning_ms", C.c_float), ("raster_ms", C.c_float),
+                ("draws", C.c_uint32)]
+
+
 # every symbol include/fauxgl_b200.h declares: (name, restype, argtypes)
 _P = C.c_void_p
 ABI = [
@@ -88,6 +93,7 @@ ABI = [
     ("fgl_clear_color", C.c_int, [_P, C.POINTER(C.c_uint8)]),
     ("fgl_clear_depth", C.c_int, [_P, C.c_double]),
     ("fgl_mesh_create", C.c_int, [_P, C.POINTER(_MeshDesc), C.POINTER(_P)]),
+    ("fgl_mesh_update", C.c_int, [_P, _P, C.POINTER(_MeshDesc)]),
     ("fgl_mesh_destroy", C.c_int, [_P]),
     ("fgl_mesh_counts", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("fgl_mesh_transform", C.c_int, [_P, _P, C.POINTER(C.c_double)]),
@@ -100,6 +106,8 @@ ABI = [
     ("fgl_draw_lines_async", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64]),
     ("fgl_sync", C.c_int, [_P, C.POINTER(_Info)]),
     ("fgl_get_draw_stats", C.c_int, [_P, C.POINTER(DrawStats)]),
+    ("fgl_set_profiling", C.c_int, [_P, C.c_int]),
+    ("fgl_get_stage_times", C.c_int, [_P, C.POINTER(StageTimes)]),
     ("fgl_read_color", C.c_int, [_P, _P, C.c_size_t]),
     ("fgl_read_depth", C.c_int, [_P, _P]),
     ("fgl_write_color", C.c_int, [_P, _P, C.c_size_t]),
@@ -159,7 +167,23 @@ class DeviceMesh:
     def __init__(self, ctx: "Context", mesh: Mesh, attributes=("position", "normal", "texture", "color")):
         self.ctx = ctx
         self.generation = mesh.generation
+        self.attributes = tuple(attributes)
         self.num_triangles, self.num_lines = mesh.num_triangles, mesh.num_lines
+        d, keep = self._desc(mesh, self.attributes)
+        self.handle = _P()
+        _check(capi().fgl_mesh_create(ctx._h, C.byref(d), C.byref(self.handle)), ctx._h)
+        self._fin = weakref.finalize(self, capi().fgl_mesh_destroy, self.handle)
+
+    def update(self, mesh: Mesh, attributes=None):
+        """fgl_mesh_update: re-upload (a subset of) the attributes into the same device buffers."""
+        assert (mesh.num_triangles, mesh.num_lines) == (self.num_triangles, self.num_lines)
+        attributes = self.attributes if attributes is None else tuple(attributes)
+        d, keep = self._desc(mesh, attributes, position="position" in attributes)
+        _check(capi().fgl_mesh_update(self.ctx._h, self.handle, C.byref(d)), self.ctx._h)
+        self.generation = mesh.generation
+
+    @staticmethod
+    def _desc(mesh: Mesh, attributes, position=True):
         d = _MeshDesc()
         keep = []
 
@@ -170,18 +194,16 @@ class DeviceMesh:
             keep.append(a)
             return a.ctypes.data
         d.ntriangles = mesh.num_triangles
-        d.position = arr(mesh.position, True)
+        d.position = arr(mesh.position, position)
         d.normal = arr(mesh.normal, "normal" in attributes)
         d.texture = arr(mesh.texture, "texture" in attributes)
         d.color = arr(mesh.color, "color" in attributes)
         d.nlines = mesh.num_lines
-        d.lposition = arr(mesh.lposition, True)
+        d.lposition = arr(mesh.lposition, position)
         d.lnormal = arr(mesh.lnormal, "normal" in attributes)
         d.ltexture = arr(mesh.ltexture, "texture" in attributes)
         d.lcolor = arr(mesh.lcolor, "color" in attributes)
-        self.handle = _P()
-        _check(capi().fgl_mesh_create(ctx._h, C.byref(d), C.byref(self.handle)), ctx._h)
-        self._fin = weakref.finalize(self, capi().fgl_mesh_destroy, self.handle)
+        return d, keep
 
     def Transform(self, matrix: Matrix):
         """Mesh.Transform on the device (mesh.go:167-175)."""
@@ -222,6 +244,9 @@ class Context:
         self._meshes = weakref.WeakKeyDictionary()   # Mesh -> DeviceMesh
         self._textures = weakref.WeakKeyDictionary()  # ImageTexture -> DeviceTexture
         self._keep = None
+        # which vertex attributes DrawMesh(host_mesh) uploads; a Phong+ObjectColor scene needs
+        # only position+normal (the reference copies all 17 doubles per vertex regardless)
+        self.upload_attributes = ("position", "normal", "texture", "color")
 
     # -- lifetime ------------------------------------------------------------------
     def Close(self):
@@ -230,9 +255,12 @@ class Context:
         self._fin()
 
     # -- buffers -------------------------------------------------------------------
-    def Image(self) -> np.ndarray:
-        """context.go:83: ColorBuffer as (H,W,4) uint8, NRGBA."""
-        out = np.empty((self.Height, self.Width, 4), dtype=np.uint8)
+    def Image(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """context.go:83: ColorBuffer as (H,W,4) uint8, NRGBA.  ``out`` may be a
+        caller-owned (e.g. pinned) buffer to read into."""
+        if out is None:
+            out = np.empty((self.Height, self.Width, 4), dtype=np.uint8)
+        assert out.shape == (self.Height, self.Width, 4) and out.dtype == np.uint8 and out.flags.c_contiguous
         _check(capi().fgl_read_color(self._h, out.ctypes.data, 0), self._h)
         return out
 
@@ -309,9 +337,11 @@ class Context:
         if isinstance(mesh, DeviceMesh):
             return mesh
         dm = self._meshes.get(mesh)
-        if dm is None or dm.generation != mesh.generation:
-            dm = DeviceMesh(self, mesh)
+        if dm is None or (dm.num_triangles, dm.num_lines) != (mesh.num_triangles, mesh.num_lines):
+            dm = DeviceMesh(self, mesh, self.upload_attributes)
             self._meshes[mesh] = dm
+        elif dm.generation != mesh.generation:
+            dm.update(mesh)   # mutated on the host since the last draw: re-upload in place
         return dm
 
     def DrawTriangles(self, mesh, first: int = 0, count: Optional[int] = None) -> RasterizeInfo:  # context.go:413
@@ -348,6 +378,14 @@ class Context:
         info = _Info()
         _check(capi().fgl_sync(self._h, C.byref(info)), self._h)
         return RasterizeInfo(info.total_pixels, info.updated_pixels)
+
+    def SetProfiling(self, enabled: bool):
+        _check(capi().fgl_set_profiling(self._h, int(enabled)), self._h)
+
+    def StageTimes(self) -> StageTimes:
+        s = StageTimes()
+        _check(capi().fgl_get_stage_times(self._h, C.byref(s)), self._h)
+        return s
 
     def DrawStats(self) -> DrawStats:
         s = DrawStats()

@@ -43,7 +43,12 @@ struct fgl_mesh {
     uint64_t nt, nl;
     double *tpos, *tnrm, *ttex, *tcol;  // planar, triangles
     double *lpos, *lnrm, *ltex, *lcol;  // planar, lines
+    double *staging;                    // AoS landing buffer for H2D copies (kept for fgl_mesh_update)
+    size_t staging_elems;
 };
+
+constexpr int PROF_RING = 32;
+struct ProfSlot { cudaEvent_t e[4]; };
 
 struct fgl_ctx {
     int device;
@@ -60,6 +65,12 @@ struct fgl_ctx {
     DrawCounters *acc_dev;             // async accumulation (total/updated/overflow)
     bool async_pending;
     fgl_draw_stats stats;
+    // per-stage profiling (fgl_set_profiling)
+    bool profiling;
+    ProfSlot prof[PROF_RING];
+    int prof_used;          // slots recorded since the last drain
+    bool prof_created;
+    fgl_stage_times prof_acc;
 };
 
 namespace {
@@ -88,58 +99,71 @@ void dev_free(T *&p) {
 }
 
 void free_work(WorkBuffers &wb) {
-    dev_free(wb.prim_nrec); dev_free(wb.prim_rec_off); dev_free(wb.recs); dev_free(wb.rec_tiles);
-    dev_free(wb.rec_npairs); dev_free(wb.rec_pair_off); dev_free(wb.clip_pool);
-    dev_free(wb.pair_key[0]); dev_free(wb.pair_key[1]); dev_free(wb.pair_val[0]); dev_free(wb.pair_val[1]);
+    dev_free(wb.prim_nrec); dev_free(wb.prim_rec_off); dev_free(wb.recs); dev_free(wb.rec_rows);
+    dev_free(wb.rec_row_off); dev_free(wb.clip_pool); dev_free(wb.row_nseg); dev_free(wb.row_seg_off);
+    dev_free(wb.segs);
+    dev_free(wb.seg_key[0]); dev_free(wb.seg_key[1]); dev_free(wb.seg_val[0]); dev_free(wb.seg_val[1]);
     dev_free(wb.scan_tmp);
-    wb.cap_prims = wb.cap_records = wb.cap_pairs = wb.cap_clip = 0;
+    wb.cap_prims = wb.cap_records = wb.cap_rows = wb.cap_segs = wb.cap_clip = 0;
+    wb.scan_tmp_words = 0;
 }
 
+struct Caps { uint64_t prims, records, rows, segs, clip; };
+
 // (Re)allocate work buffers so that they hold at least the given capacities.
-int ensure_work(fgl_ctx *c, uint64_t prims, uint64_t records, uint64_t pairs, uint64_t clip) {
+int ensure_work(fgl_ctx *c, const Caps &want) {
     WorkBuffers &wb = c->wb;
     const uint64_t LIM = 0xfffffff0ull;
-    if (prims > LIM || records > LIM || pairs > LIM || clip > LIM)
+    if (want.prims > LIM || want.records > LIM || want.rows > LIM || want.segs > LIM || want.clip > LIM)
         return fail(c, FGL_E_INVALID, "draw too large for 32-bit work indices");
-    bool scan_dirty = false;
-    if (prims > wb.cap_prims) {
+    if (want.prims > wb.cap_prims) {
         dev_free(wb.prim_nrec); dev_free(wb.prim_rec_off);
-        CK(c, dev_alloc(&wb.prim_nrec, prims));
-        CK(c, dev_alloc(&wb.prim_rec_off, prims + 1));
-        wb.cap_prims = (uint32_t)prims;
-        scan_dirty = true;
+        CK(c, dev_alloc(&wb.prim_nrec, want.prims));
+        CK(c, dev_alloc(&wb.prim_rec_off, want.prims + 1));
+        wb.cap_prims = (uint32_t)want.prims;
     }
-    if (records > wb.cap_records) {
-        dev_free(wb.recs); dev_free(wb.rec_tiles); dev_free(wb.rec_npairs); dev_free(wb.rec_pair_off);
-        CK(c, dev_alloc(&wb.recs, records));
-        CK(c, dev_alloc(&wb.rec_tiles, records));
-        CK(c, dev_alloc(&wb.rec_npairs, records));
-        CK(c, dev_alloc(&wb.rec_pair_off, records + 1));
-        wb.cap_records = (uint32_t)records;
-        scan_dirty = true;
+    if (want.records > wb.cap_records) {
+        dev_free(wb.recs); dev_free(wb.rec_rows); dev_free(wb.rec_row_off);
+        CK(c, dev_alloc(&wb.recs, want.records));
+        CK(c, dev_alloc(&wb.rec_rows, want.records));
+        CK(c, dev_alloc(&wb.rec_row_off, want.records + 1));
+        wb.cap_records = (uint32_t)want.records;
     }
-    if (pairs > wb.cap_pairs) {
+    if (want.rows > wb.cap_rows) {
+        dev_free(wb.row_nseg); dev_free(wb.row_seg_off);
+        CK(c, dev_alloc(&wb.row_nseg, want.rows));
+        CK(c, dev_alloc(&wb.row_seg_off, want.rows + 1));
+        wb.cap_rows = (uint32_t)want.rows;
+    }
+    if (want.segs > wb.cap_segs) {
+        dev_free(wb.segs);
+        CK(c, dev_alloc(&wb.segs, want.segs));
         for (int k = 0; k < 2; k++) {
-            dev_free(wb.pair_key[k]); dev_free(wb.pair_val[k]);
-            CK(c, dev_alloc(&wb.pair_key[k], pairs));
-            CK(c, dev_alloc(&wb.pair_val[k], pairs));
+            dev_free(wb.seg_key[k]); dev_free(wb.seg_val[k]);
+            CK(c, dev_alloc(&wb.seg_key[k], want.segs));
+            CK(c, dev_alloc(&wb.seg_val[k], want.segs));
         }
-        wb.cap_pairs = (uint32_t)pairs;
+        wb.cap_segs = (uint32_t)want.segs;
     }
-    if (clip > wb.cap_clip) {
+    if (want.clip > wb.cap_clip) {
         dev_free(wb.clip_pool);
-        CK(c, dev_alloc(&wb.clip_pool, clip));
-        wb.cap_clip = (uint32_t)clip;
+        CK(c, dev_alloc(&wb.clip_pool, want.clip));
+        wb.cap_clip = (uint32_t)want.clip;
     }
-    if (scan_dirty || !wb.scan_tmp) {
-        const size_t words = std::max(scan_tmp_words(wb.cap_prims), scan_tmp_words(wb.cap_records));
-        if (words > wb.scan_tmp_words) {
-            dev_free(wb.scan_tmp);
-            CK(c, dev_alloc(&wb.scan_tmp, words));
-            wb.scan_tmp_words = (uint32_t)words;
-        }
+    const size_t words = std::max(std::max(scan_tmp_words(wb.cap_prims), scan_tmp_words(wb.cap_records)),
+                                  scan_tmp_words(wb.cap_rows));
+    if (words > wb.scan_tmp_words) {
+        dev_free(wb.scan_tmp);
+        CK(c, dev_alloc(&wb.scan_tmp, words));
+        wb.scan_tmp_words = (uint32_t)words;
     }
     return FGL_OK;
+}
+
+Caps grown(const fgl_ctx *c, const DrawCounters &hc) {
+    auto g = [](uint32_t cap, uint32_t need) { return std::max<uint64_t>(cap, (uint64_t)need + need / 4 + 1024); };
+    return Caps{c->wb.cap_prims, g(c->wb.cap_records, hc.need_records), g(c->wb.cap_rows, hc.need_rows),
+                g(c->wb.cap_segs, hc.need_segs), g(c->wb.cap_clip, hc.need_clip)};
 }
 
 int check_ctx(fgl_ctx *c) {
@@ -154,7 +178,8 @@ __global__ void k_accumulate(const DrawCounters *cur, DrawCounters *acc) {
     acc->updated_pixels += cur->updated_pixels;
     acc->overflow |= cur->overflow;
     acc->need_records = max(acc->need_records, cur->need_records);
-    acc->need_pairs = max(acc->need_pairs, cur->need_pairs);
+    acc->need_rows = max(acc->need_rows, cur->need_rows);
+    acc->need_segs = max(acc->need_segs, cur->need_segs);
     acc->need_clip = max(acc->need_clip, cur->need_clip);
 }
 
@@ -208,15 +233,48 @@ int build_params(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const
     }
     p->first = (uint32_t)first; p->count = (uint32_t)count;
     p->is_lines = lines ? 1 : 0;
+    // Deferred shading is legal when the fragment colour can neither be Discard (context.go:241)
+    // nor take the blend path (context.go:256): the alpha is a per-draw constant then.
+    {
+        bool known = false;
+        double alpha = 0;
+        if (sh->kind == FGL_SHADER_SOLID) { known = true; alpha = sh->color[3]; }
+        else if (sh->kind == FGL_SHADER_PHONG && !uses_tex && !p->object_is_discard) { known = true; alpha = sh->object[3]; }
+        const bool blends = state->alpha_blend && alpha < 1;
+        p->deferred = (known && alpha != 0 && !blends) ? 1 : 0;
+    }
     return FGL_OK;
+}
+
+void prof_drain(fgl_ctx *c) {
+    if (!c->prof_used) return;
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < c->prof_used; i++) {
+        float g = 0, b = 0, r = 0;
+        cudaEventElapsedTime(&g, c->prof[i].e[0], c->prof[i].e[1]);
+        cudaEventElapsedTime(&b, c->prof[i].e[1], c->prof[i].e[2]);
+        cudaEventElapsedTime(&r, c->prof[i].e[2], c->prof[i].e[3]);
+        c->prof_acc.geometry_ms += g; c->prof_acc.binning_ms += b; c->prof_acc.raster_ms += r;
+    }
+    c->prof_acc.draws += (uint32_t)c->prof_used;
+    c->prof_used = 0;
 }
 
 int enqueue_draw(fgl_ctx *c, const DrawParams &p) {
     int launches = 0;
+    ProfSlot *ps = nullptr;
+    if (c->profiling) {
+        if (c->prof_used == PROF_RING) prof_drain(c);
+        ps = &c->prof[c->prof_used++];
+        cudaEventRecord(ps->e[0], c->stream);
+    }
     launches += launch_geometry(p, c->wb, c->stream);
+    if (ps) cudaEventRecord(ps->e[1], c->stream);
     int sorted = 0;
-    launches += launch_binning(p, c->wb, &sorted, c->stream);
+    launches += launch_spans(p, c->wb, &sorted, c->stream);
+    if (ps) cudaEventRecord(ps->e[2], c->stream);
     launches += launch_raster(p, c->wb, sorted, c->color, c->depth, c->stream);
+    if (ps) cudaEventRecord(ps->e[3], c->stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(c, FGL_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
     c->stats.kernel_launches = (uint32_t)launches;
@@ -225,13 +283,16 @@ int enqueue_draw(fgl_ctx *c, const DrawParams &p) {
 
 int initial_capacity(fgl_ctx *c, const DrawParams &p) {
     const uint64_t n = p.count;
-    // a primitive normally yields <= 1 record (2 for a line, 6 in wireframe); clipping may add a few
+    // a primitive normally yields <= 1 record (2 for a line, 6 in wireframe); clipping may add a few.
+    // Scanlines and segments depend on the projected size: start from a guess, the draw reports what
+    // it needed and the buffers are regrown on overflow.
     const uint64_t per = p.is_lines ? 2 : (p.state.wireframe ? 6 : 1);
     const uint64_t rec = n * per + n / 8 + 1024;
-    const uint64_t pairs = std::max<uint64_t>(rec * 2, 1u << 16);
-    const uint64_t clip = std::max<uint64_t>(n / 16, 4096);
-    return ensure_work(c, n, std::max<uint64_t>(rec, c->wb.cap_records), std::max<uint64_t>(pairs, c->wb.cap_pairs),
-                       std::max<uint64_t>(clip, c->wb.cap_clip));
+    Caps want{n, std::max<uint64_t>(rec, c->wb.cap_records), std::max<uint64_t>(rec * 4, c->wb.cap_rows),
+              std::max<uint64_t>(rec * 4, c->wb.cap_segs), std::max<uint64_t>(std::max<uint64_t>(n / 16, 4096), c->wb.cap_clip)};
+    want.rows = std::max<uint64_t>(want.rows, 1u << 16);
+    want.segs = std::max<uint64_t>(want.segs, 1u << 16);
+    return ensure_work(c, want);
 }
 
 int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const fgl_mesh *mesh, uint64_t first,
@@ -263,15 +324,12 @@ int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const 
         const DrawCounters &hc = *c->host_counters;
         if (!hc.overflow) {
             if (info) { info->total_pixels = hc.total_pixels; info->updated_pixels = hc.updated_pixels; }
-            c->stats.records = hc.n_records; c->stats.pairs = hc.n_pairs; c->stats.clip_triangles = hc.n_clip;
+            c->stats.records = hc.n_records; c->stats.pairs = hc.n_segs; c->stats.clip_triangles = hc.n_clip;
             return FGL_OK;
         }
         // the raster kernel did not run (it checks the flag): grow and re-issue
         c->stats.retries++;
-        const uint64_t rec = std::max<uint64_t>(c->wb.cap_records, (uint64_t)hc.need_records + hc.need_records / 4 + 1024);
-        const uint64_t pairs = std::max<uint64_t>(c->wb.cap_pairs, (uint64_t)hc.need_pairs + hc.need_pairs / 4 + 1024);
-        const uint64_t clip = std::max<uint64_t>(c->wb.cap_clip, (uint64_t)hc.need_clip + hc.need_clip / 4 + 1024);
-        rc = ensure_work(c, p.count, rec, pairs, clip);
+        rc = ensure_work(c, grown(c, hc));
         if (rc) return rc;
     }
     return fail(c, FGL_E_OVERFLOW, "work buffers still too small after regrowing");
@@ -297,7 +355,7 @@ int fgl_device_count(void) {
 int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     if (!out) return fail(nullptr, FGL_E_INVALID, "null out pointer");
     *out = nullptr;
-    if (width <= 0 || height <= 0 || width > 65535 * TILE_W / 4 || height > 65535 * TILE_H / 4 ||
+    if (width <= 0 || height <= 0 || width > 65535 || height > 65535 ||
         (uint64_t)width * (uint64_t)height > (1ull << 31))
         return fail(nullptr, FGL_E_INVALID, "bad framebuffer size %dx%d", width, height);
     int ndev = 0;
@@ -316,6 +374,8 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     memset(&c->wb, 0, sizeof c->wb);
     memset(&c->stats, 0, sizeof c->stats);
     c->host_counters = nullptr; c->acc_dev = nullptr; c->async_pending = false;
+    c->profiling = false; c->prof_used = 0; c->prof_created = false;
+    memset(&c->prof_acc, 0, sizeof c->prof_acc);
     const size_t npix = (size_t)width * height;
     cudaError_t err = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = dev_alloc(&c->color, npix);
@@ -358,6 +418,9 @@ int fgl_context_destroy(fgl_ctx *c) {
     dev_free(c->wb.tile_start); dev_free(c->wb.tile_end); dev_free(c->wb.counters);
     dev_free(c->acc_dev); dev_free(c->color); dev_free(c->depth); dev_free(c->resolved);
     if (c->host_counters) cudaFreeHost(c->host_counters);
+    if (c->prof_created)
+        for (int i = 0; i < PROF_RING; i++)
+            for (int k = 0; k < 4; k++) cudaEventDestroy(c->prof[i].e[k]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return FGL_OK;
@@ -392,18 +455,39 @@ int fgl_clear_depth(fgl_ctx *c, double value) {
 
 // ---- meshes ---------------------------------------------------------------------------------
 
+// Each attribute lands in its own region of the staging buffer, so all H2D copies of
+// one upload are queued back to back and the transposing ingest kernels trail them.
 static int upload_attr(fgl_ctx *c, const double *host, double **planes, uint64_t n, int nverts, int ncomp_in,
-                       int ncomp_out, double *staging) {
-    CK(c, dev_alloc(planes, (size_t)n * nverts * ncomp_out));
+                       int ncomp_out, double *staging, bool create) {
+    if (create) CK(c, dev_alloc(planes, (size_t)n * nverts * ncomp_out));
     if (n == 0) return FGL_OK;
     if (!host) {
-        CK(c, cudaMemsetAsync(*planes, 0, sizeof(double) * n * nverts * ncomp_out, c->stream));
+        if (create) CK(c, cudaMemsetAsync(*planes, 0, sizeof(double) * n * nverts * ncomp_out, c->stream));
         return FGL_OK;
     }
     CK(c, cudaMemcpyAsync(staging, host, sizeof(double) * n * nverts * ncomp_in, cudaMemcpyHostToDevice, c->stream));
     launch_mesh_ingest(staging, *planes, (uint32_t)n, nverts, ncomp_in, ncomp_out, c->stream);
     CK(c, cudaGetLastError());
     return FGL_OK;
+}
+
+static int upload_all(fgl_ctx *c, fgl_mesh *m, const fgl_mesh_desc *d, bool create) {
+    // staging regions: [pos | nrm | tex | col] for triangles, then the same for lines
+    const size_t t3 = (size_t)m->nt * 9, t4 = (size_t)m->nt * 12, l3 = (size_t)m->nl * 6, l4 = (size_t)m->nl * 8;
+    double *s = m->staging;
+    int rc = upload_attr(c, d->position, &m->tpos, m->nt, 3, 3, 3, s, create);
+    if (!rc) rc = upload_attr(c, d->normal, &m->tnrm, m->nt, 3, 3, 3, s + t3, create);
+    if (!rc) rc = upload_attr(c, d->texture, &m->ttex, m->nt, 3, 3, 2, s + 2 * t3, create);
+    if (!rc) rc = upload_attr(c, d->color, &m->tcol, m->nt, 3, 4, 4, s + 3 * t3, create);
+    s += 3 * t3 + t4;
+    if (!rc) rc = upload_attr(c, d->lposition, &m->lpos, m->nl, 2, 3, 3, s, create);
+    if (!rc) rc = upload_attr(c, d->lnormal, &m->lnrm, m->nl, 2, 3, 3, s + l3, create);
+    if (!rc) rc = upload_attr(c, d->ltexture, &m->ltex, m->nl, 2, 3, 2, s + 2 * l3, create);
+    if (!rc) rc = upload_attr(c, d->lcolor, &m->lcol, m->nl, 2, 4, 4, s + 3 * l3, create);
+    (void)l4;
+    cudaError_t se = cudaStreamSynchronize(c->stream);  // the caller may reuse its host arrays
+    if (!rc && se != cudaSuccess) rc = fail(c, FGL_E_CUDA, "mesh upload: %s", cudaGetErrorString(se));
+    return rc;
 }
 
 int fgl_mesh_create(fgl_ctx *c, const fgl_mesh_desc *d, fgl_mesh **out) {
@@ -419,25 +503,26 @@ int fgl_mesh_create(fgl_ctx *c, const fgl_mesh_desc *d, fgl_mesh **out) {
     if (!m) return fail(c, FGL_E_OOM, "host allocation failed");
     memset(m, 0, sizeof *m);
     m->device = c->device; m->nt = d->ntriangles; m->nl = d->nlines;
-    // one staging buffer, reused attribute by attribute (stream order keeps it safe)
-    const size_t stage_elems = std::max<size_t>((size_t)m->nt * 3 * 4, (size_t)m->nl * 2 * 4);
-    double *staging = nullptr;
-    cudaError_t e = dev_alloc(&staging, stage_elems);
+    m->staging_elems = (size_t)m->nt * (9 * 3 + 12) + (size_t)m->nl * (6 * 3 + 8);
+    cudaError_t e = dev_alloc(&m->staging, m->staging_elems);
     if (e != cudaSuccess) { delete m; cudaGetLastError(); return fail(c, FGL_E_OOM, "staging: %s", cudaGetErrorString(e)); }
-    rc = upload_attr(c, d->position, &m->tpos, m->nt, 3, 3, 3, staging);
-    if (!rc) rc = upload_attr(c, d->normal, &m->tnrm, m->nt, 3, 3, 3, staging);
-    if (!rc) rc = upload_attr(c, d->texture, &m->ttex, m->nt, 3, 3, 2, staging);
-    if (!rc) rc = upload_attr(c, d->color, &m->tcol, m->nt, 3, 4, 4, staging);
-    if (!rc) rc = upload_attr(c, d->lposition, &m->lpos, m->nl, 2, 3, 3, staging);
-    if (!rc) rc = upload_attr(c, d->lnormal, &m->lnrm, m->nl, 2, 3, 3, staging);
-    if (!rc) rc = upload_attr(c, d->ltexture, &m->ltex, m->nl, 2, 3, 2, staging);
-    if (!rc) rc = upload_attr(c, d->lcolor, &m->lcol, m->nl, 2, 4, 4, staging);
-    cudaError_t se = cudaStreamSynchronize(c->stream);
-    cudaFree(staging);
-    if (!rc && se != cudaSuccess) rc = fail(c, FGL_E_CUDA, "mesh upload: %s", cudaGetErrorString(se));
+    rc = upload_all(c, m, d, true);
     if (rc) { fgl_mesh_destroy(m); return rc; }
     *out = m;
     return FGL_OK;
+}
+
+int fgl_mesh_update(fgl_ctx *c, fgl_mesh *m, const fgl_mesh_desc *d) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!m || !d) return fail(c, FGL_E_INVALID, "null mesh/description");
+    if (m->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on another device");
+    if (d->ntriangles != m->nt || d->nlines != m->nl)
+        return fail(c, FGL_E_INVALID, "fgl_mesh_update needs the same primitive counts (%llu/%llu vs %llu/%llu)",
+                    (unsigned long long)d->ntriangles, (unsigned long long)d->nlines, (unsigned long long)m->nt,
+                    (unsigned long long)m->nl);
+    std::lock_guard<std::mutex> lock(c->mu);
+    return upload_all(c, m, d, false);
 }
 
 int fgl_mesh_destroy(fgl_mesh *m) {
@@ -445,6 +530,7 @@ int fgl_mesh_destroy(fgl_mesh *m) {
     cudaSetDevice(m->device);
     dev_free(m->tpos); dev_free(m->tnrm); dev_free(m->ttex); dev_free(m->tcol);
     dev_free(m->lpos); dev_free(m->lnrm); dev_free(m->ltex); dev_free(m->lcol);
+    dev_free(m->staging);
     delete m;
     return FGL_OK;
 }
@@ -560,10 +646,7 @@ int fgl_sync(fgl_ctx *c, fgl_raster_info *info) {
         const DrawCounters hc = *c->host_counters;
         if (hc.overflow) {
             // grow so that re-issuing the frame succeeds
-            ensure_work(c, c->wb.cap_prims,
-                        std::max<uint64_t>(c->wb.cap_records, (uint64_t)hc.need_records + hc.need_records / 4 + 1024),
-                        std::max<uint64_t>(c->wb.cap_pairs, (uint64_t)hc.need_pairs + hc.need_pairs / 4 + 1024),
-                        std::max<uint64_t>(c->wb.cap_clip, (uint64_t)hc.need_clip + hc.need_clip / 4 + 1024));
+            ensure_work(c, grown(c, hc));
             return fail(c, FGL_E_OVERFLOW, "an async draw outgrew its work buffers (now regrown): re-issue the frame");
         }
         if (info) { info->total_pixels = hc.total_pixels; info->updated_pixels = hc.updated_pixels; }
@@ -574,6 +657,31 @@ int fgl_sync(fgl_ctx *c, fgl_raster_info *info) {
 int fgl_get_draw_stats(const fgl_ctx *c, fgl_draw_stats *out) {
     if (!c || !out) return fail(nullptr, FGL_E_INVALID, "null argument");
     *out = c->stats;
+    return FGL_OK;
+}
+
+int fgl_set_profiling(fgl_ctx *c, int enabled) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (enabled && !c->prof_created) {
+        for (int i = 0; i < PROF_RING; i++)
+            for (int k = 0; k < 4; k++) CK(c, cudaEventCreate(&c->prof[i].e[k]));
+        c->prof_created = true;
+    }
+    if (!enabled) prof_drain(c);
+    c->profiling = enabled != 0;
+    return FGL_OK;
+}
+
+int fgl_get_stage_times(fgl_ctx *c, fgl_stage_times *out) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!out) return fail(c, FGL_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(c->mu);
+    prof_drain(c);
+    *out = c->prof_acc;
+    memset(&c->prof_acc, 0, sizeof c->prof_acc);
     return FGL_OK;
 }
 

@@ -94,8 +94,8 @@ FGL_DI int32_t sat_i32(long long v) {
     return (int32_t)(v < -L ? -L : (v > L ? L : v));
 }
 
-// Integer bounding box of a screen triangle, context.go:155-160, and its on-screen tile range.
-struct BBox { int32_t x0, x1, y0, y1; bool visible; RecTiles tiles; uint32_t npairs; };
+// Integer bounding box of a screen triangle, context.go:155-160, and its on-screen scanlines.
+struct BBox { int32_t x0, x1, y0, y1; bool visible; uint32_t rows; };
 FGL_DI BBox compute_bbox(const DrawParams &p, V3 s0, V3 s1, V3 s2) {
     BBox b;
     const double mnx = go_min(s0.x, go_min(s1.x, s2.x)), mny = go_min(s0.y, go_min(s1.y, s2.y));
@@ -114,15 +114,12 @@ FGL_DI BBox compute_bbox(const DrawParams &p, V3 s0, V3 s1, V3 s2) {
     // itself would spin for 2^63 iterations on those) is dropped instead of walked.
     constexpr int32_t FAR = 1 << 22;
     if (b.x0 < -FAR || b.y0 < -FAR || b.x1 > FAR || b.y1 > FAR) b.visible = false;
-    if (b.visible) {
-        b.tiles.tx0 = (uint16_t)(cx0 / TILE_W); b.tiles.tx1 = (uint16_t)(cx1 / TILE_W);
-        b.tiles.ty0 = (uint16_t)(cy0 / TILE_H); b.tiles.ty1 = (uint16_t)(cy1 / TILE_H);
-        b.npairs = (uint32_t)(b.tiles.tx1 - b.tiles.tx0 + 1) * (uint32_t)(b.tiles.ty1 - b.tiles.ty0 + 1);
-    } else {
-        b.tiles.tx0 = b.tiles.tx1 = b.tiles.ty0 = b.tiles.ty1 = 0;
-        b.npairs = 0;
-    }
+    b.rows = b.visible ? (uint32_t)(cy1 - cy0 + 1) : 0u;
     return b;
+}
+
+FGL_DI double edge_fn(V3 a, V3 b, V3 c) {  // context.go:147-149
+    return (b.x - c.x) * (a.y - c.y) - (b.y - c.y) * (a.x - c.x);
 }
 
 struct CountEmit {
@@ -149,12 +146,19 @@ struct WriteEmit {
         rec.s[0] = s0.x; rec.s[1] = s0.y; rec.s[2] = s0.z;
         rec.s[3] = s1.x; rec.s[4] = s1.y; rec.s[5] = s1.z;
         rec.s[6] = s2.x; rec.s[7] = s2.y; rec.s[8] = s2.z;
-        rec.w[0] = w0; rec.w[1] = w1; rec.w[2] = w2;
+        // per-triangle setup of Context.rasterize, context.go:163-181
+        const V3 pc = v3((double)b.x0 + 0.5, (double)b.y0 + 0.5, 0);
+        rec.w00 = edge_fn(s1, s2, pc);
+        rec.w01 = edge_fn(s2, s0, pc);
+        rec.w02 = edge_fn(s0, s1, pc);
+        const double a01 = s1.y - s0.y, a12 = s2.y - s1.y, a20 = s0.y - s2.y;
+        rec.ra = 1 / edge_fn(s0, s1, s2);
+        rec.r0 = 1 / w0; rec.r1 = 1 / w1; rec.r2 = 1 / w2;
+        rec.ra12 = 1 / a12; rec.ra20 = 1 / a20; rec.ra01 = 1 / a01;
         rec.src = src; rec.flags = flags;
         rec.x0 = b.x0; rec.x1 = b.x1; rec.y0 = b.y0; rec.y1 = b.y1;
         wb->recs[r] = rec;
-        wb->rec_tiles[r] = b.tiles;
-        wb->rec_npairs[r] = b.npairs;
+        wb->rec_rows[r] = b.rows;
     }
     FGL_DI uint32_t pool_alloc(const FullVertex *v) {
         const uint32_t slot = atomicAdd(&wb->counters->n_clip, 1u);
@@ -391,8 +395,8 @@ FGL_DI void process_line(const DrawParams &p, Emit &e, uint32_t prim) {
 
 __global__ void k_draw_begin(DrawCounters *ctr) {
     ctr->total_pixels = 0; ctr->updated_pixels = 0;
-    ctr->n_records = 0; ctr->n_pairs = 0; ctr->n_clip = 0; ctr->overflow = 0;
-    ctr->need_records = 0; ctr->need_pairs = 0; ctr->need_clip = 0; ctr->_pad = 0;
+    ctr->n_records = 0; ctr->n_rows = 0; ctr->n_segs = 0; ctr->n_clip = 0; ctr->overflow = 0;
+    ctr->need_records = 0; ctr->need_rows = 0; ctr->need_segs = 0; ctr->need_clip = 0; ctr->_pad = 0;
 }
 
 __global__ void __launch_bounds__(256)

@@ -11,8 +11,8 @@ namespace fgl {
 
 // ---- screen tiles -------------------------------------------------------------
 // Wide, short tiles: the reference walks each scanline left to right with
-// forward differencing (context.go:207-213), so a span that crosses a tile
-// boundary has to replay the chain from its start; wide tiles keep that rare.
+// forward differencing (context.go:207-213); a span is cut into one segment per
+// tile column it covers, so wide tiles mean few segments.
 constexpr int TILE_W = 64;
 constexpr int TILE_H = 16;
 constexpr int TILE_PIX = TILE_W * TILE_H;
@@ -29,20 +29,22 @@ struct MeshPlanes {
     uint32_t nverts;    // 3 for triangles, 2 for lines
 };
 
-// ---- raster record: one screen-space triangle handed to the tile rasteriser ----
-// (the arguments of Context.rasterize, context.go:151, minus the attributes,
-// which stay in the mesh planes / clip pool and are fetched on demand).
+// ---- raster record: one screen-space triangle with the per-triangle setup of
+// Context.rasterize (context.go:155-181) done once by the geometry stage.
 struct __align__(16) Rec {
-    double s[9];     // s0.xyz s1.xyz s2.xyz (screen space)
-    double w[3];     // Output.W of v0 v1 v2
-    uint32_t src;    // primitive index in the mesh planes, or clip-pool triangle index
-    uint32_t flags;  // REC_* below
-    int32_t x0, x1;  // integer bounding box, context.go:155-160 (saturated to int32)
+    double s[9];             // s0.xyz s1.xyz s2.xyz (screen space)
+    double w00, w01, w02;    // edge functions at the first pixel centre (x0+.5, y0+.5), context.go:163-166
+    double ra;               // 1 / edge(s0,s1,s2), context.go:175
+    double ra12, ra20, ra01; // context.go:179-181
+    double r0, r1, r2;       // 1 / Output.W, context.go:176-178
+    uint32_t src;            // primitive index in the mesh planes, or clip-pool triangle index
+    uint32_t flags;          // REC_* below
+    int32_t x0, x1;          // integer bounding box, context.go:155-160 (saturated to int32)
     int32_t y0, y1;
 };
-static_assert(sizeof(Rec) == 128, "Rec layout");
+static_assert(sizeof(Rec) == 176, "Rec layout");
 
-constexpr uint32_t REC_VMAP_MASK = 0x3f;  // 3 x 2 bits: source vertex of v0,v1,v2
+constexpr uint32_t REC_VMAP_MASK = 0x3f;    // 3 x 2 bits: source vertex of v0,v1,v2
 constexpr uint32_t REC_SRC_POOL = 1u << 6;  // src indexes the clip pool
 
 // Clip pool: vertices produced by ClipTriangle (clipping.go:54-74), AoS.
@@ -51,8 +53,16 @@ struct ClipVertex {
 };
 struct ClipTri { ClipVertex v[3]; };
 
-// Tile bounding box of a record (inclusive), for pair generation.
-struct RecTiles { uint16_t tx0, tx1, ty0, ty1; };
+// ---- span segment: the covered pixels of one scanline of one triangle inside one
+// tile, with the forward-differenced edge values at its first pixel.
+struct __align__(16) Seg {
+    double w0, w1, w2;  // w0,w1,w2 of context.go:208-213 at pixel x (before that pixel's increment)
+    uint32_t rec;       // record index
+    uint16_t x;         // first covered pixel (absolute column)
+    uint8_t yt;         // row inside the tile
+    uint8_t cnt;        // covered pixels (1..TILE_W)
+};
+static_assert(sizeof(Seg) == 32, "Seg layout");
 
 // ---- per-draw device constants ------------------------------------------------------
 struct DrawParams {
@@ -70,32 +80,38 @@ struct DrawParams {
     MeshPlanes mesh;
     uint32_t first, count;  // primitive range
     int32_t is_lines;
+    int32_t deferred;       // 1: shading cannot discard or blend -> resolve depth in order, shade final winners
 };
 
 // Device-side counters/results of one draw (also copied to pinned host memory).
 struct DrawCounters {
     unsigned long long total_pixels, updated_pixels;
-    unsigned int n_records, n_pairs, n_clip, overflow;  // overflow: bit0 records, bit1 pairs, bit2 clip pool
-    unsigned int need_records, need_pairs, need_clip, _pad;
+    unsigned int n_records, n_rows, n_segs, n_clip;
+    unsigned int overflow;  // bit0 records, bit1 rows, bit2 clip pool, bit3 segments
+    unsigned int need_records, need_rows, need_segs, need_clip, _pad;
 };
+constexpr unsigned OVF_RECORDS = 1u, OVF_ROWS = 2u, OVF_CLIP = 4u, OVF_SEGS = 8u;
 
 struct WorkBuffers {
     // geometry
     uint32_t *prim_nrec;      // [count]   records emitted per primitive
     uint32_t *prim_rec_off;   // [count+1] exclusive scan
     Rec *recs;                // [cap_records]
-    RecTiles *rec_tiles;      // [cap_records]
-    uint32_t *rec_npairs;     // [cap_records]
-    uint32_t *rec_pair_off;   // [cap_records+1]
+    uint32_t *rec_rows;       // [cap_records]   on-screen scanlines of each record
+    uint32_t *rec_row_off;    // [cap_records+1] exclusive scan
     ClipTri *clip_pool;       // [cap_clip]
-    // binning
-    uint32_t *pair_key[2];    // [cap_pairs] tile id (ping-pong for the radix sort)
-    uint32_t *pair_val[2];    // [cap_pairs] record id
+    // spans
+    uint32_t *row_nseg;       // [cap_rows]   segments of each (record, scanline)
+    uint32_t *row_seg_off;    // [cap_rows+1] exclusive scan
+    Seg *segs;                // [cap_segs]   in (record, scanline, column) order
+    // binning: stable sort of segment indices by tile
+    uint32_t *seg_key[2];     // [cap_segs] tile id (ping-pong for the radix sort)
+    uint32_t *seg_val[2];     // [cap_segs] segment index
     uint32_t *tile_start;     // [ntiles]
     uint32_t *tile_end;       // [ntiles]
     uint32_t *scan_tmp;       // block sums for scans / radix histograms
     DrawCounters *counters;   // device
-    uint32_t cap_prims, cap_records, cap_pairs, cap_clip, ntiles, scan_tmp_words;
+    uint32_t cap_prims, cap_records, cap_rows, cap_segs, cap_clip, ntiles, scan_tmp_words;
 };
 
 // ---- kernel launchers (each returns the number of kernels it launched) --------------
@@ -112,9 +128,12 @@ int launch_clear_depth(double *depth, size_t npix, double v, cudaStream_t st);
 size_t scan_tmp_words(uint32_t n_max);
 int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n_max, const unsigned int *n_dev,
                           uint32_t *tmp, cudaStream_t st);
+// stable LSD radix sort of (key,val) pairs on `bits` key bits; returns launches, *sorted_buf = buffer index
+int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsigned int *n_dev, uint32_t n_max,
+                      int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st);
 
 int launch_geometry(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
-int launch_binning(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
+int launch_spans(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
 int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,
                   cudaStream_t st);
 

@@ -1,50 +1,41 @@
-// fgl_raster.cu -- tile-parallel back end: one CTA per 64x16 screen tile keeps
-// the tile's depth (f64) and colour (NRGBA8) in shared memory, consumes its bin
-// in primitive order and writes the tile back once, coalesced.
+// fgl_raster.cu -- tile-parallel, ordered back end: one CTA per 64x16 screen tile
+// keeps the tile's depth (f64) and colour (NRGBA8) in shared memory, consumes its
+// bin of span segments in primitive order and writes the tile back once,
+// coalesced -- replacing the reference's per-pixel mutex array.
 //
-// Replaces Context.rasterize (context.go:151-281), InterpolateVertexes
-// (vertex.go:18-47), the three built-in Fragment shaders (shader.go:25,44,75),
-// ImageTexture.BilinearSample (texture.go:41-63), Color.NRGBA (color.go:56) and
-// the mutex-guarded depth retest / write / blend (context.go:245-273).
+// Replaces the per-pixel body of Context.rasterize (context.go:207-273),
+// InterpolateVertexes (vertex.go:18-47), the three built-in Fragment shaders
+// (shader.go:25,44,75), ImageTexture.BilinearSample (texture.go:41-63),
+// Color.NRGBA (color.go:56) and the depth retest / write / blend (context.go:245-273).
 //
-// Arithmetic parity.  The reference evaluates the edge functions by forward
-// differencing: per row `w00 += b12`, a skip-ahead `d`, then `w0 += a12` per
-// pixel (context.go:184-213, 275).  Those chains of float64 adds are
-// reproduced literally: work item = one (triangle, scanline) span, walked left
-// to right by one thread with the same adds in the same order, so coverage,
-// barycentrics, depth and colour come out bit-identical to a sequential run of
-// the reference in triangle-index order.
+// Arithmetic parity.  Each segment carries the reference's forward-differenced
+// edge values at its first pixel (fgl_span.cu); this kernel continues the same
+// `w += a` chain (context.go:211-213), so barycentrics, depth and colour are
+// bit-identical to a sequential run of the reference in triangle-index order.
 //
-// Ordering.  Spans of a batch are processed in parallel; pixels touched by
-// several spans of one batch are resolved in rounds: every pending fragment
-// bids its span index with a shared-memory atomicMin on a per-pixel ticket, the
-// lowest index wins, runs the reference's depth test / shade / retest / write
-// on the tile copy, and retires.  That is exactly index order per pixel, which
-// makes `<=` ties, DepthBias, blending and UpdatedPixels well defined.
+// Ordering.  RT segments are resolved in parallel; pixels touched by several
+// segments of a batch are settled in rounds: every pending fragment bids its
+// batch index with a shared-memory atomicMin on a per-pixel ticket, the lowest
+// wins, applies the reference's depth test / retest / write to the tile copy
+// and retires.  That is index order per pixel, which makes `<=` ties,
+// DepthBias, blending and UpdatedPixels well defined.
+//
+// Deferred shading.  When the draw's shader can neither discard nor blend
+// (SolidColor, or Phong with an ObjectColor and no texture, alpha != 0 and no
+// effective blending) the fragment colour cannot influence any depth decision,
+// so the ordered phase resolves depth only and records, per pixel, the winning
+// record and its edge values; the colour of the final winners is computed once
+// per pixel at the end of the tile, with every thread busy.  Otherwise
+// fragments are shaded inline, in order, exactly like the reference.
 #include "fgl_internal.h"
 #include "fgl_block.cuh"
 #include "fgl_math.cuh"
 
 namespace fgl {
 
-constexpr int RT = 256;      // threads per CTA
-constexpr int CHUNK = 128;   // triangles set up per chunk
+constexpr int RT = 256;      // threads per CTA == segments per batch
 constexpr uint32_t NO_TICKET = 0xffffffffu;
-
-struct TriSetup {
-    double a12, a20, a01, b12, b20, b01;  // context.go:167-172
-    double w00, w01, w02;                 // edge values at (x0+.5, yfirst+.5)
-    double ra, ra12, ra20, ra01;          // context.go:175,179-181
-    double r0, r1, r2;                    // 1/Output.W, context.go:176-178
-    double z0, z1, z2;                    // s0.z s1.z s2.z
-    int32_t x0, x1;                       // bbox columns
-    int32_t yfirst, nrows;                // rows of the bbox inside this tile
-    uint32_t src, flags;
-};
-
-FGL_DI double edge_fn(double ax, double ay, double bx, double by, double cx, double cy) {  // context.go:147
-    return (bx - cx) * (ay - cy) - (by - cy) * (ax - cx);
-}
+constexpr uint32_t NO_WINNER = 0xffffffffu;
 
 FGL_DI double interp1(double a, double b, double c, double bx, double by, double bz, double bw) {  // vertex.go:49-79
     double n = 0;
@@ -177,187 +168,155 @@ FGL_DI uint32_t blend_over(uint32_t dst, uint32_t c8) {
     return dr | (dg << 8) | (db << 16) | (da << 24);
 }
 
+struct SegVis {   // what the ordered phase needs from the record
+    double ra, z0, z1, z2, a12, a20, a01;
+};
+
+// One fragment, inline mode: context.go:229-273 for a pixel whose ticket this thread holds.
+FGL_DI void fragment_inline(const DrawParams &p, const fgl_state &st, const WorkBuffers &wb, const Rec &r,
+                            double w0, double w1, double w2, int pi, double *s_depth, uint32_t *s_color,
+                            unsigned long long &updated) {
+    const double b0 = w0 * r.ra, b1 = w1 * r.ra, b2 = w2 * r.ra;
+    const double z = b0 * r.s[2] + b1 * r.s[5] + b2 * r.s[8];  // context.go:230
+    const double bz = z + st.depth_bias;
+    const double dcur = s_depth[pi];
+    if (st.read_depth && bz > dcur) return;                     // context.go:232
+    const double bx = b0 * r.r0, by = b1 * r.r1, bzz = b2 * r.r2;  // context.go:236
+    const double bw = 1 / (bx + by + bzz);
+    AttrSrc a{&p, wb.clip_pool, r.src, r.flags};
+    const C4 color = shade_fragment(p, a, bx, by, bzz, bw);
+    if (c_is_discard(color)) return;                            // context.go:241
+    if (bz <= dcur || !st.read_depth) {                         // context.go:248
+        updated++;
+        if (st.write_depth) s_depth[pi] = z;
+        if (st.write_color) {
+            const uint32_t c8 = c_nrgba(color);
+            if (st.alpha_blend && color.a < 1) s_color[pi] = blend_over(s_color[pi], c8);
+            else s_color[pi] = c8;
+        }
+    }
+}
+
+template <bool DEFERRED>
 __global__ void __launch_bounds__(RT)
-k_raster(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb,
-         const uint32_t *__restrict__ pair_val, uint32_t *__restrict__ gcolor, double *__restrict__ gdepth) {
+k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb,
+       const uint32_t *__restrict__ seg_order, uint32_t *__restrict__ gcolor, double *__restrict__ gdepth) {
     const uint32_t tile = blockIdx.x;
     const uint32_t bin_beg = wb.tile_start[tile], bin_end = wb.tile_end[tile];
     if (bin_beg >= bin_end) return;
     if (wb.counters->overflow) return;  // work buffers too small: the host regrows and re-issues the draw
 
-    __shared__ double s_depth[TILE_PIX];
-    __shared__ uint32_t s_color[TILE_PIX];
-    __shared__ uint32_t s_ticket[TILE_PIX];
-    __shared__ TriSetup s_tri[CHUNK];
-    __shared__ uint32_t s_span_off[CHUNK + 1];
-    __shared__ uint32_t s_scan[RT / 32 + 1];
-    __shared__ unsigned long long s_info[2];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_depth = reinterpret_cast<double *>(smem_raw);                 // [TILE_PIX]
+    double *s_w = s_depth + TILE_PIX;                                        // [3][TILE_PIX]   (deferred only)
+    uint32_t *s_color = reinterpret_cast<uint32_t *>(s_w + (DEFERRED ? 3 * TILE_PIX : 0));  // [TILE_PIX]
+    uint32_t *s_ticket = s_color + TILE_PIX;                                 // [TILE_PIX]
+    uint32_t *s_winner = s_ticket + TILE_PIX;                                // [TILE_PIX]      (deferred only)
+    __shared__ unsigned long long s_updated;
 
     const int tid = threadIdx.x;
     const int tile_x0 = (int)(tile % (uint32_t)p.tiles_x) * TILE_W;
     const int tile_y0 = (int)(tile / (uint32_t)p.tiles_x) * TILE_H;
     const int tw = min(TILE_W, p.width - tile_x0);   // valid columns of this tile
     const int th = min(TILE_H, p.height - tile_y0);  // valid rows
-    const int tile_x1 = tile_x0 + tw - 1, tile_y1 = tile_y0 + th - 1;
 
     // ---- load the tile ------------------------------------------------------------------------
     for (int i = tid; i < TILE_PIX; i += RT) {
         const int lx = i % TILE_W, ly = i / TILE_W;
         s_ticket[i] = NO_TICKET;
+        if (DEFERRED) s_winner[i] = NO_WINNER;
         if (lx < tw && ly < th) {
             const size_t g = (size_t)(tile_y0 + ly) * p.width + (tile_x0 + lx);
             s_depth[i] = gdepth[g];
             s_color[i] = gcolor[g];
         }
     }
-    if (tid < 2) s_info[tid] = 0;
+    if (tid == 0) s_updated = 0;
     __syncthreads();
 
     const fgl_state st = p.state;
-    unsigned long long my_total = 0, my_updated = 0;
+    unsigned long long my_updated = 0;
 
-    for (uint32_t chunk = bin_beg; chunk < bin_end; chunk += CHUNK) {
-        const uint32_t ntri = min((uint32_t)CHUNK, bin_end - chunk);
-
-        // ---- per-triangle setup: context.go:163-181, rows clipped to the tile ------------------
-        uint32_t my_rows = 0;
-        if (tid < (int)ntri) {
-            const Rec *rp = wb.recs + pair_val[chunk + tid];
-            const double s0x = rp->s[0], s0y = rp->s[1], s0z = rp->s[2];
-            const double s1x = rp->s[3], s1y = rp->s[4], s1z = rp->s[5];
-            const double s2x = rp->s[6], s2y = rp->s[7], s2z = rp->s[8];
-            const int x0 = rp->x0, x1 = rp->x1, y0 = rp->y0, y1 = rp->y1;
-            TriSetup t;
-            const double px = (double)x0 + 0.5, py = (double)y0 + 0.5;
-            double w00 = edge_fn(s1x, s1y, s2x, s2y, px, py);
-            double w01 = edge_fn(s2x, s2y, s0x, s0y, px, py);
-            double w02 = edge_fn(s0x, s0y, s1x, s1y, px, py);
-            t.a01 = s1y - s0y; t.b01 = s0x - s1x;
-            t.a12 = s2y - s1y; t.b12 = s1x - s2x;
-            t.a20 = s0y - s2y; t.b20 = s2x - s0x;
-            t.ra = 1 / edge_fn(s0x, s0y, s1x, s1y, s2x, s2y);
-            t.r0 = 1 / rp->w[0]; t.r1 = 1 / rp->w[1]; t.r2 = 1 / rp->w[2];
-            t.ra12 = 1 / t.a12; t.ra20 = 1 / t.a20; t.ra01 = 1 / t.a01;
-            t.z0 = s0z; t.z1 = s1z; t.z2 = s2z;
-            const int ylo = max(y0, tile_y0), yhi = min(y1, tile_y1);
-            t.nrows = max(0, yhi - ylo + 1);
-            t.yfirst = ylo;
-            // the reference adds b12/b20/b01 once per row from y0 (context.go:275): replay it
-            if (t.nrows > 0)
-                for (int y = y0; y < ylo; y++) { w00 += t.b12; w01 += t.b20; w02 += t.b01; }
-            t.w00 = w00; t.w01 = w01; t.w02 = w02;
-            t.x0 = x0; t.x1 = x1;
-            t.src = rp->src; t.flags = rp->flags;
-            s_tri[tid] = t;
-            my_rows = (uint32_t)t.nrows;
+    for (uint32_t batch = bin_beg; batch < bin_end; batch += RT) {
+        const bool have = batch + tid < bin_end;
+        Seg sg;
+        sg.cnt = 0; sg.x = 0; sg.yt = 0; sg.rec = 0; sg.w0 = sg.w1 = sg.w2 = 0;
+        SegVis v;
+        v.ra = v.z0 = v.z1 = v.z2 = v.a12 = v.a20 = v.a01 = 0;
+        const Rec *rp = nullptr;
+        if (have) {
+            sg = wb.segs[seg_order[batch + tid]];
+            rp = wb.recs + sg.rec;
+            v.ra = rp->ra; v.z0 = rp->s[2]; v.z1 = rp->s[5]; v.z2 = rp->s[8];
+            v.a01 = rp->s[4] - rp->s[1]; v.a12 = rp->s[7] - rp->s[4]; v.a20 = rp->s[1] - rp->s[7];
         }
-        uint32_t nspans;
-        const uint32_t off = block_excl_scan<RT>(my_rows, s_scan, &nspans);
-        if (tid <= (int)ntri) s_span_off[tid] = (tid < (int)ntri) ? off : nspans;
-        __syncthreads();
+        const int xa = (int)sg.x, cnt = (int)sg.cnt;
+        const int rowbase = (int)sg.yt * TILE_W - tile_x0;
+        unsigned long long pend = cnt > 0 ? ((cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull)) << (xa - tile_x0)) : 0ull;
 
-        // ---- spans, RT at a time, in (triangle, row) order -----------------------------------------
-        for (uint32_t sbase = 0; sbase < nspans; sbase += RT) {
-            const uint32_t sid = sbase + tid;
-            const bool have = sid < nspans;
-            // span state
-            int xa = 0, cnt = 0, y = 0;
-            double wa0 = 0, wa1 = 0, wa2 = 0;
-            uint32_t tj = 0;
-            if (have) {
-                uint32_t lo = 0, hi = ntri;  // s_span_off[lo] <= sid < s_span_off[hi]
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (s_span_off[mid] <= sid) lo = mid; else hi = mid;
+        // ---- ordered resolution in rounds ---------------------------------------------------
+        while (true) {
+            if (pend) {
+                unsigned long long m = pend;
+                while (m) {
+                    const int bit = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    atomicMin(&s_ticket[(int)sg.yt * TILE_W + bit], (uint32_t)tid);
                 }
-                tj = lo;
-                const TriSetup &t = s_tri[tj];
-                const int row = (int)(sid - s_span_off[tj]);
-                y = t.yfirst + row;
-                double w00 = t.w00, w01 = t.w01, w02 = t.w02;
-                for (int k = 0; k < row; k++) { w00 += t.b12; w01 += t.b20; w02 += t.b01; }
-                // skip-ahead, context.go:185-205
-                double d = 0;
-                const double d0 = -w00 * t.ra12, d1 = -w01 * t.ra20, d2 = -w02 * t.ra01;
-                if (w00 < 0 && d0 > d) d = d0;
-                if (w01 < 0 && d1 > d) d = d1;
-                if (w02 < 0 && d2 > d) d = d2;
-                d = (double)go_int(d);
-                if (d < 0) d = 0;
-                double w0 = w00 + t.a12 * d, w1 = w01 + t.a20 * d, w2 = w02 + t.a01 * d;
-                long long x = (long long)t.x0 + go_int(d);
-                const long long xend = min((long long)t.x1, (long long)tile_x1);
-                if (x <= xend) {
-                    // replay the per-pixel adds up to the tile's first column (context.go:211-213)
-                    for (; x < tile_x0; x++) { w0 += t.a12; w1 += t.a20; w2 += t.a01; }
-                    for (; x <= xend; x++) {
-                        const double b0 = w0 * t.ra, b1 = w1 * t.ra, b2 = w2 * t.ra;
-                        if (b0 < 0 || b1 < 0 || b2 < 0) {
-                            if (cnt > 0) break;  // wasInside, context.go:216-218
-                        } else {
-                            if (cnt == 0) { xa = (int)x; wa0 = w0; wa1 = w1; wa2 = w2; }
-                            cnt++;
-                        }
-                        w0 += t.a12; w1 += t.a20; w2 += t.a01;
-                    }
-                }
-                my_total += (unsigned long long)cnt;  // context.go:229
             }
-            unsigned long long pend = cnt > 0 ? ((cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull)) << (xa - tile_x0)) : 0ull;
-            const int rowbase = (y - tile_y0) * TILE_W - tile_x0;
-
-            // ---- ordered resolution in rounds ---------------------------------------------------
-            while (true) {
-                if (pend) {
-                    unsigned long long m = pend;
-                    while (m) {
-                        const int bit = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        atomicMin(&s_ticket[(y - tile_y0) * TILE_W + bit], (uint32_t)tid);
-                    }
-                }
-                __syncthreads();
-                if (pend) {
-                    const TriSetup &t = s_tri[tj];
-                    double w0 = wa0, w1 = wa1, w2 = wa2;
-                    for (int x = xa; x < xa + cnt; x++) {
-                        const unsigned long long bitm = 1ull << (x - tile_x0);
-                        const int pi = rowbase + x;
-                        if ((pend & bitm) && s_ticket[pi] == (uint32_t)tid) {
-                            pend &= ~bitm;
-                            s_ticket[pi] = NO_TICKET;
-                            const double b0 = w0 * t.ra, b1 = w1 * t.ra, b2 = w2 * t.ra;
-                            const double z = b0 * t.z0 + b1 * t.z1 + b2 * t.z2;     // context.go:230
+            __syncthreads();
+            if (pend) {
+                double w0 = sg.w0, w1 = sg.w1, w2 = sg.w2;
+                for (int x = xa; x < xa + cnt; x++) {
+                    const unsigned long long bitm = 1ull << (x - tile_x0);
+                    const int pi = rowbase + x;
+                    if ((pend & bitm) && s_ticket[pi] == (uint32_t)tid) {
+                        pend &= ~bitm;
+                        s_ticket[pi] = NO_TICKET;
+                        if (DEFERRED) {
+                            const double b0 = w0 * v.ra, b1 = w1 * v.ra, b2 = w2 * v.ra;
+                            const double z = b0 * v.z0 + b1 * v.z1 + b2 * v.z2;  // context.go:230
                             const double bz = z + st.depth_bias;
                             const double dcur = s_depth[pi];
-                            if (!(st.read_depth && bz > dcur)) {                    // context.go:232
-                                const double bx = b0 * t.r0, by = b1 * t.r1, bzz = b2 * t.r2;  // :236
-                                const double bw = 1 / (bx + by + bzz);
-                                AttrSrc a{&p, wb.clip_pool, t.src, t.flags};
-                                const C4 color = shade_fragment(p, a, bx, by, bzz, bw);
-                                if (!c_is_discard(color)) {                         // context.go:241
-                                    if (bz <= dcur || !st.read_depth) {             // context.go:248
-                                        my_updated++;
-                                        if (st.write_depth) s_depth[pi] = z;
-                                        if (st.write_color) {
-                                            const uint32_t c8 = c_nrgba(color);
-                                            if (st.alpha_blend && color.a < 1) s_color[pi] = blend_over(s_color[pi], c8);
-                                            else s_color[pi] = c8;
-                                        }
-                                    }
+                            // context.go:232 early-out, then (no discard possible) the retest at :248
+                            if (!(st.read_depth && bz > dcur) && (bz <= dcur || !st.read_depth)) {
+                                my_updated++;
+                                if (st.write_depth) s_depth[pi] = z;
+                                if (st.write_color) {
+                                    s_winner[pi] = sg.rec;
+                                    s_w[pi] = w0; s_w[TILE_PIX + pi] = w1; s_w[2 * TILE_PIX + pi] = w2;
                                 }
                             }
+                        } else {
+                            fragment_inline(p, st, wb, *rp, w0, w1, w2, pi, s_depth, s_color, my_updated);
                         }
-                        w0 += t.a12; w1 += t.a20; w2 += t.a01;
                     }
+                    w0 += v.a12; w1 += v.a20; w2 += v.a01;  // context.go:211-213
                 }
-                if (!__syncthreads_or(pend != 0)) break;
             }
+            if (!__syncthreads_or(pend != 0)) break;
         }
-        __syncthreads();  // s_tri / s_span_off are rewritten by the next chunk
     }
 
-    // ---- write the tile back, RasterizeInfo -------------------------------------------------------
+    // ---- deferred shading of the tile's final winners ------------------------------------------
+    if (DEFERRED) {
+        __syncthreads();
+        for (int pi = tid; pi < TILE_PIX; pi += RT) {
+            const uint32_t rid = s_winner[pi];
+            if (rid == NO_WINNER) continue;
+            const Rec *rp = wb.recs + rid;
+            const double ra = rp->ra;
+            const double b0 = s_w[pi] * ra, b1 = s_w[TILE_PIX + pi] * ra, b2 = s_w[2 * TILE_PIX + pi] * ra;
+            const double bx = b0 * rp->r0, by = b1 * rp->r1, bzz = b2 * rp->r2;  // context.go:236
+            const double bw = 1 / (bx + by + bzz);
+            AttrSrc a{&p, wb.clip_pool, rp->src, rp->flags};
+            const C4 color = shade_fragment(p, a, bx, by, bzz, bw);
+            s_color[pi] = c_nrgba(color);  // SetNRGBA, context.go:269 (blending excluded by the mode)
+        }
+        __syncthreads();
+    }
+
+    // ---- write the tile back, UpdatedPixels ---------------------------------------------------------
     for (int i = tid; i < TILE_PIX; i += RT) {
         const int lx = i % TILE_W, ly = i / TILE_W;
         if (lx < tw && ly < th) {
@@ -366,26 +325,29 @@ k_raster(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffe
             gcolor[g] = s_color[i];
         }
     }
-    // warp-reduce the counters, then one atomic per warp
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        my_total += __shfl_down_sync(0xffffffffu, my_total, o);
-        my_updated += __shfl_down_sync(0xffffffffu, my_updated, o);
-    }
-    if ((tid & 31) == 0) {
-        atomicAdd(&s_info[0], my_total);
-        atomicAdd(&s_info[1], my_updated);
-    }
+    for (int o = 16; o > 0; o >>= 1) my_updated += __shfl_down_sync(0xffffffffu, my_updated, o);
+    if ((tid & 31) == 0 && my_updated) atomicAdd(&s_updated, my_updated);
     __syncthreads();
-    if (tid == 0) {
-        if (s_info[0]) atomicAdd(&wb.counters->total_pixels, s_info[0]);
-        if (s_info[1]) atomicAdd(&wb.counters->updated_pixels, s_info[1]);
-    }
+    if (tid == 0 && s_updated) atomicAdd(&wb.counters->updated_pixels, s_updated);
+}
+
+static size_t tile_smem(bool deferred) {
+    return sizeof(double) * TILE_PIX * (deferred ? 4 : 1) + sizeof(uint32_t) * TILE_PIX * (deferred ? 3 : 2);
 }
 
 int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,
                   cudaStream_t st) {
-    k_raster<<<wb.ntiles, RT, 0, st>>>(p, wb, wb.pair_val[sorted_buf], color, depth);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(true));
+        cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(false));
+        configured = true;
+    }
+    if (p.deferred)
+        k_tile<true><<<wb.ntiles, RT, tile_smem(true), st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
+    else
+        k_tile<false><<<wb.ntiles, RT, tile_smem(false), st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
     return 1;
 }
 

@@ -180,98 +180,38 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     }
 }
 
+
 // hist[256][G] -> exclusive scan in (digit-major, block-minor) order == global base of
-// each (digit, block) bucket.  Single block.
+// each (digit, block) bucket.  Single block; each thread first sums a contiguous slice.
 __global__ void __launch_bounds__(1024)
 k_radix_scan(uint32_t *__restrict__ hist, uint32_t n) {
     __shared__ uint32_t sm[1024 / 32 + 1];
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < n; base += 1024) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = i < n ? hist[i] : 0;
-        uint32_t total;
-        uint32_t ex = block_excl_scan<1024>(v, sm, &total);
-        if (i < n) hist[i] = carry + ex;
-        carry += total;
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t beg = min(threadIdx.x * per, n), end = min(beg + per, n);
+    uint32_t sum = 0;
+    for (uint32_t i = beg; i < end; i++) sum += hist[i];
+    uint32_t total;
+    uint32_t run = block_excl_scan<1024>(sum, sm, &total);
+    for (uint32_t i = beg; i < end; i++) {
+        const uint32_t v = hist[i];
+        hist[i] = run;
+        run += v;
     }
 }
 
-__global__ void k_tile_ranges(const uint32_t *__restrict__ keys, const unsigned int *__restrict__ n_dev, uint32_t n_max,
-                              uint32_t *__restrict__ tile_start, uint32_t *__restrict__ tile_end) {
-    const uint32_t n = min(*n_dev, n_max);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t k = keys[i];
-        if (i == 0 || keys[i - 1] != k) tile_start[k] = i;
-        if (i == n - 1 || keys[i + 1] != k) tile_end[k] = i + 1;
-    }
-}
-
-// Pair generation: thread per pair; the owning record is found by binary search
-// in the scanned per-record pair counts (load-balanced whatever the bbox sizes).
-__global__ void __launch_bounds__(256)
-k_emit_pairs(const uint32_t *__restrict__ rec_pair_off, const RecTiles *__restrict__ rec_tiles,
-             const DrawCounters *__restrict__ ctr, uint32_t cap_records, uint32_t cap_pairs, uint32_t tiles_x,
-             uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
-    const uint32_t nrec = min(ctr->n_records, cap_records);
-    const uint32_t npairs = min(ctr->n_pairs, cap_pairs);
-    if (ctr->overflow) return;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += gridDim.x * blockDim.x) {
-        // largest r with rec_pair_off[r] <= p
-        uint32_t lo = 0, hi = nrec;  // invariant: off[lo] <= p < off[hi]
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (rec_pair_off[mid] <= p) lo = mid; else hi = mid;
-        }
-        const RecTiles t = rec_tiles[lo];
-        const uint32_t q = p - rec_pair_off[lo];
-        const uint32_t tw = (uint32_t)t.tx1 - t.tx0 + 1u;
-        const uint32_t ty = t.ty0 + q / tw, tx = t.tx0 + q % tw;
-        keys[p] = ty * tiles_x + tx;
-        vals[p] = lo;
-    }
-}
-
-__global__ void k_set_npairs(DrawCounters *ctr, const uint32_t *__restrict__ rec_pair_off, uint32_t cap_records,
-                             uint32_t cap_pairs) {
-    const uint32_t nrec = min(ctr->n_records, cap_records);
-    const uint32_t total = rec_pair_off[nrec];
-    ctr->n_pairs = total;
-    ctr->need_pairs = total;
-    if (total > cap_pairs) ctr->overflow |= 2u;
-}
-
-int launch_binning(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st) {
-    int launches = 0;
-    // 1. per-record pair counts -> offsets; total -> counters
-    launches += launch_exclusive_scan(wb.rec_npairs, wb.rec_pair_off, wb.cap_records, &wb.counters->n_records,
-                                      wb.scan_tmp, st);
-    k_set_npairs<<<1, 1, 0, st>>>(wb.counters, wb.rec_pair_off, wb.cap_records, wb.cap_pairs);
-    launches++;
-    // 2. pairs in record order
+// Stable LSD radix sort of (key, val) on `bits` key bits, 8 bits per pass.
+int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsigned int *n_dev, uint32_t n_max,
+                      int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st) {
+    int launches = 0, cur = 0;
     const int G = RADIX_GRID;
-    k_emit_pairs<<<148 * 8, 256, 0, st>>>(wb.rec_pair_off, wb.rec_tiles, wb.counters, wb.cap_records, wb.cap_pairs,
-                                         (uint32_t)p.tiles_x, wb.pair_key[0], wb.pair_val[0]);
-    launches++;
-    // 3. stable sort by tile id
-    int bits = 1;
-    while ((1u << bits) < wb.ntiles) bits++;
-    int cur = 0;
     for (int shift = 0; shift < bits; shift += 8) {
-        k_radix_hist<<<G, RADIX_THREADS, 0, st>>>(wb.pair_key[cur], &wb.counters->n_pairs, wb.cap_pairs, shift,
-                                                  wb.scan_tmp);
-        k_radix_scan<<<1, 1024, 0, st>>>(wb.scan_tmp, RADIX_BINS * G);
-        k_radix_scatter<<<G, RADIX_THREADS, 0, st>>>(wb.pair_key[cur], wb.pair_val[cur], wb.pair_key[cur ^ 1],
-                                                     wb.pair_val[cur ^ 1], &wb.counters->n_pairs, wb.cap_pairs, shift,
-                                                     wb.scan_tmp);
+        k_radix_hist<<<G, RADIX_THREADS, 0, st>>>(key[cur], n_dev, n_max, shift, tmp);
+        k_radix_scan<<<1, 1024, 0, st>>>(tmp, RADIX_BINS * G);
+        k_radix_scatter<<<G, RADIX_THREADS, 0, st>>>(key[cur], val[cur], key[cur ^ 1], val[cur ^ 1], n_dev, n_max, shift,
+                                                     tmp);
         cur ^= 1;
         launches += 3;
     }
-    // 4. bin ranges
-    cudaMemsetAsync(wb.tile_start, 0, sizeof(uint32_t) * wb.ntiles, st);
-    cudaMemsetAsync(wb.tile_end, 0, sizeof(uint32_t) * wb.ntiles, st);
-    k_tile_ranges<<<148 * 4, 256, 0, st>>>(wb.pair_key[cur], &wb.counters->n_pairs, wb.cap_pairs, wb.tile_start,
-                                          wb.tile_end);
-    launches++;
     *sorted_buf = cur;
     return launches;
 }

@@ -1,0 +1,176 @@
+// fgl_span.cu -- span stage: one thread per (triangle, scanline) replays the
+// reference's inner loop for that row (context.go:184-221): the per-row adds from
+// y0, the skip-ahead `d`, then the per-pixel forward-differencing adds, exactly as
+// written, once, left to right.  The covered run is cut at tile-column
+// boundaries into segments that carry the edge values at their first pixel, so
+// the tile kernel continues the same chain of adds and reproduces coverage,
+// barycentrics and depth bit for bit -- without ever restarting a row.
+//
+// This stage is unordered and perfectly load-balanced (grid-wide, no barriers);
+// only covered segments reach the ordered, tile-serial back end.  Segments are
+// written in (triangle, scanline, column) order and then stably sorted by tile,
+// which keeps primitive order inside every bin.
+#include "fgl_internal.h"
+#include "fgl_block.cuh"
+#include "fgl_math.cuh"
+
+namespace fgl {
+
+template <bool EMIT>
+__device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const Rec &r, uint32_t rec_id, int y,
+                                             Seg *__restrict__ segs, uint32_t *__restrict__ keys, uint32_t base,
+                                             uint32_t cap, unsigned long long *covered) {
+    const double a01 = r.s[4] - r.s[1], b01 = r.s[0] - r.s[3];  // context.go:167-172
+    const double a12 = r.s[7] - r.s[4], b12 = r.s[3] - r.s[6];
+    const double a20 = r.s[1] - r.s[7], b20 = r.s[6] - r.s[0];
+    double w00 = r.w00, w01 = r.w01, w02 = r.w02;
+    for (int yy = r.y0; yy < y; yy++) { w00 += b12; w01 += b20; w02 += b01; }  // context.go:275-277
+    // skip-ahead, context.go:185-205
+    double d = 0;
+    const double d0 = -w00 * r.ra12, d1 = -w01 * r.ra20, d2 = -w02 * r.ra01;
+    if (w00 < 0 && d0 > d) d = d0;
+    if (w01 < 0 && d1 > d) d = d1;
+    if (w02 < 0 && d2 > d) d = d2;
+    d = (double)go_int(d);
+    if (d < 0) d = 0;
+    double w0 = w00 + a12 * d, w1 = w01 + a20 * d, w2 = w02 + a01 * d;
+    long long x = (long long)r.x0 + go_int(d);
+    const long long xend = min((long long)r.x1, (long long)p.width - 1);
+    if (x > xend) return 0;
+    for (; x < 0; x++) { w0 += a12; w1 += a20; w2 += a01; }  // left of the framebuffer: dropped (x-guard rule)
+    uint32_t nseg = 0, cnt = 0;
+    int col = -1, sx = 0;
+    double sw0 = 0, sw1 = 0, sw2 = 0;
+    bool was_inside = false;
+    const uint32_t key_row = (uint32_t)(y / TILE_H) * (uint32_t)p.tiles_x;
+    const uint8_t yt = (uint8_t)(y % TILE_H);
+    for (; x <= xend; x++) {
+        const double b0 = w0 * r.ra, b1 = w1 * r.ra, b2 = w2 * r.ra;  // context.go:208-210
+        if (b0 < 0 || b1 < 0 || b2 < 0) {
+            if (was_inside) break;  // context.go:216-218
+        } else {
+            was_inside = true;
+            const int c = (int)x / TILE_W;
+            if (cnt == 0 || c != col) {
+                if (cnt > 0) {
+                    if (EMIT && base + nseg < cap) {
+                        Seg s; s.w0 = sw0; s.w1 = sw1; s.w2 = sw2; s.rec = rec_id; s.x = (uint16_t)sx; s.yt = yt; s.cnt = (uint8_t)cnt;
+                        segs[base + nseg] = s;
+                        keys[base + nseg] = key_row + (uint32_t)col;
+                    }
+                    *covered += cnt;
+                    nseg++;
+                }
+                col = c; sx = (int)x; sw0 = w0; sw1 = w1; sw2 = w2; cnt = 0;
+            }
+            cnt++;
+        }
+        w0 += a12; w1 += a20; w2 += a01;  // context.go:211-213
+    }
+    if (cnt > 0) {
+        if (EMIT && base + nseg < cap) {
+            Seg s; s.w0 = sw0; s.w1 = sw1; s.w2 = sw2; s.rec = rec_id; s.x = (uint16_t)sx; s.yt = yt; s.cnt = (uint8_t)cnt;
+            segs[base + nseg] = s;
+            keys[base + nseg] = key_row + (uint32_t)col;
+        }
+        *covered += cnt;
+        nseg++;
+    }
+    return nseg;
+}
+
+// item i -> (record, scanline): largest r with rec_row_off[r] <= i
+__device__ __forceinline__ uint32_t find_rec(const uint32_t *__restrict__ off, uint32_t n, uint32_t i) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(256)
+k_spans(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
+    const DrawCounters *ctr = wb.counters;
+    if (ctr->overflow) return;
+    const uint32_t nrec = min(ctr->n_records, wb.cap_records);
+    const uint32_t nrows = min(ctr->n_rows, wb.cap_rows);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long covered = 0;
+    if (i < nrows) {
+        const uint32_t rid = find_rec(wb.rec_row_off, nrec, i);
+        const Rec r = wb.recs[rid];
+        const int y = max(r.y0, 0) + (int)(i - wb.rec_row_off[rid]);
+        if (EMIT) {
+            if (wb.row_nseg[i]) walk_row<true>(p, r, rid, y, wb.segs, wb.seg_key[0], wb.row_seg_off[i], wb.cap_segs, &covered);
+        } else {
+            wb.row_nseg[i] = walk_row<false>(p, r, rid, y, nullptr, nullptr, 0, 0, &covered);
+        }
+    }
+    if (!EMIT) {  // TotalPixels, context.go:229: every covered in-range pixel, before any depth test
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) covered += __shfl_down_sync(0xffffffffu, covered, o);
+        if ((threadIdx.x & 31) == 0 && covered) atomicAdd(&wb.counters->total_pixels, covered);
+    }
+}
+
+__global__ void k_set_nrows(DrawCounters *ctr, const uint32_t *__restrict__ rec_row_off, uint32_t cap_records,
+                            uint32_t cap_rows) {
+    const uint32_t nrec = min(ctr->n_records, cap_records);
+    const uint32_t total = rec_row_off[nrec];
+    ctr->n_rows = total;
+    ctr->need_rows = total;
+    if (total > cap_rows) ctr->overflow |= OVF_ROWS;
+}
+__global__ void k_set_nsegs(DrawCounters *ctr, const uint32_t *__restrict__ row_seg_off, uint32_t cap_rows,
+                            uint32_t cap_segs) {
+    if (ctr->overflow) return;
+    const uint32_t nrows = min(ctr->n_rows, cap_rows);
+    const uint32_t total = row_seg_off[nrows];
+    ctr->n_segs = total;
+    ctr->need_segs = total;
+    if (total > cap_segs) ctr->overflow |= OVF_SEGS;
+}
+__global__ void k_seg_iota(uint32_t *__restrict__ vals, const DrawCounters *__restrict__ ctr, uint32_t cap_segs) {
+    const uint32_t n = min(ctr->n_segs, cap_segs);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) vals[i] = i;
+}
+__global__ void k_tile_ranges(const uint32_t *__restrict__ keys, const unsigned int *__restrict__ n_dev, uint32_t n_max,
+                              uint32_t *__restrict__ tile_start, uint32_t *__restrict__ tile_end) {
+    const uint32_t n = min(*n_dev, n_max);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t k = keys[i];
+        if (i == 0 || keys[i - 1] != k) tile_start[k] = i;
+        if (i == n - 1 || keys[i + 1] != k) tile_end[k] = i + 1;
+    }
+}
+
+int launch_spans(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st) {
+    int launches = 0;
+    // scanlines per record -> item offsets
+    launches += launch_exclusive_scan(wb.rec_rows, wb.rec_row_off, wb.cap_records, &wb.counters->n_records,
+                                      wb.scan_tmp, st);
+    k_set_nrows<<<1, 1, 0, st>>>(wb.counters, wb.rec_row_off, wb.cap_records, wb.cap_rows);
+    const uint32_t blocks = (wb.cap_rows + 255) / 256;
+    k_spans<false><<<blocks ? blocks : 1, 256, 0, st>>>(p, wb);
+    launches += 2;
+    launches += launch_exclusive_scan(wb.row_nseg, wb.row_seg_off, wb.cap_rows, &wb.counters->n_rows, wb.scan_tmp, st);
+    k_set_nsegs<<<1, 1, 0, st>>>(wb.counters, wb.row_seg_off, wb.cap_rows, wb.cap_segs);
+    k_spans<true><<<blocks ? blocks : 1, 256, 0, st>>>(p, wb);
+    k_seg_iota<<<148 * 4, 256, 0, st>>>(wb.seg_val[0], wb.counters, wb.cap_segs);
+    launches += 3;
+    // stable sort of the segment indices by tile id
+    int bits = 1;
+    while ((1u << bits) < wb.ntiles) bits++;
+    launches += launch_sort_pairs(wb.seg_key, wb.seg_val, &wb.counters->n_segs, wb.cap_segs, bits, wb.scan_tmp,
+                                  sorted_buf, st);
+    cudaMemsetAsync(wb.tile_start, 0, sizeof(uint32_t) * wb.ntiles, st);
+    cudaMemsetAsync(wb.tile_end, 0, sizeof(uint32_t) * wb.ntiles, st);
+    k_tile_ranges<<<148 * 4, 256, 0, st>>>(wb.seg_key[*sorted_buf], &wb.counters->n_segs, wb.cap_segs, wb.tile_start,
+                                          wb.tile_end);
+    launches++;
+    return launches;
+}
+
+}  // namespace fgl

@@ -97,7 +97,7 @@ typedef struct { uint64_t total_pixels, updated_pixels; } fgl_raster_info;
 typedef struct {
     uint64_t prims_in;       /* primitives submitted                       */
     uint64_t records;        /* raster triangles after clip/cull/expansion */
-    uint64_t pairs;          /* (tile, triangle) pairs binned              */
+    uint64_t pairs;          /* covered span segments binned into tiles    */
     uint64_t clip_triangles; /* triangles produced by the clipper          */
     uint32_t tiles_x, tiles_y, tile_w, tile_h;
     uint32_t kernel_launches; /* kernels launched by that draw             */
@@ -123,6 +123,11 @@ int fgl_clear_depth(fgl_ctx *ctx, double value);
 /* Upload a mesh once; draws reference it by handle (the reference walks
  * []*Triangle on every DrawTriangles call, context.go:413-433). */
 int fgl_mesh_create(fgl_ctx *ctx, const fgl_mesh_desc *desc, fgl_mesh **out);
+/* Re-upload attributes of an existing mesh (same primitive counts) into its
+ * device buffers; NULL pointers leave that attribute untouched.  This is what
+ * the shim calls when a cached Mesh was mutated on the host between frames
+ * (examples/animate.go:66 transforms the mesh on the CPU every frame). */
+int fgl_mesh_update(fgl_ctx *ctx, fgl_mesh *mesh, const fgl_mesh_desc *desc);
 int fgl_mesh_destroy(fgl_mesh *mesh);
 int fgl_mesh_counts(const fgl_mesh *mesh, uint64_t *ntriangles, uint64_t *nlines);
 /* Mesh.Transform, mesh.go:167-175 (+ triangle.go:66-73, line.go:23-28): positions
@@ -154,6 +159,19 @@ int fgl_draw_lines_async(fgl_ctx *ctx, const fgl_state *state, const fgl_shader 
  * sum over the async draws since the previous fgl_sync. */
 int fgl_sync(fgl_ctx *ctx, fgl_raster_info *info);
 int fgl_get_draw_stats(const fgl_ctx *ctx, fgl_draw_stats *out);
+
+/* Per-stage device timing (CUDA events on the context's stream).  While enabled,
+ * every draw records events between its stages; fgl_get_stage_times waits for
+ * the stream and returns the milliseconds accumulated since the last call and
+ * the number of draws they cover. */
+typedef struct {
+    float geometry_ms;   /* vertex transform, clip, cull, setup, ordered compaction */
+    float binning_ms;    /* pair generation, stable sort by tile, bin ranges        */
+    float raster_ms;     /* tile rasteriser (coverage, depth, shading, write-back)  */
+    uint32_t draws;
+} fgl_stage_times;
+int fgl_set_profiling(fgl_ctx *ctx, int enabled);
+int fgl_get_stage_times(fgl_ctx *ctx, fgl_stage_times *out);
 
 /* Image(), context.go:83-85: ColorBuffer.Pix (NRGBA8, non-premultiplied). */
 int fgl_read_color(fgl_ctx *ctx, uint8_t *dst, size_t stride_bytes);
