@@ -162,7 +162,7 @@ struct WriteEmit {
     }
     FGL_DI uint32_t pool_alloc(const FullVertex *v) {
         const uint32_t slot = atomicAdd(&wb->counters->n_clip, 1u);
-        if (slot >= wb->cap_clip) { atomicOr(&wb->counters->overflow, 4u); return 0; }
+        if (slot >= wb->cap_clip) { atomicOr(&wb->counters->overflow, OVF_CLIP); return 0; }
         ClipTri t;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -393,14 +393,13 @@ FGL_DI void process_line(const DrawParams &p, Emit &e, uint32_t prim) {
     emit_line(p, e, s0, s1, 0, 1, w1.w, w2.w, prim, 0);
 }
 
-__global__ void k_draw_begin(DrawCounters *ctr) {
-    ctr->total_pixels = 0; ctr->updated_pixels = 0;
-    ctr->n_records = 0; ctr->n_rows = 0; ctr->n_segs = 0; ctr->n_clip = 0; ctr->overflow = 0;
-    ctr->need_records = 0; ctr->need_rows = 0; ctr->need_segs = 0; ctr->need_clip = 0; ctr->_pad = 0;
-}
-
 __global__ void __launch_bounds__(256)
-k_geom_count(const __grid_constant__ DrawParams p, uint32_t *__restrict__ prim_nrec) {
+k_geom_count(const __grid_constant__ DrawParams p, uint32_t *__restrict__ prim_nrec, DrawCounters *ctr) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // first kernel of the draw: reset its counters
+        ctr->total_pixels = 0; ctr->updated_pixels = 0;
+        ctr->n_records = 0; ctr->n_rows = 0; ctr->n_segs = 0; ctr->n_clip = 0; ctr->overflow = 0;
+        ctr->need_records = 0; ctr->need_rows = 0; ctr->need_segs = 0; ctr->need_clip = 0; ctr->_pad = 0;
+    }
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.count) return;
     CountEmit e{0};
@@ -409,15 +408,7 @@ k_geom_count(const __grid_constant__ DrawParams p, uint32_t *__restrict__ prim_n
     prim_nrec[i] = e.n;
 }
 
-__global__ void k_set_nrecords(DrawCounters *ctr, const uint32_t *__restrict__ prim_rec_off, uint32_t count,
-                               uint32_t cap_records) {
-    const uint32_t total = prim_rec_off[count];
-    ctr->n_records = total;
-    ctr->need_records = total;
-    if (total > cap_records) ctr->overflow |= 1u;
-}
-
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_geom_emit(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.count) return;
@@ -427,23 +418,16 @@ k_geom_emit(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBu
     else process_triangle(p, e, p.first + i);
 }
 
-__global__ void k_finish_geom(DrawCounters *ctr, uint32_t cap_clip) {
-    ctr->need_clip = ctr->n_clip;
-    if (ctr->n_clip > cap_clip) ctr->overflow |= 4u;
-}
-
 int launch_geometry(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {
     int launches = 0;
-    k_draw_begin<<<1, 1, 0, st>>>(wb.counters);
-    launches++;
     const uint32_t blocks = (p.count + 255) / 256;
-    k_geom_count<<<blocks, 256, 0, st>>>(p, wb.prim_nrec);
+    k_geom_count<<<blocks, 256, 0, st>>>(p, wb.prim_nrec, wb.counters);
     launches++;
-    launches += launch_exclusive_scan(wb.prim_nrec, wb.prim_rec_off, p.count, nullptr, wb.scan_tmp, st);
-    k_set_nrecords<<<1, 1, 0, st>>>(wb.counters, wb.prim_rec_off, p.count, wb.cap_records);
+    ScanSink sink{&wb.counters->n_records, &wb.counters->need_records, &wb.counters->overflow, wb.cap_records,
+                  OVF_RECORDS, nullptr, nullptr, 0};
+    launches += launch_exclusive_scan(wb.prim_nrec, wb.prim_rec_off, p.count, nullptr, wb.scan_tmp, sink, st);
     k_geom_emit<<<blocks, 256, 0, st>>>(p, wb);
-    k_finish_geom<<<1, 1, 0, st>>>(wb.counters, wb.cap_clip);
-    launches += 3;
+    launches++;
     return launches;
 }
 

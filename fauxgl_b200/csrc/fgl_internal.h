@@ -126,8 +126,17 @@ int launch_clear_depth(double *depth, size_t npix, double v, cudaStream_t st);
 // exclusive scan of in[0..n) into out[0..n], out[n] = total; n read from *n_dev if n_dev != nullptr
 // (bounded by n_max).  tmp needs >= scan_tmp_words(n_max) words.
 size_t scan_tmp_words(uint32_t n_max);
+// Where the scan publishes its total (all pointers device, any may be null): count/need = total,
+// *overflow |= bit when total > cap.  clip_*: the clip-pool counters are finalised on the way.
+struct ScanSink {
+    unsigned int *count, *need, *overflow;
+    unsigned int cap, bit;
+    const unsigned int *clip_n;
+    unsigned int *clip_need;
+    unsigned int clip_cap;
+};
 int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n_max, const unsigned int *n_dev,
-                          uint32_t *tmp, cudaStream_t st);
+                          uint32_t *tmp, const ScanSink &sink, cudaStream_t st);
 // stable LSD radix sort of (key,val) pairs on `bits` key bits; returns launches, *sorted_buf = buffer index
 int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsigned int *n_dev, uint32_t n_max,
                       int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st);

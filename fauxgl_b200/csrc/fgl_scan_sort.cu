@@ -18,7 +18,7 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr int RADIX_BINS_HOST = 256;
-constexpr int RADIX_GRID = 148 * 2;
+constexpr int RADIX_GRID = 148;
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_reduce(const uint32_t *__restrict__ in, uint32_t n_max, const unsigned int *__restrict__ n_dev,
@@ -42,7 +42,7 @@ k_scan_reduce(const uint32_t *__restrict__ in, uint32_t n_max, const unsigned in
 // One block: exclusive scan of the block sums in place; total -> out[n].
 __global__ void __launch_bounds__(1024)
 k_scan_spine(uint32_t *__restrict__ tmp, uint32_t nblocks, uint32_t *__restrict__ out, uint32_t n_max,
-             const unsigned int *__restrict__ n_dev) {
+             const unsigned int *__restrict__ n_dev, const ScanSink sink) {
     __shared__ uint32_t sm[1024 / 32 + 1];
     uint32_t carry = 0;
     for (uint32_t base = 0; base < nblocks; base += 1024) {
@@ -53,7 +53,17 @@ k_scan_spine(uint32_t *__restrict__ tmp, uint32_t nblocks, uint32_t *__restrict_
         if (i < nblocks) tmp[i] = carry + ex;
         carry += total;
     }
-    if (threadIdx.x == 0) out[n_dev ? min(*n_dev, n_max) : n_max] = carry;
+    if (threadIdx.x == 0) {
+        out[n_dev ? min(*n_dev, n_max) : n_max] = carry;
+        if (sink.count) *sink.count = carry;
+        if (sink.need) *sink.need = carry;
+        if (sink.overflow && carry > sink.cap) *sink.overflow |= sink.bit;
+        if (sink.clip_n) {
+            const unsigned int nc = *sink.clip_n;
+            *sink.clip_need = nc;
+            if (nc > sink.clip_cap) *sink.overflow |= OVF_CLIP;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
@@ -88,11 +98,11 @@ size_t scan_tmp_words(uint32_t n_max) {
 
 // out[0..n) = exclusive scan, out[n] = total (also for n == 0).
 int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n_max, const unsigned int *n_dev,
-                          uint32_t *tmp, cudaStream_t st) {
+                          uint32_t *tmp, const ScanSink &sink, cudaStream_t st) {
     uint32_t nblocks = (n_max + SCAN_TILE - 1) / SCAN_TILE;
     if (nblocks == 0) nblocks = 1;
     k_scan_reduce<<<nblocks, SCAN_THREADS, 0, st>>>(in, n_max, n_dev, tmp);
-    k_scan_spine<<<1, 1024, 0, st>>>(tmp, nblocks, out, n_max, n_dev);
+    k_scan_spine<<<1, 1024, 0, st>>>(tmp, nblocks, out, n_max, n_dev, sink);
     k_scan_down<<<nblocks, SCAN_THREADS, 0, st>>>(in, out, n_max, n_dev, tmp);
     return 3;
 }
@@ -182,21 +192,28 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
 
 
 // hist[256][G] -> exclusive scan in (digit-major, block-minor) order == global base of
-// each (digit, block) bucket.  Single block; each thread first sums a contiguous slice.
+// each (digit, block) bucket.  One CTA: the whole histogram (148 KB) is staged in shared
+// memory with coalesced loads, each thread scans a contiguous slice there (stride 37 words:
+// conflict-free), one block scan joins the slices, and the result streams back coalesced.
 __global__ void __launch_bounds__(1024)
 k_radix_scan(uint32_t *__restrict__ hist, uint32_t n) {
+    extern __shared__ uint32_t s_hist[];
     __shared__ uint32_t sm[1024 / 32 + 1];
+    for (uint32_t i = threadIdx.x; i < n; i += 1024) s_hist[i] = hist[i];
+    __syncthreads();
     const uint32_t per = (n + 1023) / 1024;
     const uint32_t beg = min(threadIdx.x * per, n), end = min(beg + per, n);
     uint32_t sum = 0;
-    for (uint32_t i = beg; i < end; i++) sum += hist[i];
+    for (uint32_t i = beg; i < end; i++) sum += s_hist[i];
     uint32_t total;
     uint32_t run = block_excl_scan<1024>(sum, sm, &total);
     for (uint32_t i = beg; i < end; i++) {
-        const uint32_t v = hist[i];
-        hist[i] = run;
+        const uint32_t v = s_hist[i];
+        s_hist[i] = run;
         run += v;
     }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += 1024) hist[i] = s_hist[i];
 }
 
 // Stable LSD radix sort of (key, val) on `bits` key bits, 8 bits per pass.
@@ -204,9 +221,15 @@ int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsi
                       int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st) {
     int launches = 0, cur = 0;
     const int G = RADIX_GRID;
+    const size_t scan_smem = sizeof(uint32_t) * RADIX_BINS * G;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_radix_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
+        configured = true;
+    }
     for (int shift = 0; shift < bits; shift += 8) {
         k_radix_hist<<<G, RADIX_THREADS, 0, st>>>(key[cur], n_dev, n_max, shift, tmp);
-        k_radix_scan<<<1, 1024, 0, st>>>(tmp, RADIX_BINS * G);
+        k_radix_scan<<<1, 1024, scan_smem, st>>>(tmp, RADIX_BINS * G);
         k_radix_scatter<<<G, RADIX_THREADS, 0, st>>>(key[cur], val[cur], key[cur ^ 1], val[cur ^ 1], n_dev, n_max, shift,
                                                      tmp);
         cur ^= 1;

@@ -16,13 +16,23 @@
 
 namespace fgl {
 
+constexpr int ST = 256;  // threads per CTA == (record, scanline) items per CTA
+
+// The fields of Rec the row walker needs.
+struct RowSetup {
+    double s0x, s0y, s1x, s1y, s2x, s2y;
+    double w00, w01, w02, ra, ra12, ra20, ra01;
+    int32_t x0, x1, y0;
+};
+
 template <bool EMIT>
-__device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const Rec &r, uint32_t rec_id, int y,
-                                             Seg *__restrict__ segs, uint32_t *__restrict__ keys, uint32_t base,
-                                             uint32_t cap, unsigned long long *covered) {
-    const double a01 = r.s[4] - r.s[1], b01 = r.s[0] - r.s[3];  // context.go:167-172
-    const double a12 = r.s[7] - r.s[4], b12 = r.s[3] - r.s[6];
-    const double a20 = r.s[1] - r.s[7], b20 = r.s[6] - r.s[0];
+__device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const RowSetup &r, uint32_t rec_id, int y,
+                                             Seg *__restrict__ segs, uint32_t *__restrict__ keys,
+                                             uint32_t *__restrict__ vals, uint32_t base, uint32_t cap,
+                                             unsigned long long *covered) {
+    const double a01 = r.s1y - r.s0y, b01 = r.s0x - r.s1x;  // context.go:167-172
+    const double a12 = r.s2y - r.s1y, b12 = r.s1x - r.s2x;
+    const double a20 = r.s0y - r.s2y, b20 = r.s2x - r.s0x;
     double w00 = r.w00, w01 = r.w01, w02 = r.w02;
     for (int yy = r.y0; yy < y; yy++) { w00 += b12; w01 += b20; w02 += b01; }  // context.go:275-277
     // skip-ahead, context.go:185-205
@@ -44,6 +54,17 @@ __device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const Rec &r, 
     bool was_inside = false;
     const uint32_t key_row = (uint32_t)(y / TILE_H) * (uint32_t)p.tiles_x;
     const uint8_t yt = (uint8_t)(y % TILE_H);
+    auto flush = [&]() {
+        if (EMIT && base + nseg < cap) {
+            Seg s;
+            s.w0 = sw0; s.w1 = sw1; s.w2 = sw2; s.rec = rec_id; s.x = (uint16_t)sx; s.yt = yt; s.cnt = (uint8_t)cnt;
+            segs[base + nseg] = s;
+            keys[base + nseg] = key_row + (uint32_t)col;
+            vals[base + nseg] = base + nseg;
+        }
+        *covered += cnt;
+        nseg++;
+    };
     for (; x <= xend; x++) {
         const double b0 = w0 * r.ra, b1 = w1 * r.ra, b2 = w2 * r.ra;  // context.go:208-210
         if (b0 < 0 || b1 < 0 || b2 < 0) {
@@ -52,60 +73,79 @@ __device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const Rec &r, 
             was_inside = true;
             const int c = (int)x / TILE_W;
             if (cnt == 0 || c != col) {
-                if (cnt > 0) {
-                    if (EMIT && base + nseg < cap) {
-                        Seg s; s.w0 = sw0; s.w1 = sw1; s.w2 = sw2; s.rec = rec_id; s.x = (uint16_t)sx; s.yt = yt; s.cnt = (uint8_t)cnt;
-                        segs[base + nseg] = s;
-                        keys[base + nseg] = key_row + (uint32_t)col;
-                    }
-                    *covered += cnt;
-                    nseg++;
-                }
+                if (cnt > 0) flush();
                 col = c; sx = (int)x; sw0 = w0; sw1 = w1; sw2 = w2; cnt = 0;
             }
             cnt++;
         }
         w0 += a12; w1 += a20; w2 += a01;  // context.go:211-213
     }
-    if (cnt > 0) {
-        if (EMIT && base + nseg < cap) {
-            Seg s; s.w0 = sw0; s.w1 = sw1; s.w2 = sw2; s.rec = rec_id; s.x = (uint16_t)sx; s.yt = yt; s.cnt = (uint8_t)cnt;
-            segs[base + nseg] = s;
-            keys[base + nseg] = key_row + (uint32_t)col;
-        }
-        *covered += cnt;
-        nseg++;
-    }
+    if (cnt > 0) flush();
     return nseg;
 }
 
-// item i -> (record, scanline): largest r with rec_row_off[r] <= i
-__device__ __forceinline__ uint32_t find_rec(const uint32_t *__restrict__ off, uint32_t n, uint32_t i) {
-    uint32_t lo = 0, hi = n;
+// Largest r in [0,n) with off[r] <= i, found by one warp with a 32-ary search (5 rounds for 2^24).
+__device__ __forceinline__ uint32_t warp_find(const uint32_t *__restrict__ off, uint32_t n, uint32_t i) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t lo = 0, hi = n;  // invariant: off[lo] <= i < off[hi]
     while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (off[mid] <= i) lo = mid; else hi = mid;
+        const uint32_t step = (hi - lo + 31) / 32;
+        const uint32_t idx = lo + (lane + 1) * step;
+        const bool le = idx < hi && off[idx] <= i;
+        const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, le));  // monotone: the first cnt lanes are true
+        const uint32_t nlo = lo + cnt * step;
+        hi = min(hi, nlo + step);
+        lo = nlo;
     }
     return lo;
 }
 
 template <bool EMIT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(ST)
 k_spans(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
     const DrawCounters *ctr = wb.counters;
     if (ctr->overflow) return;
     const uint32_t nrec = min(ctr->n_records, wb.cap_records);
     const uint32_t nrows = min(ctr->n_rows, wb.cap_rows);
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i0 = blockIdx.x * ST;
+    if (i0 >= nrows) return;
+    // The ST items of this CTA belong to at most ST consecutive records (every record has >= 1
+    // scanline): find the first with one warp, stage that window of the offset array in shared
+    // memory and let every thread finish its search there.
+    __shared__ uint32_t s_first;
+    __shared__ uint32_t s_off[ST + 1];
+    if (threadIdx.x < 32) {
+        const uint32_t r0 = warp_find(wb.rec_row_off, nrec, i0);
+        if (threadIdx.x == 0) s_first = r0;
+    }
+    __syncthreads();
+    const uint32_t r0 = s_first;
+    for (uint32_t k = threadIdx.x; k <= ST; k += ST) {
+        const uint32_t r = r0 + k;
+        s_off[k] = r <= nrec ? wb.rec_row_off[r] : 0xffffffffu;
+    }
+    __syncthreads();
+    const uint32_t i = i0 + threadIdx.x;
     unsigned long long covered = 0;
     if (i < nrows) {
-        const uint32_t rid = find_rec(wb.rec_row_off, nrec, i);
-        const Rec r = wb.recs[rid];
-        const int y = max(r.y0, 0) + (int)(i - wb.rec_row_off[rid]);
+        uint32_t lo = 0, hi = ST;  // s_off[lo] <= i < s_off[hi]  (s_off[ST] >= i0 + ST > i)
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_off[mid] <= i) lo = mid; else hi = mid;
+        }
+        const uint32_t rid = r0 + lo;
+        const Rec *rp = wb.recs + rid;
+        RowSetup r;
+        r.s0x = rp->s[0]; r.s0y = rp->s[1]; r.s1x = rp->s[3]; r.s1y = rp->s[4]; r.s2x = rp->s[6]; r.s2y = rp->s[7];
+        r.w00 = rp->w00; r.w01 = rp->w01; r.w02 = rp->w02;
+        r.ra = rp->ra; r.ra12 = rp->ra12; r.ra20 = rp->ra20; r.ra01 = rp->ra01;
+        r.x0 = rp->x0; r.x1 = rp->x1; r.y0 = rp->y0;
+        const int y = max(r.y0, 0) + (int)(i - s_off[lo]);
         if (EMIT) {
-            if (wb.row_nseg[i]) walk_row<true>(p, r, rid, y, wb.segs, wb.seg_key[0], wb.row_seg_off[i], wb.cap_segs, &covered);
+            if (wb.row_nseg[i])
+                walk_row<true>(p, r, rid, y, wb.segs, wb.seg_key[0], wb.seg_val[0], wb.row_seg_off[i], wb.cap_segs, &covered);
         } else {
-            wb.row_nseg[i] = walk_row<false>(p, r, rid, y, nullptr, nullptr, 0, 0, &covered);
+            wb.row_nseg[i] = walk_row<false>(p, r, rid, y, nullptr, nullptr, nullptr, 0, 0, &covered);
         }
     }
     if (!EMIT) {  // TotalPixels, context.go:229: every covered in-range pixel, before any depth test
@@ -115,27 +155,6 @@ k_spans(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     }
 }
 
-__global__ void k_set_nrows(DrawCounters *ctr, const uint32_t *__restrict__ rec_row_off, uint32_t cap_records,
-                            uint32_t cap_rows) {
-    const uint32_t nrec = min(ctr->n_records, cap_records);
-    const uint32_t total = rec_row_off[nrec];
-    ctr->n_rows = total;
-    ctr->need_rows = total;
-    if (total > cap_rows) ctr->overflow |= OVF_ROWS;
-}
-__global__ void k_set_nsegs(DrawCounters *ctr, const uint32_t *__restrict__ row_seg_off, uint32_t cap_rows,
-                            uint32_t cap_segs) {
-    if (ctr->overflow) return;
-    const uint32_t nrows = min(ctr->n_rows, cap_rows);
-    const uint32_t total = row_seg_off[nrows];
-    ctr->n_segs = total;
-    ctr->need_segs = total;
-    if (total > cap_segs) ctr->overflow |= OVF_SEGS;
-}
-__global__ void k_seg_iota(uint32_t *__restrict__ vals, const DrawCounters *__restrict__ ctr, uint32_t cap_segs) {
-    const uint32_t n = min(ctr->n_segs, cap_segs);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) vals[i] = i;
-}
 __global__ void k_tile_ranges(const uint32_t *__restrict__ keys, const unsigned int *__restrict__ n_dev, uint32_t n_max,
                               uint32_t *__restrict__ tile_start, uint32_t *__restrict__ tile_end) {
     const uint32_t n = min(*n_dev, n_max);
@@ -148,27 +167,24 @@ __global__ void k_tile_ranges(const uint32_t *__restrict__ keys, const unsigned 
 
 int launch_spans(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st) {
     int launches = 0;
-    // scanlines per record -> item offsets
-    launches += launch_exclusive_scan(wb.rec_rows, wb.rec_row_off, wb.cap_records, &wb.counters->n_records,
-                                      wb.scan_tmp, st);
-    k_set_nrows<<<1, 1, 0, st>>>(wb.counters, wb.rec_row_off, wb.cap_records, wb.cap_rows);
-    const uint32_t blocks = (wb.cap_rows + 255) / 256;
-    k_spans<false><<<blocks ? blocks : 1, 256, 0, st>>>(p, wb);
-    launches += 2;
-    launches += launch_exclusive_scan(wb.row_nseg, wb.row_seg_off, wb.cap_rows, &wb.counters->n_rows, wb.scan_tmp, st);
-    k_set_nsegs<<<1, 1, 0, st>>>(wb.counters, wb.row_seg_off, wb.cap_rows, wb.cap_segs);
-    k_spans<true><<<blocks ? blocks : 1, 256, 0, st>>>(p, wb);
-    k_seg_iota<<<148 * 4, 256, 0, st>>>(wb.seg_val[0], wb.counters, wb.cap_segs);
-    launches += 3;
+    DrawCounters *c = wb.counters;
+    // scanlines per record -> item offsets (this scan also finalises the clip-pool counters)
+    ScanSink rows{&c->n_rows, &c->need_rows, &c->overflow, wb.cap_rows, OVF_ROWS, &c->n_clip, &c->need_clip, wb.cap_clip};
+    launches += launch_exclusive_scan(wb.rec_rows, wb.rec_row_off, wb.cap_records, &c->n_records, wb.scan_tmp, rows, st);
+    const uint32_t blocks = (wb.cap_rows + ST - 1) / ST;
+    k_spans<false><<<blocks ? blocks : 1, ST, 0, st>>>(p, wb);
+    launches++;
+    ScanSink segs{&c->n_segs, &c->need_segs, &c->overflow, wb.cap_segs, OVF_SEGS, nullptr, nullptr, 0};
+    launches += launch_exclusive_scan(wb.row_nseg, wb.row_seg_off, wb.cap_rows, &c->n_rows, wb.scan_tmp, segs, st);
+    k_spans<true><<<blocks ? blocks : 1, ST, 0, st>>>(p, wb);
+    launches++;
     // stable sort of the segment indices by tile id
     int bits = 1;
     while ((1u << bits) < wb.ntiles) bits++;
-    launches += launch_sort_pairs(wb.seg_key, wb.seg_val, &wb.counters->n_segs, wb.cap_segs, bits, wb.scan_tmp,
-                                  sorted_buf, st);
+    launches += launch_sort_pairs(wb.seg_key, wb.seg_val, &c->n_segs, wb.cap_segs, bits, wb.scan_tmp, sorted_buf, st);
     cudaMemsetAsync(wb.tile_start, 0, sizeof(uint32_t) * wb.ntiles, st);
     cudaMemsetAsync(wb.tile_end, 0, sizeof(uint32_t) * wb.ntiles, st);
-    k_tile_ranges<<<148 * 4, 256, 0, st>>>(wb.seg_key[*sorted_buf], &wb.counters->n_segs, wb.cap_segs, wb.tile_start,
-                                          wb.tile_end);
+    k_tile_ranges<<<148 * 4, 256, 0, st>>>(wb.seg_key[*sorted_buf], &c->n_segs, wb.cap_segs, wb.tile_start, wb.tile_end);
     launches++;
     return launches;
 }
