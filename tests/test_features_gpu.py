@@ -1,0 +1,255 @@
+"""GPU tests of the rest of the C ABI: the benchmark-size mesh, SSAA resolve, mesh
+transform/update on the device, async draws, the composite kernels, a sort-last
+composite on one GPU, and the error paths.  Every check is against the CPU
+oracle (bit-exact) or a size-independent property."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import scenes
+from parity import compare_buffers, run_both
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Context(gpu_capi):
+    from fauxgl_b200.context import Context
+    return Context
+
+
+@pytest.fixture(scope="module")
+def m871k():
+    from fauxgl_b200 import synth
+    return synth.bumpy_surface()
+
+
+def test_benchmark_mesh_1080p_bit_exact(m871k, oracle_lib, Context):
+    """BASELINE config: 871 306 triangles, Phong, 1920x1080 -- full-size parity."""
+    stats = run_both(scenes.dragon_scene(m871k, 1920, 1080), oracle_lib, Context)
+    print(stats)
+    assert stats["depth_mismatch"] == 0 and stats["color_mismatch"] == 0
+    assert stats["gpu_info"] == stats["oracle_info"]
+    assert stats["gpu_info"][0][0] > 500000
+
+
+def test_benchmark_mesh_ssaa_8k_and_resolve_bit_exact(m871k, oracle_lib, Context):
+    """Same mesh at 7680x4320 (16x SSAA) + the 4x resolve."""
+    sc = scenes.dragon_scene(m871k, 7680, 4320)
+    octx = oracle_lib.OracleContext(sc.width, sc.height)
+    oinfo = sc.run(octx)
+    gctx = Context(sc.width, sc.height)
+    ginfo = sc.run(gctx)
+    stats = compare_buffers(octx.ColorBuffer, octx.DepthBuffer, gctx.Image(), gctx.DepthBuffer)
+    print(stats, oinfo, ginfo)
+    assert stats["depth_mismatch"] == 0 and stats["color_mismatch"] == 0 and ginfo == oinfo
+    got = gctx.Resolve(4)
+    want = octx.Resolve(4)
+    assert got.shape == (1080, 1920, 4) and (got == want).all()
+    gctx.Close()
+
+
+@pytest.mark.parametrize("factor,w,h", [(2, 130, 70), (4, 256, 128), (3, 99, 60), (8, 64, 64), (1, 33, 17)])
+def test_resolve_matches_oracle(factor, w, h, oracle_lib, Context):
+    rng = np.random.RandomState(factor)
+    img = rng.randint(0, 256, (h * factor, w * factor, 4)).astype(np.uint8)
+    img[: h * factor // 2, :, 3] = 255           # half opaque, half translucent (premultiply path)
+    ctx = Context(w * factor, h * factor)
+    ctx.UploadColorBuffer(img)
+    got = ctx.Resolve(factor)
+    want = oracle_lib.resolve(img, w, h)
+    assert (got == want).all()
+    ctx.Close()
+
+
+def test_mesh_transform_on_device_matches_host(Context):
+    """fgl_mesh_transform == Mesh.Transform (mesh.go:167-175), bit for bit."""
+    from fauxgl_b200 import Rotate, Radians, V
+    mesh = scenes.load_fixture("bowser_mesh")
+    mesh.BiUnitCube()
+    ctx = Context(64, 64)
+    dm = ctx.device_mesh(mesh)
+    m = Rotate(V(0, 0, 1), Radians(5)).Translate(V(0.1, -0.2, 0.3))
+    for _ in range(3):
+        dm.Transform(m)
+        mesh.Transform(m)
+    pos, nrm, _lp, _ln = dm.read()
+    assert (pos.view(np.uint64) == mesh.position.view(np.uint64)).all()
+    assert (nrm.view(np.uint64) == mesh.normal.view(np.uint64)).all()
+    ctx.Close()
+
+
+def test_animation_frames_device_transform_vs_host_transform(oracle_lib, Context):
+    """examples/animate.go:43-67: rotate 5 degrees per frame.  Device-side transform + draw equals
+    host-side transform + re-upload + draw, frame by frame."""
+    from fauxgl_b200 import Gray, HexColor, LookAt, NewPhongShader, Radians, Rotate, V
+    mesh = scenes.load_fixture("bowser_mesh")
+    mesh.BiUnitCube()
+    eye, up = V(4, 4, 2), V(0, 0, 1)
+    matrix = LookAt(eye, V(0, 0, 0), up).Perspective(30, 1.0, 1, 10)
+    shader = NewPhongShader(matrix, V(0.25, 0.5, 1).Normalize(), eye)
+    shader.ObjectColor = HexColor("#FEB41C")
+    shader.DiffuseColor, shader.SpecularColor, shader.SpecularPower = Gray(0.9), Gray(0.25), 100
+    a, b = Context(400, 400), Context(400, 400)
+    o = oracle_lib.OracleContext(400, 400)
+    a.Shader = b.Shader = o.Shader = shader
+    dm = a.device_mesh(mesh.Copy())
+    rot = Rotate(up, Radians(5))
+    for frame in range(3):
+        for c in (a, b, o):
+            c.ClearDepthBuffer()
+            c.ClearColorBufferWith(HexColor("#24221F"))
+        ia = a.DrawMesh(dm)
+        ib = b.DrawMesh(mesh)          # host mesh: re-uploaded in place after Transform (generation bump)
+        io = o.DrawMesh(mesh)
+        assert tuple(ia) == tuple(ib) == io
+        assert (a.Image() == o.ColorBuffer).all() and (b.Image() == o.ColorBuffer).all()
+        dm.Transform(rot)
+        mesh.Transform(rot)
+    a.Close(); b.Close()
+
+
+def test_async_draws_accumulate_info(oracle_lib, Context):
+    sc = scenes.shapes_multipass()
+    octx = oracle_lib.OracleContext(sc.width, sc.height)
+    oinfo = sc.run(octx)
+    gctx = Context(sc.width, sc.height)
+    sc.run(gctx)                       # sizes the work buffers
+    gctx.ClearDepthBuffer()
+    gctx.Wireframe, gctx.DepthBias = False, 0.0
+
+    class AsyncCtx:                    # same scene script, async draw calls
+        def __init__(self, c):
+            self.__dict__["c"] = c
+
+        def __getattr__(self, k):
+            return getattr(self.c, k)
+
+        def __setattr__(self, k, v):
+            setattr(self.c, k, v)
+
+        def DrawMesh(self, mesh):
+            self.c.DrawMeshAsync(mesh)
+            return (0, 0)
+    sc.run(AsyncCtx(gctx))
+    info = gctx.Sync()
+    assert tuple(info) == (sum(i[0] for i in oinfo), sum(i[1] for i in oinfo))
+    assert (gctx.Image() == octx.ColorBuffer).all()
+    gctx.Close()
+
+
+def test_work_buffers_regrow_transparently(oracle_lib, Context):
+    """A tiny first draw sizes small buffers; a big-triangle draw must regrow them (sync path)."""
+    from fauxgl_b200 import NewSolidColorShader, NewTriangleMesh, Orthographic, Color
+    ctx = Context(2048, 2048)
+    octx = oracle_lib.OracleContext(2048, 2048)
+    tri = np.array([[[-1, -1, 0], [1, -1, 0], [0, 1, 0]]] * 40, dtype=np.float64)
+    tri[:, :, 2] = np.linspace(-0.5, 0.5, 40)[:, None]
+    mesh = NewTriangleMesh(tri)
+    for c in (ctx, octx):
+        c.Shader = NewSolidColorShader(Orthographic(-1, 1, -1, 1, -1, 1), Color(0.2, 0.4, 0.6, 1))
+        c.Cull = 1
+    gi, oi = ctx.DrawTriangles(mesh), octx.DrawTriangles(mesh)
+    assert tuple(gi) == oi and ctx.DrawStats().retries >= 1
+    assert (ctx.DepthBuffer.view(np.uint64) == octx.DepthBuffer.view(np.uint64)).all()
+    ctx.Close()
+
+
+def test_composite_kernels_match_oracle_keys(oracle_lib, Context):
+    import torch
+    sc = scenes.hello()
+    ctx = Context(sc.width, sc.height)
+    sc.run(ctx)
+    keys = torch.empty(sc.width * sc.height, dtype=torch.int64, device="cuda")
+    ctx.CompositePack(keys.data_ptr())
+    ctx.Sync()
+    torch.cuda.synchronize()
+    color, depth = ctx.Image(), ctx.DepthBuffer
+    got = keys.cpu().numpy().view(np.uint64).reshape(sc.height, sc.width)
+    rng = np.random.RandomState(0)
+    for _ in range(2000):
+        y, x = rng.randint(sc.height), rng.randint(sc.width)
+        assert int(got[y, x]) == oracle_lib.pack_key(float(depth[y, x]), color[y, x].tolist())
+    # unpack(pack(.)) keeps colour exactly and depth to 32 bits
+    ctx.CompositeUnpack(keys.data_ptr())
+    assert (ctx.Image() == color).all()
+    d2 = ctx.DepthBuffer
+    cov = depth < 1e300
+    assert (d2[~cov] == depth[~cov]).all() and np.abs(d2[cov] - depth[cov]).max() < 2.4e-10
+    ctx.Close()
+
+
+@pytest.mark.parametrize("parts", [2, 4, 8])
+def test_sort_last_composite_on_one_gpu(parts, oracle_lib, Context):
+    """N triangle ranges -> N full-frame renders -> packed-key min == one render of the whole mesh
+    (up to depth ties / 32-bit depth quantisation; the mismatch count is reported)."""
+    import torch
+    from fauxgl_b200 import multigpu
+    mesh = scenes.bumpy_mesh(201, 201)
+    sc = scenes.dragon_scene(mesh, 1280, 720)
+    full = Context(sc.width, sc.height)
+    finfo = sc.run(full)
+    n = sc.width * sc.height
+    acc = torch.empty(n, dtype=torch.int64, device="cuda")
+    tmp = torch.empty(n, dtype=torch.int64, device="cuda")
+    total = 0
+    part = Context(sc.width, sc.height)
+    for r in range(parts):
+        first, count = multigpu.triangle_range(mesh.num_triangles, r, parts)
+
+        class RangeCtx:
+            def __init__(self, c):
+                self.__dict__["c"] = c
+
+            def __getattr__(self, k):
+                return getattr(self.c, k)
+
+            def __setattr__(self, k, v):
+                setattr(self.c, k, v)
+
+            def DrawMesh(self, m):
+                return self.c.DrawTriangles(m, first, count)
+        info = sc.run(RangeCtx(part))
+        total += info[0][0]
+        part.CompositePack((acc if r == 0 else tmp).data_ptr())
+        if r:
+            part.CompositeMin(acc.data_ptr(), tmp.data_ptr(), n)
+        part.Sync()
+    part.CompositeUnpack(acc.data_ptr())
+    assert total == finfo[0][0]                                   # TotalPixels adds up
+    a, b = part.Image(), full.Image()
+    mism = int((a != b).any(axis=-1).sum())
+    print("sort-last parts=%d colour mismatches: %d of %d" % (parts, mism, n))
+    assert mism <= 1e-4 * n
+    full.Close(); part.Close()
+
+
+def test_error_paths(gpu_capi, Context):
+    from fauxgl_b200 import context, NewTriangleMesh, Identity
+    with pytest.raises(context.FauxglError):
+        Context(0, 10)
+    with pytest.raises(context.FauxglError):
+        Context(16, 16, device=99)
+    ctx = Context(16, 16)
+    mesh = NewTriangleMesh(np.zeros((2, 3, 3)))
+    with pytest.raises(context.FauxglError):
+        ctx.DrawTriangles(mesh, 1, 5)                  # range outside the mesh
+    with pytest.raises(context.FauxglError):
+        ctx.Resolve(3)                                 # 16 % 3 != 0
+
+    class Custom:                                      # user-defined Shader: no device equivalent
+        def describe(self):
+            return {"kind": 7, "matrix": tuple(Identity())}
+    ctx.Shader = Custom()
+    with pytest.raises(context.FauxglError) as e:
+        ctx.DrawMesh(mesh)
+    assert e.value.status == -4
+    # the C ABI itself rejects an unknown shader kind too
+    st, sh = ctx._state(), context._Shader()
+    sh.kind = 42
+    info = context._Info()
+    dm = ctx.device_mesh(mesh)
+    rc = gpu_capi.fgl_draw_triangles(ctx._h, C.byref(st), C.byref(sh), dm.handle, 0, 2, C.byref(info))
+    assert rc == -4 and b"no CPU fallback" in gpu_capi.fgl_last_error(ctx._h)
+    ctx.Close()
