@@ -1,0 +1,402 @@
+// Package fauxgl: B200 back end for the render context.
+//
+// This file REPLACES context.go of github.com/fogleman/fauxgl.  Every other
+// file of the reference package (vector.go, matrix.go, color.go, vertex.go,
+// triangle.go, line.go, mesh.go, shader.go, texture.go, loaders, shapes ...)
+// stays as it is: they are host-side value types and mesh preparation, not the
+// hot path.  The exported surface below is the reference's, name for name
+// (context.go:11-58, 60, 83, 87, 119-145, 351-439); what changes is what runs
+// behind it: hand-written sm_100a CUDA kernels reached through the C ABI of
+// include/fauxgl_b200.h (see b200.go for the cgo binding and INTEGRATION.md).
+//
+// Differences a caller can observe, all documented in INTEGRATION.md:
+//   - ColorBuffer / DepthBuffer live on the device between draws.  Image(),
+//     DepthImage() and SyncBuffers() read them back into the exported fields;
+//     a program that writes those fields itself must call UploadBuffers().
+//   - A Shader (or Texture) that is not one of the built-ins has no device
+//     equivalent: the draw returns a zero RasterizeInfo and Err() reports it.
+//     There is no CPU fallback.
+//   - Meshes are cached on the device by *Mesh pointer.  Mesh methods that
+//     mutate (Transform, Add, SetColor, ...) are detected through a cheap
+//     fingerprint (length + bounding box + first/last vertex); code that pokes
+//     mesh.Triangles[i].V1.Color directly must call ctx.InvalidateMesh(mesh).
+//   - Primitives are drawn in index order (the reference's goroutine schedule
+//     is non-deterministic on depth ties, DepthBias, blending and
+//     UpdatedPixels; index order is one of its legal schedules).
+//
+// NOTE: the build image has no Go toolchain, so this file has been written to
+// compile against the reference package but has not been compiled; all logic
+// lives below the C ABI, which is tested through the ctypes mirror
+// (fauxgl_b200/context.py) that makes exactly these calls.
+package fauxgl
+
+import (
+	"errors"
+	"image"
+	"image/color"
+	"math"
+	"runtime"
+	"sync"
+)
+
+type Face int
+
+const (
+	_ Face = iota
+	FaceCW
+	FaceCCW
+)
+
+type Cull int
+
+const (
+	_ Cull = iota
+	CullNone
+	CullFront
+	CullBack
+)
+
+type RasterizeInfo struct {
+	TotalPixels   uint64
+	UpdatedPixels uint64
+}
+
+func (info RasterizeInfo) Add(other RasterizeInfo) RasterizeInfo {
+	return RasterizeInfo{
+		info.TotalPixels + other.TotalPixels,
+		info.UpdatedPixels + other.UpdatedPixels,
+	}
+}
+
+type Context struct {
+	Width       int
+	Height      int
+	ColorBuffer *image.NRGBA
+	DepthBuffer []float64
+	ClearColor  Color
+	Shader      Shader
+	ReadDepth   bool
+	WriteDepth  bool
+	WriteColor  bool
+	AlphaBlend  bool
+	Wireframe   bool
+	FrontFace   Face
+	Cull        Cull
+	LineWidth   float64
+	DepthBias   float64
+
+	// device side
+	mu       sync.Mutex
+	dev      *deviceContext            // b200.go
+	meshes   map[*Mesh]*deviceMesh     // device-resident copies
+	textures map[Texture]*deviceTexture
+	err      error // sticky: first error of any call
+	hostOK   bool  // exported buffers mirror the device
+}
+
+// NewContext allocates the buffers on the device (GPU 0 unless FAUXGL_DEVICE
+// selects another).  It panics only if no CUDA device exists, because the
+// reference's signature has no error return and there is no CPU fallback.
+func NewContext(width, height int) *Context {
+	dc := &Context{}
+	dc.Width = width
+	dc.Height = height
+	dc.ColorBuffer = image.NewNRGBA(image.Rect(0, 0, width, height))
+	dc.DepthBuffer = make([]float64, width*height)
+	dc.ClearColor = Transparent
+	dc.Shader = NewSolidColorShader(Identity(), Color{1, 0, 1, 1})
+	dc.ReadDepth = true
+	dc.WriteDepth = true
+	dc.WriteColor = true
+	dc.AlphaBlend = true
+	dc.Wireframe = false
+	dc.FrontFace = FaceCCW
+	dc.Cull = CullBack
+	dc.LineWidth = 2
+	dc.DepthBias = 0
+	dc.meshes = make(map[*Mesh]*deviceMesh)
+	dc.textures = make(map[Texture]*deviceTexture)
+	dev, err := newDeviceContext(width, height, deviceFromEnv())
+	if err != nil {
+		panic("fauxgl: " + err.Error())
+	}
+	dc.dev = dev
+	for i := range dc.DepthBuffer {
+		dc.DepthBuffer[i] = math.MaxFloat64
+	}
+	dc.hostOK = true
+	runtime.SetFinalizer(dc, (*Context).Close)
+	return dc
+}
+
+// Close releases the device resources.  Safe to call more than once.
+func (dc *Context) Close() {
+	dc.mu.Lock()
+	defer dc.mu.Unlock()
+	for _, m := range dc.meshes {
+		m.destroy()
+	}
+	for _, t := range dc.textures {
+		t.destroy()
+	}
+	dc.meshes, dc.textures = nil, nil
+	if dc.dev != nil {
+		dc.dev.destroy()
+		dc.dev = nil
+	}
+}
+
+// Err returns the first error any call on this context hit (unsupported
+// shader, CUDA failure ...).  The reference's draw calls have no error return.
+func (dc *Context) Err() error {
+	dc.mu.Lock()
+	defer dc.mu.Unlock()
+	return dc.err
+}
+
+func (dc *Context) fail(err error) {
+	if dc.err == nil && err != nil {
+		dc.err = err
+	}
+}
+
+// SyncBuffers reads the device buffers back into ColorBuffer and DepthBuffer.
+func (dc *Context) SyncBuffers() {
+	dc.mu.Lock()
+	defer dc.mu.Unlock()
+	dc.syncLocked()
+}
+
+func (dc *Context) syncLocked() {
+	if dc.hostOK || dc.dev == nil {
+		return
+	}
+	dc.fail(dc.dev.readColor(dc.ColorBuffer.Pix, dc.ColorBuffer.Stride))
+	dc.fail(dc.dev.readDepth(dc.DepthBuffer))
+	dc.hostOK = true
+}
+
+// UploadBuffers copies ColorBuffer and DepthBuffer to the device, for programs
+// that write the exported buffers themselves.
+func (dc *Context) UploadBuffers() {
+	dc.mu.Lock()
+	defer dc.mu.Unlock()
+	dc.fail(dc.dev.writeColor(dc.ColorBuffer.Pix, dc.ColorBuffer.Stride))
+	dc.fail(dc.dev.writeDepth(dc.DepthBuffer))
+	dc.hostOK = true
+}
+
+func (dc *Context) Image() image.Image {
+	dc.SyncBuffers()
+	return dc.ColorBuffer
+}
+
+func (dc *Context) DepthImage() image.Image {
+	dc.SyncBuffers()
+	lo := math.MaxFloat64
+	hi := -math.MaxFloat64
+	for _, d := range dc.DepthBuffer {
+		if d == math.MaxFloat64 {
+			continue
+		}
+		if d < lo {
+			lo = d
+		}
+		if d > hi {
+			hi = d
+		}
+	}
+	im := image.NewGray16(image.Rect(0, 0, dc.Width, dc.Height))
+	var i int
+	for y := 0; y < dc.Height; y++ {
+		for x := 0; x < dc.Width; x++ {
+			d := dc.DepthBuffer[i]
+			t := (d - lo) / (hi - lo)
+			if d == math.MaxFloat64 {
+				t = 1
+			}
+			im.SetGray16(x, y, color.Gray16{uint16(t * 0xffff)})
+			i++
+		}
+	}
+	return im
+}
+
+// Resolve is the device version of resize.Resize(w/factor, h/factor, Image(),
+// resize.Bilinear) that every example calls for supersampling: 16x fewer bytes
+// cross PCIe than resizing on the host.  The result is premultiplied RGBA, as
+// nfnt/resize returns for an *image.NRGBA input.
+func (dc *Context) Resolve(factor int) (*image.RGBA, error) {
+	dc.mu.Lock()
+	defer dc.mu.Unlock()
+	out := image.NewRGBA(image.Rect(0, 0, dc.Width/factor, dc.Height/factor))
+	err := dc.dev.resolve(factor, out.Pix)
+	dc.fail(err)
+	return out, err
+}
+
+func (dc *Context) ClearColorBufferWith(color Color) {
+	dc.mu.Lock()
+	defer dc.mu.Unlock()
+	c := color.NRGBA()
+	dc.fail(dc.dev.clearColor(c.R, c.G, c.B, c.A))
+	dc.hostOK = false
+}
+
+func (dc *Context) ClearColorBuffer() {
+	dc.ClearColorBufferWith(dc.ClearColor)
+}
+
+func (dc *Context) ClearDepthBufferWith(value float64) {
+	dc.mu.Lock()
+	defer dc.mu.Unlock()
+	dc.fail(dc.dev.clearDepth(value))
+	dc.hostOK = false
+}
+
+func (dc *Context) ClearDepthBuffer() {
+	dc.ClearDepthBufferWith(math.MaxFloat64)
+}
+
+// InvalidateMesh forces a re-upload of the mesh on its next draw.
+func (dc *Context) InvalidateMesh(mesh *Mesh) {
+	dc.mu.Lock()
+	defer dc.mu.Unlock()
+	if m, ok := dc.meshes[mesh]; ok {
+		m.stale = true
+	}
+}
+
+var errUnsupportedShader = errors.New(
+	"fauxgl: Shader has no device implementation (only *SolidColorShader, *TextureShader, *PhongShader); there is no CPU fallback")
+
+// describeShader resolves the Shader interface by type switch to the closed set
+// with device implementations.
+func (dc *Context) describeShader() (shaderDesc, error) {
+	var d shaderDesc
+	tex := func(t Texture) (*deviceTexture, error) {
+		if t == nil {
+			return nil, nil
+		}
+		if dt, ok := dc.textures[t]; ok {
+			return dt, nil
+		}
+		it, ok := t.(*ImageTexture)
+		if !ok {
+			return nil, errors.New("fauxgl: Texture has no device implementation (only *ImageTexture)")
+		}
+		dt, err := dc.dev.newTexture(it)
+		if err == nil {
+			dc.textures[t] = dt
+		}
+		return dt, err
+	}
+	var err error
+	switch s := dc.Shader.(type) {
+	case *SolidColorShader:
+		d.kind, d.matrix, d.color = shaderSolid, s.Matrix, s.Color
+	case *TextureShader:
+		d.kind, d.matrix = shaderTexture, s.Matrix
+		d.texture, err = tex(s.Texture)
+	case *PhongShader:
+		d.kind, d.matrix = shaderPhong, s.Matrix
+		d.light, d.camera = s.LightDirection, s.CameraPosition
+		d.object, d.ambient, d.diffuse, d.specular = s.ObjectColor, s.AmbientColor, s.DiffuseColor, s.SpecularColor
+		d.specularPower = s.SpecularPower
+		d.texture, err = tex(s.Texture)
+	default:
+		err = errUnsupportedShader
+	}
+	return d, err
+}
+
+func (dc *Context) state() stateDesc {
+	return stateDesc{dc.ReadDepth, dc.WriteDepth, dc.WriteColor, dc.AlphaBlend, dc.Wireframe,
+		int(dc.FrontFace), int(dc.Cull), dc.LineWidth, dc.DepthBias}
+}
+
+// DrawTriangles and DrawLines take the reference's slices.  When the slice is
+// exactly mesh.Triangles / mesh.Lines of a mesh drawn through DrawMesh the
+// cached device copy is used; a bare slice is uploaded as a temporary mesh.
+func (dc *Context) DrawTriangles(triangles []*Triangle) RasterizeInfo {
+	return dc.draw(&Mesh{Triangles: triangles}, true, false, true)
+}
+
+func (dc *Context) DrawLines(lines []*Line) RasterizeInfo {
+	return dc.draw(&Mesh{Lines: lines}, false, true, true)
+}
+
+func (dc *Context) DrawTriangle(t *Triangle) RasterizeInfo {
+	return dc.DrawTriangles([]*Triangle{t})
+}
+
+func (dc *Context) DrawLine(l *Line) RasterizeInfo {
+	return dc.DrawLines([]*Line{l})
+}
+
+func (dc *Context) DrawMesh(mesh *Mesh) RasterizeInfo {
+	return dc.draw(mesh, true, true, false)
+}
+
+func (dc *Context) draw(mesh *Mesh, tris, lines, temporary bool) RasterizeInfo {
+	dc.mu.Lock()
+	defer dc.mu.Unlock()
+	var result RasterizeInfo
+	if dc.dev == nil || (len(mesh.Triangles) == 0 && len(mesh.Lines) == 0) {
+		return result
+	}
+	sh, err := dc.describeShader()
+	if err != nil {
+		dc.fail(err)
+		return result
+	}
+	dm, err := dc.deviceMeshFor(mesh, temporary)
+	if err != nil {
+		dc.fail(err)
+		return result
+	}
+	if temporary {
+		defer dm.destroy()
+	}
+	st := dc.state()
+	if tris && len(mesh.Triangles) > 0 {
+		info, err := dc.dev.drawTriangles(st, sh, dm, 0, uint64(len(mesh.Triangles)))
+		dc.fail(err)
+		result = result.Add(info)
+	}
+	if lines && len(mesh.Lines) > 0 {
+		info, err := dc.dev.drawLines(st, sh, dm, 0, uint64(len(mesh.Lines)))
+		dc.fail(err)
+		result = result.Add(info)
+	}
+	dc.hostOK = false
+	return result
+}
+
+// deviceMeshFor returns the device copy of mesh, (re)uploading when the mesh is
+// new, was invalidated, or its fingerprint changed.
+func (dc *Context) deviceMeshFor(mesh *Mesh, temporary bool) (*deviceMesh, error) {
+	if temporary {
+		return dc.dev.newMesh(mesh)
+	}
+	fp := fingerprint(mesh)
+	if m, ok := dc.meshes[mesh]; ok {
+		if !m.stale && m.fp == fp {
+			return m, nil
+		}
+		if m.sameShape(mesh) {
+			err := m.update(dc.dev, mesh)
+			m.fp, m.stale = fp, false
+			return m, err
+		}
+		m.destroy()
+		delete(dc.meshes, mesh)
+	}
+	m, err := dc.dev.newMesh(mesh)
+	if err != nil {
+		return nil, err
+	}
+	m.fp = fp
+	dc.meshes[mesh] = m
+	return m, nil
+}
