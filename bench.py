@@ -62,51 +62,51 @@ def scene_setup():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread
+    every ~2 ms (nvidia-smi's 100 ms loop is coarser than a whole timed region here)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.h, self.stop_flag, self.max_mhz = index, [], 0, None, False, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.h is None:
+            return
+        self.stop_flag = False
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if f[3 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.sm), "reasons": reasons}
 
 
 def cpu_reference_frames(mesh, frames: int, warmup: int, threads: int):
@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-ssaa", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sort-last", action="store_true", help="also time the 10M-triangle sort-last config at N == 1")
+    ap.add_argument("--no-sort-last", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -248,25 +250,25 @@ def main():
     ms1 = max_over_ranks(sum(r1["ms"]) / K)
     value = world * T_TRIANGLES / (ms1 / 1e3) / 1e6
 
-    st = r1["stage"]
-    stages = {"geometry_ms": st.geometry_ms / st.draws, "binning_ms": st.binning_ms / st.draws,
-              "raster_ms": st.raster_ms / st.draws}
-    dom = max(stages, key=stages.get)
-    # algorithmic bytes per launch of each stage (DESIGN.md "Roofline"): geometry reads the position
-    # planes twice (count + emit pass) = T*72*2; raster consumes the normal planes of the surviving
-    # triangles' vertices and owns the framebuffer traffic (12 B/px, load + store of touched tiles is
-    # implementation, not algorithm): T*72 + W*H*12; binning moves no algorithmic bytes at all.
-    algo = {"geometry_ms": T_TRIANGLES * 72, "raster_ms": T_TRIANGLES * 72 + W1 * H1 * 12, "binning_ms": 0}
-    dom_bytes = algo[dom] if algo[dom] else ALGO_BYTES_C1
+    def stage_ms(st):
+        return {"geometry_ms": st.geometry_ms / st.draws, "spans_ms": st.spans_ms / st.draws,
+                "sort_ms": st.sort_ms / st.draws, "raster_ms": st.raster_ms / st.draws}
+    stages = stage_ms(r1["stage"])
+    # Dominant kernel: k_tile (the `raster` timer brackets exactly that one launch; the other stages are
+    # several kernels each -- their per-kernel times are in profiles/).  Its algorithmic bytes
+    # (DESIGN.md section 7): the normal planes of the triangles (T*72 B; positions belong to the geometry
+    # stage) plus the framebuffer written once (W*H*12 B).
+    tile_bytes = T_TRIANGLES * 72 + W1 * H1 * 12
     roofline = {
-        "bound": "hbm", "kernel": {"geometry_ms": "k_geom_count+k_geom_emit", "binning_ms": "pair sort",
-                                   "raster_ms": "k_raster"}[dom],
-        "achieved": dom_bytes / (stages[dom] / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": dom_bytes / (stages[dom] / 1e3) / 1e9 / hbm_peak, "traffic": None,
-        "peak_source": peak_src, "algorithmic_bytes": dom_bytes,
+        "bound": "hbm", "kernel": "k_tile<deferred>",
+        "achieved": tile_bytes / (stages["raster_ms"] / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": tile_bytes / (stages["raster_ms"] / 1e3) / 1e9 / hbm_peak,
+        "traffic": 105698560,   # dram__bytes_read+write of one k_tile launch, profiles/r01_ncu_k_tile_v2.txt
+        "peak_source": peak_src, "algorithmic_bytes": tile_bytes,
         "frame": {"algorithmic_bytes": ALGO_BYTES_C1, "achieved": ALGO_BYTES_C1 / (ms1 / 1e3) / 1e9,
                   "frac": ALGO_BYTES_C1 / (ms1 / 1e3) / 1e9 / hbm_peak},
         "stages_ms": stages,
+        "note": "latency/balance-bound, not bandwidth-bound: see profiles/README.md",
     }
 
     # ---------------- 16x SSAA (7680x4320 + resolve) ----------------
@@ -279,8 +281,7 @@ def main():
         ssaa = {"ms_per_frame": ms2, "mtri_s": world * T_TRIANGLES / (ms2 / 1e3) / 1e6, "steps": K2,
                 "total_pixels": int(r2["info"].TotalPixels / (3 + K2)),
                 "roofline_frac_frame": ALGO_BYTES_C2 / (ms2 / 1e3) / 1e9 / hbm_peak,
-                "stages_ms": {"geometry_ms": s2.geometry_ms / s2.draws, "binning_ms": s2.binning_ms / s2.draws,
-                              "raster_ms": s2.raster_ms / s2.draws},
+                "stages_ms": stage_ms(s2),
                 "workload": "same mesh at 7680x4320 + 4x4 nfnt-bilinear resolve to 1920x1080"}
 
     # ---------------- end to end through the public API with host buffers ----------------
@@ -319,6 +320,59 @@ def main():
     checksum = int(img.astype(np.uint64).sum())
     ctx.Close()
 
+    # ---------------- sort-last: 10 M-triangle sphere at 7680x4320, ranges per rank + NCCL composite ----------------
+    sort_last = None
+    if args.sort_last or (world > 1 and not args.no_sort_last):
+        from fauxgl_b200 import multigpu
+        nu = nv = 2237                                   # 2237 * (2*2237 - 2) = 10 003 864 triangles
+        big = synth.uv_sphere(nu, nv)
+        Tb = big.num_triangles
+        Wb, Hb = W1 * SSAA, H1 * SSAA
+        ctx = Context(Wb, Hb, local_rank)
+        sh_b, bg_b = scene_setup()
+        ctx.Shader = sh_b
+        first, count = multigpu.triangle_range(Tb, rank, world)
+        part = type(big)(big.position[first:first + count], big.normal[first:first + count])
+        del big
+        dm = DeviceMesh(ctx, part, ("position", "normal"))
+        keys = torch.empty(Wb * Hb, dtype=torch.int64, device="cuda")
+        ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
+
+        def sl_frame(sync_draw=False):
+            ctx.ClearDepthBuffer()
+            ctx.ClearColorBufferWith(bg_b)
+            if sync_draw:
+                ctx.DrawTriangles(dm)
+            else:
+                ctx.DrawMeshAsync(dm)
+            ctx.CompositePack(keys.data_ptr())
+            with torch.cuda.stream(ext):
+                multigpu.composite_min(keys)
+            ctx.CompositeUnpack(keys.data_ptr())
+        sl_frame(sync_draw=True)
+        for _ in range(2):
+            sl_frame()
+        ctx.Sync()
+        Ks = max(3, min(K, 5))
+        s_ev = [torch.cuda.Event(enable_timing=True) for _ in range(Ks)]
+        e_ev = [torch.cuda.Event(enable_timing=True) for _ in range(Ks)]
+        barrier()
+        with torch.cuda.stream(ext):
+            for i in range(Ks):
+                s_ev[i].record(ext)
+                sl_frame()
+                e_ev[i].record(ext)
+        sl_info = ctx.Sync()
+        barrier()
+        sl_ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(s_ev, e_ev)) / Ks)
+        sort_last = {"ms_per_frame": sl_ms, "mtri_s": Tb / (sl_ms / 1e3) / 1e6, "triangles": Tb, "steps": Ks,
+                     "workload": "M10M: %d-triangle unit sphere, Phong, 7680x4320; rank r draws triangles [rT/N,(r+1)T/N), "
+                                 "packed-key int64 min all-reduce (NCCL), unpack" % Tb,
+                     "composite_bytes_per_rank": Wb * Hb * 8, "scaling": "strong",
+                     "total_pixels_this_rank": int(sl_info.TotalPixels // Ks)}
+        del dm
+        ctx.Close()
+
     # ---------------- CPU baseline beside it (rank 0, N == 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -343,7 +397,7 @@ def main():
                        "timing": "CUDA events on the library's stream, per frame, summed; max over ranks"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(r1["launches_per_frame"] * K),
-            "clocks": r1["clocks"], "ssaa16": ssaa,
+            "clocks": r1["clocks"], "ssaa16": ssaa, "sort_last": sort_last,
             "raster_info": {"total_pixels": int(einfo.TotalPixels), "updated_pixels": int(einfo.UpdatedPixels),
                             "records": r1["records"], "pairs": r1["pairs"], "image_checksum": checksum},
         }

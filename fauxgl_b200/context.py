@@ -77,8 +77,8 @@ class DrawStats(C.Structure):
 
 
 class StageTimes(C.Structure):
-    _fields_ = [("geometry_ms", C.c_float), ("binning_ms", C.c_float), ("raster_ms", C.c_float),
-                ("draws", C.c_uint32)]
+    _fields_ = [("geometry_ms", C.c_float), ("spans_ms", C.c_float), ("sort_ms", C.c_float),
+                ("raster_ms", C.c_float), ("draws", C.c_uint32)]
 
 
 # every symbol include/fauxgl_b200.h declares: (name, restype, argtypes)
@@ -118,6 +118,7 @@ ABI = [
     ("fgl_composite_pack", C.c_int, [_P, _P]),
     ("fgl_composite_unpack", C.c_int, [_P, _P]),
     ("fgl_composite_min", C.c_int, [_P, _P, _P, C.c_uint64]),
+    ("fgl_debug_tile_cycles", C.c_int, [_P, _P, C.c_uint64]),
     ("fgl_stream", _P, [_P]),
     ("fgl_color_device_ptr", _P, [_P]),
     ("fgl_depth_device_ptr", _P, [_P]),

@@ -48,7 +48,8 @@ struct fgl_mesh {
 };
 
 constexpr int PROF_RING = 32;
-struct ProfSlot { cudaEvent_t e[4]; };
+constexpr int PROF_EVENTS = 5;  // start, after geometry, after spans, after sort, after tile kernel
+struct ProfSlot { cudaEvent_t e[PROF_EVENTS]; };
 
 struct fgl_ctx {
     int device;
@@ -99,9 +100,9 @@ void dev_free(T *&p) {
 }
 
 void free_work(WorkBuffers &wb) {
-    dev_free(wb.prim_nrec); dev_free(wb.prim_rec_off); dev_free(wb.recs); dev_free(wb.rec_rows);
+    dev_free(wb.lb_status); dev_free(wb.lb_ticket); dev_free(wb.recs);
     dev_free(wb.rec_row_off); dev_free(wb.clip_pool); dev_free(wb.row_nseg); dev_free(wb.row_seg_off);
-    dev_free(wb.segs);
+    dev_free(wb.row_first); dev_free(wb.row_key); dev_free(wb.segs); dev_free(wb.segv);
     dev_free(wb.seg_key[0]); dev_free(wb.seg_key[1]); dev_free(wb.seg_val[0]); dev_free(wb.seg_val[1]);
     dev_free(wb.scan_tmp);
     wb.cap_prims = wb.cap_records = wb.cap_rows = wb.cap_segs = wb.cap_clip = 0;
@@ -114,30 +115,33 @@ struct Caps { uint64_t prims, records, rows, segs, clip; };
 int ensure_work(fgl_ctx *c, const Caps &want) {
     WorkBuffers &wb = c->wb;
     const uint64_t LIM = 0xfffffff0ull;
+    if (want.records >= (1ull << 30)) return fail(c, FGL_E_INVALID, "draw too large: more than 2^30 raster records");
     if (want.prims > LIM || want.records > LIM || want.rows > LIM || want.segs > LIM || want.clip > LIM)
         return fail(c, FGL_E_INVALID, "draw too large for 32-bit work indices");
     if (want.prims > wb.cap_prims) {
-        dev_free(wb.prim_nrec); dev_free(wb.prim_rec_off);
-        CK(c, dev_alloc(&wb.prim_nrec, want.prims));
-        CK(c, dev_alloc(&wb.prim_rec_off, want.prims + 1));
+        dev_free(wb.lb_status);
+        CK(c, dev_alloc(&wb.lb_status, want.prims / 256 + 2));
+        if (!wb.lb_ticket) CK(c, dev_alloc(&wb.lb_ticket, 1));
         wb.cap_prims = (uint32_t)want.prims;
     }
     if (want.records > wb.cap_records) {
-        dev_free(wb.recs); dev_free(wb.rec_rows); dev_free(wb.rec_row_off);
+        dev_free(wb.recs); dev_free(wb.rec_row_off);
         CK(c, dev_alloc(&wb.recs, want.records));
-        CK(c, dev_alloc(&wb.rec_rows, want.records));
         CK(c, dev_alloc(&wb.rec_row_off, want.records + 1));
         wb.cap_records = (uint32_t)want.records;
     }
     if (want.rows > wb.cap_rows) {
-        dev_free(wb.row_nseg); dev_free(wb.row_seg_off);
+        dev_free(wb.row_nseg); dev_free(wb.row_seg_off); dev_free(wb.row_first); dev_free(wb.row_key);
+        CK(c, dev_alloc(&wb.row_first, want.rows));
+        CK(c, dev_alloc(&wb.row_key, want.rows));
         CK(c, dev_alloc(&wb.row_nseg, want.rows));
         CK(c, dev_alloc(&wb.row_seg_off, want.rows + 1));
         wb.cap_rows = (uint32_t)want.rows;
     }
     if (want.segs > wb.cap_segs) {
-        dev_free(wb.segs);
+        dev_free(wb.segs); dev_free(wb.segv);
         CK(c, dev_alloc(&wb.segs, want.segs));
+        CK(c, dev_alloc(&wb.segv, want.segs));
         for (int k = 0; k < 2; k++) {
             dev_free(wb.seg_key[k]); dev_free(wb.seg_val[k]);
             CK(c, dev_alloc(&wb.seg_key[k], want.segs));
@@ -250,11 +254,12 @@ void prof_drain(fgl_ctx *c) {
     if (!c->prof_used) return;
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < c->prof_used; i++) {
-        float g = 0, b = 0, r = 0;
+        float g = 0, s = 0, b = 0, r = 0;
         cudaEventElapsedTime(&g, c->prof[i].e[0], c->prof[i].e[1]);
-        cudaEventElapsedTime(&b, c->prof[i].e[1], c->prof[i].e[2]);
-        cudaEventElapsedTime(&r, c->prof[i].e[2], c->prof[i].e[3]);
-        c->prof_acc.geometry_ms += g; c->prof_acc.binning_ms += b; c->prof_acc.raster_ms += r;
+        cudaEventElapsedTime(&s, c->prof[i].e[1], c->prof[i].e[2]);
+        cudaEventElapsedTime(&b, c->prof[i].e[2], c->prof[i].e[3]);
+        cudaEventElapsedTime(&r, c->prof[i].e[3], c->prof[i].e[4]);
+        c->prof_acc.geometry_ms += g; c->prof_acc.spans_ms += s; c->prof_acc.sort_ms += b; c->prof_acc.raster_ms += r;
     }
     c->prof_acc.draws += (uint32_t)c->prof_used;
     c->prof_used = 0;
@@ -273,8 +278,10 @@ int enqueue_draw(fgl_ctx *c, const DrawParams &p) {
     int sorted = 0;
     launches += launch_spans(p, c->wb, &sorted, c->stream);
     if (ps) cudaEventRecord(ps->e[2], c->stream);
-    launches += launch_raster(p, c->wb, sorted, c->color, c->depth, c->stream);
+    launches += launch_bin(p, c->wb, &sorted, c->stream);
     if (ps) cudaEventRecord(ps->e[3], c->stream);
+    launches += launch_raster(p, c->wb, sorted, c->color, c->depth, c->stream);
+    if (ps) cudaEventRecord(ps->e[4], c->stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(c, FGL_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
     c->stats.kernel_launches = (uint32_t)launches;
@@ -307,6 +314,11 @@ int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const 
     c->stats.prims_in = count;
     c->stats.retries = 0;
     if (count == 0) return FGL_OK;
+    if (p.deferred && !c->wb.vis_winner) {  // visibility buffer of the deferred-shading path, tile-major
+        const size_t npx = (size_t)c->wb.ntiles * TILE_PIX;
+        CK(c, dev_alloc(&c->wb.vis_winner, npx));
+        CK(c, dev_alloc(&c->wb.vis_w, 3 * npx));
+    }
     rc = initial_capacity(c, p);
     if (rc) return rc;
     if (async) {
@@ -386,6 +398,12 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     c->wb.ntiles = (uint32_t)(((width + TILE_W - 1) / TILE_W) * ((height + TILE_H - 1) / TILE_H));
     if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_start, c->wb.ntiles);
     if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_end, c->wb.ntiles);
+    if (err == cudaSuccess) err = dev_alloc(&c->wb.busy_list, c->wb.ntiles);
+    if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_ctl, 1);
+    if (err == cudaSuccess && getenv("FGL_TILE_CLOCK")) {  // tuning aid: per-tile cycle counts of k_tile
+        err = dev_alloc(&c->wb.tile_clock, (size_t)c->wb.ntiles * 2);
+        if (err == cudaSuccess) err = cudaMemset(c->wb.tile_clock, 0, sizeof(unsigned long long) * c->wb.ntiles * 2);
+    }
     if (err == cudaSuccess) err = cudaMemsetAsync(c->acc_dev, 0, sizeof(DrawCounters), c->stream);
     if (err != cudaSuccess) {
         cudaGetLastError();
@@ -415,12 +433,13 @@ int fgl_context_destroy(fgl_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_work(c->wb);
-    dev_free(c->wb.tile_start); dev_free(c->wb.tile_end); dev_free(c->wb.counters);
+    dev_free(c->wb.tile_start); dev_free(c->wb.tile_end); dev_free(c->wb.counters); dev_free(c->wb.tile_clock);
+    dev_free(c->wb.busy_list); dev_free(c->wb.tile_ctl); dev_free(c->wb.vis_winner); dev_free(c->wb.vis_w);
     dev_free(c->acc_dev); dev_free(c->color); dev_free(c->depth); dev_free(c->resolved);
     if (c->host_counters) cudaFreeHost(c->host_counters);
     if (c->prof_created)
         for (int i = 0; i < PROF_RING; i++)
-            for (int k = 0; k < 4; k++) cudaEventDestroy(c->prof[i].e[k]);
+            for (int k = 0; k < PROF_EVENTS; k++) cudaEventDestroy(c->prof[i].e[k]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return FGL_OK;
@@ -666,7 +685,7 @@ int fgl_set_profiling(fgl_ctx *c, int enabled) {
     std::lock_guard<std::mutex> lock(c->mu);
     if (enabled && !c->prof_created) {
         for (int i = 0; i < PROF_RING; i++)
-            for (int k = 0; k < 4; k++) CK(c, cudaEventCreate(&c->prof[i].e[k]));
+            for (int k = 0; k < PROF_EVENTS; k++) CK(c, cudaEventCreate(&c->prof[i].e[k]));
         c->prof_created = true;
     }
     if (!enabled) prof_drain(c);
@@ -794,6 +813,17 @@ int fgl_composite_min(fgl_ctx *c, void *inout, const void *other, uint64_t count
     std::lock_guard<std::mutex> lock(c->mu);
     launch_composite_min(static_cast<unsigned long long *>(inout), static_cast<const unsigned long long *>(other), count, c->stream);
     CK(c, cudaGetLastError());
+    return FGL_OK;
+}
+
+int fgl_debug_tile_cycles(fgl_ctx *c, uint64_t *dst, uint64_t ntiles) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!c->wb.tile_clock) return fail(c, FGL_E_INVALID, "set FGL_TILE_CLOCK=1 before creating the context");
+    if (!dst || ntiles != c->wb.ntiles) return fail(c, FGL_E_INVALID, "need a buffer of 2*%u uint64", c->wb.ntiles);
+    std::lock_guard<std::mutex> lock(c->mu);
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaMemcpy(dst, c->wb.tile_clock, sizeof(uint64_t) * 2 * ntiles, cudaMemcpyDeviceToHost));
     return FGL_OK;
 }
 

@@ -122,43 +122,55 @@ FGL_DI double edge_fn(V3 a, V3 b, V3 c) {  // context.go:147-149
     return (b.x - c.x) * (a.y - c.y) - (b.y - c.y) * (a.x - c.x);
 }
 
+// Write one record at its ordered slot r; its scanlines start at row_off in the (record, scanline)
+// item space of the span stage.
+FGL_DI void write_record(const WorkBuffers *wb, uint32_t r, uint32_t row_off, const BBox &b, V3 s0, V3 s1, V3 s2,
+                         double w0, double w1, double w2, uint32_t src, uint32_t flags) {
+    if (r >= wb->cap_records) return;
+    Rec rec;
+    rec.s[0] = s0.x; rec.s[1] = s0.y; rec.s[2] = s0.z;
+    rec.s[3] = s1.x; rec.s[4] = s1.y; rec.s[5] = s1.z;
+    rec.s[6] = s2.x; rec.s[7] = s2.y; rec.s[8] = s2.z;
+    // per-triangle setup of Context.rasterize, context.go:163-181
+    const V3 pc = v3((double)b.x0 + 0.5, (double)b.y0 + 0.5, 0);
+    rec.w00 = edge_fn(s1, s2, pc);
+    rec.w01 = edge_fn(s2, s0, pc);
+    rec.w02 = edge_fn(s0, s1, pc);
+    const double a01 = s1.y - s0.y, a12 = s2.y - s1.y, a20 = s0.y - s2.y;
+    rec.ra = 1 / edge_fn(s0, s1, s2);
+    rec.r0 = 1 / w0; rec.r1 = 1 / w1; rec.r2 = 1 / w2;
+    rec.ra12 = 1 / a12; rec.ra20 = 1 / a20; rec.ra01 = 1 / a01;
+    rec.src = src; rec.flags = flags;
+    rec.x0 = b.x0; rec.x1 = b.x1; rec.y0 = b.y0; rec.y1 = b.y1;
+    wb->recs[r] = rec;
+    wb->rec_row_off[r] = row_off;
+}
+
+// First pass over a primitive: counts its records and scanlines and keeps the first record in
+// registers (the common case is exactly one), so that it can be written without recomputation
+// once the ordered offset is known.
 struct CountEmit {
-    uint32_t n;
+    uint32_t n, rows;
     static constexpr bool kWrite = false;
-    FGL_DI void record(const DrawParams &p, V3 s0, V3 s1, V3 s2, double w0, double w1, double w2, uint32_t,
-                       uint32_t) {
-        (void)w0; (void)w1; (void)w2;
-        if (compute_bbox(p, s0, s1, s2).visible) n++;
+    FGL_DI void record(const DrawParams &p, V3 a0, V3 a1, V3 a2, double, double, double, uint32_t, uint32_t) {
+        const BBox bb = compute_bbox(p, a0, a1, a2);
+        if (!bb.visible) return;
+        n++;
+        rows += bb.rows;
     }
     FGL_DI uint32_t pool_alloc(const FullVertex *) { return 0; }
 };
 struct WriteEmit {
-    uint32_t next;
+    uint32_t next, row_next;
     const WorkBuffers *wb;
     static constexpr bool kWrite = true;
     FGL_DI void record(const DrawParams &p, V3 s0, V3 s1, V3 s2, double w0, double w1, double w2, uint32_t src,
                        uint32_t flags) {
         const BBox b = compute_bbox(p, s0, s1, s2);
         if (!b.visible) return;
-        const uint32_t r = next++;
-        if (r >= wb->cap_records) return;
-        Rec rec;
-        rec.s[0] = s0.x; rec.s[1] = s0.y; rec.s[2] = s0.z;
-        rec.s[3] = s1.x; rec.s[4] = s1.y; rec.s[5] = s1.z;
-        rec.s[6] = s2.x; rec.s[7] = s2.y; rec.s[8] = s2.z;
-        // per-triangle setup of Context.rasterize, context.go:163-181
-        const V3 pc = v3((double)b.x0 + 0.5, (double)b.y0 + 0.5, 0);
-        rec.w00 = edge_fn(s1, s2, pc);
-        rec.w01 = edge_fn(s2, s0, pc);
-        rec.w02 = edge_fn(s0, s1, pc);
-        const double a01 = s1.y - s0.y, a12 = s2.y - s1.y, a20 = s0.y - s2.y;
-        rec.ra = 1 / edge_fn(s0, s1, s2);
-        rec.r0 = 1 / w0; rec.r1 = 1 / w1; rec.r2 = 1 / w2;
-        rec.ra12 = 1 / a12; rec.ra20 = 1 / a20; rec.ra01 = 1 / a01;
-        rec.src = src; rec.flags = flags;
-        rec.x0 = b.x0; rec.x1 = b.x1; rec.y0 = b.y0; rec.y1 = b.y1;
-        wb->recs[r] = rec;
-        wb->rec_rows[r] = b.rows;
+        write_record(wb, next, row_next, b, s0, s1, s2, w0, w1, w2, src, flags);
+        next++;
+        row_next += b.rows;
     }
     FGL_DI uint32_t pool_alloc(const FullVertex *v) {
         const uint32_t slot = atomicAdd(&wb->counters->n_clip, 1u);
@@ -393,42 +405,178 @@ FGL_DI void process_line(const DrawParams &p, Emit &e, uint32_t prim) {
     emit_line(p, e, s0, s1, 0, 1, w1.w, w2.w, prim, 0);
 }
 
-__global__ void __launch_bounds__(256)
-k_geom_count(const __grid_constant__ DrawParams p, uint32_t *__restrict__ prim_nrec, DrawCounters *ctr) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {  // first kernel of the draw: reset its counters
-        ctr->total_pixels = 0; ctr->updated_pixels = 0;
-        ctr->n_records = 0; ctr->n_rows = 0; ctr->n_segs = 0; ctr->n_clip = 0; ctr->overflow = 0;
-        ctr->need_records = 0; ctr->need_rows = 0; ctr->need_segs = 0; ctr->need_clip = 0; ctr->_pad = 0;
-    }
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.count) return;
-    CountEmit e{0};
-    if (p.is_lines) process_line(p, e, p.first + i);
-    else process_triangle(p, e, p.first + i);
-    prim_nrec[i] = e.n;
+// ---- single-pass ordered compaction (decoupled look-back) ---------------------------------------------
+// Virtual block ids come from an atomic ticket, so a block only ever waits for blocks that already
+// run.  status[b]: bits 63-62 flag (0 empty, 1 block aggregate, 2 inclusive prefix), bits 61-30 scanlines,
+// bits 29-0 records.
+constexpr int GT = 256;
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = (1ull << 62) - 1ull;
+
+// General path (lines, wireframe, clipped triangles), out of line so that its registers and stack
+// do not weigh on the common case.  Counting and writing run the same deterministic arithmetic.
+__device__ __noinline__ void count_general(const DrawParams &p, uint32_t prim, uint32_t *n, uint32_t *rows) {
+    CountEmit e{0, 0};
+    if (p.is_lines) process_line(p, e, prim);
+    else process_triangle(p, e, prim);
+    *n = e.n;
+    *rows = e.rows;
+}
+__device__ __noinline__ void write_general(const DrawParams &p, const WorkBuffers &wb, uint32_t prim, uint32_t rec0,
+                                           uint32_t row0) {
+    WriteEmit e{rec0, row0, &wb};
+    if (p.is_lines) process_line(p, e, prim);
+    else process_triangle(p, e, prim);
 }
 
-__global__ void __launch_bounds__(256, 2)
-k_geom_emit(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.count) return;
-    if (wb.prim_nrec[i] == 0) return;
-    WriteEmit e{wb.prim_rec_off[i], &wb};
-    if (p.is_lines) process_line(p, e, p.first + i);
-    else process_triangle(p, e, p.first + i);
+__global__ void __launch_bounds__(GT, 4)
+k_geometry(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
+    __shared__ uint32_t s_vb;
+    __shared__ unsigned long long s_base;
+    __shared__ unsigned long long s_scan[GT / 32 + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_vb = atomicAdd(wb.lb_ticket, 1u);
+    __syncthreads();
+    const uint32_t vb = s_vb;
+    const uint32_t nblocks = (p.count + GT - 1) / GT;
+    const uint32_t i = vb * GT + tid;
+
+    // Fast path, kept lean for occupancy: a triangle entirely inside the view volume, not in wireframe
+    // mode, yields at most one record, which stays in registers until its ordered slot is known.
+    // Everything else (lines, wireframe, clipped triangles) goes through the out-of-line general path.
+    uint32_t n = 0, rows = 0;
+    bool slow = false;
+    V3 s0, s1, s2;
+    double w0 = 0, w1 = 0, w2 = 0;
+    uint32_t vflags = 0;
+    BBox bb;
+    bb.visible = false;
+    if (i < p.count) {
+        const uint32_t prim = p.first + i;
+        if (p.is_lines || p.state.wireframe) {
+            slow = true;
+        } else {
+            const MeshPlanes &m = p.mesh;
+            V4 o[3];
+            bool outside = false;
+#pragma unroll
+            for (uint32_t v = 0; v < 3; v++) {
+                const V3 pos = v3(plane_at(m.pos, m.n, v, 3, 0, prim), plane_at(m.pos, m.n, v, 3, 1, prim),
+                                  plane_at(m.pos, m.n, v, 3, 2, prim));
+                o[v] = m_mul_position_w(p.matrix, pos);  // Shader.Vertex, shader.go:20,39,70
+                outside = outside || w_outside(o[v]);
+            }
+            if (outside) {
+                slow = true;
+            } else {  // drawClippedTriangle, context.go:316-341
+                V3 ndc0 = v3(o[0].x / o[0].w, o[0].y / o[0].w, o[0].z / o[0].w);
+                V3 ndc1 = v3(o[1].x / o[1].w, o[1].y / o[1].w, o[1].z / o[1].w);
+                V3 ndc2 = v3(o[2].x / o[2].w, o[2].y / o[2].w, o[2].z / o[2].w);
+                double a = (ndc1.x - ndc0.x) * (ndc2.y - ndc0.y) - (ndc2.x - ndc0.x) * (ndc1.y - ndc0.y);
+                uint32_t i0 = 0, i2 = 2;
+                if (a < 0) {
+                    V3 t = ndc0; ndc0 = ndc2; ndc2 = t;
+                    i0 = 2; i2 = 0;
+                }
+                if (p.state.cull == FGL_CULL_FRONT) a = -a;
+                if (p.state.front_face == FGL_FACE_CW) a = -a;
+                if (!(p.state.cull != FGL_CULL_NONE && a <= 0)) {
+                    s0 = m_mul_position(p.screen, ndc0);
+                    s1 = m_mul_position(p.screen, ndc1);
+                    s2 = m_mul_position(p.screen, ndc2);
+                    bb = compute_bbox(p, s0, s1, s2);
+                    if (bb.visible) {
+                        n = 1; rows = bb.rows;
+                        w0 = i0 == 0 ? o[0].w : o[2].w; w1 = o[1].w; w2 = i2 == 2 ? o[2].w : o[0].w;
+                        vflags = vmap3(i0, 1, i2);
+                    }
+                }
+            }
+        }
+        if (slow) count_general(p, prim, &n, &rows);
+    }
+    // block-wide exclusive scan of (rows << 30 | records)
+    const unsigned long long mine = ((unsigned long long)rows << 30) | n;
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long v = lane < GT / 32 ? s_scan[lane] : 0, vi = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, vi, o);
+            if (lane >= o) vi += t;
+        }
+        if (lane < GT / 32) s_scan[lane] = vi - v;
+        if (lane == GT / 32 - 1) s_scan[GT / 32] = vi;
+    }
+    __syncthreads();
+    const unsigned long long local_excl = s_scan[warp] + incl - mine;
+    const unsigned long long block_total = s_scan[GT / 32];
+
+    if (warp == 0) {
+        // warp-wide look-back: 32 predecessors per step (a serial walk over the ~600 resident blocks
+        // costs an L2 round trip per step and dominated the kernel)
+        volatile unsigned long long *status = wb.lb_status;
+        unsigned long long excl = 0;
+        if (vb > 0) {
+            if (lane == 0) status[vb] = LB_AGG | block_total;
+            __threadfence();
+            for (int top = (int)vb - 1;; top -= 32) {
+                const int idx = top - lane;
+                unsigned long long v = LB_PREFIX;  // virtual zero prefix in front of block 0
+                if (idx >= 0) {
+                    do { v = status[idx]; } while ((v >> 62) == 0);
+                }
+                const unsigned pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                const int first = pm ? __ffs(pm) - 1 : 31;  // nearest predecessor that already has a prefix
+                unsigned long long contrib = lane <= first ? (v & LB_MASK) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_down_sync(0xffffffffu, contrib, o);
+                excl += __shfl_sync(0xffffffffu, contrib, 0);
+                if (pm) break;
+            }
+        }
+        if (lane == 0) {
+            status[vb] = LB_PREFIX | (excl + block_total);
+            __threadfence();
+            s_base = excl;
+        }
+        if (lane == 0 && vb == nblocks - 1) {  // grand totals
+            const unsigned long long tot = excl + block_total;
+            const uint32_t nrec = (uint32_t)(tot & ((1ull << 30) - 1ull)), nrows = (uint32_t)(tot >> 30);
+            DrawCounters *c = wb.counters;
+            c->n_records = nrec; c->need_records = nrec;
+            c->n_rows = nrows; c->need_rows = nrows;
+            unsigned ovf = 0;
+            if (nrec > wb.cap_records) ovf |= OVF_RECORDS;
+            if (nrows > wb.cap_rows) ovf |= OVF_ROWS;
+            if (ovf) atomicOr(&c->overflow, ovf);
+            if (nrec <= wb.cap_records) wb.rec_row_off[nrec] = nrows;  // sentinel for the span stage's search
+        }
+    }
+    __syncthreads();
+    const unsigned long long base = s_base + local_excl;
+    const uint32_t rec0 = (uint32_t)(base & ((1ull << 30) - 1ull)), row0 = (uint32_t)(base >> 30);
+    if (slow) {
+        if (n > 0) write_general(p, wb, p.first + i, rec0, row0);  // run again, writing at the ordered slots
+    } else if (n == 1) {
+        write_record(&wb, rec0, row0, bb, s0, s1, s2, w0, w1, w2, p.first + i, vflags);
+    }
 }
 
 int launch_geometry(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {
-    int launches = 0;
-    const uint32_t blocks = (p.count + 255) / 256;
-    k_geom_count<<<blocks, 256, 0, st>>>(p, wb.prim_nrec, wb.counters);
-    launches++;
-    ScanSink sink{&wb.counters->n_records, &wb.counters->need_records, &wb.counters->overflow, wb.cap_records,
-                  OVF_RECORDS, nullptr, nullptr, 0};
-    launches += launch_exclusive_scan(wb.prim_nrec, wb.prim_rec_off, p.count, nullptr, wb.scan_tmp, sink, st);
-    k_geom_emit<<<blocks, 256, 0, st>>>(p, wb);
-    launches++;
-    return launches;
+    const uint32_t blocks = (p.count + GT - 1) / GT;
+    // counters + look-back state of this draw (stream-ordered before the kernel)
+    cudaMemsetAsync(wb.counters, 0, sizeof(DrawCounters), st);
+    cudaMemsetAsync(wb.lb_ticket, 0, sizeof(unsigned int), st);
+    cudaMemsetAsync(wb.lb_status, 0, sizeof(unsigned long long) * blocks, st);
+    k_geometry<<<blocks, GT, 0, st>>>(p, wb);
+    return 1;
 }
 
 }  // namespace fgl

@@ -13,8 +13,10 @@ namespace fgl {
 // Wide, short tiles: the reference walks each scanline left to right with
 // forward differencing (context.go:207-213); a span is cut into one segment per
 // tile column it covers, so wide tiles mean few segments.
+// Short: a segment never spans rows, so shrinking the tile height adds no segments; it only splits
+// dense regions over more CTAs (the kernel's duration is its heaviest tile, profiles/README.md).
 constexpr int TILE_W = 64;
-constexpr int TILE_H = 16;
+constexpr int TILE_H = 8;
 constexpr int TILE_PIX = TILE_W * TILE_H;
 
 // ---- device mesh: planar SoA ----------------------------------------------------
@@ -64,6 +66,28 @@ struct __align__(16) Seg {
 };
 static_assert(sizeof(Seg) == 32, "Seg layout");
 
+// ---- binned segment: a Seg plus the fields of its record the ordered depth phase needs, gathered
+// into tile order so the tile kernel streams its bin with coalesced loads and no dependent fetches.
+struct __align__(16) SegV {
+    double w0, w1, w2;
+    double ra, z0, z1, z2;   // 1/area and the three screen depths: z = (b0*z0 + b1*z1) + b2*z2
+    double a12, a20, a01;    // per-pixel increments of w0, w1, w2 (context.go:167-172)
+    uint32_t rec;
+    uint16_t x;
+    uint8_t yt, cnt;
+    uint32_t _pad[2];
+};
+static_assert(sizeof(SegV) == 96, "SegV layout");
+
+// Tile work queue (device): busy tiles ordered heaviest-first (bucketed by log2 of the bin size),
+// pulled by persistent CTAs with an atomic head.
+struct TileCtl {
+    uint32_t bucket_cnt[32];
+    uint32_t bucket_fill[32];
+    uint32_t nbusy;
+    uint32_t head_resolve, head_shade, _pad;
+};
+
 // ---- per-draw device constants ------------------------------------------------------
 struct DrawParams {
     fgl_state state;
@@ -94,21 +118,28 @@ constexpr unsigned OVF_RECORDS = 1u, OVF_ROWS = 2u, OVF_CLIP = 4u, OVF_SEGS = 8u
 
 struct WorkBuffers {
     // geometry
-    uint32_t *prim_nrec;      // [count]   records emitted per primitive
-    uint32_t *prim_rec_off;   // [count+1] exclusive scan
+    unsigned long long *lb_status;  // [ceil(cap_prims/256)] decoupled look-back state of the geometry kernel
+    unsigned int *lb_ticket;        // virtual block id dispenser
     Rec *recs;                // [cap_records]
-    uint32_t *rec_rows;       // [cap_records]   on-screen scanlines of each record
-    uint32_t *rec_row_off;    // [cap_records+1] exclusive scan
+    uint32_t *rec_row_off;    // [cap_records+1] first (record, scanline) item of each record; [n] = total
     ClipTri *clip_pool;       // [cap_clip]
     // spans
     uint32_t *row_nseg;       // [cap_rows]   segments of each (record, scanline)
     uint32_t *row_seg_off;    // [cap_rows+1] exclusive scan
+    Seg *row_first;           // [cap_rows]   first segment of the scanline, kept by the count pass
+    uint32_t *row_key;        // [cap_rows]   its tile id
     Seg *segs;                // [cap_segs]   in (record, scanline, column) order
     // binning: stable sort of segment indices by tile
     uint32_t *seg_key[2];     // [cap_segs] tile id (ping-pong for the radix sort)
     uint32_t *seg_val[2];     // [cap_segs] segment index
     uint32_t *tile_start;     // [ntiles]
     uint32_t *tile_end;       // [ntiles]
+    SegV *segv;               // [cap_segs]  segments in tile order (gathered after the sort)
+    uint32_t *busy_list;      // [ntiles]    non-empty tiles, heaviest first
+    TileCtl *tile_ctl;        // device
+    uint32_t *vis_winner;     // [ntiles*TILE_PIX] deferred shading: winning record per pixel, tile-major
+    double *vis_w;            // [3][ntiles*TILE_PIX] its w0,w1,w2 (allocated on the first deferred draw)
+    unsigned long long *tile_clock;  // [ntiles][2] (cycles, smid) of the last k_tile launch; null unless FGL_TILE_CLOCK=1
     uint32_t *scan_tmp;       // block sums for scans / radix histograms
     DrawCounters *counters;   // device
     uint32_t cap_prims, cap_records, cap_rows, cap_segs, cap_clip, ntiles, scan_tmp_words;
@@ -143,6 +174,7 @@ int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsi
 
 int launch_geometry(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
 int launch_spans(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
+int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
 int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,
                   cudaStream_t st);
 

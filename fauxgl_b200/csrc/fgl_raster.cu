@@ -1,7 +1,8 @@
-// fgl_raster.cu -- tile-parallel, ordered back end: one CTA per 64x16 screen tile
-// keeps the tile's depth (f64) and colour (NRGBA8) in shared memory, consumes its
-// bin of span segments in primitive order and writes the tile back once,
-// coalesced -- replacing the reference's per-pixel mutex array.
+// fgl_raster.cu -- tile-parallel, ordered back end.  Persistent CTAs pull busy 64x8
+// screen tiles heaviest-first from a device queue, keep the tile's depth (f64) (and
+// colour, when shading inline) in shared memory, consume the tile's bin of span
+// segments in primitive order and write the tile back once, coalesced -- replacing
+// the reference's per-pixel mutex array.
 //
 // Replaces the per-pixel body of Context.rasterize (context.go:207-273),
 // InterpolateVertexes (vertex.go:18-47), the three built-in Fragment shaders
@@ -9,7 +10,7 @@
 // Color.NRGBA (color.go:56) and the depth retest / write / blend (context.go:245-273).
 //
 // Arithmetic parity.  Each segment carries the reference's forward-differenced
-// edge values at its first pixel (fgl_span.cu); this kernel continues the same
+// edge values at its first pixel (fgl_span.cu); the kernels here continue the same
 // `w += a` chain (context.go:211-213), so barycentrics, depth and colour are
 // bit-identical to a sequential run of the reference in triangle-index order.
 //
@@ -22,171 +23,86 @@
 //
 // Deferred shading.  When the draw's shader can neither discard nor blend
 // (SolidColor, or Phong with an ObjectColor and no texture, alpha != 0 and no
-// effective blending) the fragment colour cannot influence any depth decision,
-// so the ordered phase resolves depth only and records, per pixel, the winning
-// record and its edge values; the colour of the final winners is computed once
-// per pixel at the end of the tile, with every thread busy.  Otherwise
-// fragments are shaded inline, in order, exactly like the reference.
+// effective blending) the fragment colour cannot influence any depth decision:
+// k_tile_resolve settles depth only and records, per pixel, the winning record and
+// its edge values; k_shade then colours each pixel's FINAL winner once, as a
+// separate full-occupancy kernel (no per-tile serial tail).  Otherwise
+// k_tile_inline shades fragments in order, exactly like the reference.
 #include "fgl_internal.h"
 #include "fgl_block.cuh"
 #include "fgl_math.cuh"
+#include "fgl_shade.cuh"
 
 namespace fgl {
 
-constexpr int RT = 256;      // threads per CTA == segments per batch
+constexpr int RT = 256;  // threads per CTA == segments per batch
 constexpr uint32_t NO_TICKET = 0xffffffffu;
 constexpr uint32_t NO_WINNER = 0xffffffffu;
+static_assert(TILE_W <= 64, "the pending mask is one 64-bit word per segment");
+static_assert(TILE_PIX % RT == 0, "k_shade splits a tile into TILE_PIX/RT chunks");
 
-FGL_DI double interp1(double a, double b, double c, double bx, double by, double bz, double bw) {  // vertex.go:49-79
-    double n = 0;
-    n = n + a * bx;
-    n = n + b * by;
-    n = n + c * bz;
-    return n * bw;
+// ---- segments into tile order -----------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_gather(const __grid_constant__ WorkBuffers wb, const uint32_t *__restrict__ seg_order) {
+    const DrawCounters *ctr = wb.counters;
+    if (ctr->overflow) return;
+    const uint32_t n = min(ctr->n_segs, wb.cap_segs);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Seg s = wb.segs[seg_order[i]];
+        const Rec *rp = wb.recs + s.rec;
+        SegV v;
+        v.w0 = s.w0; v.w1 = s.w1; v.w2 = s.w2;
+        v.ra = rp->ra; v.z0 = rp->s[2]; v.z1 = rp->s[5]; v.z2 = rp->s[8];
+        v.a01 = rp->s[4] - rp->s[1]; v.a12 = rp->s[7] - rp->s[4]; v.a20 = rp->s[1] - rp->s[7];  // context.go:167-172
+        v.rec = s.rec; v.x = s.x; v.yt = s.yt; v.cnt = s.cnt; v._pad[0] = v._pad[1] = 0;
+        wb.segv[i] = v;
+    }
 }
 
-// ---- attribute fetch: mesh planes or clip pool ---------------------------------------------
-struct AttrSrc {
-    const DrawParams *p;
-    const ClipTri *pool;
-    uint32_t src, flags;
-    FGL_DI uint32_t vsrc(int k) const { return (flags >> (2 * k)) & 3u; }
-    FGL_DI double pos(int k, int c) const {
-        if (flags & REC_SRC_POOL) return pool[src].v[vsrc(k)].pos[c];
-        return __ldg(p->mesh.pos + (size_t)(vsrc(k) * 3 + c) * p->mesh.n + src);
+// ---- busy-tile queue, heaviest first ------------------------------------------------------------------
+__global__ void k_tile_bucket(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ tile_end,
+                              uint32_t ntiles, TileCtl *ctl) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) {
+        const uint32_t cnt = tile_end[t] - tile_start[t];
+        if (cnt) atomicAdd(&ctl->bucket_cnt[31 - __clz(cnt)], 1u);
     }
-    FGL_DI double nrm(int k, int c) const {
-        if (flags & REC_SRC_POOL) return pool[src].v[vsrc(k)].nrm[c];
-        return __ldg(p->mesh.nrm + (size_t)(vsrc(k) * 3 + c) * p->mesh.n + src);
-    }
-    FGL_DI double tex(int k, int c) const {
-        if (flags & REC_SRC_POOL) return pool[src].v[vsrc(k)].tex[c];
-        return __ldg(p->mesh.tex + (size_t)(vsrc(k) * 2 + c) * p->mesh.n + src);
-    }
-    FGL_DI double col(int k, int c) const {
-        if (flags & REC_SRC_POOL) return pool[src].v[vsrc(k)].col[c];
-        return __ldg(p->mesh.col + (size_t)(vsrc(k) * 4 + c) * p->mesh.n + src);
-    }
-};
-
-// ---- texture.go -----------------------------------------------------------------------------
-FGL_DI C4 tex_at(const DrawParams &p, long long x, long long y) {  // image.At + MakeColor (color.go:25-29)
-    if (x < 0 || y < 0 || x >= p.tex_w || y >= p.tex_h) return c4(0, 0, 0, 0);
-    const uint32_t t = __ldg(reinterpret_cast<const uint32_t *>(p.tex) + (size_t)y * p.tex_w + x);
-    uint32_t r = t & 0xff, g = (t >> 8) & 0xff, b = (t >> 16) & 0xff, a = t >> 24;
-    if (p.tex_format == FGL_TEX_NRGBA) {  // color.NRGBA.RGBA(): premultiply
-        r |= r << 8; r *= a; r /= 0xff;
-        g |= g << 8; g *= a; g /= 0xff;
-        b |= b << 8; b *= a; b /= 0xff;
-        a |= a << 8;
-    } else {  // color.RGBA.RGBA()
-        r |= r << 8; g |= g << 8; b |= b << 8; a |= a << 8;
-    }
-    const double d = 65535.0;
-    return c4((double)r / d, (double)g / d, (double)b / d, (double)a / d);
 }
-__device__ __noinline__ C4 bilinear_sample(const DrawParams &p, double u, double v) {  // texture.go:41-63
-    v = 1 - v;
-    u -= floor(u);
-    v -= floor(v);
-    double x = u * (double)(p.tex_w - 1);
-    double y = v * (double)(p.tex_h - 1);
-    const long long x0 = go_int(x), y0 = go_int(y);
-    const long long x1 = x0 + 1, y1 = y0 + 1;
-    x -= (double)x0;
-    y -= (double)y0;
-    const C4 c00 = tex_at(p, x0, y0), c01 = tex_at(p, x0, y1), c10 = tex_at(p, x1, y0), c11 = tex_at(p, x1, y1);
-    C4 c = c4(0, 0, 0, 0);
-    c = c_add(c, c_muls(c00, (1 - x) * (1 - y)));
-    c = c_add(c, c_muls(c10, x * (1 - y)));
-    c = c_add(c, c_muls(c01, (1 - x) * y));
-    c = c_add(c, c_muls(c11, x * y));
-    return c;
-}
-
-// ---- fragment: interpolation (vertex.go:18-47) + Shader.Fragment (shader.go) -----------------------
-// (bx,by,bz,bw) are the perspective-corrected weights of context.go:236-237.
-__device__ __noinline__ C4 shade_fragment(const DrawParams &p, const AttrSrc &a, double bx, double by, double bz,
-                                          double bw) {
-    if (p.kind == FGL_SHADER_SOLID) return c4(p.color[0], p.color[1], p.color[2], p.color[3]);
-    if (p.kind == FGL_SHADER_TEXTURE) {
-        const double tu = interp1(a.tex(0, 0), a.tex(1, 0), a.tex(2, 0), bx, by, bz, bw);
-        const double tv = interp1(a.tex(0, 1), a.tex(1, 1), a.tex(2, 1), bx, by, bz, bw);
-        return bilinear_sample(p, tu, tv);
+__global__ void k_tile_enqueue(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ tile_end,
+                               uint32_t ntiles, TileCtl *ctl, uint32_t *__restrict__ busy_list) {
+    __shared__ uint32_t s_base[32];
+    if (threadIdx.x < 32) {  // bucket b starts after all heavier buckets
+        uint32_t base = 0;
+        for (int b = 31; b > (int)threadIdx.x; b--) base += ctl->bucket_cnt[b];
+        s_base[threadIdx.x] = base;
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->nbusy = base + ctl->bucket_cnt[0];
     }
-    // PhongShader.Fragment, shader.go:75-96
-    C4 light = c4(p.ambient[0], p.ambient[1], p.ambient[2], p.ambient[3]);
-    C4 color;
-    if (p.has_texture) {
-        const double tu = interp1(a.tex(0, 0), a.tex(1, 0), a.tex(2, 0), bx, by, bz, bw);
-        const double tv = interp1(a.tex(0, 1), a.tex(1, 1), a.tex(2, 1), bx, by, bz, bw);
-        color = bilinear_sample(p, tu, tv);
-    } else if (!p.object_is_discard) {
-        color = c4(p.object[0], p.object[1], p.object[2], p.object[3]);
-    } else {
-        color = c4(interp1(a.col(0, 0), a.col(1, 0), a.col(2, 0), bx, by, bz, bw),
-                   interp1(a.col(0, 1), a.col(1, 1), a.col(2, 1), bx, by, bz, bw),
-                   interp1(a.col(0, 2), a.col(1, 2), a.col(2, 2), bx, by, bz, bw),
-                   interp1(a.col(0, 3), a.col(1, 3), a.col(2, 3), bx, by, bz, bw));
-    }
-    const V3 normal = v_normalize(v3(interp1(a.nrm(0, 0), a.nrm(1, 0), a.nrm(2, 0), bx, by, bz, bw),
-                                     interp1(a.nrm(0, 1), a.nrm(1, 1), a.nrm(2, 1), bx, by, bz, bw),
-                                     interp1(a.nrm(0, 2), a.nrm(1, 2), a.nrm(2, 2), bx, by, bz, bw)));
-    const V3 ld = v3(p.light[0], p.light[1], p.light[2]);
-    const double diffuse = go_max(v_dot(normal, ld), 0);
-    light = c_add(light, c_muls(c4(p.diffuse[0], p.diffuse[1], p.diffuse[2], p.diffuse[3]), diffuse));
-    if (diffuse > 0 && p.specular_power > 0) {
-        const V3 position = v3(interp1(a.pos(0, 0), a.pos(1, 0), a.pos(2, 0), bx, by, bz, bw),
-                               interp1(a.pos(0, 1), a.pos(1, 1), a.pos(2, 1), bx, by, bz, bw),
-                               interp1(a.pos(0, 2), a.pos(1, 2), a.pos(2, 2), bx, by, bz, bw));
-        const V3 camera = v_normalize(v_sub(v3(p.camera[0], p.camera[1], p.camera[2]), position));
-        const V3 reflected = v_reflect(v_negate(ld), normal);
-        double specular = go_max(v_dot(camera, reflected), 0);
-        if (specular > 0) {
-            specular = go_pow(specular, p.specular_power);
-            light = c_add(light, c_muls(c4(p.specular[0], p.specular[1], p.specular[2], p.specular[3]), specular));
+    __syncthreads();
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) {
+        const uint32_t cnt = tile_end[t] - tile_start[t];
+        if (cnt) {
+            const int b = 31 - __clz(cnt);
+            busy_list[s_base[b] + atomicAdd(&ctl->bucket_fill[b], 1u)] = t;
         }
     }
-    C4 r = c_mul(color, light);
-    r = c4(go_min(r.r, 1), go_min(r.g, 1), go_min(r.b, 1), go_min(r.a, 1));
-    r.a = color.a;
-    return r;
 }
 
-// Alpha blend, context.go:256-267 (Go stdlib color.NRGBA.RGBA(), u32 arithmetic).
-FGL_DI uint32_t blend_over(uint32_t dst, uint32_t c8) {
-    const uint32_t A8 = c8 >> 24;
-    uint32_t sa = A8; sa |= sa << 8;
-    uint32_t sr = c8 & 0xff; sr |= sr << 8; sr *= A8; sr /= 0xff;
-    uint32_t sg = (c8 >> 8) & 0xff; sg |= sg << 8; sg *= A8; sg /= 0xff;
-    uint32_t sb = (c8 >> 16) & 0xff; sb |= sb << 8; sb *= A8; sb /= 0xff;
-    const uint32_t a = (0xffffu - sa) * 0x101u;
-    const uint32_t dr = (((dst & 0xff) * a / 0xffffu + sr) >> 8) & 0xff;
-    const uint32_t dg = ((((dst >> 8) & 0xff) * a / 0xffffu + sg) >> 8) & 0xff;
-    const uint32_t db = ((((dst >> 16) & 0xff) * a / 0xffffu + sb) >> 8) & 0xff;
-    const uint32_t da = (((dst >> 24) * a / 0xffffu + sa) >> 8) & 0xff;
-    return dr | (dg << 8) | (db << 16) | (da << 24);
-}
-
-struct SegVis {   // what the ordered phase needs from the record
-    double ra, z0, z1, z2, a12, a20, a01;
-};
-
+// ---- the ordered tile kernel ------------------------------------------------------------------------
 // One fragment, inline mode: context.go:229-273 for a pixel whose ticket this thread holds.
-FGL_DI void fragment_inline(const DrawParams &p, const fgl_state &st, const WorkBuffers &wb, const Rec &r,
+FGL_DI void fragment_inline(const DrawParams &p, const fgl_state &st, const WorkBuffers &wb, const SegV &v,
                             double w0, double w1, double w2, int pi, double *s_depth, uint32_t *s_color,
                             unsigned long long &updated) {
-    const double b0 = w0 * r.ra, b1 = w1 * r.ra, b2 = w2 * r.ra;
-    const double z = b0 * r.s[2] + b1 * r.s[5] + b2 * r.s[8];  // context.go:230
+    const double b0 = w0 * v.ra, b1 = w1 * v.ra, b2 = w2 * v.ra;
+    const double z = b0 * v.z0 + b1 * v.z1 + b2 * v.z2;  // context.go:230
     const double bz = z + st.depth_bias;
     const double dcur = s_depth[pi];
-    if (st.read_depth && bz > dcur) return;                     // context.go:232
-    const double bx = b0 * r.r0, by = b1 * r.r1, bzz = b2 * r.r2;  // context.go:236
+    if (st.read_depth && bz > dcur) return;               // context.go:232
+    const Rec *rp = wb.recs + v.rec;
+    const double bx = b0 * rp->r0, by = b1 * rp->r1, bzz = b2 * rp->r2;  // context.go:236
     const double bw = 1 / (bx + by + bzz);
-    AttrSrc a{&p, wb.clip_pool, r.src, r.flags};
+    AttrSrc a{&p, wb.clip_pool, rp->src, rp->flags};
     const C4 color = shade_fragment(p, a, bx, by, bzz, bw);
-    if (c_is_discard(color)) return;                            // context.go:241
-    if (bz <= dcur || !st.read_depth) {                         // context.go:248
+    if (c_is_discard(color)) return;                      // context.go:241
+    if (bz <= dcur || !st.read_depth) {                   // context.go:248
         updated++;
         if (st.write_depth) s_depth[pi] = z;
         if (st.write_color) {
@@ -199,156 +115,196 @@ FGL_DI void fragment_inline(const DrawParams &p, const fgl_state &st, const Work
 
 template <bool DEFERRED>
 __global__ void __launch_bounds__(RT)
-k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb,
-       const uint32_t *__restrict__ seg_order, uint32_t *__restrict__ gcolor, double *__restrict__ gdepth) {
-    const uint32_t tile = blockIdx.x;
-    const uint32_t bin_beg = wb.tile_start[tile], bin_end = wb.tile_end[tile];
-    if (bin_beg >= bin_end) return;
+k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb, uint32_t *__restrict__ gcolor,
+       double *__restrict__ gdepth) {
     if (wb.counters->overflow) return;  // work buffers too small: the host regrows and re-issues the draw
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_depth = reinterpret_cast<double *>(smem_raw);                 // [TILE_PIX]
-    double *s_w = s_depth + TILE_PIX;                                        // [3][TILE_PIX]   (deferred only)
-    uint32_t *s_color = reinterpret_cast<uint32_t *>(s_w + (DEFERRED ? 3 * TILE_PIX : 0));  // [TILE_PIX]
-    uint32_t *s_ticket = s_color + TILE_PIX;                                 // [TILE_PIX]
-    uint32_t *s_winner = s_ticket + TILE_PIX;                                // [TILE_PIX]      (deferred only)
-    __shared__ unsigned long long s_updated;
+    double *s_depth = reinterpret_cast<double *>(smem_raw);                                 // [TILE_PIX]
+    double *s_w = s_depth + TILE_PIX;                                                        // [3][TILE_PIX] (deferred)
+    uint32_t *s_color = reinterpret_cast<uint32_t *>(s_w + (DEFERRED ? 3 * TILE_PIX : 0));  // [TILE_PIX] (inline)
+    uint32_t *s_ticket = s_color + (DEFERRED ? 0 : TILE_PIX);                                // [TILE_PIX]
+    uint32_t *s_winner = s_ticket + TILE_PIX;                                                // [TILE_PIX] (deferred)
+    __shared__ uint32_t s_q;
 
     const int tid = threadIdx.x;
-    const int tile_x0 = (int)(tile % (uint32_t)p.tiles_x) * TILE_W;
-    const int tile_y0 = (int)(tile / (uint32_t)p.tiles_x) * TILE_H;
-    const int tw = min(TILE_W, p.width - tile_x0);   // valid columns of this tile
-    const int th = min(TILE_H, p.height - tile_y0);  // valid rows
-
-    // ---- load the tile ------------------------------------------------------------------------
-    for (int i = tid; i < TILE_PIX; i += RT) {
-        const int lx = i % TILE_W, ly = i / TILE_W;
-        s_ticket[i] = NO_TICKET;
-        if (DEFERRED) s_winner[i] = NO_WINNER;
-        if (lx < tw && ly < th) {
-            const size_t g = (size_t)(tile_y0 + ly) * p.width + (tile_x0 + lx);
-            s_depth[i] = gdepth[g];
-            s_color[i] = gcolor[g];
-        }
-    }
-    if (tid == 0) s_updated = 0;
-    __syncthreads();
-
     const fgl_state st = p.state;
     unsigned long long my_updated = 0;
+    TileCtl *ctl = wb.tile_ctl;
 
-    for (uint32_t batch = bin_beg; batch < bin_end; batch += RT) {
-        const bool have = batch + tid < bin_end;
-        Seg sg;
-        sg.cnt = 0; sg.x = 0; sg.yt = 0; sg.rec = 0; sg.w0 = sg.w1 = sg.w2 = 0;
-        SegVis v;
-        v.ra = v.z0 = v.z1 = v.z2 = v.a12 = v.a20 = v.a01 = 0;
-        const Rec *rp = nullptr;
-        if (have) {
-            sg = wb.segs[seg_order[batch + tid]];
-            rp = wb.recs + sg.rec;
-            v.ra = rp->ra; v.z0 = rp->s[2]; v.z1 = rp->s[5]; v.z2 = rp->s[8];
-            v.a01 = rp->s[4] - rp->s[1]; v.a12 = rp->s[7] - rp->s[4]; v.a20 = rp->s[1] - rp->s[7];
-        }
-        const int xa = (int)sg.x, cnt = (int)sg.cnt;
-        const int rowbase = (int)sg.yt * TILE_W - tile_x0;
-        unsigned long long pend = cnt > 0 ? ((cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull)) << (xa - tile_x0)) : 0ull;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_q = atomicAdd(&ctl->head_resolve, 1u);
+        __syncthreads();
+        const uint32_t q = s_q;
+        if (q >= ctl->nbusy) break;
+        const uint32_t tile = wb.busy_list[q];
+        const uint32_t bin_beg = wb.tile_start[tile], bin_end = wb.tile_end[tile];
+        const long long t_begin = wb.tile_clock ? clock64() : 0;
+        const int tile_x0 = (int)(tile % (uint32_t)p.tiles_x) * TILE_W;
+        const int tile_y0 = (int)(tile / (uint32_t)p.tiles_x) * TILE_H;
+        const int tw = min(TILE_W, p.width - tile_x0);   // valid columns of this tile
+        const int th = min(TILE_H, p.height - tile_y0);  // valid rows
 
-        // ---- ordered resolution in rounds ---------------------------------------------------
-        while (true) {
-            if (pend) {
-                unsigned long long m = pend;
-                while (m) {
-                    const int bit = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    atomicMin(&s_ticket[(int)sg.yt * TILE_W + bit], (uint32_t)tid);
-                }
+        // ---- load the tile ----------------------------------------------------------------------
+        for (int i = tid; i < TILE_PIX; i += RT) {
+            const int lx = i % TILE_W, ly = i / TILE_W;
+            s_ticket[i] = NO_TICKET;
+            if (DEFERRED) s_winner[i] = NO_WINNER;
+            if (lx < tw && ly < th) {
+                const size_t g = (size_t)(tile_y0 + ly) * p.width + (tile_x0 + lx);
+                s_depth[i] = gdepth[g];
+                if (!DEFERRED) s_color[i] = gcolor[g];
             }
-            __syncthreads();
-            if (pend) {
-                double w0 = sg.w0, w1 = sg.w1, w2 = sg.w2;
-                for (int x = xa; x < xa + cnt; x++) {
-                    const unsigned long long bitm = 1ull << (x - tile_x0);
-                    const int pi = rowbase + x;
-                    if ((pend & bitm) && s_ticket[pi] == (uint32_t)tid) {
-                        pend &= ~bitm;
-                        s_ticket[pi] = NO_TICKET;
-                        if (DEFERRED) {
-                            const double b0 = w0 * v.ra, b1 = w1 * v.ra, b2 = w2 * v.ra;
-                            const double z = b0 * v.z0 + b1 * v.z1 + b2 * v.z2;  // context.go:230
-                            const double bz = z + st.depth_bias;
-                            const double dcur = s_depth[pi];
-                            // context.go:232 early-out, then (no discard possible) the retest at :248
-                            if (!(st.read_depth && bz > dcur) && (bz <= dcur || !st.read_depth)) {
-                                my_updated++;
-                                if (st.write_depth) s_depth[pi] = z;
-                                if (st.write_color) {
-                                    s_winner[pi] = sg.rec;
-                                    s_w[pi] = w0; s_w[TILE_PIX + pi] = w1; s_w[2 * TILE_PIX + pi] = w2;
-                                }
-                            }
-                        } else {
-                            fragment_inline(p, st, wb, *rp, w0, w1, w2, pi, s_depth, s_color, my_updated);
-                        }
+        }
+        __syncthreads();
+
+        for (uint32_t batch = bin_beg; batch < bin_end; batch += RT) {
+            SegV v;
+            v.cnt = 0; v.x = 0; v.yt = 0;
+            if (batch + tid < bin_end) v = wb.segv[batch + tid];  // coalesced, in tile order
+            const int xa = (int)v.x, cnt = (int)v.cnt;
+            const int rowbase = (int)v.yt * TILE_W - tile_x0;
+            unsigned long long pend = cnt > 0 ? ((cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull)) << (xa - tile_x0)) : 0ull;
+
+            // ---- ordered resolution in rounds ---------------------------------------------------
+            while (true) {
+                if (pend) {
+                    unsigned long long m = pend;
+                    while (m) {
+                        const int bit = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        atomicMin(&s_ticket[(int)v.yt * TILE_W + bit], (uint32_t)tid);
                     }
-                    w0 += v.a12; w1 += v.a20; w2 += v.a01;  // context.go:211-213
+                }
+                __syncthreads();
+                if (pend) {
+                    double w0 = v.w0, w1 = v.w1, w2 = v.w2;
+                    for (int x = xa; x < xa + cnt; x++) {
+                        const unsigned long long bitm = 1ull << (x - tile_x0);
+                        const int pi = rowbase + x;
+                        if ((pend & bitm) && s_ticket[pi] == (uint32_t)tid) {
+                            pend &= ~bitm;
+                            s_ticket[pi] = NO_TICKET;
+                            if (DEFERRED) {
+                                const double b0 = w0 * v.ra, b1 = w1 * v.ra, b2 = w2 * v.ra;
+                                const double z = b0 * v.z0 + b1 * v.z1 + b2 * v.z2;  // context.go:230
+                                const double bz = z + st.depth_bias;
+                                const double dcur = s_depth[pi];
+                                // context.go:232 early-out, then (no discard possible) the retest at :248
+                                if (!(st.read_depth && bz > dcur) && (bz <= dcur || !st.read_depth)) {
+                                    my_updated++;
+                                    if (st.write_depth) s_depth[pi] = z;
+                                    if (st.write_color) {
+                                        s_winner[pi] = v.rec;
+                                        s_w[pi] = w0; s_w[TILE_PIX + pi] = w1; s_w[2 * TILE_PIX + pi] = w2;
+                                    }
+                                }
+                            } else {
+                                fragment_inline(p, st, wb, v, w0, w1, w2, pi, s_depth, s_color, my_updated);
+                            }
+                        }
+                        w0 += v.a12; w1 += v.a20; w2 += v.a01;  // context.go:211-213
+                    }
+                }
+                if (!__syncthreads_or(pend != 0)) break;
+            }
+        }
+
+        // ---- write the tile back -----------------------------------------------------------------
+        const size_t vbase = (size_t)tile * TILE_PIX;
+        const size_t vplane = (size_t)wb.ntiles * TILE_PIX;
+        for (int i = tid; i < TILE_PIX; i += RT) {
+            const int lx = i % TILE_W, ly = i / TILE_W;
+            if (lx < tw && ly < th) {
+                const size_t g = (size_t)(tile_y0 + ly) * p.width + (tile_x0 + lx);
+                if (st.write_depth) gdepth[g] = s_depth[i];
+                if (!DEFERRED) gcolor[g] = s_color[i];
+            }
+            if (DEFERRED && st.write_color) {
+                const uint32_t win = s_winner[i];
+                wb.vis_winner[vbase + i] = win;
+                if (win != NO_WINNER) {
+                    wb.vis_w[vbase + i] = s_w[i];
+                    wb.vis_w[vplane + vbase + i] = s_w[TILE_PIX + i];
+                    wb.vis_w[2 * vplane + vbase + i] = s_w[2 * TILE_PIX + i];
                 }
             }
-            if (!__syncthreads_or(pend != 0)) break;
+        }
+        if (wb.tile_clock && tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            wb.tile_clock[2 * tile] = (unsigned long long)(clock64() - t_begin);
+            wb.tile_clock[2 * tile + 1] = ((unsigned long long)smid << 32) | (bin_end - bin_beg);
         }
     }
 
-    // ---- deferred shading of the tile's final winners ------------------------------------------
-    if (DEFERRED) {
-        __syncthreads();
-        for (int pi = tid; pi < TILE_PIX; pi += RT) {
-            const uint32_t rid = s_winner[pi];
-            if (rid == NO_WINNER) continue;
-            const Rec *rp = wb.recs + rid;
-            const double ra = rp->ra;
-            const double b0 = s_w[pi] * ra, b1 = s_w[TILE_PIX + pi] * ra, b2 = s_w[2 * TILE_PIX + pi] * ra;
-            const double bx = b0 * rp->r0, by = b1 * rp->r1, bzz = b2 * rp->r2;  // context.go:236
-            const double bw = 1 / (bx + by + bzz);
-            AttrSrc a{&p, wb.clip_pool, rp->src, rp->flags};
-            const C4 color = shade_fragment(p, a, bx, by, bzz, bw);
-            s_color[pi] = c_nrgba(color);  // SetNRGBA, context.go:269 (blending excluded by the mode)
-        }
-        __syncthreads();
-    }
-
-    // ---- write the tile back, UpdatedPixels ---------------------------------------------------------
-    for (int i = tid; i < TILE_PIX; i += RT) {
-        const int lx = i % TILE_W, ly = i / TILE_W;
-        if (lx < tw && ly < th) {
-            const size_t g = (size_t)(tile_y0 + ly) * p.width + (tile_x0 + lx);
-            gdepth[g] = s_depth[i];
-            gcolor[g] = s_color[i];
-        }
-    }
+    // UpdatedPixels: one atomic per warp per CTA lifetime
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) my_updated += __shfl_down_sync(0xffffffffu, my_updated, o);
-    if ((tid & 31) == 0 && my_updated) atomicAdd(&s_updated, my_updated);
-    __syncthreads();
-    if (tid == 0 && s_updated) atomicAdd(&wb.counters->updated_pixels, s_updated);
+    if ((tid & 31) == 0 && my_updated) atomicAdd(&wb.counters->updated_pixels, my_updated);
+}
+
+// ---- deferred shading of the final winners ---------------------------------------------------------------
+__global__ void __launch_bounds__(RT)
+k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb, uint32_t *__restrict__ gcolor) {
+    if (wb.counters->overflow) return;
+    constexpr uint32_t CHUNKS = TILE_PIX / RT;
+    __shared__ uint32_t s_q;
+    TileCtl *ctl = wb.tile_ctl;
+    const size_t vplane = (size_t)wb.ntiles * TILE_PIX;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_q = atomicAdd(&ctl->head_shade, 1u);
+        __syncthreads();
+        const uint32_t q = s_q;
+        if (q >= ctl->nbusy * CHUNKS) break;
+        const uint32_t tile = wb.busy_list[q / CHUNKS];
+        const int pi = (int)(q % CHUNKS) * RT + (int)threadIdx.x;
+        const size_t vi = (size_t)tile * TILE_PIX + pi;
+        const uint32_t rid = wb.vis_winner[vi];
+        if (rid == NO_WINNER) continue;
+        const Rec *rp = wb.recs + rid;
+        const double ra = rp->ra;
+        const double b0 = wb.vis_w[vi] * ra, b1 = wb.vis_w[vplane + vi] * ra, b2 = wb.vis_w[2 * vplane + vi] * ra;
+        const double bx = b0 * rp->r0, by = b1 * rp->r1, bzz = b2 * rp->r2;  // context.go:236
+        const double bw = 1 / (bx + by + bzz);
+        AttrSrc a{&p, wb.clip_pool, rp->src, rp->flags};
+        const C4 color = shade_fragment(p, a, bx, by, bzz, bw);
+        const int x = (int)(tile % (uint32_t)p.tiles_x) * TILE_W + pi % TILE_W;
+        const int y = (int)(tile / (uint32_t)p.tiles_x) * TILE_H + pi / TILE_W;
+        gcolor[(size_t)y * p.width + x] = c_nrgba(color);  // SetNRGBA, context.go:269 (blending excluded by the mode)
+    }
 }
 
 static size_t tile_smem(bool deferred) {
-    return sizeof(double) * TILE_PIX * (deferred ? 4 : 1) + sizeof(uint32_t) * TILE_PIX * (deferred ? 3 : 2);
+    return deferred ? sizeof(double) * TILE_PIX * 4 + sizeof(uint32_t) * TILE_PIX * 2
+                    : sizeof(double) * TILE_PIX + sizeof(uint32_t) * TILE_PIX * 2;
 }
 
 int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,
                   cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(true));
-        cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(false));
-        configured = true;
+    cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(true));
+    cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(false));
+    int launches = 0;
+    cudaMemsetAsync(wb.tile_ctl, 0, sizeof(TileCtl), st);
+    k_gather<<<148 * 8, 256, 0, st>>>(wb, wb.seg_val[sorted_buf]);
+    k_tile_bucket<<<148, 256, 0, st>>>(wb.tile_start, wb.tile_end, wb.ntiles, wb.tile_ctl);
+    k_tile_enqueue<<<148, 256, 0, st>>>(wb.tile_start, wb.tile_end, wb.ntiles, wb.tile_ctl, wb.busy_list);
+    launches += 3;
+    const uint32_t grid = wb.ntiles < 148u * 4u ? wb.ntiles : 148u * 4u;
+    if (p.deferred) {
+        k_tile<true><<<grid, RT, tile_smem(true), st>>>(p, wb, color, depth);
+        launches++;
+        if (p.state.write_color) {
+            k_shade<<<148 * 4, RT, 0, st>>>(p, wb, color);
+            launches++;
+        }
+    } else {
+        k_tile<false><<<grid, RT, tile_smem(false), st>>>(p, wb, color, depth);
+        launches++;
     }
-    if (p.deferred)
-        k_tile<true><<<wb.ntiles, RT, tile_smem(true), st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
-    else
-        k_tile<false><<<wb.ntiles, RT, tile_smem(false), st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
-    return 1;
+    return launches;
 }
 
 }  // namespace fgl

@@ -6,17 +6,23 @@
 // the tile kernel continues the same chain of adds and reproduces coverage,
 // barycentrics and depth bit for bit -- without ever restarting a row.
 //
-// This stage is unordered and perfectly load-balanced (grid-wide, no barriers);
+// This stage is unordered and load-balanced (grid-wide, no ordering barriers);
 // only covered segments reach the ordered, tile-serial back end.  Segments are
 // written in (triangle, scanline, column) order and then stably sorted by tile,
 // which keeps primitive order inside every bin.
+//
+// Two passes around one scan (ordered compaction): the walk pass counts the
+// segments of every scanline and parks the first one (almost every scanline of a
+// small triangle has exactly one); the place pass copies parked segments to their
+// ordered slots and re-walks only the scanlines that cross a tile boundary.
 #include "fgl_internal.h"
 #include "fgl_block.cuh"
 #include "fgl_math.cuh"
 
 namespace fgl {
 
-constexpr int ST = 256;  // threads per CTA == (record, scanline) items per CTA
+constexpr int ST = 256;            // threads per CTA == (record, scanline) items per virtual block
+constexpr int SPAN_GRID = 148 * 8;  // persistent grid: virtual blocks are strided over it
 
 // The fields of Rec the row walker needs.
 struct RowSetup {
@@ -24,8 +30,18 @@ struct RowSetup {
     double w00, w01, w02, ra, ra12, ra20, ra01;
     int32_t x0, x1, y0;
 };
+__device__ __forceinline__ RowSetup load_setup(const Rec *rp) {
+    RowSetup r;
+    r.s0x = rp->s[0]; r.s0y = rp->s[1]; r.s1x = rp->s[3]; r.s1y = rp->s[4]; r.s2x = rp->s[6]; r.s2y = rp->s[7];
+    r.w00 = rp->w00; r.w01 = rp->w01; r.w02 = rp->w02;
+    r.ra = rp->ra; r.ra12 = rp->ra12; r.ra20 = rp->ra20; r.ra01 = rp->ra01;
+    r.x0 = rp->x0; r.x1 = rp->x1; r.y0 = rp->y0;
+    return r;
+}
 
-template <bool EMIT>
+// Walk one scanline.  FIRST: keep only the first segment (to *first / *first_key) and count;
+// otherwise write every segment to segs/keys/vals[base...].  Returns the number of segments.
+template <bool FIRST>
 __device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const RowSetup &r, uint32_t rec_id, int y,
                                              Seg *__restrict__ segs, uint32_t *__restrict__ keys,
                                              uint32_t *__restrict__ vals, uint32_t base, uint32_t cap,
@@ -55,12 +71,13 @@ __device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const RowSetup
     const uint32_t key_row = (uint32_t)(y / TILE_H) * (uint32_t)p.tiles_x;
     const uint8_t yt = (uint8_t)(y % TILE_H);
     auto flush = [&]() {
-        if (EMIT && base + nseg < cap) {
+        const uint32_t slot = FIRST ? base : base + nseg;
+        if ((FIRST ? nseg == 0 : true) && slot < cap) {
             Seg s;
             s.w0 = sw0; s.w1 = sw1; s.w2 = sw2; s.rec = rec_id; s.x = (uint16_t)sx; s.yt = yt; s.cnt = (uint8_t)cnt;
-            segs[base + nseg] = s;
-            keys[base + nseg] = key_row + (uint32_t)col;
-            vals[base + nseg] = base + nseg;
+            segs[slot] = s;
+            keys[slot] = key_row + (uint32_t)col;
+            if (!FIRST) vals[slot] = slot;
         }
         *covered += cnt;
         nseg++;
@@ -100,58 +117,75 @@ __device__ __forceinline__ uint32_t warp_find(const uint32_t *__restrict__ off, 
     return lo;
 }
 
-template <bool EMIT>
+// Pass 1: walk every (record, scanline); row_nseg, row_first/row_key; TotalPixels.
 __global__ void __launch_bounds__(ST)
-k_spans(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
+k_span_walk(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
     const DrawCounters *ctr = wb.counters;
     if (ctr->overflow) return;
     const uint32_t nrec = min(ctr->n_records, wb.cap_records);
     const uint32_t nrows = min(ctr->n_rows, wb.cap_rows);
-    const uint32_t i0 = blockIdx.x * ST;
-    if (i0 >= nrows) return;
-    // The ST items of this CTA belong to at most ST consecutive records (every record has >= 1
-    // scanline): find the first with one warp, stage that window of the offset array in shared
-    // memory and let every thread finish its search there.
     __shared__ uint32_t s_first;
     __shared__ uint32_t s_off[ST + 1];
-    if (threadIdx.x < 32) {
-        const uint32_t r0 = warp_find(wb.rec_row_off, nrec, i0);
-        if (threadIdx.x == 0) s_first = r0;
-    }
-    __syncthreads();
-    const uint32_t r0 = s_first;
-    for (uint32_t k = threadIdx.x; k <= ST; k += ST) {
-        const uint32_t r = r0 + k;
-        s_off[k] = r <= nrec ? wb.rec_row_off[r] : 0xffffffffu;
-    }
-    __syncthreads();
-    const uint32_t i = i0 + threadIdx.x;
     unsigned long long covered = 0;
-    if (i < nrows) {
-        uint32_t lo = 0, hi = ST;  // s_off[lo] <= i < s_off[hi]  (s_off[ST] >= i0 + ST > i)
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s_off[mid] <= i) lo = mid; else hi = mid;
+    for (uint32_t i0 = blockIdx.x * ST; i0 < nrows; i0 += gridDim.x * ST) {
+        // The ST items of this virtual block belong to at most ST consecutive records (every record has
+        // >= 1 scanline): find the first with one warp, stage that window of the offset array in shared
+        // memory and let every thread finish its search there.
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint32_t r0 = warp_find(wb.rec_row_off, nrec, i0);
+            if (threadIdx.x == 0) s_first = r0;
         }
-        const uint32_t rid = r0 + lo;
-        const Rec *rp = wb.recs + rid;
-        RowSetup r;
-        r.s0x = rp->s[0]; r.s0y = rp->s[1]; r.s1x = rp->s[3]; r.s1y = rp->s[4]; r.s2x = rp->s[6]; r.s2y = rp->s[7];
-        r.w00 = rp->w00; r.w01 = rp->w01; r.w02 = rp->w02;
-        r.ra = rp->ra; r.ra12 = rp->ra12; r.ra20 = rp->ra20; r.ra01 = rp->ra01;
-        r.x0 = rp->x0; r.x1 = rp->x1; r.y0 = rp->y0;
-        const int y = max(r.y0, 0) + (int)(i - s_off[lo]);
-        if (EMIT) {
-            if (wb.row_nseg[i])
-                walk_row<true>(p, r, rid, y, wb.segs, wb.seg_key[0], wb.seg_val[0], wb.row_seg_off[i], wb.cap_segs, &covered);
-        } else {
-            wb.row_nseg[i] = walk_row<false>(p, r, rid, y, nullptr, nullptr, nullptr, 0, 0, &covered);
+        __syncthreads();
+        const uint32_t r0 = s_first;
+        for (uint32_t k = threadIdx.x; k <= ST; k += ST) {
+            const uint32_t r = r0 + k;
+            s_off[k] = r <= nrec ? wb.rec_row_off[r] : 0xffffffffu;
+        }
+        __syncthreads();
+        const uint32_t i = i0 + threadIdx.x;
+        if (i < nrows) {
+            uint32_t lo = 0, hi = ST;  // s_off[lo] <= i < s_off[hi]  (s_off[ST] >= i0 + ST > i)
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_off[mid] <= i) lo = mid; else hi = mid;
+            }
+            const uint32_t rid = r0 + lo;
+            const RowSetup r = load_setup(wb.recs + rid);
+            const int y = max(r.y0, 0) + (int)(i - s_off[lo]);
+            wb.row_nseg[i] = walk_row<true>(p, r, rid, y, wb.row_first, wb.row_key, nullptr, i, wb.cap_rows, &covered);
         }
     }
-    if (!EMIT) {  // TotalPixels, context.go:229: every covered in-range pixel, before any depth test
+    // TotalPixels, context.go:229: every covered in-range pixel, before any depth test
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) covered += __shfl_down_sync(0xffffffffu, covered, o);
-        if ((threadIdx.x & 31) == 0 && covered) atomicAdd(&wb.counters->total_pixels, covered);
+    for (int o = 16; o > 0; o >>= 1) covered += __shfl_down_sync(0xffffffffu, covered, o);
+    if ((threadIdx.x & 31) == 0 && covered) atomicAdd(&wb.counters->total_pixels, covered);
+}
+
+// Pass 2: place the segments at their ordered slots.
+__global__ void __launch_bounds__(ST)
+k_span_place(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
+    const DrawCounters *ctr = wb.counters;
+    if (ctr->overflow) return;
+    const uint32_t nrows = min(ctr->n_rows, wb.cap_rows);
+    unsigned long long dummy = 0;
+    for (uint32_t i = blockIdx.x * ST + threadIdx.x; i < nrows; i += gridDim.x * ST) {
+        const uint32_t n = wb.row_nseg[i];
+        if (n == 0) continue;
+        const uint32_t base = wb.row_seg_off[i];
+        const Seg s = wb.row_first[i];
+        const uint32_t key = wb.row_key[i];
+        if (n == 1) {
+            if (base < wb.cap_segs) {
+                wb.segs[base] = s;
+                wb.seg_key[0][base] = key;
+                wb.seg_val[0][base] = base;
+            }
+        } else {  // the scanline crosses tile columns: walk it again, writing every segment
+            const RowSetup r = load_setup(wb.recs + s.rec);
+            const int y = (int)(key / (uint32_t)p.tiles_x) * TILE_H + (int)s.yt;
+            walk_row<false>(p, r, s.rec, y, wb.segs, wb.seg_key[0], wb.seg_val[0], base, wb.cap_segs, &dummy);
+        }
     }
 }
 
@@ -166,18 +200,25 @@ __global__ void k_tile_ranges(const uint32_t *__restrict__ keys, const unsigned 
 }
 
 int launch_spans(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st) {
+    (void)sorted_buf;
     int launches = 0;
     DrawCounters *c = wb.counters;
-    // scanlines per record -> item offsets (this scan also finalises the clip-pool counters)
-    ScanSink rows{&c->n_rows, &c->need_rows, &c->overflow, wb.cap_rows, OVF_ROWS, &c->n_clip, &c->need_clip, wb.cap_clip};
-    launches += launch_exclusive_scan(wb.rec_rows, wb.rec_row_off, wb.cap_records, &c->n_records, wb.scan_tmp, rows, st);
-    const uint32_t blocks = (wb.cap_rows + ST - 1) / ST;
-    k_spans<false><<<blocks ? blocks : 1, ST, 0, st>>>(p, wb);
+    const uint32_t vblocks = (wb.cap_rows + ST - 1) / ST;
+    const uint32_t grid = vblocks < (uint32_t)SPAN_GRID ? (vblocks ? vblocks : 1) : (uint32_t)SPAN_GRID;
+    k_span_walk<<<grid, ST, 0, st>>>(p, wb);
     launches++;
-    ScanSink segs{&c->n_segs, &c->need_segs, &c->overflow, wb.cap_segs, OVF_SEGS, nullptr, nullptr, 0};
+    // (this scan's spine also finalises the clip-pool counters)
+    ScanSink segs{&c->n_segs, &c->need_segs, &c->overflow, wb.cap_segs, OVF_SEGS, &c->n_clip, &c->need_clip, wb.cap_clip};
     launches += launch_exclusive_scan(wb.row_nseg, wb.row_seg_off, wb.cap_rows, &c->n_rows, wb.scan_tmp, segs, st);
-    k_spans<true><<<blocks ? blocks : 1, ST, 0, st>>>(p, wb);
+    k_span_place<<<grid, ST, 0, st>>>(p, wb);
     launches++;
+    return launches;
+}
+
+int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st) {
+    (void)p;
+    int launches = 0;
+    DrawCounters *c = wb.counters;
     // stable sort of the segment indices by tile id
     int bits = 1;
     while ((1u << bits) < wb.ntiles) bits++;

@@ -165,9 +165,10 @@ int fgl_get_draw_stats(const fgl_ctx *ctx, fgl_draw_stats *out);
  * the stream and returns the milliseconds accumulated since the last call and
  * the number of draws they cover. */
 typedef struct {
-    float geometry_ms;   /* vertex transform, clip, cull, setup, ordered compaction */
-    float binning_ms;    /* pair generation, stable sort by tile, bin ranges        */
-    float raster_ms;     /* tile rasteriser (coverage, depth, shading, write-back)  */
+    float geometry_ms;   /* vertex transform, clip, cull, setup, ordered compaction    */
+    float spans_ms;      /* exact scanline walk -> covered span segments              */
+    float sort_ms;       /* stable sort of segments by tile, bin ranges               */
+    float raster_ms;     /* k_tile alone: ordered depth resolve, shading, write-back  */
     uint32_t draws;
 } fgl_stage_times;
 int fgl_set_profiling(fgl_ctx *ctx, int enabled);
@@ -202,6 +203,11 @@ int fgl_read_resolved(fgl_ctx *ctx, uint8_t *dst_rgba8);
 int fgl_composite_pack(fgl_ctx *ctx, void *keys_dev);
 int fgl_composite_unpack(fgl_ctx *ctx, const void *keys_dev);
 int fgl_composite_min(fgl_ctx *ctx, void *keys_dev_inout, const void *keys_dev_other, uint64_t count);
+
+/* Tuning aid: with FGL_TILE_CLOCK=1 in the environment when the context is created, the
+ * tile kernel records, per screen tile, its SM cycles and (smid << 32 | segments in its bin);
+ * dst receives 2*ntiles uint64 (ntiles = tiles_x * tiles_y of fgl_draw_stats). */
+int fgl_debug_tile_cycles(fgl_ctx *ctx, uint64_t *dst, uint64_t ntiles);
 
 /* Interop for the host harness (timing with CUDA events on the launching
  * stream; zero-copy views of the buffers). */
