@@ -102,7 +102,7 @@ void dev_free(T *&p) {
 void free_work(WorkBuffers &wb) {
     dev_free(wb.lb_status); dev_free(wb.lb_ticket); dev_free(wb.recs);
     dev_free(wb.rec_row_off); dev_free(wb.clip_pool); dev_free(wb.row_nseg); dev_free(wb.row_seg_off);
-    dev_free(wb.row_first); dev_free(wb.row_key); dev_free(wb.segs); dev_free(wb.segv);
+    dev_free(wb.row_first); dev_free(wb.row_key); dev_free(wb.segv);
     dev_free(wb.seg_key[0]); dev_free(wb.seg_key[1]); dev_free(wb.seg_val[0]); dev_free(wb.seg_val[1]);
     dev_free(wb.scan_tmp);
     wb.cap_prims = wb.cap_records = wb.cap_rows = wb.cap_segs = wb.cap_clip = 0;
@@ -139,8 +139,7 @@ int ensure_work(fgl_ctx *c, const Caps &want) {
         wb.cap_rows = (uint32_t)want.rows;
     }
     if (want.segs > wb.cap_segs) {
-        dev_free(wb.segs); dev_free(wb.segv);
-        CK(c, dev_alloc(&wb.segs, want.segs));
+        dev_free(wb.segv);
         CK(c, dev_alloc(&wb.segv, want.segs));
         for (int k = 0; k < 2; k++) {
             dev_free(wb.seg_key[k]); dev_free(wb.seg_val[k]);

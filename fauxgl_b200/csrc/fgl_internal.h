@@ -128,13 +128,12 @@ struct WorkBuffers {
     uint32_t *row_seg_off;    // [cap_rows+1] exclusive scan
     Seg *row_first;           // [cap_rows]   first segment of the scanline, kept by the count pass
     uint32_t *row_key;        // [cap_rows]   its tile id
-    Seg *segs;                // [cap_segs]   in (record, scanline, column) order
     // binning: stable sort of segment indices by tile
     uint32_t *seg_key[2];     // [cap_segs] tile id (ping-pong for the radix sort)
     uint32_t *seg_val[2];     // [cap_segs] segment index
     uint32_t *tile_start;     // [ntiles]
     uint32_t *tile_end;       // [ntiles]
-    SegV *segv;               // [cap_segs]  segments in tile order (gathered after the sort)
+    SegV *segv;               // [cap_segs]  segments in (record, scanline, column) order; bins index into it
     uint32_t *busy_list;      // [ntiles]    non-empty tiles, heaviest first
     TileCtl *tile_ctl;        // device
     uint32_t *vis_winner;     // [ntiles*TILE_PIX] deferred shading: winning record per pixel, tile-major

@@ -41,24 +41,6 @@ constexpr uint32_t NO_WINNER = 0xffffffffu;
 static_assert(TILE_W <= 64, "the pending mask is one 64-bit word per segment");
 static_assert(TILE_PIX % RT == 0, "k_shade splits a tile into TILE_PIX/RT chunks");
 
-// ---- segments into tile order -----------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_gather(const __grid_constant__ WorkBuffers wb, const uint32_t *__restrict__ seg_order) {
-    const DrawCounters *ctr = wb.counters;
-    if (ctr->overflow) return;
-    const uint32_t n = min(ctr->n_segs, wb.cap_segs);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const Seg s = wb.segs[seg_order[i]];
-        const Rec *rp = wb.recs + s.rec;
-        SegV v;
-        v.w0 = s.w0; v.w1 = s.w1; v.w2 = s.w2;
-        v.ra = rp->ra; v.z0 = rp->s[2]; v.z1 = rp->s[5]; v.z2 = rp->s[8];
-        v.a01 = rp->s[4] - rp->s[1]; v.a12 = rp->s[7] - rp->s[4]; v.a20 = rp->s[1] - rp->s[7];  // context.go:167-172
-        v.rec = s.rec; v.x = s.x; v.yt = s.yt; v.cnt = s.cnt; v._pad[0] = v._pad[1] = 0;
-        wb.segv[i] = v;
-    }
-}
-
 // ---- busy-tile queue, heaviest first ------------------------------------------------------------------
 __global__ void k_tile_bucket(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ tile_end,
                               uint32_t ntiles, TileCtl *ctl) {
@@ -114,9 +96,9 @@ FGL_DI void fragment_inline(const DrawParams &p, const fgl_state &st, const Work
 }
 
 template <bool DEFERRED>
-__global__ void __launch_bounds__(RT)
-k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb, uint32_t *__restrict__ gcolor,
-       double *__restrict__ gdepth) {
+__global__ void __launch_bounds__(RT, 3)
+k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb,
+       const uint32_t *__restrict__ seg_order, uint32_t *__restrict__ gcolor, double *__restrict__ gdepth) {
     if (wb.counters->overflow) return;  // work buffers too small: the host regrows and re-issues the draw
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -159,10 +141,21 @@ k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers
         }
         __syncthreads();
 
+        // The bin is a range of the sorted index array; segments are fetched through it two batches
+        // ahead (index) / one batch ahead (segment), so neither load sits on the critical path.
+        auto load_idx = [&](uint32_t i) { return i < bin_end ? seg_order[i] : 0xffffffffu; };
+        auto load_seg = [&](uint32_t idx) {
+            SegV s;
+            s.cnt = 0; s.x = 0; s.yt = 0;
+            if (idx != 0xffffffffu) s = wb.segv[idx];
+            return s;
+        };
+        SegV v_next = load_seg(load_idx(bin_beg + tid));
+        uint32_t idx_next2 = load_idx(bin_beg + RT + tid);
         for (uint32_t batch = bin_beg; batch < bin_end; batch += RT) {
-            SegV v;
-            v.cnt = 0; v.x = 0; v.yt = 0;
-            if (batch + tid < bin_end) v = wb.segv[batch + tid];  // coalesced, in tile order
+            const SegV v = v_next;
+            v_next = load_seg(idx_next2);
+            idx_next2 = load_idx(batch + 2 * RT + tid);
             const int xa = (int)v.x, cnt = (int)v.cnt;
             const int rowbase = (int)v.yt * TILE_W - tile_x0;
             unsigned long long pend = cnt > 0 ? ((cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull)) << (xa - tile_x0)) : 0ull;
@@ -246,7 +239,7 @@ k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers
 }
 
 // ---- deferred shading of the final winners ---------------------------------------------------------------
-__global__ void __launch_bounds__(RT)
+__global__ void __launch_bounds__(RT, 4)
 k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb, uint32_t *__restrict__ gcolor) {
     if (wb.counters->overflow) return;
     constexpr uint32_t CHUNKS = TILE_PIX / RT;
@@ -264,16 +257,67 @@ k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         const size_t vi = (size_t)tile * TILE_PIX + pi;
         const uint32_t rid = wb.vis_winner[vi];
         if (rid == NO_WINNER) continue;
-        const Rec *rp = wb.recs + rid;
-        const double ra = rp->ra;
-        const double b0 = wb.vis_w[vi] * ra, b1 = wb.vis_w[vplane + vi] * ra, b2 = wb.vis_w[2 * vplane + vi] * ra;
-        const double bx = b0 * rp->r0, by = b1 * rp->r1, bzz = b2 * rp->r2;  // context.go:236
-        const double bw = 1 / (bx + by + bzz);
-        AttrSrc a{&p, wb.clip_pool, rp->src, rp->flags};
-        const C4 color = shade_fragment(p, a, bx, by, bzz, bw);
         const int x = (int)(tile % (uint32_t)p.tiles_x) * TILE_W + pi % TILE_W;
         const int y = (int)(tile / (uint32_t)p.tiles_x) * TILE_H + pi / TILE_W;
-        gcolor[(size_t)y * p.width + x] = c_nrgba(color);  // SetNRGBA, context.go:269 (blending excluded by the mode)
+        uint32_t *out = gcolor + (size_t)y * p.width + x;
+        if (p.kind == FGL_SHADER_SOLID) {  // SolidColorShader.Fragment, shader.go:25-27: nothing to interpolate
+            *out = c_nrgba(c4(p.color[0], p.color[1], p.color[2], p.color[3]));
+            continue;
+        }
+        // The deferred mode only admits Phong with an ObjectColor and no texture (fgl_api.cu), so the
+        // attribute set is fixed: 9 normal + 9 position components.  All loads are issued up front.
+        const Rec *rp = wb.recs + rid;
+        const double ra = rp->ra, r0 = rp->r0, r1 = rp->r1, r2 = rp->r2;
+        const uint32_t src = rp->src, flags = rp->flags;
+        const double w0 = wb.vis_w[vi], w1 = wb.vis_w[vplane + vi], w2 = wb.vis_w[2 * vplane + vi];
+        double n[3][3], pos[3][3];
+        if (flags & REC_SRC_POOL) {
+            const ClipTri *ct = wb.clip_pool + src;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const ClipVertex *cv = &ct->v[(flags >> (2 * k)) & 3u];
+#pragma unroll
+                for (int c = 0; c < 3; c++) { n[k][c] = cv->nrm[c]; pos[k][c] = cv->pos[c]; }
+            }
+        } else {
+            const size_t N = p.mesh.n;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const size_t vs = (flags >> (2 * k)) & 3u;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    n[k][c] = __ldg(p.mesh.nrm + (vs * 3 + c) * N + src);
+                    pos[k][c] = __ldg(p.mesh.pos + (vs * 3 + c) * N + src);
+                }
+            }
+        }
+        const double b0 = w0 * ra, b1 = w1 * ra, b2 = w2 * ra;
+        const double bx = b0 * r0, by = b1 * r1, bzz = b2 * r2;  // context.go:236
+        const double bw = 1 / (bx + by + bzz);
+        // PhongShader.Fragment, shader.go:75-96
+        const V3 normal = v_normalize(v3(interp1(n[0][0], n[1][0], n[2][0], bx, by, bzz, bw),
+                                         interp1(n[0][1], n[1][1], n[2][1], bx, by, bzz, bw),
+                                         interp1(n[0][2], n[1][2], n[2][2], bx, by, bzz, bw)));
+        const V3 ld = v3(p.light[0], p.light[1], p.light[2]);
+        C4 light = c4(p.ambient[0], p.ambient[1], p.ambient[2], p.ambient[3]);
+        const double diffuse = go_max(v_dot(normal, ld), 0);
+        light = c_add(light, c_muls(c4(p.diffuse[0], p.diffuse[1], p.diffuse[2], p.diffuse[3]), diffuse));
+        if (diffuse > 0 && p.specular_power > 0) {
+            const V3 position = v3(interp1(pos[0][0], pos[1][0], pos[2][0], bx, by, bzz, bw),
+                                   interp1(pos[0][1], pos[1][1], pos[2][1], bx, by, bzz, bw),
+                                   interp1(pos[0][2], pos[1][2], pos[2][2], bx, by, bzz, bw));
+            const V3 camera = v_normalize(v_sub(v3(p.camera[0], p.camera[1], p.camera[2]), position));
+            const V3 reflected = v_reflect(v_negate(ld), normal);
+            double specular = go_max(v_dot(camera, reflected), 0);
+            if (specular > 0) {
+                specular = go_pow(specular, p.specular_power);
+                light = c_add(light, c_muls(c4(p.specular[0], p.specular[1], p.specular[2], p.specular[3]), specular));
+            }
+        }
+        const C4 color = c4(p.object[0], p.object[1], p.object[2], p.object[3]);
+        C4 r = c_mul(color, light);
+        r = c4(go_min(r.r, 1), go_min(r.g, 1), go_min(r.b, 1), color.a);
+        *out = c_nrgba(r);  // SetNRGBA, context.go:269 (blending excluded by the mode)
     }
 }
 
@@ -288,20 +332,19 @@ int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, ui
     cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(false));
     int launches = 0;
     cudaMemsetAsync(wb.tile_ctl, 0, sizeof(TileCtl), st);
-    k_gather<<<148 * 8, 256, 0, st>>>(wb, wb.seg_val[sorted_buf]);
     k_tile_bucket<<<148, 256, 0, st>>>(wb.tile_start, wb.tile_end, wb.ntiles, wb.tile_ctl);
     k_tile_enqueue<<<148, 256, 0, st>>>(wb.tile_start, wb.tile_end, wb.ntiles, wb.tile_ctl, wb.busy_list);
-    launches += 3;
+    launches += 2;
     const uint32_t grid = wb.ntiles < 148u * 4u ? wb.ntiles : 148u * 4u;
     if (p.deferred) {
-        k_tile<true><<<grid, RT, tile_smem(true), st>>>(p, wb, color, depth);
+        k_tile<true><<<grid, RT, tile_smem(true), st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
         launches++;
         if (p.state.write_color) {
             k_shade<<<148 * 4, RT, 0, st>>>(p, wb, color);
             launches++;
         }
     } else {
-        k_tile<false><<<grid, RT, tile_smem(false), st>>>(p, wb, color, depth);
+        k_tile<false><<<grid, RT, tile_smem(false), st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
         launches++;
     }
     return launches;

@@ -28,6 +28,7 @@ constexpr int SPAN_GRID = 148 * 8;  // persistent grid: virtual blocks are strid
 struct RowSetup {
     double s0x, s0y, s1x, s1y, s2x, s2y;
     double w00, w01, w02, ra, ra12, ra20, ra01;
+    double z0, z1, z2;
     int32_t x0, x1, y0;
 };
 __device__ __forceinline__ RowSetup load_setup(const Rec *rp) {
@@ -35,17 +36,29 @@ __device__ __forceinline__ RowSetup load_setup(const Rec *rp) {
     r.s0x = rp->s[0]; r.s0y = rp->s[1]; r.s1x = rp->s[3]; r.s1y = rp->s[4]; r.s2x = rp->s[6]; r.s2y = rp->s[7];
     r.w00 = rp->w00; r.w01 = rp->w01; r.w02 = rp->w02;
     r.ra = rp->ra; r.ra12 = rp->ra12; r.ra20 = rp->ra20; r.ra01 = rp->ra01;
+    r.z0 = rp->s[2]; r.z1 = rp->s[5]; r.z2 = rp->s[8];
     r.x0 = rp->x0; r.x1 = rp->x1; r.y0 = rp->y0;
     return r;
 }
 
-// Walk one scanline.  FIRST: keep only the first segment (to *first / *first_key) and count;
-// otherwise write every segment to segs/keys/vals[base...].  Returns the number of segments.
+// A segment with the record fields the ordered depth phase needs (SegV).
+__device__ __forceinline__ SegV make_segv(double w0, double w1, double w2, double ra, double z0, double z1, double z2,
+                                          double a12, double a20, double a01, uint32_t rec, uint16_t x, uint8_t yt,
+                                          uint8_t cnt) {
+    SegV v;
+    v.w0 = w0; v.w1 = w1; v.w2 = w2; v.ra = ra; v.z0 = z0; v.z1 = z1; v.z2 = z2;
+    v.a12 = a12; v.a20 = a20; v.a01 = a01;
+    v.rec = rec; v.x = x; v.yt = yt; v.cnt = cnt; v._pad[0] = v._pad[1] = 0;
+    return v;
+}
+
+// Walk one scanline.  FIRST: park only the first segment (first[base], keys[base]) and count;
+// otherwise write every segment as a SegV to segv/keys/vals[base...].  Returns the number of segments.
 template <bool FIRST>
 __device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const RowSetup &r, uint32_t rec_id, int y,
-                                             Seg *__restrict__ segs, uint32_t *__restrict__ keys,
-                                             uint32_t *__restrict__ vals, uint32_t base, uint32_t cap,
-                                             unsigned long long *covered) {
+                                             Seg *__restrict__ first, SegV *__restrict__ segv,
+                                             uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t base,
+                                             uint32_t cap, unsigned long long *covered) {
     const double a01 = r.s1y - r.s0y, b01 = r.s0x - r.s1x;  // context.go:167-172
     const double a12 = r.s2y - r.s1y, b12 = r.s1x - r.s2x;
     const double a20 = r.s0y - r.s2y, b20 = r.s2x - r.s0x;
@@ -73,11 +86,16 @@ __device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const RowSetup
     auto flush = [&]() {
         const uint32_t slot = FIRST ? base : base + nseg;
         if ((FIRST ? nseg == 0 : true) && slot < cap) {
-            Seg s;
-            s.w0 = sw0; s.w1 = sw1; s.w2 = sw2; s.rec = rec_id; s.x = (uint16_t)sx; s.yt = yt; s.cnt = (uint8_t)cnt;
-            segs[slot] = s;
+            if (FIRST) {
+                Seg s;
+                s.w0 = sw0; s.w1 = sw1; s.w2 = sw2; s.rec = rec_id; s.x = (uint16_t)sx; s.yt = yt; s.cnt = (uint8_t)cnt;
+                first[slot] = s;
+            } else {
+                segv[slot] = make_segv(sw0, sw1, sw2, r.ra, r.z0, r.z1, r.z2, a12, a20, a01, rec_id, (uint16_t)sx, yt,
+                                       (uint8_t)cnt);
+                vals[slot] = slot;
+            }
             keys[slot] = key_row + (uint32_t)col;
-            if (!FIRST) vals[slot] = slot;
         }
         *covered += cnt;
         nseg++;
@@ -153,7 +171,7 @@ k_span_walk(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBu
             const uint32_t rid = r0 + lo;
             const RowSetup r = load_setup(wb.recs + rid);
             const int y = max(r.y0, 0) + (int)(i - s_off[lo]);
-            wb.row_nseg[i] = walk_row<true>(p, r, rid, y, wb.row_first, wb.row_key, nullptr, i, wb.cap_rows, &covered);
+            wb.row_nseg[i] = walk_row<true>(p, r, rid, y, wb.row_first, nullptr, wb.row_key, nullptr, i, wb.cap_rows, &covered);
         }
     }
     // TotalPixels, context.go:229: every covered in-range pixel, before any depth test
@@ -176,15 +194,17 @@ k_span_place(const __grid_constant__ DrawParams p, const __grid_constant__ WorkB
         const Seg s = wb.row_first[i];
         const uint32_t key = wb.row_key[i];
         if (n == 1) {
-            if (base < wb.cap_segs) {
-                wb.segs[base] = s;
+            if (base < wb.cap_segs) {  // records are visited in order here: the Rec reads are near-sequential
+                const Rec *rp = wb.recs + s.rec;
+                wb.segv[base] = make_segv(s.w0, s.w1, s.w2, rp->ra, rp->s[2], rp->s[5], rp->s[8], rp->s[7] - rp->s[4],
+                                          rp->s[1] - rp->s[7], rp->s[4] - rp->s[1], s.rec, s.x, s.yt, s.cnt);
                 wb.seg_key[0][base] = key;
                 wb.seg_val[0][base] = base;
             }
         } else {  // the scanline crosses tile columns: walk it again, writing every segment
             const RowSetup r = load_setup(wb.recs + s.rec);
             const int y = (int)(key / (uint32_t)p.tiles_x) * TILE_H + (int)s.yt;
-            walk_row<false>(p, r, s.rec, y, wb.segs, wb.seg_key[0], wb.seg_val[0], base, wb.cap_segs, &dummy);
+            walk_row<false>(p, r, s.rec, y, nullptr, wb.segv, wb.seg_key[0], wb.seg_val[0], base, wb.cap_segs, &dummy);
         }
     }
 }

@@ -24,6 +24,7 @@ shader, bg = bench.scene_setup()
 ctx = Context(bench.W1 * args.scale, bench.H1 * args.scale)
 ctx.Shader = shader
 dm = DeviceMesh(ctx, mesh, ("position", "normal"))
+ctx.DrawMesh(dm)  # synchronous first draw sizes the work buffers
 for _ in range(args.frames):
     ctx.ClearDepthBuffer()
     ctx.ClearColorBufferWith(bg)
