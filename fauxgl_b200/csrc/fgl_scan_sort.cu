@@ -222,11 +222,8 @@ int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsi
     int launches = 0, cur = 0;
     const int G = RADIX_GRID;
     const size_t scan_smem = sizeof(uint32_t) * RADIX_BINS * G;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_radix_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
-        configured = true;
-    }
+    // per device and cheap: set on every call (a process may drive several GPUs)
+    cudaFuncSetAttribute(k_radix_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
     for (int shift = 0; shift < bits; shift += 8) {
         k_radix_hist<<<G, RADIX_THREADS, 0, st>>>(key[cur], n_dev, n_max, shift, tmp);
         k_radix_scan<<<1, 1024, scan_smem, st>>>(tmp, RADIX_BINS * G);
