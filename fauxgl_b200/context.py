@@ -118,6 +118,10 @@ ABI = [
     ("fgl_composite_pack", C.c_int, [_P, _P]),
     ("fgl_composite_unpack", C.c_int, [_P, _P]),
     ("fgl_composite_min", C.c_int, [_P, _P, _P, C.c_uint64]),
+    ("fgl_ipc_export", C.c_int, [_P, _P, _P]),
+    ("fgl_ipc_open", C.c_int, [_P, _P, _P, C.POINTER(_P), C.POINTER(_P)]),
+    ("fgl_ipc_close", C.c_int, [_P, _P, _P]),
+    ("fgl_composite_peer", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
     ("fgl_debug_tile_cycles", C.c_int, [_P, _P, C.c_uint64]),
     ("fgl_stream", _P, [_P]),
     ("fgl_color_device_ptr", _P, [_P]),
@@ -411,6 +415,27 @@ class Context:
 
     def CompositeMin(self, inout_ptr: int, other_ptr: int, count: int):
         _check(capi().fgl_composite_min(self._h, inout_ptr, other_ptr, count), self._h)
+
+    def IpcExport(self):
+        """(color_handle, depth_handle): 64-byte CUDA IPC handles of this context's buffers."""
+        hc, hd = C.create_string_buffer(64), C.create_string_buffer(64)
+        _check(capi().fgl_ipc_export(self._h, hc, hd), self._h)
+        return hc.raw, hd.raw
+
+    def IpcOpen(self, color_handle: bytes, depth_handle: bytes):
+        pc, pd = _P(), _P()
+        _check(capi().fgl_ipc_open(self._h, color_handle, depth_handle, C.byref(pc), C.byref(pd)), self._h)
+        return pc.value, pd.value
+
+    def IpcClose(self, color_ptr: int, depth_ptr: int):
+        _check(capi().fgl_ipc_close(self._h, color_ptr, depth_ptr), self._h)
+
+    def CompositePeer(self, rank: int, color_ptrs, depth_ptrs):
+        """One fused kernel: min-depth composite of this rank's stripe over all ranks' buffers (P2P)."""
+        n = len(color_ptrs)
+        ca = (_P * n)(*color_ptrs)
+        da = (_P * n)(*depth_ptrs)
+        _check(capi().fgl_composite_peer(self._h, int(rank), n, ca, da), self._h)
 
     # -- interop ---------------------------------------------------------------------------------
     @property

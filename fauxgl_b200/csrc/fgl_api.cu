@@ -815,6 +815,55 @@ int fgl_composite_min(fgl_ctx *c, void *inout, const void *other, uint64_t count
     return FGL_OK;
 }
 
+int fgl_ipc_export(fgl_ctx *c, void *color_handle, void *depth_handle) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!color_handle || !depth_handle) return fail(c, FGL_E_INVALID, "null handle buffer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == FGL_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t hc, hd;
+    CK(c, cudaIpcGetMemHandle(&hc, c->color));
+    CK(c, cudaIpcGetMemHandle(&hd, c->depth));
+    memcpy(color_handle, &hc, sizeof hc);
+    memcpy(depth_handle, &hd, sizeof hd);
+    return FGL_OK;
+}
+
+int fgl_ipc_open(fgl_ctx *c, const void *color_handle, const void *depth_handle, void **color_ptr, void **depth_ptr) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!color_handle || !depth_handle || !color_ptr || !depth_ptr) return fail(c, FGL_E_INVALID, "null argument");
+    cudaIpcMemHandle_t hc, hd;
+    memcpy(&hc, color_handle, sizeof hc);
+    memcpy(&hd, depth_handle, sizeof hd);
+    CK(c, cudaIpcOpenMemHandle(color_ptr, hc, cudaIpcMemLazyEnablePeerAccess));
+    CK(c, cudaIpcOpenMemHandle(depth_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return FGL_OK;
+}
+
+int fgl_ipc_close(fgl_ctx *c, void *color_ptr, void *depth_ptr) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (color_ptr) CK(c, cudaIpcCloseMemHandle(color_ptr));
+    if (depth_ptr) CK(c, cudaIpcCloseMemHandle(depth_ptr));
+    return FGL_OK;
+}
+
+int fgl_composite_peer(fgl_ctx *c, int rank, int nranks, void *const *color, void *const *depth) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (nranks < 1 || nranks > FGL_MAX_PEERS || rank < 0 || rank >= nranks || !color || !depth)
+        return fail(c, FGL_E_INVALID, "bad rank %d / nranks %d (at most %d peers)", rank, nranks, FGL_MAX_PEERS);
+    for (int r = 0; r < nranks; r++)
+        if (!color[r] || !depth[r]) return fail(c, FGL_E_INVALID, "null buffer pointer for rank %d", r);
+    std::lock_guard<std::mutex> lock(c->mu);
+    const size_t npix = (size_t)c->w * c->h;
+    const size_t px0 = npix * (size_t)rank / nranks, px1 = npix * (size_t)(rank + 1) / nranks;
+    launch_composite_peer(reinterpret_cast<uint32_t *const *>(color), reinterpret_cast<double *const *>(depth), nranks,
+                          px0, px1, c->stream);
+    CK(c, cudaGetLastError());
+    return FGL_OK;
+}
+
 int fgl_debug_tile_cycles(fgl_ctx *c, uint64_t *dst, uint64_t ntiles) {
     int rc = check_ctx(c);
     if (rc) return rc;

@@ -169,6 +169,49 @@ int launch_composite_unpack(uint32_t *color, double *depth, const unsigned long 
     k_composite_unpack<<<148 * 8, 256, 0, st>>>(color, depth, keys, npix);
     return 1;
 }
+// ---- peer-memory composite: compute + exchange in ONE kernel over NVLink ---------------------------------
+// Rank r owns the pixel stripe [px0, px1).  For each of its pixels it loads the float64 depth of every
+// rank straight from that rank's depth buffer (P2P loads through NVLink/NVSwitch), picks the smallest --
+// on a tie the HIGHER rank, i.e. the later triangle range, which is what the reference's `<=` retest
+// (context.go:248) gives in index order -- fetches only the winner's colour, and stores depth + colour into
+// every rank's buffers (P2P stores).  Unlike the 32-bit packed key this keeps the float64 depth, so the
+// composite equals a single-GPU render bit for bit (order-independent state only: see multigpu.py).
+struct PeerBuffers {
+    uint32_t *color[FGL_MAX_PEERS];
+    double *depth[FGL_MAX_PEERS];
+};
+__global__ void __launch_bounds__(256)
+k_composite_peer(const PeerBuffers P, int nranks, size_t px0, size_t px1) {
+    for (size_t i = px0 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < px1; i += (size_t)gridDim.x * blockDim.x) {
+        double d[FGL_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < FGL_MAX_PEERS; r++)
+            if (r < nranks) d[r] = __ldcv(P.depth[r] + i);  // all loads in flight before the first compare
+        double best = d[0];
+        int win = 0;
+#pragma unroll
+        for (int r = 1; r < FGL_MAX_PEERS; r++)
+            if (r < nranks && d[r] <= best) { best = d[r]; win = r; }
+        const uint32_t c = __ldcv(P.color[win] + i);
+#pragma unroll
+        for (int r = 0; r < FGL_MAX_PEERS; r++)
+            if (r < nranks) {
+                if (d[r] != best) P.depth[r][i] = best;
+                P.color[r][i] = c;
+            }
+    }
+}
+int launch_composite_peer(uint32_t *const *color, double *const *depth, int nranks, size_t px0, size_t px1,
+                          cudaStream_t st) {
+    PeerBuffers P;
+    for (int r = 0; r < FGL_MAX_PEERS; r++) {
+        P.color[r] = r < nranks ? color[r] : nullptr;
+        P.depth[r] = r < nranks ? depth[r] : nullptr;
+    }
+    if (px1 > px0) k_composite_peer<<<148 * 8, 256, 0, st>>>(P, nranks, px0, px1);
+    return 1;
+}
+
 int launch_composite_min(unsigned long long *inout, const unsigned long long *other, size_t n, cudaStream_t st) {
     k_composite_min<<<148 * 8, 256, 0, st>>>(reinterpret_cast<long long *>(inout),
                                             reinterpret_cast<const long long *>(other), n);

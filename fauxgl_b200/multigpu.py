@@ -51,6 +51,55 @@ def composite_min(keys, group=None):
     return keys
 
 
+class PeerComposite:
+    """Sort-last composite over peer memory: ONE kernel per rank does the depth compare and the exchange
+    with P2P loads/stores through NVLink (fgl_composite_peer) instead of pack -> NCCL all-reduce -> unpack.
+    It keeps the float64 depth and breaks ties towards the higher rank (the later triangle range), so the
+    result equals a single-GPU render bit for bit in the order-independent state.
+
+    Buffers are shared through CUDA IPC handles exchanged once with ``all_gather_object``; host barriers
+    fence the kernel (all ranks drawn before anyone reads; all composited before anyone draws again)."""
+
+    def __init__(self, ctx, rank: int, world: int, group=None):
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        mine = ctx.IpcExport()
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, mine, group=group)
+        else:
+            handles[0] = mine
+        self.color, self.depth, self._opened = [], [], []
+        for r, (hc, hd) in enumerate(handles):
+            if r == rank:
+                self.color.append(ctx.color_ptr)
+                self.depth.append(ctx.depth_ptr)
+            else:
+                pc, pd = ctx.IpcOpen(hc, hd)
+                self._opened.append((pc, pd))
+                self.color.append(pc)
+                self.depth.append(pd)
+
+    def _barrier(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def composite(self):
+        """Call after this rank's draws of the frame; returns when every rank holds the full frame."""
+        info = self.ctx.Sync()               # (RasterizeInfo of this rank's async draws, if any)
+        self._barrier()                      # every rank's buffers are final
+        self.ctx.CompositePeer(self.rank, self.color, self.depth)
+        self.ctx.Sync()
+        self._barrier()                      # every stripe has been written everywhere
+        return info
+
+    def close(self):
+        for pc, pd in self._opened:
+            self.ctx.IpcClose(pc, pd)
+        self._opened = []
+
+
 def sort_last_draw(ctx, mesh, keys, rank: int, world: int, group=None):
     """Draw this rank's triangle range and composite: afterwards every rank's
     colour buffer holds the full image.  `keys` is a CUDA int64 tensor of

@@ -204,6 +204,25 @@ int fgl_composite_pack(fgl_ctx *ctx, void *keys_dev);
 int fgl_composite_unpack(fgl_ctx *ctx, const void *keys_dev);
 int fgl_composite_min(fgl_ctx *ctx, void *keys_dev_inout, const void *keys_dev_other, uint64_t count);
 
+/* Peer-memory composite: the exact, fused alternative to pack / all-reduce / unpack.  Every rank
+ * exports CUDA IPC handles of its colour and depth buffers (fgl_ipc_export, 64 bytes each), the host
+ * exchanges them (torch.distributed / MPI / a Go channel), and every rank opens its peers' handles
+ * (fgl_ipc_open).  fgl_composite_peer then runs ONE kernel on this rank that, for this rank's stripe of
+ * the frame, loads every rank's float64 depth over NVLink (P2P), selects the nearest -- on a tie the
+ * higher rank, i.e. the later triangle range, the reference's `<=` rule (context.go:248) -- and stores
+ * the winning depth and colour into ALL ranks' buffers.  color[r]/depth[r] are the device pointers of
+ * rank r (this rank's own entries are fgl_color/depth_device_ptr).  The caller must make sure all ranks
+ * have finished drawing before any rank calls it, and that all have returned from fgl_sync before
+ * anyone draws again (a host barrier each; see fauxgl_b200/multigpu.py).  The result equals a single-GPU
+ * render of the whole mesh bit for bit when ReadDepth, WriteDepth are on, DepthBias is 0 and the output is
+ * opaque. */
+#define FGL_MAX_PEERS 8
+#define FGL_IPC_HANDLE_BYTES 64
+int fgl_ipc_export(fgl_ctx *ctx, void *color_handle, void *depth_handle);
+int fgl_ipc_open(fgl_ctx *ctx, const void *color_handle, const void *depth_handle, void **color_ptr, void **depth_ptr);
+int fgl_ipc_close(fgl_ctx *ctx, void *color_ptr, void *depth_ptr);
+int fgl_composite_peer(fgl_ctx *ctx, int rank, int nranks, void *const *color, void *const *depth);
+
 /* Tuning aid: with FGL_TILE_CLOCK=1 in the environment when the context is created, the
  * tile kernel records, per screen tile, its SM cycles and (smid << 32 | segments in its bin);
  * dst receives 2*ntiles uint64 (ntiles = tiles_x * tiles_y of fgl_draw_stats). */

@@ -225,6 +225,51 @@ def test_sort_last_composite_on_one_gpu(parts, oracle_lib, Context):
     full.Close(); part.Close()
 
 
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_peer_composite_kernel_is_exact(parts, oracle_lib, Context):
+    """fgl_composite_peer (the fused P2P composite) on one GPU: N contexts stand in for N ranks.  It keeps
+    the float64 depth and breaks ties towards the later triangle range, so every 'rank' must end up with
+    exactly the single-context render: bit-identical depth AND colour, no tolerance."""
+    from fauxgl_b200 import multigpu
+    mesh = scenes.bumpy_mesh(201, 201)
+    sc = scenes.dragon_scene(mesh, 1283, 717)        # not a multiple of the tile size or of `parts`
+    full = Context(sc.width, sc.height)
+    finfo = sc.run(full)
+    ctxs = [Context(sc.width, sc.height) for _ in range(parts)]
+    total = 0
+    for r, c in enumerate(ctxs):
+        first, count = multigpu.triangle_range(mesh.num_triangles, r, parts)
+
+        class RangeCtx:
+            def __init__(self, c):
+                self.__dict__["c"] = c
+
+            def __getattr__(self, k):
+                return getattr(self.c, k)
+
+            def __setattr__(self, k, v):
+                setattr(self.c, k, v)
+
+            def DrawMesh(self, m):
+                return self.c.DrawTriangles(m, first, count)
+        total += sc.run(RangeCtx(c))[0][0]
+    for c in ctxs:
+        c.Sync()
+    colors = [c.color_ptr for c in ctxs]
+    depths = [c.depth_ptr for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.CompositePeer(r, colors, depths)           # each 'rank' composites its own stripe into all buffers
+    for c in ctxs:
+        c.Sync()
+    assert total == finfo[0][0]
+    want_c, want_d = full.Image(), full.DepthBuffer
+    for c in ctxs:
+        assert (c.DepthBuffer.view(np.uint64) == want_d.view(np.uint64)).all()
+        assert (c.Image() == want_c).all()
+        c.Close()
+    full.Close()
+
+
 def test_error_paths(gpu_capi, Context):
     from fauxgl_b200 import context, NewTriangleMesh, Identity
     with pytest.raises(context.FauxglError):
