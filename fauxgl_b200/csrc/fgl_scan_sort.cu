@@ -134,18 +134,31 @@ k_radix_hist(const uint32_t *__restrict__ keys, const unsigned int *__restrict__
     for (uint32_t i = beg + threadIdx.x; i < end; i += RADIX_THREADS)
         atomicAdd(&h[(keys[i] >> shift) & 0xff], 1u);
     __syncthreads();
-    hist[threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+    hist[blockIdx.x * RADIX_BINS + threadIdx.x] = h[threadIdx.x];  // [block][digit]: coalesced here and in the scatter
 }
 
 __global__ void __launch_bounds__(RADIX_THREADS)
 k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                 const unsigned int *__restrict__ n_dev, uint32_t n_max, int shift,
-                const uint32_t *__restrict__ hist_scanned /*[256][grid]*/) {
+                const uint32_t *__restrict__ hist /*[grid][256], raw counts*/) {
     __shared__ uint32_t cursor[RADIX_BINS];
     __shared__ uint32_t warp_cnt[RADIX_THREADS / 32][RADIX_BINS];
+    __shared__ uint32_t s_scan[RADIX_THREADS / 32 + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    cursor[threadIdx.x] = hist_scanned[threadIdx.x * gridDim.x + blockIdx.x];
+    {   // Every block derives its own bucket bases from the raw histogram (151 KB, L2 resident): thread d sums
+        // digit d over all blocks (coalesced across threads) -- no separate scan kernel.
+        uint32_t row = 0, before = 0;
+        for (uint32_t b = 0; b < gridDim.x; b++) {
+            const uint32_t v = hist[b * RADIX_BINS + threadIdx.x];
+            row += v;
+            if (b < blockIdx.x) before += v;
+        }
+        uint32_t total;
+        const uint32_t digit_base = block_excl_scan<RADIX_THREADS>(row, s_scan, &total);
+        cursor[threadIdx.x] = digit_base + before;
+    }
+    __syncthreads();
     const uint32_t n = min(*n_dev, n_max);
     uint32_t beg, end;
     radix_segment(n, beg, end);
@@ -226,11 +239,10 @@ int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsi
     cudaFuncSetAttribute(k_radix_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
     for (int shift = 0; shift < bits; shift += 8) {
         k_radix_hist<<<G, RADIX_THREADS, 0, st>>>(key[cur], n_dev, n_max, shift, tmp);
-        k_radix_scan<<<1, 1024, scan_smem, st>>>(tmp, RADIX_BINS * G);
         k_radix_scatter<<<G, RADIX_THREADS, 0, st>>>(key[cur], val[cur], key[cur ^ 1], val[cur ^ 1], n_dev, n_max, shift,
                                                      tmp);
         cur ^= 1;
-        launches += 3;
+        launches += 2;
     }
     *sorted_buf = cur;
     return launches;
