@@ -15,9 +15,11 @@ namespace fgl {
 // tile column it covers, so wide tiles mean few segments.
 // Short: a segment never spans rows, so shrinking the tile height adds no segments; it only splits
 // dense regions over more CTAs (the kernel's duration is its heaviest tile, profiles/README.md).
+// The height is chosen per context: 4 rows while the tile count still fits the 16-bit sort key
+// (two radix passes), else 8.
 constexpr int TILE_W = 64;
-constexpr int TILE_H = 8;
-constexpr int TILE_PIX = TILE_W * TILE_H;
+constexpr int TILE_H_MAX = 8;
+constexpr int TILE_PIX = TILE_W * TILE_H_MAX;  // upper bound (shared-memory sizing)
 
 // ---- device mesh: planar SoA ----------------------------------------------------
 // plane(attr, v, c)[i] = attr_base[(v * ncomp + c) * n + i]; a warp reading one
@@ -86,6 +88,7 @@ struct TileCtl {
     uint32_t bucket_fill[32];
     uint32_t nbusy;
     uint32_t head_resolve, head_shade, _pad;
+    uint32_t sm_arrivals[256];  // CTAs of the tile kernel that have started on each SM
 };
 
 // ---- per-draw device constants ------------------------------------------------------
@@ -99,6 +102,7 @@ struct DrawParams {
     int32_t tex_w, tex_h, tex_format, object_is_discard;
     // framebuffer
     int32_t width, height, tiles_x, tiles_y;
+    int32_t tile_h, _pad_tile;  // rows per tile (4 or 8)
     double screen[16];  // Screen(w,h), matrix.go:119-128
     // input
     MeshPlanes mesh;
@@ -135,6 +139,8 @@ struct WorkBuffers {
     uint32_t *tile_end;       // [ntiles]
     SegV *segv;               // [cap_segs]  segments in (record, scanline, column) order; bins index into it
     uint32_t *busy_list;      // [ntiles]    non-empty tiles, heaviest first
+    uint32_t *tile_claimed;   // [ntiles]    queue entry already taken (static first assignment + dynamic queue)
+    uint32_t nsm;             // SMs of the device
     TileCtl *tile_ctl;        // device
     uint32_t *vis_winner;     // [ntiles*TILE_PIX] deferred shading: winning record per pixel, tile-major
     double *vis_w;            // [3][ntiles*TILE_PIX] its w0,w1,w2 (allocated on the first deferred draw)

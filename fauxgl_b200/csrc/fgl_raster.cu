@@ -39,7 +39,7 @@ constexpr int RT = 256;  // threads per CTA == segments per batch
 constexpr uint32_t NO_TICKET = 0xffffffffu;
 constexpr uint32_t NO_WINNER = 0xffffffffu;
 static_assert(TILE_W <= 64, "the pending mask is one 64-bit word per segment");
-static_assert(TILE_PIX % RT == 0, "k_shade splits a tile into TILE_PIX/RT chunks");
+static_assert((TILE_W * 4) % RT == 0, "k_shade splits a tile into chunks of RT pixels");
 
 // ---- busy-tile queue, heaviest first ------------------------------------------------------------------
 __global__ void k_tile_bucket(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ tile_end,
@@ -114,22 +114,47 @@ k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers
     unsigned long long my_updated = 0;
     TileCtl *ctl = wb.tile_ctl;
 
+    const int tpix = TILE_W * p.tile_h;
+    bool first = true;
     while (true) {
         __syncthreads();
-        if (tid == 0) s_q = atomicAdd(&ctl->head_resolve, 1u);
+        if (tid == 0) {
+            // Queue entries are ordered heaviest-first.  A CTA's FIRST tile is assigned by (SM, arrival
+            // order on that SM) so that the heaviest tiles start on different SMs instead of on the few
+            // SMs whose CTAs happen to start first; afterwards tiles are pulled dynamically.  Every entry
+            // is claimed with an atomic exchange, so each tile is processed exactly once.
+            const uint32_t nbusy = ctl->nbusy;
+            uint32_t q = 0xffffffffu;
+            if (first) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                if (smid < wb.nsm && smid < 256u) {
+                    const uint32_t slot = atomicAdd(&ctl->sm_arrivals[smid], 1u);
+                    const unsigned long long cand = (unsigned long long)slot * wb.nsm + smid;
+                    if (cand < nbusy && atomicExch(&wb.tile_claimed[cand], 1u) == 0u) q = (uint32_t)cand;
+                }
+            }
+            while (q == 0xffffffffu) {
+                const uint32_t qq = atomicAdd(&ctl->head_resolve, 1u);
+                if (qq >= nbusy) break;
+                if (atomicExch(&wb.tile_claimed[qq], 1u) == 0u) q = qq;
+            }
+            s_q = q;
+        }
+        first = false;
         __syncthreads();
         const uint32_t q = s_q;
-        if (q >= ctl->nbusy) break;
+        if (q == 0xffffffffu) break;
         const uint32_t tile = wb.busy_list[q];
         const uint32_t bin_beg = wb.tile_start[tile], bin_end = wb.tile_end[tile];
         const long long t_begin = wb.tile_clock ? clock64() : 0;
         const int tile_x0 = (int)(tile % (uint32_t)p.tiles_x) * TILE_W;
-        const int tile_y0 = (int)(tile / (uint32_t)p.tiles_x) * TILE_H;
+        const int tile_y0 = (int)(tile / (uint32_t)p.tiles_x) * p.tile_h;
         const int tw = min(TILE_W, p.width - tile_x0);   // valid columns of this tile
-        const int th = min(TILE_H, p.height - tile_y0);  // valid rows
+        const int th = min(p.tile_h, p.height - tile_y0);  // valid rows
 
         // ---- load the tile ----------------------------------------------------------------------
-        for (int i = tid; i < TILE_PIX; i += RT) {
+        for (int i = tid; i < tpix; i += RT) {
             const int lx = i % TILE_W, ly = i / TILE_W;
             s_ticket[i] = NO_TICKET;
             if (DEFERRED) s_winner[i] = NO_WINNER;
@@ -205,9 +230,9 @@ k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers
         }
 
         // ---- write the tile back -----------------------------------------------------------------
-        const size_t vbase = (size_t)tile * TILE_PIX;
-        const size_t vplane = (size_t)wb.ntiles * TILE_PIX;
-        for (int i = tid; i < TILE_PIX; i += RT) {
+        const size_t vbase = (size_t)tile * tpix;
+        const size_t vplane = (size_t)wb.ntiles * tpix;
+        for (int i = tid; i < tpix; i += RT) {
             const int lx = i % TILE_W, ly = i / TILE_W;
             if (lx < tw && ly < th) {
                 const size_t g = (size_t)(tile_y0 + ly) * p.width + (tile_x0 + lx);
@@ -242,10 +267,11 @@ k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers
 __global__ void __launch_bounds__(RT, 4)
 k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb, uint32_t *__restrict__ gcolor) {
     if (wb.counters->overflow) return;
-    constexpr uint32_t CHUNKS = TILE_PIX / RT;
+    const int tpix = TILE_W * p.tile_h;
+    const uint32_t CHUNKS = (uint32_t)tpix / RT;
     __shared__ uint32_t s_q;
     TileCtl *ctl = wb.tile_ctl;
-    const size_t vplane = (size_t)wb.ntiles * TILE_PIX;
+    const size_t vplane = (size_t)wb.ntiles * tpix;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_q = atomicAdd(&ctl->head_shade, 1u);
@@ -254,11 +280,11 @@ k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         if (q >= ctl->nbusy * CHUNKS) break;
         const uint32_t tile = wb.busy_list[q / CHUNKS];
         const int pi = (int)(q % CHUNKS) * RT + (int)threadIdx.x;
-        const size_t vi = (size_t)tile * TILE_PIX + pi;
+        const size_t vi = (size_t)tile * tpix + pi;
         const uint32_t rid = wb.vis_winner[vi];
         if (rid == NO_WINNER) continue;
         const int x = (int)(tile % (uint32_t)p.tiles_x) * TILE_W + pi % TILE_W;
-        const int y = (int)(tile / (uint32_t)p.tiles_x) * TILE_H + pi / TILE_W;
+        const int y = (int)(tile / (uint32_t)p.tiles_x) * p.tile_h + pi / TILE_W;
         uint32_t *out = gcolor + (size_t)y * p.width + x;
         if (p.kind == FGL_SHADER_SOLID) {  // SolidColorShader.Fragment, shader.go:25-27: nothing to interpolate
             *out = c_nrgba(c4(p.color[0], p.color[1], p.color[2], p.color[3]));
@@ -332,6 +358,7 @@ int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, ui
     cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(false));
     int launches = 0;
     cudaMemsetAsync(wb.tile_ctl, 0, sizeof(TileCtl), st);
+    cudaMemsetAsync(wb.tile_claimed, 0, sizeof(uint32_t) * wb.ntiles, st);
     k_tile_bucket<<<148, 256, 0, st>>>(wb.tile_start, wb.tile_end, wb.ntiles, wb.tile_ctl);
     k_tile_enqueue<<<148, 256, 0, st>>>(wb.tile_start, wb.tile_end, wb.ntiles, wb.tile_ctl, wb.busy_list);
     launches += 2;

@@ -81,8 +81,8 @@ __device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const RowSetup
     int col = -1, sx = 0;
     double sw0 = 0, sw1 = 0, sw2 = 0;
     bool was_inside = false;
-    const uint32_t key_row = (uint32_t)(y / TILE_H) * (uint32_t)p.tiles_x;
-    const uint8_t yt = (uint8_t)(y % TILE_H);
+    const uint32_t key_row = (uint32_t)(y / p.tile_h) * (uint32_t)p.tiles_x;
+    const uint8_t yt = (uint8_t)(y % p.tile_h);
     auto flush = [&]() {
         const uint32_t slot = FIRST ? base : base + nseg;
         if ((FIRST ? nseg == 0 : true) && slot < cap) {
@@ -203,7 +203,7 @@ k_span_place(const __grid_constant__ DrawParams p, const __grid_constant__ WorkB
             }
         } else {  // the scanline crosses tile columns: walk it again, writing every segment
             const RowSetup r = load_setup(wb.recs + s.rec);
-            const int y = (int)(key / (uint32_t)p.tiles_x) * TILE_H + (int)s.yt;
+            const int y = (int)(key / (uint32_t)p.tiles_x) * p.tile_h + (int)s.yt;
             walk_row<false>(p, r, s.rec, y, nullptr, wb.segv, wb.seg_key[0], wb.seg_val[0], base, wb.cap_segs, &dummy);
         }
     }
