@@ -254,17 +254,17 @@ def main():
         return {"geometry_ms": st.geometry_ms / st.draws, "spans_ms": st.spans_ms / st.draws,
                 "sort_ms": st.sort_ms / st.draws, "raster_ms": st.raster_ms / st.draws}
     stages = stage_ms(r1["stage"])
-    # Dominant kernel: k_tile (the `raster` timer brackets exactly that one launch; the other stages are
-    # several kernels each -- their per-kernel times are in profiles/).  Its algorithmic bytes
-    # (DESIGN.md section 7): the normal planes of the triangles (T*72 B; positions belong to the geometry
-    # stage) plus the framebuffer written once (W*H*12 B).
-    tile_bytes = T_TRIANGLES * 72 + W1 * H1 * 12
+    # Dominant kernel: k_geometry (the largest single launch of the frame in the ncu launch list,
+    # profiles/r01_launch_table_v3_final.txt; the `geometry` timer brackets exactly that launch -- the
+    # other stages are several kernels each).  Its algorithmic bytes: the position
+    # planes, T * 72 B, read once (the records it writes are implementation, not algorithm).
+    geo_bytes = T_TRIANGLES * 72
     roofline = {
-        "bound": "hbm", "kernel": "k_tile<deferred>",
-        "achieved": tile_bytes / (stages["raster_ms"] / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": tile_bytes / (stages["raster_ms"] / 1e3) / 1e9 / hbm_peak,
-        "traffic": 105698560,   # dram__bytes_read+write of one k_tile launch, profiles/r01_ncu_k_tile_v2.txt
-        "peak_source": peak_src, "algorithmic_bytes": tile_bytes,
+        "bound": "hbm", "kernel": "k_geometry",
+        "achieved": geo_bytes / (stages["geometry_ms"] / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": geo_bytes / (stages["geometry_ms"] / 1e3) / 1e9 / hbm_peak,
+        "traffic": 116287488,   # dram__bytes_read+write of one k_geometry launch, profiles/r01_ncu_v3_geometry_spans_sort.txt
+        "peak_source": peak_src, "algorithmic_bytes": geo_bytes,
         "frame": {"algorithmic_bytes": ALGO_BYTES_C1, "achieved": ALGO_BYTES_C1 / (ms1 / 1e3) / 1e9,
                   "frac": ALGO_BYTES_C1 / (ms1 / 1e3) / 1e9 / hbm_peak},
         "stages_ms": stages,
