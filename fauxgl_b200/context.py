@@ -19,7 +19,8 @@ import numpy as np
 
 from .color import Color, Transparent
 from .matrix import Identity, Matrix
-from .mesh import Mesh
+from .mesh import Box, Mesh
+from .vector import Vector
 from .shader import (SHADER_PHONG, SHADER_SOLID, SHADER_TEXTURE, ImageTexture, PhongShader,
                      SolidColorShader, TextureShader)
 
@@ -94,6 +95,8 @@ ABI = [
     ("fgl_clear_depth", C.c_int, [_P, C.c_double]),
     ("fgl_mesh_create", C.c_int, [_P, C.POINTER(_MeshDesc), C.POINTER(_P)]),
     ("fgl_mesh_update", C.c_int, [_P, _P, C.POINTER(_MeshDesc)]),
+    ("fgl_mesh_create_stl", C.c_int, [_P, _P, C.c_uint64, C.POINTER(_P)]),
+    ("fgl_mesh_bounds", C.c_int, [_P, _P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("fgl_mesh_destroy", C.c_int, [_P]),
     ("fgl_mesh_counts", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("fgl_mesh_transform", C.c_int, [_P, _P, C.POINTER(C.c_double)]),
@@ -102,6 +105,8 @@ ABI = [
     ("fgl_texture_destroy", C.c_int, [_P]),
     ("fgl_draw_triangles", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64, C.POINTER(_Info)]),
     ("fgl_draw_lines", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64, C.POINTER(_Info)]),
+    ("fgl_draw_triangles_each", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64, _P, C.POINTER(_Info)]),
+    ("fgl_draw_lines_each", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64, _P, C.POINTER(_Info)]),
     ("fgl_draw_triangles_async", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64]),
     ("fgl_draw_lines_async", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64]),
     ("fgl_sync", C.c_int, [_P, C.POINTER(_Info)]),
@@ -110,6 +115,7 @@ ABI = [
     ("fgl_get_stage_times", C.c_int, [_P, C.POINTER(StageTimes)]),
     ("fgl_read_color", C.c_int, [_P, _P, C.c_size_t]),
     ("fgl_read_depth", C.c_int, [_P, _P]),
+    ("fgl_depth_image", C.c_int, [_P, _P]),
     ("fgl_write_color", C.c_int, [_P, _P, C.c_size_t]),
     ("fgl_write_depth", C.c_int, [_P, _P]),
     ("fgl_resolve", C.c_int, [_P, C.c_int, _P]),
@@ -178,6 +184,52 @@ class DeviceMesh:
         self.handle = _P()
         _check(capi().fgl_mesh_create(ctx._h, C.byref(d), C.byref(self.handle)), ctx._h)
         self._fin = weakref.finalize(self, capi().fgl_mesh_destroy, self.handle)
+
+    @classmethod
+    def FromSTL(cls, ctx: "Context", source) -> "DeviceMesh":
+        """LoadSTL (stl.go:23-57) of a BINARY STL straight to the device layout: only the 50-byte
+        records cross PCIe (fgl_mesh_create_stl).  ``source`` is a path or the file's bytes."""
+        if isinstance(source, (str, os.PathLike)):
+            with open(source, "rb") as f:
+                source = f.read()
+        data = bytes(source)
+        count = int.from_bytes(data[80:84], "little") if len(data) >= 84 else -1
+        if count < 0 or len(data) != 84 + 50 * count:
+            raise FauxglError(-1, "not a binary STL (ASCII files go through mesh.LoadSTL)")
+        rec = np.frombuffer(data, dtype=np.uint8, count=50 * count, offset=84)
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.generation = 0
+        self.attributes = ("position", "normal")
+        self.num_triangles, self.num_lines = count, 0
+        self.handle = _P()
+        _check(capi().fgl_mesh_create_stl(ctx._h, rec.ctypes.data if count else None, count, C.byref(self.handle)), ctx._h)
+        self._fin = weakref.finalize(self, capi().fgl_mesh_destroy, self.handle)
+        return self
+
+    def BoundingBox(self) -> Box:
+        """Mesh.BoundingBox (mesh.go:153-165) of the device copy."""
+        mn, mx = (C.c_double * 3)(), (C.c_double * 3)()
+        _check(capi().fgl_mesh_bounds(self.ctx._h, self.handle, mn, mx), self.ctx._h)
+        return Box(Vector(*mn), Vector(*mx))
+
+    def FitInside(self, box: Box, anchor: Vector) -> Matrix:
+        """Mesh.FitInside (mesh.go:142-151) without the mesh leaving the device."""
+        bb = self.BoundingBox()
+        scale = box.Size().Div(bb.Size()).MinComponent()
+        extra = box.Size().Sub(bb.Size().MulScalar(scale))
+        matrix = Identity()
+        matrix = matrix.Translate(bb.Min.Negate())
+        matrix = matrix.Scale(Vector(scale, scale, scale))
+        matrix = matrix.Translate(box.Min.Add(extra.Mul(anchor)))
+        self.Transform(matrix)
+        return matrix
+
+    def BiUnitCube(self) -> Matrix:  # mesh.go:127-130
+        return self.FitInside(Box(Vector(-1.0, -1.0, -1.0), Vector(1.0, 1.0, 1.0)), Vector(0.5, 0.5, 0.5))
+
+    def UnitCube(self) -> Matrix:  # mesh.go:122-125
+        return self.FitInside(Box(Vector(-0.5, -0.5, -0.5), Vector(0.5, 0.5, 0.5)), Vector(0.5, 0.5, 0.5))
 
     def update(self, mesh: Mesh, attributes=None):
         """fgl_mesh_update: re-upload (a subset of) the attributes into the same device buffers."""
@@ -279,6 +331,12 @@ class Context:
         _check(capi().fgl_read_depth(self._h, out.ctypes.data), self._h)
         return out
 
+    def DepthImage(self) -> np.ndarray:
+        """context.go:87-117: the depth buffer as a Gray16 image, (H,W) uint16, normalised on the device."""
+        out = np.empty((self.Height, self.Width), dtype=np.uint16)
+        _check(capi().fgl_depth_image(self._h, out.ctypes.data), self._h)
+        return out
+
     def UploadColorBuffer(self, pix: np.ndarray):
         pix = np.ascontiguousarray(pix, dtype=np.uint8)
         assert pix.shape == (self.Height, self.Width, 4)
@@ -364,6 +422,27 @@ class Context:
         st, sh = self._state(), self._shader()
         _check(capi().fgl_draw_lines(self._h, C.byref(st), C.byref(sh), dm.handle, first, count, C.byref(info)), self._h)
         return RasterizeInfo(info.total_pixels, info.updated_pixels)
+
+    def _draw_each(self, fn, dm, first, count):
+        infos = np.zeros((count, 2), dtype=np.uint64)
+        info = _Info()
+        st, sh = self._state(), self._shader()
+        _check(fn(self._h, C.byref(st), C.byref(sh), dm.handle, first, count, infos.ctypes.data if count else None,
+                  C.byref(info)), self._h)
+        return infos
+
+    def DrawLinesEach(self, mesh, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """One (TotalPixels, UpdatedPixels) row per line, as if each were drawn with Context.DrawLine
+        (context.go:351-368) in index order -- examples/silhouette.go:163-166 -- in one launch sequence."""
+        dm = self.device_mesh(mesh)
+        count = dm.num_lines - first if count is None else count
+        return self._draw_each(capi().fgl_draw_lines_each, dm, first, count)
+
+    def DrawTrianglesEach(self, mesh, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """One (TotalPixels, UpdatedPixels) row per triangle (Context.DrawTriangle, context.go:370-389)."""
+        dm = self.device_mesh(mesh)
+        count = dm.num_triangles - first if count is None else count
+        return self._draw_each(capi().fgl_draw_triangles_each, dm, first, count)
 
     def DrawMesh(self, mesh) -> RasterizeInfo:  # context.go:435
         info1 = self.DrawTriangles(mesh)

@@ -66,6 +66,10 @@ struct fgl_ctx {
     DrawCounters *host_counters;       // pinned
     DrawCounters *acc_dev;             // async accumulation (total/updated/overflow)
     bool async_pending;
+    unsigned long long *prim_info;     // per-primitive RasterizeInfo of fgl_draw_*_each, [prim_info_cap][2]
+    uint64_t prim_info_cap;
+    unsigned long long *scratch;       // 8 words: reductions of fgl_mesh_bounds / fgl_depth_image
+    uint16_t *gray16;                  // DepthImage staging, allocated on first use
     fgl_draw_stats stats;
     // per-stage profiling (fgl_set_profiling)
     bool profiling;
@@ -274,6 +278,7 @@ int enqueue_draw(fgl_ctx *c, const DrawParams &p) {
         ps = &c->prof[c->prof_used++];
         cudaEventRecord(ps->e[0], c->stream);
     }
+    if (p.prim_info) cudaMemsetAsync(p.prim_info, 0, sizeof(unsigned long long) * 2 * p.count, c->stream);
     launches += launch_geometry(p, c->wb, c->stream);
     if (ps) cudaEventRecord(ps->e[1], c->stream);
     int sorted = 0;
@@ -304,7 +309,8 @@ int initial_capacity(fgl_ctx *c, const DrawParams &p) {
 }
 
 int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const fgl_mesh *mesh, uint64_t first,
-                uint64_t count, bool lines, bool async, fgl_raster_info *info) {
+                uint64_t count, bool lines, bool async, fgl_raster_info *info, fgl_raster_info *each = nullptr,
+                bool want_each = false) {
     int rc = check_ctx(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(c->mu);
@@ -314,7 +320,18 @@ int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const 
     if (rc) return rc;
     c->stats.prims_in = count;
     c->stats.retries = 0;
+    if (want_each && !each && count) return fail(c, FGL_E_INVALID, "null per-primitive info array");
     if (count == 0) return FGL_OK;
+    if (want_each) {
+        static_assert(sizeof(fgl_raster_info) == 2 * sizeof(unsigned long long), "fgl_raster_info layout");
+        if (count > c->prim_info_cap) {
+            dev_free(c->prim_info);
+            c->prim_info_cap = 0;
+            CK(c, dev_alloc(&c->prim_info, (size_t)count * 2));
+            c->prim_info_cap = count;
+        }
+        p.prim_info = c->prim_info;
+    }
     if (p.deferred && !c->wb.vis_winner) {  // visibility buffer of the deferred-shading path, tile-major
         const size_t npx = (size_t)c->wb.ntiles * TILE_W * c->tile_h;
         CK(c, dev_alloc(&c->wb.vis_winner, npx));
@@ -336,6 +353,10 @@ int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const 
         CK(c, cudaStreamSynchronize(c->stream));
         const DrawCounters &hc = *c->host_counters;
         if (!hc.overflow) {
+            if (p.prim_info) {
+                CK(c, cudaMemcpyAsync(each, p.prim_info, sizeof(fgl_raster_info) * count, cudaMemcpyDeviceToHost, c->stream));
+                CK(c, cudaStreamSynchronize(c->stream));
+            }
             if (info) { info->total_pixels = hc.total_pixels; info->updated_pixels = hc.updated_pixels; }
             c->stats.records = hc.n_records; c->stats.pairs = hc.n_segs; c->stats.clip_triangles = hc.n_clip;
             return FGL_OK;
@@ -387,6 +408,7 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     memset(&c->wb, 0, sizeof c->wb);
     memset(&c->stats, 0, sizeof c->stats);
     c->host_counters = nullptr; c->acc_dev = nullptr; c->async_pending = false;
+    c->prim_info = nullptr; c->prim_info_cap = 0; c->scratch = nullptr; c->gray16 = nullptr;
     c->profiling = false; c->prof_used = 0; c->prof_created = false;
     memset(&c->prof_acc, 0, sizeof c->prof_acc);
     const size_t npix = (size_t)width * height;
@@ -395,6 +417,7 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     if (err == cudaSuccess) err = dev_alloc(&c->depth, npix);
     if (err == cudaSuccess) err = dev_alloc(&c->wb.counters, 1);
     if (err == cudaSuccess) err = dev_alloc(&c->acc_dev, 1);
+    if (err == cudaSuccess) err = dev_alloc(&c->scratch, 8);
     if (err == cudaSuccess) err = cudaMallocHost(reinterpret_cast<void **>(&c->host_counters), sizeof(DrawCounters));
     {   // short tiles split dense regions over more CTAs; keep the tile id within 16 bits (two radix passes)
         const int tx = (width + TILE_W - 1) / TILE_W;
@@ -443,6 +466,7 @@ int fgl_context_destroy(fgl_ctx *c) {
     free_work(c->wb);
     dev_free(c->wb.tile_start); dev_free(c->wb.tile_end); dev_free(c->wb.counters); dev_free(c->wb.tile_clock);
     dev_free(c->wb.busy_list); dev_free(c->wb.tile_claimed); dev_free(c->wb.tile_ctl); dev_free(c->wb.vis_winner); dev_free(c->wb.vis_w);
+    dev_free(c->prim_info); dev_free(c->scratch); dev_free(c->gray16);
     dev_free(c->acc_dev); dev_free(c->color); dev_free(c->depth); dev_free(c->resolved);
     if (c->host_counters) cudaFreeHost(c->host_counters);
     if (c->prof_created)
@@ -552,6 +576,70 @@ int fgl_mesh_update(fgl_ctx *c, fgl_mesh *m, const fgl_mesh_desc *d) {
     return upload_all(c, m, d, false);
 }
 
+int fgl_mesh_create_stl(fgl_ctx *c, const uint8_t *records, uint64_t count, fgl_mesh **out) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!out || (count && !records)) return fail(c, FGL_E_INVALID, "null STL records/out pointer");
+    *out = nullptr;
+    if (count > 0xfffffff0ull) return fail(c, FGL_E_INVALID, "mesh too large");
+    std::lock_guard<std::mutex> lock(c->mu);
+    fgl_mesh *m = new (std::nothrow) fgl_mesh();
+    if (!m) return fail(c, FGL_E_OOM, "host allocation failed");
+    memset(m, 0, sizeof *m);
+    m->device = c->device; m->nt = count; m->nl = 0;
+    m->staging_elems = (size_t)m->nt * (9 * 3 + 12);  // 312 B per triangle: also holds the 50-byte records (+ padding)
+    cudaError_t e = dev_alloc(&m->staging, m->staging_elems);
+    if (e == cudaSuccess) e = dev_alloc(&m->tpos, (size_t)count * 9);
+    if (e == cudaSuccess) e = dev_alloc(&m->tnrm, (size_t)count * 9);
+    if (e == cudaSuccess) e = dev_alloc(&m->ttex, (size_t)count * 6);
+    if (e == cudaSuccess) e = dev_alloc(&m->tcol, (size_t)count * 12);
+    if (e == cudaSuccess) e = dev_alloc(&m->lpos, 1);
+    if (e == cudaSuccess) e = dev_alloc(&m->lnrm, 1);
+    if (e == cudaSuccess) e = dev_alloc(&m->ltex, 1);
+    if (e == cudaSuccess) e = dev_alloc(&m->lcol, 1);
+    if (e == cudaSuccess && count) {
+        e = cudaMemcpyAsync(m->staging, records, (size_t)count * 50, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(m->ttex, 0, sizeof(double) * count * 6, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(m->tcol, 0, sizeof(double) * count * 12, c->stream);
+        if (e == cudaSuccess) {
+            launch_stl_ingest(reinterpret_cast<const uint8_t *>(m->staging), m->tpos, m->tnrm, (uint32_t)count, c->stream);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // the caller may free `records`
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fgl_mesh_destroy(m);
+        return fail(c, e == cudaErrorMemoryAllocation ? FGL_E_OOM : FGL_E_CUDA, "STL upload: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return FGL_OK;
+}
+
+int fgl_mesh_bounds(fgl_ctx *c, const fgl_mesh *m, double mn[3], double mx[3]) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!m || !mn || !mx) return fail(c, FGL_E_INVALID, "null mesh/out pointer");
+    if (m->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on another device");
+    std::lock_guard<std::mutex> lock(c->mu);
+    unsigned long long h[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
+    CK(c, cudaMemcpyAsync(c->scratch, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+    launch_mesh_bounds(m->tpos, (uint32_t)m->nt, 3, c->scratch, c->stream);
+    launch_mesh_bounds(m->lpos, (uint32_t)m->nl, 2, c->scratch, c->stream);
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(h, c->scratch, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 3; k++) {
+        if (h[k] == ~0ull || h[3 + k] == 0ull) { mn[k] = 0; mx[k] = 0; continue; }  // EmptyBox
+        for (int e = 0; e < 2; e++) {
+            const unsigned long long key = h[3 * e + k];
+            const unsigned long long bits = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
+            memcpy(e ? &mx[k] : &mn[k], &bits, sizeof bits);
+        }
+    }
+    return FGL_OK;
+}
+
 int fgl_mesh_destroy(fgl_mesh *m) {
     if (!m) return FGL_OK;
     cudaSetDevice(m->device);
@@ -649,6 +737,14 @@ int fgl_draw_lines(fgl_ctx *c, const fgl_state *s, const fgl_shader *sh, const f
                    uint64_t count, fgl_raster_info *info) {
     return draw_common(c, s, sh, m, first, count, true, false, info);
 }
+int fgl_draw_triangles_each(fgl_ctx *c, const fgl_state *s, const fgl_shader *sh, const fgl_mesh *m, uint64_t first,
+                            uint64_t count, fgl_raster_info *infos, fgl_raster_info *info) {
+    return draw_common(c, s, sh, m, first, count, false, false, info, infos, true);
+}
+int fgl_draw_lines_each(fgl_ctx *c, const fgl_state *s, const fgl_shader *sh, const fgl_mesh *m, uint64_t first,
+                        uint64_t count, fgl_raster_info *infos, fgl_raster_info *info) {
+    return draw_common(c, s, sh, m, first, count, true, false, info, infos, true);
+}
 int fgl_draw_triangles_async(fgl_ctx *c, const fgl_state *s, const fgl_shader *sh, const fgl_mesh *m, uint64_t first,
                              uint64_t count) {
     return draw_common(c, s, sh, m, first, count, false, true, nullptr);
@@ -734,6 +830,20 @@ int fgl_read_depth(fgl_ctx *c, double *dst) {
     CK(c, cudaStreamSynchronize(c->stream));
     return FGL_OK;
 }
+int fgl_depth_image(fgl_ctx *c, uint16_t *dst) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!dst) return fail(c, FGL_E_INVALID, "null destination");
+    std::lock_guard<std::mutex> lock(c->mu);
+    const size_t npix = (size_t)c->w * c->h;
+    if (!c->gray16) CK(c, dev_alloc(&c->gray16, npix));
+    launch_depth_image(c->depth, npix, c->gray16, c->scratch, c->stream);
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(dst, c->gray16, npix * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return FGL_OK;
+}
+
 int fgl_write_color(fgl_ctx *c, const uint8_t *src, size_t stride) {
     int rc = check_ctx(c);
     if (rc) return rc;

@@ -158,7 +158,7 @@ struct CountEmit {
         n++;
         rows += bb.rows;
     }
-    FGL_DI uint32_t pool_alloc(const FullVertex *) { return 0; }
+    FGL_DI uint32_t pool_alloc(const FullVertex *, uint32_t) { return 0; }
 };
 struct WriteEmit {
     uint32_t next, row_next;
@@ -172,7 +172,7 @@ struct WriteEmit {
         next++;
         row_next += b.rows;
     }
-    FGL_DI uint32_t pool_alloc(const FullVertex *v) {
+    FGL_DI uint32_t pool_alloc(const FullVertex *v, uint32_t prim) {
         const uint32_t slot = atomicAdd(&wb->counters->n_clip, 1u);
         if (slot >= wb->cap_clip) { atomicOr(&wb->counters->overflow, OVF_CLIP); return 0; }
         ClipTri t;
@@ -183,6 +183,7 @@ struct WriteEmit {
             t.v[k].tex[0] = v[k].tu; t.v[k].tex[1] = v[k].tv;
             t.v[k].col[0] = v[k].col.r; t.v[k].col[1] = v[k].col.g; t.v[k].col[2] = v[k].col.b; t.v[k].col[3] = v[k].col.a;
         }
+        t.prim = prim; t._pad = 0;
         wb->clip_pool[slot] = t;
         return slot;
     }
@@ -352,7 +353,7 @@ __device__ __noinline__ void clip_and_emit(const DrawParams &p, Emit &e, uint32_
             CountEmit probe{0};
             emit_clipped_triangle(p, probe, oo, 0, 0);
             if (probe.n == 0) continue;
-            const uint32_t slot = e.pool_alloc(nv);
+            const uint32_t slot = e.pool_alloc(nv, prim);
             emit_clipped_triangle(p, e, oo, slot, REC_SRC_POOL);
         } else {
             emit_clipped_triangle(p, e, oo, 0, REC_SRC_POOL);

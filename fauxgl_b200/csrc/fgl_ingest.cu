@@ -1,0 +1,150 @@
+// fgl_ingest.cu -- data formats either side of the draw, handled on the device so that only
+// the compact form crosses PCIe: binary STL records -> planar f64 mesh (stl.go:86-154),
+// Mesh.BoundingBox (mesh.go:153-165) and Context.DepthImage (context.go:87-117).
+#include "fgl_internal.h"
+#include "fgl_math.cuh"
+
+namespace fgl {
+
+// Order-preserving map of an IEEE double onto uint64 (all non-NaN values, -0 < +0), so that
+// minima / maxima can be taken with integer atomics.
+FGL_DI unsigned long long ord_key(double d) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+FGL_DI double ord_value(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+FGL_DI unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_down_sync(0xffffffffu, v, o);
+        v = t < v ? t : v;
+    }
+    return v;
+}
+FGL_DI unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_down_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+// ---- binary STL -> planes ---------------------------------------------------------------------
+// A record is 50 bytes: normal (3 x f32, ignored by the loader), 3 vertices (9 x f32), 2 attribute
+// bytes.  A CTA stages 256 records (12 800 contiguous bytes) in shared memory with word loads,
+// then one thread per triangle widens the positions (makeFloat, stl.go:82-84) and computes the
+// face normal Triangle.Normal(), triangle.go:33-37, which the loader stores in all three vertices.
+constexpr int STL_T = 256;
+__global__ void __launch_bounds__(STL_T)
+k_stl_ingest(const uint8_t *__restrict__ rec, double *__restrict__ pos, double *__restrict__ nrm, uint32_t n) {
+    __shared__ uint32_t s_words[STL_T * 50 / 4];
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t b0 = blockIdx.x * STL_T; b0 < n; b0 += gridDim.x * STL_T) {
+        const uint32_t cnt = min((uint32_t)STL_T, n - b0);
+        const uint32_t nwords = (cnt * 50 + 3) / 4;  // the staging buffer is padded to a word
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(rec + (size_t)b0 * 50);
+        __syncthreads();
+        for (uint32_t w = tid; w < nwords; w += STL_T) s_words[w] = src[w];
+        __syncthreads();
+        if (tid < cnt) {
+            const uint16_t *h = reinterpret_cast<const uint16_t *>(s_words) + tid * 25 + 6;  // byte 50*tid + 12
+            double f[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++)
+                f[k] = (double)__uint_as_float((uint32_t)h[2 * k] | ((uint32_t)h[2 * k + 1] << 16));
+            const V3 v1 = v3(f[0], f[1], f[2]), v2 = v3(f[3], f[4], f[5]), v3_ = v3(f[6], f[7], f[8]);
+            const V3 nn = v_normalize(v_cross(v_sub(v2, v1), v_sub(v3_, v1)));
+            const size_t i = b0 + tid;
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+                pos[(size_t)(v * 3 + 0) * n + i] = f[v * 3 + 0];
+                pos[(size_t)(v * 3 + 1) * n + i] = f[v * 3 + 1];
+                pos[(size_t)(v * 3 + 2) * n + i] = f[v * 3 + 2];
+                nrm[(size_t)(v * 3 + 0) * n + i] = nn.x;
+                nrm[(size_t)(v * 3 + 1) * n + i] = nn.y;
+                nrm[(size_t)(v * 3 + 2) * n + i] = nn.z;
+            }
+        }
+    }
+}
+int launch_stl_ingest(const uint8_t *records, double *pos, double *nrm, uint32_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    const uint32_t blocks = (n + STL_T - 1) / STL_T;
+    k_stl_ingest<<<blocks < 148u * 8u ? blocks : 148u * 8u, STL_T, 0, st>>>(records, pos, nrm, n);
+    return 1;
+}
+
+// ---- bounding box -----------------------------------------------------------------------------
+// bounds[c] = min key of component c, bounds[3 + c] = max key; the caller initialises them to
+// ~0 / 0 and decodes with ord_value on the host side of the ABI (same bit trick).
+__global__ void k_mesh_bounds(const double *__restrict__ pos, uint32_t n, int nverts, unsigned long long *bounds) {
+    unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0ull, 0ull, 0ull};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        for (int v = 0; v < nverts; v++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double d = pos[(size_t)(v * 3 + c) * n + i];
+                if (d != d) continue;
+                const unsigned long long k = ord_key(d);
+                lo[c] = k < lo[c] ? k : lo[c];
+                hi[c] = k > hi[c] ? k : hi[c];
+            }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const unsigned long long a = warp_min_u64(lo[c]), b = warp_max_u64(hi[c]);
+        if ((threadIdx.x & 31) == 0) {
+            if (a != ~0ull) atomicMin(&bounds[c], a);
+            if (b != 0ull) atomicMax(&bounds[3 + c], b);
+        }
+    }
+}
+int launch_mesh_bounds(const double *pos, uint32_t n, int nverts, unsigned long long *bounds, cudaStream_t st) {
+    if (n == 0) return 0;
+    const uint32_t blocks = (n + 255) / 256;
+    k_mesh_bounds<<<blocks < 148u * 8u ? blocks : 148u * 8u, 256, 0, st>>>(pos, n, nverts, bounds);
+    return 1;
+}
+
+// ---- DepthImage, context.go:87-117 --------------------------------------------------------------
+constexpr double GO_MAX_FLOAT64 = 1.7976931348623157e308;
+__global__ void k_depth_range(const double *__restrict__ depth, size_t npix, unsigned long long *range) {
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        const double d = depth[i];
+        if (d == GO_MAX_FLOAT64 || d != d) continue;  // :91-93; a NaN never passes `d < lo` / `d > hi`
+        const unsigned long long k = ord_key(d);
+        lo = k < lo ? k : lo;
+        hi = k > hi ? k : hi;
+    }
+    lo = warp_min_u64(lo);
+    hi = warp_max_u64(hi);
+    if ((threadIdx.x & 31) == 0) {
+        if (lo != ~0ull) atomicMin(&range[0], lo);
+        if (hi != 0ull) atomicMax(&range[1], hi);
+    }
+}
+__global__ void k_depth_gray16(const double *__restrict__ depth, size_t npix, const unsigned long long *range,
+                               uint16_t *__restrict__ out) {
+    const double lo = range[0] == ~0ull ? GO_MAX_FLOAT64 : ord_value(range[0]);   // :88
+    const double hi = range[1] == 0ull ? -GO_MAX_FLOAT64 : ord_value(range[1]);   // :89
+    const double span = hi - lo;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        const double d = depth[i];
+        double t = (d - lo) / span;               // :107
+        if (d == GO_MAX_FLOAT64) t = 1;           // :108-110
+        out[i] = (uint16_t)(go_int(t * 65535.0) & 0xffff);  // uint16(t * 0xffff), :111
+    }
+}
+int launch_depth_image(const double *depth, size_t npix, uint16_t *out, unsigned long long *scratch, cudaStream_t st) {
+    static const unsigned long long init[2] = {~0ull, 0ull};
+    cudaMemcpyAsync(scratch, init, sizeof init, cudaMemcpyHostToDevice, st);
+    k_depth_range<<<148 * 8, 256, 0, st>>>(depth, npix, scratch);
+    k_depth_gray16<<<148 * 8, 256, 0, st>>>(depth, npix, scratch, out);
+    return 2;
+}
+
+}  // namespace fgl

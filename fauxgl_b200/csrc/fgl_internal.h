@@ -55,7 +55,10 @@ constexpr uint32_t REC_SRC_POOL = 1u << 6;  // src indexes the clip pool
 struct ClipVertex {
     double pos[3], nrm[3], tex[2], col[4];
 };
-struct ClipTri { ClipVertex v[3]; };
+struct ClipTri {
+    ClipVertex v[3];
+    uint32_t prim, _pad;  // mesh primitive the triangle was clipped from (per-primitive RasterizeInfo)
+};
 
 // ---- span segment: the covered pixels of one scanline of one triangle inside one
 // tile, with the forward-differenced edge values at its first pixel.
@@ -109,6 +112,8 @@ struct DrawParams {
     uint32_t first, count;  // primitive range
     int32_t is_lines;
     int32_t deferred;       // 1: shading cannot discard or blend -> resolve depth in order, shade final winners
+    // per-primitive RasterizeInfo (fgl_draw_*_each): [count][2] = (TotalPixels, UpdatedPixels); null otherwise
+    unsigned long long *prim_info;
 };
 
 // Device-side counters/results of one draw (also copied to pinned host memory).
@@ -150,6 +155,15 @@ struct WorkBuffers {
     uint32_t cap_prims, cap_records, cap_rows, cap_segs, cap_clip, ntiles, scan_tmp_words;
 };
 
+#ifdef __CUDACC__
+// Index (relative to the draw's first primitive) of the mesh primitive a record came from.
+__device__ __forceinline__ uint32_t rec_primitive(const WorkBuffers &wb, const DrawParams &p, uint32_t rec) {
+    const Rec *rp = wb.recs + rec;
+    const uint32_t src = rp->src;
+    return ((rp->flags & REC_SRC_POOL) ? wb.clip_pool[src].prim : src) - p.first;
+}
+#endif
+
 // ---- kernel launchers (each returns the number of kernels it launched) --------------
 int launch_mesh_ingest(const double *aos, double *planes, uint32_t n, int nverts, int ncomp_in, int ncomp_out,
                        cudaStream_t st);
@@ -183,6 +197,12 @@ int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cuda
 int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,
                   cudaStream_t st);
 
+// binary STL records (50 B each) -> position / normal planes, stl.go:86-154
+int launch_stl_ingest(const uint8_t *records, double *pos, double *nrm, uint32_t n, cudaStream_t st);
+// bounding box of position planes: bounds[0..2] = ordered-u64 min, [3..5] = max (see fgl_post.cu)
+int launch_mesh_bounds(const double *pos, uint32_t n, int nverts, unsigned long long *bounds, cudaStream_t st);
+// DepthImage, context.go:87-117; scratch = 2 x u64
+int launch_depth_image(const double *depth, size_t npix, uint16_t *out, unsigned long long *scratch, cudaStream_t st);
 int launch_resolve(const uint32_t *src, int sw, int sh, uint32_t *dst, int factor, cudaStream_t st);
 int launch_composite_pack(const uint32_t *color, const double *depth, unsigned long long *keys, size_t npix,
                           cudaStream_t st);

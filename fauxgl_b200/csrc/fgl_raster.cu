@@ -95,7 +95,8 @@ FGL_DI void fragment_inline(const DrawParams &p, const fgl_state &st, const Work
     }
 }
 
-template <bool DEFERRED>
+// EACH: also attribute UpdatedPixels to the primitive of every segment (fgl_draw_*_each).
+template <bool DEFERRED, bool EACH>
 __global__ void __launch_bounds__(RT, 3)
 k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb,
        const uint32_t *__restrict__ seg_order, uint32_t *__restrict__ gcolor, double *__restrict__ gdepth) {
@@ -198,6 +199,7 @@ k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers
                 __syncthreads();
                 if (pend) {
                     double w0 = v.w0, w1 = v.w1, w2 = v.w2;
+                    const unsigned long long updated_before = my_updated;
                     for (int x = xa; x < xa + cnt; x++) {
                         const unsigned long long bitm = 1ull << (x - tile_x0);
                         const int pi = rowbase + x;
@@ -224,6 +226,8 @@ k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers
                         }
                         w0 += v.a12; w1 += v.a20; w2 += v.a01;  // context.go:211-213
                     }
+                    if (EACH && my_updated != updated_before)
+                        atomicAdd(&p.prim_info[2 * (size_t)rec_primitive(wb, p, v.rec) + 1], my_updated - updated_before);
                 }
                 if (!__syncthreads_or(pend != 0)) break;
             }
@@ -354,8 +358,9 @@ static size_t tile_smem(bool deferred) {
 
 int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,
                   cudaStream_t st) {
-    cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(true));
-    cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(false));
+    auto tile_kernel = p.deferred ? (p.prim_info ? k_tile<true, true> : k_tile<true, false>)
+                                  : (p.prim_info ? k_tile<false, true> : k_tile<false, false>);
+    cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(p.deferred));
     int launches = 0;
     cudaMemsetAsync(wb.tile_ctl, 0, sizeof(TileCtl), st);
     cudaMemsetAsync(wb.tile_claimed, 0, sizeof(uint32_t) * wb.ntiles, st);
@@ -364,14 +369,14 @@ int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, ui
     launches += 2;
     const uint32_t grid = wb.ntiles < 148u * 4u ? wb.ntiles : 148u * 4u;
     if (p.deferred) {
-        k_tile<true><<<grid, RT, tile_smem(true), st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
+        tile_kernel<<<grid, RT, tile_smem(true), st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
         launches++;
         if (p.state.write_color) {
             k_shade<<<148 * 4, RT, 0, st>>>(p, wb, color);
             launches++;
         }
     } else {
-        k_tile<false><<<grid, RT, tile_smem(false), st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
+        tile_kernel<<<grid, RT, tile_smem(false), st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
         launches++;
     }
     return launches;

@@ -171,7 +171,10 @@ k_span_walk(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBu
             const uint32_t rid = r0 + lo;
             const RowSetup r = load_setup(wb.recs + rid);
             const int y = max(r.y0, 0) + (int)(i - s_off[lo]);
+            const unsigned long long before = covered;
             wb.row_nseg[i] = walk_row<true>(p, r, rid, y, wb.row_first, nullptr, wb.row_key, nullptr, i, wb.cap_rows, &covered);
+            if (p.prim_info && covered != before)  // per-primitive TotalPixels (fgl_draw_*_each)
+                atomicAdd(&p.prim_info[2 * (size_t)rec_primitive(wb, p, rid)], covered - before);
         }
     }
     // TotalPixels, context.go:229: every covered in-range pixel, before any depth test

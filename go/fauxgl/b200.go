@@ -106,6 +106,10 @@ func (d *deviceContext) writeDepth(depth []float64) error {
 	return lastError(d.h, C.fgl_write_depth(d.h, (*C.double)(unsafe.Pointer(&depth[0]))))
 }
 
+func (d *deviceContext) depthImage(dst []uint16) error {
+	return lastError(d.h, C.fgl_depth_image(d.h, (*C.uint16_t)(unsafe.Pointer(&dst[0]))))
+}
+
 func (d *deviceContext) resolve(factor int, dst []uint8) error {
 	return lastError(d.h, C.fgl_resolve(d.h, C.int(factor), (*C.uint8_t)(unsafe.Pointer(&dst[0]))))
 }
@@ -285,4 +289,18 @@ func (d *deviceContext) drawLines(st stateDesc, sh shaderDesc, m *deviceMesh, fi
 	var info C.fgl_raster_info
 	rc := C.fgl_draw_lines(d.h, &cst, &csh, m.h, C.uint64_t(first), C.uint64_t(count), &info)
 	return RasterizeInfo{uint64(info.total_pixels), uint64(info.updated_pixels)}, lastError(d.h, rc)
+}
+
+// drawEach fills out[i] with the RasterizeInfo of primitive i (RasterizeInfo is two
+// uint64, the layout of fgl_raster_info).
+func (d *deviceContext) drawEach(st stateDesc, sh shaderDesc, m *deviceMesh, lines bool, out []RasterizeInfo) error {
+	cst, csh := st.c(), sh.c()
+	infos := (*C.fgl_raster_info)(unsafe.Pointer(&out[0]))
+	var rc C.int
+	if lines {
+		rc = C.fgl_draw_lines_each(d.h, &cst, &csh, m.h, 0, C.uint64_t(len(out)), infos, nil)
+	} else {
+		rc = C.fgl_draw_triangles_each(d.h, &cst, &csh, m.h, 0, C.uint64_t(len(out)), infos, nil)
+	}
+	return lastError(d.h, rc)
 }

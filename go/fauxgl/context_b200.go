@@ -33,7 +33,6 @@ package fauxgl
 import (
 	"errors"
 	"image"
-	"image/color"
 	"math"
 	"runtime"
 	"sync"
@@ -192,31 +191,22 @@ func (dc *Context) Image() image.Image {
 }
 
 func (dc *Context) DepthImage() image.Image {
-	dc.SyncBuffers()
-	lo := math.MaxFloat64
-	hi := -math.MaxFloat64
-	for _, d := range dc.DepthBuffer {
-		if d == math.MaxFloat64 {
-			continue
-		}
-		if d < lo {
-			lo = d
-		}
-		if d > hi {
-			hi = d
-		}
-	}
+	// normalised on the device (fgl_depth_image); only 2 bytes per pixel come back
+	dc.mu.Lock()
+	defer dc.mu.Unlock()
 	im := image.NewGray16(image.Rect(0, 0, dc.Width, dc.Height))
-	var i int
-	for y := 0; y < dc.Height; y++ {
-		for x := 0; x < dc.Width; x++ {
-			d := dc.DepthBuffer[i]
-			t := (d - lo) / (hi - lo)
-			if d == math.MaxFloat64 {
-				t = 1
-			}
-			im.SetGray16(x, y, color.Gray16{uint16(t * 0xffff)})
-			i++
+	if dc.dev == nil {
+		return im
+	}
+	{
+		gray := make([]uint16, dc.Width*dc.Height)
+		if err := dc.dev.depthImage(gray); err != nil {
+			dc.fail(err)
+			return im
+		}
+		for i, g := range gray { // Gray16.Pix is big-endian
+			im.Pix[2*i] = uint8(g >> 8)
+			im.Pix[2*i+1] = uint8(g)
 		}
 	}
 	return im
@@ -336,6 +326,45 @@ func (dc *Context) DrawLine(l *Line) RasterizeInfo {
 
 func (dc *Context) DrawMesh(mesh *Mesh) RasterizeInfo {
 	return dc.draw(mesh, true, true, false)
+}
+
+// DrawLinesEach returns what a loop of DrawLine over lines would return, one
+// RasterizeInfo per line in index order, from a single launch sequence
+// (examples/silhouette.go:163-166 tests each line's UpdatedPixels/TotalPixels).
+func (dc *Context) DrawLinesEach(lines []*Line) []RasterizeInfo {
+	return dc.drawEach(&Mesh{Lines: lines}, true)
+}
+
+// DrawTrianglesEach is the same for DrawTriangle.
+func (dc *Context) DrawTrianglesEach(triangles []*Triangle) []RasterizeInfo {
+	return dc.drawEach(&Mesh{Triangles: triangles}, false)
+}
+
+func (dc *Context) drawEach(mesh *Mesh, lines bool) []RasterizeInfo {
+	dc.mu.Lock()
+	defer dc.mu.Unlock()
+	n := len(mesh.Triangles)
+	if lines {
+		n = len(mesh.Lines)
+	}
+	result := make([]RasterizeInfo, n)
+	if dc.dev == nil || n == 0 {
+		return result
+	}
+	sh, err := dc.describeShader()
+	if err != nil {
+		dc.fail(err)
+		return result
+	}
+	dm, err := dc.dev.newMesh(mesh)
+	if err != nil {
+		dc.fail(err)
+		return result
+	}
+	defer dm.destroy()
+	dc.fail(dc.dev.drawEach(dc.state(), sh, dm, lines, result))
+	dc.hostOK = false
+	return result
 }
 
 func (dc *Context) draw(mesh *Mesh, tris, lines, temporary bool) RasterizeInfo {

@@ -223,6 +223,15 @@ class Context {
         check(fgl_read_depth(h_, out.data()), h_);
         return out;
     }
+    std::vector<uint16_t> DepthImage() {  // context.go:87-117, Gray16
+        std::vector<uint16_t> out((size_t)Width * Height);
+        check(fgl_depth_image(h_, out.data()), h_);
+        return out;
+    }
+    // One RasterizeInfo per line / triangle, as a loop of Context.DrawLine / DrawTriangle would return
+    // (context.go:351-389; examples/silhouette.go:163-166), in one launch sequence.
+    std::vector<RasterizeInfo> DrawLinesEach(const Mesh &mesh) { return draw_each(mesh, true); }
+    std::vector<RasterizeInfo> DrawTrianglesEach(const Mesh &mesh) { return draw_each(mesh, false); }
     std::vector<uint8_t> Resolve(int factor) {  // resize.Resize(w/f, h/f, Image(), resize.Bilinear)
         std::vector<uint8_t> out((size_t)(Width / factor) * (Height / factor) * 4);
         check(fgl_resolve(h_, factor, out.data()), h_);
@@ -231,13 +240,11 @@ class Context {
     fgl_ctx *handle() { return h_; }
 
   private:
-    RasterizeInfo draw(const Mesh &mesh, bool tris, bool lines) {
+    void setup(const Mesh &mesh, fgl_state &st, fgl_shader &sh) {
         if (mesh_src_ != &mesh || mesh_gen_ != mesh.generation) upload(mesh);
-        fgl_state st{};
         st.read_depth = ReadDepth; st.write_depth = WriteDepth; st.write_color = WriteColor;
         st.alpha_blend = AlphaBlend; st.wireframe = Wireframe; st.front_face = FrontFace; st.cull = cull;
         st.line_width = LineWidth; st.depth_bias = DepthBias;
-        fgl_shader sh{};
         sh.kind = shader.kind;
         std::memcpy(sh.matrix, shader.matrix.m, sizeof sh.matrix);
         auto p3 = [](double *d, Vector v) { d[0] = v.X; d[1] = v.Y; d[2] = v.Z; };
@@ -256,6 +263,11 @@ class Context {
             }
             sh.texture = tex_;
         }
+    }
+    RasterizeInfo draw(const Mesh &mesh, bool tris, bool lines) {
+        fgl_state st{};
+        fgl_shader sh{};
+        setup(mesh, st, sh);
         RasterizeInfo result;
         fgl_raster_info info{};
         if (tris && mesh.NumTriangles()) {
@@ -267,6 +279,17 @@ class Context {
             result = result.Add({info.total_pixels, info.updated_pixels});
         }
         return result;
+    }
+    std::vector<RasterizeInfo> draw_each(const Mesh &mesh, bool lines) {
+        fgl_state st{};
+        fgl_shader sh{};
+        setup(mesh, st, sh);
+        const size_t n = lines ? mesh.NumLines() : mesh.NumTriangles();
+        std::vector<fgl_raster_info> infos(n);
+        if (n) check((lines ? fgl_draw_lines_each : fgl_draw_triangles_each)(h_, &st, &sh, mesh_, 0, n, infos.data(), nullptr), h_);
+        std::vector<RasterizeInfo> out(n);
+        for (size_t i = 0; i < n; i++) out[i] = {infos[i].total_pixels, infos[i].updated_pixels};
+        return out;
     }
     void upload(const Mesh &mesh) {
         fgl_mesh_desc d{};

@@ -137,6 +137,16 @@ int fgl_mesh_transform(fgl_ctx *ctx, fgl_mesh *mesh, const double matrix[16]);
 int fgl_mesh_read(fgl_ctx *ctx, const fgl_mesh *mesh, double *position, double *normal,
                   double *lposition, double *lnormal);
 
+/* loadSTLB, stl.go:86-154, straight to the device layout: `records` are the `count` 50-byte
+ * triangle records of a binary STL file (everything after the 84-byte header).  Only these bytes
+ * cross PCIe; a kernel widens the float32 positions (makeFloat, stl.go:82-84) and gives every
+ * vertex the face normal Triangle.Normal() (triangle.go:33-37), as the loader does.  Texture
+ * coordinates and colours are zero. */
+int fgl_mesh_create_stl(fgl_ctx *ctx, const uint8_t *records, uint64_t count, fgl_mesh **out);
+/* Mesh.BoundingBox, mesh.go:153-165, of the device copy (triangles and lines).  An empty mesh gives
+ * the zero box.  NaN coordinates are ignored (math.Min/Max would propagate them). */
+int fgl_mesh_bounds(fgl_ctx *ctx, const fgl_mesh *mesh, double min_xyz[3], double max_xyz[3]);
+
 /* NewImageTexture, texture.go:27-30.  rgba8: h rows of w RGBA8 texels. */
 int fgl_texture_create(fgl_ctx *ctx, const uint8_t *rgba8, int width, int height, int format, fgl_tex **out);
 int fgl_texture_destroy(fgl_tex *tex);
@@ -149,6 +159,17 @@ int fgl_draw_triangles(fgl_ctx *ctx, const fgl_state *state, const fgl_shader *s
 /* DrawLines, context.go:391-411. */
 int fgl_draw_lines(fgl_ctx *ctx, const fgl_state *state, const fgl_shader *shader,
                    const fgl_mesh *mesh, uint64_t first, uint64_t count, fgl_raster_info *info);
+/* The same draws with one RasterizeInfo PER PRIMITIVE: infos[i] is what Context.DrawTriangle /
+ * Context.DrawLine (context.go:370-389, 351-368) would have returned for primitive first+i had the
+ * caller drawn the primitives one by one in index order (examples/silhouette.go:163-166 decides
+ * line visibility from UpdatedPixels/TotalPixels of each DrawLine).  One launch sequence for the
+ * whole range; `info` (may be NULL) receives the sum. */
+int fgl_draw_triangles_each(fgl_ctx *ctx, const fgl_state *state, const fgl_shader *shader,
+                            const fgl_mesh *mesh, uint64_t first, uint64_t count, fgl_raster_info *infos,
+                            fgl_raster_info *info);
+int fgl_draw_lines_each(fgl_ctx *ctx, const fgl_state *state, const fgl_shader *shader,
+                        const fgl_mesh *mesh, uint64_t first, uint64_t count, fgl_raster_info *infos,
+                        fgl_raster_info *info);
 /* Same draws, enqueued without waiting; the RasterizeInfo of all draws since
  * the last fgl_sync is accumulated and returned by fgl_sync. */
 int fgl_draw_triangles_async(fgl_ctx *ctx, const fgl_state *state, const fgl_shader *shader,
@@ -178,6 +199,10 @@ int fgl_get_stage_times(fgl_ctx *ctx, fgl_stage_times *out);
 int fgl_read_color(fgl_ctx *ctx, uint8_t *dst, size_t stride_bytes);
 /* DepthBuffer, context.go:44. */
 int fgl_read_depth(fgl_ctx *ctx, double *dst);
+/* DepthImage(), context.go:87-117: the depth buffer as Gray16, normalised on the device between
+ * the smallest and largest depth that is not math.MaxFloat64; cleared pixels give 0xffff.  dst
+ * receives width*height uint16 (host). */
+int fgl_depth_image(fgl_ctx *ctx, uint16_t *dst);
 /* The reference exposes both buffers as writable fields; these upload them. */
 int fgl_write_color(fgl_ctx *ctx, const uint8_t *src, size_t stride_bytes);
 int fgl_write_depth(fgl_ctx *ctx, const double *src);

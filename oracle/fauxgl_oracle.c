@@ -714,6 +714,59 @@ void oracle_draw_lines(octx *c, const oshader *s, const overtex *lines, size_t n
     draw_prims(c, s, (const Vertex *)lines, nlines, nthreads, 1, info);
 }
 
+/* One RasterizeInfo per primitive, drawn one by one in index order: what a caller
+ * looping over Context.DrawTriangle / DrawLine sees (context.go:351-389;
+ * examples/silhouette.go:163-166 uses the per-line UpdatedPixels/TotalPixels). */
+void oracle_draw_each(octx *c, const oshader *s, const overtex *prims, size_t n, int is_lines, oinfo *infos) {
+    Draw dr;
+    dr.c = c; dr.s = s; dr.locks = NULL;
+    m_screen(c->width, c->height, dr.screen);
+    const Vertex *v = (const Vertex *)prims;
+    for (size_t i = 0; i < n; i++) infos[i] = is_lines ? draw_line(&dr, v + 2 * i) : draw_triangle(&dr, v + 3 * i);
+}
+
+/* Context.DepthImage, context.go:87-117: Gray16 of the depth buffer. */
+void oracle_depth_image(const double *depth, int width, int height, uint16_t *out) {
+    const double MAXF = 1.7976931348623157e308;
+    double lo = MAXF, hi = -MAXF;                                                    /* :88-89 */
+    size_t n = (size_t)width * (size_t)height;
+    for (size_t i = 0; i < n; i++) {
+        double d = depth[i];
+        if (d == MAXF) continue;                                                     /* :91-93 */
+        if (d < lo) lo = d;
+        if (d > hi) hi = d;
+    }
+    for (size_t i = 0; i < n; i++) {
+        double d = depth[i];
+        double t = (d - lo) / (hi - lo);                                             /* :107 */
+        if (d == MAXF) t = 1;                                                        /* :108-110 */
+        out[i] = (uint16_t)(go_int(t * 65535.0) & 0xffff);                           /* :111 uint16(t * 0xffff) */
+    }
+}
+
+/* loadSTLB, stl.go:86-154: `records` = n 50-byte binary STL triangle records.  out = 3n
+ * vertices: positions widened from float32 (makeFloat, :82-84), normals = Triangle.Normal()
+ * (triangle.go:33-37) copied to the three vertices; everything else zero. */
+void oracle_stl_triangles(const uint8_t *records, size_t n, overtex *out) {
+    memset(out, 0, sizeof(overtex) * 3 * n);
+    Vertex *v = (Vertex *)out;
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t *b = records + 50 * i;
+        V3 p[3];
+        for (int k = 0; k < 3; k++) {
+            float f[3];
+            for (int c = 0; c < 3; c++) {
+                const uint8_t *q = b + 12 + 12 * k + 4 * c;
+                uint32_t bits = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+                memcpy(&f[c], &bits, 4);
+            }
+            p[k] = v3((double)f[0], (double)f[1], (double)f[2]);
+        }
+        V3 nn = v_normalize(v_cross(v_sub(p[1], p[0]), v_sub(p[2], p[0])));
+        for (int k = 0; k < 3; k++) { v[3 * i + k].position = p[k]; v[3 * i + k].normal = nn; }
+    }
+}
+
 /* ---- SSAA resolve: nfnt/resize Bilinear on *image.NRGBA -------------------
  * External dependency, absent from /root/reference and unpinned (no go.mod);
  * restated from the published algorithm of github.com/nfnt/resize

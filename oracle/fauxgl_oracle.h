@@ -83,6 +83,14 @@ void oracle_draw_triangles(octx *c, const oshader *s, const overtex *tris,
 void oracle_draw_lines(octx *c, const oshader *s, const overtex *lines,
                        size_t nlines, int nthreads, oinfo *info);
 
+/* Primitives drawn one by one in index order, one RasterizeInfo each (Context.DrawTriangle /
+ * DrawLine return values, context.go:351-389). */
+void oracle_draw_each(octx *c, const oshader *s, const overtex *prims, size_t n, int is_lines, oinfo *infos);
+/* Context.DepthImage, context.go:87-117 -> width*height Gray16 values. */
+void oracle_depth_image(const double *depth, int width, int height, uint16_t *out);
+/* loadSTLB, stl.go:86-154: n 50-byte records -> 3n vertices (position, face normal). */
+void oracle_stl_triangles(const uint8_t *records, size_t n, overtex *out);
+
 /* Per-stage probes used by unit tests. */
 /* DrawTriangle up to (not including) rasterize: emits the post-clip,
  * post-cull, post-swap triangles as 3 overtex + 3 screen vectors each.

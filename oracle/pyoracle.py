@@ -76,6 +76,9 @@ def lib():
         L.oracle_resolve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.oracle_pack_key.argtypes = [C.c_double, C.c_void_p]
         L.oracle_pack_key.restype = C.c_uint64
+        L.oracle_draw_each.argtypes = [C.POINTER(OCtx), C.POINTER(OShader), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.oracle_depth_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.oracle_stl_triangles.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         _lib = L
     return _lib
 
@@ -178,8 +181,35 @@ class OracleContext:
         b = self.DrawLines(mesh)
         return (a[0] + b[0], a[1] + b[1])
 
+    def _draw_each(self, verts: np.ndarray, is_lines: bool) -> np.ndarray:
+        c = self._ctx()
+        s, keep = make_oshader(self.Shader)
+        verts = np.ascontiguousarray(verts, dtype=np.float64)
+        infos = np.zeros((len(verts), 2), dtype=np.uint64)
+        lib().oracle_draw_each(C.byref(c), C.byref(s), verts.ctypes.data, len(verts), int(is_lines), infos.ctypes.data)
+        del keep
+        return infos
+
+    def DrawLinesEach(self, mesh, first=0, count=None) -> np.ndarray:
+        """[(TotalPixels, UpdatedPixels)] of Context.DrawLine per line, context.go:351-368."""
+        v = mesh.line_vertices()
+        count = len(v) - first if count is None else count
+        return self._draw_each(v[first:first + count], True)
+
+    def DrawTrianglesEach(self, mesh, first=0, count=None) -> np.ndarray:
+        """[(TotalPixels, UpdatedPixels)] of Context.DrawTriangle per triangle, context.go:370-389."""
+        v = mesh.triangle_vertices()
+        count = len(v) - first if count is None else count
+        return self._draw_each(v[first:first + count], False)
+
     def Image(self) -> np.ndarray:
         return self.ColorBuffer
+
+    def DepthImage(self) -> np.ndarray:  # context.go:87-117
+        out = np.empty((self.Height, self.Width), dtype=np.uint16)
+        d = np.ascontiguousarray(self.DepthBuffer, dtype=np.float64)
+        lib().oracle_depth_image(d.ctypes.data, self.Width, self.Height, out.ctypes.data)
+        return out
 
     def Resolve(self, factor: int) -> np.ndarray:
         dw, dh = self.Width // factor, self.Height // factor
@@ -193,6 +223,23 @@ def resolve(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
     out = np.empty((dh, dw, 4), dtype=np.uint8)
     lib().oracle_resolve(src.ctypes.data, src.shape[1], src.shape[0], dw, dh, out.ctypes.data)
     return out
+
+
+def depth_image(depth: np.ndarray) -> np.ndarray:
+    d = np.ascontiguousarray(depth, dtype=np.float64)
+    out = np.empty(d.shape, dtype=np.uint16)
+    lib().oracle_depth_image(d.ctypes.data, d.shape[1], d.shape[0], out.ctypes.data)
+    return out
+
+
+def stl_triangles(records: bytes):
+    """(position [n,3,3], normal [n,3,3]) of loadSTLB (stl.go:86-154) for n 50-byte records."""
+    n = len(records) // 50
+    buf = np.frombuffer(records, dtype=np.uint8, count=n * 50).copy()
+    out = np.zeros((n * 3, 17), dtype=np.float64)
+    lib().oracle_stl_triangles(buf.ctypes.data, n, out.ctypes.data)
+    out = out.reshape(n, 3, 17)
+    return out[:, :, 0:3].copy(), out[:, :, 3:6].copy()
 
 
 def pack_key(depth: float, rgba) -> int:

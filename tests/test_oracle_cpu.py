@@ -175,3 +175,74 @@ def test_c_oracle_matches_python_restatement(oracle_lib):
         pc = np.array(pctx.color, dtype=np.uint8).reshape(H, W, 4)
         assert (pd.view(np.uint64) == octx.DepthBuffer.view(np.uint64)).all()
         assert (pc == octx.ColorBuffer).all()
+
+
+def test_depth_image_matches_numpy_restatement(oracle_lib):
+    """oracle_depth_image (context.go:87-117) against a direct numpy statement of the same formula."""
+    sc = scenes.hello()
+    o = oracle_lib.OracleContext(sc.width, sc.height)
+    assert (o.DepthImage() == 0xffff).all()          # nothing drawn: every pixel cleared -> t = 1
+    sc.run(o)
+    d = o.DepthBuffer
+    mx = np.finfo(np.float64).max
+    drawn = d != mx
+    lo, hi = d[drawn].min(), d[drawn].max()
+    with np.errstate(over="ignore"):
+        t = np.where(drawn, (d - lo) / (hi - lo), 1.0)
+    want = np.trunc(t * 65535.0).astype(np.uint16)
+    got = o.DepthImage()
+    assert got.dtype == np.uint16 and (got == want).all()
+    assert got[drawn].min() == 0 and got[drawn].max() == 0xffff and (got[~drawn] == 0xffff).all()
+    # one depth value only: (d - lo) / 0 = NaN -> uint16(NaN) is 0 on amd64
+    flat = np.full((4, 5), mx)
+    flat[1, 2] = 0.5
+    g = oracle_lib.depth_image(flat)
+    assert g[1, 2] == 0 and (np.delete(g.ravel(), 7) == 0xffff).all()
+
+
+def test_stl_records_match_python_loader(oracle_lib, tmp_path):
+    """oracle_stl_triangles (stl.go:86-154) == the Python mirror's LoadSTL on the same bytes."""
+    import struct
+    from fauxgl_b200 import mesh as fmesh
+    rng = np.random.default_rng(11)
+    pos = rng.uniform(-50, 50, size=(300, 3, 3)).astype("<f4")
+    pos[17] = pos[17][1]    # degenerate: NaN normal, as in the reference
+    rec = np.zeros((300, 50), dtype=np.uint8)
+    rec[:, 12:48] = pos.reshape(300, 9).view(np.uint8).reshape(300, 36)
+    data = b"x" * 80 + struct.pack("<I", 300) + rec.tobytes()
+    path = tmp_path / "t.stl"
+    path.write_bytes(data)
+    m = fmesh.LoadSTL(str(path))
+    p, n = oracle_lib.stl_triangles(data[84:])
+    assert (p == pos.astype(np.float64)).all()
+    assert (m.position.view(np.uint64) == p.view(np.uint64)).all()
+    assert (np.ascontiguousarray(m.normal).view(np.uint64) == n.view(np.uint64)).all()
+    assert np.isnan(n[17]).all() and np.allclose(np.linalg.norm(np.delete(n, 17, axis=0)[:, 0], axis=1), 1.0)
+
+
+def test_draw_each_equals_one_primitive_draws(oracle_lib):
+    """oracle_draw_each: per-primitive RasterizeInfo == DrawLines/DrawTriangles over one primitive at a time."""
+    sc = scenes.lines_scene()
+    a, b = oracle_lib.OracleContext(sc.width, sc.height), oracle_lib.OracleContext(sc.width, sc.height)
+    captured = {}
+
+    class Capture:
+        def __init__(self, c):
+            self.__dict__["c"] = c
+
+        def __getattr__(self, k):
+            return getattr(self.c, k)
+
+        def __setattr__(self, k, v):
+            setattr(self.c, k, v)
+
+        def DrawLines(self, m, *args):
+            captured.setdefault("lines", m)
+            return (0, 0)
+    sc.run(Capture(a)); sc.run(Capture(b))
+    lines = captured["lines"]
+    each = a.DrawLinesEach(lines)
+    one = np.array([b.DrawLines(lines, i, 1) for i in range(lines.num_lines)], dtype=np.uint64)
+    assert (each == one).all()
+    assert (a.ColorBuffer == b.ColorBuffer).all()
+    assert each[:, 0].sum() > 1000 and (each[:, 1] <= each[:, 0]).all()
