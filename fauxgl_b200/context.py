@@ -88,6 +88,8 @@ ABI = [
     ("fgl_abi_version", C.c_int, []),
     ("fgl_last_error", C.c_char_p, [_P]),
     ("fgl_device_count", C.c_int, []),
+    ("fgl_host_alloc", C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    ("fgl_host_free", C.c_int, [_P]),
     ("fgl_context_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     ("fgl_context_destroy", C.c_int, [_P]),
     ("fgl_context_size", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -97,6 +99,8 @@ ABI = [
     ("fgl_mesh_update", C.c_int, [_P, _P, C.POINTER(_MeshDesc)]),
     ("fgl_mesh_create_stl", C.c_int, [_P, _P, C.c_uint64, C.POINTER(_P)]),
     ("fgl_mesh_bounds", C.c_int, [_P, _P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    ("fgl_mesh_update_async", C.c_int, [_P, _P, C.POINTER(_MeshDesc)]),
+    ("fgl_mesh_upload_wait", C.c_int, [_P, _P]),
     ("fgl_mesh_destroy", C.c_int, [_P]),
     ("fgl_mesh_counts", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("fgl_mesh_transform", C.c_int, [_P, _P, C.POINTER(C.c_double)]),
@@ -110,6 +114,9 @@ ABI = [
     ("fgl_draw_triangles_async", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64]),
     ("fgl_draw_lines_async", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64]),
     ("fgl_sync", C.c_int, [_P, C.POINTER(_Info)]),
+    ("fgl_frame_end", C.c_int, [_P, _P, C.c_size_t, C.POINTER(_P)]),
+    ("fgl_fence_wait", C.c_int, [_P, _P, C.POINTER(_Info)]),
+    ("fgl_fence_destroy", C.c_int, [_P]),
     ("fgl_get_draw_stats", C.c_int, [_P, C.POINTER(DrawStats)]),
     ("fgl_set_profiling", C.c_int, [_P, C.c_int]),
     ("fgl_get_stage_times", C.c_int, [_P, C.POINTER(StageTimes)]),
@@ -161,6 +168,33 @@ def _check(rc: int, ctx=None):
 
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """A numpy array in page-locked host memory (fgl_host_alloc), freed with the array."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = _P()
+    _check(capi().fgl_host_alloc(n, C.byref(p)))
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, capi().fgl_host_free, p)
+    return arr
+
+
+class Fence:
+    """fgl_fence: completion of one pipelined frame (Context.FrameEnd)."""
+
+    def __init__(self, ctx: "Context"):
+        self.ctx = ctx
+        self.handle = _P()
+        self._fin = None
+
+    def wait(self) -> RasterizeInfo:
+        info = _Info()
+        if self.handle:
+            _check(capi().fgl_fence_wait(self.ctx._h, self.handle, C.byref(info)), self.ctx._h)
+        return RasterizeInfo(info.total_pixels, info.updated_pixels)
 
 
 class DeviceTexture:
@@ -261,6 +295,20 @@ class DeviceMesh:
         d.ltexture = arr(mesh.ltexture, "texture" in attributes)
         d.lcolor = arr(mesh.lcolor, "color" in attributes)
         return d, keep
+
+    def update_async(self, mesh: Mesh, attributes=None):
+        """fgl_mesh_update_async: enqueue the re-upload on the copy stream and return; ``mesh``'s arrays
+        (pinned for a real overlap, see ``pinned_empty``) must stay unchanged until ``upload_wait``."""
+        assert (mesh.num_triangles, mesh.num_lines) == (self.num_triangles, self.num_lines)
+        attributes = self.attributes if attributes is None else tuple(attributes)
+        d, keep = self._desc(mesh, attributes, position="position" in attributes)
+        self._pending = keep
+        _check(capi().fgl_mesh_update_async(self.ctx._h, self.handle, C.byref(d)), self.ctx._h)
+        self.generation = mesh.generation
+
+    def upload_wait(self):
+        _check(capi().fgl_mesh_upload_wait(self.ctx._h, self.handle), self.ctx._h)
+        self._pending = None
 
     def Transform(self, matrix: Matrix):
         """Mesh.Transform on the device (mesh.go:167-175)."""
@@ -462,6 +510,18 @@ class Context:
         info = _Info()
         _check(capi().fgl_sync(self._h, C.byref(info)), self._h)
         return RasterizeInfo(info.total_pixels, info.updated_pixels)
+
+    def FrameEnd(self, out: Optional[np.ndarray] = None, fence: Optional[Fence] = None) -> Fence:
+        """fgl_frame_end: enqueue the read-back of the colour buffer into ``out`` ((H,W,4) uint8, pinned for
+        a real overlap) and of the frame's RasterizeInfo, and return a fence; ``fence.wait()`` blocks until
+        exactly this frame is in host memory while later frames keep running."""
+        if out is not None:
+            assert out.shape == (self.Height, self.Width, 4) and out.dtype == np.uint8 and out.flags.c_contiguous
+        fence = Fence(self) if fence is None else fence
+        _check(capi().fgl_frame_end(self._h, None if out is None else out.ctypes.data, 0, C.byref(fence.handle)), self._h)
+        if fence._fin is None:
+            fence._fin = weakref.finalize(fence, capi().fgl_fence_destroy, fence.handle)
+        return fence
 
     def SetProfiling(self, enabled: bool):
         _check(capi().fgl_set_profiling(self._h, int(enabled)), self._h)

@@ -45,6 +45,17 @@ struct fgl_mesh {
     double *lpos, *lnrm, *ltex, *lcol;  // planar, lines
     double *staging;                    // AoS landing buffer for H2D copies (kept for fgl_mesh_update)
     size_t staging_elems;
+    // streaming uploads (fgl_mesh_update_async): the copy stream and the draw stream hand the
+    // buffers back and forth through these two events
+    cudaEvent_t ev_uploaded, ev_drawn;
+    bool has_events, upload_pending, drawn_recorded;
+};
+
+struct fgl_fence {
+    int device;
+    cudaEvent_t done;
+    DrawCounters *counters;  // pinned: the frame's accumulated RasterizeInfo / overflow flags
+    bool recorded;
 };
 
 constexpr int PROF_RING = 32;
@@ -56,6 +67,7 @@ struct fgl_ctx {
     int w, h;
     int tile_h;
     cudaStream_t stream;
+    cudaStream_t copy_stream;          // H2D of streaming mesh uploads, overlapping the draw stream
     std::mutex mu;
     std::string err;
     uint32_t *color;
@@ -179,6 +191,23 @@ int check_ctx(fgl_ctx *c) {
     cudaError_t e = cudaSetDevice(c->device);
     if (e != cudaSuccess) return fail(c, FGL_E_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e));
     return FGL_OK;
+}
+
+// A mesh whose last upload went through the copy stream is handed to the draw stream here; after the
+// draw stream used it, `release` lets the next streaming upload know when it may overwrite the buffers.
+void mesh_acquire(fgl_ctx *c, const fgl_mesh *cm) {
+    fgl_mesh *m = const_cast<fgl_mesh *>(cm);
+    if (m->upload_pending) {
+        cudaStreamWaitEvent(c->stream, m->ev_uploaded, 0);
+        m->upload_pending = false;
+    }
+}
+void mesh_release(fgl_ctx *c, const fgl_mesh *cm) {
+    fgl_mesh *m = const_cast<fgl_mesh *>(cm);
+    if (m->has_events) {
+        cudaEventRecord(m->ev_drawn, c->stream);
+        m->drawn_recorded = true;
+    }
 }
 
 __global__ void k_accumulate(const DrawCounters *cur, DrawCounters *acc) {
@@ -339,10 +368,12 @@ int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const 
     }
     rc = initial_capacity(c, p);
     if (rc) return rc;
+    mesh_acquire(c, mesh);
     if (async) {
         rc = enqueue_draw(c, p);
         if (rc) return rc;
         k_accumulate<<<1, 1, 0, c->stream>>>(c->wb.counters, c->acc_dev);
+        mesh_release(c, mesh);
         c->async_pending = true;
         return FGL_OK;
     }
@@ -353,6 +384,7 @@ int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const 
         CK(c, cudaStreamSynchronize(c->stream));
         const DrawCounters &hc = *c->host_counters;
         if (!hc.overflow) {
+            mesh_release(c, mesh);
             if (p.prim_info) {
                 CK(c, cudaMemcpyAsync(each, p.prim_info, sizeof(fgl_raster_info) * count, cudaMemcpyDeviceToHost, c->stream));
                 CK(c, cudaStreamSynchronize(c->stream));
@@ -386,6 +418,25 @@ int fgl_device_count(void) {
     return n;
 }
 
+int fgl_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(nullptr, FGL_E_INVALID, "null out pointer");
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, e == cudaErrorMemoryAllocation ? FGL_E_OOM : FGL_E_CUDA, "cudaMallocHost(%zu): %s", bytes,
+                    cudaGetErrorString(e));
+    }
+    return FGL_OK;
+}
+int fgl_host_free(void *p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, FGL_E_CUDA, "cudaFreeHost failed");
+    }
+    return FGL_OK;
+}
+
 int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     if (!out) return fail(nullptr, FGL_E_INVALID, "null out pointer");
     *out = nullptr;
@@ -412,7 +463,9 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     c->profiling = false; c->prof_used = 0; c->prof_created = false;
     memset(&c->prof_acc, 0, sizeof c->prof_acc);
     const size_t npix = (size_t)width * height;
+    c->stream = nullptr; c->copy_stream = nullptr;
     cudaError_t err = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = dev_alloc(&c->color, npix);
     if (err == cudaSuccess) err = dev_alloc(&c->depth, npix);
     if (err == cudaSuccess) err = dev_alloc(&c->wb.counters, 1);
@@ -462,6 +515,7 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
 int fgl_context_destroy(fgl_ctx *c) {
     if (!c) return FGL_OK;
     cudaSetDevice(c->device);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_work(c->wb);
     dev_free(c->wb.tile_start); dev_free(c->wb.tile_end); dev_free(c->wb.counters); dev_free(c->wb.tile_clock);
@@ -509,34 +563,37 @@ int fgl_clear_depth(fgl_ctx *c, double value) {
 // Each attribute lands in its own region of the staging buffer, so all H2D copies of
 // one upload are queued back to back and the transposing ingest kernels trail them.
 static int upload_attr(fgl_ctx *c, const double *host, double **planes, uint64_t n, int nverts, int ncomp_in,
-                       int ncomp_out, double *staging, bool create) {
+                       int ncomp_out, double *staging, bool create, cudaStream_t st) {
     if (create) CK(c, dev_alloc(planes, (size_t)n * nverts * ncomp_out));
     if (n == 0) return FGL_OK;
     if (!host) {
-        if (create) CK(c, cudaMemsetAsync(*planes, 0, sizeof(double) * n * nverts * ncomp_out, c->stream));
+        if (create) CK(c, cudaMemsetAsync(*planes, 0, sizeof(double) * n * nverts * ncomp_out, st));
         return FGL_OK;
     }
-    CK(c, cudaMemcpyAsync(staging, host, sizeof(double) * n * nverts * ncomp_in, cudaMemcpyHostToDevice, c->stream));
-    launch_mesh_ingest(staging, *planes, (uint32_t)n, nverts, ncomp_in, ncomp_out, c->stream);
+    CK(c, cudaMemcpyAsync(staging, host, sizeof(double) * n * nverts * ncomp_in, cudaMemcpyHostToDevice, st));
+    launch_mesh_ingest(staging, *planes, (uint32_t)n, nverts, ncomp_in, ncomp_out, st);
     CK(c, cudaGetLastError());
     return FGL_OK;
 }
 
-static int upload_all(fgl_ctx *c, fgl_mesh *m, const fgl_mesh_desc *d, bool create) {
+static int upload_all(fgl_ctx *c, fgl_mesh *m, const fgl_mesh_desc *d, bool create, cudaStream_t st = nullptr,
+                      bool wait = true) {
+    if (!st) st = c->stream;
     // staging regions: [pos | nrm | tex | col] for triangles, then the same for lines
     const size_t t3 = (size_t)m->nt * 9, t4 = (size_t)m->nt * 12, l3 = (size_t)m->nl * 6, l4 = (size_t)m->nl * 8;
     double *s = m->staging;
-    int rc = upload_attr(c, d->position, &m->tpos, m->nt, 3, 3, 3, s, create);
-    if (!rc) rc = upload_attr(c, d->normal, &m->tnrm, m->nt, 3, 3, 3, s + t3, create);
-    if (!rc) rc = upload_attr(c, d->texture, &m->ttex, m->nt, 3, 3, 2, s + 2 * t3, create);
-    if (!rc) rc = upload_attr(c, d->color, &m->tcol, m->nt, 3, 4, 4, s + 3 * t3, create);
+    int rc = upload_attr(c, d->position, &m->tpos, m->nt, 3, 3, 3, s, create, st);
+    if (!rc) rc = upload_attr(c, d->normal, &m->tnrm, m->nt, 3, 3, 3, s + t3, create, st);
+    if (!rc) rc = upload_attr(c, d->texture, &m->ttex, m->nt, 3, 3, 2, s + 2 * t3, create, st);
+    if (!rc) rc = upload_attr(c, d->color, &m->tcol, m->nt, 3, 4, 4, s + 3 * t3, create, st);
     s += 3 * t3 + t4;
-    if (!rc) rc = upload_attr(c, d->lposition, &m->lpos, m->nl, 2, 3, 3, s, create);
-    if (!rc) rc = upload_attr(c, d->lnormal, &m->lnrm, m->nl, 2, 3, 3, s + l3, create);
-    if (!rc) rc = upload_attr(c, d->ltexture, &m->ltex, m->nl, 2, 3, 2, s + 2 * l3, create);
-    if (!rc) rc = upload_attr(c, d->lcolor, &m->lcol, m->nl, 2, 4, 4, s + 3 * l3, create);
+    if (!rc) rc = upload_attr(c, d->lposition, &m->lpos, m->nl, 2, 3, 3, s, create, st);
+    if (!rc) rc = upload_attr(c, d->lnormal, &m->lnrm, m->nl, 2, 3, 3, s + l3, create, st);
+    if (!rc) rc = upload_attr(c, d->ltexture, &m->ltex, m->nl, 2, 3, 2, s + 2 * l3, create, st);
+    if (!rc) rc = upload_attr(c, d->lcolor, &m->lcol, m->nl, 2, 4, 4, s + 3 * l3, create, st);
     (void)l4;
-    cudaError_t se = cudaStreamSynchronize(c->stream);  // the caller may reuse its host arrays
+    if (!wait) return rc;
+    cudaError_t se = cudaStreamSynchronize(st);  // the caller may reuse its host arrays
     if (!rc && se != cudaSuccess) rc = fail(c, FGL_E_CUDA, "mesh upload: %s", cudaGetErrorString(se));
     return rc;
 }
@@ -573,7 +630,39 @@ int fgl_mesh_update(fgl_ctx *c, fgl_mesh *m, const fgl_mesh_desc *d) {
                     (unsigned long long)d->ntriangles, (unsigned long long)d->nlines, (unsigned long long)m->nt,
                     (unsigned long long)m->nl);
     std::lock_guard<std::mutex> lock(c->mu);
+    mesh_acquire(c, m);
     return upload_all(c, m, d, false);
+}
+
+int fgl_mesh_update_async(fgl_ctx *c, fgl_mesh *m, const fgl_mesh_desc *d) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!m || !d) return fail(c, FGL_E_INVALID, "null mesh/description");
+    if (m->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on another device");
+    if (d->ntriangles != m->nt || d->nlines != m->nl)
+        return fail(c, FGL_E_INVALID, "fgl_mesh_update_async needs the same primitive counts");
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!m->has_events) {
+        CK(c, cudaEventCreateWithFlags(&m->ev_uploaded, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&m->ev_drawn, cudaEventDisableTiming));
+        m->has_events = true;
+        // everything enqueued on the draw stream so far may still read the buffers
+        cudaEventRecord(m->ev_drawn, c->stream);
+        m->drawn_recorded = true;
+    }
+    if (m->drawn_recorded) CK(c, cudaStreamWaitEvent(c->copy_stream, m->ev_drawn, 0));
+    rc = upload_all(c, m, d, false, c->copy_stream, false);
+    CK(c, cudaEventRecord(m->ev_uploaded, c->copy_stream));
+    m->upload_pending = true;
+    return rc;
+}
+
+int fgl_mesh_upload_wait(fgl_ctx *c, fgl_mesh *m) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!m) return fail(c, FGL_E_INVALID, "null mesh");
+    if (m->has_events) CK(c, cudaEventSynchronize(m->ev_uploaded));
+    return FGL_OK;
 }
 
 int fgl_mesh_create_stl(fgl_ctx *c, const uint8_t *records, uint64_t count, fgl_mesh **out) {
@@ -623,6 +712,7 @@ int fgl_mesh_bounds(fgl_ctx *c, const fgl_mesh *m, double mn[3], double mx[3]) {
     if (m->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on another device");
     std::lock_guard<std::mutex> lock(c->mu);
     unsigned long long h[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
+    mesh_acquire(c, m);
     CK(c, cudaMemcpyAsync(c->scratch, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
     launch_mesh_bounds(m->tpos, (uint32_t)m->nt, 3, c->scratch, c->stream);
     launch_mesh_bounds(m->lpos, (uint32_t)m->nl, 2, c->scratch, c->stream);
@@ -646,6 +736,7 @@ int fgl_mesh_destroy(fgl_mesh *m) {
     dev_free(m->tpos); dev_free(m->tnrm); dev_free(m->ttex); dev_free(m->tcol);
     dev_free(m->lpos); dev_free(m->lnrm); dev_free(m->ltex); dev_free(m->lcol);
     dev_free(m->staging);
+    if (m->has_events) { cudaEventDestroy(m->ev_uploaded); cudaEventDestroy(m->ev_drawn); }
     delete m;
     return FGL_OK;
 }
@@ -663,8 +754,10 @@ int fgl_mesh_transform(fgl_ctx *c, fgl_mesh *m, const double matrix[16]) {
     if (!m || !matrix) return fail(c, FGL_E_INVALID, "null mesh/matrix");
     if (m->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on another device");
     std::lock_guard<std::mutex> lock(c->mu);
+    mesh_acquire(c, m);
     launch_mesh_transform(m->tpos, m->tnrm, (uint32_t)m->nt, 3, matrix, c->stream);
     launch_mesh_transform(m->lpos, m->lnrm, (uint32_t)m->nl, 2, matrix, c->stream);
+    mesh_release(c, m);
     CK(c, cudaGetLastError());
     return FGL_OK;
 }
@@ -686,6 +779,7 @@ int fgl_mesh_read(fgl_ctx *c, const fgl_mesh *m, double *position, double *norma
     if (rc) return rc;
     if (!m) return fail(c, FGL_E_INVALID, "null mesh");
     std::lock_guard<std::mutex> lock(c->mu);
+    mesh_acquire(c, m);
     rc = read_attr(c, m->tpos, position, m->nt, 3, 3);
     if (!rc) rc = read_attr(c, m->tnrm, normal, m->nt, 3, 3);
     if (!rc) rc = read_attr(c, m->lpos, lposition, m->nl, 2, 3);
@@ -774,6 +868,68 @@ int fgl_sync(fgl_ctx *c, fgl_raster_info *info) {
         }
         if (info) { info->total_pixels = hc.total_pixels; info->updated_pixels = hc.updated_pixels; }
     }
+    return FGL_OK;
+}
+
+int fgl_frame_end(fgl_ctx *c, uint8_t *color_dst, size_t stride, fgl_fence **fence) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!fence) return fail(c, FGL_E_INVALID, "null fence pointer");
+    if (stride == 0) stride = (size_t)c->w * 4;
+    if (stride < (size_t)c->w * 4) return fail(c, FGL_E_INVALID, "stride too small");
+    std::lock_guard<std::mutex> lock(c->mu);
+    fgl_fence *f = *fence;
+    if (!f) {
+        f = new (std::nothrow) fgl_fence();
+        if (!f) return fail(c, FGL_E_OOM, "host allocation failed");
+        f->device = c->device; f->counters = nullptr; f->recorded = false;
+        cudaError_t e = cudaEventCreateWithFlags(&f->done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void **>(&f->counters), sizeof(DrawCounters));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            delete f;
+            return fail(c, FGL_E_CUDA, "fence: %s", cudaGetErrorString(e));
+        }
+        *fence = f;
+    } else if (f->device != c->device) {
+        return fail(c, FGL_E_INVALID, "fence belongs to another device");
+    }
+    if (color_dst)
+        CK(c, cudaMemcpy2DAsync(color_dst, stride, c->color, (size_t)c->w * 4, (size_t)c->w * 4, c->h,
+                                cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(f->counters, c->acc_dev, sizeof(DrawCounters), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemsetAsync(c->acc_dev, 0, sizeof(DrawCounters), c->stream));
+    CK(c, cudaEventRecord(f->done, c->stream));
+    f->recorded = true;
+    c->async_pending = false;
+    return FGL_OK;
+}
+
+int fgl_fence_wait(fgl_ctx *c, fgl_fence *f, fgl_raster_info *info) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!f) return fail(c, FGL_E_INVALID, "null fence");
+    if (info) { info->total_pixels = 0; info->updated_pixels = 0; }
+    if (!f->recorded) return FGL_OK;
+    CK(c, cudaEventSynchronize(f->done));
+    f->recorded = false;
+    const DrawCounters hc = *f->counters;
+    if (hc.overflow) {
+        std::lock_guard<std::mutex> lock(c->mu);
+        ensure_work(c, grown(c, hc));
+        return fail(c, FGL_E_OVERFLOW, "an async draw of this frame outgrew its work buffers (now regrown): re-issue the frame");
+    }
+    if (info) { info->total_pixels = hc.total_pixels; info->updated_pixels = hc.updated_pixels; }
+    return FGL_OK;
+}
+
+int fgl_fence_destroy(fgl_fence *f) {
+    if (!f) return FGL_OK;
+    cudaSetDevice(f->device);
+    cudaEventSynchronize(f->done);
+    cudaEventDestroy(f->done);
+    if (f->counters) cudaFreeHost(f->counters);
+    delete f;
     return FGL_OK;
 }
 

@@ -109,6 +109,12 @@ int fgl_abi_version(void);
 const char *fgl_last_error(const fgl_ctx *ctx);
 int fgl_device_count(void);
 
+/* Page-locked host memory for the streaming entry points (fgl_mesh_update_async, fgl_frame_end): copies
+ * from/to it are asynchronous and run at full PCIe rate.  A Go caller keeps flattened meshes here (C
+ * memory, no Go pointers inside: cgo may pass it freely). */
+int fgl_host_alloc(size_t bytes, void **out);
+int fgl_host_free(void *ptr);
+
 /* NewContext, context.go:60-81: colour buffer zeroed (transparent), depth
  * buffer cleared to math.MaxFloat64. */
 int fgl_context_create(int width, int height, int device, fgl_ctx **out);
@@ -128,6 +134,14 @@ int fgl_mesh_create(fgl_ctx *ctx, const fgl_mesh_desc *desc, fgl_mesh **out);
  * the shim calls when a cached Mesh was mutated on the host between frames
  * (examples/animate.go:66 transforms the mesh on the CPU every frame). */
 int fgl_mesh_update(fgl_ctx *ctx, fgl_mesh *mesh, const fgl_mesh_desc *desc);
+/* Streaming variant for frame pipelines (examples/animate.go re-poses the mesh on the host every frame):
+ * the copies and the transposing kernels run on the context's copy stream and the call returns at
+ * once; draws that use the mesh afterwards wait for the upload on the device, and the upload itself
+ * waits for earlier draws that still read the buffers.  With two meshes used alternately the upload of
+ * frame i+1 overlaps the draw of frame i.  The host arrays (pinned memory for a real overlap) must stay
+ * unchanged until fgl_mesh_upload_wait returns. */
+int fgl_mesh_update_async(fgl_ctx *ctx, fgl_mesh *mesh, const fgl_mesh_desc *desc);
+int fgl_mesh_upload_wait(fgl_ctx *ctx, fgl_mesh *mesh);
 int fgl_mesh_destroy(fgl_mesh *mesh);
 int fgl_mesh_counts(const fgl_mesh *mesh, uint64_t *ntriangles, uint64_t *nlines);
 /* Mesh.Transform, mesh.go:167-175 (+ triangle.go:66-73, line.go:23-28): positions
@@ -179,6 +193,15 @@ int fgl_draw_lines_async(fgl_ctx *ctx, const fgl_state *state, const fgl_shader 
 /* Wait for everything enqueued on the context; info (may be NULL) receives the
  * sum over the async draws since the previous fgl_sync. */
 int fgl_sync(fgl_ctx *ctx, fgl_raster_info *info);
+/* End of a pipelined frame: enqueues the read-back of the colour buffer into color_dst (may be NULL;
+ * pinned memory for a real overlap; stride 0 = width*4) and of the RasterizeInfo accumulated by the async
+ * draws since the previous fgl_sync / fgl_frame_end, restarts that accumulation and records a fence.  *fence
+ * is created when NULL and reused otherwise.  fgl_fence_wait blocks until that frame's results are in host
+ * memory -- later frames keep running -- and returns its RasterizeInfo, or FGL_E_OVERFLOW like fgl_sync. */
+typedef struct fgl_fence fgl_fence;
+int fgl_frame_end(fgl_ctx *ctx, uint8_t *color_dst, size_t stride_bytes, fgl_fence **fence);
+int fgl_fence_wait(fgl_ctx *ctx, fgl_fence *fence, fgl_raster_info *info);
+int fgl_fence_destroy(fgl_fence *fence);
 int fgl_get_draw_stats(const fgl_ctx *ctx, fgl_draw_stats *out);
 
 /* Per-stage device timing (CUDA events on the context's stream).  While enabled,
