@@ -117,7 +117,8 @@ void dev_free(T *&p) {
 }
 
 void free_work(WorkBuffers &wb) {
-    dev_free(wb.lb_status); dev_free(wb.lb_ticket); dev_free(wb.recs);
+    dev_free(wb.blk_agg); dev_free(wb.blk_base); dev_free(wb.blk_region); dev_free(wb.recs);
+    dev_free(wb.rec_local_row); dev_free(wb.rec_slot);
     dev_free(wb.rec_row_off); dev_free(wb.clip_pool); dev_free(wb.row_nseg); dev_free(wb.row_seg_off);
     dev_free(wb.row_first); dev_free(wb.row_key); dev_free(wb.segv);
     dev_free(wb.seg_key[0]); dev_free(wb.seg_key[1]); dev_free(wb.seg_val[0]); dev_free(wb.seg_val[1]);
@@ -136,13 +137,16 @@ int ensure_work(fgl_ctx *c, const Caps &want) {
     if (want.prims > LIM || want.records > LIM || want.rows > LIM || want.segs > LIM || want.clip > LIM)
         return fail(c, FGL_E_INVALID, "draw too large for 32-bit work indices");
     if (want.prims > wb.cap_prims) {
-        dev_free(wb.lb_status);
-        CK(c, dev_alloc(&wb.lb_status, want.prims / 256 + 2));
-        if (!wb.lb_ticket) CK(c, dev_alloc(&wb.lb_ticket, 1));
+        dev_free(wb.blk_agg); dev_free(wb.blk_base); dev_free(wb.blk_region);
+        CK(c, dev_alloc(&wb.blk_agg, want.prims / 256 + 2));
+        CK(c, dev_alloc(&wb.blk_base, want.prims / 256 + 2));
+        CK(c, dev_alloc(&wb.blk_region, want.prims / 256 + 2));
         wb.cap_prims = (uint32_t)want.prims;
     }
     if (want.records > wb.cap_records) {
-        dev_free(wb.recs); dev_free(wb.rec_row_off);
+        dev_free(wb.recs); dev_free(wb.rec_row_off); dev_free(wb.rec_local_row); dev_free(wb.rec_slot);
+        CK(c, dev_alloc(&wb.rec_local_row, want.records));
+        CK(c, dev_alloc(&wb.rec_slot, want.records + 1));
         CK(c, dev_alloc(&wb.recs, want.records));
         CK(c, dev_alloc(&wb.rec_row_off, want.records + 1));
         wb.cap_records = (uint32_t)want.records;

@@ -122,8 +122,8 @@ FGL_DI double edge_fn(V3 a, V3 b, V3 c) {  // context.go:147-149
     return (b.x - c.x) * (a.y - c.y) - (b.y - c.y) * (a.x - c.x);
 }
 
-// Write one record at its ordered slot r; its scanlines start at row_off in the (record, scanline)
-// item space of the span stage.
+// Write one record at slot r; its scanlines start at row_off within the block's share of the
+// (record, scanline) item space of the span stage.
 FGL_DI void write_record(const WorkBuffers *wb, uint32_t r, uint32_t row_off, const BBox &b, V3 s0, V3 s1, V3 s2,
                          double w0, double w1, double w2, uint32_t src, uint32_t flags) {
     if (r >= wb->cap_records) return;
@@ -143,7 +143,7 @@ FGL_DI void write_record(const WorkBuffers *wb, uint32_t r, uint32_t row_off, co
     rec.src = src; rec.flags = flags;
     rec.x0 = b.x0; rec.x1 = b.x1; rec.y0 = b.y0; rec.y1 = b.y1;
     wb->recs[r] = rec;
-    wb->rec_row_off[r] = row_off;
+    wb->rec_local_row[r] = row_off;
 }
 
 // First pass over a primitive: counts its records and scanlines and keeps the first record in
@@ -406,12 +406,15 @@ FGL_DI void process_line(const DrawParams &p, Emit &e, uint32_t prim) {
     emit_line(p, e, s0, s1, 0, 1, w1.w, w2.w, prim, 0);
 }
 
-// ---- single-pass ordered compaction (decoupled look-back) ---------------------------------------------
-// Virtual block ids come from an atomic ticket, so a block only ever waits for blocks that already
-// run.  status[b]: bits 63-62 flag (0 empty, 1 block aggregate, 2 inclusive prefix), bits 61-30 scanlines,
-// bits 29-0 records.
+// ---- single-pass compaction without inter-block waits ------------------------------------------------
+// Every block scans its own (scanlines << 30 | records) counts, takes a region of the record array
+// with one atomic and writes its records there -- in primitive order inside the region, regions in
+// arrival order.  The block aggregates are scanned by whichever block finishes last, and k_rec_index
+// lists the record slots in primitive order (rec_slot, rec_row_off) for the span stage.  An ordered
+// look-back was measured first: blocks behind a slow block (many visible triangles) idled at the barrier
+// for their prefix (44 % of warp time, profiles/README.md).
 constexpr int GT = 256;
-constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = (1ull << 62) - 1ull;
+constexpr unsigned long long REC_MASK = (1ull << 30) - 1ull;
 
 // General path (lines, wireframe, clipped triangles), out of line so that its registers and stack
 // do not weigh on the common case.  Counting and writing run the same deterministic arithmetic.
@@ -431,13 +434,11 @@ __device__ __noinline__ void write_general(const DrawParams &p, const WorkBuffer
 
 __global__ void __launch_bounds__(GT, 4)
 k_geometry(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
-    __shared__ uint32_t s_vb;
-    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_region;
+    __shared__ bool s_last;
     __shared__ unsigned long long s_scan[GT / 32 + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_vb = atomicAdd(wb.lb_ticket, 1u);
-    __syncthreads();
-    const uint32_t vb = s_vb;
+    const uint32_t vb = blockIdx.x;
     const uint32_t nblocks = (p.count + GT - 1) / GT;
     const uint32_t i = vb * GT + tid;
 
@@ -519,54 +520,81 @@ k_geometry(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuf
     const unsigned long long local_excl = s_scan[warp] + incl - mine;
     const unsigned long long block_total = s_scan[GT / 32];
 
-    if (warp == 0) {
-        // warp-wide look-back: 32 predecessors per step (a serial walk over the ~600 resident blocks
-        // costs an L2 round trip per step and dominated the kernel)
-        volatile unsigned long long *status = wb.lb_status;
-        unsigned long long excl = 0;
-        if (vb > 0) {
-            if (lane == 0) status[vb] = LB_AGG | block_total;
-            __threadfence();
-            for (int top = (int)vb - 1;; top -= 32) {
-                const int idx = top - lane;
-                unsigned long long v = LB_PREFIX;  // virtual zero prefix in front of block 0
-                if (idx >= 0) {
-                    do { v = status[idx]; } while ((v >> 62) == 0);
-                }
-                const unsigned pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-                const int first = pm ? __ffs(pm) - 1 : 31;  // nearest predecessor that already has a prefix
-                unsigned long long contrib = lane <= first ? (v & LB_MASK) : 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_down_sync(0xffffffffu, contrib, o);
-                excl += __shfl_sync(0xffffffffu, contrib, 0);
-                if (pm) break;
-            }
-        }
-        if (lane == 0) {
-            status[vb] = LB_PREFIX | (excl + block_total);
-            __threadfence();
-            s_base = excl;
-        }
-        if (lane == 0 && vb == nblocks - 1) {  // grand totals
-            const unsigned long long tot = excl + block_total;
-            const uint32_t nrec = (uint32_t)(tot & ((1ull << 30) - 1ull)), nrows = (uint32_t)(tot >> 30);
-            DrawCounters *c = wb.counters;
-            c->n_records = nrec; c->need_records = nrec;
-            c->n_rows = nrows; c->need_rows = nrows;
-            unsigned ovf = 0;
-            if (nrec > wb.cap_records) ovf |= OVF_RECORDS;
-            if (nrows > wb.cap_rows) ovf |= OVF_ROWS;
-            if (ovf) atomicOr(&c->overflow, ovf);
-            if (nrec <= wb.cap_records) wb.rec_row_off[nrec] = nrows;  // sentinel for the span stage's search
-        }
+    if (tid == 0) {
+        const uint32_t brec = (uint32_t)(block_total & REC_MASK);
+        s_region = brec ? atomicAdd(&wb.counters->rec_cursor, brec) : 0u;
+        wb.blk_agg[vb] = block_total;
+        wb.blk_region[vb] = s_region;
+        __threadfence();
+        s_last = atomicAdd(&wb.counters->blocks_done, 1u) == nblocks - 1u;
     }
     __syncthreads();
-    const unsigned long long base = s_base + local_excl;
-    const uint32_t rec0 = (uint32_t)(base & ((1ull << 30) - 1ull)), row0 = (uint32_t)(base >> 30);
+    const uint32_t rec0 = s_region + (uint32_t)(local_excl & REC_MASK), row0 = (uint32_t)(local_excl >> 30);
     if (slow) {
-        if (n > 0) write_general(p, wb, p.first + i, rec0, row0);  // run again, writing at the ordered slots
+        if (n > 0) write_general(p, wb, p.first + i, rec0, row0);  // run again, writing at the block's slots
     } else if (n == 1) {
         write_record(&wb, rec0, row0, bb, s0, s1, s2, w0, w1, w2, p.first + i, vflags);
+    }
+    if (!s_last) return;
+
+    // Last block: exclusive scan of the block aggregates (a few thousand entries), grand totals.
+    __threadfence();
+    const uint32_t per = (nblocks + GT - 1) / GT;
+    const uint32_t b0 = min((uint32_t)tid * per, nblocks), b1 = min(b0 + per, nblocks);
+    unsigned long long sum = 0;
+    for (uint32_t b = b0; b < b1; b++) sum += __ldcg(&wb.blk_agg[b]);
+    unsigned long long incl2 = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl2, o);
+        if (lane >= o) incl2 += t;
+    }
+    __syncthreads();  // s_scan is reused
+    if (lane == 31) s_scan[warp] = incl2;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long v = lane < GT / 32 ? s_scan[lane] : 0, vi = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, vi, o);
+            if (lane >= o) vi += t;
+        }
+        if (lane < GT / 32) s_scan[lane] = vi - v;
+        if (lane == GT / 32 - 1) s_scan[GT / 32] = vi;
+    }
+    __syncthreads();
+    unsigned long long run = s_scan[warp] + incl2 - sum;
+    for (uint32_t b = b0; b < b1; b++) {
+        wb.blk_base[b] = run;
+        run += __ldcg(&wb.blk_agg[b]);
+    }
+    if (tid == 0) {
+        const unsigned long long tot = s_scan[GT / 32];
+        const uint32_t nrec = (uint32_t)(tot & REC_MASK), nrows = (uint32_t)(tot >> 30);
+        DrawCounters *c = wb.counters;
+        c->n_records = nrec; c->need_records = nrec;
+        c->n_rows = nrows; c->need_rows = nrows;
+        unsigned ovf = 0;
+        if (nrec > wb.cap_records) ovf |= OVF_RECORDS;
+        if (nrows > wb.cap_rows) ovf |= OVF_ROWS;
+        if (ovf) atomicOr(&c->overflow, ovf);
+        if (nrec <= wb.cap_records) wb.rec_row_off[nrec] = nrows;  // sentinel for the span stage's search
+    }
+}
+
+// Record slots in primitive order: rec_slot[c], and the first span-stage item of record c, rec_row_off[c].
+__global__ void __launch_bounds__(GT)
+k_rec_index(const __grid_constant__ WorkBuffers wb, uint32_t nblocks) {
+    if (wb.counters->overflow) return;
+    for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const unsigned long long agg = wb.blk_agg[b], base = wb.blk_base[b];
+        const uint32_t cnt = (uint32_t)(agg & REC_MASK), region = wb.blk_region[b];
+        const uint32_t rec_base = (uint32_t)(base & REC_MASK), row_base = (uint32_t)(base >> 30);
+        for (uint32_t k = threadIdx.x; k < cnt; k += GT) {
+            const uint32_t slot = region + k, c = rec_base + k;
+            wb.rec_slot[c] = slot;
+            wb.rec_row_off[c] = row_base + wb.rec_local_row[slot];
+        }
     }
 }
 
@@ -574,10 +602,9 @@ int launch_geometry(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st)
     const uint32_t blocks = (p.count + GT - 1) / GT;
     // counters + look-back state of this draw (stream-ordered before the kernel)
     cudaMemsetAsync(wb.counters, 0, sizeof(DrawCounters), st);
-    cudaMemsetAsync(wb.lb_ticket, 0, sizeof(unsigned int), st);
-    cudaMemsetAsync(wb.lb_status, 0, sizeof(unsigned long long) * blocks, st);
     k_geometry<<<blocks, GT, 0, st>>>(p, wb);
-    return 1;
+    k_rec_index<<<blocks < 148u * 8u ? blocks : 148u * 8u, GT, 0, st>>>(wb, blocks);
+    return 2;
 }
 
 }  // namespace fgl

@@ -122,15 +122,23 @@ struct DrawCounters {
     unsigned int n_records, n_rows, n_segs, n_clip;
     unsigned int overflow;  // bit0 records, bit1 rows, bit2 clip pool, bit3 segments
     unsigned int need_records, need_rows, need_segs, need_clip, _pad;
+    unsigned int rec_cursor;   // geometry stage: next free record slot (regions are handed out per block)
+    unsigned int blocks_done;  // geometry stage: blocks that have published their aggregate
 };
 constexpr unsigned OVF_RECORDS = 1u, OVF_ROWS = 2u, OVF_CLIP = 4u, OVF_SEGS = 8u;
 
 struct WorkBuffers {
     // geometry
-    unsigned long long *lb_status;  // [ceil(cap_prims/256)] decoupled look-back state of the geometry kernel
-    unsigned int *lb_ticket;        // virtual block id dispenser
-    Rec *recs;                // [cap_records]
-    uint32_t *rec_row_off;    // [cap_records+1] first (record, scanline) item of each record; [n] = total
+    // The geometry kernel never waits for other blocks: a block takes a region of `recs` with one atomic
+    // (slots are in block-arrival order), publishes (scanlines << 30 | records), and the last block to
+    // finish scans the aggregates; k_rec_index then lists the slots in primitive order.
+    unsigned long long *blk_agg;    // [ceil(cap_prims/256)] scanlines << 30 | records of each geometry block
+    unsigned long long *blk_base;   // [ceil(cap_prims/256)] exclusive prefix of blk_agg
+    uint32_t *blk_region;           // [ceil(cap_prims/256)] first record slot of the block
+    Rec *recs;                // [cap_records]   indexed by slot
+    uint32_t *rec_local_row;  // [cap_records]   by slot: scanline offset of the record inside its block
+    uint32_t *rec_slot;       // [cap_records+1] by primitive order: slot of the record
+    uint32_t *rec_row_off;    // [cap_records+1] by primitive order: first (record, scanline) item; [n] = total
     ClipTri *clip_pool;       // [cap_clip]
     // spans
     uint32_t *row_nseg;       // [cap_rows]   segments of each (record, scanline)

@@ -144,6 +144,7 @@ k_span_walk(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBu
     const uint32_t nrows = min(ctr->n_rows, wb.cap_rows);
     __shared__ uint32_t s_first;
     __shared__ uint32_t s_off[ST + 1];
+    __shared__ uint32_t s_slot[ST + 1];
     unsigned long long covered = 0;
     for (uint32_t i0 = blockIdx.x * ST; i0 < nrows; i0 += gridDim.x * ST) {
         // The ST items of this virtual block belong to at most ST consecutive records (every record has
@@ -159,6 +160,7 @@ k_span_walk(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBu
         for (uint32_t k = threadIdx.x; k <= ST; k += ST) {
             const uint32_t r = r0 + k;
             s_off[k] = r <= nrec ? wb.rec_row_off[r] : 0xffffffffu;
+            s_slot[k] = r < nrec ? wb.rec_slot[r] : 0u;
         }
         __syncthreads();
         const uint32_t i = i0 + threadIdx.x;
@@ -168,7 +170,7 @@ k_span_walk(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBu
                 const uint32_t mid = (lo + hi) >> 1;
                 if (s_off[mid] <= i) lo = mid; else hi = mid;
             }
-            const uint32_t rid = r0 + lo;
+            const uint32_t rid = s_slot[lo];  // records live at their block's slots, not in primitive order
             const RowSetup r = load_setup(wb.recs + rid);
             const int y = max(r.y0, 0) + (int)(i - s_off[lo]);
             const unsigned long long before = covered;
