@@ -109,8 +109,9 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n_max, con
 
 // ---- stable LSD radix sort on 8-bit digits -------------------------------------------
 
-constexpr int RADIX_THREADS = 256;
+constexpr int RADIX_THREADS = 1024;  // one CTA per SM: many warps hide the load latency of each chunk
 constexpr int RADIX_BINS = 256;
+constexpr int RADIX_WARPS = RADIX_THREADS / 32;
 
 __device__ __forceinline__ void radix_segment(uint32_t n, uint32_t &beg, uint32_t &end) {
     // contiguous segment of block b; multiple of RADIX_THREADS so sub-tiles stay aligned
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(RADIX_THREADS)
 k_radix_hist(const uint32_t *__restrict__ keys, const unsigned int *__restrict__ n_dev, uint32_t n_max, int shift,
              uint32_t *__restrict__ hist /*[256][grid]*/) {
     __shared__ uint32_t h[RADIX_BINS];
-    h[threadIdx.x] = 0;
+    if (threadIdx.x < RADIX_BINS) h[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t n = min(*n_dev, n_max);
     uint32_t beg, end;
@@ -134,7 +135,8 @@ k_radix_hist(const uint32_t *__restrict__ keys, const unsigned int *__restrict__
     for (uint32_t i = beg + threadIdx.x; i < end; i += RADIX_THREADS)
         atomicAdd(&h[(keys[i] >> shift) & 0xff], 1u);
     __syncthreads();
-    hist[blockIdx.x * RADIX_BINS + threadIdx.x] = h[threadIdx.x];  // [block][digit]: coalesced here and in the scatter
+    if (threadIdx.x < RADIX_BINS)
+        hist[blockIdx.x * RADIX_BINS + threadIdx.x] = h[threadIdx.x];  // [block][digit]: coalesced here and in the scatter
 }
 
 __global__ void __launch_bounds__(RADIX_THREADS)
@@ -143,28 +145,35 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
                 const unsigned int *__restrict__ n_dev, uint32_t n_max, int shift,
                 const uint32_t *__restrict__ hist /*[grid][256], raw counts*/) {
     __shared__ uint32_t cursor[RADIX_BINS];
-    __shared__ uint32_t warp_cnt[RADIX_THREADS / 32][RADIX_BINS];
-    __shared__ uint32_t s_scan[RADIX_THREADS / 32 + 1];
+    __shared__ uint32_t warp_cnt[RADIX_WARPS][RADIX_BINS];
+    __shared__ uint32_t s_scan[RADIX_WARPS + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    {   // Every block derives its own bucket bases from the raw histogram (151 KB, L2 resident): thread d sums
-        // digit d over all blocks (coalesced across threads) -- no separate scan kernel.
+    {   // Every block derives its own bucket bases from the raw histogram (151 KB, L2 resident): four threads
+        // per digit sum it over all blocks (coalesced across threads) -- no separate scan kernel.
+        const uint32_t d = threadIdx.x & (RADIX_BINS - 1), q = threadIdx.x / RADIX_BINS;
+        constexpr uint32_t Q = RADIX_THREADS / RADIX_BINS;
         uint32_t row = 0, before = 0;
-        for (uint32_t b = 0; b < gridDim.x; b++) {
-            const uint32_t v = hist[b * RADIX_BINS + threadIdx.x];
+        for (uint32_t b = q; b < gridDim.x; b += Q) {
+            const uint32_t v = hist[b * RADIX_BINS + d];
             row += v;
             if (b < blockIdx.x) before += v;
         }
+        warp_cnt[q][d] = row;
+        warp_cnt[Q + q][d] = before;
+        __syncthreads();
+        row = before = 0;
+        if (threadIdx.x < RADIX_BINS)
+            for (uint32_t k = 0; k < Q; k++) { row += warp_cnt[k][d]; before += warp_cnt[Q + k][d]; }
         uint32_t total;
         const uint32_t digit_base = block_excl_scan<RADIX_THREADS>(row, s_scan, &total);
-        cursor[threadIdx.x] = digit_base + before;
+        if (threadIdx.x < RADIX_BINS) cursor[d] = digit_base + before;
     }
     __syncthreads();
     const uint32_t n = min(*n_dev, n_max);
     uint32_t beg, end;
     radix_segment(n, beg, end);
     for (uint32_t base = beg; base < end; base += RADIX_THREADS) {
-#pragma unroll
-        for (int w = 0; w < RADIX_THREADS / 32; w++) warp_cnt[w][threadIdx.x] = 0;
+        for (int k = threadIdx.x; k < RADIX_WARPS * RADIX_BINS; k += RADIX_THREADS) (&warp_cnt[0][0])[k] = 0;
         __syncthreads();
         const uint32_t i = base + threadIdx.x;
         const bool valid = i < end;
@@ -179,26 +188,24 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
             if (rank == 0) warp_cnt[warp][d] = __popc(peers);
         }
         __syncthreads();
-        // thread t turns the per-warp counts of digit t into exclusive offsets
-        {
-            uint32_t run = 0;
-#pragma unroll
-            for (int w = 0; w < RADIX_THREADS / 32; w++) {
+        // thread t < 256 turns the per-warp counts of digit t into exclusive offsets
+        uint32_t run = 0;
+        if (threadIdx.x < RADIX_BINS) {
+#pragma unroll 8
+            for (int w = 0; w < RADIX_WARPS; w++) {
                 uint32_t c = warp_cnt[w][threadIdx.x];
                 warp_cnt[w][threadIdx.x] = run;
                 run += c;
             }
-            // stash the digit total in the high half via a second array-free trick:
-            // cursor is advanced after the scatter below, so keep `run` in a register.
-            __syncthreads();
-            if (valid) {
-                uint32_t pos = cursor[d] + warp_cnt[warp][d] + rank;
-                keys_out[pos] = key;
-                vals_out[pos] = val;
-            }
-            __syncthreads();
-            cursor[threadIdx.x] += run;
         }
+        __syncthreads();
+        if (valid) {
+            uint32_t pos = cursor[d] + warp_cnt[warp][d] + rank;
+            keys_out[pos] = key;
+            vals_out[pos] = val;
+        }
+        __syncthreads();
+        if (threadIdx.x < RADIX_BINS) cursor[threadIdx.x] += run;
         __syncthreads();
     }
 }
