@@ -65,7 +65,6 @@ struct ProfSlot { cudaEvent_t e[PROF_EVENTS]; };
 struct fgl_ctx {
     int device;
     int w, h;
-    int tile_h;
     cudaStream_t stream;
     cudaStream_t copy_stream;          // H2D of streaming mesh uploads, overlapping the draw stream
     std::mutex mu;
@@ -260,8 +259,7 @@ int build_params(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const
     }
     p->width = c->w; p->height = c->h;
     p->tiles_x = (c->w + TILE_W - 1) / TILE_W;
-    p->tile_h = c->tile_h;
-    p->tiles_y = (c->h + c->tile_h - 1) / c->tile_h;
+    p->tiles_y = c->h;
     // Screen(w, h), matrix.go:119-128
     const double w2 = (double)c->w / 2, h2 = (double)c->h / 2;
     const double scr[16] = {w2, 0, 0, w2, 0, -h2, 0, h2, 0, 0, 0.5, 0.5, 0, 0, 0, 1};
@@ -365,11 +363,8 @@ int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const 
         }
         p.prim_info = c->prim_info;
     }
-    if (p.deferred && !c->wb.vis_winner) {  // visibility buffer of the deferred-shading path, tile-major
-        const size_t npx = (size_t)c->wb.ntiles * TILE_W * c->tile_h;
-        CK(c, dev_alloc(&c->wb.vis_winner, npx));
-        CK(c, dev_alloc(&c->wb.vis_w, 3 * npx));
-    }
+    if (p.deferred && !c->wb.vis_seg)  // winners of the deferred-shading path, strip-major
+        CK(c, dev_alloc(&c->wb.vis_seg, (size_t)c->wb.ntiles * TILE_W));
     rc = initial_capacity(c, p);
     if (rc) return rc;
     mesh_acquire(c, mesh);
@@ -476,17 +471,15 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     if (err == cudaSuccess) err = dev_alloc(&c->acc_dev, 1);
     if (err == cudaSuccess) err = dev_alloc(&c->scratch, 8);
     if (err == cudaSuccess) err = cudaMallocHost(reinterpret_cast<void **>(&c->host_counters), sizeof(DrawCounters));
-    {   // short tiles split dense regions over more CTAs; keep the tile id within 16 bits (two radix passes)
+    {   // strips of 64 x 1 pixels
         const int tx = (width + TILE_W - 1) / TILE_W;
-        c->tile_h = (long long)tx * ((height + 3) / 4) <= 65536 ? 4 : TILE_H_MAX;
-        c->wb.ntiles = (uint32_t)(tx * ((height + c->tile_h - 1) / c->tile_h));
+        c->wb.ntiles = (uint32_t)tx * (uint32_t)height;
         cudaDeviceProp prop;
         c->wb.nsm = cudaGetDeviceProperties(&prop, device) == cudaSuccess ? (uint32_t)prop.multiProcessorCount : 148u;
     }
     if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_start, c->wb.ntiles);
     if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_end, c->wb.ntiles);
     if (err == cudaSuccess) err = dev_alloc(&c->wb.busy_list, c->wb.ntiles);
-    if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_claimed, c->wb.ntiles);
     if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_ctl, 1);
     if (err == cudaSuccess && getenv("FGL_TILE_CLOCK")) {  // tuning aid: per-tile cycle counts of k_tile
         err = dev_alloc(&c->wb.tile_clock, (size_t)c->wb.ntiles * 2);
@@ -501,8 +494,8 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
         return rc;
     }
     c->stats.tiles_x = (uint32_t)((width + TILE_W - 1) / TILE_W);
-    c->stats.tiles_y = (uint32_t)((height + c->tile_h - 1) / c->tile_h);
-    c->stats.tile_w = TILE_W; c->stats.tile_h = (uint32_t)c->tile_h;
+    c->stats.tiles_y = (uint32_t)height;
+    c->stats.tile_w = TILE_W; c->stats.tile_h = 1;
     // NewContext: image.NewNRGBA is zeroed; ClearDepthBuffer() -> math.MaxFloat64 (context.go:64,79)
     launch_clear_color(c->color, npix, 0u, c->stream);
     launch_clear_depth(c->depth, npix, 1.7976931348623157e308, c->stream);
@@ -523,7 +516,7 @@ int fgl_context_destroy(fgl_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_work(c->wb);
     dev_free(c->wb.tile_start); dev_free(c->wb.tile_end); dev_free(c->wb.counters); dev_free(c->wb.tile_clock);
-    dev_free(c->wb.busy_list); dev_free(c->wb.tile_claimed); dev_free(c->wb.tile_ctl); dev_free(c->wb.vis_winner); dev_free(c->wb.vis_w);
+    dev_free(c->wb.tile_ctl); dev_free(c->wb.busy_list); dev_free(c->wb.vis_seg);
     dev_free(c->prim_info); dev_free(c->scratch); dev_free(c->gray16);
     dev_free(c->acc_dev); dev_free(c->color); dev_free(c->depth); dev_free(c->resolved);
     if (c->host_counters) cudaFreeHost(c->host_counters);

@@ -9,17 +9,13 @@
 
 namespace fgl {
 
-// ---- screen tiles -------------------------------------------------------------
-// Wide, short tiles: the reference walks each scanline left to right with
-// forward differencing (context.go:207-213); a span is cut into one segment per
-// tile column it covers, so wide tiles mean few segments.
-// Short: a segment never spans rows, so shrinking the tile height adds no segments; it only splits
-// dense regions over more CTAs (the kernel's duration is its heaviest tile, profiles/README.md).
-// The height is chosen per context: 4 rows while the tile count still fits the 16-bit sort key
-// (two radix passes), else 8.
+// ---- screen strips ------------------------------------------------------------
+// The framebuffer is binned into strips of 64 x 1 pixels.  The reference walks each scanline
+// left to right with forward differencing (context.go:207-213); a covered run is cut into one
+// segment per strip it crosses, so wide strips mean few segments, and a segment never spans
+// rows, so one-row strips add none.  One warp resolves a strip (fgl_raster.cu): a 64-bit mask
+// per lane describes the pixels a segment still has to write.
 constexpr int TILE_W = 64;
-constexpr int TILE_H_MAX = 8;
-constexpr int TILE_PIX = TILE_W * TILE_H_MAX;  // upper bound (shared-memory sizing)
 
 // ---- device mesh: planar SoA ----------------------------------------------------
 // plane(attr, v, c)[i] = attr_base[(v * ncomp + c) * n + i]; a warp reading one
@@ -66,33 +62,33 @@ struct __align__(16) Seg {
     double w0, w1, w2;  // w0,w1,w2 of context.go:208-213 at pixel x (before that pixel's increment)
     uint32_t rec;       // record index
     uint16_t x;         // first covered pixel (absolute column)
-    uint8_t yt;         // row inside the tile
+    uint8_t yt;         // unused (strips are one row tall)
     uint8_t cnt;        // covered pixels (1..TILE_W)
 };
 static_assert(sizeof(Seg) == 32, "Seg layout");
 
-// ---- binned segment: a Seg plus the fields of its record the ordered depth phase needs, gathered
-// into tile order so the tile kernel streams its bin with coalesced loads and no dependent fetches.
+// ---- binned segment: a Seg plus every field of its record the back end needs (depth phase, perspective
+// weights, attribute source), so that neither the strip kernel nor the shading kernel chases the record.
+// 128 bytes: one cache line per segment.
 struct __align__(16) SegV {
     double w0, w1, w2;
     double ra, z0, z1, z2;   // 1/area and the three screen depths: z = (b0*z0 + b1*z1) + b2*z2
     double a12, a20, a01;    // per-pixel increments of w0, w1, w2 (context.go:167-172)
-    uint32_t rec;
-    uint16_t x;
-    uint8_t yt, cnt;
-    uint32_t _pad[2];
+    double r0, r1, r2;       // 1 / Output.W of the three vertices, context.go:176-178
+    uint32_t src;            // primitive index in the mesh planes, or clip-pool triangle index
+    uint32_t flags;          // REC_* (vertex map, pool bit)
+    uint16_t x;              // first covered pixel (absolute column)
+    uint8_t yt, cnt;         // (unused), covered pixels (1..TILE_W)
+    uint32_t _pad[3];
 };
-static_assert(sizeof(SegV) == 96, "SegV layout");
+static_assert(sizeof(SegV) == 128, "SegV layout");
 
-// Tile work queue (device): busy tiles ordered heaviest-first (bucketed by log2 of the bin size),
-// pulled by persistent CTAs with an atomic head.
+// Strip work queue (device): k_tile_ranges lists the busy strips, warps of the strip kernel pull them.
 struct TileCtl {
-    uint32_t bucket_cnt[32];
-    uint32_t bucket_fill[32];
-    uint32_t nbusy;
-    uint32_t head_resolve, head_shade, _pad;
-    uint32_t sm_arrivals[256];  // CTAs of the tile kernel that have started on each SM
+    uint32_t nheavy, nlight;  // busy_list[0 .. nheavy) = heavy strips, busy_list[ntiles-1 .. ntiles-nlight] = the others
+    uint32_t head, _pad;
 };
+constexpr uint32_t HEAVY_SEGS = 96;  // a strip with at least this many segments is queued first
 
 // ---- per-draw device constants ------------------------------------------------------
 struct DrawParams {
@@ -104,8 +100,7 @@ struct DrawParams {
     const uint8_t *tex;
     int32_t tex_w, tex_h, tex_format, object_is_discard;
     // framebuffer
-    int32_t width, height, tiles_x, tiles_y;
-    int32_t tile_h, _pad_tile;  // rows per tile (4 or 8)
+    int32_t width, height, tiles_x, tiles_y;  // strips per row (ceil(width/64)), strip rows (= height)
     double screen[16];  // Screen(w,h), matrix.go:119-128
     // input
     MeshPlanes mesh;
@@ -148,27 +143,28 @@ struct WorkBuffers {
     // binning: stable sort of segment indices by tile
     uint32_t *seg_key[2];     // [cap_segs] tile id (ping-pong for the radix sort)
     uint32_t *seg_val[2];     // [cap_segs] segment index
-    uint32_t *tile_start;     // [ntiles]
+    uint32_t *tile_start;     // [ntiles]    bin of strip t = sorted positions [tile_start[t], tile_end[t])
     uint32_t *tile_end;       // [ntiles]
     SegV *segv;               // [cap_segs]  segments in (record, scanline, column) order; bins index into it
-    uint32_t *busy_list;      // [ntiles]    non-empty tiles, heaviest first
-    uint32_t *tile_claimed;   // [ntiles]    queue entry already taken (static first assignment + dynamic queue)
+    uint32_t *busy_list;      // [ntiles]    strips with a non-empty bin, heavy ones from the front, the rest from the back
     uint32_t nsm;             // SMs of the device
     TileCtl *tile_ctl;        // device
-    uint32_t *vis_winner;     // [ntiles*TILE_PIX] deferred shading: winning record per pixel, tile-major
-    double *vis_w;            // [3][ntiles*TILE_PIX] its w0,w1,w2 (allocated on the first deferred draw)
-    unsigned long long *tile_clock;  // [ntiles][2] (cycles, smid) of the last k_tile launch; null unless FGL_TILE_CLOCK=1
+    uint32_t *vis_seg;        // [ntiles*TILE_W] deferred shading: per pixel of a busy strip, the segment (index into
+                              //                 segv) whose fragment won, or 0xffffffff (allocated on the first deferred draw)
+    unsigned long long *tile_clock;  // [ntiles][2] (cycles, smid<<32|segments) of the last k_strip launch; null unless FGL_TILE_CLOCK=1
     uint32_t *scan_tmp;       // block sums for scans / radix histograms
     DrawCounters *counters;   // device
-    uint32_t cap_prims, cap_records, cap_rows, cap_segs, cap_clip, ntiles, scan_tmp_words;
+    uint32_t cap_prims, cap_records, cap_rows, cap_segs, cap_clip, ntiles, scan_tmp_words;  // ntiles = strips = tiles_x * height
 };
 
 #ifdef __CUDACC__
-// Index (relative to the draw's first primitive) of the mesh primitive a record came from.
+// Index (relative to the draw's first primitive) of the mesh primitive a record / segment came from.
+__device__ __forceinline__ uint32_t src_primitive(const WorkBuffers &wb, const DrawParams &p, uint32_t src, uint32_t flags) {
+    return ((flags & REC_SRC_POOL) ? wb.clip_pool[src].prim : src) - p.first;
+}
 __device__ __forceinline__ uint32_t rec_primitive(const WorkBuffers &wb, const DrawParams &p, uint32_t rec) {
     const Rec *rp = wb.recs + rec;
-    const uint32_t src = rp->src;
-    return ((rp->flags & REC_SRC_POOL) ? wb.clip_pool[src].prim : src) - p.first;
+    return src_primitive(wb, p, rp->src, rp->flags);
 }
 #endif
 

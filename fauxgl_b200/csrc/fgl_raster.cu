@@ -1,8 +1,9 @@
-// fgl_raster.cu -- tile-parallel, ordered back end.  Persistent CTAs pull busy 64x8
-// screen tiles heaviest-first from a device queue, keep the tile's depth (f64) (and
-// colour, when shading inline) in shared memory, consume the tile's bin of span
-// segments in primitive order and write the tile back once, coalesced -- replacing
-// the reference's per-pixel mutex array.
+// fgl_raster.cu -- strip-parallel, ordered back end.  The framebuffer is cut into
+// strips of 64 x 1 pixels; the bin of a strip is the range of the stably sorted
+// segment array that carries its id.  ONE WARP owns a strip: it keeps the strip's
+// depth (f64) -- and colour, when shading inline -- in shared memory, consumes the
+// bin 32 segments at a time in primitive order, and writes the strip back once,
+// coalesced.  This replaces the reference's per-pixel mutex array.
 //
 // Replaces the per-pixel body of Context.rasterize (context.go:207-273),
 // InterpolateVertexes (vertex.go:18-47), the three built-in Fragment shaders
@@ -10,24 +11,36 @@
 // Color.NRGBA (color.go:56) and the depth retest / write / blend (context.go:245-273).
 //
 // Arithmetic parity.  Each segment carries the reference's forward-differenced
-// edge values at its first pixel (fgl_span.cu); the kernels here continue the same
+// edge values at its first pixel (fgl_span.cu); the lanes here continue the same
 // `w += a` chain (context.go:211-213), so barycentrics, depth and colour are
 // bit-identical to a sequential run of the reference in triangle-index order.
 //
-// Ordering.  RT segments are resolved in parallel; pixels touched by several
-// segments of a batch are settled in rounds: every pending fragment bids its
-// batch index with a shared-memory atomicMin on a per-pixel ticket, the lowest
-// wins, applies the reference's depth test / retest / write to the tile copy
-// and retires.  That is index order per pixel, which makes `<=` ties,
-// DepthBias, blending and UpdatedPixels well defined.
+// Ordering without barriers.  Lane i of a chunk holds the i-th segment in
+// primitive order.  If no two segments of the chunk share a pixel (the common
+// case, one popcount test) every lane just walks its segment.  Otherwise:
+//   * deferred mode: every segment lane stages the depths of its fragments and
+//     registers itself in a per-pixel cover mask; then every PIXEL lane replays
+//     the fragments of its pixel in lane order == primitive order against a
+//     running depth in registers -- the serial part of the reference's per-pixel
+//     order shrinks to one shared-memory load and a compare per fragment;
+//   * inline mode: a pixel is `ready` for lane i when no earlier lane still wants
+//     it (exclusive prefix-OR of the pending masks); ready pixels are resolved,
+//     the masks shrink, until all are empty.
+// Either way every pixel sees its fragments in primitive order, which makes `<=`
+// ties, DepthBias, blending and UpdatedPixels well defined, and the only
+// synchronisation is __syncwarp.  (An earlier version resolved 256 segments per
+// CTA in rounds separated by __syncthreads with shared-memory tickets: 35 cycles
+// per segment, and the heaviest 64x4 tile of the benchmark frame WAS the kernel's
+// duration, profiles/README.md.)
 //
 // Deferred shading.  When the draw's shader can neither discard nor blend
 // (SolidColor, or Phong with an ObjectColor and no texture, alpha != 0 and no
 // effective blending) the fragment colour cannot influence any depth decision:
-// k_tile_resolve settles depth only and records, per pixel, the winning record and
-// its edge values; k_shade then colours each pixel's FINAL winner once, as a
-// separate full-occupancy kernel (no per-tile serial tail).  Otherwise
-// k_tile_inline shades fragments in order, exactly like the reference.
+// the strip kernel settles depth only and records, per pixel, WHICH segment won;
+// k_shade then colours each pixel's FINAL winner once, pixel-parallel at full
+// occupancy: it re-walks the winner's chain of adds from the segment start to the
+// pixel (a few DADDs) and evaluates Phong.  Otherwise fragments are shaded inline,
+// in order, exactly like the reference.
 #include "fgl_internal.h"
 #include "fgl_block.cuh"
 #include "fgl_math.cuh"
@@ -35,272 +48,316 @@
 
 namespace fgl {
 
-constexpr int RT = 256;  // threads per CTA == segments per batch
-constexpr uint32_t NO_TICKET = 0xffffffffu;
+constexpr int SWARPS = 8;               // warps (= strips in flight) per CTA
+constexpr int STHREADS = SWARPS * 32;
 constexpr uint32_t NO_WINNER = 0xffffffffu;
-static_assert(TILE_W <= 64, "the pending mask is one 64-bit word per segment");
-static_assert((TILE_W * 4) % RT == 0, "k_shade splits a tile into chunks of RT pixels");
+constexpr uint32_t NO_SEG = 0xffffffffu;
+static_assert(TILE_W == 64, "a strip is one 64-bit pending mask wide");
 
-// ---- busy-tile queue, heaviest first ------------------------------------------------------------------
-__global__ void k_tile_bucket(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ tile_end,
-                              uint32_t ntiles, TileCtl *ctl) {
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) {
-        const uint32_t cnt = tile_end[t] - tile_start[t];
-        if (cnt) atomicAdd(&ctl->bucket_cnt[31 - __clz(cnt)], 1u);
+constexpr int ZCAP = 256;  // fragments of a chunk the pixel-parallel resolution can stage
+template <bool DEFERRED> struct StripMem;
+template <> struct StripMem<true> {
+    double depth[TILE_W];
+    uint32_t winseg[TILE_W]; // segment (index into segv) whose fragment currently owns the pixel
+    // pixel-parallel resolution of a chunk whose segments overlap
+    double zbuf[ZCAP];       // depth of every fragment of the chunk, segment-major
+    uint32_t cover[TILE_W];  // lanes (= segments, in primitive order) that cover the pixel
+    uint32_t segidx[32];     // segv index of the lane's segment
+    uint32_t upd[32];        // UpdatedPixels per segment (per-primitive RasterizeInfo only)
+    uint16_t segbase[32];    // first zbuf slot of the segment
+    uint8_t segxa[32];       // its first pixel
+};
+template <> struct StripMem<false> {
+    double depth[TILE_W];
+    uint32_t color[TILE_W];
+};
+
+// Exclusive prefix-OR over the lanes of a warp.
+FGL_DI unsigned long long warp_excl_or(unsigned long long v, int lane) {
+    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t tl = __shfl_up_sync(0xffffffffu, lo, o), th = __shfl_up_sync(0xffffffffu, hi, o);
+        if (lane >= o) { lo |= tl; hi |= th; }
     }
-}
-__global__ void k_tile_enqueue(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ tile_end,
-                               uint32_t ntiles, TileCtl *ctl, uint32_t *__restrict__ busy_list) {
-    __shared__ uint32_t s_base[32];
-    if (threadIdx.x < 32) {  // bucket b starts after all heavier buckets
-        uint32_t base = 0;
-        for (int b = 31; b > (int)threadIdx.x; b--) base += ctl->bucket_cnt[b];
-        s_base[threadIdx.x] = base;
-        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->nbusy = base + ctl->bucket_cnt[0];
-    }
-    __syncthreads();
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) {
-        const uint32_t cnt = tile_end[t] - tile_start[t];
-        if (cnt) {
-            const int b = 31 - __clz(cnt);
-            busy_list[s_base[b] + atomicAdd(&ctl->bucket_fill[b], 1u)] = t;
-        }
-    }
+    lo = __shfl_up_sync(0xffffffffu, lo, 1);
+    hi = __shfl_up_sync(0xffffffffu, hi, 1);
+    if (lane == 0) lo = hi = 0;
+    return ((unsigned long long)hi << 32) | lo;
 }
 
-// ---- the ordered tile kernel ------------------------------------------------------------------------
-// One fragment, inline mode: context.go:229-273 for a pixel whose ticket this thread holds.
+// One fragment, inline mode: context.go:229-273 for strip pixel pi.
 FGL_DI void fragment_inline(const DrawParams &p, const fgl_state &st, const WorkBuffers &wb, const SegV &v,
-                            double w0, double w1, double w2, int pi, double *s_depth, uint32_t *s_color,
-                            unsigned long long &updated) {
+                            double w0, double w1, double w2, int pi, StripMem<false> &sm, unsigned long long &updated) {
     const double b0 = w0 * v.ra, b1 = w1 * v.ra, b2 = w2 * v.ra;
     const double z = b0 * v.z0 + b1 * v.z1 + b2 * v.z2;  // context.go:230
     const double bz = z + st.depth_bias;
-    const double dcur = s_depth[pi];
+    const double dcur = sm.depth[pi];
     if (st.read_depth && bz > dcur) return;               // context.go:232
-    const Rec *rp = wb.recs + v.rec;
-    const double bx = b0 * rp->r0, by = b1 * rp->r1, bzz = b2 * rp->r2;  // context.go:236
+    const double bx = b0 * v.r0, by = b1 * v.r1, bzz = b2 * v.r2;  // context.go:236
     const double bw = 1 / (bx + by + bzz);
-    AttrSrc a{&p, wb.clip_pool, rp->src, rp->flags};
+    AttrSrc a{&p, wb.clip_pool, v.src, v.flags};
     const C4 color = shade_fragment(p, a, bx, by, bzz, bw);
     if (c_is_discard(color)) return;                      // context.go:241
     if (bz <= dcur || !st.read_depth) {                   // context.go:248
         updated++;
-        if (st.write_depth) s_depth[pi] = z;
+        if (st.write_depth) sm.depth[pi] = z;
         if (st.write_color) {
             const uint32_t c8 = c_nrgba(color);
-            if (st.alpha_blend && color.a < 1) s_color[pi] = blend_over(s_color[pi], c8);
-            else s_color[pi] = c8;
+            if (st.alpha_blend && color.a < 1) sm.color[pi] = blend_over(sm.color[pi], c8);
+            else sm.color[pi] = c8;
         }
     }
+}
+
+// Deferred mode, one fragment whose depth z is known: context.go:232 early-out, then (no discard possible)
+// the retest at :248; the winning segment is remembered for the shading kernel.
+FGL_DI void resolve_deferred(const fgl_state &st, StripMem<true> &sm, int pi, double z, uint32_t seg,
+                             unsigned long long &updated) {
+    const double bz = z + st.depth_bias;
+    const double dcur = sm.depth[pi];
+    if (!(st.read_depth && bz > dcur) && (bz <= dcur || !st.read_depth)) {
+        updated++;
+        if (st.write_depth) sm.depth[pi] = z;
+        sm.winseg[pi] = seg;
+    }
+}
+
+FGL_DI uint32_t strip_at(const WorkBuffers &wb, uint32_t nheavy, uint32_t q) {
+    return q < nheavy ? wb.busy_list[q] : wb.busy_list[wb.ntiles - 1u - (q - nheavy)];
 }
 
 // EACH: also attribute UpdatedPixels to the primitive of every segment (fgl_draw_*_each).
 template <bool DEFERRED, bool EACH>
-__global__ void __launch_bounds__(RT, 3)
-k_tile(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb,
-       const uint32_t *__restrict__ seg_order, uint32_t *__restrict__ gcolor, double *__restrict__ gdepth) {
+__global__ void __launch_bounds__(STHREADS, DEFERRED ? 4 : 3)
+k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb,
+        const uint32_t *__restrict__ seg_order, uint32_t *__restrict__ gcolor, double *__restrict__ gdepth) {
     if (wb.counters->overflow) return;  // work buffers too small: the host regrows and re-issues the draw
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_depth = reinterpret_cast<double *>(smem_raw);                                 // [TILE_PIX]
-    double *s_w = s_depth + TILE_PIX;                                                        // [3][TILE_PIX] (deferred)
-    uint32_t *s_color = reinterpret_cast<uint32_t *>(s_w + (DEFERRED ? 3 * TILE_PIX : 0));  // [TILE_PIX] (inline)
-    uint32_t *s_ticket = s_color + (DEFERRED ? 0 : TILE_PIX);                                // [TILE_PIX]
-    uint32_t *s_winner = s_ticket + TILE_PIX;                                                // [TILE_PIX] (deferred)
-    __shared__ uint32_t s_q;
-
-    const int tid = threadIdx.x;
+    __shared__ StripMem<DEFERRED> s_all[SWARPS];
+    const int lane = threadIdx.x & 31;
+    StripMem<DEFERRED> &sm = s_all[threadIdx.x >> 5];
     const fgl_state st = p.state;
     unsigned long long my_updated = 0;
-    TileCtl *ctl = wb.tile_ctl;
-
-    const int tpix = TILE_W * p.tile_h;
-    bool first = true;
-    while (true) {
-        __syncthreads();
-        if (tid == 0) {
-            // Queue entries are ordered heaviest-first.  A CTA's FIRST tile is assigned by (SM, arrival
-            // order on that SM) so that the heaviest tiles start on different SMs instead of on the few
-            // SMs whose CTAs happen to start first; afterwards tiles are pulled dynamically.  Every entry
-            // is claimed with an atomic exchange, so each tile is processed exactly once.
-            const uint32_t nbusy = ctl->nbusy;
-            uint32_t q = 0xffffffffu;
-            if (first) {
-                unsigned smid;
-                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-                if (smid < wb.nsm && smid < 256u) {
-                    const uint32_t slot = atomicAdd(&ctl->sm_arrivals[smid], 1u);
-                    const unsigned long long cand = (unsigned long long)slot * wb.nsm + smid;
-                    if (cand < nbusy && atomicExch(&wb.tile_claimed[cand], 1u) == 0u) q = (uint32_t)cand;
-                }
-            }
-            while (q == 0xffffffffu) {
-                const uint32_t qq = atomicAdd(&ctl->head_resolve, 1u);
-                if (qq >= nbusy) break;
-                if (atomicExch(&wb.tile_claimed[qq], 1u) == 0u) q = qq;
-            }
-            s_q = q;
-        }
-        first = false;
-        __syncthreads();
-        const uint32_t q = s_q;
-        if (q == 0xffffffffu) break;
-        const uint32_t tile = wb.busy_list[q];
-        const uint32_t bin_beg = wb.tile_start[tile], bin_end = wb.tile_end[tile];
-        const long long t_begin = wb.tile_clock ? clock64() : 0;
-        const int tile_x0 = (int)(tile % (uint32_t)p.tiles_x) * TILE_W;
-        const int tile_y0 = (int)(tile / (uint32_t)p.tiles_x) * p.tile_h;
-        const int tw = min(TILE_W, p.width - tile_x0);   // valid columns of this tile
-        const int th = min(p.tile_h, p.height - tile_y0);  // valid rows
-
-        // ---- load the tile ----------------------------------------------------------------------
-        for (int i = tid; i < tpix; i += RT) {
-            const int lx = i % TILE_W, ly = i / TILE_W;
-            s_ticket[i] = NO_TICKET;
-            if (DEFERRED) s_winner[i] = NO_WINNER;
-            if (lx < tw && ly < th) {
-                const size_t g = (size_t)(tile_y0 + ly) * p.width + (tile_x0 + lx);
-                s_depth[i] = gdepth[g];
-                if (!DEFERRED) s_color[i] = gcolor[g];
-            }
-        }
-        __syncthreads();
-
-        // The bin is a range of the sorted index array; segments are fetched through it two batches
-        // ahead (index) / one batch ahead (segment), so neither load sits on the critical path.
-        auto load_idx = [&](uint32_t i) { return i < bin_end ? seg_order[i] : 0xffffffffu; };
-        auto load_seg = [&](uint32_t idx) {
-            SegV s;
-            s.cnt = 0; s.x = 0; s.yt = 0;
-            if (idx != 0xffffffffu) s = wb.segv[idx];
-            return s;
-        };
-        SegV v_next = load_seg(load_idx(bin_beg + tid));
-        uint32_t idx_next2 = load_idx(bin_beg + RT + tid);
-        for (uint32_t batch = bin_beg; batch < bin_end; batch += RT) {
-            const SegV v = v_next;
-            v_next = load_seg(idx_next2);
-            idx_next2 = load_idx(batch + 2 * RT + tid);
-            const int xa = (int)v.x, cnt = (int)v.cnt;
-            const int rowbase = (int)v.yt * TILE_W - tile_x0;
-            unsigned long long pend = cnt > 0 ? ((cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull)) << (xa - tile_x0)) : 0ull;
-
-            // ---- ordered resolution in rounds ---------------------------------------------------
-            while (true) {
-                if (pend) {
-                    unsigned long long m = pend;
-                    while (m) {
-                        const int bit = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        atomicMin(&s_ticket[(int)v.yt * TILE_W + bit], (uint32_t)tid);
-                    }
-                }
-                __syncthreads();
-                if (pend) {
-                    double w0 = v.w0, w1 = v.w1, w2 = v.w2;
-                    const unsigned long long updated_before = my_updated;
-                    for (int x = xa; x < xa + cnt; x++) {
-                        const unsigned long long bitm = 1ull << (x - tile_x0);
-                        const int pi = rowbase + x;
-                        if ((pend & bitm) && s_ticket[pi] == (uint32_t)tid) {
-                            pend &= ~bitm;
-                            s_ticket[pi] = NO_TICKET;
-                            if (DEFERRED) {
-                                const double b0 = w0 * v.ra, b1 = w1 * v.ra, b2 = w2 * v.ra;
-                                const double z = b0 * v.z0 + b1 * v.z1 + b2 * v.z2;  // context.go:230
-                                const double bz = z + st.depth_bias;
-                                const double dcur = s_depth[pi];
-                                // context.go:232 early-out, then (no discard possible) the retest at :248
-                                if (!(st.read_depth && bz > dcur) && (bz <= dcur || !st.read_depth)) {
-                                    my_updated++;
-                                    if (st.write_depth) s_depth[pi] = z;
-                                    if (st.write_color) {
-                                        s_winner[pi] = v.rec;
-                                        s_w[pi] = w0; s_w[TILE_PIX + pi] = w1; s_w[2 * TILE_PIX + pi] = w2;
-                                    }
-                                }
-                            } else {
-                                fragment_inline(p, st, wb, v, w0, w1, w2, pi, s_depth, s_color, my_updated);
-                            }
-                        }
-                        w0 += v.a12; w1 += v.a20; w2 += v.a01;  // context.go:211-213
-                    }
-                    if (EACH && my_updated != updated_before)
-                        atomicAdd(&p.prim_info[2 * (size_t)rec_primitive(wb, p, v.rec) + 1], my_updated - updated_before);
-                }
-                if (!__syncthreads_or(pend != 0)) break;
-            }
-        }
-
-        // ---- write the tile back -----------------------------------------------------------------
-        const size_t vbase = (size_t)tile * tpix;
-        const size_t vplane = (size_t)wb.ntiles * tpix;
-        for (int i = tid; i < tpix; i += RT) {
-            const int lx = i % TILE_W, ly = i / TILE_W;
-            if (lx < tw && ly < th) {
-                const size_t g = (size_t)(tile_y0 + ly) * p.width + (tile_x0 + lx);
-                if (st.write_depth) gdepth[g] = s_depth[i];
-                if (!DEFERRED) gcolor[g] = s_color[i];
-            }
-            if (DEFERRED && st.write_color) {
-                const uint32_t win = s_winner[i];
-                wb.vis_winner[vbase + i] = win;
-                if (win != NO_WINNER) {
-                    wb.vis_w[vbase + i] = s_w[i];
-                    wb.vis_w[vplane + vbase + i] = s_w[TILE_PIX + i];
-                    wb.vis_w[2 * vplane + vbase + i] = s_w[2 * TILE_PIX + i];
-                }
-            }
-        }
-        if (wb.tile_clock && tid == 0) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            wb.tile_clock[2 * tile] = (unsigned long long)(clock64() - t_begin);
-            wb.tile_clock[2 * tile + 1] = ((unsigned long long)smid << 32) | (bin_end - bin_beg);
-        }
+    if constexpr (DEFERRED) {  // scratch of the pixel-parallel resolution: every use leaves it clean
+        sm.cover[lane] = 0; sm.cover[lane + 32] = 0;
+        sm.upd[lane] = 0;
+        __syncwarp();
     }
 
-    // UpdatedPixels: one atomic per warp per CTA lifetime
+    // Busy strips, heavy ones first (k_tile_ranges), are pulled dynamically; the pull for the NEXT strip
+    // and its bin range are requested while the current strip is processed.
+    const uint32_t nheavy = wb.tile_ctl->nheavy, nbusy = nheavy + wb.tile_ctl->nlight;
+    const uint32_t pull = nbusy > 32768u ? 4u : 1u;  // same-address atomics: keep their number in the low thousands
+    uint32_t q = 0, q_end = 0;  // current pull [q, q_end)
+    if (lane == 0) q = atomicAdd(&wb.tile_ctl->head, pull);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    q_end = min(q + pull, nbusy);
+    uint32_t strip = 0, bin_beg = 0, bin_end = 0;
+    if (q < nbusy) {
+        strip = strip_at(wb, nheavy, q);
+        bin_beg = wb.tile_start[strip]; bin_end = wb.tile_end[strip];
+    }
+    while (q < nbusy) {
+        // request the next strip: the atomic now, its dependent loads further down
+        uint32_t nq = q + 1, nq_end = q_end;
+        if (nq >= q_end) {
+            if (lane == 0) nq = atomicAdd(&wb.tile_ctl->head, pull);
+        }
+        const long long t_begin = wb.tile_clock ? clock64() : 0;
+        const uint32_t nseg = bin_end - bin_beg;
+        const int x0 = (int)(strip % (uint32_t)p.tiles_x) * TILE_W;
+        const int y = (int)(strip / (uint32_t)p.tiles_x);
+        const int tw = min(TILE_W, p.width - x0);  // valid columns of this strip
+        const size_t grow = (size_t)y * p.width + x0;
+
+        // ---- load the strip --------------------------------------------------------------
+        __syncwarp();
+        uint32_t idx_next = bin_beg + lane < bin_end ? seg_order[bin_beg + lane] : NO_SEG;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int i = lane + 32 * h;
+            if constexpr (DEFERRED) sm.winseg[i] = NO_WINNER;
+            if (i < tw) {
+                sm.depth[i] = gdepth[grow + i];
+                if constexpr (!DEFERRED) sm.color[i] = gcolor[grow + i];
+            }
+        }
+        if (q + 1 >= q_end) {
+            nq = __shfl_sync(0xffffffffu, nq, 0);
+            nq_end = min(nq + pull, nbusy);
+        }
+        uint32_t nstrip = 0;
+        if (nq < nbusy) nstrip = strip_at(wb, nheavy, nq);
+        __syncwarp();
+        const unsigned long long updated_at_start = my_updated;
+
+        // ---- the bin, 32 segments at a time ------------------------------------------------
+        for (uint32_t chunk = bin_beg; chunk < bin_end; chunk += 32) {
+            const uint32_t idx = idx_next;
+            idx_next = chunk + 32 + lane < bin_end ? seg_order[chunk + 32 + lane] : NO_SEG;
+            SegV v;
+            v.cnt = 0; v.x = (uint16_t)x0;
+            if (idx != NO_SEG) v = wb.segv[idx];
+            const int xa = (int)v.x - x0, cnt = (int)v.cnt;
+            unsigned long long pend = cnt > 0 ? ((cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull)) << xa) : 0ull;
+            const unsigned long long updated_before = my_updated;
+
+            // no two segments of the chunk overlap <=> popcounts add up
+            const uint32_t orl = __reduce_or_sync(0xffffffffu, (uint32_t)pend);
+            const uint32_t orh = __reduce_or_sync(0xffffffffu, (uint32_t)(pend >> 32));
+            const uint32_t nfrag = __reduce_add_sync(0xffffffffu, (uint32_t)cnt);
+            const bool disjoint = nfrag == (uint32_t)(__popc(orl) + __popc(orh));
+            bool staged = false;
+            if constexpr (DEFERRED) {
+                if (!disjoint && nfrag <= (uint32_t)ZCAP) {
+                    // (1) every segment lane stages the depths of its fragments and registers itself in the
+                    // cover mask of its pixels; (2) every PIXEL lane replays the fragments of its pixel in lane
+                    // order == primitive order against a running depth in registers.
+                    staged = true;
+                    const uint32_t fbase = warp_incl_scan((uint32_t)cnt) - (uint32_t)cnt;
+                    sm.segbase[lane] = (uint16_t)fbase;
+                    sm.segxa[lane] = (uint8_t)xa;
+                    sm.segidx[lane] = idx;
+                    {
+                        double w0 = v.w0, w1 = v.w1, w2 = v.w2;
+                        for (int k = 0; k < cnt; k++) {
+                            const double b0 = w0 * v.ra, b1 = w1 * v.ra, b2 = w2 * v.ra;
+                            sm.zbuf[fbase + k] = b0 * v.z0 + b1 * v.z1 + b2 * v.z2;  // context.go:230
+                            atomicOr(&sm.cover[xa + k], 1u << lane);
+                            w0 += v.a12; w1 += v.a20; w2 += v.a01;  // context.go:211-213
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int pix = lane + 32 * h;
+                        uint32_t m = sm.cover[pix];
+                        if (m) {
+                            sm.cover[pix] = 0;
+                            double d = sm.depth[pix];
+                            int win = -1;
+                            while (m) {
+                                const int j = __ffs(m) - 1;
+                                m &= m - 1;
+                                const double z = sm.zbuf[(int)sm.segbase[j] + pix - (int)sm.segxa[j]];
+                                const double bz = z + st.depth_bias;
+                                // context.go:232 early-out, then (no discard possible) the retest at :248
+                                if (!(st.read_depth && bz > d) && (bz <= d || !st.read_depth)) {
+                                    my_updated++;
+                                    if (st.write_depth) d = z;
+                                    win = j;
+                                    if constexpr (EACH) atomicAdd(&sm.upd[j], 1u);
+                                }
+                            }
+                            if (win >= 0) {
+                                if (st.write_depth) sm.depth[pix] = d;
+                                sm.winseg[pix] = sm.segidx[win];
+                            }
+                        }
+                    }
+                    if constexpr (EACH) {
+                        __syncwarp();
+                        const uint32_t u = sm.upd[lane];
+                        sm.upd[lane] = 0;
+                        if (u) atomicAdd(&p.prim_info[2 * (size_t)src_primitive(wb, p, v.src, v.flags) + 1], (unsigned long long)u);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (!staged) {
+                while (true) {
+                    const unsigned long long ready = disjoint ? pend : (pend & ~warp_excl_or(pend, lane));
+                    if (ready) {
+                        double w0 = v.w0, w1 = v.w1, w2 = v.w2;
+                        const int last = 63 - __clzll((long long)ready);
+                        for (int pi = xa; pi <= last; pi++) {
+                            if ((ready >> pi) & 1ull) {
+                                if constexpr (DEFERRED) {
+                                    const double b0 = w0 * v.ra, b1 = w1 * v.ra, b2 = w2 * v.ra;
+                                    const double z = b0 * v.z0 + b1 * v.z1 + b2 * v.z2;  // context.go:230
+                                    resolve_deferred(st, sm, pi, z, idx, my_updated);
+                                } else {
+                                    fragment_inline(p, st, wb, v, w0, w1, w2, pi, sm, my_updated);
+                                }
+                            }
+                            w0 += v.a12; w1 += v.a20; w2 += v.a01;  // context.go:211-213
+                        }
+                        pend &= ~ready;
+                    }
+                    __syncwarp();
+                    if (disjoint || !__any_sync(0xffffffffu, pend != 0)) break;
+                }
+                if (EACH && my_updated != updated_before)
+                    atomicAdd(&p.prim_info[2 * (size_t)src_primitive(wb, p, v.src, v.flags) + 1], my_updated - updated_before);
+            }
+        }
+        // the next strip's bin range (its id has arrived by now)
+        uint32_t nbeg = 0, nend = 0;
+        if (nq < nbusy) { nbeg = wb.tile_start[nstrip]; nend = wb.tile_end[nstrip]; }
+
+        // ---- write the strip back ---------------------------------------------------------------
+        const bool touched = __any_sync(0xffffffffu, my_updated != updated_at_start);
+        if constexpr (DEFERRED) {
+            if (st.write_color) {  // k_shade reads the winners of every busy strip
+                wb.vis_seg[(size_t)strip * TILE_W + lane] = sm.winseg[lane];
+                wb.vis_seg[(size_t)strip * TILE_W + lane + 32] = sm.winseg[lane + 32];
+            }
+        } else {
+            if (touched && st.write_color) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int i = lane + 32 * h;
+                    if (i < tw) gcolor[grow + i] = sm.color[i];
+                }
+            }
+        }
+        if (touched && st.write_depth) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int i = lane + 32 * h;
+                if (i < tw) gdepth[grow + i] = sm.depth[i];
+            }
+        }
+        if (wb.tile_clock && lane == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            wb.tile_clock[2 * strip] = (unsigned long long)(clock64() - t_begin);
+            wb.tile_clock[2 * strip + 1] = ((unsigned long long)smid << 32) | nseg;
+        }
+        q = nq; q_end = nq_end; strip = nstrip; bin_beg = nbeg; bin_end = nend;
+    }
+
+    // UpdatedPixels: one atomic per warp per kernel
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) my_updated += __shfl_down_sync(0xffffffffu, my_updated, o);
-    if ((tid & 31) == 0 && my_updated) atomicAdd(&wb.counters->updated_pixels, my_updated);
+    if (lane == 0 && my_updated) atomicAdd(&wb.counters->updated_pixels, my_updated);
 }
 
-// ---- deferred shading of the final winners ---------------------------------------------------------------
-__global__ void __launch_bounds__(RT, 4)
+// ---- deferred shading of the final winners -------------------------------------------------------------
+// One thread per pixel of every busy strip.  The deferred mode only admits SolidColor, or Phong with an
+// ObjectColor and no texture (fgl_api.cu), so the attribute set is fixed: 9 normal + 9 position components.
+constexpr int SHT = 256;
+__global__ void __launch_bounds__(SHT, 4)
 k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb, uint32_t *__restrict__ gcolor) {
     if (wb.counters->overflow) return;
-    const int tpix = TILE_W * p.tile_h;
-    const uint32_t CHUNKS = (uint32_t)tpix / RT;
-    __shared__ uint32_t s_q;
-    TileCtl *ctl = wb.tile_ctl;
-    const size_t vplane = (size_t)wb.ntiles * tpix;
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_q = atomicAdd(&ctl->head_shade, 1u);
-        __syncthreads();
-        const uint32_t q = s_q;
-        if (q >= ctl->nbusy * CHUNKS) break;
-        const uint32_t tile = wb.busy_list[q / CHUNKS];
-        const int pi = (int)(q % CHUNKS) * RT + (int)threadIdx.x;
-        const size_t vi = (size_t)tile * tpix + pi;
-        const uint32_t rid = wb.vis_winner[vi];
-        if (rid == NO_WINNER) continue;
-        const int x = (int)(tile % (uint32_t)p.tiles_x) * TILE_W + pi % TILE_W;
-        const int y = (int)(tile / (uint32_t)p.tiles_x) * p.tile_h + pi / TILE_W;
+    const uint32_t nheavy = wb.tile_ctl->nheavy, nbusy = nheavy + wb.tile_ctl->nlight;
+    constexpr uint32_t SPB = SHT / TILE_W;  // strips per CTA pass
+    const int pix = threadIdx.x % TILE_W;
+    for (uint32_t q = blockIdx.x * SPB + threadIdx.x / TILE_W; q < nbusy; q += gridDim.x * SPB) {
+        const uint32_t strip = strip_at(wb, nheavy, q);
+        const uint32_t sidx = wb.vis_seg[(size_t)strip * TILE_W + pix];
+        if (sidx == NO_WINNER) continue;
+        const int x = (int)(strip % (uint32_t)p.tiles_x) * TILE_W + pix;
+        const int y = (int)(strip / (uint32_t)p.tiles_x);
         uint32_t *out = gcolor + (size_t)y * p.width + x;
         if (p.kind == FGL_SHADER_SOLID) {  // SolidColorShader.Fragment, shader.go:25-27: nothing to interpolate
             *out = c_nrgba(c4(p.color[0], p.color[1], p.color[2], p.color[3]));
             continue;
         }
-        // The deferred mode only admits Phong with an ObjectColor and no texture (fgl_api.cu), so the
-        // attribute set is fixed: 9 normal + 9 position components.  All loads are issued up front.
-        const Rec *rp = wb.recs + rid;
-        const double ra = rp->ra, r0 = rp->r0, r1 = rp->r1, r2 = rp->r2;
-        const uint32_t src = rp->src, flags = rp->flags;
-        const double w0 = wb.vis_w[vi], w1 = wb.vis_w[vplane + vi], w2 = wb.vis_w[2 * vplane + vi];
-        double n[3][3], pos[3][3];
+        const SegV *sp = wb.segv + sidx;
+        const uint32_t src = sp->src, flags = sp->flags;
+        double n[3][3], pos[3][3];  // all attribute loads are issued up front
         if (flags & REC_SRC_POOL) {
             const ClipTri *ct = wb.clip_pool + src;
 #pragma unroll
@@ -321,8 +378,15 @@ k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                 }
             }
         }
+        // the winner's edge values: the segment's chain of adds from its first pixel (context.go:211-213)
+        double w0 = sp->w0, w1 = sp->w1, w2 = sp->w2;
+        {
+            const double a12 = sp->a12, a20 = sp->a20, a01 = sp->a01;
+            for (int k = x - (int)sp->x; k > 0; k--) { w0 += a12; w1 += a20; w2 += a01; }
+        }
+        const double ra = sp->ra;
         const double b0 = w0 * ra, b1 = w1 * ra, b2 = w2 * ra;
-        const double bx = b0 * r0, by = b1 * r1, bzz = b2 * r2;  // context.go:236
+        const double bx = b0 * sp->r0, by = b1 * sp->r1, bzz = b2 * sp->r2;  // context.go:236
         const double bw = 1 / (bx + by + bzz);
         // PhongShader.Fragment, shader.go:75-96
         const V3 normal = v_normalize(v3(interp1(n[0][0], n[1][0], n[2][0], bx, by, bzz, bw),
@@ -351,32 +415,17 @@ k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     }
 }
 
-static size_t tile_smem(bool deferred) {
-    return deferred ? sizeof(double) * TILE_PIX * 4 + sizeof(uint32_t) * TILE_PIX * 2
-                    : sizeof(double) * TILE_PIX + sizeof(uint32_t) * TILE_PIX * 2;
-}
-
 int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,
                   cudaStream_t st) {
-    auto tile_kernel = p.deferred ? (p.prim_info ? k_tile<true, true> : k_tile<true, false>)
-                                  : (p.prim_info ? k_tile<false, true> : k_tile<false, false>);
-    cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(p.deferred));
-    int launches = 0;
-    cudaMemsetAsync(wb.tile_ctl, 0, sizeof(TileCtl), st);
-    cudaMemsetAsync(wb.tile_claimed, 0, sizeof(uint32_t) * wb.ntiles, st);
-    k_tile_bucket<<<148, 256, 0, st>>>(wb.tile_start, wb.tile_end, wb.ntiles, wb.tile_ctl);
-    k_tile_enqueue<<<148, 256, 0, st>>>(wb.tile_start, wb.tile_end, wb.ntiles, wb.tile_ctl, wb.busy_list);
-    launches += 2;
-    const uint32_t grid = wb.ntiles < 148u * 4u ? wb.ntiles : 148u * 4u;
-    if (p.deferred) {
-        tile_kernel<<<grid, RT, tile_smem(true), st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
-        launches++;
-        if (p.state.write_color) {
-            k_shade<<<148 * 4, RT, 0, st>>>(p, wb, color);
-            launches++;
-        }
-    } else {
-        tile_kernel<<<grid, RT, tile_smem(false), st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
+    auto strip_kernel = p.deferred ? (p.prim_info ? k_strip<true, true> : k_strip<true, false>)
+                                   : (p.prim_info ? k_strip<false, true> : k_strip<false, false>);
+    const uint32_t per_sm = p.deferred ? 4u : 3u;
+    const uint32_t want = (wb.ntiles + SWARPS - 1u) / SWARPS;  // never more warps than strips
+    const uint32_t grid = want < wb.nsm * per_sm ? (want ? want : 1u) : wb.nsm * per_sm;
+    strip_kernel<<<grid, STHREADS, 0, st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
+    int launches = 1;
+    if (p.deferred && p.state.write_color) {
+        k_shade<<<wb.nsm * 8u, SHT, 0, st>>>(p, wb, color);
         launches++;
     }
     return launches;

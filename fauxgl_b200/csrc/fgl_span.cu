@@ -41,14 +41,20 @@ __device__ __forceinline__ RowSetup load_setup(const Rec *rp) {
     return r;
 }
 
-// A segment with the record fields the ordered depth phase needs (SegV).
+// A segment with the record fields the back end needs (SegV).
+struct RecTail { double r0, r1, r2; uint32_t src, flags; };
+__device__ __forceinline__ RecTail load_tail(const Rec *rp) {
+    RecTail t;
+    t.r0 = rp->r0; t.r1 = rp->r1; t.r2 = rp->r2; t.src = rp->src; t.flags = rp->flags;
+    return t;
+}
 __device__ __forceinline__ SegV make_segv(double w0, double w1, double w2, double ra, double z0, double z1, double z2,
-                                          double a12, double a20, double a01, uint32_t rec, uint16_t x, uint8_t yt,
-                                          uint8_t cnt) {
+                                          double a12, double a20, double a01, const RecTail &t, uint16_t x, uint8_t cnt) {
     SegV v;
     v.w0 = w0; v.w1 = w1; v.w2 = w2; v.ra = ra; v.z0 = z0; v.z1 = z1; v.z2 = z2;
     v.a12 = a12; v.a20 = a20; v.a01 = a01;
-    v.rec = rec; v.x = x; v.yt = yt; v.cnt = cnt; v._pad[0] = v._pad[1] = 0;
+    v.r0 = t.r0; v.r1 = t.r1; v.r2 = t.r2; v.src = t.src; v.flags = t.flags;
+    v.x = x; v.yt = 0; v.cnt = cnt; v._pad[0] = v._pad[1] = v._pad[2] = 0;
     return v;
 }
 
@@ -58,7 +64,7 @@ template <bool FIRST>
 __device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const RowSetup &r, uint32_t rec_id, int y,
                                              Seg *__restrict__ first, SegV *__restrict__ segv,
                                              uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t base,
-                                             uint32_t cap, unsigned long long *covered) {
+                                             uint32_t cap, unsigned long long *covered, const RecTail *tail = nullptr) {
     const double a01 = r.s1y - r.s0y, b01 = r.s0x - r.s1x;  // context.go:167-172
     const double a12 = r.s2y - r.s1y, b12 = r.s1x - r.s2x;
     const double a20 = r.s0y - r.s2y, b20 = r.s2x - r.s0x;
@@ -81,8 +87,8 @@ __device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const RowSetup
     int col = -1, sx = 0;
     double sw0 = 0, sw1 = 0, sw2 = 0;
     bool was_inside = false;
-    const uint32_t key_row = (uint32_t)(y / p.tile_h) * (uint32_t)p.tiles_x;
-    const uint8_t yt = (uint8_t)(y % p.tile_h);
+    const uint32_t key_row = (uint32_t)y * (uint32_t)p.tiles_x;  // strip id = y * tiles_x + column
+    const uint8_t yt = 0;
     auto flush = [&]() {
         const uint32_t slot = FIRST ? base : base + nseg;
         if ((FIRST ? nseg == 0 : true) && slot < cap) {
@@ -91,8 +97,7 @@ __device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const RowSetup
                 s.w0 = sw0; s.w1 = sw1; s.w2 = sw2; s.rec = rec_id; s.x = (uint16_t)sx; s.yt = yt; s.cnt = (uint8_t)cnt;
                 first[slot] = s;
             } else {
-                segv[slot] = make_segv(sw0, sw1, sw2, r.ra, r.z0, r.z1, r.z2, a12, a20, a01, rec_id, (uint16_t)sx, yt,
-                                       (uint8_t)cnt);
+                segv[slot] = make_segv(sw0, sw1, sw2, r.ra, r.z0, r.z1, r.z2, a12, a20, a01, *tail, (uint16_t)sx, (uint8_t)cnt);
                 vals[slot] = slot;
             }
             keys[slot] = key_row + (uint32_t)col;
@@ -202,25 +207,55 @@ k_span_place(const __grid_constant__ DrawParams p, const __grid_constant__ WorkB
             if (base < wb.cap_segs) {  // records are visited in order here: the Rec reads are near-sequential
                 const Rec *rp = wb.recs + s.rec;
                 wb.segv[base] = make_segv(s.w0, s.w1, s.w2, rp->ra, rp->s[2], rp->s[5], rp->s[8], rp->s[7] - rp->s[4],
-                                          rp->s[1] - rp->s[7], rp->s[4] - rp->s[1], s.rec, s.x, s.yt, s.cnt);
+                                          rp->s[1] - rp->s[7], rp->s[4] - rp->s[1], load_tail(rp), s.x, s.cnt);
                 wb.seg_key[0][base] = key;
                 wb.seg_val[0][base] = base;
             }
         } else {  // the scanline crosses tile columns: walk it again, writing every segment
             const RowSetup r = load_setup(wb.recs + s.rec);
-            const int y = (int)(key / (uint32_t)p.tiles_x) * p.tile_h + (int)s.yt;
-            walk_row<false>(p, r, s.rec, y, nullptr, wb.segv, wb.seg_key[0], wb.seg_val[0], base, wb.cap_segs, &dummy);
+            const RecTail tail = load_tail(wb.recs + s.rec);
+            const int y = (int)(key / (uint32_t)p.tiles_x);
+            walk_row<false>(p, r, s.rec, y, nullptr, wb.segv, wb.seg_key[0], wb.seg_val[0], base, wb.cap_segs, &dummy, &tail);
         }
     }
 }
 
+// Bin ranges of the sorted key array, and the list of busy strips: heavy strips (>= HEAVY_SEGS segments)
+// are appended from the front, the others from the back, so that the strip kernel starts the long ones
+// first.  Only entries of strips that occur are written -- and only those are read (through the busy
+// list), so the arrays are never cleared.
 __global__ void k_tile_ranges(const uint32_t *__restrict__ keys, const unsigned int *__restrict__ n_dev, uint32_t n_max,
-                              uint32_t *__restrict__ tile_start, uint32_t *__restrict__ tile_end) {
+                              uint32_t *__restrict__ tile_start, uint32_t *__restrict__ tile_end,
+                              uint32_t *__restrict__ busy_list, uint32_t ntiles, TileCtl *ctl) {
     const uint32_t n = min(*n_dev, n_max);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t k = keys[i];
-        if (i == 0 || keys[i - 1] != k) tile_start[k] = i;
-        if (i == n - 1 || keys[i + 1] != k) tile_end[k] = i + 1;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
+        const uint32_t i = i0 + lane;
+        bool starts = false, heavy = false;
+        uint32_t k = 0;
+        if (i < n) {
+            k = keys[i];
+            starts = i == 0 || keys[i - 1] != k;
+            if (starts) {
+                tile_start[k] = i;
+                heavy = i + HEAVY_SEGS - 1u < n && keys[i + HEAVY_SEGS - 1u] == k;
+            }
+            if (i == n - 1 || keys[i + 1] != k) tile_end[k] = i + 1;
+        }
+        // warp-aggregated append of the strips that start in this warp's window
+        const uint32_t mh = __ballot_sync(0xffffffffu, starts && heavy), ml = __ballot_sync(0xffffffffu, starts && !heavy);
+        if (mh) {
+            uint32_t base = 0;
+            if (lane == (uint32_t)(__ffs(mh) - 1)) base = atomicAdd(&ctl->nheavy, (uint32_t)__popc(mh));
+            base = __shfl_sync(0xffffffffu, base, __ffs(mh) - 1);
+            if (starts && heavy) busy_list[base + __popc(mh & ((1u << lane) - 1u))] = k;
+        }
+        if (ml) {
+            uint32_t base = 0;
+            if (lane == (uint32_t)(__ffs(ml) - 1)) base = atomicAdd(&ctl->nlight, (uint32_t)__popc(ml));
+            base = __shfl_sync(0xffffffffu, base, __ffs(ml) - 1);
+            if (starts && !heavy) busy_list[ntiles - 1u - (base + __popc(ml & ((1u << lane) - 1u)))] = k;
+        }
     }
 }
 
@@ -248,9 +283,9 @@ int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cuda
     int bits = 1;
     while ((1u << bits) < wb.ntiles) bits++;
     launches += launch_sort_pairs(wb.seg_key, wb.seg_val, &c->n_segs, wb.cap_segs, bits, wb.scan_tmp, sorted_buf, st);
-    cudaMemsetAsync(wb.tile_start, 0, sizeof(uint32_t) * wb.ntiles, st);
-    cudaMemsetAsync(wb.tile_end, 0, sizeof(uint32_t) * wb.ntiles, st);
-    k_tile_ranges<<<148 * 4, 256, 0, st>>>(wb.seg_key[*sorted_buf], &c->n_segs, wb.cap_segs, wb.tile_start, wb.tile_end);
+    cudaMemsetAsync(wb.tile_ctl, 0, sizeof(TileCtl), st);
+    k_tile_ranges<<<148 * 4, 256, 0, st>>>(wb.seg_key[*sorted_buf], &c->n_segs, wb.cap_segs, wb.tile_start, wb.tile_end,
+                                           wb.busy_list, wb.ntiles, wb.tile_ctl);
     launches++;
     return launches;
 }
