@@ -65,6 +65,7 @@ struct ProfSlot { cudaEvent_t e[PROF_EVENTS]; };
 struct fgl_ctx {
     int device;
     int w, h;
+    int front_mode;                    // 0 auto, 1 fused front end always, 2 split stages always (FGL_FRONT)
     cudaStream_t stream;
     cudaStream_t copy_stream;          // H2D of streaming mesh uploads, overlapping the draw stream
     std::mutex mu;
@@ -137,9 +138,9 @@ int ensure_work(fgl_ctx *c, const Caps &want) {
         return fail(c, FGL_E_INVALID, "draw too large for 32-bit work indices");
     if (want.prims > wb.cap_prims) {
         dev_free(wb.blk_agg); dev_free(wb.blk_base); dev_free(wb.blk_region);
-        CK(c, dev_alloc(&wb.blk_agg, want.prims / 256 + 2));
-        CK(c, dev_alloc(&wb.blk_base, want.prims / 256 + 2));
-        CK(c, dev_alloc(&wb.blk_region, want.prims / 256 + 2));
+        CK(c, dev_alloc(&wb.blk_agg, want.prims / 128 + 2));
+        CK(c, dev_alloc(&wb.blk_base, want.prims / 128 + 2));
+        CK(c, dev_alloc(&wb.blk_region, want.prims / 128 + 2));
         wb.cap_prims = (uint32_t)want.prims;
     }
     if (want.records > wb.cap_records) {
@@ -301,6 +302,17 @@ void prof_drain(fgl_ctx *c) {
     c->prof_used = 0;
 }
 
+// Front end of a draw.  Large draws take the fused kernel (k_front): every block of 128 primitives walks its
+// own scanlines, which balances well when there are thousands of blocks.  Small draws keep the split
+// stages, whose span kernels spread the scanlines of a few large triangles over the whole GPU.
+// FGL_FRONT=fused|split (read when the context is created) forces one of them, for tests and tuning.
+constexpr uint64_t FUSED_MIN_PRIMS = 16384;
+bool use_fused_front(const fgl_ctx *c, const DrawParams &p) {
+    if (c->front_mode == 1) return true;
+    if (c->front_mode == 2) return false;
+    return p.count >= FUSED_MIN_PRIMS;
+}
+
 int enqueue_draw(fgl_ctx *c, const DrawParams &p) {
     int launches = 0;
     ProfSlot *ps = nullptr;
@@ -310,11 +322,18 @@ int enqueue_draw(fgl_ctx *c, const DrawParams &p) {
         cudaEventRecord(ps->e[0], c->stream);
     }
     if (p.prim_info) cudaMemsetAsync(p.prim_info, 0, sizeof(unsigned long long) * 2 * p.count, c->stream);
-    launches += launch_geometry(p, c->wb, c->stream);
-    if (ps) cudaEventRecord(ps->e[1], c->stream);
     int sorted = 0;
-    launches += launch_spans(p, c->wb, &sorted, c->stream);
-    if (ps) cudaEventRecord(ps->e[2], c->stream);
+    if (use_fused_front(c, p)) {
+        // large draws: geometry and spans in one kernel (the split stage timers then read: geometry = k_front +
+        // k_seg_index, spans = 0)
+        launches += launch_front(p, c->wb, c->stream);
+        if (ps) { cudaEventRecord(ps->e[1], c->stream); cudaEventRecord(ps->e[2], c->stream); }
+    } else {
+        launches += launch_geometry(p, c->wb, c->stream);
+        if (ps) cudaEventRecord(ps->e[1], c->stream);
+        launches += launch_spans(p, c->wb, &sorted, c->stream);
+        if (ps) cudaEventRecord(ps->e[2], c->stream);
+    }
     launches += launch_bin(p, c->wb, &sorted, c->stream);
     if (ps) cudaEventRecord(ps->e[3], c->stream);
     launches += launch_raster(p, c->wb, sorted, c->color, c->depth, c->stream);
@@ -454,6 +473,10 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     fgl_ctx *c = new (std::nothrow) fgl_ctx();
     if (!c) return fail(nullptr, FGL_E_OOM, "host allocation failed");
     c->device = device; c->w = width; c->h = height;
+    {
+        const char *fm = getenv("FGL_FRONT");
+        c->front_mode = !fm ? 0 : (strcmp(fm, "fused") == 0 ? 1 : (strcmp(fm, "split") == 0 ? 2 : 0));
+    }
     c->color = nullptr; c->depth = nullptr; c->resolved = nullptr; c->rw = c->rh = 0;
     memset(&c->wb, 0, sizeof c->wb);
     memset(&c->stats, 0, sizeof c->stats);

@@ -10,7 +10,9 @@
 // scan, and an emit pass that re-runs the same arithmetic (deterministic, so
 // both passes agree) and writes each record at its ordered slot.
 #include "fgl_internal.h"
+#include "fgl_block.cuh"
 #include "fgl_math.cuh"
+#include "fgl_walk.cuh"
 
 namespace fgl {
 
@@ -95,7 +97,7 @@ FGL_DI int32_t sat_i32(long long v) {
 }
 
 // Integer bounding box of a screen triangle, context.go:155-160, and its on-screen scanlines.
-struct BBox { int32_t x0, x1, y0, y1; bool visible; uint32_t rows; };
+struct BBox { int32_t x0, x1, y0, y1; bool visible; uint32_t rows, cols; };  // cols: strips a row can touch
 FGL_DI BBox compute_bbox(const DrawParams &p, V3 s0, V3 s1, V3 s2) {
     BBox b;
     const double mnx = go_min(s0.x, go_min(s1.x, s2.x)), mny = go_min(s0.y, go_min(s1.y, s2.y));
@@ -115,6 +117,7 @@ FGL_DI BBox compute_bbox(const DrawParams &p, V3 s0, V3 s1, V3 s2) {
     constexpr int32_t FAR = 1 << 22;
     if (b.x0 < -FAR || b.y0 < -FAR || b.x1 > FAR || b.y1 > FAR) b.visible = false;
     b.rows = b.visible ? (uint32_t)(cy1 - cy0 + 1) : 0u;
+    b.cols = b.visible ? (uint32_t)(cx1 / TILE_W - cx0 / TILE_W + 1) : 0u;
     return b;
 }
 
@@ -151,12 +154,14 @@ FGL_DI void write_record(const WorkBuffers *wb, uint32_t r, uint32_t row_off, co
 // once the ordered offset is known.
 struct CountEmit {
     uint32_t n, rows;
+    unsigned long long cells;  // sum of rows x strip columns: an upper bound of the segments
     static constexpr bool kWrite = false;
     FGL_DI void record(const DrawParams &p, V3 a0, V3 a1, V3 a2, double, double, double, uint32_t, uint32_t) {
         const BBox bb = compute_bbox(p, a0, a1, a2);
         if (!bb.visible) return;
         n++;
         rows += bb.rows;
+        cells += (unsigned long long)bb.rows * bb.cols;
     }
     FGL_DI uint32_t pool_alloc(const FullVertex *, uint32_t) { return 0; }
 };
@@ -164,6 +169,8 @@ struct WriteEmit {
     uint32_t next, row_next;
     const WorkBuffers *wb;
     static constexpr bool kWrite = true;
+    FGL_DI bool wants(uint32_t) const { return true; }
+    FGL_DI void skip(uint32_t) {}
     FGL_DI void record(const DrawParams &p, V3 s0, V3 s1, V3 s2, double w0, double w1, double w2, uint32_t src,
                        uint32_t flags) {
         const BBox b = compute_bbox(p, s0, s1, s2);
@@ -350,9 +357,12 @@ __device__ __noinline__ void clip_and_emit(const DrawParams &p, Emit &e, uint32_
         const V4 oo[3] = {nv[0].out, nv[1].out, nv[2].out};
         if (Emit::kWrite) {
             // only allocate a pool slot if the fan triangle survives culling: probe with a counter
-            CountEmit probe{0};
+            CountEmit probe{0, 0, 0};
             emit_clipped_triangle(p, probe, oo, 0, 0);
             if (probe.n == 0) continue;
+            if constexpr (Emit::kWrite) {
+                if (!e.wants(probe.n)) { e.skip(probe.n); continue; }  // none of its records is wanted in this pass
+            }
             const uint32_t slot = e.pool_alloc(nv, prim);
             emit_clipped_triangle(p, e, oo, slot, REC_SRC_POOL);
         } else {
@@ -418,12 +428,14 @@ constexpr unsigned long long REC_MASK = (1ull << 30) - 1ull;
 
 // General path (lines, wireframe, clipped triangles), out of line so that its registers and stack
 // do not weigh on the common case.  Counting and writing run the same deterministic arithmetic.
-__device__ __noinline__ void count_general(const DrawParams &p, uint32_t prim, uint32_t *n, uint32_t *rows) {
-    CountEmit e{0, 0};
+__device__ __noinline__ void count_general(const DrawParams &p, uint32_t prim, uint32_t *n, uint32_t *rows,
+                                           unsigned long long *cells = nullptr) {
+    CountEmit e{0, 0, 0};
     if (p.is_lines) process_line(p, e, prim);
     else process_triangle(p, e, prim);
     *n = e.n;
     *rows = e.rows;
+    if (cells) *cells = e.cells;
 }
 __device__ __noinline__ void write_general(const DrawParams &p, const WorkBuffers &wb, uint32_t prim, uint32_t rec0,
                                            uint32_t row0) {
@@ -596,6 +608,328 @@ k_rec_index(const __grid_constant__ WorkBuffers wb, uint32_t nblocks) {
             wb.rec_row_off[c] = row_base + wb.rec_local_row[slot];
         }
     }
+}
+
+
+// ================================================================================================
+// Fused front end of large draws: geometry + span stage in ONE kernel.
+//
+// A block takes FT consecutive primitives.  Its raster records never leave the SM: they are set up in
+// shared memory, and the same threads then walk their scanlines -- FT (record, scanline) items at a time,
+// the item -> record map being a binary search in a shared-memory offset table -- count the segments of
+// each row (the first one stays in registers), compact them in order with a block scan and store them as
+// SegV.  Compared with k_geometry -> k_rec_index -> k_span_walk -> scan x3 -> k_span_place this removes
+// the 176-byte record round trip through HBM, the per-row record search in global memory, the global row
+// arrays and six launches (profiles/README.md).
+//
+// Order without waiting for other blocks: a block reserves, with one atomic, a region of the
+// segment array large enough for an upper bound of its segments (sum over records of rows x strip columns,
+// known after the geometry phase) and fills it from the front in (primitive, scanline, column) order; regions
+// are in block-arrival order.  Every block publishes its exact segment count, the last block to finish scans
+// the counts, and k_seg_index lists the segments in primitive order for the stable sort by strip.
+constexpr int FT = 128;
+constexpr unsigned long long CELL_SHIFT = 24, NREC_MASK = (1ull << CELL_SHIFT) - 1ull;
+static_assert(FT * 64 < (1 << CELL_SHIFT), "records of one block fit the low bits of its aggregate");
+
+struct __align__(16) SRec {  // a raster record in shared memory: RowSetup + the back end's tail
+    double s0x, s0y, s1x, s1y, s2x, s2y;
+    double w00, w01, w02, ra, ra12, ra20, ra01;
+    double z0, z1, z2;
+    double r0, r1, r2;
+    int32_t x0, x1, y0;
+    uint32_t rows;
+    uint32_t src, flags;
+};
+static_assert(sizeof(SRec) == 176, "SRec layout");
+
+// Per-triangle setup of Context.rasterize, context.go:155-181 (the same arithmetic as write_record).
+FGL_DI void fill_srec(SRec &r, const BBox &b, V3 s0, V3 s1, V3 s2, double w0, double w1, double w2, uint32_t src,
+                      uint32_t flags) {
+    r.s0x = s0.x; r.s0y = s0.y; r.s1x = s1.x; r.s1y = s1.y; r.s2x = s2.x; r.s2y = s2.y;
+    r.z0 = s0.z; r.z1 = s1.z; r.z2 = s2.z;
+    const V3 pc = v3((double)b.x0 + 0.5, (double)b.y0 + 0.5, 0);
+    r.w00 = edge_fn(s1, s2, pc);
+    r.w01 = edge_fn(s2, s0, pc);
+    r.w02 = edge_fn(s0, s1, pc);
+    const double a01 = s1.y - s0.y, a12 = s2.y - s1.y, a20 = s0.y - s2.y;
+    r.ra = 1 / edge_fn(s0, s1, s2);
+    r.r0 = 1 / w0; r.r1 = 1 / w1; r.r2 = 1 / w2;
+    r.ra12 = 1 / a12; r.ra20 = 1 / a20; r.ra01 = 1 / a01;
+    r.x0 = b.x0; r.x1 = b.x1; r.y0 = b.y0; r.rows = b.rows;
+    r.src = src; r.flags = flags;
+}
+
+// Emits the records of one primitive whose block-local index falls into the window [win0, win1).
+struct SmemEmit {
+    uint32_t next, win0, win1;
+    SRec *s_rec;
+    const WorkBuffers *wb;
+    static constexpr bool kWrite = true;
+    FGL_DI bool wants(uint32_t n) const { return next < win1 && next + n > win0; }
+    FGL_DI void skip(uint32_t n) { next += n; }
+    FGL_DI void record(const DrawParams &p, V3 s0, V3 s1, V3 s2, double w0, double w1, double w2, uint32_t src,
+                       uint32_t flags) {
+        const BBox b = compute_bbox(p, s0, s1, s2);
+        if (!b.visible) return;
+        if (next >= win0 && next < win1) fill_srec(s_rec[next - win0], b, s0, s1, s2, w0, w1, w2, src, flags);
+        next++;
+    }
+    FGL_DI uint32_t pool_alloc(const FullVertex *v, uint32_t prim) {
+        WriteEmit w{0, 0, wb};
+        return w.pool_alloc(v, prim);
+    }
+};
+__device__ __noinline__ void emit_general_smem(const DrawParams &p, const WorkBuffers &wb, uint32_t prim, uint32_t rec0,
+                                               uint32_t win0, uint32_t win1, SRec *s_rec) {
+    SmemEmit e{rec0, win0, win1, s_rec, &wb};
+    if (p.is_lines) process_line(p, e, prim);
+    else process_triangle(p, e, prim);
+}
+
+__global__ void __launch_bounds__(FT, 4)
+k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
+    __shared__ SRec s_rec[FT];
+    __shared__ uint32_t s_rowoff[FT + 1];
+    __shared__ uint16_t s_order[FT];
+    __shared__ unsigned long long s_scan[FT / 32 + 1];
+    __shared__ uint32_t s_scan32[FT / 32 + 1];
+    __shared__ unsigned long long s_region;
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t vb = blockIdx.x;
+    const uint32_t nblocks = (p.count + FT - 1) / FT;
+    const uint32_t i = vb * FT + tid;
+    const uint32_t prim = p.first + i;
+
+    // ---- geometry: one thread per primitive -----------------------------------------------------
+    // Fast path: a triangle entirely inside the view volume, not in wireframe mode, yields at most one
+    // record, set up straight into this thread's shared-memory slot.  Lines, wireframe and triangles
+    // that need clipping are only counted here (out-of-line general path).
+    uint32_t n = 0;
+    unsigned long long cells = 0;
+    bool slow = false;
+    if (i < p.count) {
+        if (p.is_lines || p.state.wireframe) {
+            slow = true;
+        } else {
+            const MeshPlanes &m = p.mesh;
+            V4 o[3];
+            bool outside = false;
+#pragma unroll
+            for (uint32_t v = 0; v < 3; v++) {
+                const V3 pos = v3(plane_at(m.pos, m.n, v, 3, 0, prim), plane_at(m.pos, m.n, v, 3, 1, prim),
+                                  plane_at(m.pos, m.n, v, 3, 2, prim));
+                o[v] = m_mul_position_w(p.matrix, pos);  // Shader.Vertex, shader.go:20,39,70
+                outside = outside || w_outside(o[v]);
+            }
+            if (outside) {
+                slow = true;
+            } else {  // drawClippedTriangle, context.go:316-341
+                V3 ndc0 = v3(o[0].x / o[0].w, o[0].y / o[0].w, o[0].z / o[0].w);
+                V3 ndc1 = v3(o[1].x / o[1].w, o[1].y / o[1].w, o[1].z / o[1].w);
+                V3 ndc2 = v3(o[2].x / o[2].w, o[2].y / o[2].w, o[2].z / o[2].w);
+                double a = (ndc1.x - ndc0.x) * (ndc2.y - ndc0.y) - (ndc2.x - ndc0.x) * (ndc1.y - ndc0.y);
+                uint32_t i0 = 0, i2 = 2;
+                if (a < 0) {
+                    V3 t = ndc0; ndc0 = ndc2; ndc2 = t;
+                    i0 = 2; i2 = 0;
+                }
+                if (p.state.cull == FGL_CULL_FRONT) a = -a;
+                if (p.state.front_face == FGL_FACE_CW) a = -a;
+                if (!(p.state.cull != FGL_CULL_NONE && a <= 0)) {
+                    const V3 s0 = m_mul_position(p.screen, ndc0), s1 = m_mul_position(p.screen, ndc1),
+                             s2 = m_mul_position(p.screen, ndc2);
+                    const BBox bb = compute_bbox(p, s0, s1, s2);
+                    if (bb.visible) {
+                        n = 1;
+                        cells = (unsigned long long)bb.rows * bb.cols;
+                        fill_srec(s_rec[tid], bb, s0, s1, s2, i0 == 0 ? o[0].w : o[2].w, o[1].w, i2 == 2 ? o[2].w : o[0].w,
+                                  prim, vmap3(i0, 1, i2));
+                    }
+                }
+            }
+        }
+        if (slow) {
+            uint32_t rows_unused;
+            count_general(p, prim, &n, &rows_unused, &cells);
+        }
+    }
+    const bool general = __syncthreads_or(slow && n > 0) != 0;  // also orders the s_rec writes
+
+    // block-wide exclusive scan of (cells << CELL_SHIFT | records)
+    const unsigned long long mine = (cells << CELL_SHIFT) | n;
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long v = lane < FT / 32 ? s_scan[lane] : 0, vi = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, vi, o);
+            if (lane >= o) vi += t;
+        }
+        if (lane < FT / 32) s_scan[lane] = vi - v;
+        if (lane == FT / 32 - 1) s_scan[FT / 32] = vi;
+    }
+    __syncthreads();
+    const uint32_t rec_off = (uint32_t)((s_scan[warp] + incl - mine) & NREC_MASK);
+    const unsigned long long block_total = s_scan[FT / 32];
+    const uint32_t nrec_blk = (uint32_t)(block_total & NREC_MASK);
+    if (tid == 0) s_region = nrec_blk ? atomicAdd(&wb.counters->seg_cursor, block_total >> CELL_SHIFT) : 0ull;
+    if (!general && n == 1) s_order[rec_off] = (uint16_t)tid;
+    __syncthreads();
+    const unsigned long long region = s_region;
+
+    // ---- spans: FT records per window, FT (record, scanline) items per pass --------------------------------
+    uint32_t seg_run = 0;  // segments this block has stored so far (block-uniform)
+    unsigned long long covered = 0;
+    ParkedSeg first;
+    first.w0 = first.w1 = first.w2 = 0; first.x = 0; first.cnt = 0; first.key = 0;
+    for (uint32_t win0 = 0; win0 < nrec_blk; win0 += FT) {
+        const uint32_t nw = min((uint32_t)FT, nrec_blk - win0);
+        if (general) {  // re-run the deterministic geometry, keeping the records of this window
+            __syncthreads();
+            if (n > 0 && rec_off < win0 + nw && rec_off + n > win0) emit_general_smem(p, wb, prim, rec_off, win0, win0 + nw, s_rec);
+            if (tid < (int)nw) s_order[tid] = (uint16_t)tid;
+            __syncthreads();
+        }
+        uint32_t items;
+        {
+            const uint32_t rows = tid < (int)nw ? s_rec[s_order[tid]].rows : 0u;
+            const uint32_t ex = block_excl_scan<FT>(rows, s_scan32, &items);
+            s_rowoff[tid] = ex;
+            if (tid == 0) s_rowoff[FT] = items;
+            __syncthreads();
+        }
+        for (uint32_t c0 = 0; c0 < items; c0 += FT) {
+            const uint32_t it = c0 + tid;
+            uint32_t nseg = 0, ridx = 0;
+            int y = 0;
+            if (it < items) {
+                uint32_t lo = 0, hi = nw;  // s_rowoff[lo] <= it < s_rowoff[hi] (entries >= nw hold `items`)
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (s_rowoff[mid] <= it) lo = mid; else hi = mid;
+                }
+                ridx = s_order[lo];
+                const SRec &r = s_rec[ridx];
+                y = max(r.y0, 0) + (int)(it - s_rowoff[lo]);
+                const unsigned long long before = covered;
+                nseg = walk_row_segments<false>(p, r, y, first, nullptr, nullptr, nullptr, 0, 0, &covered);
+                if (p.prim_info && covered != before)  // per-primitive TotalPixels (fgl_draw_*_each)
+                    atomicAdd(&p.prim_info[2 * (size_t)src_primitive(wb, p, r.src, r.flags)], covered - before);
+            }
+            uint32_t chunk_total;
+            const uint32_t ex = block_excl_scan<FT>(nseg, s_scan32, &chunk_total);
+            if (nseg) {
+                const unsigned long long slot64 = region + seg_run + ex;
+                const SRec &r = s_rec[ridx];
+                RecTail tail;
+                tail.r0 = r.r0; tail.r1 = r.r1; tail.r2 = r.r2; tail.src = r.src; tail.flags = r.flags;
+                if (slot64 + nseg <= (unsigned long long)wb.cap_segs) {
+                    const uint32_t slot = (uint32_t)slot64;
+                    if (nseg == 1) {
+                        wb.segv[slot] = make_segv(first.w0, first.w1, first.w2, r.ra, r.z0, r.z1, r.z2, r.s2y - r.s1y,
+                                                  r.s0y - r.s2y, r.s1y - r.s0y, tail, (uint16_t)first.x, (uint8_t)first.cnt);
+                        wb.seg_key[1][slot] = first.key;
+                    } else {  // the scanline crosses strip boundaries: walk it again, storing every segment
+                        unsigned long long dummy = 0;
+                        walk_row_segments<true>(p, r, y, first, &tail, wb.segv, wb.seg_key[1], slot, wb.cap_segs, &dummy);
+                    }
+                }
+            }
+            seg_run += chunk_total;
+        }
+    }
+
+    // TotalPixels, context.go:229: every covered in-range pixel, before any depth test
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) covered += __shfl_down_sync(0xffffffffu, covered, o);
+    if (lane == 0 && covered) atomicAdd(&wb.counters->total_pixels, covered);
+
+    // ---- publish; the last block scans the aggregates ---------------------------------------------------
+    if (tid == 0) {
+        wb.blk_agg[vb] = ((unsigned long long)seg_run << 32) | nrec_blk;
+        wb.blk_region[vb] = (uint32_t)min(region, 0xffffffffull);
+        __threadfence();
+        s_last = atomicAdd(&wb.counters->blocks_done, 1u) == nblocks - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const uint32_t per = (nblocks + FT - 1) / FT;
+    const uint32_t b0 = min((uint32_t)tid * per, nblocks), b1 = min(b0 + per, nblocks);
+    unsigned long long sum = 0;  // segments << 32 | records (records of a draw < 2^30)
+    for (uint32_t b = b0; b < b1; b++) sum += __ldcg(&wb.blk_agg[b]);
+    unsigned long long incl2 = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl2, o);
+        if (lane >= o) incl2 += t;
+    }
+    if (lane == 31) s_scan[warp] = incl2;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long v = lane < FT / 32 ? s_scan[lane] : 0, vi = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, vi, o);
+            if (lane >= o) vi += t;
+        }
+        if (lane < FT / 32) s_scan[lane] = vi - v;
+        if (lane == FT / 32 - 1) s_scan[FT / 32] = vi;
+    }
+    __syncthreads();
+    unsigned long long run = s_scan[warp] + incl2 - sum;
+    for (uint32_t b = b0; b < b1; b++) {
+        wb.blk_base[b] = run >> 32;  // ordered position of the block's first segment
+        run += __ldcg(&wb.blk_agg[b]);
+    }
+    if (tid == 0) {
+        const unsigned long long tot = s_scan[FT / 32];
+        DrawCounters *c = wb.counters;
+        const unsigned long long cells_total = c->seg_cursor;  // every block has made its reservation
+        const uint32_t nsegs = (uint32_t)(tot >> 32);
+        c->n_records = (uint32_t)tot; c->need_records = 0;
+        c->n_rows = 0; c->need_rows = 0;
+        c->n_segs = nsegs;
+        c->need_segs = (unsigned int)min(cells_total, 0xfffffff0ull);
+        const unsigned nc = c->n_clip;
+        c->need_clip = nc;
+        unsigned ovf = 0;
+        if (cells_total > (unsigned long long)wb.cap_segs) ovf |= OVF_SEGS;
+        if (nc > wb.cap_clip) ovf |= OVF_CLIP;
+        if (ovf) atomicOr(&c->overflow, ovf);
+    }
+}
+
+// Segments in primitive order for the stable sort: position blk_base[b] + k  <-  slot blk_region[b] + k.
+__global__ void __launch_bounds__(256)
+k_seg_index(const __grid_constant__ WorkBuffers wb, uint32_t nblocks) {
+    if (wb.counters->overflow) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nblocks; b += nwarps) {
+        const uint32_t cnt = (uint32_t)(wb.blk_agg[b] >> 32), base = (uint32_t)wb.blk_base[b], region = wb.blk_region[b];
+        for (uint32_t k = lane; k < cnt; k += 32) {
+            wb.seg_key[0][base + k] = wb.seg_key[1][region + k];
+            wb.seg_val[0][base + k] = region + k;
+        }
+    }
+}
+
+int launch_front(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {
+    const uint32_t blocks = (p.count + FT - 1) / FT;
+    cudaMemsetAsync(wb.counters, 0, sizeof(DrawCounters), st);
+    k_front<<<blocks, FT, 0, st>>>(p, wb);
+    const uint32_t g = (blocks + 7u) / 8u;
+    k_seg_index<<<g < 148u * 8u ? g : 148u * 8u, 256, 0, st>>>(wb, blocks);
+    return 2;
 }
 
 int launch_geometry(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {

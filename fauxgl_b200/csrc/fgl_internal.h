@@ -119,6 +119,7 @@ struct DrawCounters {
     unsigned int need_records, need_rows, need_segs, need_clip, _pad;
     unsigned int rec_cursor;   // geometry stage: next free record slot (regions are handed out per block)
     unsigned int blocks_done;  // geometry stage: blocks that have published their aggregate
+    unsigned long long seg_cursor;  // fused front end: next free segment slot (regions are handed out per block)
 };
 constexpr unsigned OVF_RECORDS = 1u, OVF_ROWS = 2u, OVF_CLIP = 4u, OVF_SEGS = 8u;
 
@@ -127,9 +128,11 @@ struct WorkBuffers {
     // The geometry kernel never waits for other blocks: a block takes a region of `recs` with one atomic
     // (slots are in block-arrival order), publishes (scanlines << 30 | records), and the last block to
     // finish scans the aggregates; k_rec_index then lists the slots in primitive order.
-    unsigned long long *blk_agg;    // [ceil(cap_prims/256)] scanlines << 30 | records of each geometry block
-    unsigned long long *blk_base;   // [ceil(cap_prims/256)] exclusive prefix of blk_agg
-    uint32_t *blk_region;           // [ceil(cap_prims/256)] first record slot of the block
+    // (k_front uses the same three arrays for its 128-primitive blocks: segments << 32 | records, the
+    // ordered position of the block's first segment, the first SEGMENT slot of the block.)
+    unsigned long long *blk_agg;    // [cap_prims/128+2] scanlines << 30 | records of each geometry block
+    unsigned long long *blk_base;   // [cap_prims/128+2] exclusive prefix of blk_agg
+    uint32_t *blk_region;           // [cap_prims/128+2] first record slot of the block
     Rec *recs;                // [cap_records]   indexed by slot
     uint32_t *rec_local_row;  // [cap_records]   by slot: scanline offset of the record inside its block
     uint32_t *rec_slot;       // [cap_records+1] by primitive order: slot of the record
@@ -196,6 +199,9 @@ int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsi
                       int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st);
 
 int launch_geometry(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
+// fused geometry + span stage of large draws (k_front, k_seg_index): leaves (seg_key[0], seg_val[0]) in
+// primitive order, like launch_geometry + launch_spans
+int launch_front(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
 int launch_spans(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
 int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
 int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,

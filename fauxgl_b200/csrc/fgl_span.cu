@@ -18,6 +18,7 @@
 #include "fgl_internal.h"
 #include "fgl_block.cuh"
 #include "fgl_math.cuh"
+#include "fgl_walk.cuh"
 
 namespace fgl {
 
@@ -41,87 +42,10 @@ __device__ __forceinline__ RowSetup load_setup(const Rec *rp) {
     return r;
 }
 
-// A segment with the record fields the back end needs (SegV).
-struct RecTail { double r0, r1, r2; uint32_t src, flags; };
 __device__ __forceinline__ RecTail load_tail(const Rec *rp) {
     RecTail t;
     t.r0 = rp->r0; t.r1 = rp->r1; t.r2 = rp->r2; t.src = rp->src; t.flags = rp->flags;
     return t;
-}
-__device__ __forceinline__ SegV make_segv(double w0, double w1, double w2, double ra, double z0, double z1, double z2,
-                                          double a12, double a20, double a01, const RecTail &t, uint16_t x, uint8_t cnt) {
-    SegV v;
-    v.w0 = w0; v.w1 = w1; v.w2 = w2; v.ra = ra; v.z0 = z0; v.z1 = z1; v.z2 = z2;
-    v.a12 = a12; v.a20 = a20; v.a01 = a01;
-    v.r0 = t.r0; v.r1 = t.r1; v.r2 = t.r2; v.src = t.src; v.flags = t.flags;
-    v.x = x; v.yt = 0; v.cnt = cnt; v._pad[0] = v._pad[1] = v._pad[2] = 0;
-    return v;
-}
-
-// Walk one scanline.  FIRST: park only the first segment (first[base], keys[base]) and count;
-// otherwise write every segment as a SegV to segv/keys/vals[base...].  Returns the number of segments.
-template <bool FIRST>
-__device__ __forceinline__ uint32_t walk_row(const DrawParams &p, const RowSetup &r, uint32_t rec_id, int y,
-                                             Seg *__restrict__ first, SegV *__restrict__ segv,
-                                             uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t base,
-                                             uint32_t cap, unsigned long long *covered, const RecTail *tail = nullptr) {
-    const double a01 = r.s1y - r.s0y, b01 = r.s0x - r.s1x;  // context.go:167-172
-    const double a12 = r.s2y - r.s1y, b12 = r.s1x - r.s2x;
-    const double a20 = r.s0y - r.s2y, b20 = r.s2x - r.s0x;
-    double w00 = r.w00, w01 = r.w01, w02 = r.w02;
-    for (int yy = r.y0; yy < y; yy++) { w00 += b12; w01 += b20; w02 += b01; }  // context.go:275-277
-    // skip-ahead, context.go:185-205
-    double d = 0;
-    const double d0 = -w00 * r.ra12, d1 = -w01 * r.ra20, d2 = -w02 * r.ra01;
-    if (w00 < 0 && d0 > d) d = d0;
-    if (w01 < 0 && d1 > d) d = d1;
-    if (w02 < 0 && d2 > d) d = d2;
-    d = (double)go_int(d);
-    if (d < 0) d = 0;
-    double w0 = w00 + a12 * d, w1 = w01 + a20 * d, w2 = w02 + a01 * d;
-    long long x = (long long)r.x0 + go_int(d);
-    const long long xend = min((long long)r.x1, (long long)p.width - 1);
-    if (x > xend) return 0;
-    for (; x < 0; x++) { w0 += a12; w1 += a20; w2 += a01; }  // left of the framebuffer: dropped (x-guard rule)
-    uint32_t nseg = 0, cnt = 0;
-    int col = -1, sx = 0;
-    double sw0 = 0, sw1 = 0, sw2 = 0;
-    bool was_inside = false;
-    const uint32_t key_row = (uint32_t)y * (uint32_t)p.tiles_x;  // strip id = y * tiles_x + column
-    const uint8_t yt = 0;
-    auto flush = [&]() {
-        const uint32_t slot = FIRST ? base : base + nseg;
-        if ((FIRST ? nseg == 0 : true) && slot < cap) {
-            if (FIRST) {
-                Seg s;
-                s.w0 = sw0; s.w1 = sw1; s.w2 = sw2; s.rec = rec_id; s.x = (uint16_t)sx; s.yt = yt; s.cnt = (uint8_t)cnt;
-                first[slot] = s;
-            } else {
-                segv[slot] = make_segv(sw0, sw1, sw2, r.ra, r.z0, r.z1, r.z2, a12, a20, a01, *tail, (uint16_t)sx, (uint8_t)cnt);
-                vals[slot] = slot;
-            }
-            keys[slot] = key_row + (uint32_t)col;
-        }
-        *covered += cnt;
-        nseg++;
-    };
-    for (; x <= xend; x++) {
-        const double b0 = w0 * r.ra, b1 = w1 * r.ra, b2 = w2 * r.ra;  // context.go:208-210
-        if (b0 < 0 || b1 < 0 || b2 < 0) {
-            if (was_inside) break;  // context.go:216-218
-        } else {
-            was_inside = true;
-            const int c = (int)x / TILE_W;
-            if (cnt == 0 || c != col) {
-                if (cnt > 0) flush();
-                col = c; sx = (int)x; sw0 = w0; sw1 = w1; sw2 = w2; cnt = 0;
-            }
-            cnt++;
-        }
-        w0 += a12; w1 += a20; w2 += a01;  // context.go:211-213
-    }
-    if (cnt > 0) flush();
-    return nseg;
 }
 
 // Largest r in [0,n) with off[r] <= i, found by one warp with a 32-ary search (5 rounds for 2^24).
@@ -179,7 +103,15 @@ k_span_walk(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBu
             const RowSetup r = load_setup(wb.recs + rid);
             const int y = max(r.y0, 0) + (int)(i - s_off[lo]);
             const unsigned long long before = covered;
-            wb.row_nseg[i] = walk_row<true>(p, r, rid, y, wb.row_first, nullptr, wb.row_key, nullptr, i, wb.cap_rows, &covered);
+            ParkedSeg f;
+            const uint32_t nseg = walk_row_segments<false>(p, r, y, f, nullptr, nullptr, nullptr, 0, 0, &covered);
+            wb.row_nseg[i] = nseg;
+            if (nseg) {  // park the first segment (almost every scanline of a small triangle has exactly one)
+                Seg sg;
+                sg.w0 = f.w0; sg.w1 = f.w1; sg.w2 = f.w2; sg.rec = rid; sg.x = (uint16_t)f.x; sg.yt = 0; sg.cnt = (uint8_t)f.cnt;
+                wb.row_first[i] = sg;
+                wb.row_key[i] = f.key;
+            }
             if (p.prim_info && covered != before)  // per-primitive TotalPixels (fgl_draw_*_each)
                 atomicAdd(&p.prim_info[2 * (size_t)rec_primitive(wb, p, rid)], covered - before);
         }
@@ -215,7 +147,9 @@ k_span_place(const __grid_constant__ DrawParams p, const __grid_constant__ WorkB
             const RowSetup r = load_setup(wb.recs + s.rec);
             const RecTail tail = load_tail(wb.recs + s.rec);
             const int y = (int)(key / (uint32_t)p.tiles_x);
-            walk_row<false>(p, r, s.rec, y, nullptr, wb.segv, wb.seg_key[0], wb.seg_val[0], base, wb.cap_segs, &dummy, &tail);
+            ParkedSeg f;
+            walk_row_segments<true>(p, r, y, f, &tail, wb.segv, wb.seg_key[0], base, wb.cap_segs, &dummy);
+            for (uint32_t k = 0; k < n && base + k < wb.cap_segs; k++) wb.seg_val[0][base + k] = base + k;
         }
     }
 }

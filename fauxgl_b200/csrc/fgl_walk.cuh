@@ -1,0 +1,102 @@
+// fgl_walk.cuh -- the scanline walker shared by the two front ends (fgl_span.cu:
+// grid-wide span stage of small draws; fgl_geom.cu: k_front, the fused geometry +
+// span kernel of large draws).
+//
+// One call replays the reference's inner loop for one row of one triangle
+// (context.go:184-221): the per-row adds from y0, the skip-ahead `d`, then the
+// per-pixel forward-differencing adds, exactly as written, once, left to right.
+// The covered run is cut at strip boundaries (64 pixels) into segments that carry
+// the edge values at their first pixel, so the back end continues the same chain of
+// adds and reproduces coverage, barycentrics and depth bit for bit.
+#pragma once
+#include "fgl_internal.h"
+#include "fgl_math.cuh"
+
+namespace fgl {
+
+// The per-record fields the back end needs besides the walk itself.
+struct RecTail { double r0, r1, r2; uint32_t src, flags; };
+
+__device__ __forceinline__ SegV make_segv(double w0, double w1, double w2, double ra, double z0, double z1, double z2,
+                                          double a12, double a20, double a01, const RecTail &t, uint16_t x, uint8_t cnt) {
+    SegV v;
+    v.w0 = w0; v.w1 = w1; v.w2 = w2; v.ra = ra; v.z0 = z0; v.z1 = z1; v.z2 = z2;
+    v.a12 = a12; v.a20 = a20; v.a01 = a01;
+    v.r0 = t.r0; v.r1 = t.r1; v.r2 = t.r2; v.src = t.src; v.flags = t.flags;
+    v.x = x; v.yt = 0; v.cnt = cnt; v._pad[0] = v._pad[1] = v._pad[2] = 0;
+    return v;
+}
+
+// First segment of a row, kept in registers between the counting walk and the write.
+struct ParkedSeg {
+    double w0, w1, w2;
+    int32_t x;      // first covered pixel
+    uint32_t cnt;   // covered pixels
+    uint32_t key;   // strip id
+};
+
+// Walk row y of the triangle described by r (any struct with the fields s0x..s2y, w00..w02, ra, ra12, ra20,
+// ra01, z0..z2, x0, x1, y0).  Returns the number of segments and adds the covered pixels to *covered.
+//   WRITE == false: the first segment is returned in `first`, nothing is stored.
+//   WRITE == true : every segment k is stored as segv[base + k] / keys[base + k] (if base + k < cap).
+template <bool WRITE, class R>
+__device__ __forceinline__ uint32_t walk_row_segments(const DrawParams &p, const R &r, int y, ParkedSeg &first,
+                                                      const RecTail *tail, SegV *__restrict__ segv,
+                                                      uint32_t *__restrict__ keys, uint32_t base, uint32_t cap,
+                                                      unsigned long long *covered) {
+    const double a01 = r.s1y - r.s0y, b01 = r.s0x - r.s1x;  // context.go:167-172
+    const double a12 = r.s2y - r.s1y, b12 = r.s1x - r.s2x;
+    const double a20 = r.s0y - r.s2y, b20 = r.s2x - r.s0x;
+    double w00 = r.w00, w01 = r.w01, w02 = r.w02;
+    for (int yy = r.y0; yy < y; yy++) { w00 += b12; w01 += b20; w02 += b01; }  // context.go:275-277
+    // skip-ahead, context.go:185-205
+    double d = 0;
+    const double d0 = -w00 * r.ra12, d1 = -w01 * r.ra20, d2 = -w02 * r.ra01;
+    if (w00 < 0 && d0 > d) d = d0;
+    if (w01 < 0 && d1 > d) d = d1;
+    if (w02 < 0 && d2 > d) d = d2;
+    d = (double)go_int(d);
+    if (d < 0) d = 0;
+    double w0 = w00 + a12 * d, w1 = w01 + a20 * d, w2 = w02 + a01 * d;
+    long long x = (long long)r.x0 + go_int(d);
+    const long long xend = min((long long)r.x1, (long long)p.width - 1);
+    if (x > xend) return 0;
+    for (; x < 0; x++) { w0 += a12; w1 += a20; w2 += a01; }  // left of the framebuffer: dropped (x-guard rule)
+    uint32_t nseg = 0, cnt = 0;
+    int col = -1, sx = 0;
+    double sw0 = 0, sw1 = 0, sw2 = 0;
+    bool was_inside = false;
+    const uint32_t key_row = (uint32_t)y * (uint32_t)p.tiles_x;  // strip id = y * tiles_x + column
+    auto flush = [&]() {
+        if (WRITE) {
+            const uint32_t slot = base + nseg;
+            if (slot < cap) {
+                segv[slot] = make_segv(sw0, sw1, sw2, r.ra, r.z0, r.z1, r.z2, a12, a20, a01, *tail, (uint16_t)sx, (uint8_t)cnt);
+                keys[slot] = key_row + (uint32_t)col;
+            }
+        } else if (nseg == 0) {
+            first.w0 = sw0; first.w1 = sw1; first.w2 = sw2; first.x = sx; first.cnt = cnt; first.key = key_row + (uint32_t)col;
+        }
+        *covered += cnt;
+        nseg++;
+    };
+    for (; x <= xend; x++) {
+        const double b0 = w0 * r.ra, b1 = w1 * r.ra, b2 = w2 * r.ra;  // context.go:208-210
+        if (b0 < 0 || b1 < 0 || b2 < 0) {
+            if (was_inside) break;  // context.go:216-218
+        } else {
+            was_inside = true;
+            const int c = (int)x / TILE_W;
+            if (cnt == 0 || c != col) {
+                if (cnt > 0) flush();
+                col = c; sx = (int)x; sw0 = w0; sw1 = w1; sw2 = w2; cnt = 0;
+            }
+            cnt++;
+        }
+        w0 += a12; w1 += a20; w2 += a01;  // context.go:211-213
+    }
+    if (cnt > 0) flush();
+    return nseg;
+}
+
+}  // namespace fgl
