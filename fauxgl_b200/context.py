@@ -148,10 +148,11 @@ def capi():
     """Load libfauxgl_b200.so (built by fauxgl_b200.build / __graft_entry__.build)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("FGL_LIB", LIB_PATH)  # tuning aid: a variant built by tools/build_variant.py
+        if not os.path.exists(path):
             raise FauxglError(-3, "libfauxgl_b200.so has not been built (python -m fauxgl_b200.build); "
                                   "there is no CPU fallback")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         for name, res, args in ABI:
             fn = getattr(L, name)
             fn.restype = res

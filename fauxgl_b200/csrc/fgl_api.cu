@@ -138,9 +138,9 @@ int ensure_work(fgl_ctx *c, const Caps &want) {
         return fail(c, FGL_E_INVALID, "draw too large for 32-bit work indices");
     if (want.prims > wb.cap_prims) {
         dev_free(wb.blk_agg); dev_free(wb.blk_base); dev_free(wb.blk_region);
-        CK(c, dev_alloc(&wb.blk_agg, want.prims / 128 + 2));
-        CK(c, dev_alloc(&wb.blk_base, want.prims / 128 + 2));
-        CK(c, dev_alloc(&wb.blk_region, want.prims / 128 + 2));
+        CK(c, dev_alloc(&wb.blk_agg, want.prims / 32 + 8));
+        CK(c, dev_alloc(&wb.blk_base, want.prims / 32 + 8));
+        CK(c, dev_alloc(&wb.blk_region, want.prims / 32 + 8));
         wb.cap_prims = (uint32_t)want.prims;
     }
     if (want.records > wb.cap_records) {

@@ -35,4 +35,27 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *smem, 
     return r;
 }
 
+// The same with ONE barrier: the warp totals go to one of two alternating buffers (smem[2][THREADS/32]) and
+// every thread adds up the totals of the warps before its own.  `parity` must alternate between successive
+// calls that share the buffers (the barrier of call k orders the reads of call k-1 before the writes of k+1).
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_excl_scan1(uint32_t v, uint32_t (*smem)[THREADS / 32], uint32_t &parity,
+                                                     uint32_t *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t incl = warp_incl_scan(v);
+    uint32_t *buf = smem[parity & 1u];
+    parity ^= 1u;
+    if (lane == 31) buf[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) {
+        const uint32_t t = buf[w];
+        if (w < warp) before += t;
+        all += t;
+    }
+    *total = all;
+    return before + incl - v;
+}
+
 }  // namespace fgl

@@ -627,7 +627,10 @@ k_rec_index(const __grid_constant__ WorkBuffers wb, uint32_t nblocks) {
 // known after the geometry phase) and fills it from the front in (primitive, scanline, column) order; regions
 // are in block-arrival order.  Every block publishes its exact segment count, the last block to finish scans
 // the counts, and k_seg_index lists the segments in primitive order for the stable sort by strip.
-constexpr int FT = 128;
+#ifndef FGL_FRONT_FT
+#define FGL_FRONT_FT 128
+#endif
+constexpr int FT = FGL_FRONT_FT;
 constexpr unsigned long long CELL_SHIFT = 24, NREC_MASK = (1ull << CELL_SHIFT) - 1ull;
 static_assert(FT * 64 < (1 << CELL_SHIFT), "records of one block fit the low bits of its aggregate");
 
@@ -686,13 +689,17 @@ __device__ __noinline__ void emit_general_smem(const DrawParams &p, const WorkBu
     else process_triangle(p, e, prim);
 }
 
-__global__ void __launch_bounds__(FT, 4)
+#ifndef FGL_FRONT_MINB
+#define FGL_FRONT_MINB 6
+#endif
+__global__ void __launch_bounds__(FT, FGL_FRONT_MINB)
 k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
     __shared__ SRec s_rec[FT];
     __shared__ uint32_t s_rowoff[FT + 1];
     __shared__ uint16_t s_order[FT];
     __shared__ unsigned long long s_scan[FT / 32 + 1];
-    __shared__ uint32_t s_scan32[FT / 32 + 1];
+    __shared__ uint32_t s_scan32[2][FT / 32];
+    uint32_t scan_parity = 0;
     __shared__ unsigned long long s_region;
     __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -801,7 +808,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         uint32_t items;
         {
             const uint32_t rows = tid < (int)nw ? s_rec[s_order[tid]].rows : 0u;
-            const uint32_t ex = block_excl_scan<FT>(rows, s_scan32, &items);
+            const uint32_t ex = block_excl_scan1<FT>(rows, s_scan32, scan_parity, &items);
             s_rowoff[tid] = ex;
             if (tid == 0) s_rowoff[FT] = items;
             __syncthreads();
@@ -825,7 +832,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                     atomicAdd(&p.prim_info[2 * (size_t)src_primitive(wb, p, r.src, r.flags)], covered - before);
             }
             uint32_t chunk_total;
-            const uint32_t ex = block_excl_scan<FT>(nseg, s_scan32, &chunk_total);
+            const uint32_t ex = block_excl_scan1<FT>(nseg, s_scan32, scan_parity, &chunk_total);
             if (nseg) {
                 const unsigned long long slot64 = region + seg_run + ex;
                 const SRec &r = s_rec[ridx];

@@ -128,11 +128,11 @@ struct WorkBuffers {
     // The geometry kernel never waits for other blocks: a block takes a region of `recs` with one atomic
     // (slots are in block-arrival order), publishes (scanlines << 30 | records), and the last block to
     // finish scans the aggregates; k_rec_index then lists the slots in primitive order.
-    // (k_front uses the same three arrays for its 128-primitive blocks: segments << 32 | records, the
-    // ordered position of the block's first segment, the first SEGMENT slot of the block.)
-    unsigned long long *blk_agg;    // [cap_prims/128+2] scanlines << 30 | records of each geometry block
-    unsigned long long *blk_base;   // [cap_prims/128+2] exclusive prefix of blk_agg
-    uint32_t *blk_region;           // [cap_prims/128+2] first record slot of the block
+    // (k_front uses the same three arrays with one entry per WARP, 32 primitives: segments << 32 | records,
+    // the ordered position of the warp's first segment, the first SEGMENT slot of the warp.)
+    unsigned long long *blk_agg;    // [cap_prims/32+8] scanlines << 30 | records of each geometry block
+    unsigned long long *blk_base;   // [cap_prims/32+8] exclusive prefix of blk_agg
+    uint32_t *blk_region;           // [cap_prims/32+8] first record slot of the block
     Rec *recs;                // [cap_records]   indexed by slot
     uint32_t *rec_local_row;  // [cap_records]   by slot: scanline offset of the record inside its block
     uint32_t *rec_slot;       // [cap_records+1] by primitive order: slot of the record

@@ -17,7 +17,7 @@ namespace fgl {
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-constexpr int RADIX_BINS_HOST = 256;
+constexpr int RADIX_BINS_HOST = 1024;
 constexpr int RADIX_GRID = 148;
 
 __global__ void __launch_bounds__(SCAN_THREADS)
@@ -107,149 +107,169 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n_max, con
     return 3;
 }
 
-// ---- stable LSD radix sort on 8-bit digits -------------------------------------------
+// ---- stable LSD radix sort, 8- or 10-bit digits ---------------------------------------------
+// One CTA of 1024 threads per SM; every CTA owns a contiguous segment of the input, cut into tiles of
+// 4096 pairs.  Inside a tile warp w owns the 128 consecutive pairs [128 w, 128 w + 128) and takes them in
+// four coalesced rounds of 32, so (warp, round, lane) order IS input order and the ranks below are stable:
+//   rank = pairs with the same digit in earlier warps of the tile      (prefix over warp_cnt[.][digit])
+//        + pairs with the same digit in earlier rounds of this warp    (running warp_cnt[warp][digit])
+//        + lanes with the same digit and a lower lane id               (MATCH.ANY)
+// Four pairs per thread amortise the per-tile clearing and the prefix over the warps, which is what makes
+// 1024 bins affordable: strip ids of an 8K framebuffer (19 bits) sort in two passes instead of three.
 
-constexpr int RADIX_THREADS = 1024;  // one CTA per SM: many warps hide the load latency of each chunk
-constexpr int RADIX_BINS = 256;
+constexpr int RADIX_THREADS = 1024;
 constexpr int RADIX_WARPS = RADIX_THREADS / 32;
+constexpr int RADIX_ITEMS = 4;
+constexpr int RADIX_TILE = RADIX_THREADS * RADIX_ITEMS;
 
 __device__ __forceinline__ void radix_segment(uint32_t n, uint32_t &beg, uint32_t &end) {
-    // contiguous segment of block b; multiple of RADIX_THREADS so sub-tiles stay aligned
+    // contiguous segment of block b; a multiple of the tile so that tiles stay aligned
     uint32_t per = (n + gridDim.x - 1) / gridDim.x;
-    per = (per + RADIX_THREADS - 1) / RADIX_THREADS * RADIX_THREADS;
+    per = (per + RADIX_TILE - 1) / RADIX_TILE * RADIX_TILE;
     uint64_t b = (uint64_t)blockIdx.x * per;
     beg = b < n ? (uint32_t)b : n;
     uint64_t e = b + per;
     end = e < n ? (uint32_t)e : n;
 }
 
+template <int BITS>
 __global__ void __launch_bounds__(RADIX_THREADS)
 k_radix_hist(const uint32_t *__restrict__ keys, const unsigned int *__restrict__ n_dev, uint32_t n_max, int shift,
-             uint32_t *__restrict__ hist /*[256][grid]*/) {
-    __shared__ uint32_t h[RADIX_BINS];
-    if (threadIdx.x < RADIX_BINS) h[threadIdx.x] = 0;
+             uint32_t *__restrict__ hist /*[grid][BINS]*/) {
+    constexpr int BINS = 1 << BITS;
+    __shared__ uint32_t h[BINS];
+    for (int k = threadIdx.x; k < BINS; k += RADIX_THREADS) h[k] = 0;
     __syncthreads();
     const uint32_t n = min(*n_dev, n_max);
     uint32_t beg, end;
     radix_segment(n, beg, end);
     for (uint32_t i = beg + threadIdx.x; i < end; i += RADIX_THREADS)
-        atomicAdd(&h[(keys[i] >> shift) & 0xff], 1u);
+        atomicAdd(&h[(keys[i] >> shift) & (BINS - 1)], 1u);
     __syncthreads();
-    if (threadIdx.x < RADIX_BINS)
-        hist[blockIdx.x * RADIX_BINS + threadIdx.x] = h[threadIdx.x];  // [block][digit]: coalesced here and in the scatter
+    for (int k = threadIdx.x; k < BINS; k += RADIX_THREADS)
+        hist[blockIdx.x * BINS + k] = h[k];  // [block][digit]: coalesced here and in the scatter
 }
 
+template <int BITS>
 __global__ void __launch_bounds__(RADIX_THREADS)
 k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                 const unsigned int *__restrict__ n_dev, uint32_t n_max, int shift,
-                const uint32_t *__restrict__ hist /*[grid][256], raw counts*/) {
-    __shared__ uint32_t cursor[RADIX_BINS];
-    __shared__ uint32_t warp_cnt[RADIX_WARPS][RADIX_BINS];
+                const uint32_t *__restrict__ hist /*[grid][BINS], raw counts*/) {
+    constexpr int BINS = 1 << BITS;
+    constexpr int DPT = (BINS + RADIX_THREADS - 1) / RADIX_THREADS;  // digits per thread in the bucket-base scan (1)
+    static_assert(DPT == 1, "one digit per thread in the bucket-base scan");
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t *cursor = s_dyn;                                   // [BINS]
+    uint32_t(*warp_cnt)[BINS] = reinterpret_cast<uint32_t(*)[BINS]>(s_dyn + BINS);  // [RADIX_WARPS][BINS]
     __shared__ uint32_t s_scan[RADIX_WARPS + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    {   // Every block derives its own bucket bases from the raw histogram (151 KB, L2 resident): four threads
-        // per digit sum it over all blocks (coalesced across threads) -- no separate scan kernel.
-        const uint32_t d = threadIdx.x & (RADIX_BINS - 1), q = threadIdx.x / RADIX_BINS;
-        constexpr uint32_t Q = RADIX_THREADS / RADIX_BINS;
+    {   // Every block derives its own bucket bases from the raw histogram (L2 resident): Q threads per digit
+        // sum it over all blocks (coalesced across threads) -- no separate scan kernel.
+        constexpr uint32_t Q = RADIX_THREADS / BINS;  // 4 (8 bits) or 1 (10 bits)
+        const uint32_t d = threadIdx.x & (BINS - 1), q = threadIdx.x / BINS;
         uint32_t row = 0, before = 0;
         for (uint32_t b = q; b < gridDim.x; b += Q) {
-            const uint32_t v = hist[b * RADIX_BINS + d];
+            const uint32_t v = hist[b * BINS + d];
             row += v;
             if (b < blockIdx.x) before += v;
         }
-        warp_cnt[q][d] = row;
-        warp_cnt[Q + q][d] = before;
-        __syncthreads();
-        row = before = 0;
-        if (threadIdx.x < RADIX_BINS)
-            for (uint32_t k = 0; k < Q; k++) { row += warp_cnt[k][d]; before += warp_cnt[Q + k][d]; }
+        if (Q > 1) {
+            warp_cnt[q][d] = row;
+            warp_cnt[Q + q][d] = before;
+            __syncthreads();
+            row = before = 0;
+            if (threadIdx.x < BINS)
+                for (uint32_t k = 0; k < Q; k++) { row += warp_cnt[k][d]; before += warp_cnt[Q + k][d]; }
+        }
         uint32_t total;
-        const uint32_t digit_base = block_excl_scan<RADIX_THREADS>(row, s_scan, &total);
-        if (threadIdx.x < RADIX_BINS) cursor[d] = digit_base + before;
+        const uint32_t digit_base = block_excl_scan<RADIX_THREADS>(threadIdx.x < BINS ? row : 0u, s_scan, &total);
+        if (threadIdx.x < BINS) cursor[d] = digit_base + before;
     }
     __syncthreads();
     const uint32_t n = min(*n_dev, n_max);
     uint32_t beg, end;
     radix_segment(n, beg, end);
-    for (uint32_t base = beg; base < end; base += RADIX_THREADS) {
-        for (int k = threadIdx.x; k < RADIX_WARPS * RADIX_BINS; k += RADIX_THREADS) (&warp_cnt[0][0])[k] = 0;
+    const uint32_t ltmask = (1u << lane) - 1u;
+    for (uint32_t base = beg; base < end; base += RADIX_TILE) {
+        for (int k = threadIdx.x; k < RADIX_WARPS * BINS; k += RADIX_THREADS) (&warp_cnt[0][0])[k] = 0;
         __syncthreads();
-        const uint32_t i = base + threadIdx.x;
-        const bool valid = i < end;
-        uint32_t key = 0, val = 0, d = 0;
-        if (valid) { key = keys_in[i]; val = vals_in[i]; d = (key >> shift) & 0xff; }
-        // stable rank inside the warp: lanes with the same digit and a lower lane id
-        const uint32_t active = __ballot_sync(0xffffffffu, valid);
-        uint32_t rank = 0;
-        if (valid) {
-            uint32_t peers = __match_any_sync(active, d);
-            rank = __popc(peers & ((1u << lane) - 1u));
-            if (rank == 0) warp_cnt[warp][d] = __popc(peers);
+        uint32_t key[RADIX_ITEMS], val[RADIX_ITEMS], rank[RADIX_ITEMS];
+        bool valid[RADIX_ITEMS];
+        const uint32_t wbase = base + warp * (32 * RADIX_ITEMS);
+#pragma unroll
+        for (int r = 0; r < RADIX_ITEMS; r++) {  // loads first: independent of the ranking
+            const uint32_t i = wbase + r * 32 + lane;
+            valid[r] = i < end;
+            key[r] = valid[r] ? keys_in[i] : 0u;
+            val[r] = valid[r] ? vals_in[i] : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < RADIX_ITEMS; r++) {
+            const uint32_t d = (key[r] >> shift) & (BINS - 1);
+            const uint32_t active = __ballot_sync(0xffffffffu, valid[r]);
+            rank[r] = 0;
+            if (valid[r]) {
+                const uint32_t peers = __match_any_sync(active, d);
+                const int leader = __ffs(peers) - 1;
+                uint32_t old = 0;
+                if (lane == leader) { old = warp_cnt[warp][d]; warp_cnt[warp][d] = old + __popc(peers); }
+                old = __shfl_sync(peers, old, leader);
+                rank[r] = old + __popc(peers & ltmask);
+            }
+            __syncwarp();
         }
         __syncthreads();
-        // thread t < 256 turns the per-warp counts of digit t into exclusive offsets
+        // thread t < BINS turns the per-warp counts of digit t into exclusive offsets
         uint32_t run = 0;
-        if (threadIdx.x < RADIX_BINS) {
+        if (threadIdx.x < BINS) {
 #pragma unroll 8
             for (int w = 0; w < RADIX_WARPS; w++) {
-                uint32_t c = warp_cnt[w][threadIdx.x];
+                const uint32_t c = warp_cnt[w][threadIdx.x];
                 warp_cnt[w][threadIdx.x] = run;
                 run += c;
             }
         }
         __syncthreads();
-        if (valid) {
-            uint32_t pos = cursor[d] + warp_cnt[warp][d] + rank;
-            keys_out[pos] = key;
-            vals_out[pos] = val;
+#pragma unroll
+        for (int r = 0; r < RADIX_ITEMS; r++) {
+            if (valid[r]) {
+                const uint32_t d = (key[r] >> shift) & (BINS - 1);
+                const uint32_t pos = cursor[d] + warp_cnt[warp][d] + rank[r];
+                keys_out[pos] = key[r];
+                vals_out[pos] = val[r];
+            }
         }
         __syncthreads();
-        if (threadIdx.x < RADIX_BINS) cursor[threadIdx.x] += run;
+        if (threadIdx.x < BINS) cursor[threadIdx.x] += run;
         __syncthreads();
     }
 }
 
-
-// hist[256][G] -> exclusive scan in (digit-major, block-minor) order == global base of
-// each (digit, block) bucket.  One CTA: the whole histogram (148 KB) is staged in shared
-// memory with coalesced loads, each thread scans a contiguous slice there (stride 37 words:
-// conflict-free), one block scan joins the slices, and the result streams back coalesced.
-__global__ void __launch_bounds__(1024)
-k_radix_scan(uint32_t *__restrict__ hist, uint32_t n) {
-    extern __shared__ uint32_t s_hist[];
-    __shared__ uint32_t sm[1024 / 32 + 1];
-    for (uint32_t i = threadIdx.x; i < n; i += 1024) s_hist[i] = hist[i];
-    __syncthreads();
-    const uint32_t per = (n + 1023) / 1024;
-    const uint32_t beg = min(threadIdx.x * per, n), end = min(beg + per, n);
-    uint32_t sum = 0;
-    for (uint32_t i = beg; i < end; i++) sum += s_hist[i];
-    uint32_t total;
-    uint32_t run = block_excl_scan<1024>(sum, sm, &total);
-    for (uint32_t i = beg; i < end; i++) {
-        const uint32_t v = s_hist[i];
-        s_hist[i] = run;
-        run += v;
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += 1024) hist[i] = s_hist[i];
+template <int BITS>
+static int radix_pass(uint32_t *const key[2], uint32_t *const val[2], int cur, const unsigned int *n_dev, uint32_t n_max,
+                      int shift, uint32_t *tmp, cudaStream_t st) {
+    constexpr int BINS = 1 << BITS;
+    const size_t smem = sizeof(uint32_t) * (size_t)BINS * (RADIX_WARPS + 1);
+    // per device and cheap: set on every call (a process may drive several GPUs)
+    cudaFuncSetAttribute(k_radix_scatter<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_radix_hist<BITS><<<RADIX_GRID, RADIX_THREADS, 0, st>>>(key[cur], n_dev, n_max, shift, tmp);
+    k_radix_scatter<BITS><<<RADIX_GRID, RADIX_THREADS, smem, st>>>(key[cur], val[cur], key[cur ^ 1], val[cur ^ 1], n_dev,
+                                                                  n_max, shift, tmp);
+    return 2;
 }
 
-// Stable LSD radix sort of (key, val) on `bits` key bits, 8 bits per pass.
+// Stable LSD radix sort of (key, val) on `bits` key bits: as few passes as 10-bit digits allow, 8-bit digits
+// when they need no more passes (smaller histograms).
 int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsigned int *n_dev, uint32_t n_max,
                       int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st) {
     int launches = 0, cur = 0;
-    const int G = RADIX_GRID;
-    const size_t scan_smem = sizeof(uint32_t) * RADIX_BINS * G;
-    // per device and cheap: set on every call (a process may drive several GPUs)
-    cudaFuncSetAttribute(k_radix_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
-    for (int shift = 0; shift < bits; shift += 8) {
-        k_radix_hist<<<G, RADIX_THREADS, 0, st>>>(key[cur], n_dev, n_max, shift, tmp);
-        k_radix_scatter<<<G, RADIX_THREADS, 0, st>>>(key[cur], val[cur], key[cur ^ 1], val[cur ^ 1], n_dev, n_max, shift,
-                                                     tmp);
+    const int passes = (bits + 9) / 10;
+    const bool narrow = passes * 8 >= bits;
+    for (int shift = 0; shift < bits; shift += narrow ? 8 : 10) {
+        launches += narrow ? radix_pass<8>(key, val, cur, n_dev, n_max, shift, tmp, st)
+                           : radix_pass<10>(key, val, cur, n_dev, n_max, shift, tmp, st);
         cur ^= 1;
-        launches += 2;
     }
     *sorted_buf = cur;
     return launches;

@@ -158,13 +158,18 @@ k_span_place(const __grid_constant__ DrawParams p, const __grid_constant__ WorkB
 // are appended from the front, the others from the back, so that the strip kernel starts the long ones
 // first.  Only entries of strips that occur are written -- and only those are read (through the busy
 // list), so the arrays are never cleared.
-__global__ void k_tile_ranges(const uint32_t *__restrict__ keys, const unsigned int *__restrict__ n_dev, uint32_t n_max,
-                              uint32_t *__restrict__ tile_start, uint32_t *__restrict__ tile_end,
-                              uint32_t *__restrict__ busy_list, uint32_t ntiles, TileCtl *ctl) {
+constexpr int TR_THREADS = 1024;
+__global__ void __launch_bounds__(TR_THREADS)
+k_tile_ranges(const uint32_t *__restrict__ keys, const unsigned int *__restrict__ n_dev, uint32_t n_max,
+              uint32_t *__restrict__ tile_start, uint32_t *__restrict__ tile_end,
+              uint32_t *__restrict__ busy_list, uint32_t ntiles, TileCtl *ctl) {
+    __shared__ uint32_t s_cnt[2], s_base[2];
     const uint32_t n = min(*n_dev, n_max);
     const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
-        const uint32_t i = i0 + lane;
+    for (uint32_t i0 = blockIdx.x * TR_THREADS; i0 < n; i0 += gridDim.x * TR_THREADS) {
+        if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t i = i0 + threadIdx.x;
         bool starts = false, heavy = false;
         uint32_t k = 0;
         if (i < n) {
@@ -176,19 +181,25 @@ __global__ void k_tile_ranges(const uint32_t *__restrict__ keys, const unsigned 
             }
             if (i == n - 1 || keys[i + 1] != k) tile_end[k] = i + 1;
         }
-        // warp-aggregated append of the strips that start in this warp's window
+        // list the strips that start in this window: warp ballot -> CTA counters -> ONE global atomic per list
         const uint32_t mh = __ballot_sync(0xffffffffu, starts && heavy), ml = __ballot_sync(0xffffffffu, starts && !heavy);
-        if (mh) {
-            uint32_t base = 0;
-            if (lane == (uint32_t)(__ffs(mh) - 1)) base = atomicAdd(&ctl->nheavy, (uint32_t)__popc(mh));
-            base = __shfl_sync(0xffffffffu, base, __ffs(mh) - 1);
-            if (starts && heavy) busy_list[base + __popc(mh & ((1u << lane) - 1u))] = k;
+        uint32_t wh = 0, wl = 0;
+        if (lane == 0) {
+            if (mh) wh = atomicAdd(&s_cnt[0], (uint32_t)__popc(mh));
+            if (ml) wl = atomicAdd(&s_cnt[1], (uint32_t)__popc(ml));
         }
-        if (ml) {
-            uint32_t base = 0;
-            if (lane == (uint32_t)(__ffs(ml) - 1)) base = atomicAdd(&ctl->nlight, (uint32_t)__popc(ml));
-            base = __shfl_sync(0xffffffffu, base, __ffs(ml) - 1);
-            if (starts && !heavy) busy_list[ntiles - 1u - (base + __popc(ml & ((1u << lane) - 1u)))] = k;
+        wh = __shfl_sync(0xffffffffu, wh, 0);
+        wl = __shfl_sync(0xffffffffu, wl, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_base[0] = s_cnt[0] ? atomicAdd(&ctl->nheavy, s_cnt[0]) : 0u;
+            s_base[1] = s_cnt[1] ? atomicAdd(&ctl->nlight, s_cnt[1]) : 0u;
+        }
+        __syncthreads();
+        if (starts) {
+            const uint32_t lt = (1u << lane) - 1u;
+            if (heavy) busy_list[s_base[0] + wh + __popc(mh & lt)] = k;
+            else busy_list[ntiles - 1u - (s_base[1] + wl + __popc(ml & lt))] = k;
         }
     }
 }
@@ -218,7 +229,7 @@ int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cuda
     while ((1u << bits) < wb.ntiles) bits++;
     launches += launch_sort_pairs(wb.seg_key, wb.seg_val, &c->n_segs, wb.cap_segs, bits, wb.scan_tmp, sorted_buf, st);
     cudaMemsetAsync(wb.tile_ctl, 0, sizeof(TileCtl), st);
-    k_tile_ranges<<<148 * 4, 256, 0, st>>>(wb.seg_key[*sorted_buf], &c->n_segs, wb.cap_segs, wb.tile_start, wb.tile_end,
+    k_tile_ranges<<<148, TR_THREADS, 0, st>>>(wb.seg_key[*sorted_buf], &c->n_segs, wb.cap_segs, wb.tile_start, wb.tile_end,
                                            wb.busy_list, wb.ntiles, wb.tile_ctl);
     launches++;
     return launches;

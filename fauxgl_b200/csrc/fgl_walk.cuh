@@ -35,8 +35,74 @@ struct ParkedSeg {
     uint32_t key;   // strip id
 };
 
+// Per-triangle constants of the row walk (context.go:167-181).
+struct EdgeSetup {
+    double a01, b01, a12, b12, a20, b20;
+    double ra, ra12, ra20, ra01;
+    int32_t x0, x1;
+};
+template <class R>
+__device__ __forceinline__ EdgeSetup edge_setup(const R &r) {
+    EdgeSetup e;
+    e.a01 = r.s1y - r.s0y; e.b01 = r.s0x - r.s1x;  // context.go:167-172
+    e.a12 = r.s2y - r.s1y; e.b12 = r.s1x - r.s2x;
+    e.a20 = r.s0y - r.s2y; e.b20 = r.s2x - r.s0x;
+    e.ra = r.ra; e.ra12 = r.ra12; e.ra20 = r.ra20; e.ra01 = r.ra01;
+    e.x0 = r.x0; e.x1 = r.x1;
+    return e;
+}
+
+// One row, given the edge values (w00, w01, w02) at its first pixel centre (x0 + .5, y + .5):
+// context.go:185-221.  emit(w0, w1, w2, x, cnt, strip) is called for every segment, left to right.
+// Returns the number of segments; adds the covered pixels to *covered.
+template <class F>
+__device__ __forceinline__ uint32_t walk_row_core(const DrawParams &p, const EdgeSetup &e, int y, double w00, double w01,
+                                                  double w02, F &&emit, unsigned long long *covered) {
+    // skip-ahead, context.go:185-205
+    double d = 0;
+    const double d0 = -w00 * e.ra12, d1 = -w01 * e.ra20, d2 = -w02 * e.ra01;
+    if (w00 < 0 && d0 > d) d = d0;
+    if (w01 < 0 && d1 > d) d = d1;
+    if (w02 < 0 && d2 > d) d = d2;
+    d = (double)go_int(d);
+    if (d < 0) d = 0;
+    double w0 = w00 + e.a12 * d, w1 = w01 + e.a20 * d, w2 = w02 + e.a01 * d;
+    long long x = (long long)e.x0 + go_int(d);
+    const long long xend = min((long long)e.x1, (long long)p.width - 1);
+    if (x > xend) return 0;
+    for (; x < 0; x++) { w0 += e.a12; w1 += e.a20; w2 += e.a01; }  // left of the framebuffer: dropped (x-guard rule)
+    uint32_t nseg = 0, cnt = 0;
+    int col = -1, sx = 0;
+    double sw0 = 0, sw1 = 0, sw2 = 0;
+    bool was_inside = false;
+    const uint32_t key_row = (uint32_t)y * (uint32_t)p.tiles_x;  // strip id = y * tiles_x + column
+    // Exact early exit.  fl(w + a) is monotone in w, so an edge value whose per-pixel increment is <= 0 never
+    // grows along the row, and neither does b = fl(w * ra) for ra > 0: once such a b is negative, every later
+    // pixel of the row is outside as well -- the reference would test them all and find nothing.
+    const bool pos = e.ra > 0;
+    const bool n12 = pos && e.a12 <= 0, n20 = pos && e.a20 <= 0, n01 = pos && e.a01 <= 0;
+    for (; x <= xend; x++) {
+        const double b0 = w0 * e.ra, b1 = w1 * e.ra, b2 = w2 * e.ra;  // context.go:208-210
+        if (b0 < 0 || b1 < 0 || b2 < 0) {
+            if (was_inside) break;  // context.go:216-218
+            if ((n12 && b0 < 0) || (n20 && b1 < 0) || (n01 && b2 < 0)) break;
+        } else {
+            was_inside = true;
+            const int c = (int)x / TILE_W;
+            if (cnt == 0 || c != col) {
+                if (cnt > 0) { emit(sw0, sw1, sw2, sx, cnt, key_row + (uint32_t)col); *covered += cnt; nseg++; }
+                col = c; sx = (int)x; sw0 = w0; sw1 = w1; sw2 = w2; cnt = 0;
+            }
+            cnt++;
+        }
+        w0 += e.a12; w1 += e.a20; w2 += e.a01;  // context.go:211-213
+    }
+    if (cnt > 0) { emit(sw0, sw1, sw2, sx, cnt, key_row + (uint32_t)col); *covered += cnt; nseg++; }
+    return nseg;
+}
+
 // Walk row y of the triangle described by r (any struct with the fields s0x..s2y, w00..w02, ra, ra12, ra20,
-// ra01, z0..z2, x0, x1, y0).  Returns the number of segments and adds the covered pixels to *covered.
+// ra01, z0..z2, x0, x1, y0): the per-row adds are replayed from y0 (context.go:275-277).
 //   WRITE == false: the first segment is returned in `first`, nothing is stored.
 //   WRITE == true : every segment k is stored as segv[base + k] / keys[base + k] (if base + k < cap).
 template <bool WRITE, class R>
@@ -44,59 +110,22 @@ __device__ __forceinline__ uint32_t walk_row_segments(const DrawParams &p, const
                                                       const RecTail *tail, SegV *__restrict__ segv,
                                                       uint32_t *__restrict__ keys, uint32_t base, uint32_t cap,
                                                       unsigned long long *covered) {
-    const double a01 = r.s1y - r.s0y, b01 = r.s0x - r.s1x;  // context.go:167-172
-    const double a12 = r.s2y - r.s1y, b12 = r.s1x - r.s2x;
-    const double a20 = r.s0y - r.s2y, b20 = r.s2x - r.s0x;
+    const EdgeSetup e = edge_setup(r);
     double w00 = r.w00, w01 = r.w01, w02 = r.w02;
-    for (int yy = r.y0; yy < y; yy++) { w00 += b12; w01 += b20; w02 += b01; }  // context.go:275-277
-    // skip-ahead, context.go:185-205
-    double d = 0;
-    const double d0 = -w00 * r.ra12, d1 = -w01 * r.ra20, d2 = -w02 * r.ra01;
-    if (w00 < 0 && d0 > d) d = d0;
-    if (w01 < 0 && d1 > d) d = d1;
-    if (w02 < 0 && d2 > d) d = d2;
-    d = (double)go_int(d);
-    if (d < 0) d = 0;
-    double w0 = w00 + a12 * d, w1 = w01 + a20 * d, w2 = w02 + a01 * d;
-    long long x = (long long)r.x0 + go_int(d);
-    const long long xend = min((long long)r.x1, (long long)p.width - 1);
-    if (x > xend) return 0;
-    for (; x < 0; x++) { w0 += a12; w1 += a20; w2 += a01; }  // left of the framebuffer: dropped (x-guard rule)
-    uint32_t nseg = 0, cnt = 0;
-    int col = -1, sx = 0;
-    double sw0 = 0, sw1 = 0, sw2 = 0;
-    bool was_inside = false;
-    const uint32_t key_row = (uint32_t)y * (uint32_t)p.tiles_x;  // strip id = y * tiles_x + column
-    auto flush = [&]() {
+    for (int yy = r.y0; yy < y; yy++) { w00 += e.b12; w01 += e.b20; w02 += e.b01; }  // context.go:275-277
+    uint32_t k = 0;
+    return walk_row_core(p, e, y, w00, w01, w02, [&](double sw0, double sw1, double sw2, int sx, uint32_t cnt, uint32_t key) {
         if (WRITE) {
-            const uint32_t slot = base + nseg;
+            const uint32_t slot = base + k;
             if (slot < cap) {
-                segv[slot] = make_segv(sw0, sw1, sw2, r.ra, r.z0, r.z1, r.z2, a12, a20, a01, *tail, (uint16_t)sx, (uint8_t)cnt);
-                keys[slot] = key_row + (uint32_t)col;
+                segv[slot] = make_segv(sw0, sw1, sw2, r.ra, r.z0, r.z1, r.z2, e.a12, e.a20, e.a01, *tail, (uint16_t)sx, (uint8_t)cnt);
+                keys[slot] = key;
             }
-        } else if (nseg == 0) {
-            first.w0 = sw0; first.w1 = sw1; first.w2 = sw2; first.x = sx; first.cnt = cnt; first.key = key_row + (uint32_t)col;
+        } else if (k == 0) {
+            first.w0 = sw0; first.w1 = sw1; first.w2 = sw2; first.x = sx; first.cnt = cnt; first.key = key;
         }
-        *covered += cnt;
-        nseg++;
-    };
-    for (; x <= xend; x++) {
-        const double b0 = w0 * r.ra, b1 = w1 * r.ra, b2 = w2 * r.ra;  // context.go:208-210
-        if (b0 < 0 || b1 < 0 || b2 < 0) {
-            if (was_inside) break;  // context.go:216-218
-        } else {
-            was_inside = true;
-            const int c = (int)x / TILE_W;
-            if (cnt == 0 || c != col) {
-                if (cnt > 0) flush();
-                col = c; sx = (int)x; sw0 = w0; sw1 = w1; sw2 = w2; cnt = 0;
-            }
-            cnt++;
-        }
-        w0 += a12; w1 += a20; w2 += a01;  // context.go:211-213
-    }
-    if (cnt > 0) flush();
-    return nseg;
+        k++;
+    }, covered);
 }
 
 }  // namespace fgl
