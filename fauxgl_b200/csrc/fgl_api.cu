@@ -500,13 +500,11 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
         cudaDeviceProp prop;
         c->wb.nsm = cudaGetDeviceProperties(&prop, device) == cudaSuccess ? (uint32_t)prop.multiProcessorCount : 148u;
     }
-    if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_start, c->wb.ntiles);
-    if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_end, c->wb.ntiles);
     if (err == cudaSuccess) err = dev_alloc(&c->wb.busy_list, c->wb.ntiles);
     if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_ctl, 1);
     if (err == cudaSuccess && getenv("FGL_TILE_CLOCK")) {  // tuning aid: per-tile cycle counts of k_tile
-        err = dev_alloc(&c->wb.tile_clock, (size_t)c->wb.ntiles * 2);
-        if (err == cudaSuccess) err = cudaMemset(c->wb.tile_clock, 0, sizeof(unsigned long long) * c->wb.ntiles * 2);
+        err = dev_alloc(&c->wb.tile_clock, (size_t)c->wb.ntiles * 2 + 16);  // + 16 path counters of k_strip
+        if (err == cudaSuccess) err = cudaMemset(c->wb.tile_clock, 0, sizeof(unsigned long long) * ((size_t)c->wb.ntiles * 2 + 16));
     }
     if (err == cudaSuccess) err = cudaMemsetAsync(c->acc_dev, 0, sizeof(DrawCounters), c->stream);
     if (err != cudaSuccess) {
@@ -538,7 +536,7 @@ int fgl_context_destroy(fgl_ctx *c) {
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_work(c->wb);
-    dev_free(c->wb.tile_start); dev_free(c->wb.tile_end); dev_free(c->wb.counters); dev_free(c->wb.tile_clock);
+    dev_free(c->wb.counters); dev_free(c->wb.tile_clock);
     dev_free(c->wb.tile_ctl); dev_free(c->wb.busy_list); dev_free(c->wb.vis_seg);
     dev_free(c->prim_info); dev_free(c->scratch); dev_free(c->gray16);
     dev_free(c->acc_dev); dev_free(c->color); dev_free(c->depth); dev_free(c->resolved);
@@ -1163,7 +1161,8 @@ int fgl_debug_tile_cycles(fgl_ctx *c, uint64_t *dst, uint64_t ntiles) {
     int rc = check_ctx(c);
     if (rc) return rc;
     if (!c->wb.tile_clock) return fail(c, FGL_E_INVALID, "set FGL_TILE_CLOCK=1 before creating the context");
-    if (!dst || ntiles != c->wb.ntiles) return fail(c, FGL_E_INVALID, "need a buffer of 2*%u uint64", c->wb.ntiles);
+    if (!dst || (ntiles != c->wb.ntiles && ntiles != c->wb.ntiles + 8))  // + 8: also the 16 path counters
+        return fail(c, FGL_E_INVALID, "need a buffer of 2*%u uint64", c->wb.ntiles);
     std::lock_guard<std::mutex> lock(c->mu);
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaMemcpy(dst, c->wb.tile_clock, sizeof(uint64_t) * 2 * ntiles, cudaMemcpyDeviceToHost));

@@ -591,6 +591,7 @@ k_geometry(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuf
         if (nrows > wb.cap_rows) ovf |= OVF_ROWS;
         if (ovf) atomicOr(&c->overflow, ovf);
         if (nrec <= wb.cap_records) wb.rec_row_off[nrec] = nrows;  // sentinel for the span stage's search
+        wb.tile_ctl->nheavy = 0; wb.tile_ctl->nlight = 0; wb.tile_ctl->head = 0;  // the busy-strip list of this draw
     }
 }
 
@@ -900,6 +901,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     if (tid == 0) {
         const unsigned long long tot = s_scan[FT / 32];
         DrawCounters *c = wb.counters;
+        wb.tile_ctl->nheavy = 0; wb.tile_ctl->nlight = 0; wb.tile_ctl->head = 0;  // the busy-strip list of this draw
         const unsigned long long cells_total = c->seg_cursor;  // every block has made its reservation
         const uint32_t nsegs = (uint32_t)(tot >> 32);
         c->n_records = (uint32_t)tot; c->need_records = 0;
@@ -916,17 +918,22 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
 }
 
 // Segments in primitive order for the stable sort: position blk_base[b] + k  <-  slot blk_region[b] + k.
+// One thread per ordered position; its block is found by binary search in blk_base (a few thousand entries,
+// cache resident).
 __global__ void __launch_bounds__(256)
-k_seg_index(const __grid_constant__ WorkBuffers wb, uint32_t nblocks) {
-    if (wb.counters->overflow) return;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nblocks; b += nwarps) {
-        const uint32_t cnt = (uint32_t)(wb.blk_agg[b] >> 32), base = (uint32_t)wb.blk_base[b], region = wb.blk_region[b];
-        for (uint32_t k = lane; k < cnt; k += 32) {
-            wb.seg_key[0][base + k] = wb.seg_key[1][region + k];
-            wb.seg_val[0][base + k] = region + k;
+k_seg_index(const __grid_constant__ WorkBuffers wb, uint32_t nent) {
+    const DrawCounters *ctr = wb.counters;
+    if (ctr->overflow) return;
+    const uint32_t n = min(ctr->n_segs, wb.cap_segs);
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = nent;  // blk_base[lo] <= pos < blk_base[hi]  (blk_base[nent] = n, never read)
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((uint32_t)__ldg(&wb.blk_base[mid]) <= pos) lo = mid; else hi = mid;
         }
+        const uint32_t slot = wb.blk_region[lo] + (pos - (uint32_t)wb.blk_base[lo]);
+        wb.seg_key[0][pos] = wb.seg_key[1][slot];
+        wb.seg_val[0][pos] = slot;
     }
 }
 
@@ -934,8 +941,7 @@ int launch_front(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {
     const uint32_t blocks = (p.count + FT - 1) / FT;
     cudaMemsetAsync(wb.counters, 0, sizeof(DrawCounters), st);
     k_front<<<blocks, FT, 0, st>>>(p, wb);
-    const uint32_t g = (blocks + 7u) / 8u;
-    k_seg_index<<<g < 148u * 8u ? g : 148u * 8u, 256, 0, st>>>(wb, blocks);
+    k_seg_index<<<148 * 8, 256, 0, st>>>(wb, blocks);
     return 2;
 }
 

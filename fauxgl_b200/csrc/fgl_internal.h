@@ -15,7 +15,10 @@ namespace fgl {
 // segment per strip it crosses, so wide strips mean few segments, and a segment never spans
 // rows, so one-row strips add none.  One warp resolves a strip (fgl_raster.cu): a 64-bit mask
 // per lane describes the pixels a segment still has to write.
-constexpr int TILE_W = 64;
+#ifndef FGL_TILE_W
+#define FGL_TILE_W 64
+#endif
+constexpr int TILE_W = FGL_TILE_W;
 
 // ---- device mesh: planar SoA ----------------------------------------------------
 // plane(attr, v, c)[i] = attr_base[(v * ncomp + c) * n + i]; a warp reading one
@@ -146,10 +149,9 @@ struct WorkBuffers {
     // binning: stable sort of segment indices by tile
     uint32_t *seg_key[2];     // [cap_segs] tile id (ping-pong for the radix sort)
     uint32_t *seg_val[2];     // [cap_segs] segment index
-    uint32_t *tile_start;     // [ntiles]    bin of strip t = sorted positions [tile_start[t], tile_end[t])
-    uint32_t *tile_end;       // [ntiles]
     SegV *segv;               // [cap_segs]  segments in (record, scanline, column) order; bins index into it
-    uint32_t *busy_list;      // [ntiles]    strips with a non-empty bin, heavy ones from the front, the rest from the back
+    uint2 *busy_list;         // [ntiles]    (strip, first sorted position of its bin) of every strip with a non-empty bin:
+                              //             heavy ones from the front, the rest from the back
     uint32_t nsm;             // SMs of the device
     TileCtl *tile_ctl;        // device
     uint32_t *vis_seg;        // [ntiles*TILE_W] deferred shading: per pixel of a busy strip, the segment (index into

@@ -56,6 +56,16 @@ k_resolve(const uint32_t *__restrict__ src, int sw, int sh, uint32_t *__restrict
     const int rows = (RES_OY - 1) * factor + W.flen;  // source rows this tile needs
     const int row_start = factor * oy0 + W.start0;
     const int tid = threadIdx.y * RES_OX + threadIdx.x;
+    // Fast path of the usual 4x4 SSAA (8 taps, weights <= 255, sum a power of two) for opaque pixels away from
+    // the left/right border: three aligned 16-byte loads bring in the 8 taps, the bytes are transposed into one
+    // word per channel (PRMT) and each channel is two 4-way byte dot products (DP4A) -- the same integer
+    // arithmetic as the generic loop below (with alpha == 255 the premultiplication r * a / 255 is the identity).
+    const bool fast4 = factor == 4 && W.flen == 8 && W.sum == 1024 && (sw & 3) == 0;
+    uint32_t cA = 0, cB = 0;
+    if (fast4) {
+        cA = (uint32_t)W.coeff[0] | ((uint32_t)W.coeff[1] << 8) | ((uint32_t)W.coeff[2] << 16) | ((uint32_t)W.coeff[3] << 24);
+        cB = (uint32_t)W.coeff[4] | ((uint32_t)W.coeff[5] << 8) | ((uint32_t)W.coeff[6] << 16) | ((uint32_t)W.coeff[7] << 24);
+    }
     // pass 1: horizontal (resizeNRGBA)
     for (int idx = tid; idx < rows * RES_OX; idx += RES_OX * RES_OY) {
         const int r = idx / RES_OX, c = idx % RES_OX;
@@ -66,6 +76,22 @@ k_resolve(const uint32_t *__restrict__ src, int sw, int sh, uint32_t *__restrict
             sy = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy);  // pass 2 clamps its (row) index the same way
             const uint32_t *row = src + (size_t)sy * sw;
             const int start = factor * ox + W.start0;
+            if (fast4 && start >= 2 && start + 10 <= sw) {  // taps start .. start+7 = pixels 2..9 of the 12 loaded
+                const uint4 *q = reinterpret_cast<const uint4 *>(row + (start - 2));
+                const uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+                const uint32_t p0 = v0.z, p1 = v0.w, p2 = v1.x, p3 = v1.y, p4 = v1.z, p5 = v1.w, p6 = v2.x, p7 = v2.y;
+                if (((p0 & p1 & p2 & p3 & p4 & p5 & p6 & p7) >> 24) == 0xffu) {
+                    const uint32_t lo = __byte_perm(p0, p1, 0x5140), hi = __byte_perm(p2, p3, 0x5140);      // r r g g
+                    const uint32_t lo2 = __byte_perm(p0, p1, 0x7362), hi2 = __byte_perm(p2, p3, 0x7362);    // b b a a
+                    const uint32_t mo = __byte_perm(p4, p5, 0x5140), mi = __byte_perm(p6, p7, 0x5140);
+                    const uint32_t mo2 = __byte_perm(p4, p5, 0x7362), mi2 = __byte_perm(p6, p7, 0x7362);
+                    const uint32_t rr = __dp4a(__byte_perm(mo, mi, 0x5410), cB, __dp4a(__byte_perm(lo, hi, 0x5410), cA, 0u));
+                    const uint32_t gg = __dp4a(__byte_perm(mo, mi, 0x7632), cB, __dp4a(__byte_perm(lo, hi, 0x7632), cA, 0u));
+                    const uint32_t bb = __dp4a(__byte_perm(mo2, mi2, 0x5410), cB, __dp4a(__byte_perm(lo2, hi2, 0x5410), cA, 0u));
+                    s_temp[idx] = (rr >> 10) | ((gg >> 10) << 8) | ((bb >> 10) << 16) | 0xff000000u;  // alpha: 1024 * 255 >> 10
+                    continue;
+                }
+            }
             int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
             for (int i = 0; i < W.flen; i++) {
                 const int coeff = W.coeff[i];

@@ -52,15 +52,16 @@ constexpr int SWARPS = 8;               // warps (= strips in flight) per CTA
 constexpr int STHREADS = SWARPS * 32;
 constexpr uint32_t NO_WINNER = 0xffffffffu;
 constexpr uint32_t NO_SEG = 0xffffffffu;
-static_assert(TILE_W == 64, "a strip is one 64-bit pending mask wide");
+static_assert(TILE_W == 64 || TILE_W == 32, "a strip is one 64-bit pending mask wide at most");
+constexpr int STRIP_H = TILE_W / 32;  // pixels per lane
 
 constexpr int ZCAP = 256;  // fragments of a chunk the pixel-parallel resolution can stage
 template <bool DEFERRED> struct StripMem;
 template <> struct StripMem<true> {
+    double zbuf[ZCAP];       // depth of every fragment of the chunk, segment-major
     double depth[TILE_W];
     uint32_t winseg[TILE_W]; // segment (index into segv) whose fragment currently owns the pixel
     // pixel-parallel resolution of a chunk whose segments overlap
-    double zbuf[ZCAP];       // depth of every fragment of the chunk, segment-major
     uint32_t cover[TILE_W];  // lanes (= segments, in primitive order) that cover the pixel
     uint32_t segidx[32];     // segv index of the lane's segment
     uint32_t upd[32];        // UpdatedPixels per segment (per-primitive RasterizeInfo only)
@@ -123,15 +124,17 @@ FGL_DI void resolve_deferred(const fgl_state &st, StripMem<true> &sm, int pi, do
     }
 }
 
-FGL_DI uint32_t strip_at(const WorkBuffers &wb, uint32_t nheavy, uint32_t q) {
+FGL_DI uint2 busy_at(const WorkBuffers &wb, uint32_t nheavy, uint32_t q) {
     return q < nheavy ? wb.busy_list[q] : wb.busy_list[wb.ntiles - 1u - (q - nheavy)];
 }
+FGL_DI void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
 // EACH: also attribute UpdatedPixels to the primitive of every segment (fgl_draw_*_each).
 template <bool DEFERRED, bool EACH>
 __global__ void __launch_bounds__(STHREADS, DEFERRED ? 4 : 3)
 k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb,
-        const uint32_t *__restrict__ seg_order, uint32_t *__restrict__ gcolor, double *__restrict__ gdepth) {
+        const uint32_t *__restrict__ seg_order, const uint32_t *__restrict__ seg_keys, uint32_t *__restrict__ gcolor,
+        double *__restrict__ gdepth) {
     if (wb.counters->overflow) return;  // work buffers too small: the host regrows and re-issues the draw
 
     __shared__ StripMem<DEFERRED> s_all[SWARPS];
@@ -140,32 +143,38 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     const fgl_state st = p.state;
     unsigned long long my_updated = 0;
     if constexpr (DEFERRED) {  // scratch of the pixel-parallel resolution: every use leaves it clean
-        sm.cover[lane] = 0; sm.cover[lane + 32] = 0;
+        for (int h = 0; h < STRIP_H; h++) sm.cover[lane + 32 * h] = 0;
         sm.upd[lane] = 0;
         __syncwarp();
     }
 
-    // Busy strips, heavy ones first (k_tile_ranges), are pulled dynamically; the pull for the NEXT strip
-    // and its bin range are requested while the current strip is processed.
+    // Busy strips (heavy ones first in the list, k_tile_ranges) are dealt out round-robin over all warps of the
+    // grid.  The strip loop is software-pipelined so that no dependent load is waited for: while strip t is
+    // processed, the list entry of t+3, the first 32 (segment, key) pairs of t+2 and an L2 prefetch of the first
+    // segments and the depth row of t+1 are in flight.
+    const uint32_t nsegs = min(wb.counters->n_segs, wb.cap_segs);
     const uint32_t nheavy = wb.tile_ctl->nheavy, nbusy = nheavy + wb.tile_ctl->nlight;
-    const uint32_t pull = nbusy > 32768u ? 4u : 1u;  // same-address atomics: keep their number in the low thousands
-    uint32_t q = 0, q_end = 0;  // current pull [q, q_end)
-    if (lane == 0) q = atomicAdd(&wb.tile_ctl->head, pull);
-    q = __shfl_sync(0xffffffffu, q, 0);
-    q_end = min(q + pull, nbusy);
-    uint32_t strip = 0, bin_beg = 0, bin_end = 0;
-    if (q < nbusy) {
-        strip = strip_at(wb, nheavy, q);
-        bin_beg = wb.tile_start[strip]; bin_end = wb.tile_end[strip];
-    }
-    while (q < nbusy) {
-        // request the next strip: the atomic now, its dependent loads further down
-        uint32_t nq = q + 1, nq_end = q_end;
-        if (nq >= q_end) {
-            if (lane == 0) nq = atomicAdd(&wb.tile_ctl->head, pull);
-        }
+    const uint32_t nwarps = gridDim.x * SWARPS;
+    uint32_t q = blockIdx.x * SWARPS + (threadIdx.x >> 5);
+    auto load_entry = [&](uint32_t qq) { return qq < nbusy ? busy_at(wb, nheavy, qq) : make_uint2(0xffffffffu, 0u); };
+    // (segment index, valid) of sorted position pos for a bin of `strip`
+    auto load_pair = [&](uint32_t strip, uint32_t pos) {
+        uint32_t idx = NO_SEG;
+        if (strip != 0xffffffffu && pos < nsegs && seg_keys[pos] == strip) idx = seg_order[pos];
+        return idx;
+    };
+    uint2 e0 = load_entry(q), e1 = load_entry(q + nwarps), e2 = load_entry(q + 2 * nwarps);
+    uint32_t ik0 = load_pair(e0.x, e0.y + lane), ik1 = load_pair(e1.x, e1.y + lane);
+    while (e0.x != 0xffffffffu) {
+        const uint32_t strip = e0.x, bin_beg = e0.y;
+        // pipeline: entry of t+3, pairs of t+2, prefetch of t+1
+        const uint2 e3 = load_entry(q + 3 * nwarps);
+        const uint32_t ik2 = load_pair(e2.x, e2.y + lane);
+        if (ik1 != NO_SEG) prefetch_l2(wb.segv + ik1);
+        if (e1.x != 0xffffffffu && lane < TILE_W / 16)
+            prefetch_l2(gdepth + (size_t)(e1.x / (uint32_t)p.tiles_x) * p.width + (e1.x % (uint32_t)p.tiles_x) * TILE_W + lane * 16);
         const long long t_begin = wb.tile_clock ? clock64() : 0;
-        const uint32_t nseg = bin_end - bin_beg;
+        uint32_t nseg = 0;
         const int x0 = (int)(strip % (uint32_t)p.tiles_x) * TILE_W;
         const int y = (int)(strip / (uint32_t)p.tiles_x);
         const int tw = min(TILE_W, p.width - x0);  // valid columns of this strip
@@ -173,9 +182,8 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
 
         // ---- load the strip --------------------------------------------------------------
         __syncwarp();
-        uint32_t idx_next = bin_beg + lane < bin_end ? seg_order[bin_beg + lane] : NO_SEG;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < STRIP_H; h++) {
             const int i = lane + 32 * h;
             if constexpr (DEFERRED) sm.winseg[i] = NO_WINNER;
             if (i < tw) {
@@ -183,22 +191,19 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                 if constexpr (!DEFERRED) sm.color[i] = gcolor[grow + i];
             }
         }
-        if (q + 1 >= q_end) {
-            nq = __shfl_sync(0xffffffffu, nq, 0);
-            nq_end = min(nq + pull, nbusy);
-        }
-        uint32_t nstrip = 0;
-        if (nq < nbusy) nstrip = strip_at(wb, nheavy, nq);
         __syncwarp();
         const unsigned long long updated_at_start = my_updated;
 
-        // ---- the bin, 32 segments at a time ------------------------------------------------
-        for (uint32_t chunk = bin_beg; chunk < bin_end; chunk += 32) {
-            const uint32_t idx = idx_next;
-            idx_next = chunk + 32 + lane < bin_end ? seg_order[chunk + 32 + lane] : NO_SEG;
+        // ---- the bin, 32 segments at a time; the pairs of chunk c+2 and an L2 prefetch of the segments of chunk
+        // c+1 are in flight while chunk c is resolved.  The bin ends where the sorted key changes. -------------
+        uint32_t idx = ik0, idx_b = load_pair(strip, bin_beg + 32 + lane);
+        for (uint32_t chunk = bin_beg; __any_sync(0xffffffffu, idx != NO_SEG); chunk += 32) {
+            const uint32_t idx_c = load_pair(strip, chunk + 64 + lane);
+            nseg += (uint32_t)__popc(__ballot_sync(0xffffffffu, idx != NO_SEG));
             SegV v;
             v.cnt = 0; v.x = (uint16_t)x0;
             if (idx != NO_SEG) v = wb.segv[idx];
+            if (idx_b != NO_SEG) prefetch_l2(wb.segv + idx_b);
             const int xa = (int)v.x - x0, cnt = (int)v.cnt;
             unsigned long long pend = cnt > 0 ? ((cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull)) << xa) : 0ull;
             const unsigned long long updated_before = my_updated;
@@ -209,6 +214,12 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             const uint32_t nfrag = __reduce_add_sync(0xffffffffu, (uint32_t)cnt);
             const bool disjoint = nfrag == (uint32_t)(__popc(orl) + __popc(orh));
             bool staged = false;
+            if (wb.tile_clock && lane == 0) {  // tuning aid: chunks / fragments by resolution path
+                unsigned long long *dbg = wb.tile_clock + 2 * (size_t)wb.ntiles;
+                const int path = disjoint ? 0 : ((DEFERRED && nfrag <= (uint32_t)ZCAP) ? 1 : 2);
+                atomicAdd(&dbg[path], 1ull);
+                atomicAdd(&dbg[4 + path], (unsigned long long)nfrag);
+            }
             if constexpr (DEFERRED) {
                 if (!disjoint && nfrag <= (uint32_t)ZCAP) {
                     // (1) every segment lane stages the depths of its fragments and registers itself in the
@@ -230,7 +241,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                     }
                     __syncwarp();
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
+                    for (int h = 0; h < STRIP_H; h++) {
                         const int pix = lane + 32 * h;
                         uint32_t m = sm.cover[pix];
                         if (m) {
@@ -286,27 +297,25 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                         pend &= ~ready;
                     }
                     __syncwarp();
+                    if (wb.tile_clock && lane == 0 && !disjoint) atomicAdd(&wb.tile_clock[2 * (size_t)wb.ntiles + 8], 1ull);
                     if (disjoint || !__any_sync(0xffffffffu, pend != 0)) break;
                 }
                 if (EACH && my_updated != updated_before)
                     atomicAdd(&p.prim_info[2 * (size_t)src_primitive(wb, p, v.src, v.flags) + 1], my_updated - updated_before);
             }
+            idx = idx_b; idx_b = idx_c;
         }
-        // the next strip's bin range (its id has arrived by now)
-        uint32_t nbeg = 0, nend = 0;
-        if (nq < nbusy) { nbeg = wb.tile_start[nstrip]; nend = wb.tile_end[nstrip]; }
 
         // ---- write the strip back ---------------------------------------------------------------
         const bool touched = __any_sync(0xffffffffu, my_updated != updated_at_start);
         if constexpr (DEFERRED) {
             if (st.write_color) {  // k_shade reads the winners of every busy strip
-                wb.vis_seg[(size_t)strip * TILE_W + lane] = sm.winseg[lane];
-                wb.vis_seg[(size_t)strip * TILE_W + lane + 32] = sm.winseg[lane + 32];
+                for (int h = 0; h < STRIP_H; h++) wb.vis_seg[(size_t)strip * TILE_W + lane + 32 * h] = sm.winseg[lane + 32 * h];
             }
         } else {
             if (touched && st.write_color) {
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
+                for (int h = 0; h < STRIP_H; h++) {
                     const int i = lane + 32 * h;
                     if (i < tw) gcolor[grow + i] = sm.color[i];
                 }
@@ -314,7 +323,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         }
         if (touched && st.write_depth) {
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
+            for (int h = 0; h < STRIP_H; h++) {
                 const int i = lane + 32 * h;
                 if (i < tw) gdepth[grow + i] = sm.depth[i];
             }
@@ -325,7 +334,9 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             wb.tile_clock[2 * strip] = (unsigned long long)(clock64() - t_begin);
             wb.tile_clock[2 * strip + 1] = ((unsigned long long)smid << 32) | nseg;
         }
-        q = nq; q_end = nq_end; strip = nstrip; bin_beg = nbeg; bin_end = nend;
+        q += nwarps;
+        e0 = e1; e1 = e2; e2 = e3;
+        ik0 = ik1; ik1 = ik2;
     }
 
     // UpdatedPixels: one atomic per warp per kernel
@@ -345,7 +356,7 @@ k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     constexpr uint32_t SPB = SHT / TILE_W;  // strips per CTA pass
     const int pix = threadIdx.x % TILE_W;
     for (uint32_t q = blockIdx.x * SPB + threadIdx.x / TILE_W; q < nbusy; q += gridDim.x * SPB) {
-        const uint32_t strip = strip_at(wb, nheavy, q);
+        const uint32_t strip = busy_at(wb, nheavy, q).x;
         const uint32_t sidx = wb.vis_seg[(size_t)strip * TILE_W + pix];
         if (sidx == NO_WINNER) continue;
         const int x = (int)(strip % (uint32_t)p.tiles_x) * TILE_W + pix;
@@ -422,7 +433,7 @@ int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, ui
     const uint32_t per_sm = p.deferred ? 4u : 3u;
     const uint32_t want = (wb.ntiles + SWARPS - 1u) / SWARPS;  // never more warps than strips
     const uint32_t grid = want < wb.nsm * per_sm ? (want ? want : 1u) : wb.nsm * per_sm;
-    strip_kernel<<<grid, STHREADS, 0, st>>>(p, wb, wb.seg_val[sorted_buf], color, depth);
+    strip_kernel<<<grid, STHREADS, 0, st>>>(p, wb, wb.seg_val[sorted_buf], wb.seg_key[sorted_buf], color, depth);
     int launches = 1;
     if (p.deferred && p.state.write_color) {
         k_shade<<<wb.nsm * 8u, SHT, 0, st>>>(p, wb, color);

@@ -259,13 +259,15 @@ static int radix_pass(uint32_t *const key[2], uint32_t *const val[2], int cur, c
     return 2;
 }
 
-// Stable LSD radix sort of (key, val) on `bits` key bits: as few passes as 10-bit digits allow, 8-bit digits
-// when they need no more passes (smaller histograms).
+// Stable LSD radix sort of (key, val) on `bits` key bits.  8-bit digits: measured on the 8K benchmark frame
+// (3.3 M pairs, 19 key bits) three 8-bit passes take 3 x 43 us, two 10-bit passes 2 x 76 us -- clearing and
+// scanning 32 x 1024 counters per tile costs more than the third pass.  10-bit digits are used only when
+// they save a pass AND the sort is small enough to be latency-bound (a launch saved > work added).
 int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsigned int *n_dev, uint32_t n_max,
                       int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st) {
     int launches = 0, cur = 0;
     const int passes = (bits + 9) / 10;
-    const bool narrow = passes * 8 >= bits;
+    const bool narrow = passes * 8 >= bits || n_max > (1u << 18);
     for (int shift = 0; shift < bits; shift += narrow ? 8 : 10) {
         launches += narrow ? radix_pass<8>(key, val, cur, n_dev, n_max, shift, tmp, st)
                            : radix_pass<10>(key, val, cur, n_dev, n_max, shift, tmp, st);

@@ -154,52 +154,64 @@ k_span_place(const __grid_constant__ DrawParams p, const __grid_constant__ WorkB
     }
 }
 
-// Bin ranges of the sorted key array, and the list of busy strips: heavy strips (>= HEAVY_SEGS segments)
-// are appended from the front, the others from the back, so that the strip kernel starts the long ones
-// first.  Only entries of strips that occur are written -- and only those are read (through the busy
-// list), so the arrays are never cleared.
+// The list of busy strips: (strip, first position of its bin in the sorted array); a bin ends where the sorted
+// key changes.  Heavy strips (>= HEAVY_SEGS segments) are appended from the front, the others from the back,
+// so that the strip kernel starts the long ones first.
 constexpr int TR_THREADS = 1024;
+// Each CTA owns a contiguous part of the sorted array and goes over it twice: first it only counts the strips
+// that start there (heavy / light), reserves its share of the busy list with ONE global atomic per list, then
+// it fills in the entries (ranks inside the CTA from shared-memory counters).
 __global__ void __launch_bounds__(TR_THREADS)
 k_tile_ranges(const uint32_t *__restrict__ keys, const unsigned int *__restrict__ n_dev, uint32_t n_max,
-              uint32_t *__restrict__ tile_start, uint32_t *__restrict__ tile_end,
-              uint32_t *__restrict__ busy_list, uint32_t ntiles, TileCtl *ctl) {
-    __shared__ uint32_t s_cnt[2], s_base[2];
+              uint2 *__restrict__ busy_list, uint32_t ntiles, TileCtl *ctl) {
+    __shared__ uint32_t s_cnt[2], s_base[2], s_fill[2];
     const uint32_t n = min(*n_dev, n_max);
     const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t i0 = blockIdx.x * TR_THREADS; i0 < n; i0 += gridDim.x * TR_THREADS) {
-        if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
-        __syncthreads();
-        const uint32_t i = i0 + threadIdx.x;
-        bool starts = false, heavy = false;
+    uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    per = (per + TR_THREADS - 1) / TR_THREADS * TR_THREADS;
+    const uint64_t b64 = (uint64_t)blockIdx.x * per;
+    const uint32_t beg = b64 < n ? (uint32_t)b64 : n, end = b64 + per < n ? (uint32_t)(b64 + per) : n;
+    if (threadIdx.x < 2) { s_cnt[threadIdx.x] = 0; s_fill[threadIdx.x] = 0; }
+    __syncthreads();
+    auto classify = [&](uint32_t i, uint32_t &k, bool &heavy) {  // does a strip start at i?
+        if (i >= end) return false;
+        k = keys[i];
+        if (!(i == 0 || keys[i - 1] != k)) return false;
+        heavy = i + HEAVY_SEGS - 1u < n && keys[i + HEAVY_SEGS - 1u] == k;
+        return true;
+    };
+    uint32_t nh = 0, nl = 0;
+    for (uint32_t i = beg + threadIdx.x; i < end; i += TR_THREADS) {
         uint32_t k = 0;
-        if (i < n) {
-            k = keys[i];
-            starts = i == 0 || keys[i - 1] != k;
-            if (starts) {
-                tile_start[k] = i;
-                heavy = i + HEAVY_SEGS - 1u < n && keys[i + HEAVY_SEGS - 1u] == k;
-            }
-            if (i == n - 1 || keys[i + 1] != k) tile_end[k] = i + 1;
-        }
-        // list the strips that start in this window: warp ballot -> CTA counters -> ONE global atomic per list
+        bool heavy = false;
+        if (classify(i, k, heavy)) { if (heavy) nh++; else nl++; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { nh += __shfl_down_sync(0xffffffffu, nh, o); nl += __shfl_down_sync(0xffffffffu, nl, o); }
+    if (lane == 0) { if (nh) atomicAdd(&s_cnt[0], nh); if (nl) atomicAdd(&s_cnt[1], nl); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_base[0] = s_cnt[0] ? atomicAdd(&ctl->nheavy, s_cnt[0]) : 0u;
+        s_base[1] = s_cnt[1] ? atomicAdd(&ctl->nlight, s_cnt[1]) : 0u;
+    }
+    __syncthreads();
+    for (uint32_t i0 = beg; i0 < end; i0 += TR_THREADS) {
+        const uint32_t i = i0 + threadIdx.x;
+        uint32_t k = 0;
+        bool heavy = false;
+        const bool starts = classify(i, k, heavy);
         const uint32_t mh = __ballot_sync(0xffffffffu, starts && heavy), ml = __ballot_sync(0xffffffffu, starts && !heavy);
         uint32_t wh = 0, wl = 0;
         if (lane == 0) {
-            if (mh) wh = atomicAdd(&s_cnt[0], (uint32_t)__popc(mh));
-            if (ml) wl = atomicAdd(&s_cnt[1], (uint32_t)__popc(ml));
+            if (mh) wh = atomicAdd(&s_fill[0], (uint32_t)__popc(mh));
+            if (ml) wl = atomicAdd(&s_fill[1], (uint32_t)__popc(ml));
         }
         wh = __shfl_sync(0xffffffffu, wh, 0);
         wl = __shfl_sync(0xffffffffu, wl, 0);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            s_base[0] = s_cnt[0] ? atomicAdd(&ctl->nheavy, s_cnt[0]) : 0u;
-            s_base[1] = s_cnt[1] ? atomicAdd(&ctl->nlight, s_cnt[1]) : 0u;
-        }
-        __syncthreads();
         if (starts) {
             const uint32_t lt = (1u << lane) - 1u;
-            if (heavy) busy_list[s_base[0] + wh + __popc(mh & lt)] = k;
-            else busy_list[ntiles - 1u - (s_base[1] + wl + __popc(ml & lt))] = k;
+            if (heavy) busy_list[s_base[0] + wh + __popc(mh & lt)] = make_uint2(k, i);
+            else busy_list[ntiles - 1u - (s_base[1] + wl + __popc(ml & lt))] = make_uint2(k, i);
         }
     }
 }
@@ -228,8 +240,7 @@ int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cuda
     int bits = 1;
     while ((1u << bits) < wb.ntiles) bits++;
     launches += launch_sort_pairs(wb.seg_key, wb.seg_val, &c->n_segs, wb.cap_segs, bits, wb.scan_tmp, sorted_buf, st);
-    cudaMemsetAsync(wb.tile_ctl, 0, sizeof(TileCtl), st);
-    k_tile_ranges<<<148, TR_THREADS, 0, st>>>(wb.seg_key[*sorted_buf], &c->n_segs, wb.cap_segs, wb.tile_start, wb.tile_end,
+    k_tile_ranges<<<148, TR_THREADS, 0, st>>>(wb.seg_key[*sorted_buf], &c->n_segs, wb.cap_segs,
                                            wb.busy_list, wb.ntiles, wb.tile_ctl);
     launches++;
     return launches;

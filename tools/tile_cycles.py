@@ -32,8 +32,11 @@ for _ in range(3):
     info = ctx.DrawMesh(dm)
 st = ctx.DrawStats()
 nt = st.tiles_x * st.tiles_y
-buf = np.zeros((nt, 2), dtype=np.uint64)
-_check(capi().fgl_debug_tile_cycles(ctx._h, buf.ctypes.data, nt), ctx._h)
+full = np.zeros((nt + 8, 2), dtype=np.uint64)
+_check(capi().fgl_debug_tile_cycles(ctx._h, full.ctypes.data, nt + 8), ctx._h)
+buf, dbg = full[:nt], full[nt:].ravel()
+print("chunks by path (3 draws): disjoint %d staged %d generic %d; fragments %d / %d / %d; generic rounds %d" % (
+    dbg[0], dbg[1], dbg[2], dbg[4], dbg[5], dbg[6], dbg[8]))
 cyc = buf[:, 0].astype(np.int64)
 smid = (buf[:, 1] >> np.uint64(32)).astype(np.int64)
 segs = (buf[:, 1] & np.uint64(0xffffffff)).astype(np.int64)
