@@ -324,10 +324,12 @@ int enqueue_draw(fgl_ctx *c, const DrawParams &p) {
     if (p.prim_info) cudaMemsetAsync(p.prim_info, 0, sizeof(unsigned long long) * 2 * p.count, c->stream);
     int sorted = 0;
     if (use_fused_front(c, p)) {
-        // large draws: geometry and spans in one kernel (the split stage timers then read: geometry = k_front +
-        // k_seg_index, spans = 0)
+        // large draws: geometry and spans in one kernel (the stage timers then read: geometry = k_front alone,
+        // spans = k_seg_index)
         launches += launch_front(p, c->wb, c->stream);
-        if (ps) { cudaEventRecord(ps->e[1], c->stream); cudaEventRecord(ps->e[2], c->stream); }
+        if (ps) cudaEventRecord(ps->e[1], c->stream);
+        launches += launch_seg_index(p, c->wb, c->stream);
+        if (ps) cudaEventRecord(ps->e[2], c->stream);
     } else {
         launches += launch_geometry(p, c->wb, c->stream);
         if (ps) cudaEventRecord(ps->e[1], c->stream);

@@ -941,8 +941,12 @@ int launch_front(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {
     const uint32_t blocks = (p.count + FT - 1) / FT;
     cudaMemsetAsync(wb.counters, 0, sizeof(DrawCounters), st);
     k_front<<<blocks, FT, 0, st>>>(p, wb);
+    return 1;
+}
+int launch_seg_index(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {
+    const uint32_t blocks = (p.count + FT - 1) / FT;
     k_seg_index<<<148 * 8, 256, 0, st>>>(wb, blocks);
-    return 2;
+    return 1;
 }
 
 int launch_geometry(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {

@@ -201,9 +201,10 @@ int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsi
                       int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st);
 
 int launch_geometry(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
-// fused geometry + span stage of large draws (k_front, k_seg_index): leaves (seg_key[0], seg_val[0]) in
+// fused geometry + span stage of large draws: k_front, then k_seg_index leaves (seg_key[0], seg_val[0]) in
 // primitive order, like launch_geometry + launch_spans
 int launch_front(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
+int launch_seg_index(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
 int launch_spans(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
 int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
 int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,

@@ -160,7 +160,10 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     // (segment index, valid) of sorted position pos for a bin of `strip`
     auto load_pair = [&](uint32_t strip, uint32_t pos) {
         uint32_t idx = NO_SEG;
-        if (strip != 0xffffffffu && pos < nsegs && seg_keys[pos] == strip) idx = seg_order[pos];
+        if (strip != 0xffffffffu && pos < nsegs) {  // two independent loads, then the select
+            const uint32_t k = seg_keys[pos], o = seg_order[pos];
+            if (k == strip) idx = o;
+        }
         return idx;
     };
     uint2 e0 = load_entry(q), e1 = load_entry(q + nwarps), e2 = load_entry(q + 2 * nwarps);

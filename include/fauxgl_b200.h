@@ -209,10 +209,12 @@ int fgl_get_draw_stats(const fgl_ctx *ctx, fgl_draw_stats *out);
  * the stream and returns the milliseconds accumulated since the last call and
  * the number of draws they cover. */
 typedef struct {
-    float geometry_ms;   /* vertex transform, clip, cull, setup, ordered compaction    */
-    float spans_ms;      /* exact scanline walk -> covered span segments              */
-    float sort_ms;       /* stable sort of segments by tile, bin ranges               */
-    float raster_ms;     /* k_tile alone: ordered depth resolve, shading, write-back  */
+    float geometry_ms;   /* large draws: k_front alone (vertex transform, clip, cull, setup AND the exact scanline
+                            walk, fused); small draws: the geometry kernel                              */
+    float spans_ms;      /* large draws: k_seg_index (segments listed in primitive order); small draws: the
+                            grid-wide span kernels                                                      */
+    float sort_ms;       /* stable sort of segments by strip, busy-strip list                           */
+    float raster_ms;     /* k_strip (ordered depth resolve) + k_shade (deferred shading of the winners) */
     uint32_t draws;
 } fgl_stage_times;
 int fgl_set_profiling(fgl_ctx *ctx, int enabled);

@@ -63,6 +63,43 @@ def test_resolve_matches_oracle(factor, w, h, oracle_lib, Context):
     ctx.Close()
 
 
+@pytest.mark.parametrize("w,h", [(256, 128), (67, 33)])
+def test_resolve_opaque_4x_fast_path_matches_oracle(w, h, oracle_lib, Context):
+    """Opaque pixels at factor 4 take the DP4A fast path away from the left/right border (the generic loop
+    elsewhere); a few translucent pixels inside force the generic loop in the middle of fast rows."""
+    rng = np.random.RandomState(7)
+    img = rng.randint(0, 256, (h * 4, w * 4, 4)).astype(np.uint8)
+    img[..., 3] = 255
+    img[5::37, 3::53, 3] = rng.randint(0, 255, img[5::37, 3::53, 3].shape)
+    ctx = Context(w * 4, h * 4)
+    ctx.UploadColorBuffer(img)
+    got = ctx.Resolve(4)
+    want = oracle_lib.resolve(img, w, h)
+    assert (got == want).all()
+    ctx.Close()
+
+
+@pytest.mark.parametrize("front", ["fused", "split"])
+def test_work_buffers_regrow_under_both_front_ends(front, oracle_lib, Context, monkeypatch):
+    """Large triangles after a context sized for nothing: the segment capacity overflows, the synchronous draw
+    regrows and re-issues (the fused front end reserves rows x strips per record, the split one counts)."""
+    from fauxgl_b200 import NewSolidColorShader, NewTriangleMesh, Orthographic, Color
+    monkeypatch.setenv("FGL_FRONT", front)
+    ctx = Context(2048, 2048)
+    octx = oracle_lib.OracleContext(2048, 2048)
+    tri = np.array([[[-1, -1, 0], [1, -1, 0], [0, 1, 0]]] * 60, dtype=np.float64)
+    tri[:, :, 2] = np.linspace(-0.5, 0.5, 60)[:, None]
+    mesh = NewTriangleMesh(tri)
+    for c in (ctx, octx):
+        c.Shader = NewSolidColorShader(Orthographic(-1, 1, -1, 1, -1, 1), Color(0.2, 0.4, 0.6, 1))
+        c.Cull = 1
+    gi, oi = ctx.DrawTriangles(mesh), octx.DrawTriangles(mesh)
+    assert tuple(gi) == oi and ctx.DrawStats().retries >= 1
+    assert (ctx.DepthBuffer.view(np.uint64) == octx.DepthBuffer.view(np.uint64)).all()
+    assert (ctx.Image() == octx.ColorBuffer).all()
+    ctx.Close()
+
+
 def test_mesh_transform_on_device_matches_host(Context):
     """fgl_mesh_transform == Mesh.Transform (mesh.go:167-175), bit for bit."""
     from fauxgl_b200 import Rotate, Radians, V
