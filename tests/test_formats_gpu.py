@@ -134,9 +134,11 @@ def test_depth_image_matches_oracle(oracle_lib, Context):
     ctx.Close()
 
 
-def test_per_line_rasterize_info_matches_sequential_drawline(oracle_lib, Context):
+@pytest.mark.parametrize("front", ["split", "fused"])
+def test_per_line_rasterize_info_matches_sequential_drawline(front, oracle_lib, Context, monkeypatch):
     """fgl_draw_lines_each == a loop of Context.DrawLine (examples/silhouette.go:163-166): occluder first,
-    then biased lines whose UpdatedPixels/TotalPixels ratio decides visibility."""
+    then biased lines whose UpdatedPixels/TotalPixels ratio decides visibility.  Under both front ends."""
+    monkeypatch.setenv("FGL_FRONT", front)
     from fauxgl_b200 import HexColor, LookAt, NewSolidColorShader, Scale, V, White, Black, synth  # noqa: F401
     from fauxgl_b200.mesh import Mesh
     cube = synth.NewCube()
@@ -170,10 +172,12 @@ def test_per_line_rasterize_info_matches_sequential_drawline(oracle_lib, Context
     ctx.Close()
 
 
+@pytest.mark.parametrize("front", ["split", "fused"])
 @pytest.mark.parametrize("wireframe", [False, True])
-def test_per_triangle_rasterize_info_with_clipping(wireframe, oracle_lib, Context):
+def test_per_triangle_rasterize_info_with_clipping(wireframe, front, oracle_lib, Context, monkeypatch):
     """fgl_draw_triangles_each == a loop of Context.DrawTriangle (context.go:370-389), including triangles
     the clipper splits (their fan triangles count towards the source triangle) and wireframe mode."""
+    monkeypatch.setenv("FGL_FRONT", front)
     sc = scenes.bowser_close()
     ctx, o = Context(sc.width, sc.height), oracle_lib.OracleContext(sc.width, sc.height)
     mesh = {}
