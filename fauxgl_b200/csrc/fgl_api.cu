@@ -65,6 +65,7 @@ struct ProfSlot { cudaEvent_t e[PROF_EVENTS]; };
 struct fgl_ctx {
     int device;
     int w, h;
+    int tile_w;                        // strip width of this context: 32 or 64 (fgl_internal.h)
     int front_mode;                    // 0 auto, 1 fused front end always, 2 split stages always (FGL_FRONT)
     cudaStream_t stream;
     cudaStream_t copy_stream;          // H2D of streaming mesh uploads, overlapping the draw stream
@@ -259,7 +260,8 @@ int build_params(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const
         p->tex_w = sh->texture->w; p->tex_h = sh->texture->h; p->tex_format = sh->texture->format;
     }
     p->width = c->w; p->height = c->h;
-    p->tiles_x = (c->w + TILE_W - 1) / TILE_W;
+    p->tile_w = c->tile_w; p->tile_shift = c->tile_w == 64 ? 6 : 5;
+    p->tiles_x = (c->w + c->tile_w - 1) / c->tile_w;
     p->tiles_y = c->h;
     // Screen(w, h), matrix.go:119-128
     const double w2 = (double)c->w / 2, h2 = (double)c->h / 2;
@@ -385,7 +387,7 @@ int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const 
         p.prim_info = c->prim_info;
     }
     if (p.deferred && !c->wb.vis_seg)  // winners of the deferred-shading path, strip-major
-        CK(c, dev_alloc(&c->wb.vis_seg, (size_t)c->wb.ntiles * TILE_W));
+        CK(c, dev_alloc(&c->wb.vis_seg, (size_t)c->wb.ntiles * c->tile_w));
     rc = initial_capacity(c, p);
     if (rc) return rc;
     mesh_acquire(c, mesh);
@@ -497,7 +499,9 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     if (err == cudaSuccess) err = dev_alloc(&c->scratch, 8);
     if (err == cudaSuccess) err = cudaMallocHost(reinterpret_cast<void **>(&c->host_counters), sizeof(DrawCounters));
     {   // strips of 64 x 1 pixels
-        const int tx = (width + TILE_W - 1) / TILE_W;
+        const char *tw = getenv("FGL_STRIP_W");  // tuning aid: force 32 or 64
+        c->tile_w = tw && atoi(tw) == 32 ? 32 : (tw && atoi(tw) == 64 ? 64 : ((uint64_t)width * height <= (4ull << 20) ? 32 : 64));
+        const int tx = (width + c->tile_w - 1) / c->tile_w;
         c->wb.ntiles = (uint32_t)tx * (uint32_t)height;
         cudaDeviceProp prop;
         c->wb.nsm = cudaGetDeviceProperties(&prop, device) == cudaSuccess ? (uint32_t)prop.multiProcessorCount : 148u;
@@ -516,9 +520,9 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
         fgl_context_destroy(c);
         return rc;
     }
-    c->stats.tiles_x = (uint32_t)((width + TILE_W - 1) / TILE_W);
+    c->stats.tiles_x = (uint32_t)((width + c->tile_w - 1) / c->tile_w);
     c->stats.tiles_y = (uint32_t)height;
-    c->stats.tile_w = TILE_W; c->stats.tile_h = 1;
+    c->stats.tile_w = (uint32_t)c->tile_w; c->stats.tile_h = 1;
     // NewContext: image.NewNRGBA is zeroed; ClearDepthBuffer() -> math.MaxFloat64 (context.go:64,79)
     launch_clear_color(c->color, npix, 0u, c->stream);
     launch_clear_depth(c->depth, npix, 1.7976931348623157e308, c->stream);

@@ -117,7 +117,7 @@ FGL_DI BBox compute_bbox(const DrawParams &p, V3 s0, V3 s1, V3 s2) {
     constexpr int32_t FAR = 1 << 22;
     if (b.x0 < -FAR || b.y0 < -FAR || b.x1 > FAR || b.y1 > FAR) b.visible = false;
     b.rows = b.visible ? (uint32_t)(cy1 - cy0 + 1) : 0u;
-    b.cols = b.visible ? (uint32_t)(cx1 / TILE_W - cx0 / TILE_W + 1) : 0u;
+    b.cols = b.visible ? (uint32_t)((cx1 >> p.tile_shift) - (cx0 >> p.tile_shift) + 1) : 0u;
     return b;
 }
 

@@ -14,7 +14,10 @@ namespace fgl {
 // left to right with forward differencing (context.go:207-213); a covered run is cut into one
 // segment per strip it crosses, so wide strips mean few segments, and a segment never spans
 // rows, so one-row strips add none.  One warp resolves a strip (fgl_raster.cu): a 64-bit mask
-// per lane describes the pixels a segment still has to write.
+// per lane describes the pixels a segment still has to write.  TILE_W is the widest strip; a context
+// uses 32-pixel strips up to 4 Mpixel (the heaviest strips, which bound the strip kernel's duration,
+// halve; measured 84 -> 77 us at 1920x1080) and 64-pixel strips above (fewer segments and strips;
+// measured 408 vs 442 us at 7680x4320).
 #ifndef FGL_TILE_W
 #define FGL_TILE_W 64
 #endif
@@ -103,7 +106,8 @@ struct DrawParams {
     const uint8_t *tex;
     int32_t tex_w, tex_h, tex_format, object_is_discard;
     // framebuffer
-    int32_t width, height, tiles_x, tiles_y;  // strips per row (ceil(width/64)), strip rows (= height)
+    int32_t width, height, tiles_x, tiles_y;  // strips per row (ceil(width / tile_w)), strip rows (= height)
+    int32_t tile_w, tile_shift;               // strip width of this context: 32 or 64 pixels (<= TILE_W), and its log2
     double screen[16];  // Screen(w,h), matrix.go:119-128
     // input
     MeshPlanes mesh;

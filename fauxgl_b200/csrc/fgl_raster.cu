@@ -52,8 +52,8 @@ constexpr int SWARPS = 8;               // warps (= strips in flight) per CTA
 constexpr int STHREADS = SWARPS * 32;
 constexpr uint32_t NO_WINNER = 0xffffffffu;
 constexpr uint32_t NO_SEG = 0xffffffffu;
-static_assert(TILE_W == 64 || TILE_W == 32, "a strip is one 64-bit pending mask wide at most");
-constexpr int STRIP_H = TILE_W / 32;  // pixels per lane
+static_assert(TILE_W == 64, "a strip is one 64-bit pending mask wide at most");
+constexpr int STRIP_H = TILE_W / 32;  // pixels per lane at most (p.tile_w / 32 are used)
 
 constexpr int ZCAP = 256;  // fragments of a chunk the pixel-parallel resolution can stage
 template <bool DEFERRED> struct StripMem;
@@ -142,6 +142,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     StripMem<DEFERRED> &sm = s_all[threadIdx.x >> 5];
     const fgl_state st = p.state;
     unsigned long long my_updated = 0;
+    const int tile_w = p.tile_w, strip_h = tile_w >> 5;  // strip width of this context (32 or 64), pixels per lane
     if constexpr (DEFERRED) {  // scratch of the pixel-parallel resolution: every use leaves it clean
         for (int h = 0; h < STRIP_H; h++) sm.cover[lane + 32 * h] = 0;
         sm.upd[lane] = 0;
@@ -174,19 +175,19 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         const uint2 e3 = load_entry(q + 3 * nwarps);
         const uint32_t ik2 = load_pair(e2.x, e2.y + lane);
         if (ik1 != NO_SEG) prefetch_l2(wb.segv + ik1);
-        if (e1.x != 0xffffffffu && lane < TILE_W / 16)
-            prefetch_l2(gdepth + (size_t)(e1.x / (uint32_t)p.tiles_x) * p.width + (e1.x % (uint32_t)p.tiles_x) * TILE_W + lane * 16);
+        if (e1.x != 0xffffffffu && lane < tile_w / 16)
+            prefetch_l2(gdepth + (size_t)(e1.x / (uint32_t)p.tiles_x) * p.width + (e1.x % (uint32_t)p.tiles_x) * tile_w + lane * 16);
         const long long t_begin = wb.tile_clock ? clock64() : 0;
         uint32_t nseg = 0;
-        const int x0 = (int)(strip % (uint32_t)p.tiles_x) * TILE_W;
+        const int x0 = (int)(strip % (uint32_t)p.tiles_x) * tile_w;
         const int y = (int)(strip / (uint32_t)p.tiles_x);
-        const int tw = min(TILE_W, p.width - x0);  // valid columns of this strip
+        const int tw = min(tile_w, p.width - x0);  // valid columns of this strip
         const size_t grow = (size_t)y * p.width + x0;
 
         // ---- load the strip --------------------------------------------------------------
         __syncwarp();
 #pragma unroll
-        for (int h = 0; h < STRIP_H; h++) {
+        for (int h = 0; h < strip_h; h++) {
             const int i = lane + 32 * h;
             if constexpr (DEFERRED) sm.winseg[i] = NO_WINNER;
             if (i < tw) {
@@ -244,7 +245,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                     }
                     __syncwarp();
 #pragma unroll
-                    for (int h = 0; h < STRIP_H; h++) {
+                    for (int h = 0; h < strip_h; h++) {
                         const int pix = lane + 32 * h;
                         uint32_t m = sm.cover[pix];
                         if (m) {
@@ -313,12 +314,12 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         const bool touched = __any_sync(0xffffffffu, my_updated != updated_at_start);
         if constexpr (DEFERRED) {
             if (st.write_color) {  // k_shade reads the winners of every busy strip
-                for (int h = 0; h < STRIP_H; h++) wb.vis_seg[(size_t)strip * TILE_W + lane + 32 * h] = sm.winseg[lane + 32 * h];
+                for (int h = 0; h < strip_h; h++) wb.vis_seg[(size_t)strip * tile_w + lane + 32 * h] = sm.winseg[lane + 32 * h];
             }
         } else {
             if (touched && st.write_color) {
 #pragma unroll
-                for (int h = 0; h < STRIP_H; h++) {
+                for (int h = 0; h < strip_h; h++) {
                     const int i = lane + 32 * h;
                     if (i < tw) gcolor[grow + i] = sm.color[i];
                 }
@@ -326,7 +327,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         }
         if (touched && st.write_depth) {
 #pragma unroll
-            for (int h = 0; h < STRIP_H; h++) {
+            for (int h = 0; h < strip_h; h++) {
                 const int i = lane + 32 * h;
                 if (i < tw) gdepth[grow + i] = sm.depth[i];
             }
@@ -356,13 +357,13 @@ __global__ void __launch_bounds__(SHT, 4)
 k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb, uint32_t *__restrict__ gcolor) {
     if (wb.counters->overflow) return;
     const uint32_t nheavy = wb.tile_ctl->nheavy, nbusy = nheavy + wb.tile_ctl->nlight;
-    constexpr uint32_t SPB = SHT / TILE_W;  // strips per CTA pass
-    const int pix = threadIdx.x % TILE_W;
-    for (uint32_t q = blockIdx.x * SPB + threadIdx.x / TILE_W; q < nbusy; q += gridDim.x * SPB) {
+    const uint32_t tile_w = (uint32_t)p.tile_w, SPB = SHT / tile_w;  // strips per CTA pass
+    const int pix = (int)(threadIdx.x % tile_w);
+    for (uint32_t q = blockIdx.x * SPB + threadIdx.x / tile_w; q < nbusy; q += gridDim.x * SPB) {
         const uint32_t strip = busy_at(wb, nheavy, q).x;
-        const uint32_t sidx = wb.vis_seg[(size_t)strip * TILE_W + pix];
+        const uint32_t sidx = wb.vis_seg[(size_t)strip * tile_w + pix];
         if (sidx == NO_WINNER) continue;
-        const int x = (int)(strip % (uint32_t)p.tiles_x) * TILE_W + pix;
+        const int x = (int)((strip % (uint32_t)p.tiles_x) * tile_w) + pix;
         const int y = (int)(strip / (uint32_t)p.tiles_x);
         uint32_t *out = gcolor + (size_t)y * p.width + x;
         if (p.kind == FGL_SHADER_SOLID) {  // SolidColorShader.Fragment, shader.go:25-27: nothing to interpolate

@@ -88,7 +88,7 @@ __device__ __forceinline__ uint32_t walk_row_core(const DrawParams &p, const Edg
             if ((n12 && b0 < 0) || (n20 && b1 < 0) || (n01 && b2 < 0)) break;
         } else {
             was_inside = true;
-            const int c = (int)x / TILE_W;
+            const int c = (int)x >> p.tile_shift;
             if (cnt == 0 || c != col) {
                 if (cnt > 0) { emit(sw0, sw1, sw2, sx, cnt, key_row + (uint32_t)col); *covered += cnt; nseg++; }
                 col = c; sx = (int)x; sw0 = w0; sw1 = w1; sw2 = w2; cnt = 0;

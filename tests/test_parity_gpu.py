@@ -37,3 +37,14 @@ def test_scene_matches_oracle_under_both_front_ends(name, front, oracle_lib, gpu
     assert stats["depth_mismatch"] == 0, stats
     assert stats["color_mismatch"] == 0, stats
     assert stats["gpu_info"] == stats["oracle_info"], stats
+
+
+@pytest.mark.parametrize("strip_w", ["32", "64"])
+@pytest.mark.parametrize("name", ["hello", "bowser_close", "shapes_multipass", "lines", "edge_cases", "capsule_phong_texture"])
+def test_scene_matches_oracle_for_both_strip_widths(name, strip_w, oracle_lib, gpu_capi, monkeypatch):
+    """A context bins into 32-pixel strips up to 4 Mpixel and 64-pixel strips above; FGL_STRIP_W forces one."""
+    from fauxgl_b200.context import Context
+    monkeypatch.setenv("FGL_STRIP_W", strip_w)
+    stats = run_both(scenes.SCENES[name](), oracle_lib, Context)
+    assert stats["depth_mismatch"] == 0 and stats["color_mismatch"] == 0, stats
+    assert stats["gpu_info"] == stats["oracle_info"], stats
