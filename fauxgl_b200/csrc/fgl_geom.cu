@@ -634,6 +634,7 @@ k_rec_index(const __grid_constant__ WorkBuffers wb, uint32_t nblocks) {
 constexpr int FT = FGL_FRONT_FT;
 constexpr unsigned long long CELL_SHIFT = 24, NREC_MASK = (1ull << CELL_SHIFT) - 1ull;
 static_assert(FT * 64 < (1 << CELL_SHIFT), "records of one block fit the low bits of its aggregate");
+static_assert((FT & (FT - 1)) == 0, "the item -> record search halves a power of two");
 
 struct __align__(16) SRec {  // a raster record in shared memory: RowSetup + the back end's tail
     double s0x, s0y, s1x, s1y, s2x, s2y;
@@ -819,16 +820,15 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             uint32_t nseg = 0, ridx = 0;
             int y = 0;
             if (it < items) {
-                uint32_t lo = 0, hi = nw;  // s_rowoff[lo] <= it < s_rowoff[hi] (entries >= nw hold `items`)
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (s_rowoff[mid] <= it) lo = mid; else hi = mid;
-                }
+                uint32_t lo = 0;  // the last entry with s_rowoff[lo] <= it (entries >= nw hold `items`): branch-free
+#pragma unroll
+                for (uint32_t step = FT / 2; step > 0; step >>= 1)
+                    if (s_rowoff[lo + step] <= it) lo += step;
                 ridx = s_order[lo];
                 const SRec &r = s_rec[ridx];
                 y = max(r.y0, 0) + (int)(it - s_rowoff[lo]);
                 const unsigned long long before = covered;
-                nseg = walk_row_segments<false>(p, r, y, first, nullptr, nullptr, nullptr, 0, 0, &covered);
+                nseg = walk_row_count(p, r, y, first, &covered);
                 if (p.prim_info && covered != before)  // per-primitive TotalPixels (fgl_draw_*_each)
                     atomicAdd(&p.prim_info[2 * (size_t)src_primitive(wb, p, r.src, r.flags)], covered - before);
             }

@@ -101,6 +101,89 @@ __device__ __forceinline__ uint32_t walk_row_core(const DrawParams &p, const Edg
     return nseg;
 }
 
+// b0 < 0, b1 < 0, b2 < 0 (context.go:215) as a bit mask / as one predicate.  Written in PTX so that the three
+// IEEE compares stay three DSETP: the optimiser otherwise rewrites `a < 0 || b < 0` into a NaN-aware minimum
+// (DSETP.MIN + selects + moves, 30-40 instructions per pixel of the loops below).
+__device__ __forceinline__ uint32_t neg_mask3(double b0, double b1, double b2) {
+    uint32_t m;
+    asm("{\n\t.reg .pred p0, p1, p2;\n\t.reg .u32 t1, t2;\n\t"
+        "setp.lt.f64 p0, %1, 0d0000000000000000;\n\t"
+        "setp.lt.f64 p1, %2, 0d0000000000000000;\n\t"
+        "setp.lt.f64 p2, %3, 0d0000000000000000;\n\t"
+        "selp.u32 %0, 1, 0, p0;\n\t"
+        "selp.u32 t1, 2, 0, p1;\n\t"
+        "selp.u32 t2, 4, 0, p2;\n\t"
+        "or.b32 %0, %0, t1;\n\t"
+        "or.b32 %0, %0, t2;\n\t}"
+        : "=r"(m) : "d"(b0), "d"(b1), "d"(b2));
+    return m;
+}
+__device__ __forceinline__ bool any_neg3(double b0, double b1, double b2) {
+    uint32_t m;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.lt.f64 p, %1, 0d0000000000000000;\n\t"
+        "setp.lt.or.f64 p, %2, 0d0000000000000000, p;\n\t"
+        "setp.lt.or.f64 p, %3, 0d0000000000000000, p;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(m) : "d"(b0), "d"(b1), "d"(b2));
+    return m != 0;
+}
+
+// Count pass of the fused front end: the covered run of row y, found with two lean loops (skip the pixels left of
+// the run, then count the run) instead of the per-pixel strip bookkeeping of walk_row_core -- the same chain of adds
+// and the same tests, so the run, and the edge values at its first pixel, are those of walk_row_core bit for bit;
+// the strip cuts follow from the run's end points.  Returns the number of segments, the first one in `first`.
+template <class R>
+__device__ __forceinline__ uint32_t walk_row_count(const DrawParams &p, const R &r, int y, ParkedSeg &first,
+                                                   unsigned long long *covered) {
+    const double a01 = r.s1y - r.s0y, b01 = r.s0x - r.s1x;  // context.go:167-172
+    const double a12 = r.s2y - r.s1y, b12 = r.s1x - r.s2x;
+    const double a20 = r.s0y - r.s2y, b20 = r.s2x - r.s0x;
+    double w00 = r.w00, w01 = r.w01, w02 = r.w02;
+    for (int yy = r.y0; yy < y; yy++) { w00 += b12; w01 += b20; w02 += b01; }  // context.go:275-277
+    // skip-ahead, context.go:185-205
+    double d = 0;
+    const double d0 = -w00 * r.ra12, d1 = -w01 * r.ra20, d2 = -w02 * r.ra01;
+    if (w00 < 0 && d0 > d) d = d0;
+    if (w01 < 0 && d1 > d) d = d1;
+    if (w02 < 0 && d2 > d) d = d2;
+    const long long di = go_int(d);
+    d = (double)di;
+    if (d < 0) d = 0;
+    double w0 = w00 + a12 * d, w1 = w01 + a20 * d, w2 = w02 + a01 * d;
+    // x0 + int(d) of the clamped d (context.go:207); beyond 2^40 the row starts right of any bounding box
+    long long xl = (long long)r.x0 + (di < 0 ? 0ll : (di > (1ll << 40) ? (1ll << 40) : di));
+    const int xe = min(r.x1, p.width - 1);
+    if (xl > (long long)xe) return 0;
+    for (; xl < 0; xl++) { w0 += a12; w1 += a20; w2 += a01; }  // left of the framebuffer: dropped (x-guard rule)
+    if (xl > (long long)xe) return 0;
+    int x = (int)xl;
+    const double ra = r.ra;
+    // Exact early exit, see walk_row_core: an edge whose per-pixel increment is <= 0 never recovers (ra > 0).
+    const bool pos = ra > 0;
+    const bool n12 = pos && a12 <= 0, n20 = pos && a20 <= 0, n01 = pos && a01 <= 0;
+    const uint32_t dead = (n12 ? 1u : 0u) | (n20 ? 2u : 0u) | (n01 ? 4u : 0u);
+    for (;;) {  // pixels left of the run (context.go:208-219 with wasInside == false)
+        const uint32_t out = neg_mask3(w0 * ra, w1 * ra, w2 * ra);
+        if (out == 0) break;
+        if (out & dead) return 0;
+        w0 += a12; w1 += a20; w2 += a01;  // context.go:211-213
+        if (++x > xe) return 0;
+    }
+    first.w0 = w0; first.w1 = w1; first.w2 = w2; first.x = x;
+    const int xs = x;
+    do {  // the run: up to the first outside pixel (context.go:216-218) or the end of the row
+        w0 += a12; w1 += a20; w2 += a01;
+        if (++x > xe) break;
+    } while (!any_neg3(w0 * ra, w1 * ra, w2 * ra));
+    const uint32_t n = (uint32_t)(x - xs);
+    *covered += n;
+    const int c0 = xs >> p.tile_shift, c1 = (x - 1) >> p.tile_shift;
+    first.cnt = min(n, (uint32_t)(((c0 + 1) << p.tile_shift) - xs));
+    first.key = (uint32_t)y * (uint32_t)p.tiles_x + (uint32_t)c0;
+    return (uint32_t)(c1 - c0 + 1);
+}
+
 // Walk row y of the triangle described by r (any struct with the fields s0x..s2y, w00..w02, ra, ra12, ra20,
 // ra01, z0..z2, x0, x1, y0): the per-row adds are replayed from y0 (context.go:275-277).
 //   WRITE == false: the first segment is returned in `first`, nothing is stored.
