@@ -14,6 +14,8 @@
 
 using namespace fgl;
 
+namespace fgl { bool g_pdl = true; }
+
 namespace {
 
 thread_local std::string t_last_error;
@@ -69,6 +71,11 @@ struct fgl_ctx {
     int front_mode;                    // 0 auto, 1 fused front end always, 2 split stages always (FGL_FRONT)
     cudaStream_t stream;
     cudaStream_t copy_stream;          // H2D of streaming mesh uploads, overlapping the draw stream
+    // Clears run on a stream of their own: the front end of the next draw touches no framebuffer, so the clear
+    // of a frame overlaps its k_front instead of preceding it (fb_clear_begin / fb_clear_end / fb_join below).
+    cudaStream_t fb_stream;
+    cudaEvent_t ev_fb_free, ev_cleared;
+    bool clear_overlap, clear_pending;
     std::mutex mu;
     std::string err;
     uint32_t *color;
@@ -103,6 +110,28 @@ int fail(fgl_ctx *ctx, int code, const char *fmt, ...) {
     t_last_error = buf;
     if (ctx) ctx->err = buf;
     return code;
+}
+
+// A clear waits for everything queued on the draw stream so far (it may read or write the framebuffer) ...
+cudaStream_t fb_clear_begin(fgl_ctx *c) {
+    if (!c->clear_overlap) return c->stream;
+    if (!c->clear_pending) {  // (still pending: nothing that touches the framebuffer was queued since the last clear)
+        cudaEventRecord(c->ev_fb_free, c->stream);
+        cudaStreamWaitEvent(c->fb_stream, c->ev_fb_free, 0);
+    }
+    return c->fb_stream;
+}
+void fb_clear_end(fgl_ctx *c) {
+    if (!c->clear_overlap) return;
+    cudaEventRecord(c->ev_cleared, c->fb_stream);
+    c->clear_pending = true;
+}
+// ... and whatever touches the framebuffer on the draw stream next waits for the clear.
+void fb_join(fgl_ctx *c) {
+    if (c->clear_pending) {
+        cudaStreamWaitEvent(c->stream, c->ev_cleared, 0);
+        c->clear_pending = false;
+    }
 }
 
 template <class T>
@@ -216,6 +245,7 @@ void mesh_release(fgl_ctx *c, const fgl_mesh *cm) {
 }
 
 __global__ void k_accumulate(const DrawCounters *cur, DrawCounters *acc) {
+    pdl_wait();
     acc->total_pixels += cur->total_pixels;
     acc->updated_pixels += cur->updated_pixels;
     acc->overflow |= cur->overflow;
@@ -340,6 +370,7 @@ int enqueue_draw(fgl_ctx *c, const DrawParams &p) {
     }
     launches += launch_bin(p, c->wb, &sorted, c->stream);
     if (ps) cudaEventRecord(ps->e[3], c->stream);
+    fb_join(c);  // the front end and the binning ran beside a pending clear; the strips need the framebuffer
     launches += launch_raster(p, c->wb, sorted, c->color, c->depth, c->stream);
     if (ps) cudaEventRecord(ps->e[4], c->stream);
     cudaError_t e = cudaGetLastError();
@@ -394,7 +425,7 @@ int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const 
     if (async) {
         rc = enqueue_draw(c, p);
         if (rc) return rc;
-        k_accumulate<<<1, 1, 0, c->stream>>>(c->wb.counters, c->acc_dev);
+        launch_pdl(k_accumulate, 1, 1, 0, c->stream, (const DrawCounters *)c->wb.counters, c->acc_dev);
         mesh_release(c, mesh);
         c->async_pending = true;
         return FGL_OK;
@@ -489,9 +520,21 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     c->profiling = false; c->prof_used = 0; c->prof_created = false;
     memset(&c->prof_acc, 0, sizeof c->prof_acc);
     const size_t npix = (size_t)width * height;
-    c->stream = nullptr; c->copy_stream = nullptr;
+    c->stream = nullptr; c->copy_stream = nullptr; c->fb_stream = nullptr;
+    c->ev_fb_free = nullptr; c->ev_cleared = nullptr; c->clear_pending = false;
+    {
+        const char *pd = getenv("FGL_PDL");  // tuning aid: 0 launches every kernel fully serialised
+        fgl::g_pdl = !(pd && atoi(pd) == 0);
+    }
+    {
+        const char *co = getenv("FGL_CLEAR_OVERLAP");  // tuning aid: 0 keeps the clears on the draw stream
+        c->clear_overlap = !(co && atoi(co) == 0);
+    }
     cudaError_t err = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->fb_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_fb_free, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_cleared, cudaEventDisableTiming);
     if (err == cudaSuccess) err = dev_alloc(&c->color, npix);
     if (err == cudaSuccess) err = dev_alloc(&c->depth, npix);
     if (err == cudaSuccess) err = dev_alloc(&c->wb.counters, 1);
@@ -540,6 +583,9 @@ int fgl_context_destroy(fgl_ctx *c) {
     if (!c) return FGL_OK;
     cudaSetDevice(c->device);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->fb_stream) { cudaStreamSynchronize(c->fb_stream); cudaStreamDestroy(c->fb_stream); }
+    if (c->ev_fb_free) cudaEventDestroy(c->ev_fb_free);
+    if (c->ev_cleared) cudaEventDestroy(c->ev_cleared);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_work(c->wb);
     dev_free(c->wb.counters); dev_free(c->wb.tile_clock);
@@ -568,7 +614,8 @@ int fgl_clear_color(fgl_ctx *c, const uint8_t rgba[4]) {
     if (!rgba) return fail(c, FGL_E_INVALID, "null colour");
     std::lock_guard<std::mutex> lock(c->mu);
     const uint32_t v = (uint32_t)rgba[0] | ((uint32_t)rgba[1] << 8) | ((uint32_t)rgba[2] << 16) | ((uint32_t)rgba[3] << 24);
-    launch_clear_color(c->color, (size_t)c->w * c->h, v, c->stream);
+    launch_clear_color(c->color, (size_t)c->w * c->h, v, fb_clear_begin(c));
+    fb_clear_end(c);
     CK(c, cudaGetLastError());
     return FGL_OK;
 }
@@ -577,7 +624,8 @@ int fgl_clear_depth(fgl_ctx *c, double value) {
     int rc = check_ctx(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(c->mu);
-    launch_clear_depth(c->depth, (size_t)c->w * c->h, value, c->stream);
+    launch_clear_depth(c->depth, (size_t)c->w * c->h, value, fb_clear_begin(c));
+    fb_clear_end(c);
     CK(c, cudaGetLastError());
     return FGL_OK;
 }
@@ -877,6 +925,7 @@ int fgl_sync(fgl_ctx *c, fgl_raster_info *info) {
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(c->mu);
     if (info) { info->total_pixels = 0; info->updated_pixels = 0; }
+    fb_join(c);
     if (c->async_pending) {
         CK(c, cudaMemcpyAsync(c->host_counters, c->acc_dev, sizeof(DrawCounters), cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaMemsetAsync(c->acc_dev, 0, sizeof(DrawCounters), c->stream));
@@ -918,6 +967,7 @@ int fgl_frame_end(fgl_ctx *c, uint8_t *color_dst, size_t stride, fgl_fence **fen
     } else if (f->device != c->device) {
         return fail(c, FGL_E_INVALID, "fence belongs to another device");
     }
+    fb_join(c);
     if (color_dst)
         CK(c, cudaMemcpy2DAsync(color_dst, stride, c->color, (size_t)c->w * 4, (size_t)c->w * 4, c->h,
                                 cudaMemcpyDeviceToHost, c->stream));
@@ -997,6 +1047,7 @@ int fgl_read_color(fgl_ctx *c, uint8_t *dst, size_t stride) {
     if (stride == 0) stride = (size_t)c->w * 4;
     if (stride < (size_t)c->w * 4) return fail(c, FGL_E_INVALID, "stride too small");
     std::lock_guard<std::mutex> lock(c->mu);
+    fb_join(c);
     CK(c, cudaMemcpy2DAsync(dst, stride, c->color, (size_t)c->w * 4, (size_t)c->w * 4, c->h, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return FGL_OK;
@@ -1006,6 +1057,7 @@ int fgl_read_depth(fgl_ctx *c, double *dst) {
     if (rc) return rc;
     if (!dst) return fail(c, FGL_E_INVALID, "null destination");
     std::lock_guard<std::mutex> lock(c->mu);
+    fb_join(c);
     CK(c, cudaMemcpyAsync(dst, c->depth, sizeof(double) * c->w * c->h, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return FGL_OK;
@@ -1017,6 +1069,7 @@ int fgl_depth_image(fgl_ctx *c, uint16_t *dst) {
     std::lock_guard<std::mutex> lock(c->mu);
     const size_t npix = (size_t)c->w * c->h;
     if (!c->gray16) CK(c, dev_alloc(&c->gray16, npix));
+    fb_join(c);
     launch_depth_image(c->depth, npix, c->gray16, c->scratch, c->stream);
     CK(c, cudaGetLastError());
     CK(c, cudaMemcpyAsync(dst, c->gray16, npix * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
@@ -1031,6 +1084,7 @@ int fgl_write_color(fgl_ctx *c, const uint8_t *src, size_t stride) {
     if (stride == 0) stride = (size_t)c->w * 4;
     if (stride < (size_t)c->w * 4) return fail(c, FGL_E_INVALID, "stride too small");
     std::lock_guard<std::mutex> lock(c->mu);
+    fb_join(c);
     CK(c, cudaMemcpy2DAsync(c->color, (size_t)c->w * 4, src, stride, (size_t)c->w * 4, c->h, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return FGL_OK;
@@ -1040,6 +1094,7 @@ int fgl_write_depth(fgl_ctx *c, const double *src) {
     if (rc) return rc;
     if (!src) return fail(c, FGL_E_INVALID, "null source");
     std::lock_guard<std::mutex> lock(c->mu);
+    fb_join(c);
     CK(c, cudaMemcpyAsync(c->depth, src, sizeof(double) * c->w * c->h, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return FGL_OK;
@@ -1054,6 +1109,7 @@ int fgl_resolve_device(fgl_ctx *c, int factor) {
         return fail(c, FGL_E_INVALID, "resolve factor %d must be in [1,16] and divide %dx%d", factor, c->w, c->h);
     std::lock_guard<std::mutex> lock(c->mu);
     const int dw = c->w / factor, dh = c->h / factor;
+    fb_join(c);
     if (dw != c->rw || dh != c->rh) {
         dev_free(c->resolved);
         CK(c, dev_alloc(&c->resolved, (size_t)dw * dh));
@@ -1091,6 +1147,7 @@ int fgl_composite_pack(fgl_ctx *c, void *keys_dev) {
     if (rc) return rc;
     if (!keys_dev) return fail(c, FGL_E_INVALID, "null key buffer");
     std::lock_guard<std::mutex> lock(c->mu);
+    fb_join(c);
     launch_composite_pack(c->color, c->depth, static_cast<unsigned long long *>(keys_dev), (size_t)c->w * c->h, c->stream);
     CK(c, cudaGetLastError());
     return FGL_OK;
@@ -1100,6 +1157,7 @@ int fgl_composite_unpack(fgl_ctx *c, const void *keys_dev) {
     if (rc) return rc;
     if (!keys_dev) return fail(c, FGL_E_INVALID, "null key buffer");
     std::lock_guard<std::mutex> lock(c->mu);
+    fb_join(c);
     launch_composite_unpack(c->color, c->depth, static_cast<const unsigned long long *>(keys_dev), (size_t)c->w * c->h, c->stream);
     CK(c, cudaGetLastError());
     return FGL_OK;
@@ -1157,6 +1215,7 @@ int fgl_composite_peer(fgl_ctx *c, int rank, int nranks, void *const *color, voi
     std::lock_guard<std::mutex> lock(c->mu);
     const size_t npix = (size_t)c->w * c->h;
     const size_t px0 = npix * (size_t)rank / nranks, px1 = npix * (size_t)(rank + 1) / nranks;
+    fb_join(c);
     launch_composite_peer(reinterpret_cast<uint32_t *const *>(color), reinterpret_cast<double *const *>(depth), nranks,
                           px0, px1, c->stream);
     CK(c, cudaGetLastError());

@@ -705,6 +705,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     __shared__ unsigned long long s_region;
     __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();  // k_seg_index may be scheduled while the last wave of this grid drains
     const uint32_t vb = blockIdx.x;
     const uint32_t nblocks = (p.count + FT - 1) / FT;
     const uint32_t i = vb * FT + tid;
@@ -922,6 +923,8 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
 // cache resident).
 __global__ void __launch_bounds__(256)
 k_seg_index(const __grid_constant__ WorkBuffers wb, uint32_t nent) {
+    pdl_wait();
+    pdl_trigger();
     const DrawCounters *ctr = wb.counters;
     if (ctr->overflow) return;
     const uint32_t n = min(ctr->n_segs, wb.cap_segs);
@@ -945,7 +948,7 @@ int launch_front(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {
 }
 int launch_seg_index(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {
     const uint32_t blocks = (p.count + FT - 1) / FT;
-    k_seg_index<<<148 * 8, 256, 0, st>>>(wb, blocks);
+    launch_pdl(k_seg_index, 148 * 8, 256, 0, st, wb, blocks);
     return 1;
 }
 

@@ -75,17 +75,22 @@ static_assert(sizeof(Seg) == 32, "Seg layout");
 
 // ---- binned segment: a Seg plus every field of its record the back end needs (depth phase, perspective
 // weights, attribute source), so that neither the strip kernel nor the shading kernel chases the record.
-// 128 bytes: one cache line per segment.
-struct __align__(16) SegV {
+// 128 bytes: one cache line per segment.  The first 96 bytes (SegHead: three sectors) are all the depth phase of
+// the strip kernel reads; the perspective weights behind them are for shading only.
+struct __align__(16) SegHead {
     double w0, w1, w2;
     double ra, z0, z1, z2;   // 1/area and the three screen depths: z = (b0*z0 + b1*z1) + b2*z2
     double a12, a20, a01;    // per-pixel increments of w0, w1, w2 (context.go:167-172)
-    double r0, r1, r2;       // 1 / Output.W of the three vertices, context.go:176-178
-    uint32_t src;            // primitive index in the mesh planes, or clip-pool triangle index
-    uint32_t flags;          // REC_* (vertex map, pool bit)
     uint16_t x;              // first covered pixel (absolute column)
     uint8_t yt, cnt;         // (unused), covered pixels (1..TILE_W)
-    uint32_t _pad[3];
+    uint32_t src;            // primitive index in the mesh planes, or clip-pool triangle index
+    uint32_t flags;          // REC_* (vertex map, pool bit)
+    uint32_t _pad0;
+};
+static_assert(sizeof(SegHead) == 96, "SegHead layout");
+struct __align__(16) SegV : SegHead {
+    double r0, r1, r2;       // 1 / Output.W of the three vertices, context.go:176-178
+    uint32_t _pad[2];
 };
 static_assert(sizeof(SegV) == 128, "SegV layout");
 
@@ -167,6 +172,35 @@ struct WorkBuffers {
 };
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch ------------------------------------------------------------------
+// The kernels of one draw are short (3-130 us) and strictly ordered; launched with the programmatic-serialisation
+// attribute, the next kernel's CTAs are scheduled while the last wave of its predecessor drains and block in
+// pdl_wait() until that grid has completed and flushed -- the launch latency and ramp of ~10 kernels per frame
+// overlap instead of adding up.  Rules: a kernel launched through launch_pdl() calls pdl_wait() before it reads
+// or writes anything and before any early return (completion must stay transitive along the chain); pdl_trigger()
+// at the top lets the successor be scheduled as soon as every CTA of this grid is resident.  Both are no-ops
+// in a kernel that was launched without the attribute.  FGL_PDL=0 turns the attribute off (tuning aid).
+extern bool g_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef FGL_PDL_TRIGGER
+#define FGL_PDL_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if FGL_PDL_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+template <class... P, class... A>
+inline cudaError_t launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr; cfg.numAttrs = g_pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 // Index (relative to the draw's first primitive) of the mesh primitive a record / segment came from.
 __device__ __forceinline__ uint32_t src_primitive(const WorkBuffers &wb, const DrawParams &p, uint32_t src, uint32_t flags) {
     return ((flags & REC_SRC_POOL) ? wb.clip_pool[src].prim : src) - p.first;

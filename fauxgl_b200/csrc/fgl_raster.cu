@@ -46,8 +46,29 @@
 #include "fgl_math.cuh"
 #include "fgl_shade.cuh"
 
+#include <type_traits>
+
 namespace fgl {
 
+// CTAs per SM of the deferred strip kernel.  3 (80 registers) rather than 4 (64): at 64 the compiler spills values
+// that were just loaded, and a spill store is a consumer -- it waits for the load the pipeline wanted to leave in
+// flight (heaviest strip of the benchmark frame 69.5 k -> 42.4 k cycles, strip stage 78 -> 66 us at 1080p).
+#ifndef FGL_STRIP_MINB
+#define FGL_STRIP_MINB 3
+#endif
+#ifndef FGL_COOP_FACTOR
+#define FGL_COOP_FACTOR 1  // heavy strips go to whole CTAs while there are at most this many per CTA
+#endif
+#ifndef FGL_STRIP_PHASES
+#define FGL_STRIP_PHASES 0  // tuning aid (variant build): cycles per phase of the chunks of heavy strips -> tile_clock[2 * ntiles + 10 ..]
+#endif
+#if FGL_STRIP_PHASES
+#define PHASE_CLOCK(var, dep) long long var; { uint32_t dep_ = (uint32_t)(dep); asm volatile("mov.u32 %0, %0;" : "+r"(dep_)); __syncwarp(); var = clock64(); }
+#define PHASE_SET(var, dep) { uint32_t dep_ = (uint32_t)(dep); asm volatile("mov.u32 %0, %0;" : "+r"(dep_)); __syncwarp(); var = clock64(); }
+#else
+#define PHASE_CLOCK(var, dep)
+#define PHASE_SET(var, dep)
+#endif
 constexpr int SWARPS = 8;               // warps (= strips in flight) per CTA
 constexpr int STHREADS = SWARPS * 32;
 constexpr uint32_t NO_WINNER = 0xffffffffu;
@@ -57,16 +78,23 @@ constexpr int STRIP_H = TILE_W / 32;  // pixels per lane at most (p.tile_w / 32 
 
 constexpr int ZCAP = 256;  // fragments of a chunk the pixel-parallel resolution can stage
 template <bool DEFERRED> struct StripMem;
+// Gather of a chunk's 32 segment heads (deferred mode).  Eight lanes per record, six of them copy one 16-byte
+// piece each with cp.async straight into shared memory: one warp instruction touches 4 cache lines instead of 32,
+// no register holds data in flight, and the copy of the NEXT chunk of the warp's stream (the next 32 segments of
+// this strip, or the first 32 of its next strip) runs while the current one is resolved -- the segment records
+// are scattered over the whole array and come from DRAM (ncu: 99 % L2 misses, profiles/README.md), and a dependent
+// gather per chunk was the strip kernel's critical path.  Every lane then reads its own record back.
+constexpr int REC_STRIDE16 = 6;  // record stride in the staging buffer, in 16-byte units (2-way bank conflict on the read)
 template <> struct StripMem<true> {
-    double zbuf[ZCAP];       // depth of every fragment of the chunk, segment-major
+    double zbuf[ZCAP];                   // depth of every fragment of the chunk, segment-major
+    uint4 recbuf[32 * REC_STRIDE16];     // staging of the gather: refilled as soon as the lanes hold their records
     double depth[TILE_W];
     uint32_t winseg[TILE_W]; // segment (index into segv) whose fragment currently owns the pixel
     // pixel-parallel resolution of a chunk whose segments overlap
     uint32_t cover[TILE_W];  // lanes (= segments, in primitive order) that cover the pixel
     uint32_t segidx[32];     // segv index of the lane's segment
     uint32_t upd[32];        // UpdatedPixels per segment (per-primitive RasterizeInfo only)
-    uint16_t segbase[32];    // first zbuf slot of the segment
-    uint8_t segxa[32];       // its first pixel
+    int16_t segoff[32];      // first zbuf slot of the segment - its first pixel: fragment of pixel i = zbuf[segoff + i]
 };
 template <> struct StripMem<false> {
     double depth[TILE_W];
@@ -128,18 +156,88 @@ FGL_DI uint2 busy_at(const WorkBuffers &wb, uint32_t nheavy, uint32_t q) {
     return q < nheavy ? wb.busy_list[q] : wb.busy_list[wb.ntiles - 1u - (q - nheavy)];
 }
 FGL_DI void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+#ifndef FGL_SEG_PREFETCH
+#define FGL_SEG_PREFETCH 1  // sectors of a segment record prefetched into L2 ahead of its chunk (tuning aid: 0, 1, 4)
+#endif
+#ifndef FGL_SEG_LOAD
+#define FGL_SEG_LOAD 0      // 0: plain loads, 1: ld.global.cg (L2 only), 2: ld.global.nc (tuning aid)
+#endif
+FGL_DI void prefetch_seg(const SegV *sp) {
+#if FGL_SEG_PREFETCH >= 1
+    prefetch_l2(sp);
+#endif
+#if FGL_SEG_PREFETCH >= 4
+    prefetch_l2(reinterpret_cast<const char *>(sp) + 32);
+    prefetch_l2(reinterpret_cast<const char *>(sp) + 64);
+    prefetch_l2(reinterpret_cast<const char *>(sp) + 96);
+#endif
+}
+FGL_DI void gather_issue(uint4 *buf, const SegV *__restrict__ segv, uint32_t idx, int lane) {
+    const int piece = lane & 7, sub = lane >> 3;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t ridx = __shfl_sync(0xffffffffu, idx, r * 4 + sub);
+        if (ridx != NO_SEG && piece < 6) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf + (r * 4 + sub) * REC_STRIDE16 + piece);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const uint4 *>(segv + ridx) + piece)
+                         : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+FGL_DI void gather_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+FGL_DI SegHead gather_take(const uint4 *buf, uint32_t idx, int lane, int x0) {
+    SegHead h;
+    uint4 *hp = reinterpret_cast<uint4 *>(&h);
+#pragma unroll
+    for (int k = 0; k < 6; k++) hp[k] = buf[lane * REC_STRIDE16 + k];
+    if (idx == NO_SEG) { h.cnt = 0; h.x = (uint16_t)x0; }
+    return h;
+}
+FGL_DI SegHead load_head(const SegV *sp) {  // lane-per-record load (rare paths)
+    SegHead h;
+    uint4 *hp = reinterpret_cast<uint4 *>(&h);
+#pragma unroll
+    for (int k = 0; k < 6; k++) hp[k] = reinterpret_cast<const uint4 *>(sp)[k];
+    return h;
+}
+FGL_DI SegV load_seg(const SegV *sp) {
+#if FGL_SEG_LOAD == 0
+    return *sp;
+#else
+    SegV v;
+    const uint4 *s = reinterpret_cast<const uint4 *>(sp);
+    uint4 *d = reinterpret_cast<uint4 *>(&v);
+#pragma unroll
+    for (int k = 0; k < 8; k++) d[k] = FGL_SEG_LOAD == 1 ? __ldcg(s + k) : __ldg(s + k);
+    return v;
+#endif
+}
 
 // EACH: also attribute UpdatedPixels to the primitive of every segment (fgl_draw_*_each).
+//
+// Heavy strips (deferred mode).  A bin of hundreds of segments -- the poles of a parametric surface put 400+
+// sub-pixel slivers into one 32-pixel strip -- used to be one warp's serial chain of 32-segment steps and WAS the
+// kernel's duration (profiles/README.md).  The expensive part of a step, gathering the segments and walking their
+// depths into shared memory, does not depend on order; only the per-pixel replay does.  So the strips at the head
+// of the busy list (>= HEAVY_SEGS segments) are taken by whole CTAs: the eight warps stage eight consecutive
+// 32-segment chunks at once, then warp 0 replays the eight chunks in order, one lane per pixel.  Same fragments,
+// same order, same tests -- for every render state.
 template <bool DEFERRED, bool EACH>
-__global__ void __launch_bounds__(STHREADS, DEFERRED ? 4 : 3)
+__global__ void __launch_bounds__(STHREADS, DEFERRED ? FGL_STRIP_MINB : 3)
 k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb,
         const uint32_t *__restrict__ seg_order, const uint32_t *__restrict__ seg_keys, uint32_t *__restrict__ gcolor,
         double *__restrict__ gdepth) {
+    pdl_wait();
+    pdl_trigger();
     if (wb.counters->overflow) return;  // work buffers too small: the host regrows and re-issues the draw
 
-    __shared__ StripMem<DEFERRED> s_all[SWARPS];
-    const int lane = threadIdx.x & 31;
-    StripMem<DEFERRED> &sm = s_all[threadIdx.x >> 5];
+    extern __shared__ __align__(16) unsigned char s_raw[];  // SWARPS x StripMem (over the 48 KB static limit when deferred)
+    StripMem<DEFERRED> *const s_all = reinterpret_cast<StripMem<DEFERRED> *>(s_raw);
+    __shared__ uint32_t s_nseg;          // heavy strips: segments of the strip (tuning aid)
+    __shared__ uint32_t s_flag[SWARPS];  // heavy strips: 0 = the warp's chunk is empty, 1 = staged, 2 = too many fragments to stage
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    StripMem<DEFERRED> &sm = s_all[warp];
     const fgl_state st = p.state;
     unsigned long long my_updated = 0;
     const int tile_w = p.tile_w, strip_h = tile_w >> 5;  // strip width of this context (32 or 64), pixels per lane
@@ -148,16 +246,16 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         sm.upd[lane] = 0;
         __syncwarp();
     }
-
-    // Busy strips (heavy ones first in the list, k_tile_ranges) are dealt out round-robin over all warps of the
-    // grid.  The strip loop is software-pipelined so that no dependent load is waited for: while strip t is
-    // processed, the list entry of t+3, the first 32 (segment, key) pairs of t+2 and an L2 prefetch of the first
-    // segments and the depth row of t+1 are in flight.
     const uint32_t nsegs = min(wb.counters->n_segs, wb.cap_segs);
     const uint32_t nheavy = wb.tile_ctl->nheavy, nbusy = nheavy + wb.tile_ctl->nlight;
-    const uint32_t nwarps = gridDim.x * SWARPS;
-    uint32_t q = blockIdx.x * SWARPS + (threadIdx.x >> 5);
-    auto load_entry = [&](uint32_t qq) { return qq < nbusy ? busy_at(wb, nheavy, qq) : make_uint2(0xffffffffu, 0u); };
+    // (key, segment index) of sorted position pos, raw: nothing here consumes the loaded values, so the loads stay
+    // in flight until pair_idx() resolves them an iteration (or a strip) later
+    auto load_raw = [&](uint32_t pos) {
+        uint2 r = make_uint2(0xffffffffu, 0u);
+        if (pos < nsegs) { r.x = seg_keys[pos]; r.y = seg_order[pos]; }
+        return r;
+    };
+    auto pair_idx = [&](uint32_t strip, uint2 raw) { return (raw.x == strip && strip != 0xffffffffu) ? raw.y : NO_SEG; };
     // (segment index, valid) of sorted position pos for a bin of `strip`
     auto load_pair = [&](uint32_t strip, uint32_t pos) {
         uint32_t idx = NO_SEG;
@@ -167,16 +265,229 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         }
         return idx;
     };
+
+    // ---- building blocks of a 32-segment chunk ---------------------------------------------------------------
+    // (1) every segment lane stages the depths of its fragments in d.zbuf and registers itself in the cover mask
+    // of its pixels
+    auto stage_chunk = [&](auto &d, const auto &v, uint32_t idx, int xa, int cnt) {
+        const uint32_t fbase = warp_incl_scan((uint32_t)cnt) - (uint32_t)cnt;
+        d.segoff[lane] = (int16_t)((int)fbase - xa);
+        d.segidx[lane] = idx;
+        double w0 = v.w0, w1 = v.w1, w2 = v.w2;
+        for (int k = 0; k < cnt; k++) {
+            const double b0 = w0 * v.ra, b1 = w1 * v.ra, b2 = w2 * v.ra;
+            d.zbuf[fbase + k] = b0 * v.z0 + b1 * v.z1 + b2 * v.z2;  // context.go:230
+            atomicOr(&d.cover[xa + k], 1u << lane);
+            w0 += v.a12; w1 += v.a20; w2 += v.a01;  // context.go:211-213
+        }
+    };
+    // (2) every PIXEL lane replays the staged fragments of its pixel in lane order == primitive order against a
+    // running depth in registers; the strip's depth and winners live in t
+    auto replay_chunk = [&](auto &d, auto &t) {
+#pragma unroll
+        for (int h = 0; h < strip_h; h++) {
+            const int pix = lane + 32 * h;
+            uint32_t m = d.cover[pix];
+            if (m) {
+                d.cover[pix] = 0;
+                double dcur = t.depth[pix];
+                int win = -1;
+                // Four fragments at a time: their depths are fetched first (independent loads, two shared-memory
+                // levels each), then tested in order -- the serial chain per fragment is the compare alone.  At
+                // the poles of a parametric surface hundreds of fragments pile onto one pixel.
+                while (m) {
+                    int jj[4];
+                    double zz[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        jj[u] = m ? __ffs(m) - 1 : -1;
+                        m &= m - 1;
+                    }
+                    int off[4];  // (missing fragments read segment 0's slot: any staged value, never tested)
+#pragma unroll
+                    for (int u = 0; u < 4; u++) off[u] = (int)d.segoff[jj[u] & 31];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) zz[u] = d.zbuf[jj[u] >= 0 ? off[u] + pix : 0];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const double z = zz[u];
+                        const double bz = z + st.depth_bias;
+                        // context.go:232 early-out, then (no discard possible) the retest at :248
+                        if (jj[u] >= 0 && !(st.read_depth && bz > dcur) && (bz <= dcur || !st.read_depth)) {
+                            my_updated++;
+                            if (st.write_depth) dcur = z;
+                            win = jj[u];
+                            if constexpr (EACH) atomicAdd(&d.upd[jj[u]], 1u);
+                        }
+                    }
+                }
+                if (win >= 0) {
+                    if (st.write_depth) t.depth[pix] = dcur;
+                    t.winseg[pix] = d.segidx[win];
+                }
+            }
+        }
+    };
+    // per-primitive UpdatedPixels of a staged chunk, by the lanes that hold its segments
+    auto flush_each = [&](auto &d, const auto &v) {
+        const uint32_t u = d.upd[lane];
+        d.upd[lane] = 0;
+        if (u) atomicAdd(&p.prim_info[2 * (size_t)src_primitive(wb, p, v.src, v.flags) + 1], (unsigned long long)u);
+    };
+    // (3) without staging: lanes walk their segments straight against the strip t; overlapping segments take turns
+    // (a pixel is ready for lane i when no earlier lane still wants it)
+    auto direct_chunk = [&](auto &t, const auto &v, uint32_t idx, int xa, unsigned long long pend, bool disjoint) {
+        const unsigned long long updated_before = my_updated;
+        while (true) {
+            const unsigned long long ready = disjoint ? pend : (pend & ~warp_excl_or(pend, lane));
+            if (ready) {
+                double w0 = v.w0, w1 = v.w1, w2 = v.w2;
+                const int last = 63 - __clzll((long long)ready);
+                for (int pi = xa; pi <= last; pi++) {
+                    if ((ready >> pi) & 1ull) {
+                        if constexpr (DEFERRED) {
+                            const double b0 = w0 * v.ra, b1 = w1 * v.ra, b2 = w2 * v.ra;
+                            const double z = b0 * v.z0 + b1 * v.z1 + b2 * v.z2;  // context.go:230
+                            resolve_deferred(st, t, pi, z, idx, my_updated);
+                        } else {
+                            fragment_inline(p, st, wb, v, w0, w1, w2, pi, t, my_updated);
+                        }
+                    }
+                    w0 += v.a12; w1 += v.a20; w2 += v.a01;  // context.go:211-213
+                }
+                pend &= ~ready;
+            }
+            __syncwarp();
+            if (FGL_STRIP_PHASES && wb.tile_clock && lane == 0 && !disjoint) atomicAdd(&wb.tile_clock[2 * (size_t)wb.ntiles + 8], 1ull);
+            if (disjoint || !__any_sync(0xffffffffu, pend != 0)) break;
+        }
+        if (EACH && my_updated != updated_before)
+            atomicAdd(&p.prim_info[2 * (size_t)src_primitive(wb, p, v.src, v.flags) + 1], my_updated - updated_before);
+    };
+    auto pend_mask = [](int xa, int cnt) {
+        return cnt > 0 ? ((cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull)) << xa) : 0ull;
+    };
+
+    if (wb.tile_clock && threadIdx.x == 0 && blockIdx.x == 0) wb.tile_clock[2 * (size_t)wb.ntiles + 9] = nheavy;  // tuning aid
+    // ---- heavy strips: one CTA per strip ------------------------------------------------------------------------
+    uint32_t light0 = 0;  // first entry of the per-warp part of the busy list
+    // Only when every CTA gets at most one: with thousands of long bins (large triangles at 8K) there is enough
+    // strip-level parallelism and eight independent warps beat eight warps in lock step.
+    if constexpr (DEFERRED) {
+    if (nheavy <= (uint32_t)FGL_COOP_FACTOR * gridDim.x) {
+        light0 = nheavy;
+        auto &t = s_all[0];  // the strip: depth and winners
+        for (uint32_t hq = blockIdx.x; hq < nheavy; hq += gridDim.x) {
+            const uint2 e = wb.busy_list[hq];
+            const uint32_t strip = e.x, bin_beg = e.y;
+            const long long t_begin = wb.tile_clock ? clock64() : 0;
+            const int x0 = (int)(strip % (uint32_t)p.tiles_x) * tile_w;
+            const int y = (int)(strip / (uint32_t)p.tiles_x);
+            const int tw = min(tile_w, p.width - x0);
+            const size_t grow = (size_t)y * p.width + x0;
+            __syncthreads();  // the previous strip of this CTA is written back
+            if (threadIdx.x == 0) s_nseg = 0;
+            if (warp == 0) {
+#pragma unroll
+                for (int h = 0; h < strip_h; h++) {
+                    const int i = lane + 32 * h;
+                    t.winseg[i] = NO_WINNER;
+                    if (i < tw) t.depth[i] = gdepth[grow + i];
+                }
+            }
+            const unsigned long long updated_at_start = my_updated;
+            uint32_t idx = load_pair(strip, bin_beg + warp * 32 + lane);
+            gather_issue(sm.recbuf, wb.segv, idx, lane);
+            for (uint32_t round = bin_beg;; round += SWARPS * 32) {
+                const uint32_t idx_next = load_pair(strip, round + SWARPS * 32 + warp * 32 + lane);
+                gather_wait();
+                __syncwarp();
+                const SegHead v = gather_take(sm.recbuf, idx, lane, x0);
+                __syncwarp();
+                gather_issue(sm.recbuf, wb.segv, idx_next, lane);  // the warp's chunk of the next round, while this one is resolved
+                const int xa = (int)v.x - x0, cnt = (int)v.cnt;
+                const uint32_t have = __ballot_sync(0xffffffffu, idx != NO_SEG);
+                const uint32_t nfrag = __reduce_add_sync(0xffffffffu, (uint32_t)cnt);
+                const bool can_stage = nfrag <= (uint32_t)ZCAP;
+                if (have && can_stage) stage_chunk(sm, v, idx, xa, cnt);
+                if (lane == 0) s_flag[warp] = have ? (can_stage ? 1u : 2u) : 0u;
+                if (have && !can_stage) sm.segidx[lane] = idx;
+                __syncthreads();
+                if (warp == 0) {
+                    for (int c = 0; c < SWARPS; c++) {
+                        const uint32_t f = s_flag[c];
+                        if (f == 0) break;
+                        if (f == 1) {
+                            replay_chunk(s_all[c], t);
+                        } else {  // rare (long segments): warp 0 walks the chunk itself, in order
+                            const uint32_t ic = s_all[c].segidx[lane];
+                            SegHead vc;
+                            vc.cnt = 0; vc.x = (uint16_t)x0;
+                            if (ic != NO_SEG) vc = load_head(wb.segv + ic);
+                            const int xc = (int)vc.x - x0;
+                            direct_chunk(t, vc, ic, xc, pend_mask(xc, (int)vc.cnt), false);
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+                if constexpr (EACH) {
+                    if (have && can_stage) flush_each(sm, v);
+                }
+                if (wb.tile_clock && lane == 0 && have) atomicAdd(&s_nseg, (uint32_t)__popc(have));
+                const bool more = s_flag[SWARPS - 1] != 0;
+                idx = idx_next;
+                __syncthreads();  // s_flag is rewritten by the next round
+                if (!more) break;
+            }
+            if (warp == 0) {
+                const bool touched = __any_sync(0xffffffffu, my_updated != updated_at_start);
+                if (st.write_color)
+                    for (int h = 0; h < strip_h; h++) wb.vis_seg[(size_t)strip * tile_w + lane + 32 * h] = t.winseg[lane + 32 * h];
+                if (touched && st.write_depth) {
+#pragma unroll
+                    for (int h = 0; h < strip_h; h++) {
+                        const int i = lane + 32 * h;
+                        if (i < tw) gdepth[grow + i] = t.depth[i];
+                    }
+                }
+            }
+            if (wb.tile_clock && threadIdx.x == 0) {  // (s_nseg is complete: the last round ended with a barrier)
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                wb.tile_clock[2 * strip] = (unsigned long long)(clock64() - t_begin);
+                wb.tile_clock[2 * strip + 1] = ((unsigned long long)smid << 32) | s_nseg;
+            }
+        }
+        __syncthreads();  // s_all[0] goes back to warp 0's own strips
+    }
+    }
+
+    // ---- the other strips: one warp per strip --------------------------------------------------------------------
+    // Dealt out round-robin over all warps of the grid.  The strip loop is software-pipelined so that no dependent
+    // load is waited for: while strip t is processed, the list entry of t+3, the first 32 (segment, key) pairs of
+    // t+2 and an L2 prefetch of the first segments and the depth row of t+1 are in flight.
+    const uint32_t nwarps = gridDim.x * SWARPS;
+    uint32_t q = light0 + blockIdx.x * SWARPS + (uint32_t)warp;
+    // list entries are loaded raw as well (index clamped, validity from the position)
+    auto load_entry = [&](uint32_t qq) { return busy_at(wb, nheavy, min(qq, nbusy ? nbusy - 1u : 0u)); };
     uint2 e0 = load_entry(q), e1 = load_entry(q + nwarps), e2 = load_entry(q + 2 * nwarps);
-    uint32_t ik0 = load_pair(e0.x, e0.y + lane), ik1 = load_pair(e1.x, e1.y + lane);
-    while (e0.x != 0xffffffffu) {
+    // the first 64 pairs of strips t and t+1 (a = positions 0..31, b = 32..63)
+    uint2 r0a = load_raw(e0.y + lane), r0b = load_raw(e0.y + 32 + lane);
+    uint2 r1a = load_raw(e1.y + lane), r1b = load_raw(e1.y + 32 + lane);
+    if constexpr (DEFERRED) gather_issue(sm.recbuf, wb.segv, q < nbusy ? pair_idx(e0.x, r0a) : NO_SEG, lane);
+    while (q < nbusy) {
         const uint32_t strip = e0.x, bin_beg = e0.y;
+        const uint32_t strip1 = q + nwarps < nbusy ? e1.x : 0xffffffffu;  // the warp's next strip
         // pipeline: entry of t+3, pairs of t+2, prefetch of t+1
         const uint2 e3 = load_entry(q + 3 * nwarps);
-        const uint32_t ik2 = load_pair(e2.x, e2.y + lane);
-        if (ik1 != NO_SEG) prefetch_l2(wb.segv + ik1);
-        if (e1.x != 0xffffffffu && lane < tile_w / 16)
-            prefetch_l2(gdepth + (size_t)(e1.x / (uint32_t)p.tiles_x) * p.width + (e1.x % (uint32_t)p.tiles_x) * tile_w + lane * 16);
+        const uint2 r2a = load_raw(e2.y + lane), r2b = load_raw(e2.y + 32 + lane);
+        if constexpr (!DEFERRED) {
+            const uint32_t ik1 = pair_idx(strip1, r1a);
+            if (ik1 != NO_SEG) prefetch_seg(wb.segv + ik1);
+        }
+        if (strip1 != 0xffffffffu && lane < tile_w / 16)
+            prefetch_l2(gdepth + (size_t)(strip1 / (uint32_t)p.tiles_x) * p.width + (strip1 % (uint32_t)p.tiles_x) * tile_w + lane * 16);
         const long long t_begin = wb.tile_clock ? clock64() : 0;
         uint32_t nseg = 0;
         const int x0 = (int)(strip % (uint32_t)p.tiles_x) * tile_w;
@@ -198,19 +509,38 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         __syncwarp();
         const unsigned long long updated_at_start = my_updated;
 
-        // ---- the bin, 32 segments at a time; the pairs of chunk c+2 and an L2 prefetch of the segments of chunk
-        // c+1 are in flight while chunk c is resolved.  The bin ends where the sorted key changes. -------------
-        uint32_t idx = ik0, idx_b = load_pair(strip, bin_beg + 32 + lane);
+        // ---- the bin, 32 segments at a time; the pairs of chunk c+2 are loaded (raw) and the records of chunk c+1
+        // copied while chunk c is resolved.  The bin ends where the sorted key changes. -------------
+        uint32_t idx = pair_idx(strip, r0a);
+        uint2 rb = r0b;
         for (uint32_t chunk = bin_beg; __any_sync(0xffffffffu, idx != NO_SEG); chunk += 32) {
-            const uint32_t idx_c = load_pair(strip, chunk + 64 + lane);
+            PHASE_CLOCK(pc0, idx)
+            const uint2 rc = load_raw(chunk + 64 + lane);
+            const uint32_t idx_b = pair_idx(strip, rb);
             nseg += (uint32_t)__popc(__ballot_sync(0xffffffffu, idx != NO_SEG));
-            SegV v;
-            v.cnt = 0; v.x = (uint16_t)x0;
-            if (idx != NO_SEG) v = wb.segv[idx];
-            if (idx_b != NO_SEG) prefetch_l2(wb.segv + idx_b);
+            PHASE_CLOCK(pc0a, idx_b)
+#if FGL_STRIP_PHASES
+            long long pc0b = 0;
+#endif
+            std::conditional_t<DEFERRED, SegHead, SegV> v;
+            if constexpr (DEFERRED) {
+                // the next chunk of this warp's stream: the next 32 segments of the strip, or the first 32 of its
+                // next strip; its copy runs while this chunk is resolved
+                gather_wait();
+                __syncwarp();
+                v = gather_take(sm.recbuf, idx, lane, x0);
+                __syncwarp();
+                PHASE_SET(pc0b, v.cnt)
+                const uint32_t nidx = __any_sync(0xffffffffu, idx_b != NO_SEG) ? idx_b : pair_idx(strip1, r1a);
+                gather_issue(sm.recbuf, wb.segv, nidx, lane);
+            } else {
+                v.cnt = 0; v.x = (uint16_t)x0;
+                if (idx != NO_SEG) v = load_seg(wb.segv + idx);
+                if (idx_b != NO_SEG) prefetch_seg(wb.segv + idx_b);
+            }
             const int xa = (int)v.x - x0, cnt = (int)v.cnt;
-            unsigned long long pend = cnt > 0 ? ((cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull)) << xa) : 0ull;
-            const unsigned long long updated_before = my_updated;
+            PHASE_CLOCK(pc1, __reduce_add_sync(0xffffffffu, (uint32_t)cnt + (uint32_t)__double2loint(v.a01)))
+            const unsigned long long pend = pend_mask(xa, cnt);
 
             // no two segments of the chunk overlap <=> popcounts add up
             const uint32_t orl = __reduce_or_sync(0xffffffffu, (uint32_t)pend);
@@ -218,7 +548,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             const uint32_t nfrag = __reduce_add_sync(0xffffffffu, (uint32_t)cnt);
             const bool disjoint = nfrag == (uint32_t)(__popc(orl) + __popc(orh));
             bool staged = false;
-            if (wb.tile_clock && lane == 0) {  // tuning aid: chunks / fragments by resolution path
+            if (FGL_STRIP_PHASES && wb.tile_clock && lane == 0) {  // tuning aid (variant build: same-address atomics distort the timing): chunks / fragments by resolution path
                 unsigned long long *dbg = wb.tile_clock + 2 * (size_t)wb.ntiles;
                 const int path = disjoint ? 0 : ((DEFERRED && nfrag <= (uint32_t)ZCAP) ? 1 : 2);
                 atomicAdd(&dbg[path], 1ull);
@@ -226,88 +556,33 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             }
             if constexpr (DEFERRED) {
                 if (!disjoint && nfrag <= (uint32_t)ZCAP) {
-                    // (1) every segment lane stages the depths of its fragments and registers itself in the
-                    // cover mask of its pixels; (2) every PIXEL lane replays the fragments of its pixel in lane
-                    // order == primitive order against a running depth in registers.
                     staged = true;
-                    const uint32_t fbase = warp_incl_scan((uint32_t)cnt) - (uint32_t)cnt;
-                    sm.segbase[lane] = (uint16_t)fbase;
-                    sm.segxa[lane] = (uint8_t)xa;
-                    sm.segidx[lane] = idx;
-                    {
-                        double w0 = v.w0, w1 = v.w1, w2 = v.w2;
-                        for (int k = 0; k < cnt; k++) {
-                            const double b0 = w0 * v.ra, b1 = w1 * v.ra, b2 = w2 * v.ra;
-                            sm.zbuf[fbase + k] = b0 * v.z0 + b1 * v.z1 + b2 * v.z2;  // context.go:230
-                            atomicOr(&sm.cover[xa + k], 1u << lane);
-                            w0 += v.a12; w1 += v.a20; w2 += v.a01;  // context.go:211-213
-                        }
-                    }
+                    PHASE_CLOCK(pc2, nfrag)
+                    stage_chunk(sm, v, idx, xa, cnt);
                     __syncwarp();
-#pragma unroll
-                    for (int h = 0; h < strip_h; h++) {
-                        const int pix = lane + 32 * h;
-                        uint32_t m = sm.cover[pix];
-                        if (m) {
-                            sm.cover[pix] = 0;
-                            double d = sm.depth[pix];
-                            int win = -1;
-                            while (m) {
-                                const int j = __ffs(m) - 1;
-                                m &= m - 1;
-                                const double z = sm.zbuf[(int)sm.segbase[j] + pix - (int)sm.segxa[j]];
-                                const double bz = z + st.depth_bias;
-                                // context.go:232 early-out, then (no discard possible) the retest at :248
-                                if (!(st.read_depth && bz > d) && (bz <= d || !st.read_depth)) {
-                                    my_updated++;
-                                    if (st.write_depth) d = z;
-                                    win = j;
-                                    if constexpr (EACH) atomicAdd(&sm.upd[j], 1u);
-                                }
-                            }
-                            if (win >= 0) {
-                                if (st.write_depth) sm.depth[pix] = d;
-                                sm.winseg[pix] = sm.segidx[win];
-                            }
-                        }
-                    }
+                    PHASE_CLOCK(pc3, sm.cover[lane])
+                    replay_chunk(sm, sm);
                     if constexpr (EACH) {
                         __syncwarp();
-                        const uint32_t u = sm.upd[lane];
-                        sm.upd[lane] = 0;
-                        if (u) atomicAdd(&p.prim_info[2 * (size_t)src_primitive(wb, p, v.src, v.flags) + 1], (unsigned long long)u);
+                        flush_each(sm, v);
                     }
                     __syncwarp();
-                }
-            }
-            if (!staged) {
-                while (true) {
-                    const unsigned long long ready = disjoint ? pend : (pend & ~warp_excl_or(pend, lane));
-                    if (ready) {
-                        double w0 = v.w0, w1 = v.w1, w2 = v.w2;
-                        const int last = 63 - __clzll((long long)ready);
-                        for (int pi = xa; pi <= last; pi++) {
-                            if ((ready >> pi) & 1ull) {
-                                if constexpr (DEFERRED) {
-                                    const double b0 = w0 * v.ra, b1 = w1 * v.ra, b2 = w2 * v.ra;
-                                    const double z = b0 * v.z0 + b1 * v.z1 + b2 * v.z2;  // context.go:230
-                                    resolve_deferred(st, sm, pi, z, idx, my_updated);
-                                } else {
-                                    fragment_inline(p, st, wb, v, w0, w1, w2, pi, sm, my_updated);
-                                }
-                            }
-                            w0 += v.a12; w1 += v.a20; w2 += v.a01;  // context.go:211-213
-                        }
-                        pend &= ~ready;
+                    PHASE_CLOCK(pc4, sm.winseg[lane])
+#if FGL_STRIP_PHASES
+                    if (wb.tile_clock && lane == 0 && (FGL_STRIP_PHASES == 3 || q - light0 < nheavy)) {
+                        unsigned long long *ph = wb.tile_clock + 2 * (size_t)wb.ntiles + 10;
+                        atomicAdd(&ph[0], 1ull);
+                        atomicAdd(&ph[1], (unsigned long long)(pc0a - pc0));  // (key, index) pairs of chunk + 2
+                        atomicAdd(&ph[2], (unsigned long long)(pc0b - pc0a)); // wait for the records, take them
+                        atomicAdd(&ph[3], (unsigned long long)(pc1 - pc0b));  // issue the next gather
+                        atomicAdd(&ph[4], (unsigned long long)(pc3 - pc1));   // overlap test + staging
+                        atomicAdd(&ph[5], (unsigned long long)(pc4 - pc3));   // replay
                     }
-                    __syncwarp();
-                    if (wb.tile_clock && lane == 0 && !disjoint) atomicAdd(&wb.tile_clock[2 * (size_t)wb.ntiles + 8], 1ull);
-                    if (disjoint || !__any_sync(0xffffffffu, pend != 0)) break;
+#endif
                 }
-                if (EACH && my_updated != updated_before)
-                    atomicAdd(&p.prim_info[2 * (size_t)src_primitive(wb, p, v.src, v.flags) + 1], my_updated - updated_before);
             }
-            idx = idx_b; idx_b = idx_c;
+            if (!staged) direct_chunk(sm, v, idx, xa, pend, disjoint);
+            idx = idx_b; rb = rc;
         }
 
         // ---- write the strip back ---------------------------------------------------------------
@@ -340,7 +615,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         }
         q += nwarps;
         e0 = e1; e1 = e2; e2 = e3;
-        ik0 = ik1; ik1 = ik2;
+        r0a = r1a; r0b = r1b; r1a = r2a; r1b = r2b;
     }
 
     // UpdatedPixels: one atomic per warp per kernel
@@ -355,6 +630,8 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
 constexpr int SHT = 256;
 __global__ void __launch_bounds__(SHT, 4)
 k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb, uint32_t *__restrict__ gcolor) {
+    pdl_wait();
+    pdl_trigger();
     if (wb.counters->overflow) return;
     const uint32_t nheavy = wb.tile_ctl->nheavy, nbusy = nheavy + wb.tile_ctl->nlight;
     const uint32_t tile_w = (uint32_t)p.tile_w, SPB = SHT / tile_w;  // strips per CTA pass
@@ -434,13 +711,16 @@ int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, ui
                   cudaStream_t st) {
     auto strip_kernel = p.deferred ? (p.prim_info ? k_strip<true, true> : k_strip<true, false>)
                                    : (p.prim_info ? k_strip<false, true> : k_strip<false, false>);
-    const uint32_t per_sm = p.deferred ? 4u : 3u;
+    const uint32_t per_sm = p.deferred ? (uint32_t)FGL_STRIP_MINB : 3u;
     const uint32_t want = (wb.ntiles + SWARPS - 1u) / SWARPS;  // never more warps than strips
     const uint32_t grid = want < wb.nsm * per_sm ? (want ? want : 1u) : wb.nsm * per_sm;
-    strip_kernel<<<grid, STHREADS, 0, st>>>(p, wb, wb.seg_val[sorted_buf], wb.seg_key[sorted_buf], color, depth);
+    const size_t smem = (p.deferred ? sizeof(StripMem<true>) : sizeof(StripMem<false>)) * SWARPS;
+    cudaFuncSetAttribute(strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device, cheap
+    launch_pdl(strip_kernel, grid, STHREADS, smem, st, p, wb, (const uint32_t *)wb.seg_val[sorted_buf],
+               (const uint32_t *)wb.seg_key[sorted_buf], color, depth);
     int launches = 1;
     if (p.deferred && p.state.write_color) {
-        k_shade<<<wb.nsm * 8u, SHT, 0, st>>>(p, wb, color);
+        launch_pdl(k_shade, wb.nsm * 8u, SHT, 0, st, p, wb, color);
         launches++;
     }
     return launches;

@@ -138,6 +138,8 @@ k_radix_hist(const uint32_t *__restrict__ keys, const unsigned int *__restrict__
              uint32_t *__restrict__ hist /*[grid][BINS]*/) {
     constexpr int BINS = 1 << BITS;
     __shared__ uint32_t h[BINS];
+    pdl_wait();
+    pdl_trigger();
     for (int k = threadIdx.x; k < BINS; k += RADIX_THREADS) h[k] = 0;
     __syncthreads();
     const uint32_t n = min(*n_dev, n_max);
@@ -158,6 +160,8 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
                 const uint32_t *__restrict__ hist /*[grid][BINS], raw counts*/) {
     constexpr int BINS = 1 << BITS;
     constexpr int DPT = (BINS + RADIX_THREADS - 1) / RADIX_THREADS;  // digits per thread in the bucket-base scan (1)
+    pdl_wait();
+    pdl_trigger();
     static_assert(DPT == 1, "one digit per thread in the bucket-base scan");
     extern __shared__ uint32_t s_dyn[];
     uint32_t *cursor = s_dyn;                                   // [BINS]
@@ -253,9 +257,9 @@ static int radix_pass(uint32_t *const key[2], uint32_t *const val[2], int cur, c
     const size_t smem = sizeof(uint32_t) * (size_t)BINS * (RADIX_WARPS + 1);
     // per device and cheap: set on every call (a process may drive several GPUs)
     cudaFuncSetAttribute(k_radix_scatter<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_radix_hist<BITS><<<RADIX_GRID, RADIX_THREADS, 0, st>>>(key[cur], n_dev, n_max, shift, tmp);
-    k_radix_scatter<BITS><<<RADIX_GRID, RADIX_THREADS, smem, st>>>(key[cur], val[cur], key[cur ^ 1], val[cur ^ 1], n_dev,
-                                                                  n_max, shift, tmp);
+    launch_pdl(k_radix_hist<BITS>, RADIX_GRID, RADIX_THREADS, 0, st, key[cur], n_dev, n_max, shift, tmp);
+    launch_pdl(k_radix_scatter<BITS>, RADIX_GRID, RADIX_THREADS, smem, st, key[cur], val[cur], key[cur ^ 1], val[cur ^ 1],
+               n_dev, n_max, shift, tmp);
     return 2;
 }
 

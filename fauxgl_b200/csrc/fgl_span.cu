@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(TR_THREADS)
 k_tile_ranges(const uint32_t *__restrict__ keys, const unsigned int *__restrict__ n_dev, uint32_t n_max,
               uint2 *__restrict__ busy_list, uint32_t ntiles, TileCtl *ctl) {
     __shared__ uint32_t s_cnt[2], s_base[2], s_fill[2];
+    pdl_wait();
+    pdl_trigger();
     const uint32_t n = min(*n_dev, n_max);
     const uint32_t lane = threadIdx.x & 31;
     uint32_t per = (n + gridDim.x - 1) / gridDim.x;
@@ -240,8 +242,8 @@ int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cuda
     int bits = 1;
     while ((1u << bits) < wb.ntiles) bits++;
     launches += launch_sort_pairs(wb.seg_key, wb.seg_val, &c->n_segs, wb.cap_segs, bits, wb.scan_tmp, sorted_buf, st);
-    k_tile_ranges<<<148, TR_THREADS, 0, st>>>(wb.seg_key[*sorted_buf], &c->n_segs, wb.cap_segs,
-                                           wb.busy_list, wb.ntiles, wb.tile_ctl);
+    launch_pdl(k_tile_ranges, 148, TR_THREADS, 0, st, wb.seg_key[*sorted_buf], &c->n_segs, wb.cap_segs, wb.busy_list,
+               wb.ntiles, wb.tile_ctl);
     launches++;
     return launches;
 }

@@ -23,7 +23,7 @@ __device__ __forceinline__ SegV make_segv(double w0, double w1, double w2, doubl
     v.w0 = w0; v.w1 = w1; v.w2 = w2; v.ra = ra; v.z0 = z0; v.z1 = z1; v.z2 = z2;
     v.a12 = a12; v.a20 = a20; v.a01 = a01;
     v.r0 = t.r0; v.r1 = t.r1; v.r2 = t.r2; v.src = t.src; v.flags = t.flags;
-    v.x = x; v.yt = 0; v.cnt = cnt; v._pad[0] = v._pad[1] = v._pad[2] = 0;
+    v.x = x; v.yt = 0; v.cnt = cnt; v._pad0 = 0; v._pad[0] = v._pad[1] = 0;
     return v;
 }
 

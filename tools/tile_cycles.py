@@ -35,8 +35,12 @@ nt = st.tiles_x * st.tiles_y
 full = np.zeros((nt + 8, 2), dtype=np.uint64)
 _check(capi().fgl_debug_tile_cycles(ctx._h, full.ctypes.data, nt + 8), ctx._h)
 buf, dbg = full[:nt], full[nt:].ravel()
-print("chunks by path (3 draws): disjoint %d staged %d generic %d; fragments %d / %d / %d; generic rounds %d" % (
-    dbg[0], dbg[1], dbg[2], dbg[4], dbg[5], dbg[6], dbg[8]))
+print("chunks by path (3 draws): disjoint %d staged %d generic %d; fragments %d / %d / %d; generic rounds %d; heavy strips %d" % (
+    dbg[0], dbg[1], dbg[2], dbg[4], dbg[5], dbg[6], dbg[8], dbg[9]))
+if dbg[10]:  # variant built with -DFGL_STRIP_PHASES=1: staged chunks of heavy strips
+    n = float(dbg[10])
+    print("heavy-strip staged chunks %d: cycles per chunk  pairs(c+2) %.0f  records wait+take %.0f  issue next gather %.0f  overlap test + stage %.0f  replay %.0f" % (
+        dbg[10], dbg[11] / n, dbg[12] / n, dbg[13] / n, dbg[14] / n, dbg[15] / n))
 cyc = buf[:, 0].astype(np.int64)
 smid = (buf[:, 1] >> np.uint64(32)).astype(np.int64)
 segs = (buf[:, 1] & np.uint64(0xffffffff)).astype(np.int64)
