@@ -202,7 +202,7 @@ def main():
     hbm_peak, peak_src = load_peaks()
 
     # ---------------- device-resident throughput (value) ----------------
-    def timed_frames(width, height, resolve, steps, warmup, profile):
+    def timed_frames(width, height, resolve, steps, warmup, profile, probe=False):
         ctx = Context(width, height, local_rank)
         ctx.Shader = shader
         dm = DeviceMesh(ctx, mesh, ("position", "normal"))
@@ -243,13 +243,18 @@ def main():
             ctx.SetProfiling(False)
         out = {"ms": ms, "info": info, "records": int(stats.records), "pairs": int(stats.pairs),
                "launches_per_frame": int(launches_per_frame), "clocks": clocks, "stage": st}
+        if probe:   # fragment-rate bound: 64-bit atomicMin on a depth-buffer-sized array of this box
+            out["atomic_ops_per_s"] = ctx.ProbeAtomicRate(1 << 26)
         del dm
         ctx.Close()
         return out
 
-    r1 = timed_frames(W1, H1, 0, K, Wm, True)
+    # `value`: no stage events between the kernels (they would serialise the programmatic dependent launches);
+    # the per-stage times come from a second, shorter pass with the library's stage timers on.
+    r1 = timed_frames(W1, H1, 0, K, Wm, False, probe=(rank == 0))
     ms1 = max_over_ranks(sum(r1["ms"]) / K)
     value = world * T_TRIANGLES / (ms1 / 1e3) / 1e6
+    r1["stage"] = timed_frames(W1, H1, 0, max(3, min(K, 10)), 3, True)["stage"]
 
     def stage_ms(st):
         return {"geometry_ms": st.geometry_ms / st.draws, "spans_ms": st.spans_ms / st.draws,
@@ -260,6 +265,16 @@ def main():
     # 64-byte counter memset before it).  Its algorithmic bytes: the position planes,
     # T * 72 B, read once -- the segments it writes are implementation, not algorithm.
     geo_bytes = T_TRIANGLES * 72
+    frame_fragments = int(r1["info"].TotalPixels // K)   # RasterizeInfo.TotalPixels of one frame (Sync() returns the timed frames' sum)
+    fragment_bound = None
+    if r1.get("atomic_ops_per_s"):
+        f_us = frame_fragments / r1["atomic_ops_per_s"] * 1e6
+        h_us = ALGO_BYTES_C1 / (hbm_peak * 1e9) * 1e6
+        fragment_bound = {"fragments_per_frame": frame_fragments, "atomic_min_u64_per_s": r1["atomic_ops_per_s"],
+                          "bound_us": f_us, "hbm_bound_us": h_us, "slower_bound": "hbm" if h_us >= f_us else "fragment",
+                          "frac_of_slower_bound": max(f_us, h_us) / (ms1 * 1e3),
+                          "primitive": "global 64-bit atomicMin on random words of a 1920x1080 u64 array, measured on this "
+                                       "box (fgl_probe_atomic_rate); the path itself resolves fragments in shared memory"}
     roofline = {
         "bound": "hbm", "kernel": "k_front",
         "achieved": geo_bytes / (stages["geometry_ms"] / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -268,7 +283,7 @@ def main():
         "peak_source": peak_src, "algorithmic_bytes": geo_bytes,
         "frame": {"algorithmic_bytes": ALGO_BYTES_C1, "achieved": ALGO_BYTES_C1 / (ms1 / 1e3) / 1e9,
                   "frac": ALGO_BYTES_C1 / (ms1 / 1e3) / 1e9 / hbm_peak},
-        "stages_ms": stages,
+        "stages_ms": stages, "fragment_bound": fragment_bound,
         "note": "issue/latency-bound float64 replay of the reference's arithmetic, not bandwidth-bound: "
                 "63.6 M warp instructions at 0.55 IPC per scheduler, see profiles/README.md",
     }
@@ -277,11 +292,11 @@ def main():
     ssaa = None
     if not args.no_ssaa:
         K2 = max(3, min(K, 10))
-        r2 = timed_frames(W1 * SSAA, H1 * SSAA, SSAA, K2, 3, True)
+        r2 = timed_frames(W1 * SSAA, H1 * SSAA, SSAA, K2, 3, False)
         ms2 = max_over_ranks(sum(r2["ms"]) / K2)
-        s2 = r2["stage"]
+        s2 = timed_frames(W1 * SSAA, H1 * SSAA, SSAA, 3, 3, True)["stage"]
         ssaa = {"ms_per_frame": ms2, "mtri_s": world * T_TRIANGLES / (ms2 / 1e3) / 1e6, "steps": K2,
-                "total_pixels": int(r2["info"].TotalPixels / (3 + K2)),
+                "total_pixels": int(r2["info"].TotalPixels // K2),
                 "roofline_frac_frame": ALGO_BYTES_C2 / (ms2 / 1e3) / 1e9 / hbm_peak,
                 "stages_ms": stage_ms(s2),
                 "workload": "same mesh at 7680x4320 + 4x4 nfnt-bilinear resolve to 1920x1080"}

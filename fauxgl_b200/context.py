@@ -136,6 +136,7 @@ ABI = [
     ("fgl_ipc_close", C.c_int, [_P, _P, _P]),
     ("fgl_composite_peer", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
     ("fgl_debug_tile_cycles", C.c_int, [_P, _P, C.c_uint64]),
+    ("fgl_probe_atomic_rate", C.c_int, [_P, C.c_uint64, C.POINTER(C.c_double)]),
     ("fgl_stream", _P, [_P]),
     ("fgl_color_device_ptr", _P, [_P]),
     ("fgl_depth_device_ptr", _P, [_P]),
@@ -536,6 +537,13 @@ class Context:
         s = DrawStats()
         _check(capi().fgl_get_draw_stats(self._h, C.byref(s)), self._h)
         return s
+
+    def ProbeAtomicRate(self, ops: int = 1 << 26) -> float:
+        """64-bit atomicMin operations per second on a depth-buffer-sized array of this device: the
+        denominator of the fragment-rate bound (see include/fauxgl_b200.h)."""
+        r = C.c_double(0)
+        _check(capi().fgl_probe_atomic_rate(self._h, int(ops), C.byref(r)), self._h)
+        return float(r.value)
 
     # -- SSAA resolve (resize.Resize(..., resize.Bilinear) in the examples) -------------
     def Resolve(self, factor: int) -> np.ndarray:

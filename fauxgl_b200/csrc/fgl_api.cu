@@ -1234,6 +1234,37 @@ int fgl_debug_tile_cycles(fgl_ctx *c, uint64_t *dst, uint64_t ntiles) {
     return FGL_OK;
 }
 
+int fgl_probe_atomic_rate(fgl_ctx *c, uint64_t ops, double *ops_per_second) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!ops_per_second || ops == 0) return fail(c, FGL_E_INVALID, "null result pointer / zero operations");
+    std::lock_guard<std::mutex> lock(c->mu);
+    const size_t words = (size_t)c->w * c->h;
+    unsigned long long *buf = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = dev_alloc(&buf, words);
+    if (e == cudaSuccess) e = cudaMemsetAsync(buf, 0xff, words * sizeof(unsigned long long), c->stream);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    float ms = 0;
+    if (e == cudaSuccess) {
+        launch_atomic_probe(buf, words, ops / 8 + 1, c->stream);  // warm-up
+        cudaEventRecord(e0, c->stream);
+        launch_atomic_probe(buf, words, ops, c->stream);
+        cudaEventRecord(e1, c->stream);
+        e = cudaEventSynchronize(e1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    dev_free(buf);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(c, FGL_E_CUDA, "atomic probe: %s", cudaGetErrorString(e)); }
+    const unsigned long long threads = 148ull * 8ull * 256ull;
+    const unsigned long long done = (ops + threads - 1) / threads * threads;
+    *ops_per_second = ms > 0 ? (double)done / ((double)ms * 1e-3) : 0.0;
+    return FGL_OK;
+}
+
 void *fgl_stream(const fgl_ctx *c) { return c ? (void *)c->stream : nullptr; }
 void *fgl_color_device_ptr(const fgl_ctx *c) { return c ? (void *)c->color : nullptr; }
 void *fgl_depth_device_ptr(const fgl_ctx *c) { return c ? (void *)c->depth : nullptr; }

@@ -790,10 +790,13 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     const uint32_t rec_off = (uint32_t)((s_scan[warp] + incl - mine) & NREC_MASK);
     const unsigned long long block_total = s_scan[FT / 32];
     const uint32_t nrec_blk = (uint32_t)(block_total & NREC_MASK);
-    if (tid == 0) s_region = nrec_blk ? atomicAdd(&wb.counters->seg_cursor, block_total >> CELL_SHIFT) : 0ull;
+    // The reservation's round trip is not waited for here: thread 0 keeps the old cursor in a register and hands it
+    // to the block just before the first compaction barrier below, a scan and a row walk later.
+    unsigned long long my_region = 0;
+    if (tid == 0 && nrec_blk) my_region = atomicAdd(&wb.counters->seg_cursor, block_total >> CELL_SHIFT);
     if (!general && n == 1) s_order[rec_off] = (uint16_t)tid;
     __syncthreads();
-    const unsigned long long region = s_region;
+    unsigned long long region = 0;
 
     // ---- spans: FT records per window, FT (record, scanline) items per pass --------------------------------
     uint32_t seg_run = 0;  // segments this block has stored so far (block-uniform)
@@ -834,7 +837,9 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                     atomicAdd(&p.prim_info[2 * (size_t)src_primitive(wb, p, r.src, r.flags)], covered - before);
             }
             uint32_t chunk_total;
+            if (tid == 0) s_region = my_region;
             const uint32_t ex = block_excl_scan1<FT>(nseg, s_scan32, scan_parity, &chunk_total);
+            region = s_region;
             if (nseg) {
                 const unsigned long long slot64 = region + seg_run + ex;
                 const SRec &r = s_rec[ridx];
@@ -864,7 +869,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     // ---- publish; the last block scans the aggregates ---------------------------------------------------
     if (tid == 0) {
         wb.blk_agg[vb] = ((unsigned long long)seg_run << 32) | nrec_blk;
-        wb.blk_region[vb] = (uint32_t)min(region, 0xffffffffull);
+        wb.blk_region[vb] = (uint32_t)min(my_region, 0xffffffffull);
         __threadfence();
         s_last = atomicAdd(&wb.counters->blocks_done, 1u) == nblocks - 1u;
     }

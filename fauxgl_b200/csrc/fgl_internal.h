@@ -260,6 +260,8 @@ int launch_composite_pack(const uint32_t *color, const double *depth, unsigned l
 int launch_composite_unpack(uint32_t *color, double *depth, const unsigned long long *keys, size_t npix,
                             cudaStream_t st);
 int launch_composite_min(unsigned long long *inout, const unsigned long long *other, size_t n, cudaStream_t st);
+// `ops` 64-bit atomicMin on pseudo-random words of buf[0..words) (fgl_probe_atomic_rate)
+int launch_atomic_probe(unsigned long long *buf, size_t words, unsigned long long ops, cudaStream_t st);
 int launch_composite_peer(uint32_t *const *color, double *const *depth, int nranks, size_t px0, size_t px1,
                           cudaStream_t st);
 

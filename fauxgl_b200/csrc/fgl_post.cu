@@ -244,4 +244,23 @@ int launch_composite_min(unsigned long long *inout, const unsigned long long *ot
     return 1;
 }
 
+// ---- fragment-rate probe ---------------------------------------------------------------------------------
+// Every thread issues atomicMin(u64) on pseudo-random words (a 64-bit LCG per thread, so neighbouring lanes hit
+// unrelated addresses, like fragments of unrelated triangles), with the depth-like key decreasing slowly so that a
+// share of the operations actually writes.
+__global__ void __launch_bounds__(256)
+k_atomic_probe(unsigned long long *__restrict__ buf, size_t words, unsigned long long ops_per_thread) {
+    unsigned long long x = 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1ull);
+    for (unsigned long long k = 0; k < ops_per_thread; k++) {
+        x = x * 6364136223846793005ull + 1442695040888963407ull;
+        const size_t w = (size_t)((x >> 20) % words);
+        atomicMin(&buf[w], (x >> 1) | 1ull);
+    }
+}
+int launch_atomic_probe(unsigned long long *buf, size_t words, unsigned long long ops, cudaStream_t st) {
+    const unsigned threads = 148u * 8u * 256u;
+    k_atomic_probe<<<148 * 8, 256, 0, st>>>(buf, words, (ops + threads - 1) / threads);
+    return 1;
+}
+
 }  // namespace fgl

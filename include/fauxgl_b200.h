@@ -278,6 +278,14 @@ int fgl_composite_peer(fgl_ctx *ctx, int rank, int nranks, void *const *color, v
  * dst receives 2*ntiles uint64 (ntiles = tiles_x * tiles_y of fgl_draw_stats). */
 int fgl_debug_tile_cycles(fgl_ctx *ctx, uint64_t *dst, uint64_t ntiles);
 
+/* Fragment-rate bound of the roofline: the reference resolves every fragment with a locked
+ * read-modify-write of DepthBuffer[i] (context.go:245-273); the device primitive that could replace it one
+ * fragment at a time is a 64-bit atomicMin on a packed (depth, colour) key.  This measures that primitive on the
+ * context's device: `ops` atomicMin on uniformly random words of a buffer of width*height uint64 (the depth buffer's
+ * footprint), timed with CUDA events; *ops_per_second receives the rate.  The path itself does not use global
+ * atomics per fragment (strips resolve in shared memory); the figure is the denominator of bound (b). */
+int fgl_probe_atomic_rate(fgl_ctx *ctx, uint64_t ops, double *ops_per_second);
+
 /* Interop for the host harness (timing with CUDA events on the launching
  * stream; zero-copy views of the buffers). */
 void *fgl_stream(const fgl_ctx *ctx);            /* cudaStream_t */
