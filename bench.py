@@ -220,7 +220,7 @@ def main():
             frame()
         info = ctx.Sync()
         stats = ctx.DrawStats()
-        launches_per_frame = 2 + stats.kernel_launches + 1 + (1 if resolve else 0)
+        launches_per_frame = 2 + stats.kernel_launches + (1 if resolve else 0)   # clears + the async draw (+ resolve)
         if profile:
             ctx.SetProfiling(True)
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]

@@ -246,13 +246,7 @@ void mesh_release(fgl_ctx *c, const fgl_mesh *cm) {
 
 __global__ void k_accumulate(const DrawCounters *cur, DrawCounters *acc) {
     pdl_wait();
-    acc->total_pixels += cur->total_pixels;
-    acc->updated_pixels += cur->updated_pixels;
-    acc->overflow |= cur->overflow;
-    acc->need_records = max(acc->need_records, cur->need_records);
-    acc->need_rows = max(acc->need_rows, cur->need_rows);
-    acc->need_segs = max(acc->need_segs, cur->need_segs);
-    acc->need_clip = max(acc->need_clip, cur->need_clip);
+    accumulate_counters(cur, acc);
 }
 
 int build_params(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const fgl_mesh *mesh, uint64_t first,
@@ -345,7 +339,7 @@ bool use_fused_front(const fgl_ctx *c, const DrawParams &p) {
     return p.count >= FUSED_MIN_PRIMS;
 }
 
-int enqueue_draw(fgl_ctx *c, const DrawParams &p) {
+int enqueue_draw(fgl_ctx *c, const DrawParams &p, bool async) {
     int launches = 0;
     ProfSlot *ps = nullptr;
     if (c->profiling) {
@@ -371,7 +365,12 @@ int enqueue_draw(fgl_ctx *c, const DrawParams &p) {
     launches += launch_bin(p, c->wb, &sorted, c->stream);
     if (ps) cudaEventRecord(ps->e[3], c->stream);
     fb_join(c);  // the front end and the binning ran beside a pending clear; the strips need the framebuffer
-    launches += launch_raster(p, c->wb, sorted, c->color, c->depth, c->stream);
+    bool accumulated = false;
+    launches += launch_raster(p, c->wb, sorted, c->color, c->depth, async ? c->acc_dev : nullptr, &accumulated, c->stream);
+    if (async && !accumulated) {  // (the deferred-shading kernel does it on the way, other paths need the extra launch)
+        launch_pdl(k_accumulate, 1, 1, 0, c->stream, (const DrawCounters *)c->wb.counters, c->acc_dev);
+        launches++;
+    }
     if (ps) cudaEventRecord(ps->e[4], c->stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(c, FGL_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
@@ -423,15 +422,14 @@ int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const 
     if (rc) return rc;
     mesh_acquire(c, mesh);
     if (async) {
-        rc = enqueue_draw(c, p);
+        rc = enqueue_draw(c, p, true);
         if (rc) return rc;
-        launch_pdl(k_accumulate, 1, 1, 0, c->stream, (const DrawCounters *)c->wb.counters, c->acc_dev);
         mesh_release(c, mesh);
         c->async_pending = true;
         return FGL_OK;
     }
     for (int attempt = 0; attempt < 6; attempt++) {
-        rc = enqueue_draw(c, p);
+        rc = enqueue_draw(c, p, false);
         if (rc) return rc;
         CK(c, cudaMemcpyAsync(c->host_counters, c->wb.counters, sizeof(DrawCounters), cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));

@@ -924,8 +924,8 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
 }
 
 // Segments in primitive order for the stable sort: position blk_base[b] + k  <-  slot blk_region[b] + k.
-// One thread per ordered position; its block is found by binary search in blk_base (a few thousand entries,
-// cache resident).
+// One warp per block of the front end: three loads tell it where its segments are, then it copies them with
+// coalesced reads and writes (no per-position search for the block).
 __global__ void __launch_bounds__(256)
 k_seg_index(const __grid_constant__ WorkBuffers wb, uint32_t nent) {
     pdl_wait();
@@ -933,15 +933,17 @@ k_seg_index(const __grid_constant__ WorkBuffers wb, uint32_t nent) {
     const DrawCounters *ctr = wb.counters;
     if (ctr->overflow) return;
     const uint32_t n = min(ctr->n_segs, wb.cap_segs);
-    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
-        uint32_t lo = 0, hi = nent;  // blk_base[lo] <= pos < blk_base[hi]  (blk_base[nent] = n, never read)
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if ((uint32_t)__ldg(&wb.blk_base[mid]) <= pos) lo = mid; else hi = mid;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nent; b += nwarps) {
+        const uint32_t cnt = (uint32_t)(wb.blk_agg[b] >> 32), base = (uint32_t)wb.blk_base[b], region = wb.blk_region[b];
+        for (uint32_t k = lane; k < cnt; k += 32u) {
+            const uint32_t pos = base + k, slot = region + k;
+            if (pos < n) {
+                wb.seg_key[0][pos] = wb.seg_key[1][slot];
+                wb.seg_val[0][pos] = slot;
+            }
         }
-        const uint32_t slot = wb.blk_region[lo] + (pos - (uint32_t)wb.blk_base[lo]);
-        wb.seg_key[0][pos] = wb.seg_key[1][slot];
-        wb.seg_val[0][pos] = slot;
     }
 }
 

@@ -128,7 +128,8 @@ struct DrawCounters {
     unsigned long long total_pixels, updated_pixels;
     unsigned int n_records, n_rows, n_segs, n_clip;
     unsigned int overflow;  // bit0 records, bit1 rows, bit2 clip pool, bit3 segments
-    unsigned int need_records, need_rows, need_segs, need_clip, _pad;
+    unsigned int need_records, need_rows, need_segs, need_clip;
+    unsigned int shade_done;   // CTAs of k_shade that have finished (the last one accumulates the frame's counters)
     unsigned int rec_cursor;   // geometry stage: next free record slot (regions are handed out per block)
     unsigned int blocks_done;  // geometry stage: blocks that have published their aggregate
     unsigned long long seg_cursor;  // fused front end: next free segment slot (regions are handed out per block)
@@ -245,8 +246,20 @@ int launch_front(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
 int launch_seg_index(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
 int launch_spans(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
 int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
+// acc (nullable): counters of the frame's async draws; *accumulated tells whether the draw's counters were added
+// to it by the last kernel (k_shade's last CTA) -- otherwise the caller launches k_accumulate
 int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,
-                  cudaStream_t st);
+                  DrawCounters *acc, bool *accumulated, cudaStream_t st);
+// acc += cur (total/updated pixels, overflow, needs): one thread
+__device__ __forceinline__ void accumulate_counters(const DrawCounters *cur, DrawCounters *acc) {
+    acc->total_pixels += cur->total_pixels;
+    acc->updated_pixels += cur->updated_pixels;
+    acc->overflow |= cur->overflow;
+    acc->need_records = max(acc->need_records, cur->need_records);
+    acc->need_rows = max(acc->need_rows, cur->need_rows);
+    acc->need_segs = max(acc->need_segs, cur->need_segs);
+    acc->need_clip = max(acc->need_clip, cur->need_clip);
+}
 
 // binary STL records (50 B each) -> position / normal planes, stl.go:86-154
 int launch_stl_ingest(const uint8_t *records, double *pos, double *nrm, uint32_t n, cudaStream_t st);

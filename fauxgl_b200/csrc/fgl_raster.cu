@@ -50,12 +50,17 @@
 
 namespace fgl {
 
-// CTAs per SM of the deferred strip kernel.  3 (80 registers) rather than 4 (64): at 64 the compiler spills values
-// that were just loaded, and a spill store is a consumer -- it waits for the load the pipeline wanted to leave in
-// flight (heaviest strip of the benchmark frame 69.5 k -> 42.4 k cycles, strip stage 78 -> 66 us at 1080p).
+// CTAs per SM of the deferred strip kernel.  At 4 (64 registers) the compiler spills values that were just loaded,
+// and a spill store is a consumer -- it waits for the load the pipeline wanted to leave in flight (heaviest strip of
+// the benchmark frame 69.5 k cycles at 4 CTAs/SM, 42.4 k at 3; k_strip 36.7 us at 3, 28.7 us at 2 with no spill at all;
+// at 7680x4320, where the kernel is throughput-bound, 2 and 3 measure the same).
 #ifndef FGL_STRIP_MINB
-#define FGL_STRIP_MINB 3
+#define FGL_STRIP_MINB 2
 #endif
+#ifndef FGL_HEAVY_SKIP
+#define FGL_HEAVY_SKIP 3  // rounds a warp sits out after a heavy strip (strip stage at 1080p: 74 / 68 / 64 us for 0 / 2 / 3)
+#endif
+constexpr uint32_t HEAVY_SKIP = FGL_HEAVY_SKIP;
 #ifndef FGL_COOP_FACTOR
 #define FGL_COOP_FACTOR 1  // heavy strips go to whole CTAs while there are at most this many per CTA
 #endif
@@ -467,20 +472,31 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     // Dealt out round-robin over all warps of the grid.  The strip loop is software-pipelined so that no dependent
     // load is waited for: while strip t is processed, the list entry of t+3, the first 32 (segment, key) pairs of
     // t+2 and an L2 prefetch of the first segments and the depth row of t+1 are in flight.
-    const uint32_t nwarps = gridDim.x * SWARPS;
-    uint32_t q = light0 + blockIdx.x * SWARPS + (uint32_t)warp;
+    const uint32_t nwarps = gridDim.x * SWARPS, gw = blockIdx.x * SWARPS + (uint32_t)warp;
+    // The t-th strip of this warp.  Plain round-robin over the list -- except that a warp whose first strip is a
+    // heavy one (list positions < nheavy) sits out the next HEAVY_SKIP rounds: a heavy bin costs several average
+    // ones, and with equal counts those warps were the kernel's tail (heaviest strip 21 us + three more strips).
+    const bool weighted = light0 == 0 && nheavy > 0 && nheavy < nwarps;
+    auto qpos = [&](uint32_t t) -> uint32_t {
+        if (!weighted) return light0 + gw + t * nwarps;
+        const uint32_t wl = nwarps - nheavy;  // warps without a heavy strip
+        if (gw < nheavy) return t == 0 ? gw : nheavy + (HEAVY_SKIP + 1u) * wl + (t - 1u) * nwarps + gw;
+        return t <= HEAVY_SKIP ? nheavy + t * wl + (gw - nheavy)
+                               : nheavy + (HEAVY_SKIP + 1u) * wl + (t - HEAVY_SKIP - 1u) * nwarps + gw;
+    };
+    uint32_t t_strip = 0, q = qpos(0);
     // list entries are loaded raw as well (index clamped, validity from the position)
     auto load_entry = [&](uint32_t qq) { return busy_at(wb, nheavy, min(qq, nbusy ? nbusy - 1u : 0u)); };
-    uint2 e0 = load_entry(q), e1 = load_entry(q + nwarps), e2 = load_entry(q + 2 * nwarps);
+    uint2 e0 = load_entry(q), e1 = load_entry(qpos(1)), e2 = load_entry(qpos(2));
     // the first 64 pairs of strips t and t+1 (a = positions 0..31, b = 32..63)
     uint2 r0a = load_raw(e0.y + lane), r0b = load_raw(e0.y + 32 + lane);
     uint2 r1a = load_raw(e1.y + lane), r1b = load_raw(e1.y + 32 + lane);
     if constexpr (DEFERRED) gather_issue(sm.recbuf, wb.segv, q < nbusy ? pair_idx(e0.x, r0a) : NO_SEG, lane);
     while (q < nbusy) {
         const uint32_t strip = e0.x, bin_beg = e0.y;
-        const uint32_t strip1 = q + nwarps < nbusy ? e1.x : 0xffffffffu;  // the warp's next strip
+        const uint32_t strip1 = qpos(t_strip + 1) < nbusy ? e1.x : 0xffffffffu;  // the warp's next strip
         // pipeline: entry of t+3, pairs of t+2, prefetch of t+1
-        const uint2 e3 = load_entry(q + 3 * nwarps);
+        const uint2 e3 = load_entry(qpos(t_strip + 3));
         const uint2 r2a = load_raw(e2.y + lane), r2b = load_raw(e2.y + 32 + lane);
         if constexpr (!DEFERRED) {
             const uint32_t ik1 = pair_idx(strip1, r1a);
@@ -613,7 +629,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             wb.tile_clock[2 * strip] = (unsigned long long)(clock64() - t_begin);
             wb.tile_clock[2 * strip + 1] = ((unsigned long long)smid << 32) | nseg;
         }
-        q += nwarps;
+        q = qpos(++t_strip);
         e0 = e1; e1 = e2; e2 = e3;
         r0a = r1a; r0b = r1b; r1a = r2a; r1b = r2b;
     }
@@ -629,11 +645,13 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
 // ObjectColor and no texture (fgl_api.cu), so the attribute set is fixed: 9 normal + 9 position components.
 constexpr int SHT = 256;
 __global__ void __launch_bounds__(SHT, 4)
-k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb, uint32_t *__restrict__ gcolor) {
+k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb, uint32_t *__restrict__ gcolor,
+        DrawCounters *acc) {
     pdl_wait();
     pdl_trigger();
-    if (wb.counters->overflow) return;
-    const uint32_t nheavy = wb.tile_ctl->nheavy, nbusy = nheavy + wb.tile_ctl->nlight;
+    const uint32_t nheavy = wb.tile_ctl->nheavy;
+    // (work buffers too small: nothing to shade, but the overflow flag still has to reach the frame's counters)
+    const uint32_t nbusy = wb.counters->overflow ? 0u : nheavy + wb.tile_ctl->nlight;
     const uint32_t tile_w = (uint32_t)p.tile_w, SPB = SHT / tile_w;  // strips per CTA pass
     const int pix = (int)(threadIdx.x % tile_w);
     for (uint32_t q = blockIdx.x * SPB + threadIdx.x / tile_w; q < nbusy; q += gridDim.x * SPB) {
@@ -705,10 +723,19 @@ k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         r = c4(go_min(r.r, 1), go_min(r.g, 1), go_min(r.b, 1), color.a);
         *out = c_nrgba(r);  // SetNRGBA, context.go:269 (blending excluded by the mode)
     }
+    // Async draws: the last CTA to finish adds the draw's counters to the frame's (this was a kernel of its own).
+    if (acc) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&wb.counters->shade_done, 1u) == gridDim.x - 1u) accumulate_counters(wb.counters, acc);
+        }
+    }
 }
 
 int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,
-                  cudaStream_t st) {
+                  DrawCounters *acc, bool *accumulated, cudaStream_t st) {
+    *accumulated = false;
     auto strip_kernel = p.deferred ? (p.prim_info ? k_strip<true, true> : k_strip<true, false>)
                                    : (p.prim_info ? k_strip<false, true> : k_strip<false, false>);
     const uint32_t per_sm = p.deferred ? (uint32_t)FGL_STRIP_MINB : 3u;
@@ -720,7 +747,8 @@ int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, ui
                (const uint32_t *)wb.seg_key[sorted_buf], color, depth);
     int launches = 1;
     if (p.deferred && p.state.write_color) {
-        launch_pdl(k_shade, wb.nsm * 8u, SHT, 0, st, p, wb, color);
+        launch_pdl(k_shade, wb.nsm * 8u, SHT, 0, st, p, wb, color, acc);
+        *accumulated = acc != nullptr;
         launches++;
     }
     return launches;
