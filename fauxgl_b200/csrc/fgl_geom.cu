@@ -691,6 +691,26 @@ __device__ __noinline__ void emit_general_smem(const DrawParams &p, const WorkBu
     else process_triangle(p, e, prim);
 }
 
+// Conservative back-face filter for triangles inside the view volume (all w > 0).  The reference culls on the sign
+// of a = (ndc1.X-ndc0.X)*(ndc2.Y-ndc0.Y) - (ndc2.X-ndc0.X)*(ndc1.Y-ndc0.Y) computed in float64 from the divided
+// coordinates (context.go:318-336).  In real arithmetic a = D / (w0 w1 w2) with D = det[(x0 y0 w0)(x1 y1 w1)(x2 y2 w2)];
+// |ndc| <= 1 bounds the rounding error of the computed a by ~50 ulp(1) = 5.6e-15, and the error of D evaluated
+// below by ~8 ulp of M, the same sum with absolute values.  So when s*D < -(1e-12 w0 w1 w2 + 1e-14 M), s = +-1 the
+// orientation the state culls, the reference's a has the culled sign for certain and the nine divisions, the
+// screen transform and the set-up can be skipped; every other triangle (and any NaN/Inf) takes the full path, whose
+// arithmetic decides.  Whole warps of back-facing triangles (they come in runs) then cost a few multiplications.
+FGL_DI bool surely_culled(const DrawParams &p, const V4 *o) {
+    if (p.state.cull == FGL_CULL_NONE) return false;
+    const double p1 = o[1].y * o[2].w, p2 = o[2].y * o[1].w, p3 = o[1].x * o[2].w, p4 = o[2].x * o[1].w;
+    const double p5 = o[1].x * o[2].y, p6 = o[2].x * o[1].y;
+    double d = (o[0].x * (p1 - p2) - o[0].y * (p3 - p4)) + o[0].w * (p5 - p6);
+    const double m = (fabs(o[0].x) * (fabs(p1) + fabs(p2)) + fabs(o[0].y) * (fabs(p3) + fabs(p4))) +
+                     fabs(o[0].w) * (fabs(p5) + fabs(p6));
+    const double w = o[0].w * o[1].w * o[2].w;
+    if ((p.state.cull == FGL_CULL_FRONT) != (p.state.front_face == FGL_FACE_CW)) d = -d;
+    return w > 0 && d < -(1e-12 * w + 1e-14 * m);
+}
+
 #ifndef FGL_FRONT_MINB
 #define FGL_FRONT_MINB 6
 #endif
@@ -734,6 +754,8 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             }
             if (outside) {
                 slow = true;
+            } else if (surely_culled(p, o)) {
+                // (n stays 0: the reference computes a signed area that is provably on the culled side)
             } else {  // drawClippedTriangle, context.go:316-341
                 V3 ndc0 = v3(o[0].x / o[0].w, o[0].y / o[0].w, o[0].z / o[0].w);
                 V3 ndc1 = v3(o[1].x / o[1].w, o[1].y / o[1].w, o[1].z / o[1].w);
