@@ -105,6 +105,7 @@ ABI = [
     ("fgl_mesh_counts", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("fgl_mesh_transform", C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     ("fgl_mesh_read", C.c_int, [_P, _P, _P, _P, _P, _P]),
+    ("fgl_mesh_smooth_normals", C.c_int, [_P, _P]),
     ("fgl_texture_create", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     ("fgl_texture_destroy", C.c_int, [_P]),
     ("fgl_draw_triangles", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64, C.POINTER(_Info)]),
@@ -316,6 +317,10 @@ class DeviceMesh:
         """Mesh.Transform on the device (mesh.go:167-175)."""
         m = (C.c_double * 16)(*matrix)
         _check(capi().fgl_mesh_transform(self.ctx._h, self.handle, m), self.ctx._h)
+
+    def SmoothNormals(self):
+        """Mesh.SmoothNormals on the device (mesh.go:105-120), bit-identical to the host mirror."""
+        _check(capi().fgl_mesh_smooth_normals(self.ctx._h, self.handle), self.ctx._h)
 
     def read(self):
         pos = np.empty((self.num_triangles, 3, 3)); nrm = np.empty((self.num_triangles, 3, 3))

@@ -832,6 +832,42 @@ int fgl_mesh_transform(fgl_ctx *c, fgl_mesh *m, const double matrix[16]) {
     return FGL_OK;
 }
 
+int fgl_mesh_smooth_normals(fgl_ctx *c, fgl_mesh *m) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!m) return fail(c, FGL_E_INVALID, "null mesh");
+    if (m->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on another device");
+    if (m->nt == 0) return FGL_OK;
+    if (m->nt > 0x55555555ull) return fail(c, FGL_E_INVALID, "mesh too large for 32-bit corner indices");
+    std::lock_guard<std::mutex> lock(c->mu);
+    const uint32_t n = (uint32_t)m->nt, nc = 3u * n;
+    uint32_t *key[2] = {nullptr, nullptr}, *val[2] = {nullptr, nullptr}, *tmp = nullptr;
+    unsigned int *n_dev = nullptr;
+    cudaError_t e = dev_alloc(&key[0], nc);
+    if (e == cudaSuccess) e = dev_alloc(&key[1], nc);
+    if (e == cudaSuccess) e = dev_alloc(&val[0], nc);
+    if (e == cudaSuccess) e = dev_alloc(&val[1], nc);
+    if (e == cudaSuccess) e = dev_alloc(&tmp, scan_tmp_words(nc));
+    if (e == cudaSuccess) e = dev_alloc(&n_dev, 1);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(n_dev, &nc, sizeof nc, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        mesh_acquire(c, m);
+        launch_corner_hash(m->tpos, n, key[0], val[0], c->stream);
+        int sorted = 0;
+        launch_sort_pairs(key, val, n_dev, nc, 32, tmp, &sorted, c->stream);
+        launch_smooth_groups(key[sorted], val[sorted], m->tpos, m->tnrm, n, c->stream);
+        mesh_release(c, m);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // the temporaries are freed below
+    }
+    dev_free(key[0]); dev_free(key[1]); dev_free(val[0]); dev_free(val[1]); dev_free(tmp); dev_free(n_dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, e == cudaErrorMemoryAllocation ? FGL_E_OOM : FGL_E_CUDA, "smooth normals: %s", cudaGetErrorString(e));
+    }
+    return FGL_OK;
+}
+
 static int read_attr(fgl_ctx *c, const double *planes, double *host, uint64_t n, int nverts, int ncomp) {
     if (!host || n == 0) return FGL_OK;
     double *staging = nullptr;

@@ -147,4 +147,84 @@ int launch_depth_image(const double *depth, size_t npix, uint16_t *out, unsigned
     return 2;
 }
 
+// ---- Mesh.SmoothNormals, mesh.go:105-120 ----------------------------------------------------------
+// Corner c = 3 t + v (the order the reference's loops visit them: t0.V1, t0.V2, t0.V3, t1.V1, ...).
+FGL_DI V3 corner_position(const double *__restrict__ pos, uint32_t n, uint32_t c) {
+    const uint32_t t = c / 3u, v = c % 3u;
+    // (+ 0.0: -0 -> +0, the two are the same map key in Go)
+    return v3(pos[(size_t)(v * 3 + 0) * n + t] + 0.0, pos[(size_t)(v * 3 + 1) * n + t] + 0.0, pos[(size_t)(v * 3 + 2) * n + t] + 0.0);
+}
+FGL_DI bool same_position(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }  // NaN: never
+__global__ void __launch_bounds__(256)
+k_corner_hash(const double *__restrict__ pos, uint32_t n, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const uint32_t nc = 3u * n;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+        const V3 p = corner_position(pos, n, c);
+        unsigned long long h = 0x9E3779B97F4A7C15ull;
+        const unsigned long long w[3] = {(unsigned long long)__double_as_longlong(p.x), (unsigned long long)__double_as_longlong(p.y),
+                                         (unsigned long long)__double_as_longlong(p.z)};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {  // splitmix64-style mixing of the three bit patterns
+            h ^= w[k] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+            h = (h ^ (h >> 30)) * 0xBF58476D1CE4E5B9ull;
+            h = (h ^ (h >> 27)) * 0x94D049BB133111EBull;
+            h ^= h >> 31;
+        }
+        keys[c] = (uint32_t)(h >> 32);
+        vals[c] = c;
+    }
+}
+// One thread per sorted pair.  The pairs of one position are contiguous up to hash collisions and, the sort being
+// stable, in corner order.  (Go map semantics for the key: +0 == -0; a NaN component makes the key unfindable.)
+// The first corner of a position (no equal position earlier in its hash run) is the
+// group's leader: it adds the members' normals in order, starting from zero like `lookup[k].Add(n)` on an empty map
+// entry, normalises (vector.go:83-86) and stores the result to every member.  A corner's normal is read and written
+// by its own leader only, so the update is in place.
+__global__ void __launch_bounds__(256)
+k_smooth_groups(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, const double *__restrict__ pos,
+                double *__restrict__ nrm, uint32_t n) {
+    const uint32_t nc = 3u * n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
+        const uint32_t key = keys[i];
+        const V3 p = corner_position(pos, n, vals[i]);
+        if (p.x != p.x || p.y != p.y || p.z != p.z) {
+            // a NaN position is a map key that is never found again: lookup[t.V1.Position] yields the zero Vector
+            const uint32_t c = vals[i], t = c / 3u, v = c % 3u;
+            nrm[(size_t)(v * 3 + 0) * n + t] = 0; nrm[(size_t)(v * 3 + 1) * n + t] = 0; nrm[(size_t)(v * 3 + 2) * n + t] = 0;
+            continue;
+        }
+        bool leader = true;
+        for (uint32_t j = i; j > 0 && keys[j - 1] == key; j--)
+            if (same_position(corner_position(pos, n, vals[j - 1]), p)) { leader = false; break; }
+        if (!leader) continue;
+        V3 acc = v3(0, 0, 0);
+        for (uint32_t j = i; j < nc && keys[j] == key; j++) {
+            const uint32_t c = vals[j];
+            if (j != i && !same_position(corner_position(pos, n, c), p)) continue;
+            const uint32_t t = c / 3u, v = c % 3u;
+            acc = v_add(acc, v3(nrm[(size_t)(v * 3 + 0) * n + t], nrm[(size_t)(v * 3 + 1) * n + t], nrm[(size_t)(v * 3 + 2) * n + t]));
+        }
+        const V3 r = v_normalize(acc);
+        for (uint32_t j = i; j < nc && keys[j] == key; j++) {
+            const uint32_t c = vals[j];
+            if (j != i && !same_position(corner_position(pos, n, c), p)) continue;
+            const uint32_t t = c / 3u, v = c % 3u;
+            nrm[(size_t)(v * 3 + 0) * n + t] = r.x;
+            nrm[(size_t)(v * 3 + 1) * n + t] = r.y;
+            nrm[(size_t)(v * 3 + 2) * n + t] = r.z;
+        }
+    }
+}
+int launch_corner_hash(const double *pos, uint32_t n, uint32_t *keys, uint32_t *vals, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_corner_hash<<<148 * 8, 256, 0, st>>>(pos, n, keys, vals);
+    return 1;
+}
+int launch_smooth_groups(const uint32_t *keys, const uint32_t *vals, const double *pos, double *nrm, uint32_t n,
+                         cudaStream_t st) {
+    if (n == 0) return 0;
+    k_smooth_groups<<<148 * 8, 256, 0, st>>>(keys, vals, pos, nrm, n);
+    return 1;
+}
+
 }  // namespace fgl

@@ -261,6 +261,11 @@ __device__ __forceinline__ void accumulate_counters(const DrawCounters *cur, Dra
     acc->need_clip = max(acc->need_clip, cur->need_clip);
 }
 
+// Mesh.SmoothNormals, mesh.go:105-120: (hash, corner) pairs of the 3n corners, then -- on the pairs sorted by hash --
+// the group sums in corner order, written to every member
+int launch_corner_hash(const double *pos, uint32_t n, uint32_t *keys, uint32_t *vals, cudaStream_t st);
+int launch_smooth_groups(const uint32_t *keys, const uint32_t *vals, const double *pos, double *nrm, uint32_t n,
+                         cudaStream_t st);
 // binary STL records (50 B each) -> position / normal planes, stl.go:86-154
 int launch_stl_ingest(const uint8_t *records, double *pos, double *nrm, uint32_t n, cudaStream_t st);
 // bounding box of position planes: bounds[0..2] = ordered-u64 min, [3..5] = max (see fgl_post.cu)

@@ -209,6 +209,9 @@ class Mesh:
                     keep = dot >= threshold
                     acc = np.where(keep[:, None], acc + x, acc)
                 out[members[:, i]] = _normalize_rows(acc)
+        # a position with a NaN component is a map key that is never found again: the corner's list is nil and
+        # Vector{}.Normalize() = 0 * (1/0) = NaN (mesh.go:80-88)
+        out[np.isnan(self.position.reshape(-1, 3)).any(axis=1)] = np.nan
         self.normal = out.reshape(-1, 3, 3)
         self.generation += 1
 
@@ -226,6 +229,9 @@ class Mesh:
             acc = _normalize_rows(acc)
             for i in range(k):
                 out[members[:, i]] = acc
+        # a position with a NaN component is a map key that is never found again (NaN != NaN): the final
+        # lookup[t.V1.Position] returns the zero Vector (mesh.go:115-119)
+        out[np.isnan(self.position.reshape(-1, 3)).any(axis=1)] = 0.0
         self.normal = out.reshape(-1, 3, 3)
         self.generation += 1
 

@@ -211,6 +211,22 @@ func (m *deviceMesh) update(d *deviceContext, mesh *Mesh) error {
 	return lastError(d.h, C.fgl_mesh_update(d.h, m.h, &desc))
 }
 
+// transform applies Mesh.Transform (mesh.go:167-175) to the device copy: an animate.go-style loop can rotate
+// the resident mesh every frame without flattening and uploading it again.
+func (m *deviceMesh) transform(d *deviceContext, matrix Matrix) error {
+	mm := [16]C.double{
+		C.double(matrix.X00), C.double(matrix.X01), C.double(matrix.X02), C.double(matrix.X03),
+		C.double(matrix.X10), C.double(matrix.X11), C.double(matrix.X12), C.double(matrix.X13),
+		C.double(matrix.X20), C.double(matrix.X21), C.double(matrix.X22), C.double(matrix.X23),
+		C.double(matrix.X30), C.double(matrix.X31), C.double(matrix.X32), C.double(matrix.X33)}
+	return lastError(d.h, C.fgl_mesh_transform(d.h, m.h, &mm[0]))
+}
+
+// smoothNormals is Mesh.SmoothNormals (mesh.go:105-120) on the device copy, bit-identical to the host loop.
+func (m *deviceMesh) smoothNormals(d *deviceContext) error {
+	return lastError(d.h, C.fgl_mesh_smooth_normals(d.h, m.h))
+}
+
 func (m *deviceMesh) destroy() {
 	if m.h != nil {
 		C.fgl_mesh_destroy(m.h)

@@ -147,6 +147,12 @@ int fgl_mesh_counts(const fgl_mesh *mesh, uint64_t *ntriangles, uint64_t *nlines
 /* Mesh.Transform, mesh.go:167-175 (+ triangle.go:66-73, line.go:23-28): positions
  * by MulPosition, normals by MulDirection (normalised), on the device. */
 int fgl_mesh_transform(fgl_ctx *ctx, fgl_mesh *mesh, const double matrix[16]);
+/* Mesh.SmoothNormals, mesh.go:105-120, on the device: every triangle corner receives the normalised sum of the
+ * normals of all corners at exactly the same position.  The sums are taken in the reference's order (triangle
+ * index, then V1, V2, V3, starting from the zero vector), so the result is bit-identical: corners are grouped by a
+ * stable sort on a hash of the position, collisions are separated by comparing the positions themselves (+0 == -0;
+ * a corner whose position has a NaN component gets the zero vector, as a Go map never finds a NaN key again).  Lines are left alone, as in the reference. */
+int fgl_mesh_smooth_normals(fgl_ctx *ctx, fgl_mesh *mesh);
 /* Read the device copy back (same layout as fgl_mesh_desc; any pointer may be NULL). */
 int fgl_mesh_read(fgl_ctx *ctx, const fgl_mesh *mesh, double *position, double *normal,
                   double *lposition, double *lnormal);

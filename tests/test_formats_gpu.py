@@ -264,3 +264,39 @@ def test_frame_pipeline_matches_synchronous_frames(oracle_lib, Context):
             assert (o.ColorBuffer == got[k][0]).all()
     assert len({g[1] for g in got}) > 1   # the frames do differ
     ctx.Close(); ref.Close()
+
+
+def test_device_smooth_normals_match_host_bit_for_bit(Context):
+    """fgl_mesh_smooth_normals == Mesh.SmoothNormals (mesh.go:105-120): sums in corner order from the zero vector,
+    groups by exact position (+0 == -0, NaN never equal).  The host mirror is itself checked against a naive
+    dictionary implementation in test_host_cpu.py."""
+    from fauxgl_b200 import mesh as fmesh, synth
+    from fauxgl_b200.context import DeviceMesh
+    ctx = Context(64, 64)
+    cases = []
+    # the benchmark surface: ~6 corners per position, two poles with 1320 corners each
+    cases.append(synth.bumpy_surface(triangles=60000, nu=201, nv=201, smooth=False))
+    # a loaded mesh with flat face normals
+    cases.append(scenes.load_fixture("bowser_mesh"))
+    # hand-made: -0 / +0 coordinates share a position, a NaN position is never found again (zero normal), a
+    # degenerate sum normalises to NaN
+    pos = np.array([[[0.0, 0, 0], [1, 0, 0], [0, 1, 0]],
+                    [[-0.0, 0, 0], [0, 1, 0], [-1, 0, 0]],
+                    [[np.nan, 0, 0], [1, 0, 0], [0, -0.0, 0.0]],
+                    [[np.nan, 0, 0], [2, 2, 2], [2, 2, 2]]], dtype=np.float64)
+    nrm = np.array([[[0, 0, 1.0], [0, 0, 1], [0, 1, 0]],
+                    [[0, 0, -1.0], [0, -1, 0], [1, 0, 0]],
+                    [[1, 0, 0.0], [0, 1, 0], [0.5, 0.25, -0.0]],
+                    [[0, 1, 0.0], [0, 0, 1], [0, 0, 3]]], dtype=np.float64)
+    cases.append(fmesh.NewTriangleMesh(pos, nrm, fix_normals=False))
+    for m in cases:
+        dm = DeviceMesh(ctx, m, ("position", "normal"))
+        dm.SmoothNormals()
+        _, dn, _, _ = dm.read()
+        host = fmesh.Mesh(m.position.copy(), m.normal.copy())
+        host.SmoothNormals()
+        assert same_bits(dn, host.normal), "device SmoothNormals differs from the host restatement"
+        nanpos = np.isnan(m.position).any(axis=2)
+        assert (host.normal[nanpos] == 0).all()   # Go: lookup[NaN key] -> Vector{}
+        dm.Close()
+    ctx.Close()
