@@ -11,6 +11,7 @@ missing, construction raises ``FauxglError``.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import weakref
 from typing import NamedTuple, Optional
@@ -106,6 +107,7 @@ ABI = [
     ("fgl_mesh_transform", C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     ("fgl_mesh_read", C.c_int, [_P, _P, _P, _P, _P, _P]),
     ("fgl_mesh_smooth_normals", C.c_int, [_P, _P]),
+    ("fgl_mesh_smooth_normals_threshold", C.c_int, [_P, _P, C.c_double]),
     ("fgl_texture_create", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     ("fgl_texture_destroy", C.c_int, [_P]),
     ("fgl_draw_triangles", C.c_int, [_P, C.POINTER(_State), C.POINTER(_Shader), _P, C.c_uint64, C.c_uint64, C.POINTER(_Info)]),
@@ -321,6 +323,10 @@ class DeviceMesh:
     def SmoothNormals(self):
         """Mesh.SmoothNormals on the device (mesh.go:105-120), bit-identical to the host mirror."""
         _check(capi().fgl_mesh_smooth_normals(self.ctx._h, self.handle), self.ctx._h)
+
+    def SmoothNormalsThreshold(self, radians: float):
+        """Mesh.SmoothNormalsThreshold on the device (mesh.go:80-103); the cosine is taken here, on the host."""
+        _check(capi().fgl_mesh_smooth_normals_threshold(self.ctx._h, self.handle, math.cos(radians)), self.ctx._h)
 
     def read(self):
         pos = np.empty((self.num_triangles, 3, 3)); nrm = np.empty((self.num_triangles, 3, 3))

@@ -832,7 +832,7 @@ int fgl_mesh_transform(fgl_ctx *c, fgl_mesh *m, const double matrix[16]) {
     return FGL_OK;
 }
 
-int fgl_mesh_smooth_normals(fgl_ctx *c, fgl_mesh *m) {
+static int smooth_normals_common(fgl_ctx *c, fgl_mesh *m, bool with_threshold, double threshold) {
     int rc = check_ctx(c);
     if (rc) return rc;
     if (!m) return fail(c, FGL_E_INVALID, "null mesh");
@@ -843,29 +843,40 @@ int fgl_mesh_smooth_normals(fgl_ctx *c, fgl_mesh *m) {
     const uint32_t n = (uint32_t)m->nt, nc = 3u * n;
     uint32_t *key[2] = {nullptr, nullptr}, *val[2] = {nullptr, nullptr}, *tmp = nullptr;
     unsigned int *n_dev = nullptr;
+    double *nout = nullptr;
     cudaError_t e = dev_alloc(&key[0], nc);
     if (e == cudaSuccess) e = dev_alloc(&key[1], nc);
     if (e == cudaSuccess) e = dev_alloc(&val[0], nc);
     if (e == cudaSuccess) e = dev_alloc(&val[1], nc);
     if (e == cudaSuccess) e = dev_alloc(&tmp, scan_tmp_words(nc));
     if (e == cudaSuccess) e = dev_alloc(&n_dev, 1);
+    if (e == cudaSuccess && with_threshold) e = dev_alloc(&nout, (size_t)n * 9);
     if (e == cudaSuccess) e = cudaMemcpyAsync(n_dev, &nc, sizeof nc, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) {
         mesh_acquire(c, m);
         launch_corner_hash(m->tpos, n, key[0], val[0], c->stream);
         int sorted = 0;
         launch_sort_pairs(key, val, n_dev, nc, 32, tmp, &sorted, c->stream);
-        launch_smooth_groups(key[sorted], val[sorted], m->tpos, m->tnrm, n, c->stream);
+        if (with_threshold) {
+            launch_smooth_threshold(key[sorted], val[sorted], m->tpos, m->tnrm, nout, n, threshold, c->stream);
+            cudaMemcpyAsync(m->tnrm, nout, sizeof(double) * 9 * n, cudaMemcpyDeviceToDevice, c->stream);
+        } else {
+            launch_smooth_groups(key[sorted], val[sorted], m->tpos, m->tnrm, n, c->stream);
+        }
         mesh_release(c, m);
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // the temporaries are freed below
     }
-    dev_free(key[0]); dev_free(key[1]); dev_free(val[0]); dev_free(val[1]); dev_free(tmp); dev_free(n_dev);
+    dev_free(key[0]); dev_free(key[1]); dev_free(val[0]); dev_free(val[1]); dev_free(tmp); dev_free(n_dev); dev_free(nout);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(c, e == cudaErrorMemoryAllocation ? FGL_E_OOM : FGL_E_CUDA, "smooth normals: %s", cudaGetErrorString(e));
     }
     return FGL_OK;
+}
+int fgl_mesh_smooth_normals(fgl_ctx *c, fgl_mesh *m) { return smooth_normals_common(c, m, false, 0); }
+int fgl_mesh_smooth_normals_threshold(fgl_ctx *c, fgl_mesh *m, double cos_threshold) {
+    return smooth_normals_common(c, m, true, cos_threshold);
 }
 
 static int read_attr(fgl_ctx *c, const double *planes, double *host, uint64_t n, int nverts, int ncomp) {

@@ -215,6 +215,39 @@ k_smooth_groups(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
         }
     }
 }
+// Mesh.SmoothNormalsThreshold, mesh.go:80-103: one thread per sorted pair = per corner; it walks its hash run from
+// the start (corner order) and adds the normals at its own position that pass the filter against ITS normal.
+__global__ void __launch_bounds__(256)
+k_smooth_threshold(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, const double *__restrict__ pos,
+                   const double *__restrict__ nin, double *__restrict__ nout, uint32_t n, double threshold) {
+    const uint32_t nc = 3u * n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
+        const uint32_t key = keys[i], ci = vals[i], ti = ci / 3u, vi = ci % 3u;
+        const V3 p = corner_position(pos, n, ci);
+        const V3 mine = v3(nin[(size_t)(vi * 3 + 0) * n + ti], nin[(size_t)(vi * 3 + 1) * n + ti], nin[(size_t)(vi * 3 + 2) * n + ti]);
+        V3 acc = v3(0, 0, 0);
+        if (p.x == p.x && p.y == p.y && p.z == p.z) {  // (a NaN key is never found again: the list is empty)
+            uint32_t j = i;
+            while (j > 0 && keys[j - 1] == key) j--;
+            for (; j < nc && keys[j] == key; j++) {
+                const uint32_t c = vals[j], t = c / 3u, v = c % 3u;
+                if (j != i && !same_position(corner_position(pos, n, c), p)) continue;
+                const V3 x = v3(nin[(size_t)(v * 3 + 0) * n + t], nin[(size_t)(v * 3 + 1) * n + t], nin[(size_t)(v * 3 + 2) * n + t]);
+                if (v_dot(x, mine) >= threshold) acc = v_add(acc, x);  // mesh.go:82-86
+            }
+        }
+        const V3 r = v_normalize(acc);
+        nout[(size_t)(vi * 3 + 0) * n + ti] = r.x;
+        nout[(size_t)(vi * 3 + 1) * n + ti] = r.y;
+        nout[(size_t)(vi * 3 + 2) * n + ti] = r.z;
+    }
+}
+int launch_smooth_threshold(const uint32_t *keys, const uint32_t *vals, const double *pos, const double *nrm_in,
+                            double *nrm_out, uint32_t n, double threshold, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_smooth_threshold<<<148 * 8, 256, 0, st>>>(keys, vals, pos, nrm_in, nrm_out, n, threshold);
+    return 1;
+}
 int launch_corner_hash(const double *pos, uint32_t n, uint32_t *keys, uint32_t *vals, cudaStream_t st) {
     if (n == 0) return 0;
     k_corner_hash<<<148 * 8, 256, 0, st>>>(pos, n, keys, vals);

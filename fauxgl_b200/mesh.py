@@ -211,7 +211,9 @@ class Mesh:
                 out[members[:, i]] = _normalize_rows(acc)
         # a position with a NaN component is a map key that is never found again: the corner's list is nil and
         # Vector{}.Normalize() = 0 * (1/0) = NaN (mesh.go:80-88)
-        out[np.isnan(self.position.reshape(-1, 3)).any(axis=1)] = np.nan
+        nanpos = np.isnan(self.position.reshape(-1, 3)).any(axis=1)
+        if nanpos.any():
+            out[nanpos] = _normalize_rows(np.zeros((int(nanpos.sum()), 3), dtype=_F))  # 0 * Inf, as computed
         self.normal = out.reshape(-1, 3, 3)
         self.generation += 1
 

@@ -21,6 +21,7 @@ import "C"
 import (
 	"errors"
 	"image"
+	"math"
 	"os"
 	"strconv"
 	"unsafe"
@@ -225,6 +226,11 @@ func (m *deviceMesh) transform(d *deviceContext, matrix Matrix) error {
 // smoothNormals is Mesh.SmoothNormals (mesh.go:105-120) on the device copy, bit-identical to the host loop.
 func (m *deviceMesh) smoothNormals(d *deviceContext) error {
 	return lastError(d.h, C.fgl_mesh_smooth_normals(d.h, m.h))
+}
+
+// smoothNormalsThreshold is Mesh.SmoothNormalsThreshold (mesh.go:90-103); math.Cos is taken here, in Go.
+func (m *deviceMesh) smoothNormalsThreshold(d *deviceContext, radians float64) error {
+	return lastError(d.h, C.fgl_mesh_smooth_normals_threshold(d.h, m.h, C.double(math.Cos(radians))))
 }
 
 func (m *deviceMesh) destroy() {

@@ -153,6 +153,11 @@ int fgl_mesh_transform(fgl_ctx *ctx, fgl_mesh *mesh, const double matrix[16]);
  * stable sort on a hash of the position, collisions are separated by comparing the positions themselves (+0 == -0;
  * a corner whose position has a NaN component gets the zero vector, as a Go map never finds a NaN key again).  Lines are left alone, as in the reference. */
 int fgl_mesh_smooth_normals(fgl_ctx *ctx, fgl_mesh *mesh);
+/* Mesh.SmoothNormalsThreshold, mesh.go:80-103: a corner's new normal is the normalised sum, in corner order, of
+ * those normals x at its position with x.Dot(normal) >= cos_threshold.  The caller passes the cosine itself
+ * (math.Cos(radians) evaluated by the host language), so no libm difference can move the comparison.  A corner
+ * whose position has a NaN component gets NaN (empty list: Vector{}.Normalize()). */
+int fgl_mesh_smooth_normals_threshold(fgl_ctx *ctx, fgl_mesh *mesh, double cos_threshold);
 /* Read the device copy back (same layout as fgl_mesh_desc; any pointer may be NULL). */
 int fgl_mesh_read(fgl_ctx *ctx, const fgl_mesh *mesh, double *position, double *normal,
                   double *lposition, double *lnormal);

@@ -298,5 +298,16 @@ def test_device_smooth_normals_match_host_bit_for_bit(Context):
         assert same_bits(dn, host.normal), "device SmoothNormals differs from the host restatement"
         nanpos = np.isnan(m.position).any(axis=2)
         assert (host.normal[nanpos] == 0).all()   # Go: lookup[NaN key] -> Vector{}
+        # SmoothNormalsThreshold (mesh.go:80-103) on the same inputs
+        from fauxgl_b200 import Radians
+        for deg in (30.0, 75.0):
+            dm = DeviceMesh(ctx, m, ("position", "normal"))
+            dm.SmoothNormalsThreshold(Radians(deg))
+            _, dn, _, _ = dm.read()
+            host = fmesh.Mesh(m.position.copy(), m.normal.copy())
+            host.SmoothNormalsThreshold(Radians(deg))
+            assert same_bits(dn, host.normal), "device SmoothNormalsThreshold differs from the host restatement"
+            assert np.isnan(host.normal[nanpos]).all()   # Go: nil list -> Vector{}.Normalize() = NaN
+            dm.Close()
         dm.Close()
     ctx.Close()
