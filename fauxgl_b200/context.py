@@ -85,6 +85,14 @@ class StageTimes(C.Structure):
 
 # every symbol include/fauxgl_b200.h declares: (name, restype, argtypes)
 _P = C.c_void_p
+
+
+class IndexedDesc(C.Structure):
+    """fgl_indexed_desc (include/fauxgl_b200.h)."""
+    _fields_ = [("v", _P), ("vt", _P), ("vn", _P), ("nv", C.c_uint64), ("nvt", C.c_uint64), ("nvn", C.c_uint64),
+                ("corners", _P), ("ntriangles", C.c_uint64)]
+
+
 ABI = [
     ("fgl_abi_version", C.c_int, []),
     ("fgl_last_error", C.c_char_p, [_P]),
@@ -106,6 +114,7 @@ ABI = [
     ("fgl_mesh_counts", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("fgl_mesh_transform", C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     ("fgl_mesh_read", C.c_int, [_P, _P, _P, _P, _P, _P]),
+    ("fgl_mesh_create_indexed", C.c_int, [_P, _P, C.POINTER(_P)]),
     ("fgl_mesh_smooth_normals", C.c_int, [_P, _P]),
     ("fgl_mesh_smooth_normals_threshold", C.c_int, [_P, _P, C.c_double]),
     ("fgl_texture_create", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
@@ -243,6 +252,30 @@ class DeviceMesh:
         self.num_triangles, self.num_lines = count, 0
         self.handle = _P()
         _check(capi().fgl_mesh_create_stl(ctx._h, rec.ctypes.data if count else None, count, C.byref(self.handle)), ctx._h)
+        self._fin = weakref.finalize(self, capi().fgl_mesh_destroy, self.handle)
+        return self
+
+    @classmethod
+    def FromOBJ(cls, ctx: "Context", path) -> "DeviceMesh":
+        """LoadOBJ (obj.go:19-79) with the expansion on the device: the text is parsed on the host
+        (``mesh.ParseOBJ``), the v / vt / vn tables and 36 B of indices per triangle cross PCIe, and
+        ``fgl_mesh_create_indexed`` gathers them into the planes and applies Triangle.FixNormals."""
+        from .mesh import ParseOBJ
+        vs, vts, vns, corners = ParseOBJ(path)
+        keep = [np.ascontiguousarray(vs, dtype=np.float64), np.ascontiguousarray(vts, dtype=np.float64),
+                np.ascontiguousarray(vns, dtype=np.float64), np.ascontiguousarray(corners, dtype=np.int32)]
+        d = IndexedDesc()
+        d.v, d.vt, d.vn = (C.cast(a.ctypes.data, _P) for a in keep[:3])
+        d.nv, d.nvt, d.nvn = len(keep[0]), len(keep[1]), len(keep[2])
+        d.corners = C.cast(keep[3].ctypes.data, _P)
+        d.ntriangles = len(keep[3])
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.generation = 0
+        self.attributes = ("position", "normal", "texture")
+        self.num_triangles, self.num_lines = int(d.ntriangles), 0
+        self.handle = _P()
+        _check(capi().fgl_mesh_create_indexed(ctx._h, C.byref(d), C.byref(self.handle)), ctx._h)
         self._fin = weakref.finalize(self, capi().fgl_mesh_destroy, self.handle)
         return self
 

@@ -775,6 +775,63 @@ int fgl_mesh_create_stl(fgl_ctx *c, const uint8_t *records, uint64_t count, fgl_
     return FGL_OK;
 }
 
+int fgl_mesh_create_indexed(fgl_ctx *c, const fgl_indexed_desc *d, fgl_mesh **out) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!out || !d) return fail(c, FGL_E_INVALID, "null descriptor/out pointer");
+    *out = nullptr;
+    const uint64_t count = d->ntriangles;
+    if (count > 0xfffffff0ull) return fail(c, FGL_E_INVALID, "mesh too large");
+    if (count && (!d->corners || !d->v || !d->vt || !d->vn || !d->nv || !d->nvt || !d->nvn))
+        return fail(c, FGL_E_INVALID, "null / empty table in an indexed mesh");
+    for (uint64_t k = 0; k < count * 3; k++) {  // the reference panics on an index outside its table
+        const int32_t *x = d->corners + k * 3;
+        if (x[0] < 0 || (uint64_t)x[0] >= d->nv || x[1] < 0 || (uint64_t)x[1] >= d->nvt || x[2] < 0 || (uint64_t)x[2] >= d->nvn)
+            return fail(c, FGL_E_INVALID, "corner %llu of the indexed mesh points outside its table", (unsigned long long)k);
+    }
+    std::lock_guard<std::mutex> lock(c->mu);
+    fgl_mesh *m = new (std::nothrow) fgl_mesh();
+    if (!m) return fail(c, FGL_E_OOM, "host allocation failed");
+    memset(m, 0, sizeof *m);
+    m->device = c->device; m->nt = count; m->nl = 0;
+    m->staging_elems = (size_t)m->nt * (9 * 3 + 12);  // as fgl_mesh_create: later fgl_mesh_update calls land here
+    double *tv = nullptr, *tvt = nullptr, *tvn = nullptr;
+    int32_t *tc = nullptr;
+    cudaError_t e = dev_alloc(&m->staging, m->staging_elems);
+    if (e == cudaSuccess) e = dev_alloc(&m->tpos, (size_t)count * 9);
+    if (e == cudaSuccess) e = dev_alloc(&m->tnrm, (size_t)count * 9);
+    if (e == cudaSuccess) e = dev_alloc(&m->ttex, (size_t)count * 6);
+    if (e == cudaSuccess) e = dev_alloc(&m->tcol, (size_t)count * 12);
+    if (e == cudaSuccess) e = dev_alloc(&m->lpos, 1);
+    if (e == cudaSuccess) e = dev_alloc(&m->lnrm, 1);
+    if (e == cudaSuccess) e = dev_alloc(&m->ltex, 1);
+    if (e == cudaSuccess) e = dev_alloc(&m->lcol, 1);
+    if (e == cudaSuccess && count) {
+        e = dev_alloc(&tv, (size_t)d->nv * 3);
+        if (e == cudaSuccess) e = dev_alloc(&tvt, (size_t)d->nvt * 3);
+        if (e == cudaSuccess) e = dev_alloc(&tvn, (size_t)d->nvn * 3);
+        if (e == cudaSuccess) e = dev_alloc(&tc, (size_t)count * 9);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tv, d->v, sizeof(double) * 3 * d->nv, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tvt, d->vt, sizeof(double) * 3 * d->nvt, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tvn, d->vn, sizeof(double) * 3 * d->nvn, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tc, d->corners, sizeof(int32_t) * 9 * count, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(m->tcol, 0, sizeof(double) * count * 12, c->stream);
+        if (e == cudaSuccess) {
+            launch_indexed_ingest(tv, tvt, tvn, tc, m->tpos, m->tnrm, m->ttex, (uint32_t)count, c->stream);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // the caller may free its arrays
+    }
+    dev_free(tv); dev_free(tvt); dev_free(tvn); dev_free(tc);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fgl_mesh_destroy(m);
+        return fail(c, e == cudaErrorMemoryAllocation ? FGL_E_OOM : FGL_E_CUDA, "indexed mesh upload: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return FGL_OK;
+}
+
 int fgl_mesh_bounds(fgl_ctx *c, const fgl_mesh *m, double mn[3], double mx[3]) {
     int rc = check_ctx(c);
     if (rc) return rc;

@@ -147,6 +147,47 @@ int launch_depth_image(const double *depth, size_t npix, uint16_t *out, unsigned
     return 2;
 }
 
+// ---- indexed (OBJ) mesh -> planes, obj.go:58-74 --------------------------------------------------
+// One thread per triangle: gather the three corners from the tables, then Triangle.FixNormals (triangle.go:46-58):
+// a corner whose normal == Vector{} (so -0 counts) takes the face normal Triangle.Normal() (triangle.go:33-37).
+__global__ void __launch_bounds__(256)
+k_indexed_ingest(const double *__restrict__ tv, const double *__restrict__ tvt, const double *__restrict__ tvn,
+                 const int32_t *__restrict__ corners, double *__restrict__ pos, double *__restrict__ nrm,
+                 double *__restrict__ tex, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        V3 p[3], nn[3];
+        double uv[3][2];
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            const int32_t *c = corners + ((size_t)i * 3 + v) * 3;
+            const double *a = tv + (size_t)c[0] * 3, *b = tvt + (size_t)c[1] * 3, *d = tvn + (size_t)c[2] * 3;
+            p[v] = v3(a[0], a[1], a[2]);
+            uv[v][0] = b[0]; uv[v][1] = b[1];
+            nn[v] = v3(d[0], d[1], d[2]);
+        }
+        const V3 face = v_normalize(v_cross(v_sub(p[1], p[0]), v_sub(p[2], p[0])));
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            if (nn[v].x == 0 && nn[v].y == 0 && nn[v].z == 0) nn[v] = face;
+            pos[(size_t)(v * 3 + 0) * n + i] = p[v].x;
+            pos[(size_t)(v * 3 + 1) * n + i] = p[v].y;
+            pos[(size_t)(v * 3 + 2) * n + i] = p[v].z;
+            nrm[(size_t)(v * 3 + 0) * n + i] = nn[v].x;
+            nrm[(size_t)(v * 3 + 1) * n + i] = nn[v].y;
+            nrm[(size_t)(v * 3 + 2) * n + i] = nn[v].z;
+            tex[(size_t)(v * 2 + 0) * n + i] = uv[v][0];
+            tex[(size_t)(v * 2 + 1) * n + i] = uv[v][1];
+        }
+    }
+}
+int launch_indexed_ingest(const double *v, const double *vt, const double *vn, const int32_t *corners, double *pos,
+                          double *nrm, double *tex, uint32_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    const uint32_t blocks = (n + 255) / 256;
+    k_indexed_ingest<<<blocks < 148u * 8u ? blocks : 148u * 8u, 256, 0, st>>>(v, vt, vn, corners, pos, nrm, tex, n);
+    return 1;
+}
+
 // ---- Mesh.SmoothNormals, mesh.go:105-120 ----------------------------------------------------------
 // Corner c = 3 t + v (the order the reference's loops visit them: t0.V1, t0.V2, t0.V3, t1.V1, ...).
 FGL_DI V3 corner_position(const double *__restrict__ pos, uint32_t n, uint32_t c) {

@@ -269,6 +269,9 @@ int launch_smooth_groups(const uint32_t *keys, const uint32_t *vals, const doubl
 // Mesh.SmoothNormalsThreshold: nrm_out (planes, separate from nrm_in: every corner reads all normals of its group)
 int launch_smooth_threshold(const uint32_t *keys, const uint32_t *vals, const double *pos, const double *nrm_in,
                             double *nrm_out, uint32_t n, double threshold, cudaStream_t st);
+// indexed (OBJ-shaped) mesh -> position / normal / texture planes, obj.go:58-74 + triangle.go:46-58
+int launch_indexed_ingest(const double *v, const double *vt, const double *vn, const int32_t *corners, double *pos,
+                          double *nrm, double *tex, uint32_t n, cudaStream_t st);
 // binary STL records (50 B each) -> position / normal planes, stl.go:86-154
 int launch_stl_ingest(const uint8_t *records, double *pos, double *nrm, uint32_t n, cudaStream_t st);
 // bounding box of position planes: bounds[0..2] = ordered-u64 min, [3..5] = max (see fgl_post.cu)

@@ -300,11 +300,15 @@ def _parse_float(s: str) -> float:  # util.go:65-72 (errors -> 0)
 
 # -- obj.go ---------------------------------------------------------------------------
 
-def LoadOBJ(path: str) -> Mesh:  # obj.go:19-79
+def ParseOBJ(path: str):  # obj.go:19-79, the text part
+    """Parse an OBJ file into the loader's tables: ``(vs, vts, vns, corners)`` with vs/vts/vns float64 (n,3)
+    arrays whose entry 0 is the zero vector of the reference's 1-based tables (obj.go:26-28) and corners an
+    int32 (T,3,3) array of (v, vt, vn) table indices per triangle corner, polygons triangulated as fans
+    (obj.go:58-60).  ``LoadOBJ`` expands it on the host, ``DeviceMesh.FromOBJ`` on the device."""
     vs = [(0.0, 0.0, 0.0)]
     vts = [(0.0, 0.0, 0.0)]
     vns = [(0.0, 0.0, 0.0)]
-    P, N, U = [], [], []
+    corners = []
 
     def parse_index(value: str, length: int) -> int:  # obj.go:10-17
         try:
@@ -338,14 +342,20 @@ def LoadOBJ(path: str) -> Mesh:  # obj.go:19-79
                     ft.append(parse_index(vertex[1], len(vts)))
                     fn.append(parse_index(vertex[2], len(vns)))
                 for i in range(1, len(fv) - 1):
-                    i1, i2, i3 = 0, i, i + 1
-                    P.append((vs[fv[i1]], vs[fv[i2]], vs[fv[i3]]))
-                    N.append((vns[fn[i1]], vns[fn[i2]], vns[fn[i3]]))
-                    U.append((vts[ft[i1]], vts[ft[i2]], vts[ft[i3]]))
-    T = len(P)
-    position = np.array(P, dtype=_F).reshape(T, 3, 3)
-    normal = np.array(N, dtype=_F).reshape(T, 3, 3)
-    texture = np.array(U, dtype=_F).reshape(T, 3, 3)
+                    corners.append([(fv[k], ft[k], fn[k]) for k in (0, i, i + 1)])
+    for tri in corners:  # Go panics on an index outside its table; so does this loader
+        for iv, it, inn in tri:
+            if not (0 <= iv < len(vs) and 0 <= it < len(vts) and 0 <= inn < len(vns)):
+                raise IndexError("OBJ face index out of range")
+    return (np.array(vs, dtype=_F).reshape(-1, 3), np.array(vts, dtype=_F).reshape(-1, 3),
+            np.array(vns, dtype=_F).reshape(-1, 3), np.array(corners, dtype=np.int32).reshape(-1, 3, 3))
+
+
+def LoadOBJ(path: str) -> Mesh:  # obj.go:19-79
+    vs, vts, vns, corners = ParseOBJ(path)
+    position = vs[corners[:, :, 0]]
+    texture = vts[corners[:, :, 1]]
+    normal = vns[corners[:, :, 2]]
     return NewTriangleMesh(position, normal, texture)
 
 

@@ -147,6 +147,20 @@ int fgl_mesh_counts(const fgl_mesh *mesh, uint64_t *ntriangles, uint64_t *nlines
 /* Mesh.Transform, mesh.go:167-175 (+ triangle.go:66-73, line.go:23-28): positions
  * by MulPosition, normals by MulDirection (normalised), on the device. */
 int fgl_mesh_transform(fgl_ctx *ctx, fgl_mesh *mesh, const double matrix[16]);
+/* An indexed triangle mesh in the shape LoadOBJ parses (obj.go:19-79): the v / vt / vn tables (entry 0 = the zero
+ * vector of the reference's 1-based tables) and, per triangle corner, one index into each.  The expansion to the
+ * planar device layout -- the gather of obj.go:61-72 and Triangle.FixNormals (triangle.go:46-58: a zero normal
+ * becomes the face normal) -- runs on the device, so 36 B of indices per triangle cross PCIe instead of 216 B of
+ * expanded float64 attributes.  Indices are validated on the host (FGL_E_INVALID; the reference panics). */
+typedef struct fgl_indexed_desc {
+    const double *v;        /* [nv][3]  */
+    const double *vt;       /* [nvt][3] (Z unused by the built-in shaders) */
+    const double *vn;       /* [nvn][3] */
+    uint64_t nv, nvt, nvn;
+    const int32_t *corners; /* [ntriangles][3][3]: (v, vt, vn) index of V1, V2, V3 */
+    uint64_t ntriangles;
+} fgl_indexed_desc;
+int fgl_mesh_create_indexed(fgl_ctx *ctx, const fgl_indexed_desc *desc, fgl_mesh **out);
 /* Mesh.SmoothNormals, mesh.go:105-120, on the device: every triangle corner receives the normalised sum of the
  * normals of all corners at exactly the same position.  The sums are taken in the reference's order (triangle
  * index, then V1, V2, V3, starting from the zero vector), so the result is bit-identical: corners are grouped by a

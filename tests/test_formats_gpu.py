@@ -311,3 +311,79 @@ def test_device_smooth_normals_match_host_bit_for_bit(Context):
             dm.Close()
         dm.Close()
     ctx.Close()
+
+
+OBJ_TEXT = """# a box with quads, a pentagon fan, negative indices, missing vt / vn, a zero normal
+v -1 -1 -1
+v  1 -1 -1
+v  1  1 -1
+v -1  1 -1
+v -1 -1  1
+v  1 -1  1
+v  1  1  1
+v -1  1  1
+v  0  2  0.5
+vt 0 0
+vt 1 0
+vt 1 1
+vt 0 1
+vt 0.5 0.25
+vn 0 0 -1
+vn 0 0 1
+vn 0 -0 0
+vn 0.6 0 0.8
+f 1/1/1 4/4/1 3/3/1 2/2/1
+f 5/1/2 6/2/2 7/3/2 8/4/2
+f 1//3 2//3 6//3 5//3
+f 2/2 3/3 7/4 6/1
+f -6 -2 -1 -3 -7
+f 4/4/4 8/1/4 7/5/-1
+f 1 5 8 4
+"""
+
+
+def test_obj_indexed_ingest_matches_host_loader(Context, tmp_path):
+    """fgl_mesh_create_indexed == the expansion of LoadOBJ (obj.go:58-74) + Triangle.FixNormals
+    (triangle.go:46-58): positions, normals and a texture-shaded render are bit-identical."""
+    from fauxgl_b200 import (HexColor, LoadOBJ, LookAt, NewPhongShader, V, Radians)
+    from fauxgl_b200.context import DeviceMesh, FauxglError
+    from fauxgl_b200.shader import NewImageTexture
+    path = tmp_path / "box.obj"
+    path.write_text(OBJ_TEXT)
+    host = LoadOBJ(str(path))
+    assert host.num_triangles == 2 + 2 + 2 + 2 + 3 + 1 + 2
+    ctx = Context(320, 240)
+    dm = DeviceMesh.FromOBJ(ctx, str(path))
+    dpos, dnrm, _, _ = dm.read()
+    assert same_bits(dpos, host.position) and same_bits(dnrm, host.normal)
+    # the texture coordinates: compare through a textured Phong render of both copies
+    rng = np.random.default_rng(5)
+    texels = rng.integers(0, 256, size=(16, 16, 4), dtype=np.uint8)
+    texels[..., 3] = 255
+    eye = V(3, 2.5, 4)
+    matrix = LookAt(eye, V(0, 0.3, 0), V(0, 1, 0)).Perspective(40, 320 / 240, 1, 20)
+    images = []
+    for mesh in (dm, DeviceMesh(ctx, host, ("position", "normal", "texture"))):
+        sh = NewPhongShader(matrix, V(-0.75, 1, 0.25).Normalize(), eye)
+        sh.Texture = NewImageTexture(texels)
+        ctx.Shader = sh
+        ctx.ClearDepthBuffer()
+        ctx.ClearColorBufferWith(HexColor("#102030"))
+        info = ctx.DrawMesh(mesh)
+        images.append((ctx.Image().copy(), tuple(info)))
+    assert images[0][1] == images[1][1] and images[0][1][0] > 0
+    assert (images[0][0] == images[1][0]).all()
+    # an index outside its table is refused (the reference panics)
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    from fauxgl_b200 import mesh as fmesh
+    vs, vts, vns, corners = fmesh.ParseOBJ(str(bad))
+    corners = corners.copy(); corners[0, 0, 0] = 9
+    from fauxgl_b200.context import IndexedDesc, capi, _P
+    import ctypes as C
+    d = IndexedDesc()
+    d.v, d.vt, d.vn = (C.cast(a.ctypes.data, _P) for a in (vs, vts, vns))
+    d.nv, d.nvt, d.nvn, d.corners, d.ntriangles = len(vs), len(vts), len(vns), C.cast(corners.ctypes.data, _P), 1
+    h = _P()
+    assert capi().fgl_mesh_create_indexed(ctx._h, C.byref(d), C.byref(h)) == -1
+    ctx.Close()
