@@ -335,3 +335,86 @@ def test_error_paths(gpu_capi, Context):
     rc = gpu_capi.fgl_draw_triangles(ctx._h, C.byref(st), C.byref(sh), dm.handle, 0, 2, C.byref(info))
     assert rc == -4 and b"no CPU fallback" in gpu_capi.fgl_last_error(ctx._h)
     ctx.Close()
+
+
+def _stacked_scene(kind, state):
+    """Hundreds of triangles piled onto the same few strips, so that a handful of strips hold far more than 96
+    segments each: the strip kernel hands those to whole CTAs (fgl_raster.cu, heavy strips).  kind "wide":
+    every segment spans its strip (a 32-segment chunk has more fragments than can be staged: the in-order
+    fallback); kind "narrow": slivers of a few pixels (staged chunks replayed by warp 0).  Depths are drawn
+    from a small set, so the <= tie rule decides many pixels."""
+    from fauxgl_b200 import (CullNone, Gray, HexColor, NewPhongShader, NewTriangleMesh, Orthographic, V)
+    # 640 x 360: 7 200 strips of 32 pixels, so the strip kernel runs its full grid (two CTAs per SM) and the
+    # ~100-200 heavy strips below stay under one per CTA -- the condition for the cooperative path
+    W, H = 640, 360
+    rng = np.random.RandomState(11 if kind == "wide" else 12)
+    n = 260
+    tri = []
+    for k in range(n):
+        z = -0.1 * rng.randint(0, 6)                       # few distinct depths: ties
+        if kind == "wide":
+            x0, x1 = -0.12 + 0.004 * rng.rand(), 0.33 + 0.004 * rng.rand()
+            y0 = -0.1 + 0.0003 * k
+            tri.append([(x0, y0, z), (x1, y0, z - 0.05 * rng.rand()), (0.5 * (x0 + x1), y0 + 0.2, z)])
+        else:
+            cx = -0.3 + 0.004 * rng.rand()
+            tri.append([(cx, -0.12, z), (cx + 0.012 + 0.006 * rng.rand(), -0.12, z), (cx + 0.005, 0.12, z - 0.03 * rng.rand())])
+    mesh = NewTriangleMesh(np.array(tri, dtype=np.float64))
+
+    def run(ctx):
+        ctx.ClearColorBufferWith(Gray(0.25))
+        shader = NewPhongShader(Orthographic(-1, 1, -1, 1, -1, 1), V(0.3, 0.2, 1).Normalize(), V(0, 0, 5))
+        shader.ObjectColor = HexColor("#468966")
+        ctx.Shader = shader
+        ctx.Cull = CullNone
+        if state == "bias":
+            ctx.DepthBias = -1e-3
+        elif state == "no_read":
+            ctx.ReadDepth = False
+        elif state == "no_write":
+            ctx.WriteDepth = False
+        return [ctx.DrawMesh(mesh), ctx.DrawTriangles(mesh, 17, 200)]
+    sc = scenes.Scene(W, H, run)
+    sc.mesh = mesh
+    return sc
+
+
+@pytest.mark.parametrize("state", ["default", "bias", "no_read", "no_write"])
+@pytest.mark.parametrize("kind", ["wide", "narrow"])
+def test_heavy_strips_taken_by_whole_ctas(kind, state, oracle_lib, Context):
+    """The CTA-cooperative path of the strip kernel (a few strips with hundreds of segments) is bit-exact for
+    every render state, for chunks that are staged and for chunks that are not."""
+    stats = run_both(_stacked_scene(kind, state), oracle_lib, Context)
+    print(stats)
+    assert stats["depth_mismatch"] == 0 and stats["color_mismatch"] == 0
+    assert stats["gpu_info"] == stats["oracle_info"]
+    assert stats["gpu_info"][0][0] > 15000
+
+
+@pytest.mark.parametrize("kind", ["wide", "narrow"])
+def test_heavy_strips_per_primitive_info(kind, oracle_lib, Context):
+    """fgl_draw_triangles_each through the same path: UpdatedPixels attributed per triangle."""
+    sc = _stacked_scene(kind, "default")
+    ctx, o = Context(sc.width, sc.height), oracle_lib.OracleContext(sc.width, sc.height)
+
+    class Capture:
+        def __init__(self, c):
+            self.__dict__["c"] = c
+
+        def __getattr__(self, k):
+            return getattr(self.c, k)
+
+        def __setattr__(self, k, v):
+            setattr(self.c, k, v)
+
+        def DrawMesh(self, m):
+            return (0, 0)
+
+        def DrawTriangles(self, m, *a):
+            return (0, 0)
+    sc.run(Capture(ctx)); sc.run(Capture(o))
+    got, want = ctx.DrawTrianglesEach(sc.mesh), o.DrawTrianglesEach(sc.mesh)
+    assert (got == want).all() and int(got[:, 1].sum()) > 1000
+    assert (ctx.Image() == o.ColorBuffer).all()
+    assert (ctx.DepthBuffer.view(np.uint64) == o.DepthBuffer.view(np.uint64)).all()
+    ctx.Close()
