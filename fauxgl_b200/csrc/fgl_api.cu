@@ -147,7 +147,8 @@ void dev_free(T *&p) {
 }
 
 void free_work(WorkBuffers &wb) {
-    dev_free(wb.blk_agg); dev_free(wb.blk_base); dev_free(wb.blk_region); dev_free(wb.recs);
+    dev_free(wb.blk_agg); dev_free(wb.blk_base); dev_free(wb.blk_region); dev_free(wb.blk_wcnt); dev_free(wb.blk_woff);
+    dev_free(wb.recs);
     dev_free(wb.rec_local_row); dev_free(wb.rec_slot);
     dev_free(wb.rec_row_off); dev_free(wb.clip_pool); dev_free(wb.row_nseg); dev_free(wb.row_seg_off);
     dev_free(wb.row_first); dev_free(wb.row_key); dev_free(wb.segv);
@@ -167,7 +168,9 @@ int ensure_work(fgl_ctx *c, const Caps &want) {
     if (want.prims > LIM || want.records > LIM || want.rows > LIM || want.segs > LIM || want.clip > LIM)
         return fail(c, FGL_E_INVALID, "draw too large for 32-bit work indices");
     if (want.prims > wb.cap_prims) {
-        dev_free(wb.blk_agg); dev_free(wb.blk_base); dev_free(wb.blk_region);
+        dev_free(wb.blk_agg); dev_free(wb.blk_base); dev_free(wb.blk_region); dev_free(wb.blk_wcnt); dev_free(wb.blk_woff);
+        CK(c, dev_alloc(&wb.blk_wcnt, want.prims / 32 + 8));
+        CK(c, dev_alloc(&wb.blk_woff, want.prims / 32 + 8));
         CK(c, dev_alloc(&wb.blk_agg, want.prims / 32 + 8));
         CK(c, dev_alloc(&wb.blk_base, want.prims / 32 + 8));
         CK(c, dev_alloc(&wb.blk_region, want.prims / 32 + 8));

@@ -724,6 +724,11 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     uint32_t scan_parity = 0;
     __shared__ unsigned long long s_region;
     __shared__ bool s_last;
+    // fast blocks (no clipping / lines / wireframe): every warp compacts into a sub-region of its own
+    __shared__ uint32_t s_celloff[FT];           // cells (rows x strip columns) of the records before this one
+    __shared__ uint32_t s_wcnt[FT / 32], s_wbase[FT / 32];  // segments stored by / first region offset of each warp
+    __shared__ volatile uint32_t s_region_ready;
+    if (threadIdx.x == 0) s_region_ready = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();  // k_seg_index may be scheduled while the last wave of this grid drains
     const uint32_t vb = blockIdx.x;
@@ -816,7 +821,10 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     // to the block just before the first compaction barrier below, a scan and a row walk later.
     unsigned long long my_region = 0;
     if (tid == 0 && nrec_blk) my_region = atomicAdd(&wb.counters->seg_cursor, block_total >> CELL_SHIFT);
-    if (!general && n == 1) s_order[rec_off] = (uint16_t)tid;
+    if (!general && n == 1) {
+        s_order[rec_off] = (uint16_t)tid;
+        s_celloff[rec_off] = (uint32_t)((s_scan[warp] + incl - mine) >> CELL_SHIFT);
+    }
     __syncthreads();
     unsigned long long region = 0;
 
@@ -825,6 +833,89 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     unsigned long long covered = 0;
     ParkedSeg first;
     first.w0 = first.w1 = first.w2 = 0; first.x = 0; first.cnt = 0; first.key = 0;
+    if (!general) {
+        // ---- fast blocks: no block barrier inside the walk.  The (record, scanline) items are split into FT/32
+        // contiguous ranges (multiples of 32), one per warp; a warp's segments go to the block's region at the
+        // offset given by the CELL upper bound of the items before its range -- the bound the region was sized
+        // with -- so the warps never wait for each other's counts (the block scan per 128 items and its barrier
+        // were 9 % of the kernel's stall samples).  Inside the region the warps' runs are in primitive order but
+        // not contiguous; k_seg_index closes the gaps (blk_wcnt / blk_woff).
+        uint32_t items;
+        {
+            const uint32_t rows = tid < (int)nrec_blk ? s_rec[s_order[tid]].rows : 0u;
+            const uint32_t ex = block_excl_scan1<FT>(rows, s_scan32, scan_parity, &items);
+            s_rowoff[tid] = ex;
+            if (tid == 0) s_rowoff[FT] = items;
+            __syncthreads();
+        }
+        if (tid == 0) {  // hand the reservation to the block (warp 0 absorbs what is left of its round trip)
+            s_region = my_region;
+            __threadfence_block();
+            s_region_ready = 1u;
+        }
+        auto locate = [&](uint32_t it) {  // the last entry with s_rowoff[lo] <= it (entries >= nrec_blk hold `items`)
+            uint32_t lo = 0;
+#pragma unroll
+            for (uint32_t step = FT / 2; step > 0; step >>= 1)
+                if (s_rowoff[lo + step] <= it) lo += step;
+            return lo;
+        };
+        const uint32_t ipw = (((items + FT / 32 - 1) / (FT / 32)) + 31u) & ~31u;
+        const uint32_t my0 = min((uint32_t)warp * ipw, items), my1 = min(my0 + ipw, items);
+        uint32_t wbase = 0, wrun = 0;
+        if (my0 < my1) {
+            const uint32_t lo = locate(my0);
+            const SRec &r = s_rec[s_order[lo]];
+            const uint32_t cols = (uint32_t)((min(r.x1, p.width - 1) >> p.tile_shift) - (max(r.x0, 0) >> p.tile_shift) + 1);
+            wbase = s_celloff[lo] + (my0 - s_rowoff[lo]) * cols;
+        }
+        bool have_region = false;
+        for (uint32_t c0 = my0; c0 < my1; c0 += 32) {
+            const uint32_t it = c0 + (uint32_t)lane;
+            uint32_t nseg = 0, ridx = 0;
+            int y = 0;
+            if (it < my1) {
+                const uint32_t lo = locate(it);
+                ridx = s_order[lo];
+                const SRec &r = s_rec[ridx];
+                y = max(r.y0, 0) + (int)(it - s_rowoff[lo]);
+                const unsigned long long before = covered;
+                nseg = walk_row_count(p, r, y, first, &covered);
+                if (p.prim_info && covered != before)  // per-primitive TotalPixels (fgl_draw_*_each)
+                    atomicAdd(&p.prim_info[2 * (size_t)src_primitive(wb, p, r.src, r.flags)], covered - before);
+            }
+            const uint32_t incl_w = warp_incl_scan(nseg);
+            const uint32_t ex = incl_w - nseg, chunk_total = __shfl_sync(0xffffffffu, incl_w, 31);
+            if (!have_region) {
+                while (s_region_ready == 0u) {}
+                __threadfence_block();
+                region = *(volatile unsigned long long *)&s_region;
+                have_region = true;
+            }
+            if (nseg) {
+                const unsigned long long slot64 = region + wbase + wrun + ex;
+                const SRec &r = s_rec[ridx];
+                RecTail tail;
+                tail.r0 = r.r0; tail.r1 = r.r1; tail.r2 = r.r2; tail.src = r.src; tail.flags = r.flags;
+                if (slot64 + nseg <= (unsigned long long)wb.cap_segs) {
+                    const uint32_t slot = (uint32_t)slot64;
+                    if (nseg == 1) {
+                        wb.segv[slot] = make_segv(first.w0, first.w1, first.w2, r.ra, r.z0, r.z1, r.z2, r.s2y - r.s1y,
+                                                  r.s0y - r.s2y, r.s1y - r.s0y, tail, (uint16_t)first.x, (uint8_t)first.cnt);
+                        wb.seg_key[1][slot] = first.key;
+                    } else {  // the scanline crosses strip boundaries: walk it again, storing every segment
+                        unsigned long long dummy = 0;
+                        walk_row_segments<true>(p, r, y, first, &tail, wb.segv, wb.seg_key[1], slot, wb.cap_segs, &dummy);
+                    }
+                }
+            }
+            wrun += chunk_total;
+        }
+        if (lane == 0) { s_wcnt[warp] = wrun; s_wbase[warp] = wbase; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < FT / 32; w++) seg_run += s_wcnt[w];
+    } else {
     for (uint32_t win0 = 0; win0 < nrec_blk; win0 += FT) {
         const uint32_t nw = min((uint32_t)FT, nrec_blk - win0);
         if (general) {  // re-run the deterministic geometry, keeping the records of this window
@@ -882,6 +973,11 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             seg_run += chunk_total;
         }
     }
+    if (tid == 0) {  // one contiguous run from the front of the region
+        s_wcnt[0] = seg_run; s_wbase[0] = 0;
+        for (int w = 1; w < FT / 32; w++) { s_wcnt[w] = 0; s_wbase[w] = 0; }
+    }
+    }
 
     // TotalPixels, context.go:229: every covered in-range pixel, before any depth test
 #pragma unroll
@@ -892,6 +988,9 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     if (tid == 0) {
         wb.blk_agg[vb] = ((unsigned long long)seg_run << 32) | nrec_blk;
         wb.blk_region[vb] = (uint32_t)min(my_region, 0xffffffffull);
+        static_assert(FT / 32 == 4, "blk_wcnt / blk_woff hold one entry per warp of a 128-thread block");
+        wb.blk_wcnt[vb] = make_uint4(s_wcnt[0], s_wcnt[1], s_wcnt[2], s_wcnt[3]);
+        wb.blk_woff[vb] = make_uint4(s_wbase[0], s_wbase[1], s_wbase[2], s_wbase[3]);
         __threadfence();
         s_last = atomicAdd(&wb.counters->blocks_done, 1u) == nblocks - 1u;
     }
@@ -959,8 +1058,11 @@ k_seg_index(const __grid_constant__ WorkBuffers wb, uint32_t nent) {
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
     for (uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nent; b += nwarps) {
         const uint32_t cnt = (uint32_t)(wb.blk_agg[b] >> 32), base = (uint32_t)wb.blk_base[b], region = wb.blk_region[b];
+        const uint4 wc = wb.blk_wcnt[b], wo = wb.blk_woff[b];  // the block's warps filled sub-regions of their own
+        const uint32_t c1 = wc.x, c2 = c1 + wc.y, c3 = c2 + wc.z;
         for (uint32_t k = lane; k < cnt; k += 32u) {
-            const uint32_t pos = base + k, slot = region + k;
+            const uint32_t off = k < c1 ? wo.x + k : (k < c2 ? wo.y + (k - c1) : (k < c3 ? wo.z + (k - c2) : wo.w + (k - c3)));
+            const uint32_t pos = base + k, slot = region + off;
             if (pos < n) {
                 wb.seg_key[0][pos] = wb.seg_key[1][slot];
                 wb.seg_val[0][pos] = slot;

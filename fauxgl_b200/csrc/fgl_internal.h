@@ -146,6 +146,8 @@ struct WorkBuffers {
     unsigned long long *blk_agg;    // [cap_prims/32+8] scanlines << 30 | records of each geometry block
     unsigned long long *blk_base;   // [cap_prims/32+8] exclusive prefix of blk_agg
     uint32_t *blk_region;           // [cap_prims/32+8] first record slot of the block
+    uint4 *blk_wcnt, *blk_woff;     // [cap_prims/32+8] k_front: segments stored by each of the block's four warps and the
+                                    //                  offset of each warp's run inside the block's region
     Rec *recs;                // [cap_records]   indexed by slot
     uint32_t *rec_local_row;  // [cap_records]   by slot: scanline offset of the record inside its block
     uint32_t *rec_slot;       // [cap_records+1] by primitive order: slot of the record
