@@ -260,8 +260,8 @@ def main():
         return {"geometry_ms": st.geometry_ms / st.draws, "spans_ms": st.spans_ms / st.draws,
                 "sort_ms": st.sort_ms / st.draws, "raster_ms": st.raster_ms / st.draws}
     stages = stage_ms(r1["stage"])
-    # Dominant kernel: k_front, the fused geometry + span kernel (51 % of the frame in the ncu launch list,
-    # profiles/r01_launch_table_v6.txt); the `geometry` stage timer brackets exactly that launch (and the
+    # Dominant kernel: k_front, the fused geometry + span kernel (50 % of the frame in the ncu launch list,
+    # profiles/r01_launch_table_v7.txt); the `geometry` stage timer brackets exactly that launch (and the
     # 64-byte counter memset before it).  Its algorithmic bytes: the position planes,
     # T * 72 B, read once -- the segments it writes are implementation, not algorithm.
     geo_bytes = T_TRIANGLES * 72
@@ -279,13 +279,13 @@ def main():
         "bound": "hbm", "kernel": "k_front",
         "achieved": geo_bytes / (stages["geometry_ms"] / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
         "frac": geo_bytes / (stages["geometry_ms"] / 1e3) / 1e9 / hbm_peak,
-        "traffic": 86990848,   # dram__bytes_read+write of one k_front launch, profiles/r01_ncu_v6_front_strip_shade.txt
+        "traffic": 86789120,   # dram__bytes_read+write of one k_front launch, profiles/r01_ncu_v7_front_strip_shade.txt
         "peak_source": peak_src, "algorithmic_bytes": geo_bytes,
         "frame": {"algorithmic_bytes": ALGO_BYTES_C1, "achieved": ALGO_BYTES_C1 / (ms1 / 1e3) / 1e9,
                   "frac": ALGO_BYTES_C1 / (ms1 / 1e3) / 1e9 / hbm_peak},
         "stages_ms": stages, "fragment_bound": fragment_bound,
         "note": "issue/latency-bound float64 replay of the reference's arithmetic, not bandwidth-bound: "
-                "55.0 M warp instructions at 0.49 IPC per scheduler, see profiles/README.md",
+                "54.2 M warp instructions at 0.52 IPC per scheduler, see profiles/README.md",
     }
 
     # ---------------- 16x SSAA (7680x4320 + resolve) ----------------
