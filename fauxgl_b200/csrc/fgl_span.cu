@@ -162,12 +162,13 @@ constexpr int TR_THREADS = 1024;
 // that start there (heavy / light), reserves its share of the busy list with ONE global atomic per list, then
 // it fills in the entries (ranks inside the CTA from shared-memory counters).
 __global__ void __launch_bounds__(TR_THREADS)
-k_tile_ranges(const uint32_t *__restrict__ keys, const unsigned int *__restrict__ n_dev, uint32_t n_max,
+k_tile_ranges(const uint32_t *__restrict__ keys, DrawCounters *__restrict__ ctr, uint32_t n_max,
               uint2 *__restrict__ busy_list, uint32_t ntiles, TileCtl *ctl) {
     __shared__ uint32_t s_cnt[2], s_base[2], s_fill[2];
     pdl_wait();
     pdl_trigger();
-    const uint32_t n = min(*n_dev, n_max);
+    if (ctr->overflow) return;  // the draw is going to be re-issued: its keys are incomplete
+    const uint32_t n = min(ctr->n_segs, n_max);
     const uint32_t lane = threadIdx.x & 31;
     uint32_t per = (n + gridDim.x - 1) / gridDim.x;
     per = (per + TR_THREADS - 1) / TR_THREADS * TR_THREADS;
@@ -211,9 +212,11 @@ k_tile_ranges(const uint32_t *__restrict__ keys, const unsigned int *__restrict_
         wh = __shfl_sync(0xffffffffu, wh, 0);
         wl = __shfl_sync(0xffffffffu, wl, 0);
         if (starts) {
+            // (a sorted key array has at most ntiles bins; the bound keeps a corrupted one from writing outside the list)
             const uint32_t lt = (1u << lane) - 1u;
-            if (heavy) busy_list[s_base[0] + wh + __popc(mh & lt)] = make_uint2(k, i);
-            else busy_list[ntiles - 1u - (s_base[1] + wl + __popc(ml & lt))] = make_uint2(k, i);
+            const uint32_t ph = s_base[0] + wh + __popc(mh & lt), pl = s_base[1] + wl + __popc(ml & lt);
+            if (heavy) { if (ph < ntiles) busy_list[ph] = make_uint2(k, i); }
+            else if (pl < ntiles) busy_list[ntiles - 1u - pl] = make_uint2(k, i);
         }
     }
 }
@@ -242,7 +245,7 @@ int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cuda
     int bits = 1;
     while ((1u << bits) < wb.ntiles) bits++;
     launches += launch_sort_pairs(wb.seg_key, wb.seg_val, &c->n_segs, wb.cap_segs, bits, wb.scan_tmp, sorted_buf, st);
-    launch_pdl(k_tile_ranges, 148, TR_THREADS, 0, st, wb.seg_key[*sorted_buf], &c->n_segs, wb.cap_segs, wb.busy_list,
+    launch_pdl(k_tile_ranges, 148, TR_THREADS, 0, st, (const uint32_t *)wb.seg_key[*sorted_buf], c, wb.cap_segs, wb.busy_list,
                wb.ntiles, wb.tile_ctl);
     launches++;
     return launches;
