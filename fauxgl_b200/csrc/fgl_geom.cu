@@ -848,10 +848,13 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             if (tid == 0) s_rowoff[FT] = items;
             __syncthreads();
         }
-        if (tid == 0) {  // hand the reservation to the block (warp 0 absorbs what is left of its round trip)
+        // Hand the reservation to the block: a release store of the flag after the value, acquire loads in the
+        // readers (message passing without a barrier -- compute-sanitizer's racecheck reports exactly this pair).
+        // Warp 0 absorbs what is left of the atomic's round trip; the other warps look only after their first walk.
+        const uint32_t flag_addr = (uint32_t)__cvta_generic_to_shared(const_cast<uint32_t *>(&s_region_ready));
+        if (tid == 0) {
             s_region = my_region;
-            __threadfence_block();
-            s_region_ready = 1u;
+            asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(flag_addr), "r"(1u) : "memory");
         }
         auto locate = [&](uint32_t it) {  // the last entry with s_rowoff[lo] <= it (entries >= nrec_blk hold `items`)
             uint32_t lo = 0;
@@ -887,8 +890,10 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             const uint32_t incl_w = warp_incl_scan(nseg);
             const uint32_t ex = incl_w - nseg, chunk_total = __shfl_sync(0xffffffffu, incl_w, 31);
             if (!have_region) {
-                while (s_region_ready == 0u) {}
-                __threadfence_block();
+                uint32_t ready;
+                do {
+                    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ready) : "r"(flag_addr) : "memory");
+                } while (ready == 0u);
                 region = *(volatile unsigned long long *)&s_region;
                 have_region = true;
             }
