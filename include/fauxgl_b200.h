@@ -312,7 +312,10 @@ int fgl_debug_tile_cycles(fgl_ctx *ctx, uint64_t *dst, uint64_t ntiles);
 int fgl_probe_atomic_rate(fgl_ctx *ctx, uint64_t ops, double *ops_per_second);
 
 /* Interop for the host harness (timing with CUDA events on the launching
- * stream; zero-copy views of the buffers). */
+ * stream; zero-copy views of the buffers).  Clears run on a stream of their own (they overlap the front end of
+ * the next draw); every library call that touches the framebuffer orders itself after a pending clear, but work
+ * the caller enqueues on fgl_stream() against the raw pointers does not: call fgl_sync() (or any read-back /
+ * draw) after the last clear first. */
 void *fgl_stream(const fgl_ctx *ctx);            /* cudaStream_t */
 void *fgl_color_device_ptr(const fgl_ctx *ctx);  /* width*height*4 bytes */
 void *fgl_depth_device_ptr(const fgl_ctx *ctx);  /* width*height doubles */
