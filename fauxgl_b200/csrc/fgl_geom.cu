@@ -1049,9 +1049,10 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     }
 }
 
-// Segments in primitive order for the stable sort: position blk_base[b] + k  <-  slot blk_region[b] + k.
-// One warp per block of the front end: three loads tell it where its segments are, then it copies them with
-// coalesced reads and writes (no per-position search for the block).
+// Segments in primitive order for the stable sort: position blk_base[b] + (segments of the block's earlier warps)
+// + k  <-  slot blk_region[b] + blk_woff[b][w] + k.  One warp per (front-end block, warp run): a handful of loads
+// tell it where the run is, then it copies it with coalesced reads and writes, four independent loads in flight
+// per lane (no per-position search for the block).
 __global__ void __launch_bounds__(256)
 k_seg_index(const __grid_constant__ WorkBuffers wb, uint32_t nent) {
     pdl_wait();
@@ -1060,17 +1061,30 @@ k_seg_index(const __grid_constant__ WorkBuffers wb, uint32_t nent) {
     if (ctr->overflow) return;
     const uint32_t n = min(ctr->n_segs, wb.cap_segs);
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nent; b += nwarps) {
-        const uint32_t cnt = (uint32_t)(wb.blk_agg[b] >> 32), base = (uint32_t)wb.blk_base[b], region = wb.blk_region[b];
-        const uint4 wc = wb.blk_wcnt[b], wo = wb.blk_woff[b];  // the block's warps filled sub-regions of their own
-        const uint32_t c1 = wc.x, c2 = c1 + wc.y, c3 = c2 + wc.z;
-        for (uint32_t k = lane; k < cnt; k += 32u) {
-            const uint32_t off = k < c1 ? wo.x + k : (k < c2 ? wo.y + (k - c1) : (k < c3 ? wo.z + (k - c2) : wo.w + (k - c3)));
-            const uint32_t pos = base + k, slot = region + off;
-            if (pos < n) {
-                wb.seg_key[0][pos] = wb.seg_key[1][slot];
-                wb.seg_val[0][pos] = slot;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5), ntasks = nent * 4u;
+    for (uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < ntasks; t += nwarps) {
+        const uint32_t b = t >> 2, w = t & 3u;
+        const uint4 wc = wb.blk_wcnt[b];
+        const uint32_t cnt = w == 0 ? wc.x : (w == 1 ? wc.y : (w == 2 ? wc.z : wc.w));
+        if (cnt == 0) continue;
+        const uint4 wo = wb.blk_woff[b];
+        const uint32_t before = w == 0 ? 0u : (w == 1 ? wc.x : (w == 2 ? wc.x + wc.y : wc.x + wc.y + wc.z));
+        const uint32_t pos0 = (uint32_t)wb.blk_base[b] + before;
+        const uint32_t slot0 = wb.blk_region[b] + (w == 0 ? wo.x : (w == 1 ? wo.y : (w == 2 ? wo.z : wo.w)));
+        for (uint32_t k0 = 0; k0 < cnt; k0 += 128u) {
+            uint32_t key[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t k = k0 + 32u * u + lane;
+                key[u] = (k < cnt && pos0 + k < n) ? wb.seg_key[1][slot0 + k] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t k = k0 + 32u * u + lane;
+                if (k < cnt && pos0 + k < n) {
+                    wb.seg_key[0][pos0 + k] = key[u];
+                    wb.seg_val[0][pos0 + k] = slot0 + k;
+                }
             }
         }
     }
