@@ -86,6 +86,7 @@ struct fgl_ctx {
     DrawCounters *host_counters;       // pinned
     DrawCounters *acc_dev;             // async accumulation (total/updated/overflow)
     bool async_pending;
+    bool counters_clean;               // the last draw's k_shade zeroed the device-side draw counters
     unsigned long long *prim_info;     // per-primitive RasterizeInfo of fgl_draw_*_each, [prim_info_cap][2]
     uint64_t prim_info_cap;
     unsigned long long *scratch;       // 8 words: reductions of fgl_mesh_bounds / fgl_depth_image
@@ -355,12 +356,12 @@ int enqueue_draw(fgl_ctx *c, const DrawParams &p, bool async) {
     if (use_fused_front(c, p)) {
         // large draws: geometry and spans in one kernel (the stage timers then read: geometry = k_front alone,
         // spans = k_seg_index)
-        launches += launch_front(p, c->wb, c->stream);
+        launches += launch_front(p, c->wb, c->counters_clean, c->stream);
         if (ps) cudaEventRecord(ps->e[1], c->stream);
         launches += launch_seg_index(p, c->wb, c->stream);
         if (ps) cudaEventRecord(ps->e[2], c->stream);
     } else {
-        launches += launch_geometry(p, c->wb, c->stream);
+        launches += launch_geometry(p, c->wb, c->counters_clean, c->stream);
         if (ps) cudaEventRecord(ps->e[1], c->stream);
         launches += launch_spans(p, c->wb, &sorted, c->stream);
         if (ps) cudaEventRecord(ps->e[2], c->stream);
@@ -370,6 +371,7 @@ int enqueue_draw(fgl_ctx *c, const DrawParams &p, bool async) {
     fb_join(c);  // the front end and the binning ran beside a pending clear; the strips need the framebuffer
     bool accumulated = false;
     launches += launch_raster(p, c->wb, sorted, c->color, c->depth, async ? c->acc_dev : nullptr, &accumulated, c->stream);
+    c->counters_clean = async && accumulated;  // k_shade's last CTA zeroes them after accumulating
     if (async && !accumulated) {  // (the deferred-shading kernel does it on the way, other paths need the extra launch)
         launch_pdl(k_accumulate, 1, 1, 0, c->stream, (const DrawCounters *)c->wb.counters, c->acc_dev);
         launches++;
@@ -516,7 +518,7 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     c->color = nullptr; c->depth = nullptr; c->resolved = nullptr; c->rw = c->rh = 0;
     memset(&c->wb, 0, sizeof c->wb);
     memset(&c->stats, 0, sizeof c->stats);
-    c->host_counters = nullptr; c->acc_dev = nullptr; c->async_pending = false;
+    c->host_counters = nullptr; c->acc_dev = nullptr; c->async_pending = false; c->counters_clean = false;
     c->prim_info = nullptr; c->prim_info_cap = 0; c->scratch = nullptr; c->gray16 = nullptr;
     c->profiling = false; c->prof_used = 0; c->prof_created = false;
     memset(&c->prof_acc, 0, sizeof c->prof_acc);

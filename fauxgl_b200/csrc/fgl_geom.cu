@@ -1090,9 +1090,9 @@ k_seg_index(const __grid_constant__ WorkBuffers wb, uint32_t nent) {
     }
 }
 
-int launch_front(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {
+int launch_front(const DrawParams &p, const WorkBuffers &wb, bool counters_clean, cudaStream_t st) {
     const uint32_t blocks = (p.count + FT - 1) / FT;
-    cudaMemsetAsync(wb.counters, 0, sizeof(DrawCounters), st);
+    if (!counters_clean) cudaMemsetAsync(wb.counters, 0, sizeof(DrawCounters), st);
     k_front<<<blocks, FT, 0, st>>>(p, wb);
     return 1;
 }
@@ -1102,10 +1102,10 @@ int launch_seg_index(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st
     return 1;
 }
 
-int launch_geometry(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {
+int launch_geometry(const DrawParams &p, const WorkBuffers &wb, bool counters_clean, cudaStream_t st) {
     const uint32_t blocks = (p.count + GT - 1) / GT;
     // counters + look-back state of this draw (stream-ordered before the kernel)
-    cudaMemsetAsync(wb.counters, 0, sizeof(DrawCounters), st);
+    if (!counters_clean) cudaMemsetAsync(wb.counters, 0, sizeof(DrawCounters), st);
     k_geometry<<<blocks, GT, 0, st>>>(p, wb);
     k_rec_index<<<blocks < 148u * 8u ? blocks : 148u * 8u, GT, 0, st>>>(wb, blocks);
     return 2;

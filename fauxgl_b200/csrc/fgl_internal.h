@@ -241,10 +241,11 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n_max, con
 int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsigned int *n_dev, uint32_t n_max,
                       int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st);
 
-int launch_geometry(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
+// counters_clean: the previous draw's last kernel left the draw counters zeroed (no memset node needed)
+int launch_geometry(const DrawParams &p, const WorkBuffers &wb, bool counters_clean, cudaStream_t st);
 // fused geometry + span stage of large draws: k_front, then k_seg_index leaves (seg_key[0], seg_val[0]) in
 // primitive order, like launch_geometry + launch_spans
-int launch_front(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
+int launch_front(const DrawParams &p, const WorkBuffers &wb, bool counters_clean, cudaStream_t st);
 int launch_seg_index(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
 int launch_spans(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
 int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
@@ -252,7 +253,8 @@ int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cuda
 // to it by the last kernel (k_shade's last CTA) -- otherwise the caller launches k_accumulate
 int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,
                   DrawCounters *acc, bool *accumulated, cudaStream_t st);
-// acc += cur (total/updated pixels, overflow, needs): one thread
+// acc += cur (total/updated pixels, overflow, needs): one thread.  (k_shade's last CTA then zeroes *cur for the next
+// draw, which saves that draw its memset node.)
 __device__ __forceinline__ void accumulate_counters(const DrawCounters *cur, DrawCounters *acc) {
     acc->total_pixels += cur->total_pixels;
     acc->updated_pixels += cur->updated_pixels;

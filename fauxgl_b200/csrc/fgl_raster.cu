@@ -728,7 +728,12 @@ k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
-            if (atomicAdd(&wb.counters->shade_done, 1u) == gridDim.x - 1u) accumulate_counters(wb.counters, acc);
+            if (atomicAdd(&wb.counters->shade_done, 1u) == gridDim.x - 1u) {
+                accumulate_counters(wb.counters, acc);
+                // every CTA is past its last read of the counters: leave them zeroed for the next draw
+                unsigned int *w = reinterpret_cast<unsigned int *>(wb.counters);
+                for (unsigned k = 0; k < sizeof(DrawCounters) / sizeof(unsigned int); k++) w[k] = 0u;
+            }
         }
     }
 }
