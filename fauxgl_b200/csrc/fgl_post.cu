@@ -113,7 +113,23 @@ k_resolve(const uint32_t *__restrict__ src, int sw, int sh, uint32_t *__restrict
     __syncthreads();
     // pass 2: vertical (resizeRGBA on the transposed temporary)
     const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
-    if (ox < dw && oy < dh) {
+    if (ox < dw && oy < dh && fast4) {
+        // the same fast path for the vertical pass: eight taps from shared memory, bytes transposed per channel,
+        // two DP4A per channel; sum == 1024 makes the truncating division a shift and the clamp a no-op
+        // (the weights add up to 1024 and every byte is <= 255).  No alpha condition here: pass 2 does not premultiply.
+        const uint32_t *col = s_temp + (threadIdx.y * 4) * RES_OX + threadIdx.x;
+        const uint32_t p0 = col[0], p1 = col[RES_OX], p2 = col[2 * RES_OX], p3 = col[3 * RES_OX];
+        const uint32_t p4 = col[4 * RES_OX], p5 = col[5 * RES_OX], p6 = col[6 * RES_OX], p7 = col[7 * RES_OX];
+        const uint32_t lo = __byte_perm(p0, p1, 0x5140), hi = __byte_perm(p2, p3, 0x5140);      // r r g g
+        const uint32_t lo2 = __byte_perm(p0, p1, 0x7362), hi2 = __byte_perm(p2, p3, 0x7362);    // b b a a
+        const uint32_t mo = __byte_perm(p4, p5, 0x5140), mi = __byte_perm(p6, p7, 0x5140);
+        const uint32_t mo2 = __byte_perm(p4, p5, 0x7362), mi2 = __byte_perm(p6, p7, 0x7362);
+        const uint32_t rr = __dp4a(__byte_perm(mo, mi, 0x5410), cB, __dp4a(__byte_perm(lo, hi, 0x5410), cA, 0u));
+        const uint32_t gg = __dp4a(__byte_perm(mo, mi, 0x7632), cB, __dp4a(__byte_perm(lo, hi, 0x7632), cA, 0u));
+        const uint32_t bb = __dp4a(__byte_perm(mo2, mi2, 0x5410), cB, __dp4a(__byte_perm(lo2, hi2, 0x5410), cA, 0u));
+        const uint32_t aa = __dp4a(__byte_perm(mo2, mi2, 0x7632), cB, __dp4a(__byte_perm(lo2, hi2, 0x7632), cA, 0u));
+        dst[(size_t)oy * dw + ox] = (rr >> 10) | ((gg >> 10) << 8) | ((bb >> 10) << 16) | ((aa >> 10) << 24);
+    } else if (ox < dw && oy < dh) {
         int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
         for (int i = 0; i < W.flen; i++) {
             const int coeff = W.coeff[i];
