@@ -160,7 +160,9 @@ k_span_place(const __grid_constant__ DrawParams p, const __grid_constant__ WorkB
 constexpr int TR_THREADS = 1024;
 // Each CTA owns a contiguous part of the sorted array and goes over it twice: first it only counts the strips
 // that start there (heavy / light), reserves its share of the busy list with ONE global atomic per list, then
-// it fills in the entries (ranks inside the CTA from shared-memory counters).
+// it fills in the entries (ranks inside the CTA from shared-memory counters).  A thread takes four consecutive
+// keys per step with one 16-byte load (plus the key before them), so a bin starts where a key differs from its
+// predecessor; only those few positions look 95 keys ahead for the heavy test.
 __global__ void __launch_bounds__(TR_THREADS)
 k_tile_ranges(const uint32_t *__restrict__ keys, DrawCounters *__restrict__ ctr, uint32_t n_max,
               uint2 *__restrict__ busy_list, uint32_t ntiles, TileCtl *ctl) {
@@ -170,24 +172,43 @@ k_tile_ranges(const uint32_t *__restrict__ keys, DrawCounters *__restrict__ ctr,
     if (ctr->overflow) return;  // the draw is going to be re-issued: its keys are incomplete
     const uint32_t n = min(ctr->n_segs, n_max);
     const uint32_t lane = threadIdx.x & 31;
+    constexpr uint32_t STEP = TR_THREADS * 4u;
     uint32_t per = (n + gridDim.x - 1) / gridDim.x;
-    per = (per + TR_THREADS - 1) / TR_THREADS * TR_THREADS;
+    per = (per + STEP - 1) / STEP * STEP;
     const uint64_t b64 = (uint64_t)blockIdx.x * per;
     const uint32_t beg = b64 < n ? (uint32_t)b64 : n, end = b64 + per < n ? (uint32_t)(b64 + per) : n;
     if (threadIdx.x < 2) { s_cnt[threadIdx.x] = 0; s_fill[threadIdx.x] = 0; }
     __syncthreads();
-    auto classify = [&](uint32_t i, uint32_t &k, bool &heavy) {  // does a strip start at i?
-        if (i >= end) return false;
-        k = keys[i];
-        if (!(i == 0 || keys[i - 1] != k)) return false;
-        heavy = i + HEAVY_SEGS - 1u < n && keys[i + HEAVY_SEGS - 1u] == k;
-        return true;
+    // the four keys at i .. i+3 (i a multiple of 4) and the one before them; returns the mask of positions where a
+    // bin starts and, of those, the heavy ones
+    auto classify4 = [&](uint32_t i, uint32_t k[4], uint32_t &heavy) {
+        uint32_t starts = 0;
+        heavy = 0;
+        if (i >= end) return starts;
+        if (i + 3u < n) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(keys + i);
+            k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++) k[u] = i + u < n ? keys[i + u] : 0xffffffffu;
+        }
+        uint32_t prev = i ? keys[i - 1u] : ~k[0];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) {
+            if (i + u < end && k[u] != prev) {
+                starts |= 1u << u;
+                if (i + u + HEAVY_SEGS - 1u < n && keys[i + u + HEAVY_SEGS - 1u] == k[u]) heavy |= 1u << u;
+            }
+            prev = k[u];
+        }
+        return starts;
     };
     uint32_t nh = 0, nl = 0;
-    for (uint32_t i = beg + threadIdx.x; i < end; i += TR_THREADS) {
-        uint32_t k = 0;
-        bool heavy = false;
-        if (classify(i, k, heavy)) { if (heavy) nh++; else nl++; }
+    for (uint32_t i = beg + threadIdx.x * 4u; i < end; i += STEP) {
+        uint32_t k[4], heavy;
+        const uint32_t starts = classify4(i, k, heavy);
+        nh += (uint32_t)__popc(heavy);
+        nl += (uint32_t)__popc(starts & ~heavy);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { nh += __shfl_down_sync(0xffffffffu, nh, o); nl += __shfl_down_sync(0xffffffffu, nl, o); }
@@ -198,25 +219,33 @@ k_tile_ranges(const uint32_t *__restrict__ keys, DrawCounters *__restrict__ ctr,
         s_base[1] = s_cnt[1] ? atomicAdd(&ctl->nlight, s_cnt[1]) : 0u;
     }
     __syncthreads();
-    for (uint32_t i0 = beg; i0 < end; i0 += TR_THREADS) {
-        const uint32_t i = i0 + threadIdx.x;
-        uint32_t k = 0;
-        bool heavy = false;
-        const bool starts = classify(i, k, heavy);
-        const uint32_t mh = __ballot_sync(0xffffffffu, starts && heavy), ml = __ballot_sync(0xffffffffu, starts && !heavy);
+    for (uint32_t i0 = beg; i0 < end; i0 += STEP) {  // (all threads of a warp iterate together: shuffles below)
+        const uint32_t i = i0 + threadIdx.x * 4u;
+        uint32_t k[4], heavy;
+        const uint32_t starts = classify4(i, k, heavy);
+        const uint32_t ch = (uint32_t)__popc(heavy), cl = (uint32_t)__popc(starts & ~heavy);
+        // ranks inside the warp (inclusive scans), the warp's base from the CTA counters
+        uint32_t ih = ch, il = cl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t th = __shfl_up_sync(0xffffffffu, ih, o), tl = __shfl_up_sync(0xffffffffu, il, o);
+            if ((int)lane >= o) { ih += th; il += tl; }
+        }
+        const uint32_t toth = __shfl_sync(0xffffffffu, ih, 31), totl = __shfl_sync(0xffffffffu, il, 31);
         uint32_t wh = 0, wl = 0;
         if (lane == 0) {
-            if (mh) wh = atomicAdd(&s_fill[0], (uint32_t)__popc(mh));
-            if (ml) wl = atomicAdd(&s_fill[1], (uint32_t)__popc(ml));
+            if (toth) wh = atomicAdd(&s_fill[0], toth);
+            if (totl) wl = atomicAdd(&s_fill[1], totl);
         }
         wh = __shfl_sync(0xffffffffu, wh, 0);
         wl = __shfl_sync(0xffffffffu, wl, 0);
-        if (starts) {
+        uint32_t ph = s_base[0] + wh + ih - ch, pl = s_base[1] + wl + il - cl;
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) {
+            if (!((starts >> u) & 1u)) continue;
             // (a sorted key array has at most ntiles bins; the bound keeps a corrupted one from writing outside the list)
-            const uint32_t lt = (1u << lane) - 1u;
-            const uint32_t ph = s_base[0] + wh + __popc(mh & lt), pl = s_base[1] + wl + __popc(ml & lt);
-            if (heavy) { if (ph < ntiles) busy_list[ph] = make_uint2(k, i); }
-            else if (pl < ntiles) busy_list[ntiles - 1u - pl] = make_uint2(k, i);
+            if ((heavy >> u) & 1u) { if (ph < ntiles) busy_list[ph] = make_uint2(k[u], i + u); ph++; }
+            else { if (pl < ntiles) busy_list[ntiles - 1u - pl] = make_uint2(k[u], i + u); pl++; }
         }
     }
 }
