@@ -113,10 +113,13 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n_max, con
 // four coalesced rounds of 32, so (warp, round, lane) order IS input order and the ranks below are stable:
 //   rank = pairs with the same digit in earlier warps of the tile      (prefix over warp_cnt[.][digit])
 //        + pairs with the same digit in earlier rounds of this warp    (running warp_cnt[warp][digit])
-//        + lanes with the same digit and a lower lane id               (MATCH.ANY)
+//        + lanes with the same digit and a lower lane id               (peer mask: one ballot per digit bit)
 // Four pairs per thread amortise the per-tile clearing and the prefix over the warps, which is what makes
 // 1024 bins affordable: strip ids of an 8K framebuffer (19 bits) sort in two passes instead of three.
 
+#ifndef FGL_RADIX_BALLOT
+#define FGL_RADIX_BALLOT 1  // peer mask from one ballot per digit bit (measured slightly faster than MATCH.ANY: sort stage 40.8 -> 38.8 us at 1080p, 165.5 -> 158.1 us at 8K)
+#endif
 constexpr int RADIX_THREADS = 1024;
 constexpr int RADIX_WARPS = RADIX_THREADS / 32;
 constexpr int RADIX_ITEMS = 4;
@@ -214,7 +217,16 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
             const uint32_t active = __ballot_sync(0xffffffffu, valid[r]);
             rank[r] = 0;
             if (valid[r]) {
+#if FGL_RADIX_BALLOT
+                uint32_t peers = active;  // lanes with the same digit, from one ballot per digit bit
+#pragma unroll
+                for (int b = 0; b < BITS; b++) {
+                    const uint32_t m = __ballot_sync(active, (d >> b) & 1u);
+                    peers &= ((d >> b) & 1u) ? m : ~m;
+                }
+#else
                 const uint32_t peers = __match_any_sync(active, d);
+#endif
                 const int leader = __ffs(peers) - 1;
                 uint32_t old = 0;
                 if (lane == leader) { old = warp_cnt[warp][d]; warp_cnt[warp][d] = old + __popc(peers); }
