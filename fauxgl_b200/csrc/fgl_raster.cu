@@ -492,6 +492,21 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     uint2 r0a = load_raw(e0.y + lane), r0b = load_raw(e0.y + 32 + lane);
     uint2 r1a = load_raw(e1.y + lane), r1b = load_raw(e1.y + 32 + lane);
     if constexpr (DEFERRED) gather_issue(sm.recbuf, wb.segv, q < nbusy ? pair_idx(e0.x, r0a) : NO_SEG, lane);
+    // the depth row of a strip is loaded one strip ahead as well, straight into registers (a strip belongs to one warp
+    // of this launch, so nobody else writes the row in between)
+    auto load_depth_row = [&](uint32_t strip_id, double d[STRIP_H]) {
+#pragma unroll
+        for (int h = 0; h < STRIP_H; h++) d[h] = 0;
+        if (strip_id == 0xffffffffu) return;
+        const int sx0 = (int)(strip_id % (uint32_t)p.tiles_x) * tile_w;
+        const size_t srow = (size_t)(strip_id / (uint32_t)p.tiles_x) * p.width + sx0;
+        const int stw = min(tile_w, p.width - sx0);
+#pragma unroll
+        for (int h = 0; h < STRIP_H; h++)
+            if (h < strip_h && lane + 32 * h < stw) d[h] = gdepth[srow + lane + 32 * h];
+    };
+    double dnext[STRIP_H];
+    load_depth_row(q < nbusy ? e0.x : 0xffffffffu, dnext);
     while (q < nbusy) {
         const uint32_t strip = e0.x, bin_beg = e0.y;
         const uint32_t strip1 = qpos(t_strip + 1) < nbusy ? e1.x : 0xffffffffu;  // the warp's next strip
@@ -502,8 +517,10 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             const uint32_t ik1 = pair_idx(strip1, r1a);
             if (ik1 != NO_SEG) prefetch_seg(wb.segv + ik1);
         }
-        if (strip1 != 0xffffffffu && lane < tile_w / 16)
-            prefetch_l2(gdepth + (size_t)(strip1 / (uint32_t)p.tiles_x) * p.width + (strip1 % (uint32_t)p.tiles_x) * tile_w + lane * 16);
+        double dcur[STRIP_H];
+#pragma unroll
+        for (int h = 0; h < STRIP_H; h++) dcur[h] = dnext[h];
+        load_depth_row(strip1, dnext);
         const long long t_begin = wb.tile_clock ? clock64() : 0;
         uint32_t nseg = 0;
         const int x0 = (int)(strip % (uint32_t)p.tiles_x) * tile_w;
@@ -518,7 +535,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             const int i = lane + 32 * h;
             if constexpr (DEFERRED) sm.winseg[i] = NO_WINNER;
             if (i < tw) {
-                sm.depth[i] = gdepth[grow + i];
+                sm.depth[i] = dcur[h];
                 if constexpr (!DEFERRED) sm.color[i] = gcolor[grow + i];
             }
         }
