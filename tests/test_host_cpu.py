@@ -213,3 +213,30 @@ def test_product_never_imports_the_oracle():
                     src = open(os.path.join(dirpath, fn), errors="replace").read()
                     assert "pyoracle" not in src and "fauxgl_oracle" not in src and "import oracle" not in src, \
                         os.path.join(dirpath, fn)
+
+
+def test_parse_obj_tables_and_fan_triangulation(tmp_path):
+    """mesh.ParseOBJ / LoadOBJ (obj.go:19-79): 1-based tables with a zero entry 0, negative indices counted from
+    the end, missing vt / vn -> entry 0, polygons as fans from their first vertex, FixNormals on zero normals."""
+    from fauxgl_b200 import LoadOBJ
+    from fauxgl_b200 import mesh as fmesh
+    path = tmp_path / "t.obj"
+    path.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0.5 2 0\nvt 0.25 0.75\nvn 0 0 1\n"
+                    "f 1/1/1 2/1/1 3/1/1 4/1/1\n"      # quad -> 2 triangles
+                    "f -5 -4 -3 -2 -1\n"                # pentagon, negative indices, no vt/vn -> 3 triangles
+                    "# comment\n\nf 1//1 2//1 5\n")
+    vs, vts, vns, corners = fmesh.ParseOBJ(str(path))
+    assert vs.shape == (6, 3) and vts.shape == (2, 3) and vns.shape == (2, 3) and (vs[0] == 0).all()
+    assert corners.shape == (6, 3, 3)
+    assert corners[:2, :, 0].tolist() == [[1, 2, 3], [1, 3, 4]]                     # fan from the first vertex
+    assert corners[2:5, :, 0].tolist() == [[1, 2, 3], [1, 3, 4], [1, 4, 5]]         # -5..-1 of 6 entries -> 1..5
+    assert (corners[2:5, :, 1:] == 0).all()                                         # missing vt / vn -> entry 0
+    assert corners[5].tolist() == [[1, 0, 1], [2, 0, 1], [5, 0, 0]]
+    m = LoadOBJ(str(path))
+    assert m.num_triangles == 6
+    assert (m.texture[0, :, :2] == [0.25, 0.75]).all() and (m.texture[2] == 0).all()
+    assert (m.normal[0] == [0, 0, 1]).all()
+    # zero normals are replaced by the face normal (triangle.go:46-58); the pentagon lies in z = 0 and its fan
+    # triangles wind CCW, CCW, CW
+    assert (m.normal[2:4] == [0, 0, 1]).all() and (m.normal[4, :, 2] == -1).all() and (m.normal[4, :, :2] == 0).all()
+    assert (m.normal[5, 2] == m.normal[5, 0]).all()                                 # corner 3 had no vn: face normal (0,0,1)
