@@ -99,7 +99,10 @@ struct TileCtl {
     uint32_t nheavy, nlight;  // busy_list[0 .. nheavy) = heavy strips, busy_list[ntiles-1 .. ntiles-nlight] = the others
     uint32_t head, _pad;
 };
-constexpr uint32_t HEAVY_SEGS = 96;  // a strip with at least this many segments is queued first
+#ifndef FGL_HEAVY_SEGS
+#define FGL_HEAVY_SEGS 96
+#endif
+constexpr uint32_t HEAVY_SEGS = FGL_HEAVY_SEGS;  // a strip with at least this many segments is queued first
 
 // ---- per-draw device constants ------------------------------------------------------
 struct DrawParams {
