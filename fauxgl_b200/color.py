@@ -53,3 +53,25 @@ def HexColor(x: str) -> Color:  # color.go:31-54
         r, g, b, a = int(x[0:2], 16), int(x[2:4], 16), int(x[4:6], 16), int(x[6:8], 16)
     d = 255.0
     return Color(r / d, g / d, b / d, a / d)
+
+
+def ycbcr_to_rgba64(y, cb, cr):
+    """What Go's ``color.YCbCr{Y, Cb, Cr}.RGBA()`` returns (image/color/ycbcr.go, the 16-bit variant of
+    YCbCrToRGB: fixed-point BT.601 with 0x10101 / 91881 / 22554 / 46802 / 116130), per texel, as an
+    (H, W, 4) uint16 array -- the TEX_RGBA64 upload of a texture that Go decoded to *image.YCbCr (every JPEG;
+    examples/capsule.go:35).  A Go host calls At(x, y).RGBA() itself; this numpy restatement (Go stdlib is not in
+    the reference tree: unpinned) only feeds the parity scene, oracle and device alike."""
+    import numpy as np
+    yy1 = np.asarray(y, dtype=np.int32) * 0x10101
+    cb1 = np.asarray(cb, dtype=np.int32) - 128
+    cr1 = np.asarray(cr, dtype=np.int32) - 128
+
+    def fix(v):
+        v = v.astype(np.int32)
+        ok = (v.view(np.uint32) & 0xff000000) == 0
+        return np.where(ok, v >> 8, ~(v >> 31) & 0xffff).astype(np.uint16)
+    r = fix(yy1 + 91881 * cr1)
+    g = fix(yy1 - 22554 * cb1 - 46802 * cr1)
+    b = fix(yy1 + 116130 * cb1)
+    a = np.full(r.shape, 0xffff, dtype=np.uint16)
+    return np.stack([r, g, b, a], axis=-1)

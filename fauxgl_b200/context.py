@@ -50,7 +50,7 @@ class RasterizeInfo(NamedTuple):
 class _State(C.Structure):
     _fields_ = [("read_depth", C.c_int32), ("write_depth", C.c_int32), ("write_color", C.c_int32),
                 ("alpha_blend", C.c_int32), ("wireframe", C.c_int32), ("front_face", C.c_int32),
-                ("cull", C.c_int32), ("_pad", C.c_int32), ("line_width", C.c_double), ("depth_bias", C.c_double)]
+                ("cull", C.c_int32), ("x_guard", C.c_int32), ("line_width", C.c_double), ("depth_bias", C.c_double)]
 
 
 class _Shader(C.Structure):
@@ -214,7 +214,7 @@ class Fence:
 class DeviceTexture:
     def __init__(self, ctx: "Context", tex: ImageTexture):
         self.handle = _P()
-        px = np.ascontiguousarray(tex.pixels, dtype=np.uint8)
+        px = np.ascontiguousarray(tex.pixels)   # uint8 texels, or uint16 for TEX_RGBA64
         _check(capi().fgl_texture_create(ctx._h, px.ctypes.data, tex.Width, tex.Height, tex.format,
                                          C.byref(self.handle)), ctx._h)
         self._fin = weakref.finalize(self, capi().fgl_texture_destroy, self.handle)
@@ -392,6 +392,10 @@ class Context:
         self.Cull = CullBack
         self.LineWidth = 2.0
         self.DepthBias = 0.0
+        # Not a field of the reference: False keeps its index rule (context.go:223-228: only i = y*W + x is
+        # range-checked, so a fat line leaving the screen sideways aliases into the neighbouring row); True drops
+        # every fragment with x outside [0, Width) instead.
+        self.XGuard = False
         self._meshes = weakref.WeakKeyDictionary()   # Mesh -> DeviceMesh
         self._textures = weakref.WeakKeyDictionary()  # ImageTexture -> DeviceTexture
         self._keep = None
@@ -460,6 +464,7 @@ class Context:
         s.read_depth, s.write_depth, s.write_color = int(self.ReadDepth), int(self.WriteDepth), int(self.WriteColor)
         s.alpha_blend, s.wireframe = int(self.AlphaBlend), int(self.Wireframe)
         s.front_face, s.cull = int(self.FrontFace), int(self.Cull)
+        s.x_guard = int(self.XGuard)
         s.line_width, s.depth_bias = float(self.LineWidth), float(self.DepthBias)
         return s
 
@@ -494,12 +499,30 @@ class Context:
         if isinstance(mesh, DeviceMesh):
             return mesh
         dm = self._meshes.get(mesh)
+        want = self._needed_attributes()
+        if dm is not None and not set(want) <= set(dm.attributes):
+            # first drawn with fewer attributes than this draw's shader reads (e.g. position+normal, now a
+            # TextureShader): the device copy's missing planes are zero -- upload the union instead
+            want = tuple(a for a in ("position", "normal", "texture", "color") if a in set(want) | set(dm.attributes))
+            dm = None
         if dm is None or (dm.num_triangles, dm.num_lines) != (mesh.num_triangles, mesh.num_lines):
-            dm = DeviceMesh(self, mesh, self.upload_attributes)
+            dm = DeviceMesh(self, mesh, want)
             self._meshes[mesh] = dm
         elif dm.generation != mesh.generation:
             dm.update(mesh)   # mutated on the host since the last draw: re-upload in place
         return dm
+
+    def _needed_attributes(self):
+        """``upload_attributes`` plus whatever the current shader reads beyond it (shader.go:44,75-96)."""
+        need = list(self.upload_attributes)
+        sh = self.Shader
+        if isinstance(sh, TextureShader) or (isinstance(sh, PhongShader) and sh.Texture is not None):
+            need.append("texture")
+        if isinstance(sh, PhongShader):
+            need.append("normal")
+            if sh.Texture is None and tuple(sh.ObjectColor) == (0.0, 0.0, 0.0, 0.0):
+                need.append("color")
+        return tuple(a for a in ("position", "normal", "texture", "color") if a in need)
 
     def DrawTriangles(self, mesh, first: int = 0, count: Optional[int] = None) -> RasterizeInfo:  # context.go:413
         dm = self.device_mesh(mesh)

@@ -3,6 +3,7 @@
 // translation units.  There is no CPU rendering path in this library: every
 // entry point either runs CUDA kernels or fails with an fgl_status.
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -18,7 +19,15 @@ namespace fgl { bool g_pdl = true; }
 
 namespace {
 
+// Error messages.  A failing call stores its message twice: thread-locally (a C/C++/ctypes caller asks right away
+// on the same thread) and, when a context is involved, in the context under a small mutex of its own (goroutines
+// migrate between OS threads from one cgo call to the next, so a Go caller can only rely on the context's copy).
+// Both carry a global sequence number; fgl_last_error(ctx) returns the NEWER of the two, copied into a
+// thread-local buffer, so the returned pointer is never invalidated by another thread.
 thread_local std::string t_last_error;
+thread_local unsigned long long t_last_seq = 0;
+thread_local std::string t_error_out;
+std::atomic<unsigned long long> g_error_seq{0};
 
 int fail(fgl_ctx *ctx, int code, const char *fmt, ...);
 
@@ -51,6 +60,10 @@ struct fgl_mesh {
     // buffers back and forth through these two events
     cudaEvent_t ev_uploaded, ev_drawn;
     bool has_events, upload_pending, drawn_recorded;
+    // The context whose streams order this mesh's uploads and in-place edits.  Any context of the same device may
+    // DRAW the mesh (read-only); update / transform / smooth-normals must go through the owner, and a mesh that is
+    // re-uploaded through the streaming entry point (events above) can only be drawn by its owner.
+    const fgl_ctx *owner;
 };
 
 struct fgl_fence {
@@ -77,7 +90,9 @@ struct fgl_ctx {
     cudaEvent_t ev_fb_free, ev_cleared;
     bool clear_overlap, clear_pending;
     std::mutex mu;
+    mutable std::mutex err_mu;         // guards err / err_seq only (fail() runs both inside and outside `mu`)
     std::string err;
+    unsigned long long err_seq;
     uint32_t *color;
     double *depth;
     uint32_t *resolved;
@@ -108,8 +123,14 @@ int fail(fgl_ctx *ctx, int code, const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
+    const unsigned long long seq = ++g_error_seq;
     t_last_error = buf;
-    if (ctx) ctx->err = buf;
+    t_last_seq = seq;
+    if (ctx) {
+        std::lock_guard<std::mutex> g(ctx->err_mu);
+        ctx->err = buf;
+        ctx->err_seq = seq;
+    }
     return code;
 }
 
@@ -257,6 +278,8 @@ int build_params(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const
                  uint64_t count, bool lines, DrawParams *p) {
     if (!state || !sh || !mesh) return fail(c, FGL_E_INVALID, "null state/shader/mesh");
     if (mesh->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on device %d, context on %d", mesh->device, c->device);
+    if (mesh->owner != c && mesh->has_events)
+        return fail(c, FGL_E_INVALID, "a mesh that is re-uploaded with fgl_mesh_update_async can only be drawn by the context that owns it");
     const uint64_t n = lines ? mesh->nl : mesh->nt;
     if (first > n || count > n - first) return fail(c, FGL_E_INVALID, "primitive range [%llu,+%llu) outside mesh of %llu",
                                                     (unsigned long long)first, (unsigned long long)count, (unsigned long long)n);
@@ -464,8 +487,12 @@ extern "C" {
 int fgl_abi_version(void) { return FGL_ABI_VERSION; }
 
 const char *fgl_last_error(const fgl_ctx *ctx) {
-    if (ctx && !ctx->err.empty()) return ctx->err.c_str();
-    return t_last_error.c_str();
+    t_error_out = t_last_error;
+    if (ctx) {
+        std::lock_guard<std::mutex> g(ctx->err_mu);
+        if (ctx->err_seq > t_last_seq) t_error_out = ctx->err;
+    }
+    return t_error_out.c_str();
 }
 
 int fgl_device_count(void) {
@@ -510,7 +537,7 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     CK(nullptr, cudaSetDevice(device));
     fgl_ctx *c = new (std::nothrow) fgl_ctx();
     if (!c) return fail(nullptr, FGL_E_OOM, "host allocation failed");
-    c->device = device; c->w = width; c->h = height;
+    c->device = device; c->w = width; c->h = height; c->err_seq = 0;
     {
         const char *fm = getenv("FGL_FRONT");
         c->front_mode = !fm ? 0 : (strcmp(fm, "fused") == 0 ? 1 : (strcmp(fm, "split") == 0 ? 2 : 0));
@@ -685,7 +712,7 @@ int fgl_mesh_create(fgl_ctx *c, const fgl_mesh_desc *d, fgl_mesh **out) {
     fgl_mesh *m = new (std::nothrow) fgl_mesh();
     if (!m) return fail(c, FGL_E_OOM, "host allocation failed");
     memset(m, 0, sizeof *m);
-    m->device = c->device; m->nt = d->ntriangles; m->nl = d->nlines;
+    m->device = c->device; m->owner = c; m->nt = d->ntriangles; m->nl = d->nlines;
     m->staging_elems = (size_t)m->nt * (9 * 3 + 12) + (size_t)m->nl * (6 * 3 + 8);
     cudaError_t e = dev_alloc(&m->staging, m->staging_elems);
     if (e != cudaSuccess) { delete m; cudaGetLastError(); return fail(c, FGL_E_OOM, "staging: %s", cudaGetErrorString(e)); }
@@ -700,6 +727,7 @@ int fgl_mesh_update(fgl_ctx *c, fgl_mesh *m, const fgl_mesh_desc *d) {
     if (rc) return rc;
     if (!m || !d) return fail(c, FGL_E_INVALID, "null mesh/description");
     if (m->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on another device");
+    if (m->owner != c) return fail(c, FGL_E_INVALID, "a mesh is modified through the context it was created with (any context of the device may draw it)");
     if (d->ntriangles != m->nt || d->nlines != m->nl)
         return fail(c, FGL_E_INVALID, "fgl_mesh_update needs the same primitive counts (%llu/%llu vs %llu/%llu)",
                     (unsigned long long)d->ntriangles, (unsigned long long)d->nlines, (unsigned long long)m->nt,
@@ -714,6 +742,7 @@ int fgl_mesh_update_async(fgl_ctx *c, fgl_mesh *m, const fgl_mesh_desc *d) {
     if (rc) return rc;
     if (!m || !d) return fail(c, FGL_E_INVALID, "null mesh/description");
     if (m->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on another device");
+    if (m->owner != c) return fail(c, FGL_E_INVALID, "a mesh is modified through the context it was created with (any context of the device may draw it)");
     if (d->ntriangles != m->nt || d->nlines != m->nl)
         return fail(c, FGL_E_INVALID, "fgl_mesh_update_async needs the same primitive counts");
     std::lock_guard<std::mutex> lock(c->mu);
@@ -750,7 +779,7 @@ int fgl_mesh_create_stl(fgl_ctx *c, const uint8_t *records, uint64_t count, fgl_
     fgl_mesh *m = new (std::nothrow) fgl_mesh();
     if (!m) return fail(c, FGL_E_OOM, "host allocation failed");
     memset(m, 0, sizeof *m);
-    m->device = c->device; m->nt = count; m->nl = 0;
+    m->device = c->device; m->owner = c; m->nt = count; m->nl = 0;
     m->staging_elems = (size_t)m->nt * (9 * 3 + 12);  // 312 B per triangle: also holds the 50-byte records (+ padding)
     cudaError_t e = dev_alloc(&m->staging, m->staging_elems);
     if (e == cudaSuccess) e = dev_alloc(&m->tpos, (size_t)count * 9);
@@ -798,7 +827,7 @@ int fgl_mesh_create_indexed(fgl_ctx *c, const fgl_indexed_desc *d, fgl_mesh **ou
     fgl_mesh *m = new (std::nothrow) fgl_mesh();
     if (!m) return fail(c, FGL_E_OOM, "host allocation failed");
     memset(m, 0, sizeof *m);
-    m->device = c->device; m->nt = count; m->nl = 0;
+    m->device = c->device; m->owner = c; m->nt = count; m->nl = 0;
     m->staging_elems = (size_t)m->nt * (9 * 3 + 12);  // as fgl_mesh_create: later fgl_mesh_update calls land here
     double *tv = nullptr, *tvt = nullptr, *tvn = nullptr;
     int32_t *tc = nullptr;
@@ -885,6 +914,7 @@ int fgl_mesh_transform(fgl_ctx *c, fgl_mesh *m, const double matrix[16]) {
     if (rc) return rc;
     if (!m || !matrix) return fail(c, FGL_E_INVALID, "null mesh/matrix");
     if (m->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on another device");
+    if (m->owner != c) return fail(c, FGL_E_INVALID, "a mesh is modified through the context it was created with (any context of the device may draw it)");
     std::lock_guard<std::mutex> lock(c->mu);
     mesh_acquire(c, m);
     launch_mesh_transform(m->tpos, m->tnrm, (uint32_t)m->nt, 3, matrix, c->stream);
@@ -899,6 +929,7 @@ static int smooth_normals_common(fgl_ctx *c, fgl_mesh *m, bool with_threshold, d
     if (rc) return rc;
     if (!m) return fail(c, FGL_E_INVALID, "null mesh");
     if (m->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on another device");
+    if (m->owner != c) return fail(c, FGL_E_INVALID, "a mesh is modified through the context it was created with (any context of the device may draw it)");
     if (m->nt == 0) return FGL_OK;
     if (m->nt > 0x55555555ull) return fail(c, FGL_E_INVALID, "mesh too large for 32-bit corner indices");
     std::lock_guard<std::mutex> lock(c->mu);
@@ -972,13 +1003,14 @@ int fgl_texture_create(fgl_ctx *c, const uint8_t *rgba8, int width, int height, 
     int rc = check_ctx(c);
     if (rc) return rc;
     if (!rgba8 || !out || width <= 0 || height <= 0) return fail(c, FGL_E_INVALID, "bad texture arguments");
-    if (format != FGL_TEX_RGBA && format != FGL_TEX_NRGBA) return fail(c, FGL_E_INVALID, "bad texture format %d", format);
+    if (format != FGL_TEX_RGBA && format != FGL_TEX_NRGBA && format != FGL_TEX_RGBA64)
+        return fail(c, FGL_E_INVALID, "bad texture format %d", format);
     *out = nullptr;
     std::lock_guard<std::mutex> lock(c->mu);
     fgl_tex *t = new (std::nothrow) fgl_tex();
     if (!t) return fail(c, FGL_E_OOM, "host allocation failed");
     t->device = c->device; t->w = width; t->h = height; t->format = format; t->pixels = nullptr;
-    const size_t bytes = (size_t)width * height * 4;
+    const size_t bytes = (size_t)width * height * (format == FGL_TEX_RGBA64 ? 8 : 4);
     cudaError_t e = dev_alloc(&t->pixels, bytes);
     if (e == cudaSuccess) e = cudaMemcpyAsync(t->pixels, rgba8, bytes, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -1043,7 +1075,8 @@ int fgl_sync(fgl_ctx *c, fgl_raster_info *info) {
         const DrawCounters hc = *c->host_counters;
         if (hc.overflow) {
             // grow so that re-issuing the frame succeeds
-            ensure_work(c, grown(c, hc));
+            rc = ensure_work(c, grown(c, hc));
+            if (rc) return rc;  // (out of memory while regrowing: re-issuing would not help)
             return fail(c, FGL_E_OVERFLOW, "an async draw outgrew its work buffers (now regrown): re-issue the frame");
         }
         if (info) { info->total_pixels = hc.total_pixels; info->updated_pixels = hc.updated_pixels; }
@@ -1097,7 +1130,8 @@ int fgl_fence_wait(fgl_ctx *c, fgl_fence *f, fgl_raster_info *info) {
     const DrawCounters hc = *f->counters;
     if (hc.overflow) {
         std::lock_guard<std::mutex> lock(c->mu);
-        ensure_work(c, grown(c, hc));
+        rc = ensure_work(c, grown(c, hc));
+        if (rc) return rc;
         return fail(c, FGL_E_OVERFLOW, "an async draw of this frame outgrew its work buffers (now regrown): re-issue the frame");
     }
     if (info) { info->total_pixels = hc.total_pixels; info->updated_pixels = hc.updated_pixels; }

@@ -96,6 +96,21 @@ FGL_DI int32_t sat_i32(long long v) {
     return (int32_t)(v < -L ? -L : (v > L ? L : v));
 }
 
+// Does the box stay inside the framebuffer sideways?  Then none of its pixels aliases into another row under the
+// reference's index rule, and the x-guard rule and the reference's agree on it.
+FGL_DI bool box_on_screen_x(const DrawParams &p, int32_t x0, int32_t x1) {
+    return p.state.x_guard || ((unsigned)x0 < (unsigned)p.width && (unsigned)x1 < (unsigned)p.width);
+}
+// Upper bound of the strips one scanline of the box [x0, x1] can touch (the segment regions are sized with it).
+FGL_DI uint32_t box_cols(const DrawParams &p, int32_t x0, int32_t x1) {
+    if (box_on_screen_x(p, x0, x1))
+        return (uint32_t)((min(x1, p.width - 1) >> p.tile_shift) - (max(x0, 0) >> p.tile_shift) + 1);
+    // its span in the linear index space, plus one strip per row boundary it crosses
+    const long long span = (long long)x1 - x0;
+    const long long cols = (span >> p.tile_shift) + 3 + span / p.width;
+    return (uint32_t)min(cols, (long long)p.tiles_x * ((long long)p.height + 2));
+}
+
 // Integer bounding box of a screen triangle, context.go:155-160, and its on-screen scanlines.
 struct BBox { int32_t x0, x1, y0, y1; bool visible; uint32_t rows, cols; };  // cols: strips a row can touch
 FGL_DI BBox compute_bbox(const DrawParams &p, V3 s0, V3 s1, V3 s2) {
@@ -106,18 +121,28 @@ FGL_DI BBox compute_bbox(const DrawParams &p, V3 s0, V3 s1, V3 s2) {
     b.x1 = sat_i32(go_int(ceil(mxx)));
     b.y0 = sat_i32(go_int(floor(mny)));
     b.y1 = sat_i32(go_int(ceil(mxy)));
-    // pixels outside the framebuffer are dropped (x-guard rule), so only the
-    // on-screen part of the box is binned
-    const int32_t cx0 = max(b.x0, 0), cx1 = min(b.x1, p.width - 1);
-    const int32_t cy0 = max(b.y0, 0), cy1 = min(b.y1, p.height - 1);
-    b.visible = cx0 <= cx1 && cy0 <= cy1;
     // The forward-differencing chains are replayed from (x0, y0); a box that starts
     // millions of pixels off screen (infinite/overflowing coordinates -- the reference
     // itself would spin for 2^63 iterations on those) is dropped instead of walked.
     constexpr int32_t FAR = 1 << 22;
-    if (b.x0 < -FAR || b.y0 < -FAR || b.x1 > FAR || b.y1 > FAR) b.visible = false;
-    b.rows = b.visible ? (uint32_t)(cy1 - cy0 + 1) : 0u;
-    b.cols = b.visible ? (uint32_t)((cx1 >> p.tile_shift) - (cx0 >> p.tile_shift) + 1) : 0u;
+    const bool absurd = b.x0 < -FAR || b.y0 < -FAR || b.x1 > FAR || b.y1 > FAR;
+    if (box_on_screen_x(p, b.x0, b.x1)) {
+        // only the on-screen part of the box can keep pixels
+        const int32_t cx0 = max(b.x0, 0), cx1 = min(b.x1, p.width - 1);
+        const int32_t cy0 = max(b.y0, 0), cy1 = min(b.y1, p.height - 1);
+        b.visible = !absurd && cx0 <= cx1 && cy0 <= cy1;
+        b.rows = b.visible ? (uint32_t)(cy1 - cy0 + 1) : 0u;
+    } else {
+        // The reference's index rule (context.go:223-228, fgl_walk.cuh row_x_range): row y keeps the pixels with
+        // -y*W <= x <= (H-y)*W - 1.  Rows of the box for which that range meets [x0, x1]:
+        const long long W = p.width, H = p.height;
+        const int cy0 = row_base(p, b.x1, b.y0);
+        const long long yhi = floor_div(H * W - 1 - (long long)b.x0, W);
+        const int cy1 = (int)min((long long)b.y1, yhi);
+        b.visible = !absurd && cy0 <= cy1 && b.x0 <= b.x1;
+        b.rows = b.visible ? (uint32_t)(cy1 - cy0 + 1) : 0u;
+    }
+    b.cols = b.visible ? box_cols(p, b.x0, b.x1) : 0u;
     return b;
 }
 
@@ -832,7 +857,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     uint32_t seg_run = 0;  // segments this block has stored so far (block-uniform)
     unsigned long long covered = 0;
     ParkedSeg first;
-    first.w0 = first.w1 = first.w2 = 0; first.x = 0; first.cnt = 0; first.key = 0;
+    first.w0 = first.w1 = first.w2 = 0; first.x = 0; first.cnt = 0; first.key = 0; first.wrap = 0;
     if (!general) {
         // ---- fast blocks: no block barrier inside the walk.  The (record, scanline) items are split into FT/32
         // contiguous ranges (multiples of 32), one per warp; a warp's segments go to the block's region at the
@@ -869,7 +894,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         if (my0 < my1) {
             const uint32_t lo = locate(my0);
             const SRec &r = s_rec[s_order[lo]];
-            const uint32_t cols = (uint32_t)((min(r.x1, p.width - 1) >> p.tile_shift) - (max(r.x0, 0) >> p.tile_shift) + 1);
+            const uint32_t cols = box_cols(p, r.x0, r.x1);
             wbase = s_celloff[lo] + (my0 - s_rowoff[lo]) * cols;
         }
         bool have_region = false;
@@ -881,7 +906,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                 const uint32_t lo = locate(it);
                 ridx = s_order[lo];
                 const SRec &r = s_rec[ridx];
-                y = max(r.y0, 0) + (int)(it - s_rowoff[lo]);
+                y = row_base(p, r.x1, r.y0) + (int)(it - s_rowoff[lo]);
                 const unsigned long long before = covered;
                 nseg = walk_row_count(p, r, y, first, &covered);
                 if (p.prim_info && covered != before)  // per-primitive TotalPixels (fgl_draw_*_each)
@@ -906,7 +931,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                     const uint32_t slot = (uint32_t)slot64;
                     if (nseg == 1) {
                         wb.segv[slot] = make_segv(first.w0, first.w1, first.w2, r.ra, r.z0, r.z1, r.z2, r.s2y - r.s1y,
-                                                  r.s0y - r.s2y, r.s1y - r.s0y, tail, (uint16_t)first.x, (uint8_t)first.cnt);
+                                                  r.s0y - r.s2y, r.s1y - r.s0y, tail, (uint16_t)first.x, (uint8_t)first.cnt, first.wrap);
                         wb.seg_key[1][slot] = first.key;
                     } else {  // the scanline crosses strip boundaries: walk it again, storing every segment
                         unsigned long long dummy = 0;
@@ -948,7 +973,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                     if (s_rowoff[lo + step] <= it) lo += step;
                 ridx = s_order[lo];
                 const SRec &r = s_rec[ridx];
-                y = max(r.y0, 0) + (int)(it - s_rowoff[lo]);
+                y = row_base(p, r.x1, r.y0) + (int)(it - s_rowoff[lo]);
                 const unsigned long long before = covered;
                 nseg = walk_row_count(p, r, y, first, &covered);
                 if (p.prim_info && covered != before)  // per-primitive TotalPixels (fgl_draw_*_each)
@@ -967,7 +992,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                     const uint32_t slot = (uint32_t)slot64;
                     if (nseg == 1) {
                         wb.segv[slot] = make_segv(first.w0, first.w1, first.w2, r.ra, r.z0, r.z1, r.z2, r.s2y - r.s1y,
-                                                  r.s0y - r.s2y, r.s1y - r.s0y, tail, (uint16_t)first.x, (uint8_t)first.cnt);
+                                                  r.s0y - r.s2y, r.s1y - r.s0y, tail, (uint16_t)first.x, (uint8_t)first.cnt, first.wrap);
                         wb.seg_key[1][slot] = first.key;
                     } else {  // the scanline crosses strip boundaries: walk it again, storing every segment
                         unsigned long long dummy = 0;

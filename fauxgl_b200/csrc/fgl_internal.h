@@ -52,6 +52,9 @@ static_assert(sizeof(Rec) == 176, "Rec layout");
 
 constexpr uint32_t REC_VMAP_MASK = 0x3f;    // 3 x 2 bits: source vertex of v0,v1,v2
 constexpr uint32_t REC_SRC_POOL = 1u << 6;  // src indexes the clip pool
+constexpr uint32_t REC_WRAP = 1u << 7;      // (segments only) the pixels lie outside [0, width) of the row they were covered in and
+                                            // alias into a neighbouring row (context.go:223-228): depth and blended colour are
+                                            // written there, an opaque colour is dropped (SetNRGBA's bounds check, :269)
 
 // Clip pool: vertices produced by ClipTriangle (clipping.go:54-74), AoS.
 struct ClipVertex {
@@ -68,7 +71,7 @@ struct __align__(16) Seg {
     double w0, w1, w2;  // w0,w1,w2 of context.go:208-213 at pixel x (before that pixel's increment)
     uint32_t rec;       // record index
     uint16_t x;         // first covered pixel (absolute column)
-    uint8_t yt;         // unused (strips are one row tall)
+    uint8_t yt;         // 1: the segment aliases into a neighbouring row (REC_WRAP of its SegV)
     uint8_t cnt;        // covered pixels (1..TILE_W)
 };
 static_assert(sizeof(Seg) == 32, "Seg layout");

@@ -138,22 +138,24 @@ FGL_DI void fragment_inline(const DrawParams &p, const fgl_state &st, const Work
         if (st.write_depth) sm.depth[pi] = z;
         if (st.write_color) {
             const uint32_t c8 = c_nrgba(color);
-            if (st.alpha_blend && color.a < 1) sm.color[pi] = blend_over(sm.color[pi], c8);
-            else sm.color[pi] = c8;
+            if (st.alpha_blend && color.a < 1) sm.color[pi] = blend_over(sm.color[pi], c8);  // PixOffset: lands where the index does
+            else if (!(v.flags & REC_WRAP)) sm.color[pi] = c8;  // SetNRGBA drops a pixel whose own x is outside the image, context.go:269
         }
     }
 }
 
 // Deferred mode, one fragment whose depth z is known: context.go:232 early-out, then (no discard possible)
 // the retest at :248; the winning segment is remembered for the shading kernel.
-FGL_DI void resolve_deferred(const fgl_state &st, StripMem<true> &sm, int pi, double z, uint32_t seg,
+FGL_DI void resolve_deferred(const fgl_state &st, StripMem<true> &sm, int pi, double z, uint32_t seg, bool wrapped,
                              unsigned long long &updated) {
     const double bz = z + st.depth_bias;
     const double dcur = sm.depth[pi];
     if (!(st.read_depth && bz > dcur) && (bz <= dcur || !st.read_depth)) {
         updated++;
         if (st.write_depth) sm.depth[pi] = z;
-        sm.winseg[pi] = seg;
+        // (a fragment that aliased in from a neighbouring row wins the depth but its opaque colour is dropped by
+        // SetNRGBA, context.go:269: the pixel keeps the colour of the last winner that was drawn in its own row)
+        if (!wrapped) sm.winseg[pi] = seg;
     }
 }
 
@@ -353,7 +355,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                         if constexpr (DEFERRED) {
                             const double b0 = w0 * v.ra, b1 = w1 * v.ra, b2 = w2 * v.ra;
                             const double z = b0 * v.z0 + b1 * v.z1 + b2 * v.z2;  // context.go:230
-                            resolve_deferred(st, t, pi, z, idx, my_updated);
+                            resolve_deferred(st, t, pi, z, idx, (v.flags & REC_WRAP) != 0, my_updated);
                         } else {
                             fragment_inline(p, st, wb, v, w0, w1, w2, pi, t, my_updated);
                         }
@@ -413,7 +415,8 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                 const int xa = (int)v.x - x0, cnt = (int)v.cnt;
                 const uint32_t have = __ballot_sync(0xffffffffu, idx != NO_SEG);
                 const uint32_t nfrag = __reduce_add_sync(0xffffffffu, (uint32_t)cnt);
-                const bool can_stage = nfrag <= (uint32_t)ZCAP;
+                // (staging replays depths only; aliased segments need the per-fragment colour rule of resolve_deferred)
+                const bool can_stage = nfrag <= (uint32_t)ZCAP && !__any_sync(0xffffffffu, cnt > 0 && (v.flags & REC_WRAP));
                 if (have && can_stage) stage_chunk(sm, v, idx, xa, cnt);
                 if (lane == 0) s_flag[warp] = have ? (can_stage ? 1u : 2u) : 0u;
                 if (have && !can_stage) sm.segidx[lane] = idx;
@@ -588,7 +591,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                 atomicAdd(&dbg[4 + path], (unsigned long long)nfrag);
             }
             if constexpr (DEFERRED) {
-                if (!disjoint && nfrag <= (uint32_t)ZCAP) {
+                if (!disjoint && nfrag <= (uint32_t)ZCAP && !__any_sync(0xffffffffu, cnt > 0 && (v.flags & REC_WRAP))) {
                     staged = true;
                     PHASE_CLOCK(pc2, nfrag)
                     stage_chunk(sm, v, idx, xa, cnt);

@@ -43,8 +43,15 @@ struct AttrSrc {
 // ---- texture.go -----------------------------------------------------------------------------
 FGL_DI C4 tex_at(const DrawParams &p, long long x, long long y) {  // image.At + MakeColor (color.go:25-29)
     if (x < 0 || y < 0 || x >= p.tex_w || y >= p.tex_h) return c4(0, 0, 0, 0);
+    uint32_t r, g, b, a;
+    if (p.tex_format == FGL_TEX_RGBA64) {  // the 16-bit values of Color.RGBA() themselves
+        const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p.tex) + (size_t)y * p.tex_w + x);
+        r = t.x & 0xffff; g = t.x >> 16; b = t.y & 0xffff; a = t.y >> 16;
+        const double d = 65535.0;
+        return c4((double)r / d, (double)g / d, (double)b / d, (double)a / d);
+    }
     const uint32_t t = __ldg(reinterpret_cast<const uint32_t *>(p.tex) + (size_t)y * p.tex_w + x);
-    uint32_t r = t & 0xff, g = (t >> 8) & 0xff, b = (t >> 16) & 0xff, a = t >> 24;
+    r = t & 0xff; g = (t >> 8) & 0xff; b = (t >> 16) & 0xff; a = t >> 24;
     if (p.tex_format == FGL_TEX_NRGBA) {  // color.NRGBA.RGBA(): premultiply
         r |= r << 8; r *= a; r /= 0xff;
         g |= g << 8; g *= a; g /= 0xff;

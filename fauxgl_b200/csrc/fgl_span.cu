@@ -101,16 +101,19 @@ k_span_walk(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBu
             }
             const uint32_t rid = s_slot[lo];  // records live at their block's slots, not in primitive order
             const RowSetup r = load_setup(wb.recs + rid);
-            const int y = max(r.y0, 0) + (int)(i - s_off[lo]);
+            const int y = row_base(p, r.x1, r.y0) + (int)(i - s_off[lo]);
             const unsigned long long before = covered;
             ParkedSeg f;
             const uint32_t nseg = walk_row_segments<false>(p, r, y, f, nullptr, nullptr, nullptr, 0, 0, &covered);
             wb.row_nseg[i] = nseg;
             if (nseg) {  // park the first segment (almost every scanline of a small triangle has exactly one)
                 Seg sg;
-                sg.w0 = f.w0; sg.w1 = f.w1; sg.w2 = f.w2; sg.rec = rid; sg.x = (uint16_t)f.x; sg.yt = 0; sg.cnt = (uint8_t)f.cnt;
+                sg.w0 = f.w0; sg.w1 = f.w1; sg.w2 = f.w2; sg.rec = rid; sg.x = (uint16_t)f.x; sg.cnt = (uint8_t)f.cnt;
+                sg.yt = f.wrap ? 1 : 0;
                 wb.row_first[i] = sg;
-                wb.row_key[i] = f.key;
+                // one segment: its strip; several: the scanline itself, which the place pass walks again (a row
+                // that aliases into its neighbours does not tell its own y through its first strip)
+                wb.row_key[i] = nseg == 1 ? f.key : (uint32_t)y;
             }
             if (p.prim_info && covered != before)  // per-primitive TotalPixels (fgl_draw_*_each)
                 atomicAdd(&p.prim_info[2 * (size_t)rec_primitive(wb, p, rid)], covered - before);
@@ -139,14 +142,15 @@ k_span_place(const __grid_constant__ DrawParams p, const __grid_constant__ WorkB
             if (base < wb.cap_segs) {  // records are visited in order here: the Rec reads are near-sequential
                 const Rec *rp = wb.recs + s.rec;
                 wb.segv[base] = make_segv(s.w0, s.w1, s.w2, rp->ra, rp->s[2], rp->s[5], rp->s[8], rp->s[7] - rp->s[4],
-                                          rp->s[1] - rp->s[7], rp->s[4] - rp->s[1], load_tail(rp), s.x, s.cnt);
+                                          rp->s[1] - rp->s[7], rp->s[4] - rp->s[1], load_tail(rp), s.x, s.cnt,
+                                          s.yt ? REC_WRAP : 0u);
                 wb.seg_key[0][base] = key;
                 wb.seg_val[0][base] = base;
             }
         } else {  // the scanline crosses tile columns: walk it again, writing every segment
             const RowSetup r = load_setup(wb.recs + s.rec);
             const RecTail tail = load_tail(wb.recs + s.rec);
-            const int y = (int)(key / (uint32_t)p.tiles_x);
+            const int y = (int)key;
             ParkedSeg f;
             walk_row_segments<true>(p, r, y, f, &tail, wb.segv, wb.seg_key[0], base, wb.cap_segs, &dummy);
             for (uint32_t k = 0; k < n && base + k < wb.cap_segs; k++) wb.seg_val[0][base + k] = base + k;

@@ -18,11 +18,12 @@ namespace fgl {
 struct RecTail { double r0, r1, r2; uint32_t src, flags; };
 
 __device__ __forceinline__ SegV make_segv(double w0, double w1, double w2, double ra, double z0, double z1, double z2,
-                                          double a12, double a20, double a01, const RecTail &t, uint16_t x, uint8_t cnt) {
+                                          double a12, double a20, double a01, const RecTail &t, uint16_t x, uint8_t cnt,
+                                          uint32_t wrap = 0) {
     SegV v;
     v.w0 = w0; v.w1 = w1; v.w2 = w2; v.ra = ra; v.z0 = z0; v.z1 = z1; v.z2 = z2;
     v.a12 = a12; v.a20 = a20; v.a01 = a01;
-    v.r0 = t.r0; v.r1 = t.r1; v.r2 = t.r2; v.src = t.src; v.flags = t.flags;
+    v.r0 = t.r0; v.r1 = t.r1; v.r2 = t.r2; v.src = t.src; v.flags = t.flags | wrap;
     v.x = x; v.yt = 0; v.cnt = cnt; v._pad0 = 0; v._pad[0] = v._pad[1] = 0;
     return v;
 }
@@ -30,10 +31,38 @@ __device__ __forceinline__ SegV make_segv(double w0, double w1, double w2, doubl
 // First segment of a row, kept in registers between the counting walk and the write.
 struct ParkedSeg {
     double w0, w1, w2;
-    int32_t x;      // first covered pixel
+    int32_t x;      // first covered pixel: column in the row it lands in
     uint32_t cnt;   // covered pixels
     uint32_t key;   // strip id
+    uint32_t wrap;  // REC_WRAP if the segment lies outside [0, width) of its own row (it aliases into a neighbour row)
 };
+
+// Which pixels of row y the reference keeps (context.go:223-228): i = y*W + x must satisfy 0 <= i < W*H; x itself
+// is never range-checked, so a covered pixel left or right of the framebuffer aliases into a neighbouring row --
+// it lands on pixel (i mod W, i div W): depth is tested and written there, a blended colour too (PixOffset,
+// :259), an opaque colour is dropped by SetNRGBA's bounds check (:269).  With state.x_guard such pixels are
+// dropped instead.  [xlo, xhi] is the range of x that is kept in row y (empty when xlo > xhi).
+__device__ __forceinline__ void row_x_range(const DrawParams &p, int y, long long &xlo, long long &xhi) {
+    if (p.state.x_guard) {
+        const bool on = y >= 0 && y < p.height;
+        xlo = 0; xhi = on ? (long long)p.width - 1 : -1;
+    } else {
+        xlo = -(long long)y * p.width;
+        xhi = (long long)(p.height - y) * p.width - 1;
+    }
+}
+__device__ __forceinline__ long long floor_div(long long a, long long b) {  // b > 0
+    const long long q = a / b;
+    return (a % b < 0) ? q - 1 : q;
+}
+// First row of the bounding box [x0, x1] x [y0, ..] that can keep a pixel: the (record, scanline) items of the
+// walk are counted from it.  On-screen boxes (0 <= x1 < width, the common case) start at max(y0, 0).
+__device__ __forceinline__ int row_base(const DrawParams &p, int x1, int y0) {
+    int ylo = 0;
+    if (!p.state.x_guard && (unsigned)x1 >= (unsigned)p.width)  // smallest y with -y*W <= x1
+        ylo = (int)-floor_div((long long)x1, (long long)p.width);
+    return max(y0, ylo);
+}
 
 // Per-triangle constants of the row walk (context.go:167-181).
 struct EdgeSetup {
@@ -68,14 +97,25 @@ __device__ __forceinline__ uint32_t walk_row_core(const DrawParams &p, const Edg
     if (d < 0) d = 0;
     double w0 = w00 + e.a12 * d, w1 = w01 + e.a20 * d, w2 = w02 + e.a01 * d;
     long long x = (long long)e.x0 + go_int(d);
-    const long long xend = min((long long)e.x1, (long long)p.width - 1);
+    long long xlo, xhi;
+    row_x_range(p, y, xlo, xhi);
+    const long long xend = min((long long)e.x1, xhi);
     if (x > xend) return 0;
-    for (; x < 0; x++) { w0 += e.a12; w1 += e.a20; w2 += e.a01; }  // left of the framebuffer: dropped (x-guard rule)
-    uint32_t nseg = 0, cnt = 0;
-    int col = -1, sx = 0;
-    double sw0 = 0, sw1 = 0, sw2 = 0;
+    // Pixels the reference tests but cannot keep (i < 0, or x outside the framebuffer under the x-guard rule): the
+    // chain of adds runs over them, and so does wasInside (context.go:216-219 come before the index test).
     bool was_inside = false;
-    const uint32_t key_row = (uint32_t)y * (uint32_t)p.tiles_x;  // strip id = y * tiles_x + column
+    for (; x < xlo; x++) {
+        const double b0 = w0 * e.ra, b1 = w1 * e.ra, b2 = w2 * e.ra;
+        if (b0 < 0 || b1 < 0 || b2 < 0) { if (was_inside) return 0; }
+        else was_inside = true;
+        w0 += e.a12; w1 += e.a20; w2 += e.a01;
+    }
+    // where pixel x of this row lands: (tx, ty) = (i mod W, i div W), advanced incrementally
+    const long long q = floor_div(x, (long long)p.width);
+    int tx = (int)(x - q * p.width), ty = y + (int)q;
+    uint32_t nseg = 0, cnt = 0, skey = 0, swrap = 0;
+    int sx = 0;
+    double sw0 = 0, sw1 = 0, sw2 = 0;
     // Exact early exit.  fl(w + a) is monotone in w, so an edge value whose per-pixel increment is <= 0 never
     // grows along the row, and neither does b = fl(w * ra) for ra > 0: once such a b is negative, every later
     // pixel of the row is outside as well -- the reference would test them all and find nothing.
@@ -88,16 +128,18 @@ __device__ __forceinline__ uint32_t walk_row_core(const DrawParams &p, const Edg
             if ((n12 && b0 < 0) || (n20 && b1 < 0) || (n01 && b2 < 0)) break;
         } else {
             was_inside = true;
-            const int c = (int)x >> p.tile_shift;
-            if (cnt == 0 || c != col) {
-                if (cnt > 0) { emit(sw0, sw1, sw2, sx, cnt, key_row + (uint32_t)col); *covered += cnt; nseg++; }
-                col = c; sx = (int)x; sw0 = w0; sw1 = w1; sw2 = w2; cnt = 0;
+            const uint32_t key = (uint32_t)ty * (uint32_t)p.tiles_x + (uint32_t)(tx >> p.tile_shift);
+            if (cnt == 0 || key != skey) {  // a new strip (also: the next row, after a wrap)
+                if (cnt > 0) { emit(sw0, sw1, sw2, sx, cnt, skey, swrap); *covered += cnt; nseg++; }
+                skey = key; sx = tx; sw0 = w0; sw1 = w1; sw2 = w2; cnt = 0;
+                swrap = ty != y ? REC_WRAP : 0u;
             }
             cnt++;
         }
         w0 += e.a12; w1 += e.a20; w2 += e.a01;  // context.go:211-213
+        if (++tx == p.width) { tx = 0; ty++; }
     }
-    if (cnt > 0) { emit(sw0, sw1, sw2, sx, cnt, key_row + (uint32_t)col); *covered += cnt; nseg++; }
+    if (cnt > 0) { emit(sw0, sw1, sw2, sx, cnt, skey, swrap); *covered += cnt; nseg++; }
     return nseg;
 }
 
@@ -129,6 +171,20 @@ __device__ __forceinline__ bool any_neg3(double b0, double b1, double b2) {
     return m != 0;
 }
 
+// The general walker as an out-of-line call that only reports the first segment (rows that alias into neighbours).
+static __device__ __noinline__ uint32_t walk_row_general(const DrawParams &p, const EdgeSetup e, int y, double w00, double w01,
+                                                  double w02, ParkedSeg *first, unsigned long long *covered) {
+    ParkedSeg f;
+    f.w0 = f.w1 = f.w2 = 0; f.x = 0; f.cnt = 0; f.key = 0; f.wrap = 0;
+    uint32_t k = 0;
+    const uint32_t n = walk_row_core(p, e, y, w00, w01, w02, [&](double sw0, double sw1, double sw2, int sx, uint32_t cnt, uint32_t key, uint32_t wrap) {
+        if (k == 0) { f.w0 = sw0; f.w1 = sw1; f.w2 = sw2; f.x = sx; f.cnt = cnt; f.key = key; f.wrap = wrap; }
+        k++;
+    }, covered);
+    *first = f;
+    return n;
+}
+
 // Count pass of the fused front end: the covered run of row y, found with two lean loops (skip the pixels left of
 // the run, then count the run) instead of the per-pixel strip bookkeeping of walk_row_core -- the same chain of adds
 // and the same tests, so the run, and the edge values at its first pixel, are those of walk_row_core bit for bit;
@@ -153,10 +209,21 @@ __device__ __forceinline__ uint32_t walk_row_count(const DrawParams &p, const R 
     double w0 = w00 + a12 * d, w1 = w01 + a20 * d, w2 = w02 + a01 * d;
     // x0 + int(d) of the clamped d (context.go:207); beyond 2^40 the row starts right of any bounding box
     long long xl = (long long)r.x0 + (di < 0 ? 0ll : (di > (1ll << 40) ? (1ll << 40) : di));
-    const int xe = min(r.x1, p.width - 1);
-    if (xl > (long long)xe) return 0;
-    for (; xl < 0; xl++) { w0 += a12; w1 += a20; w2 += a01; }  // left of the framebuffer: dropped (x-guard rule)
-    if (xl > (long long)xe) return 0;
+    long long xlo, xhi;
+    row_x_range(p, y, xlo, xhi);
+    const long long xe64 = min((long long)r.x1, xhi);
+    if (xl > xe64) return 0;
+    // A row that starts in front of the pixels the reference can keep, or reaches beyond the right edge, may alias
+    // into neighbouring rows (row_x_range): the general walker cuts it by the rows it lands in.
+    if (xl < max(xlo, 0ll) || xe64 >= (long long)p.width) {  // rare: out of line, its state stays off the hot path's registers
+        ParkedSeg tmp;
+        unsigned long long cov = 0;
+        const uint32_t ns = walk_row_general(p, edge_setup(r), y, w00, w01, w02, &tmp, &cov);
+        first = tmp;
+        *covered += cov;
+        return ns;
+    }
+    const int xe = (int)xe64;
     int x = (int)xl;
     const double ra = r.ra;
     // Exact early exit, see walk_row_core: an edge whose per-pixel increment is <= 0 never recovers (ra > 0).
@@ -170,7 +237,7 @@ __device__ __forceinline__ uint32_t walk_row_count(const DrawParams &p, const R 
         w0 += a12; w1 += a20; w2 += a01;  // context.go:211-213
         if (++x > xe) return 0;
     }
-    first.w0 = w0; first.w1 = w1; first.w2 = w2; first.x = x;
+    first.w0 = w0; first.w1 = w1; first.w2 = w2; first.x = x; first.wrap = 0;
     const int xs = x;
     do {  // the run: up to the first outside pixel (context.go:216-218) or the end of the row
         w0 += a12; w1 += a20; w2 += a01;
@@ -197,15 +264,15 @@ __device__ __forceinline__ uint32_t walk_row_segments(const DrawParams &p, const
     double w00 = r.w00, w01 = r.w01, w02 = r.w02;
     for (int yy = r.y0; yy < y; yy++) { w00 += e.b12; w01 += e.b20; w02 += e.b01; }  // context.go:275-277
     uint32_t k = 0;
-    return walk_row_core(p, e, y, w00, w01, w02, [&](double sw0, double sw1, double sw2, int sx, uint32_t cnt, uint32_t key) {
+    return walk_row_core(p, e, y, w00, w01, w02, [&](double sw0, double sw1, double sw2, int sx, uint32_t cnt, uint32_t key, uint32_t wrap) {
         if (WRITE) {
             const uint32_t slot = base + k;
             if (slot < cap) {
-                segv[slot] = make_segv(sw0, sw1, sw2, r.ra, r.z0, r.z1, r.z2, e.a12, e.a20, e.a01, *tail, (uint16_t)sx, (uint8_t)cnt);
+                segv[slot] = make_segv(sw0, sw1, sw2, r.ra, r.z0, r.z1, r.z2, e.a12, e.a20, e.a01, *tail, (uint16_t)sx, (uint8_t)cnt, wrap);
                 keys[slot] = key;
             }
         } else if (k == 0) {
-            first.w0 = sw0; first.w1 = sw1; first.w2 = sw2; first.x = sx; first.cnt = cnt; first.key = key;
+            first.w0 = sw0; first.w1 = sw1; first.w2 = sw2; first.x = sx; first.cnt = cnt; first.key = key; first.wrap = wrap;
         }
         k++;
     }, covered);

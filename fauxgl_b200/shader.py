@@ -14,7 +14,7 @@ from .matrix import Matrix
 from .vector import Vector
 
 SHADER_SOLID, SHADER_TEXTURE, SHADER_PHONG = 1, 2, 3
-TEX_RGBA, TEX_NRGBA = 0, 1
+TEX_RGBA, TEX_NRGBA, TEX_RGBA64 = 0, 1, 2
 
 
 class ImageTexture:
@@ -22,10 +22,11 @@ class ImageTexture:
     Go image type the decoder would have produced, because MakeColor
     (color.go:25-29) goes through its RGBA() method: TEX_RGBA for *image.RGBA
     (8-bit RGB PNGs decode to it with A=255), TEX_NRGBA for *image.NRGBA
-    (8-bit RGBA PNGs), whose RGBA() premultiplies."""
+    (8-bit RGBA PNGs), whose RGBA() premultiplies; TEX_RGBA64 for every other
+    image type: ``pixels`` is (H,W,4) uint16 holding what At(x,y).RGBA() returns."""
 
     def __init__(self, pixels: np.ndarray, format: int = TEX_RGBA):
-        pixels = np.ascontiguousarray(pixels, dtype=np.uint8)
+        pixels = np.ascontiguousarray(pixels, dtype=np.uint16 if int(format) == TEX_RGBA64 else np.uint8)
         assert pixels.ndim == 3 and pixels.shape[2] == 4
         self.pixels = pixels
         self.format = int(format)

@@ -1,11 +1,15 @@
 // cgo binding of libfauxgl_b200.so (include/fauxgl_b200.h) for the fauxgl
 // package.  One call per DrawTriangles/DrawLines, never per primitive.
 //
-// cgo may not pass memory that contains Go pointers, and []*Triangle is a slice
-// of pointers: the triangles are gathered into flat float64 arrays
-// ([T][3][k], the layout fgl_mesh_desc takes) before the call.  That gather is
-// the only per-triangle work left on the host and happens once per mesh upload,
-// not per frame.
+// cgo pointer rules.  C may not be handed Go memory that itself contains Go
+// pointers -- neither []*Triangle nor a Go-allocated fgl_mesh_desc whose fields
+// point into Go slices (cgocheck panics with "cgo argument has Go pointer to
+// unpinned Go pointer").  So the vertices are gathered into ONE block of C
+// memory per device mesh (page-locked, fgl_host_alloc: no Go pointers inside,
+// and H2D copies from it run at full PCIe rate), and the fgl_mesh_desc passed
+// to the library holds only C pointers into that block.  Plain []uint8 /
+// []float64 buffers (Pix, DepthBuffer) contain no pointers and are passed
+// directly, pinned by cgo for the duration of the call.
 //
 // Build: CGO_CFLAGS=-I<repo>/include CGO_LDFLAGS="-L<repo>/fauxgl_b200 -lfauxgl_b200"
 // (or the #cgo lines below with the library installed system-wide).
@@ -37,6 +41,7 @@ type stateDesc struct {
 	readDepth, writeDepth, writeColor, alphaBlend, wireframe bool
 	frontFace, cull                                          int
 	lineWidth, depthBias                                     float64
+	xGuard                                                   bool
 }
 
 type shaderDesc struct {
@@ -52,11 +57,17 @@ type shaderDesc struct {
 type deviceContext struct{ h *C.fgl_ctx }
 type deviceTexture struct{ h *C.fgl_tex }
 type deviceMesh struct {
-	h      *C.fgl_mesh
-	nt, nl int
-	fp     meshFingerprint
-	stale  bool
+	h       *C.fgl_mesh
+	nt, nl  int
+	host    unsafe.Pointer // C memory (fgl_host_alloc): the flattened attributes, [pos|nrm|tex|col] triangles then lines
+	hostLen int            // float64 elements in host
+	sum     uint64         // content hash of the flattened attributes the device copy holds
+	stale   bool           // InvalidateMesh: upload on the next draw whatever the hash says
+	lastUse uint64         // LRU stamp (Context.useClock)
 }
+
+// bytes the device copy occupies (planes + the staging area of the same size)
+func (m *deviceMesh) deviceBytes() int { return 2 * 8 * m.hostLen }
 
 func deviceFromEnv() int {
 	if v, err := strconv.Atoi(os.Getenv("FAUXGL_DEVICE")); err == nil {
@@ -116,100 +127,162 @@ func (d *deviceContext) resolve(factor int, dst []uint8) error {
 }
 
 // newTexture uploads an ImageTexture.  *image.RGBA (what Go's PNG decoder yields
-// for 8-bit RGB) and *image.NRGBA (8-bit RGBA) are passed through; MakeColor's
-// RGBA() conversion for each is reproduced on the device (color.go:25-29).
+// for 8-bit RGB) and *image.NRGBA (8-bit RGBA) are passed through as bytes;
+// MakeColor's RGBA() conversion for each is reproduced on the device
+// (color.go:25-29).  Every other image type -- *image.YCbCr from a JPEG
+// (examples/capsule.go:35), Gray, Paletted, RGBA64, NRGBA64, CMYK ... -- is
+// converted HERE with its own At(x, y).RGBA(), the call MakeColor makes, and
+// uploaded as the resulting 16-bit values (FGL_TEX_RGBA64): exact for any
+// image.Image, and the conversion stays in Go's image package.
 func (d *deviceContext) newTexture(t *ImageTexture) (*deviceTexture, error) {
-	var pix []uint8
-	var stride, format int
-	switch im := t.Image.(type) {
+	var format int
+	var bytes int
+	w, h := t.Width, t.Height
+	if w <= 0 || h <= 0 {
+		return nil, errors.New("fauxgl: empty texture image")
+	}
+	var src []uint8
+	var stride int
+	format, bytes = C.FGL_TEX_RGBA64, 8*w*h
+	switch im := t.Image.(type) { // (byte fast paths only for images whose origin is (0, 0), so that Pix row y is At(., y))
 	case *image.RGBA:
-		pix, stride, format = im.Pix, im.Stride, C.FGL_TEX_RGBA
-	case *image.NRGBA:
-		pix, stride, format = im.Pix, im.Stride, C.FGL_TEX_NRGBA
-	default:
-		return nil, errors.New("fauxgl: texture image type has no device path (need *image.RGBA or *image.NRGBA)")
-	}
-	if stride != 4*t.Width {
-		packed := make([]uint8, 4*t.Width*t.Height)
-		for y := 0; y < t.Height; y++ {
-			copy(packed[4*t.Width*y:4*t.Width*(y+1)], pix[stride*y:])
+		if im.Rect.Min == (image.Point{}) && im.Rect.Max.X >= w && im.Rect.Max.Y >= h {
+			src, stride, format, bytes = im.Pix, im.Stride, C.FGL_TEX_RGBA, 4*w*h
 		}
-		pix = packed
+	case *image.NRGBA:
+		if im.Rect.Min == (image.Point{}) && im.Rect.Max.X >= w && im.Rect.Max.Y >= h {
+			src, stride, format, bytes = im.Pix, im.Stride, C.FGL_TEX_NRGBA, 4*w*h
+		}
 	}
-	var h *C.fgl_tex
-	rc := C.fgl_texture_create(d.h, (*C.uint8_t)(unsafe.Pointer(&pix[0])), C.int(t.Width), C.int(t.Height), C.int(format), &h)
+	// stage in C memory: one copy, no Go pointers cross the boundary
+	buf := C.malloc(C.size_t(bytes))
+	if buf == nil {
+		return nil, errors.New("fauxgl: out of memory staging a texture")
+	}
+	defer C.free(buf)
+	if format == C.FGL_TEX_RGBA64 {
+		dst := unsafe.Slice((*uint16)(buf), 4*w*h)
+		i := 0
+		for y := 0; y < h; y++ { // ImageTexture samples At(x, y) with x, y from 0 (texture.go:56-59)
+			for x := 0; x < w; x++ {
+				r, g, bl, a := t.Image.At(x, y).RGBA()
+				dst[i], dst[i+1], dst[i+2], dst[i+3] = uint16(r), uint16(g), uint16(bl), uint16(a)
+				i += 4
+			}
+		}
+	} else {
+		dst := unsafe.Slice((*uint8)(buf), bytes)
+		for y := 0; y < h; y++ {
+			copy(dst[4*w*y:4*w*(y+1)], src[stride*y:stride*y+4*w])
+		}
+	}
+	var th *C.fgl_tex
+	rc := C.fgl_texture_create(d.h, (*C.uint8_t)(buf), C.int(w), C.int(h), C.int(format), &th)
 	if rc != 0 {
 		return nil, lastError(d.h, rc)
 	}
-	return &deviceTexture{h}, nil
+	return &deviceTexture{th}, nil
 }
 
 func (t *deviceTexture) destroy() { C.fgl_texture_destroy(t.h) }
 
-// flatten gathers []*Triangle / []*Line into the per-attribute arrays of fgl_mesh_desc.
-type flatMesh struct {
-	pos, nrm, tex, col     []float64
-	lpos, lnrm, ltex, lcol []float64
+// Layout of a device mesh's host block, in float64 elements: triangles [pos 9T | nrm 9T | tex 9T | col 12T],
+// then lines [pos 6L | nrm 6L | tex 6L | col 8L] -- the [n][verts][k] arrays fgl_mesh_desc takes.
+func hostElems(nt, nl int) int { return 39*nt + 26*nl }
+
+// mix folds one float64 into a running 64-bit content hash (xor-multiply-rotate; not cryptographic: it only has
+// to notice that a vertex changed between two draws of the same *Mesh).
+func mix(h uint64, v float64) uint64 {
+	h ^= math.Float64bits(v)
+	h *= 0x9E3779B97F4A7C15
+	return h<<29 | h>>35
 }
 
-func putVertex(v *Vertex, i int, pos, nrm, tex, col []float64) {
-	pos[3*i], pos[3*i+1], pos[3*i+2] = v.Position.X, v.Position.Y, v.Position.Z
-	nrm[3*i], nrm[3*i+1], nrm[3*i+2] = v.Normal.X, v.Normal.Y, v.Normal.Z
-	tex[3*i], tex[3*i+1], tex[3*i+2] = v.Texture.X, v.Texture.Y, v.Texture.Z
-	col[4*i], col[4*i+1], col[4*i+2], col[4*i+3] = v.Color.R, v.Color.G, v.Color.B, v.Color.A
-}
-
-func flatten(mesh *Mesh) *flatMesh {
+// flattenInto gathers []*Triangle / []*Line into buf (C memory) and returns the content hash of what it wrote.
+func flattenInto(mesh *Mesh, buf []float64) uint64 {
 	nt, nl := len(mesh.Triangles), len(mesh.Lines)
-	f := &flatMesh{
-		pos: make([]float64, 9*nt), nrm: make([]float64, 9*nt), tex: make([]float64, 9*nt), col: make([]float64, 12*nt),
-		lpos: make([]float64, 6*nl), lnrm: make([]float64, 6*nl), ltex: make([]float64, 6*nl), lcol: make([]float64, 8*nl),
+	pos, nrm, tex, col := buf[0:9*nt], buf[9*nt:18*nt], buf[18*nt:27*nt], buf[27*nt:39*nt]
+	h := uint64(nt)<<32 ^ uint64(nl)
+	put := func(v *Vertex, i int, pos, nrm, tex, col []float64) {
+		pos[3*i], pos[3*i+1], pos[3*i+2] = v.Position.X, v.Position.Y, v.Position.Z
+		nrm[3*i], nrm[3*i+1], nrm[3*i+2] = v.Normal.X, v.Normal.Y, v.Normal.Z
+		tex[3*i], tex[3*i+1], tex[3*i+2] = v.Texture.X, v.Texture.Y, v.Texture.Z
+		col[4*i], col[4*i+1], col[4*i+2], col[4*i+3] = v.Color.R, v.Color.G, v.Color.B, v.Color.A
+		h = mix(mix(mix(h, v.Position.X), v.Position.Y), v.Position.Z)
+		h = mix(mix(mix(h, v.Normal.X), v.Normal.Y), v.Normal.Z)
+		h = mix(mix(mix(h, v.Texture.X), v.Texture.Y), v.Texture.Z)
+		h = mix(mix(mix(mix(h, v.Color.R), v.Color.G), v.Color.B), v.Color.A)
 	}
 	for i, t := range mesh.Triangles {
-		putVertex(&t.V1, 3*i, f.pos, f.nrm, f.tex, f.col)
-		putVertex(&t.V2, 3*i+1, f.pos, f.nrm, f.tex, f.col)
-		putVertex(&t.V3, 3*i+2, f.pos, f.nrm, f.tex, f.col)
+		put(&t.V1, 3*i, pos, nrm, tex, col)
+		put(&t.V2, 3*i+1, pos, nrm, tex, col)
+		put(&t.V3, 3*i+2, pos, nrm, tex, col)
 	}
-	for i, l := range mesh.Lines {
-		putVertex(&l.V1, 2*i, f.lpos, f.lnrm, f.ltex, f.lcol)
-		putVertex(&l.V2, 2*i+1, f.lpos, f.lnrm, f.ltex, f.lcol)
+	l := buf[39*nt:]
+	lpos, lnrm, ltex, lcol := l[0:6*nl], l[6*nl:12*nl], l[12*nl:18*nl], l[18*nl:26*nl]
+	for i, ln := range mesh.Lines {
+		put(&ln.V1, 2*i, lpos, lnrm, ltex, lcol)
+		put(&ln.V2, 2*i+1, lpos, lnrm, ltex, lcol)
 	}
-	return f
+	return h
 }
 
-func ptr(s []float64) *C.double {
-	if len(s) == 0 {
-		return nil
-	}
-	return (*C.double)(unsafe.Pointer(&s[0]))
-}
-
-func (f *flatMesh) desc(nt, nl int) C.fgl_mesh_desc {
+// desc describes the host block to the library.  Every pointer in it is a C pointer (into m.host), so passing
+// &desc -- itself Go memory -- obeys the cgo rules.
+func (m *deviceMesh) desc() C.fgl_mesh_desc {
 	var d C.fgl_mesh_desc
+	nt, nl := m.nt, m.nl
+	at := func(off int) *C.double {
+		return (*C.double)(unsafe.Add(m.host, 8*off))
+	}
 	d.ntriangles, d.nlines = C.uint64_t(nt), C.uint64_t(nl)
-	d.position, d.normal, d.texture, d.color = ptr(f.pos), ptr(f.nrm), ptr(f.tex), ptr(f.col)
-	d.lposition, d.lnormal, d.ltexture, d.lcolor = ptr(f.lpos), ptr(f.lnrm), ptr(f.ltex), ptr(f.lcol)
+	if nt > 0 {
+		d.position, d.normal, d.texture, d.color = at(0), at(9*nt), at(18*nt), at(27*nt)
+	}
+	if nl > 0 {
+		b := 39 * nt
+		d.lposition, d.lnormal, d.ltexture, d.lcolor = at(b), at(b+6*nl), at(b+12*nl), at(b+18*nl)
+	}
 	return d
 }
 
+func (m *deviceMesh) hostSlice() []float64 {
+	return unsafe.Slice((*float64)(m.host), m.hostLen)
+}
+
 func (d *deviceContext) newMesh(mesh *Mesh) (*deviceMesh, error) {
-	f := flatten(mesh)
-	desc := f.desc(len(mesh.Triangles), len(mesh.Lines))
-	var h *C.fgl_mesh
-	if rc := C.fgl_mesh_create(d.h, &desc, &h); rc != 0 {
-		return nil, lastError(d.h, rc)
+	m := &deviceMesh{nt: len(mesh.Triangles), nl: len(mesh.Lines)}
+	m.hostLen = hostElems(m.nt, m.nl)
+	if rc := C.fgl_host_alloc(C.size_t(8*m.hostLen), &m.host); rc != 0 {
+		return nil, lastError(nil, rc)
 	}
-	return &deviceMesh{h: h, nt: len(mesh.Triangles), nl: len(mesh.Lines)}, nil
+	m.sum = flattenInto(mesh, m.hostSlice())
+	desc := m.desc()
+	if rc := C.fgl_mesh_create(d.h, &desc, &m.h); rc != 0 {
+		err := lastError(d.h, rc)
+		C.fgl_host_free(m.host)
+		return nil, err
+	}
+	return m, nil
 }
 
 func (m *deviceMesh) sameShape(mesh *Mesh) bool {
 	return m.nt == len(mesh.Triangles) && m.nl == len(mesh.Lines)
 }
 
-func (m *deviceMesh) update(d *deviceContext, mesh *Mesh) error {
-	f := flatten(mesh)
-	desc := f.desc(m.nt, m.nl)
-	return lastError(d.h, C.fgl_mesh_update(d.h, m.h, &desc))
+// refresh re-flattens the host mesh and uploads it only if its content differs from what the device holds (or the
+// mesh was invalidated).  Reports whether an upload happened.
+func (m *deviceMesh) refresh(d *deviceContext, mesh *Mesh) (bool, error) {
+	sum := flattenInto(mesh, m.hostSlice())
+	if sum == m.sum && !m.stale {
+		return false, nil
+	}
+	desc := m.desc()
+	if rc := C.fgl_mesh_update(d.h, m.h, &desc); rc != 0 {
+		return false, lastError(d.h, rc)
+	}
+	m.sum, m.stale = sum, false
+	return true, nil
 }
 
 // transform applies Mesh.Transform (mesh.go:167-175) to the device copy: an animate.go-style loop can rotate
@@ -238,23 +311,10 @@ func (m *deviceMesh) destroy() {
 		C.fgl_mesh_destroy(m.h)
 		m.h = nil
 	}
-}
-
-// meshFingerprint is a cheap change detector for meshes mutated through Mesh
-// methods between draws (mesh.Transform in examples/animate.go:66).
-type meshFingerprint struct {
-	nt, nl      int
-	first, last Vertex
-}
-
-func fingerprint(mesh *Mesh) meshFingerprint {
-	fp := meshFingerprint{nt: len(mesh.Triangles), nl: len(mesh.Lines)}
-	if fp.nt > 0 {
-		fp.first, fp.last = mesh.Triangles[0].V1, mesh.Triangles[fp.nt-1].V3
-	} else if fp.nl > 0 {
-		fp.first, fp.last = mesh.Lines[0].V1, mesh.Lines[fp.nl-1].V2
+	if m.host != nil {
+		C.fgl_host_free(m.host)
+		m.host = nil
 	}
-	return fp
 }
 
 func cbool(b bool) C.int32_t {
@@ -270,6 +330,7 @@ func (s stateDesc) c() C.fgl_state {
 	st.alpha_blend, st.wireframe = cbool(s.alphaBlend), cbool(s.wireframe)
 	st.front_face, st.cull = C.int32_t(s.frontFace), C.int32_t(s.cull)
 	st.line_width, st.depth_bias = C.double(s.lineWidth), C.double(s.depthBias)
+	st.x_guard = cbool(s.xGuard)
 	return st
 }
 

@@ -16,18 +16,25 @@
 //   - A Shader (or Texture) that is not one of the built-ins has no device
 //     equivalent: the draw returns a zero RasterizeInfo and Err() reports it.
 //     There is no CPU fallback.
-//   - Meshes are cached on the device by *Mesh pointer.  Mesh methods that
-//     mutate (Transform, Add, SetColor, ...) are detected through a cheap
-//     fingerprint (length + bounding box + first/last vertex); code that pokes
-//     mesh.Triangles[i].V1.Color directly must call ctx.InvalidateMesh(mesh).
+//   - Meshes are cached on the device by *Mesh pointer.  By default every draw
+//     re-flattens the host mesh into the mesh's pinned C block and compares a
+//     64-bit content hash over ALL vertex data with the device copy's: any
+//     mutation -- Mesh methods or direct field pokes -- is caught and
+//     re-uploaded; an unchanged mesh costs the flatten but no PCIe traffic.
+//     A program that never mutates a mesh after its first draw (or calls
+//     ctx.InvalidateMesh(mesh) when it does) sets ctx.MeshCache = MeshStatic
+//     and pays nothing per draw.  The cache is bounded (MaxCachedMeshes
+//     entries / MaxCachedMeshBytes of device memory, least recently used
+//     evicted), so a program that builds a new Mesh per frame does not leak.
 //   - Primitives are drawn in index order (the reference's goroutine schedule
 //     is non-deterministic on depth ties, DepthBias, blending and
 //     UpdatedPixels; index order is one of its legal schedules).
 //
-// NOTE: the build image has no Go toolchain, so this file has been written to
-// compile against the reference package but has not been compiled; all logic
-// lives below the C ABI, which is tested through the ctypes mirror
-// (fauxgl_b200/context.py) that makes exactly these calls.
+// NOTE: neither the build image nor the GPU box has a Go toolchain (probe:
+// profiles/r02_go_probe.txt), so this file has been written to compile against
+// the reference package but has not been compiled; all logic lives below the C
+// ABI, which is tested through the ctypes mirror (fauxgl_b200/context.py) and
+// the C++ mirror (include/fauxgl.hpp) that make exactly these calls.
 package fauxgl
 
 import (
@@ -84,14 +91,40 @@ type Context struct {
 	LineWidth   float64
 	DepthBias   float64
 
+	// Not in the reference.  XGuard: drop fragments with x outside [0, Width)
+	// instead of letting them alias into the neighbouring row as context.go:223-228
+	// does (the default, false, is the reference's behaviour).  MeshCache: see the
+	// package comment.
+	XGuard    bool
+	MeshCache MeshCachePolicy
+
 	// device side
 	mu       sync.Mutex
-	dev      *deviceContext            // b200.go
-	meshes   map[*Mesh]*deviceMesh     // device-resident copies
+	dev      *deviceContext        // b200.go
+	meshes   map[*Mesh]*deviceMesh // device-resident copies, bounded LRU
 	textures map[Texture]*deviceTexture
+	useClock uint64
 	err      error // sticky: first error of any call
 	hostOK   bool  // exported buffers mirror the device
 }
+
+// MeshCachePolicy decides how DrawMesh notices that a cached *Mesh changed on the host.
+type MeshCachePolicy int
+
+const (
+	// MeshCheck (default): re-flatten on every draw and compare a content hash of
+	// all vertex data; upload only when it differs.  Never renders stale geometry.
+	MeshCheck MeshCachePolicy = iota
+	// MeshStatic: trust the device copy until InvalidateMesh(mesh) is called.
+	MeshStatic
+)
+
+// Bounds of the device mesh cache (least recently used entries are evicted).
+var (
+	MaxCachedMeshes    = 64
+	MaxCachedMeshBytes = 8 << 30
+	MaxCachedTextures  = 32
+)
 
 // NewContext allocates the buffers on the device (GPU 0 unless FAUXGL_DEVICE
 // selects another).  It panics only if no CUDA device exists, because the
@@ -277,6 +310,12 @@ func (dc *Context) describeShader() (shaderDesc, error) {
 		}
 		dt, err := dc.dev.newTexture(it)
 		if err == nil {
+			if len(dc.textures) >= MaxCachedTextures { // bounded: drop them all, they are re-uploaded on use
+				for k, old := range dc.textures {
+					old.destroy()
+					delete(dc.textures, k)
+				}
+			}
 			dc.textures[t] = dt
 		}
 		return dt, err
@@ -302,7 +341,7 @@ func (dc *Context) describeShader() (shaderDesc, error) {
 
 func (dc *Context) state() stateDesc {
 	return stateDesc{dc.ReadDepth, dc.WriteDepth, dc.WriteColor, dc.AlphaBlend, dc.Wireframe,
-		int(dc.FrontFace), int(dc.Cull), dc.LineWidth, dc.DepthBias}
+		int(dc.FrontFace), int(dc.Cull), dc.LineWidth, dc.DepthBias, dc.XGuard}
 }
 
 // DrawTriangles and DrawLines take the reference's slices.  When the slice is
@@ -403,19 +442,20 @@ func (dc *Context) draw(mesh *Mesh, tris, lines, temporary bool) RasterizeInfo {
 }
 
 // deviceMeshFor returns the device copy of mesh, (re)uploading when the mesh is
-// new, was invalidated, or its fingerprint changed.
+// new, was invalidated, changed shape, or -- under MeshCheck -- its content hash
+// differs from the device copy's.
 func (dc *Context) deviceMeshFor(mesh *Mesh, temporary bool) (*deviceMesh, error) {
 	if temporary {
 		return dc.dev.newMesh(mesh)
 	}
-	fp := fingerprint(mesh)
+	dc.useClock++
 	if m, ok := dc.meshes[mesh]; ok {
-		if !m.stale && m.fp == fp {
-			return m, nil
-		}
 		if m.sameShape(mesh) {
-			err := m.update(dc.dev, mesh)
-			m.fp, m.stale = fp, false
+			m.lastUse = dc.useClock
+			if dc.MeshCache == MeshStatic && !m.stale {
+				return m, nil
+			}
+			_, err := m.refresh(dc.dev, mesh)
 			return m, err
 		}
 		m.destroy()
@@ -425,7 +465,30 @@ func (dc *Context) deviceMeshFor(mesh *Mesh, temporary bool) (*deviceMesh, error
 	if err != nil {
 		return nil, err
 	}
-	m.fp = fp
+	m.lastUse = dc.useClock
 	dc.meshes[mesh] = m
+	dc.evictMeshes(m)
 	return m, nil
+}
+
+// evictMeshes keeps the cache inside MaxCachedMeshes / MaxCachedMeshBytes, dropping
+// the least recently used entries (never `keep`, the mesh about to be drawn).
+func (dc *Context) evictMeshes(keep *deviceMesh) {
+	for {
+		total, n := 0, 0
+		var oldestKey *Mesh
+		var oldest *deviceMesh
+		for k, m := range dc.meshes {
+			total += m.deviceBytes()
+			n++
+			if m != keep && (oldest == nil || m.lastUse < oldest.lastUse) {
+				oldestKey, oldest = k, m
+			}
+		}
+		if oldest == nil || (n <= MaxCachedMeshes && total <= MaxCachedMeshBytes) {
+			return
+		}
+		oldest.destroy()
+		delete(dc.meshes, oldestKey)
+	}
 }

@@ -194,6 +194,7 @@ class Context {
     Face FrontFace = FaceCCW;
     Cull cull = CullBack;
     double LineWidth = 2, DepthBias = 0;
+    bool XGuard = false;  // not in the reference: true drops fragments with x outside [0, Width) (fgl_state.x_guard)
 
     Context(int width, int height, int device = 0) : Width(width), Height(height) { check(fgl_context_create(width, height, device, &h_)); }
     ~Context() {
@@ -244,7 +245,7 @@ class Context {
         if (mesh_src_ != &mesh || mesh_gen_ != mesh.generation) upload(mesh);
         st.read_depth = ReadDepth; st.write_depth = WriteDepth; st.write_color = WriteColor;
         st.alpha_blend = AlphaBlend; st.wireframe = Wireframe; st.front_face = FrontFace; st.cull = cull;
-        st.line_width = LineWidth; st.depth_bias = DepthBias;
+        st.line_width = LineWidth; st.depth_bias = DepthBias; st.x_guard = XGuard;
         sh.kind = shader.kind;
         std::memcpy(sh.matrix, shader.matrix.m, sizeof sh.matrix);
         auto p3 = [](double *d, Vector v) { d[0] = v.X; d[1] = v.Y; d[2] = v.Z; };

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FGL_ABI_VERSION 1
+#define FGL_ABI_VERSION 2
 
 typedef enum {
     FGL_OK = 0,
@@ -49,15 +49,24 @@ enum { FGL_CULL_NONE = 1, FGL_CULL_FRONT = 2, FGL_CULL_BACK = 3 };
 /* shader.go:11,30,49 -- the closed set of built-in shaders */
 enum { FGL_SHADER_SOLID = 1, FGL_SHADER_TEXTURE = 2, FGL_SHADER_PHONG = 3 };
 /* Which Go image type the texture decoded to; decides the RGBA() conversion
- * MakeColor applies (color.go:25-29): *image.RGBA or *image.NRGBA. */
-enum { FGL_TEX_RGBA = 0, FGL_TEX_NRGBA = 1 };
+ * MakeColor applies (color.go:25-29): *image.RGBA or *image.NRGBA, 4 bytes per texel.  Every other image type
+ * (*image.YCbCr from a JPEG -- examples/capsule.go:35 --, Gray, Paletted, RGBA64, NRGBA64 ...) is uploaded as
+ * FGL_TEX_RGBA64: per texel the four 16-bit values At(x, y).RGBA() returns (r, g, b, a as uint16, 8 bytes),
+ * which MakeColor divides by 0xffff -- exact for any image.Image, the conversion itself stays in the host
+ * language's image package. */
+enum { FGL_TEX_RGBA = 0, FGL_TEX_NRGBA = 1, FGL_TEX_RGBA64 = 2 };
 
 /* The render state fields of Context, context.go:47-55. */
 typedef struct {
     int32_t read_depth, write_depth, write_color, alpha_blend, wireframe;
     int32_t front_face;   /* FGL_FACE_*  */
     int32_t cull;         /* FGL_CULL_*  */
-    int32_t _pad;
+    /* 0 (default): the reference's index rule, context.go:223-228 -- a covered pixel is kept iff 0 <= y*W + x < W*H;
+     * x itself is never range-checked, so a fat line leaving the screen sideways aliases into the neighbouring
+     * row: depth is tested and written there and a blended colour too (PixOffset, :259), an opaque colour is
+     * dropped by SetNRGBA's bounds check (:269); all of them count in RasterizeInfo.  1: drop every fragment with
+     * x outside [0, width) instead (what a caller who considers the aliasing a bug wants). */
+    int32_t x_guard;
     double line_width;
     double depth_bias;
 } fgl_state;
@@ -186,8 +195,9 @@ int fgl_mesh_create_stl(fgl_ctx *ctx, const uint8_t *records, uint64_t count, fg
  * the zero box.  NaN coordinates are ignored (math.Min/Max would propagate them). */
 int fgl_mesh_bounds(fgl_ctx *ctx, const fgl_mesh *mesh, double min_xyz[3], double max_xyz[3]);
 
-/* NewImageTexture, texture.go:27-30.  rgba8: h rows of w RGBA8 texels. */
-int fgl_texture_create(fgl_ctx *ctx, const uint8_t *rgba8, int width, int height, int format, fgl_tex **out);
+/* NewImageTexture, texture.go:27-30.  texels: h rows of w texels, 4 bytes each (FGL_TEX_RGBA / FGL_TEX_NRGBA)
+ * or 4 x uint16 each (FGL_TEX_RGBA64), tightly packed. */
+int fgl_texture_create(fgl_ctx *ctx, const uint8_t *texels, int width, int height, int format, fgl_tex **out);
 int fgl_texture_destroy(fgl_tex *tex);
 
 /* DrawTriangles, context.go:413-433, over triangles [first, first+count) of

@@ -335,9 +335,14 @@ static int clip_line(Vertex l[2]) {
 /* image.Image.At + MakeColor (color.go:25-29); Go stdlib image/color RGBA(). */
 static C4 tex_at(const oshader *s, int64_t x, int64_t y) {
     if (x < 0 || y < 0 || x >= s->tex_w || y >= s->tex_h) return c4(0, 0, 0, 0);
-    const uint8_t *p = s->tex + ((size_t)y * (size_t)s->tex_w + (size_t)x) * 4;
+    const size_t t = (size_t)y * (size_t)s->tex_w + (size_t)x;
+    const uint8_t *p = s->tex + t * 4;
     uint32_t r, g, b, a;
-    if (s->tex_format == O_TEX_NRGBA) { /* color.NRGBA.RGBA() */
+    if (s->tex_format == O_TEX_RGBA64) { /* the 16-bit values of Color.RGBA() themselves (YCbCr, Gray, Paletted, *64 ...) */
+        uint16_t q[4];
+        memcpy(q, s->tex + t * 8, 8);
+        r = q[0]; g = q[1]; b = q[2]; a = q[3];
+    } else if (s->tex_format == O_TEX_NRGBA) { /* color.NRGBA.RGBA() */
         r = p[0]; r |= r << 8; r *= p[3]; r /= 0xff;
         g = p[1]; g |= g << 8; g *= p[3]; g /= 0xff;
         b = p[2]; b |= b << 8; b *= p[3]; b /= 0xff;

@@ -34,7 +34,8 @@ typedef struct {
 enum { O_SHADER_SOLID = 1, O_SHADER_TEXTURE = 2, O_SHADER_PHONG = 3 };
 enum { O_FACE_CW = 1, O_FACE_CCW = 2 };               /* context.go:13-17 */
 enum { O_CULL_NONE = 1, O_CULL_FRONT = 2, O_CULL_BACK = 3 }; /* context.go:21-26 */
-enum { O_TEX_RGBA = 0, O_TEX_NRGBA = 1 };  /* Go *image.RGBA vs *image.NRGBA */
+enum { O_TEX_RGBA = 0, O_TEX_NRGBA = 1,    /* Go *image.RGBA vs *image.NRGBA: 4 bytes per texel */
+       O_TEX_RGBA64 = 2 };                 /* any other image type: what At(x,y).RGBA() returns, 4 x uint16 per texel */
 
 /* shader.go:11-14, 30-33, 49-59 */
 typedef struct {

@@ -101,7 +101,7 @@ def make_oshader(shader) -> tuple:
     tex = d.get("texture")
     keep = None
     if tex is not None:
-        keep = np.ascontiguousarray(tex.pixels, dtype=np.uint8)
+        keep = np.ascontiguousarray(tex.pixels)   # uint8 texels, or uint16 for O_TEX_RGBA64
         s.has_texture = 1
         s.tex = keep.ctypes.data
         s.tex_h, s.tex_w = keep.shape[0], keep.shape[1]
@@ -112,7 +112,7 @@ def make_oshader(shader) -> tuple:
 class OracleContext:
     """Reference-shaped context running on the CPU oracle (context.go:40-81)."""
 
-    def __init__(self, width: int, height: int, x_guard: bool = True, threads: int = 1):
+    def __init__(self, width: int, height: int, x_guard: bool = False, threads: int = 1):
         self.Width, self.Height = width, height
         self.ColorBuffer = np.zeros((height, width, 4), dtype=np.uint8)   # image.NewNRGBA: zeroed
         self.DepthBuffer = np.empty((height, width), dtype=np.float64)
@@ -127,7 +127,7 @@ class OracleContext:
         self.Cull = 3        # CullBack
         self.LineWidth = 2.0
         self.DepthBias = 0.0
-        self.x_guard = x_guard
+        self.XGuard = x_guard           # False: the reference's rule (context.go:223-228); True: drop x outside [0, W)
         self.threads = threads
         self.ClearDepthBuffer()
 
@@ -139,7 +139,7 @@ class OracleContext:
         c.read_depth, c.write_depth, c.write_color = int(self.ReadDepth), int(self.WriteDepth), int(self.WriteColor)
         c.alpha_blend, c.wireframe = int(self.AlphaBlend), int(self.Wireframe)
         c.front_face, c.cull = int(self.FrontFace), int(self.Cull)
-        c.x_guard = int(self.x_guard)
+        c.x_guard = int(self.XGuard)
         c.line_width, c.depth_bias = float(self.LineWidth), float(self.DepthBias)
         return c
 

@@ -45,13 +45,19 @@ def main():
     save_mesh("bowser_mesh", LoadSTL(os.path.join(REF, "bowser.stl")))
     save_mesh("capsule_mesh", LoadOBJ(os.path.join(REF, "capsule.obj")), with_texture=True)
     save_mesh("cube_mesh", LoadSTL(os.path.join(REF, "cube.stl")))
+    # examples/texture.png (examples/square.go:36): the same pixels, re-encoded without the metadata chunks
+    from PIL import Image
+    im = Image.open(os.path.join(REF, "texture.png")).convert("RGB")
+    im.save(os.path.join(OUT, "texture.png"), optimize=True)
+    assert (np.asarray(Image.open(os.path.join(OUT, "texture.png"))) == np.asarray(im)).all()
+    print("texture.png", im.size, os.path.getsize(os.path.join(OUT, "texture.png")), "bytes")
 
     import scenes
     from oracle.pyoracle import OracleContext
     golden = {}
     for name in scenes.GOLDEN_SCENES:
         sc = scenes.SCENES[name]()
-        ctx = OracleContext(sc.width, sc.height, x_guard=True)
+        ctx = OracleContext(sc.width, sc.height)   # the reference's own index rule (x_guard off)
         infos = sc.run(ctx)
         golden[name] = {
             "width": sc.width, "height": sc.height,

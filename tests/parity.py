@@ -33,10 +33,12 @@ def compare_buffers(ocolor, odepth, gcolor, gdepth):
     }
 
 
-def run_both(scene, oracle_mod, gpu_ctx_cls, device=0):
-    octx = oracle_mod.OracleContext(scene.width, scene.height, x_guard=True)
+def run_both(scene, oracle_mod, gpu_ctx_cls, device=0, x_guard=False):
+    """x_guard=False (default) is the reference's own index rule on both sides (context.go:223-228)."""
+    octx = oracle_mod.OracleContext(scene.width, scene.height, x_guard=x_guard)
     oinfo = scene.run(octx)
     gctx = gpu_ctx_cls(scene.width, scene.height, device)
+    gctx.XGuard = x_guard
     ginfo = scene.run(gctx)
     gcolor, gdepth = gctx.Image(), gctx.DepthBuffer
     stats = compare_buffers(octx.ColorBuffer, octx.DepthBuffer, gcolor, gdepth)

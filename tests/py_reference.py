@@ -172,7 +172,7 @@ class PyContext:
                     continue
                 was_inside = True
                 i = y * W + xx
-                if i < 0 or i >= W * H or xx < 0 or xx >= W:
+                if i < 0 or i >= W * H:        # context.go:224: the index only -- x is never range-checked
                     continue
                 total += 1
                 z = b0 * s0[2] + b1 * s1[2] + b2 * s2[2]
@@ -198,7 +198,7 @@ class PyContext:
                             src = [(c8[k] * 0x101) * c8[3] // 0xff for k in range(3)] + [sa]
                             aa = (0xffff - sa) * 0x101
                             self.color[i] = [((self.color[i][k] * aa // 0xffff + src[k]) >> 8) & 0xff for k in range(4)]
-                        else:
+                        elif 0 <= xx < W:          # SetNRGBA's bounds check, context.go:269
                             self.color[i] = c8
             w00 += b12; w01 += b20; w02 += b01
         return (total, updated)

@@ -26,8 +26,18 @@ def load_fixture(name: str) -> Mesh:
     return Mesh(d["position"], d["normal"], d["texture"] if "texture" in d else None)
 
 
+def reference_texture() -> "ImageTexture":
+    """examples/texture.png of the reference (4096 x 4096 opaque RGB UV-checker, examples/square.go:36), re-encoded
+    pixel for pixel by tests/golden/make_fixtures.py.  Go's PNG decoder yields *image.RGBA (alpha 255) for it."""
+    from PIL import Image
+    rgb = np.asarray(Image.open(os.path.join(GOLDEN, "texture.png")).convert("RGB"))
+    px = np.concatenate([rgb, np.full(rgb.shape[:2] + (1,), 255, np.uint8)], axis=2)
+    return NewImageTexture(px, TEX_RGBA)
+
+
 def checker_texture(n=256, alpha=False) -> "ImageTexture":
-    """Deterministic procedural texture (texture.png is a 4096^2 checker we cannot ship)."""
+    """Small deterministic procedural texture (the NRGBA variant exercises the texel-alpha blend path,
+    which the opaque texture.png cannot)."""
     y, x = np.mgrid[0:n, 0:n]
     px = np.zeros((n, n, 4), dtype=np.uint8)
     chk = ((x // 16) + (y // 16)) & 1
@@ -144,6 +154,59 @@ def capsule_phong_texture():
     return Scene(768, 768, run)
 
 
+# ---- config 4 as composed in SURVEY 0.1: capsule.obj + texture.png through TextureShader (examples/square.go:54),
+# then the translucent and the wireframe + DepthBias passes of examples/shapes.go:71-78, capsule.go's camera ----
+def capsule_composed(scale=1):
+    mesh = load_fixture("capsule_mesh")
+    mesh.BiUnitCube()
+    tex = reference_texture()
+    eye, center, up = V(-3, 1, 2), V(0, 0, 0), V(0, 0, 1)
+    light = V(-1, 1, 0.25).Normalize()
+    W = H = 1024 * scale
+
+    def run(ctx):
+        ctx.ClearColorBufferWith(White)
+        matrix = _camera(eye, center, up, 40, 1.0, 1, 10)
+        ctx.Shader = NewTextureShader(matrix, tex)
+        infos = [ctx.DrawMesh(mesh)]
+        shader = NewPhongShader(matrix, light, eye)
+        shader.ObjectColor = HexColor("FFFF9D").Alpha(0.65)
+        shader.SpecularPower = 0
+        ctx.Shader = shader
+        infos.append(ctx.DrawMesh(mesh))
+        ctx.Wireframe = True
+        ctx.DepthBias = -0.00001
+        infos.append(ctx.DrawMesh(mesh))
+        return infos
+    return Scene(W, H, run)
+
+
+def capsule_ycbcr_texture():
+    """PhongShader + a texture whose Go image type is neither *image.RGBA nor *image.NRGBA (examples/capsule.go:35
+    loads a JPEG -> *image.YCbCr): the host converts with At(x,y).RGBA() and uploads the 16-bit values
+    (TEX_RGBA64).  The texels here are a deterministic stand-in run through Go's color.YCbCrToRGB restatement."""
+    from fauxgl_b200.shader import TEX_RGBA64
+    from fauxgl_b200.color import ycbcr_to_rgba64
+    mesh = load_fixture("capsule_mesh")
+    mesh.BiUnitCube()
+    n = 192
+    y, x = np.mgrid[0:n, 0:n]
+    Y = (40 + (x * 3 + y * 5) % 200).astype(np.uint8)
+    Cb = (128 + 90 * np.sin(x / 17.0)).astype(np.uint8)
+    Cr = (128 + 90 * np.cos(y / 23.0)).astype(np.uint8)
+    tex = NewImageTexture(ycbcr_to_rgba64(Y, Cb, Cr), TEX_RGBA64)
+    eye, center, up = V(-3, 1, 2), V(0, 0, 0), V(0, 0, 1)
+
+    def run(ctx):
+        ctx.ClearColorBufferWith(HexColor("#101418"))
+        matrix = _camera(eye, center, up, 40, 1.0, 1, 10)
+        shader = NewPhongShader(matrix, V(-1, 1, 0.25).Normalize(), eye)
+        shader.Texture = tex
+        ctx.Shader = shader
+        return [ctx.DrawMesh(mesh)]
+    return Scene(640, 640, run)
+
+
 # ---- examples/shapes.go:61-78: opaque pass, translucent pass, wireframe pass with DepthBias ----
 def shapes_multipass():
     rng = np.random.RandomState(1234)
@@ -213,6 +276,61 @@ def lines_scene():
         return infos
     return Scene(900, 500, run)
 
+
+
+# ---- the reference's index rule (context.go:223-228): only i = y*W + x is range-checked -----------------------
+def _offscreen_lines(W, H, lw, lw2):
+    """Lines and wireframe edges that leave the framebuffer sideways.  ClipLine / ClipTriangle cut them at the view
+    volume, i.e. exactly at x = 0 or x = W, and the fat-line quad then reaches LineWidth/2 beyond the border: the
+    reference keeps those pixels -- they alias into the neighbouring row (depth and blended colour are written there,
+    an opaque colour is dropped by SetNRGBA, all of them count in RasterizeInfo).  Corners: (W, -1) lands in row 0,
+    (-1, H) in row H-1, (-1, 0) and (W, H-1) fall off the buffer."""
+    quad = NewTriangleMesh(np.array([[(-0.95, -0.9, -0.1), (0.95, -0.9, 0.3), (0.95, 0.9, -0.1)],
+                                     [(-0.95, -0.9, -0.1), (0.95, 0.9, -0.1), (-0.95, 0.9, 0.3)]], dtype=np.float64))
+    segs = [((-2, 0.3, 0.2), (2, 0.3, 0.2)), ((0, 0, 0.1), (1.5, 1.5, 0.1)), ((0, 0, 0.1), (-1.5, -1.5, 0.1)),
+            ((0.2, 0, 0.0), (-1.5, 1.7, 0.0)), ((-0.2, 0, 0.0), (1.5, -1.7, 0.0)), ((1, -0.5, 0.4), (1, 0.5, -0.4)),
+            ((-1, -0.6, -0.3), (-1, 0.7, 0.5)), ((-3, -0.55, -0.2), (3, -0.5, 0.25)), ((0.97, -2, 0.15), (1.0, 2, 0.15))]
+    lines = NewLineMesh(np.array(segs, dtype=np.float64))
+    rng = np.random.RandomState(11)
+    lines.lcolor[:, :, :3] = rng.rand(len(segs), 2, 3)
+    lines.lcolor[:, :, 3] = 0.35 + 0.5 * rng.rand(len(segs), 2)
+    big = NewTriangleMesh(np.array([[(-3, -2.5, 0.05), (3.5, -0.2, 0.05), (-0.3, 3, 0.05)],
+                                    [(0.4, -0.8, -0.5), (2.5, 0.1, -0.5), (0.6, 0.7, -0.5)]], dtype=np.float64))
+    big.color[:, :, :] = np.array([0.2, 0.9, 0.4, 0.6])
+
+    def run(ctx):
+        ctx.ClearColorBufferWith(HexColor("#20242A"))
+        matrix = Orthographic(-1, 1, -1, 1, -1, 1)
+        ctx.Cull = CullNone
+        sh = NewPhongShader(matrix, V(0.3, 0.2, 1).Normalize(), V(0, 0, 5))
+        sh.ObjectColor = HexColor("#8090A0")
+        ctx.Shader = sh
+        infos = [ctx.DrawMesh(quad)]
+        ctx.Shader = NewSolidColorShader(matrix, HexColor("#E0C040"))      # opaque: depth-only winners + dropped colour
+        ctx.LineWidth = lw
+        infos.append(ctx.DrawLines(lines))
+        ctx.Shader = NewPhongShader(matrix, V(0, 0, 1), V(0, 0, 5))        # vertex colours, alpha < 1: blend path
+        ctx.DepthBias = -1e-3
+        ctx.LineWidth = lw2
+        infos.append(ctx.DrawLines(lines))
+        ctx.Wireframe = True                                              # edges of clipped triangles run along the border
+        ctx.LineWidth = lw
+        infos.append(ctx.DrawMesh(big))
+        ctx.Shader = NewSolidColorShader(matrix, Color(0.9, 0.3, 0.2, 1))
+        ctx.DepthBias = -2e-3
+        ctx.LineWidth = lw2
+        infos.append(ctx.DrawMesh(big))
+        return infos
+    return Scene(W, H, run)
+
+
+def offscreen_lines():
+    return _offscreen_lines(203, 77, 7.0, 3.0)
+
+
+def offscreen_lines_tiny():
+    """Line width larger than the framebuffer: fragments alias several rows away."""
+    return _offscreen_lines(40, 30, 90.0, 17.0)
 
 # ---- render-state matrix on one small mesh -------------------------------------------------------
 def _state_scene(apply):
@@ -361,8 +479,12 @@ SCENES: Dict[str, Callable[[], Scene]] = {
     "bowser_close": bowser_close,
     "capsule_texture": capsule_texture,
     "capsule_phong_texture": capsule_phong_texture,
+    "capsule_composed": capsule_composed,
+    "capsule_ycbcr_texture": capsule_ycbcr_texture,
     "shapes_multipass": shapes_multipass,
     "lines": lines_scene,
+    "offscreen_lines": offscreen_lines,
+    "offscreen_lines_tiny": offscreen_lines_tiny,
     "state_cull_front": state_cull_front,
     "state_cull_none_cw": state_cull_none_cw,
     "state_no_write_depth": state_no_write_depth,

@@ -176,7 +176,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libfauxgl_b200.so does not export " + name
         assert name in bound, "python binding misses " + name
-    assert lib.fgl_abi_version() == 1
+    assert lib.fgl_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_device():

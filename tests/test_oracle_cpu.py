@@ -31,7 +31,7 @@ def golden():
 @pytest.mark.parametrize("name", scenes.GOLDEN_SCENES)
 def test_oracle_matches_golden(name, golden, oracle_lib):
     sc = scenes.SCENES[name]()
-    ctx = pyoracle.OracleContext(sc.width, sc.height, x_guard=True)
+    ctx = pyoracle.OracleContext(sc.width, sc.height)   # the reference's own index rule
     infos = sc.run(ctx)
     g = golden[name]
     assert [list(map(int, i)) for i in infos] == g["info"]
@@ -65,9 +65,9 @@ def test_threaded_schedule_matches_sequential_when_order_free(oracle_lib):
 
 
 def test_x_guard_divergence_is_confined_to_offscreen_wrap(oracle_lib):
-    """DESIGN.md 'x-guard': the reference never range-checks x (context.go:223-228), so a fat
-    line leaving the screen wraps into the neighbouring row.  The adopted rule drops those
-    fragments.  Report and bound the divergence on the scene that provokes it."""
+    """The reference never range-checks x (context.go:223-228), so a fat line leaving the screen
+    aliases into the neighbouring row; oracle and device reproduce that by default.  The optional
+    x-guard rule (fgl_state.x_guard) drops those fragments: bound what it changes."""
     sc = scenes.lines_scene()
     faithful = pyoracle.OracleContext(sc.width, sc.height, x_guard=False)
     guarded = pyoracle.OracleContext(sc.width, sc.height, x_guard=True)
@@ -78,8 +78,7 @@ def test_x_guard_divergence_is_confined_to_offscreen_wrap(oracle_lib):
     print("x-guard divergent pixels:", len(xs), "of", diff.size, "TotalPixels", fi, gi)
     # wrapped fragments land within LineWidth of the left/right border only
     assert all(x < 8 or x >= sc.width - 8 for x in xs)
-    # this scene is built to provoke the quirk (lines leaving the screen on purpose): 49 of
-    # 450 000 pixels; the divergent count is reported in DESIGN.md rather than hidden
+    # this scene is built to provoke the quirk (lines leaving the screen on purpose): 49 of 450 000 pixels
     assert 0 < len(xs) < 100
     assert all(f[0] >= g[0] for f, g in zip(fi, gi))
 
@@ -157,7 +156,7 @@ def test_c_oracle_matches_python_restatement(oracle_lib):
     matrix = LookAt(eye, V(0, 0, 0), V(0, 0, 1)).Perspective(45, W / H, 0.5, 10)
     shader = NewPhongShader(matrix, V(0.3, 0.5, 1).Normalize(), eye)   # vertex colours (ObjectColor == Discard)
     for cull_back, bias in ((True, 0.0), (False, -1e-4)):
-        octx = pyoracle.OracleContext(W, H, x_guard=True)
+        octx = pyoracle.OracleContext(W, H)
         octx.Shader = shader
         octx.Cull = 3 if cull_back else 1
         octx.DepthBias = bias

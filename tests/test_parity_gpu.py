@@ -39,8 +39,22 @@ def test_scene_matches_oracle_under_both_front_ends(name, front, oracle_lib, gpu
     assert stats["gpu_info"] == stats["oracle_info"], stats
 
 
+@pytest.mark.parametrize("name", ["lines", "offscreen_lines", "offscreen_lines_tiny", "state_wireframe_solid", "bowser_close", "edge_cases"])
+@pytest.mark.parametrize("front", ["auto", "fused", "split"])
+def test_x_guard_option_matches_guarded_oracle(name, front, oracle_lib, gpu_capi, monkeypatch):
+    """fgl_state.x_guard = 1 (Context.XGuard): fragments with x outside [0, Width) are dropped instead of aliasing
+    into the neighbouring row (the default above is the reference's own rule, context.go:223-228)."""
+    from fauxgl_b200.context import Context
+    if front != "auto":
+        monkeypatch.setenv("FGL_FRONT", front)
+    stats = run_both(scenes.SCENES[name](), oracle_lib, Context, x_guard=True)
+    assert stats["depth_mismatch"] == 0 and stats["color_mismatch"] == 0, stats
+    assert stats["gpu_info"] == stats["oracle_info"], stats
+
+
 @pytest.mark.parametrize("strip_w", ["32", "64"])
-@pytest.mark.parametrize("name", ["hello", "bowser_close", "shapes_multipass", "lines", "edge_cases", "capsule_phong_texture"])
+@pytest.mark.parametrize("name", ["hello", "bowser_close", "shapes_multipass", "lines", "edge_cases", "capsule_phong_texture",
+                                  "offscreen_lines", "offscreen_lines_tiny"])
 def test_scene_matches_oracle_for_both_strip_widths(name, strip_w, oracle_lib, gpu_capi, monkeypatch):
     """A context bins into 32-pixel strips up to 4 Mpixel and 64-pixel strips above; FGL_STRIP_W forces one."""
     from fauxgl_b200.context import Context
@@ -48,3 +62,21 @@ def test_scene_matches_oracle_for_both_strip_widths(name, strip_w, oracle_lib, g
     stats = run_both(scenes.SCENES[name](), oracle_lib, Context)
     assert stats["depth_mismatch"] == 0 and stats["color_mismatch"] == 0, stats
     assert stats["gpu_info"] == stats["oracle_info"], stats
+
+
+def test_config4_capsule_texture_png_full_scale(oracle_lib, gpu_capi):
+    """BASELINE config 4 at the size examples/capsule.go:11-14 renders (1024 x 1024, 4x supersampled): capsule.obj +
+    the reference's 4096^2 texture.png through TextureShader, the translucent pass and the wireframe + DepthBias
+    pass of examples/shapes.go:71-78, then the 4x4 resolve -- bit-exact against the oracle."""
+    from fauxgl_b200.context import Context
+    sc = scenes.capsule_composed(scale=4)
+    octx = oracle_lib.OracleContext(sc.width, sc.height)
+    oinfo = sc.run(octx)
+    gctx = Context(sc.width, sc.height)
+    ginfo = sc.run(gctx)
+    assert ginfo == oinfo
+    gd, gc = gctx.DepthBuffer, gctx.Image()
+    assert (gd.view("u8") == octx.DepthBuffer.view("u8")).all()
+    assert (gc == octx.ColorBuffer).all()
+    assert (gctx.Resolve(4) == octx.Resolve(4)).all()
+    gctx.Close()
