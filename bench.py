@@ -34,12 +34,27 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 
 import numpy as np  # noqa: E402
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # independent streams (clears, copies, peer flags) get queues of their own
+
 T_TRIANGLES = 871306
+WORKLOAD = ("M871k: synthetic 871306-triangle bumpy closed surface, smoothed normals, Phong, 1920x1080, README camera; "
+            "one frame = ClearDepth + ClearColor + DrawMesh")
 W1, H1 = 1920, 1080
 SSAA = 4
 ALGO_BYTES_C1 = T_TRIANGLES * 144 + W1 * H1 * 12                     # 150 351 264
 ALGO_BYTES_C2 = (T_TRIANGLES * 144 + (W1 * SSAA) * (H1 * SSAA) * 12
                  + (W1 * SSAA) * (H1 * SSAA) * 4 + W1 * H1 * 4)      # 664 604 064
+
+
+def load_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed summary of the
+    latest `ncu --set full` capture (profiles/ncu_traffic.json; tools/ncu_summary.py writes the numbers)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            e = json.load(f)[kernel]
+        return int(e["dram_bytes"]), e.get("source")
+    except Exception:
+        return None, None
 
 
 def load_peaks():
@@ -114,7 +129,7 @@ def cpu_reference_frames(mesh, frames: int, warmup: int, threads: int):
     mutexes, unlocked early-Z) restated in oracle/fauxgl_oracle.c, timed per frame."""
     from oracle import pyoracle
     shader, bg = scene_setup()
-    octx = pyoracle.OracleContext(W1, H1, x_guard=True, threads=threads)
+    octx = pyoracle.OracleContext(W1, H1, threads=threads)
     octx.Shader = shader
     verts = np.ascontiguousarray(mesh.triangle_vertices())  # flattening is mesh prep, not DrawMesh
     times = []
@@ -135,21 +150,176 @@ def run_reference(args, rank):
     from fauxgl_b200 import synth
     mesh = synth.bumpy_surface()
     cores = os.cpu_count() or 1
-    times = cpu_reference_frames(mesh, args.steps, min(args.warmup, 1), cores)
+    times = cpu_reference_frames(mesh, args.steps, min(args.warmup, 5), cores)
     ms = 1e3 * sum(times) / len(times)
     value = T_TRIANGLES / (ms / 1e3) / 1e6
     line = {
         "impl": "reference", "metric": "Mtri/s, 871k-tri Phong 1080p DrawMesh", "value": value, "unit": "Mtri/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 5), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": value / (T_TRIANGLES / 0.150 / 1e6), "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "M871k: synthetic 871306-triangle bumpy closed surface, smoothed normals, Phong, 1920x1080, README camera",
-                   "frames_per_step": 1},
+        "config": {"workload": WORKLOAD, "frames_per_step": 1},
         "cpu_baseline": {"value": value, "unit": "Mtri/s", "cores": cores, "kind": "port",
                          "sample": "%d full frames (clear + DrawMesh) of the same scene, pthread restatement of the reference's "
                                    "goroutine schedule (no Go toolchain)" % len(times)},
         "e2e": {"value": value, "unit": "Mtri/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def bench_sort_last(args, rank, local_rank, world, barrier, max_over_ranks, use_dist):
+    """BASELINE config 5 (SURVEY 8d "M10M"): a 10 003 864-triangle unit sphere at 7680x4320, the triangles split over
+    the N ranks, every rank drawing into its own full-frame buffers, then the depth composite onto rank 0.  Runs at
+    every N including 1 (the anchor of the scaling curve).  Per N it reports, for both composites of the library
+    (exact sparse peer-memory kernel; NCCL stripe reduce-scatter + gather on packed keys) and both ways of splitting
+    the triangles (contiguous ranges; blocks of 4096 dealt round-robin), the frame time with its breakdown and the
+    number of pixels in which rank 0's composited frame differs from a single-GPU render of the whole mesh (which
+    rank 0 makes once, untimed) -- and asserts that count against the north star's 0.01 % budget."""
+    import torch
+    import torch.distributed as dist
+    from fauxgl_b200 import multigpu, synth
+    from fauxgl_b200.context import Context, DeviceMesh
+    K = max(3, min(args.steps, 8))
+    nu = nv = 2237                                   # 2237 * (2*2237 - 2) = 10 003 864 triangles
+    big = synth.uv_sphere(nu, nv)
+    Tb = big.num_triangles
+    Wb, Hb = W1 * SSAA, H1 * SSAA
+    npix = Wb * Hb
+    ctx = Context(Wb, Hb, local_rank)
+    sh_b, bg_b = scene_setup()
+    ctx.Shader = sh_b
+    ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
+
+    def gather_floats(x):
+        if not use_dist:
+            return [float(x)]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    def timed(frame_fn, steps, finish):
+        s_ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        m_ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        e_ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        barrier()
+        with torch.cuda.stream(ext):
+            for i in range(steps):
+                s_ev[i].record(ext)
+                frame_fn(lambda i=i: m_ev[i].record(ext))
+                e_ev[i].record(ext)
+        info = finish()
+        barrier()
+        frame = sum(a.elapsed_time(b) for a, b in zip(s_ev, e_ev)) / steps
+        draw = sum(a.elapsed_time(b) for a, b in zip(s_ev, m_ev)) / steps
+        return frame, draw, info
+
+    # ---- the single-GPU render of the whole mesh: the N = 1 anchor (timed on every rank-0) and the image to compare with
+    ref_img = single = None
+    if rank == 0:
+        dm_full = DeviceMesh(ctx, big, ("position", "normal"))
+
+        def full_frame(mark):
+            ctx.ClearDepthBuffer()
+            ctx.ClearColorBufferWith(bg_b)
+            ctx.DrawMeshAsync(dm_full)
+            mark()
+        ctx.ClearDepthBuffer(); ctx.ClearColorBufferWith(bg_b)
+        full_info = ctx.DrawTriangles(dm_full)       # synchronous: sizes the work buffers, gives the RasterizeInfo
+        ref_img = ctx.Image().copy()
+        ref_depth = ctx.DepthBuffer
+        for _ in range(2):
+            full_frame(lambda: None)
+        ctx.Sync()
+    if world == 1:
+        fms, _, _ = timed(full_frame, K, ctx.Sync)
+        ctx.SetProfiling(True)
+        for _ in range(3):
+            full_frame(lambda: None)
+        ctx.Sync()
+        st = ctx.StageTimes()
+        ctx.SetProfiling(False)
+        single = {"ms_per_frame": fms, "mtri_s": Tb / (fms / 1e3) / 1e6,
+                  "stages_ms": {"geometry_ms": st.geometry_ms / st.draws, "spans_ms": st.spans_ms / st.draws,
+                                "sort_ms": st.sort_ms / st.draws, "raster_ms": st.raster_ms / st.draws},
+                  "total_pixels": int(full_info.TotalPixels), "updated_pixels": int(full_info.UpdatedPixels)}
+    if rank == 0:
+        del dm_full
+    barrier()
+
+    runs = {}
+    for partition in ("contiguous", "interleaved"):
+        if partition == "contiguous":
+            first, count = multigpu.triangle_range(Tb, rank, world)
+            part = type(big)(big.position[first:first + count], big.normal[first:first + count])
+        else:
+            idx = multigpu.triangle_blocks(Tb, rank, world, 4096)
+            part = type(big)(big.position[idx], big.normal[idx])
+        dm = DeviceMesh(ctx, part, ("position", "normal"))
+        del part
+        ctx.ClearDepthBuffer(); ctx.ClearColorBufferWith(bg_b)
+        my_info = ctx.DrawTriangles(dm)              # synchronous: sizes the work buffers for this share
+        peer = multigpu.PeerGroup(ctx, rank, world)
+        nccl = multigpu.NcclComposite(ctx, rank, world)
+        for method, comp, finish in (("peer", lambda: peer.composite(0), lambda: (ctx.Sync(), peer.status())[0]),
+                                     ("nccl", lambda: nccl.composite(0), ctx.Sync)):
+            def frame(mark, comp=comp):
+                ctx.ClearDepthBuffer()
+                ctx.ClearColorBufferWith(bg_b)
+                ctx.DrawMeshAsync(dm)
+                mark()
+                comp()
+            for _ in range(2):
+                frame(lambda: None)
+            finish()
+            fms, dms, info = timed(frame, K, finish)
+            fms = max_over_ranks(fms)
+            draws = gather_floats(dms)
+            # correctness of what rank 0 now holds, against its own single-GPU render of the whole mesh
+            mism = dmism = None
+            if rank == 0:
+                img = ctx.Image()
+                mism = int((img != ref_img).any(axis=-1).sum())
+                if method == "peer":
+                    dmism = int((ctx.DepthBuffer.view(np.uint64) != ref_depth.view(np.uint64)).sum())
+            # stage breakdown: a second, shorter pass with the library's stage timers on
+            ctx.SetProfiling(True)
+            for _ in range(3):
+                frame(lambda: None)
+            finish()
+            stages = (peer if method == "peer" else nccl).stage_times()
+            ctx.StageTimes()
+            ctx.SetProfiling(False)
+            stages.pop("composites", None)
+            runs["%s/%s" % (partition, method)] = {
+                "ms_per_frame": fms, "mtri_s": Tb / (fms / 1e3) / 1e6,
+                "draw_ms_max": max(draws), "draw_ms_min": min(draws), "draw_ms_per_rank": draws,
+                "composite_stages_ms_rank0": stages,
+                "mismatch_px": mism, "depth_mismatch_px": dmism,
+                "mismatch_frac": None if mism is None else mism / npix}
+            if rank == 0:
+                budget = 1e-4 * npix
+                assert mism <= (0 if method == "peer" else budget), (partition, method, mism)
+                assert dmism in (None, 0), (partition, method, dmism)
+        totals = gather_floats(float(my_info.TotalPixels))
+        runs[partition + "/total_pixels_per_rank"] = [int(v) for v in totals]
+        peer.close()
+        nccl.close()
+        del dm
+        barrier()
+    ctx.Close()
+    best = min((k for k in runs if "ms_per_frame" in (runs[k] if isinstance(runs[k], dict) else {})),
+               key=lambda k: runs[k]["ms_per_frame"])
+    return {"workload": "M10M: %d-triangle unit sphere, Phong, 7680x4320, triangles split over the N ranks, composite onto "
+                        "rank 0 (order-independent state)" % Tb,
+            "triangles": Tb, "n_gpus": world, "steps": K, "scaling": "strong",
+            "ms_per_frame": runs[best]["ms_per_frame"], "mtri_s": runs[best]["mtri_s"], "best": best,
+            "mismatch_px": runs[best]["mismatch_px"], "single_gpu": single, "runs": runs,
+            "methods": {"peer": "fgl_peer_composite: exact float64 depth, sparse (dirty strips only), one P2P kernel per "
+                                "rank over NVLink, device-side flags",
+                        "nccl": "fgl_composite: packed keys (depth32<<32|rgba8), ncclReduceScatter(min, uint64) by stripe + "
+                                "ncclSend/Recv gather to rank 0, inside the library"},
+            "partitions": {"contiguous": "rank r draws triangles [rT/N, (r+1)T/N)",
+                           "interleaved": "blocks of 4096 consecutive triangles dealt round-robin"}}
 
 
 def main():
@@ -161,7 +331,6 @@ def main():
     ap.add_argument("--no-ssaa", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-batch", action="store_true")
-    ap.add_argument("--sort-last", action="store_true", help="also time the 10M-triangle sort-last config at N == 1")
     ap.add_argument("--no-sort-last", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -279,7 +448,7 @@ def main():
         "bound": "hbm", "kernel": "k_front",
         "achieved": geo_bytes / (stages["geometry_ms"] / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
         "frac": geo_bytes / (stages["geometry_ms"] / 1e3) / 1e9 / hbm_peak,
-        "traffic": 86143744,   # dram__bytes_read+write of one k_front launch, profiles/r01_ncu_v7_front_strip_shade.txt
+        "traffic": load_traffic("k_front")[0], "traffic_source": load_traffic("k_front")[1],
         "peak_source": peak_src, "algorithmic_bytes": geo_bytes,
         "frame": {"algorithmic_bytes": ALGO_BYTES_C1, "achieved": ALGO_BYTES_C1 / (ms1 / 1e3) / 1e9,
                   "frac": ALGO_BYTES_C1 / (ms1 / 1e3) / 1e9 / hbm_peak},
@@ -413,87 +582,98 @@ def main():
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / Ke)
     barrier()
     assert tuple(pinfo) == tuple(einfo) and int(pimg.astype(np.uint64).sum()) == serial_checksum
-    e2e = {"value": world * T_TRIANGLES / (e2e_ms / 1e3) / 1e6, "unit": "Mtri/s", "ms_per_step": e2e_ms, "steps": Ke,
-           "h2d_bytes_per_step": int(pin_pos.numel() * 8 + pin_nrm.numel() * 8),
+    soup = {"ms_per_step": e2e_ms, "mtri_s": world * T_TRIANGLES / (e2e_ms / 1e3) / 1e6,
+            "h2d_bytes_per_step": int(pin_pos.numel() * 8 + pin_nrm.numel() * 8), "d2h_bytes_per_step": int(W1 * H1 * 4 + 64),
+            "serial_ms_per_step": serial_ms,
+            "what": "the mesh as the reference holds it in memory, expanded per triangle corner (position + normal, 144 B "
+                    "per triangle), uploaded every frame (fgl_mesh_update_async); serial_ms_per_step = the same frame as "
+                    "blocking calls, nothing overlapped"}
+    del pipe
+
+    # The headline e2e: the same frames with the mesh kept as shared-vertex tables (Mesh.indexed(): what an OBJ file
+    # holds, obj.go:19-79).  The corner indices stay on the device; every frame uploads its v / vn tables from pinned
+    # host memory (fgl_mesh_update_indexed_async: 48 B per shared vertex), expands them on the copy stream, clears,
+    # draws and reads the image and the RasterizeInfo back -- bit-identical frames, a sixth of the PCIe bytes.
+    from fauxgl_b200.pipeline import IndexedFramePipeline
+    tv, tvn, corners = mesh.indexed()
+    pin_v = torch.empty(tv.shape, dtype=torch.float64, pin_memory=True)
+    pin_vn = torch.empty(tvn.shape, dtype=torch.float64, pin_memory=True)
+    pin_v.numpy()[...] = tv
+    pin_vn.numpy()[...] = tvn
+    ipipe = IndexedFramePipeline(ctx, pin_v.numpy(), pin_vn.numpy(), corners, depth=DEPTH)
+
+    def ipipelined(n):
+        last = None
+        for _ in range(n):
+            if len(ipipe) == DEPTH:
+                last = ipipe.collect()
+            ipipe.submit(pin_v.numpy(), pin_vn.numpy(), bg)
+        while len(ipipe):
+            last = ipipe.collect()
+        return last
+    ipipelined(3)
+    barrier()
+    t0 = time.perf_counter()
+    iimg, iinfo = ipipelined(Ke)
+    torch.cuda.synchronize()
+    idx_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / Ke)
+    barrier()
+    assert tuple(iinfo) == tuple(einfo) and int(iimg.astype(np.uint64).sum()) == serial_checksum
+    del ipipe
+
+    # examples/animate.go as the library lets it be written: the mesh lives on the device, a frame's input is the 4x4
+    # matrix of Mesh.Transform (mesh.go:167-175 on the device: fgl_mesh_transform), and the image is read back.
+    from fauxgl_b200 import Rotate, V
+    from fauxgl_b200.context import Fence, pinned_empty
+    dmt = DeviceMesh(ctx, mesh, ("position", "normal"))
+    rot = Rotate(V(0, 1, 0), 5.0 * 3.141592653589793 / 180.0)
+    slots = [(pinned_empty((H1, W1, 4), np.uint8), Fence(ctx)) for _ in range(DEPTH)]
+
+    def transform_frames(n):
+        info = None
+        for i in range(n):
+            out, fence = slots[i % DEPTH]
+            if i >= DEPTH:
+                info = fence.wait()
+            dmt.Transform(rot)
+            ctx.ClearDepthBuffer()
+            ctx.ClearColorBufferWith(bg)
+            ctx.DrawMeshAsync(dmt)
+            ctx.FrameEnd(out, fence)
+        for i in range(n, n + DEPTH):
+            info = slots[i % DEPTH][1].wait()
+        return info
+    ctx.DrawMesh(dmt)
+    transform_frames(3)
+    barrier()
+    t0 = time.perf_counter()
+    tinfo = transform_frames(Ke)
+    torch.cuda.synchronize()
+    tr_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / Ke)
+    barrier()
+    assert tinfo.TotalPixels > 0
+    del dmt
+    e2e = {"value": world * T_TRIANGLES / (idx_ms / 1e3) / 1e6, "unit": "Mtri/s", "ms_per_step": idx_ms, "steps": Ke,
+           "h2d_bytes_per_step": int(pin_v.numel() * 8 + pin_vn.numel() * 8),
            "d2h_bytes_per_step": int(W1 * H1 * 4 + 64),
            "frames_in_flight": DEPTH,
-           "serial_ms_per_step": serial_ms,
-           "what": "per frame: mesh (position+normal, pinned host) upload + clears + DrawMesh + image and RasterizeInfo "
-                   "read-back through the public API; frames pipelined two deep (fgl_mesh_update_async / fgl_frame_end), "
-                   "serial_ms_per_step = the same frame as blocking calls, nothing overlapped"}
-    del pipe
+           "what": "per frame: this frame's vertex tables (435986 shared vertices x (position + normal), pinned host memory) "
+                   "uploaded and expanded on the device by resident corner indices (fgl_mesh_update_indexed_async) + clears "
+                   "+ DrawMesh + image and RasterizeInfo read-back through the public API; frames pipelined two deep; image "
+                   "and RasterizeInfo asserted identical to the blocking per-triangle-soup path",
+           "soup_upload": soup,
+           "device_transform": {"ms_per_step": tr_ms, "mtri_s": world * T_TRIANGLES / (tr_ms / 1e3) / 1e6,
+                                "h2d_bytes_per_step": 128, "d2h_bytes_per_step": int(W1 * H1 * 4 + 64),
+                                "what": "examples/animate.go with the mesh resident: per frame Mesh.Transform(Rotate(up, 5 deg)) "
+                                        "on the device (fgl_mesh_transform, input = one 4x4 matrix) + clears + DrawMesh + image "
+                                        "and RasterizeInfo read-back, two frames in flight"}}
     checksum = int(img.astype(np.uint64).sum())
     ctx.Close()
 
-    # ---------------- sort-last: 10 M-triangle sphere at 7680x4320, ranges per rank + NCCL composite ----------------
+    # ---------------- sort-last: 10 M-triangle sphere at 7680x4320 (BASELINE config 5) ----------------
     sort_last = None
-    if args.sort_last or (world > 1 and not args.no_sort_last):
-        from fauxgl_b200 import multigpu
-        nu = nv = 2237                                   # 2237 * (2*2237 - 2) = 10 003 864 triangles
-        big = synth.uv_sphere(nu, nv)
-        Tb = big.num_triangles
-        Wb, Hb = W1 * SSAA, H1 * SSAA
-        ctx = Context(Wb, Hb, local_rank)
-        sh_b, bg_b = scene_setup()
-        ctx.Shader = sh_b
-        first, count = multigpu.triangle_range(Tb, rank, world)
-        part = type(big)(big.position[first:first + count], big.normal[first:first + count])
-        del big
-        dm = DeviceMesh(ctx, part, ("position", "normal"))
-        keys = torch.empty(Wb * Hb, dtype=torch.int64, device="cuda")
-        ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
-
-        def sl_frame(sync_draw=False):
-            ctx.ClearDepthBuffer()
-            ctx.ClearColorBufferWith(bg_b)
-            if sync_draw:
-                ctx.DrawTriangles(dm)
-            else:
-                ctx.DrawMeshAsync(dm)
-            ctx.CompositePack(keys.data_ptr())
-            with torch.cuda.stream(ext):
-                multigpu.composite_min(keys)
-            ctx.CompositeUnpack(keys.data_ptr())
-        sl_frame(sync_draw=True)
-        for _ in range(2):
-            sl_frame()
-        ctx.Sync()
-        Ks = max(3, min(K, 5))
-        s_ev = [torch.cuda.Event(enable_timing=True) for _ in range(Ks)]
-        e_ev = [torch.cuda.Event(enable_timing=True) for _ in range(Ks)]
-        barrier()
-        with torch.cuda.stream(ext):
-            for i in range(Ks):
-                s_ev[i].record(ext)
-                sl_frame()
-                e_ev[i].record(ext)
-        sl_info = ctx.Sync()
-        barrier()
-        sl_ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(s_ev, e_ev)) / Ks)
-        # the fused peer-memory composite (one P2P kernel per rank, exact f64 depth), host-fenced: wall clock
-        peer_ms = None
-        if world > 1:
-            pc = multigpu.PeerComposite(ctx, rank, world)
-            for _ in range(2):
-                ctx.ClearDepthBuffer(); ctx.ClearColorBufferWith(bg_b); ctx.DrawMeshAsync(dm); pc.composite()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(Ks):
-                ctx.ClearDepthBuffer(); ctx.ClearColorBufferWith(bg_b); ctx.DrawMeshAsync(dm); pc.composite()
-            torch.cuda.synchronize()
-            peer_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / Ks)
-            barrier()
-            pc.close()
-        sort_last = {"ms_per_frame": sl_ms, "mtri_s": Tb / (sl_ms / 1e3) / 1e6, "triangles": Tb, "steps": Ks,
-                     "workload": "M10M: %d-triangle unit sphere, Phong, 7680x4320; rank r draws triangles [rT/N,(r+1)T/N), "
-                                 "packed-key int64 min all-reduce (NCCL), unpack" % Tb,
-                     "composite_bytes_per_rank": Wb * Hb * 8, "scaling": "strong",
-                     "peer_composite_ms_per_frame": peer_ms,
-                     "peer_composite": "same draw, then ONE fused P2P kernel per rank (fgl_composite_peer: f64 depth, exact), "
-                                       "host barriers included, wall clock",
-                     "total_pixels_this_rank": int(sl_info.TotalPixels // Ks)}
-        del dm
-        ctx.Close()
+    if not args.no_sort_last:
+        sort_last = bench_sort_last(args, rank, local_rank, world, barrier, max_over_ranks, use_dist)
 
     # ---------------- CPU baseline beside it (rank 0, N == 1 only) ----------------
     cpu = None
@@ -512,9 +692,7 @@ def main():
             "steps": K, "warmup": Wm, "ms_per_step": ms1, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": value / (T_TRIANGLES / 0.150 / 1e6),   # README.md:36: ~150 ms/frame on the author's (unspecified) CPU
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "M871k: synthetic 871306-triangle bumpy closed surface, smoothed normals, Phong, "
-                                   "1920x1080, README camera; one frame = ClearDepth + ClearColor + DrawMesh",
-                       "frames_per_step": 1, "sharding": "frames per GPU, no collective" if world > 1 else "single GPU",
+            "config": {"workload": WORKLOAD, "frames_per_step": 1, "sharding": "frames per GPU, no collective" if world > 1 else "single GPU",
                        "l2": "flushed between timed frames (256 MiB memset outside the event pair)",
                        "timing": "CUDA events on the library's stream, per frame, summed; max over ranks"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

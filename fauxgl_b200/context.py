@@ -25,6 +25,7 @@ from .vector import Vector
 from .shader import (SHADER_PHONG, SHADER_SOLID, SHADER_TEXTURE, ImageTexture, PhongShader,
                      SolidColorShader, TextureShader)
 
+COMM_ID_BYTES, PEER_EXPORT_BYTES = 128, 512   # FGL_COMM_ID_BYTES, FGL_PEER_EXPORT_BYTES
 FaceCW, FaceCCW = 1, 2
 CullNone, CullFront, CullBack = 1, 2, 3
 
@@ -115,6 +116,7 @@ ABI = [
     ("fgl_mesh_transform", C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     ("fgl_mesh_read", C.c_int, [_P, _P, _P, _P, _P, _P]),
     ("fgl_mesh_create_indexed", C.c_int, [_P, _P, C.POINTER(_P)]),
+    ("fgl_mesh_update_indexed_async", C.c_int, [_P, _P, _P]),
     ("fgl_mesh_smooth_normals", C.c_int, [_P, _P]),
     ("fgl_mesh_smooth_normals_threshold", C.c_int, [_P, _P, C.c_double]),
     ("fgl_texture_create", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
@@ -147,6 +149,18 @@ ABI = [
     ("fgl_ipc_open", C.c_int, [_P, _P, _P, C.POINTER(_P), C.POINTER(_P)]),
     ("fgl_ipc_close", C.c_int, [_P, _P, _P]),
     ("fgl_composite_peer", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
+    ("fgl_comm_unique_id", C.c_int, [_P]),
+    ("fgl_comm_init", C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    ("fgl_comm_destroy", C.c_int, [_P]),
+    ("fgl_composite", C.c_int, [_P, _P, C.c_int]),
+    ("fgl_comm_stage_times", C.c_int, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    ("fgl_peer_stage_times", C.c_int, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    ("fgl_peer_export", C.c_int, [_P, _P]),
+    ("fgl_peer_group_create", C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    ("fgl_peer_group_destroy", C.c_int, [_P]),
+    ("fgl_peer_composite", C.c_int, [_P, _P, C.c_int]),
+    ("fgl_peer_composite_phase", C.c_int, [_P, _P, C.c_int, C.c_int]),
+    ("fgl_peer_status", C.c_int, [_P, _P]),
     ("fgl_debug_tile_cycles", C.c_int, [_P, _P, C.c_uint64]),
     ("fgl_probe_atomic_rate", C.c_int, [_P, C.c_uint64, C.POINTER(C.c_double)]),
     ("fgl_stream", _P, [_P]),
@@ -274,10 +288,51 @@ class DeviceMesh:
         self.generation = 0
         self.attributes = ("position", "normal", "texture")
         self.num_triangles, self.num_lines = int(d.ntriangles), 0
+        self.table_sizes = (int(d.nv), int(d.nvt), int(d.nvn))
         self.handle = _P()
         _check(capi().fgl_mesh_create_indexed(ctx._h, C.byref(d), C.byref(self.handle)), ctx._h)
         self._fin = weakref.finalize(self, capi().fgl_mesh_destroy, self.handle)
         return self
+
+    @classmethod
+    def FromIndexed(cls, ctx: "Context", v, vt, vn, corners) -> "DeviceMesh":
+        """fgl_mesh_create_indexed from tables already in memory: v / vt / vn [n][3] float64 (entry 0 of each is the
+        reference's 1-based tables' unused zero entry, or any entry -- the indices decide) and corners [T][3][3]
+        int32 (v, vt, vn index per triangle corner).  The indices stay on the device: ``update_indexed_async``
+        re-poses the mesh by sending only the tables."""
+        keep = [np.ascontiguousarray(v, dtype=np.float64), np.ascontiguousarray(vt, dtype=np.float64),
+                np.ascontiguousarray(vn, dtype=np.float64), np.ascontiguousarray(corners, dtype=np.int32)]
+        d = IndexedDesc()
+        d.v, d.vt, d.vn = (C.cast(a.ctypes.data, _P) for a in keep[:3])
+        d.nv, d.nvt, d.nvn = len(keep[0]), len(keep[1]), len(keep[2])
+        d.corners = C.cast(keep[3].ctypes.data, _P)
+        d.ntriangles = len(keep[3])
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.generation = 0
+        self.attributes = ("position", "normal", "texture")
+        self.num_triangles, self.num_lines = int(d.ntriangles), 0
+        self.table_sizes = (int(d.nv), int(d.nvt), int(d.nvn))
+        self.handle = _P()
+        _check(capi().fgl_mesh_create_indexed(ctx._h, C.byref(d), C.byref(self.handle)), ctx._h)
+        self._fin = weakref.finalize(self, capi().fgl_mesh_destroy, self.handle)
+        return self
+
+    def update_indexed_async(self, v=None, vt=None, vn=None):
+        """fgl_mesh_update_indexed_async: enqueue new v / vt / vn tables (float64 [n][3], same sizes; pinned memory
+        for a real overlap) on the copy stream and return; the arrays must stay unchanged until ``upload_wait``."""
+        d = IndexedDesc()
+        keep = []
+        for name, a, n in (("v", v, self.table_sizes[0]), ("vt", vt, self.table_sizes[1]), ("vn", vn, self.table_sizes[2])):
+            if a is None:
+                continue
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == (n, 3), (name, a.shape, n)
+            keep.append(a)
+            setattr(d, name, C.cast(a.ctypes.data, _P))
+        d.nv, d.nvt, d.nvn = self.table_sizes
+        d.ntriangles = self.num_triangles
+        self._pending = keep
+        _check(capi().fgl_mesh_update_indexed_async(self.ctx._h, self.handle, C.byref(d)), self.ctx._h)
 
     def BoundingBox(self) -> Box:
         """Mesh.BoundingBox (mesh.go:153-165) of the device copy."""
@@ -651,6 +706,13 @@ class Context:
         ca = (_P * n)(*color_ptrs)
         da = (_P * n)(*depth_ptrs)
         _check(capi().fgl_composite_peer(self._h, int(rank), n, ca, da), self._h)
+
+    # -- in-library composite (fgl_comm.cu) ---------------------------------------------------------
+    def PeerExport(self) -> bytes:
+        """fgl_peer_export: this context's record for fgl_peer_group_create (FGL_PEER_EXPORT_BYTES)."""
+        rec = C.create_string_buffer(PEER_EXPORT_BYTES)
+        _check(capi().fgl_peer_export(self._h, rec), self._h)
+        return rec.raw
 
     # -- interop ---------------------------------------------------------------------------------
     @property

@@ -11,7 +11,7 @@
 #include <new>
 #include <string>
 
-#include "fgl_internal.h"
+#include "fgl_ctx.h"
 
 using namespace fgl;
 
@@ -42,78 +42,6 @@ int fail(fgl_ctx *ctx, int code, const char *fmt, ...);
     } while (0)
 
 }  // namespace
-
-struct fgl_tex {
-    int device;
-    uint8_t *pixels;
-    int w, h, format;
-};
-
-struct fgl_mesh {
-    int device;
-    uint64_t nt, nl;
-    double *tpos, *tnrm, *ttex, *tcol;  // planar, triangles
-    double *lpos, *lnrm, *ltex, *lcol;  // planar, lines
-    double *staging;                    // AoS landing buffer for H2D copies (kept for fgl_mesh_update)
-    size_t staging_elems;
-    // streaming uploads (fgl_mesh_update_async): the copy stream and the draw stream hand the
-    // buffers back and forth through these two events
-    cudaEvent_t ev_uploaded, ev_drawn;
-    bool has_events, upload_pending, drawn_recorded;
-    // The context whose streams order this mesh's uploads and in-place edits.  Any context of the same device may
-    // DRAW the mesh (read-only); update / transform / smooth-normals must go through the owner, and a mesh that is
-    // re-uploaded through the streaming entry point (events above) can only be drawn by its owner.
-    const fgl_ctx *owner;
-};
-
-struct fgl_fence {
-    int device;
-    cudaEvent_t done;
-    DrawCounters *counters;  // pinned: the frame's accumulated RasterizeInfo / overflow flags
-    bool recorded;
-};
-
-constexpr int PROF_RING = 32;
-constexpr int PROF_EVENTS = 5;  // start, after geometry, after spans, after sort, after tile kernel
-struct ProfSlot { cudaEvent_t e[PROF_EVENTS]; };
-
-struct fgl_ctx {
-    int device;
-    int w, h;
-    int tile_w;                        // strip width of this context: 32 or 64 (fgl_internal.h)
-    int front_mode;                    // 0 auto, 1 fused front end always, 2 split stages always (FGL_FRONT)
-    cudaStream_t stream;
-    cudaStream_t copy_stream;          // H2D of streaming mesh uploads, overlapping the draw stream
-    // Clears run on a stream of their own: the front end of the next draw touches no framebuffer, so the clear
-    // of a frame overlaps its k_front instead of preceding it (fb_clear_begin / fb_clear_end / fb_join below).
-    cudaStream_t fb_stream;
-    cudaEvent_t ev_fb_free, ev_cleared;
-    bool clear_overlap, clear_pending;
-    std::mutex mu;
-    mutable std::mutex err_mu;         // guards err / err_seq only (fail() runs both inside and outside `mu`)
-    std::string err;
-    unsigned long long err_seq;
-    uint32_t *color;
-    double *depth;
-    uint32_t *resolved;
-    int rw, rh;
-    WorkBuffers wb;
-    DrawCounters *host_counters;       // pinned
-    DrawCounters *acc_dev;             // async accumulation (total/updated/overflow)
-    bool async_pending;
-    bool counters_clean;               // the last draw's k_shade zeroed the device-side draw counters
-    unsigned long long *prim_info;     // per-primitive RasterizeInfo of fgl_draw_*_each, [prim_info_cap][2]
-    uint64_t prim_info_cap;
-    unsigned long long *scratch;       // 8 words: reductions of fgl_mesh_bounds / fgl_depth_image
-    uint16_t *gray16;                  // DepthImage staging, allocated on first use
-    fgl_draw_stats stats;
-    // per-stage profiling (fgl_set_profiling)
-    bool profiling;
-    ProfSlot prof[PROF_RING];
-    int prof_used;          // slots recorded since the last drain
-    bool prof_created;
-    fgl_stage_times prof_acc;
-};
 
 namespace {
 
@@ -195,6 +123,8 @@ int ensure_work(fgl_ctx *c, const Caps &want) {
         CK(c, dev_alloc(&wb.blk_woff, want.prims / 32 + 8));
         CK(c, dev_alloc(&wb.blk_agg, want.prims / 32 + 8));
         CK(c, dev_alloc(&wb.blk_base, want.prims / 32 + 8));
+        // (its first entries double as the group sums of the fused front end, which every draw leaves zeroed)
+        CK(c, cudaMemsetAsync(wb.blk_base, 0, sizeof(unsigned long long) * (want.prims / 32 + 8), c->stream));
         CK(c, dev_alloc(&wb.blk_region, want.prims / 32 + 8));
         wb.cap_prims = (uint32_t)want.prims;
     }
@@ -482,6 +412,19 @@ int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const 
 
 }  // namespace
 
+namespace fgl {
+int api_fail(fgl_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    return fail(ctx, code, "%s", buf);
+}
+int api_check_ctx(fgl_ctx *ctx) { return check_ctx(ctx); }
+void api_fb_join(fgl_ctx *ctx) { fb_join(ctx); }
+}  // namespace fgl
+
 extern "C" {
 
 int fgl_abi_version(void) { return FGL_ABI_VERSION; }
@@ -547,6 +490,7 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     memset(&c->stats, 0, sizeof c->stats);
     c->host_counters = nullptr; c->acc_dev = nullptr; c->async_pending = false; c->counters_clean = false;
     c->prim_info = nullptr; c->prim_info_cap = 0; c->scratch = nullptr; c->gray16 = nullptr;
+    c->peer_flags = nullptr; c->peer_epoch = 0;
     c->profiling = false; c->prof_used = 0; c->prof_created = false;
     memset(&c->prof_acc, 0, sizeof c->prof_acc);
     const size_t npix = (size_t)width * height;
@@ -580,6 +524,8 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
         c->wb.nsm = cudaGetDeviceProperties(&prop, device) == cudaSuccess ? (uint32_t)prop.multiProcessorCount : 148u;
     }
     if (err == cudaSuccess) err = dev_alloc(&c->wb.busy_list, c->wb.ntiles);
+    if (err == cudaSuccess) err = dev_alloc(&c->wb.dirty, (size_t)c->wb.ntiles + 16);
+    if (err == cudaSuccess) err = cudaMemsetAsync(c->wb.dirty, 0, (size_t)c->wb.ntiles + 16, c->stream);
     if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_ctl, 1);
     if (err == cudaSuccess && getenv("FGL_TILE_CLOCK")) {  // tuning aid: per-tile cycle counts of k_tile
         err = dev_alloc(&c->wb.tile_clock, (size_t)c->wb.ntiles * 2 + 16);  // + 16 path counters of k_strip
@@ -619,8 +565,8 @@ int fgl_context_destroy(fgl_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_work(c->wb);
     dev_free(c->wb.counters); dev_free(c->wb.tile_clock);
-    dev_free(c->wb.tile_ctl); dev_free(c->wb.busy_list); dev_free(c->wb.vis_seg);
-    dev_free(c->prim_info); dev_free(c->scratch); dev_free(c->gray16);
+    dev_free(c->wb.tile_ctl); dev_free(c->wb.busy_list); dev_free(c->wb.vis_seg); dev_free(c->wb.dirty);
+    dev_free(c->prim_info); dev_free(c->scratch); dev_free(c->gray16); dev_free(c->peer_flags);
     dev_free(c->acc_dev); dev_free(c->color); dev_free(c->depth); dev_free(c->resolved);
     if (c->host_counters) cudaFreeHost(c->host_counters);
     if (c->prof_created)
@@ -654,7 +600,9 @@ int fgl_clear_depth(fgl_ctx *c, double value) {
     int rc = check_ctx(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(c->mu);
-    launch_clear_depth(c->depth, (size_t)c->w * c->h, value, fb_clear_begin(c));
+    cudaStream_t cs = fb_clear_begin(c);
+    cudaMemsetAsync(c->wb.dirty, 0, c->wb.ntiles, cs);  // no strip has drawn depth any more
+    launch_clear_depth(c->depth, (size_t)c->w * c->h, value, cs);
     fb_clear_end(c);
     CK(c, cudaGetLastError());
     return FGL_OK;
@@ -761,6 +709,35 @@ int fgl_mesh_update_async(fgl_ctx *c, fgl_mesh *m, const fgl_mesh_desc *d) {
     return rc;
 }
 
+int fgl_mesh_update_indexed_async(fgl_ctx *c, fgl_mesh *m, const fgl_indexed_desc *d) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!m || !d) return fail(c, FGL_E_INVALID, "null mesh/description");
+    if (m->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on another device");
+    if (m->owner != c) return fail(c, FGL_E_INVALID, "a mesh is modified through the context it was created with (any context of the device may draw it)");
+    if (!m->corners) return fail(c, FGL_E_INVALID, "not an indexed mesh (fgl_mesh_create_indexed)");
+    if ((d->v && d->nv != m->nv) || (d->vt && d->nvt != m->nvt) || (d->vn && d->nvn != m->nvn))
+        return fail(c, FGL_E_INVALID, "fgl_mesh_update_indexed_async needs tables of the sizes the mesh was created with");
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!m->has_events) {
+        CK(c, cudaEventCreateWithFlags(&m->ev_uploaded, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&m->ev_drawn, cudaEventDisableTiming));
+        m->has_events = true;
+        cudaEventRecord(m->ev_drawn, c->stream);  // everything enqueued on the draw stream so far may still read the planes
+        m->drawn_recorded = true;
+    }
+    cudaStream_t st = c->copy_stream;
+    if (m->drawn_recorded) CK(c, cudaStreamWaitEvent(st, m->ev_drawn, 0));
+    if (d->v) CK(c, cudaMemcpyAsync(m->tab_v, d->v, sizeof(double) * 3 * m->nv, cudaMemcpyHostToDevice, st));
+    if (d->vt) CK(c, cudaMemcpyAsync(m->tab_vt, d->vt, sizeof(double) * 3 * m->nvt, cudaMemcpyHostToDevice, st));
+    if (d->vn) CK(c, cudaMemcpyAsync(m->tab_vn, d->vn, sizeof(double) * 3 * m->nvn, cudaMemcpyHostToDevice, st));
+    launch_indexed_ingest(m->tab_v, m->tab_vt, m->tab_vn, m->corners, m->tpos, m->tnrm, m->ttex, (uint32_t)m->nt, st);
+    CK(c, cudaGetLastError());
+    CK(c, cudaEventRecord(m->ev_uploaded, st));
+    m->upload_pending = true;
+    return FGL_OK;
+}
+
 int fgl_mesh_upload_wait(fgl_ctx *c, fgl_mesh *m) {
     int rc = check_ctx(c);
     if (rc) return rc;
@@ -829,8 +806,9 @@ int fgl_mesh_create_indexed(fgl_ctx *c, const fgl_indexed_desc *d, fgl_mesh **ou
     memset(m, 0, sizeof *m);
     m->device = c->device; m->owner = c; m->nt = count; m->nl = 0;
     m->staging_elems = (size_t)m->nt * (9 * 3 + 12);  // as fgl_mesh_create: later fgl_mesh_update calls land here
-    double *tv = nullptr, *tvt = nullptr, *tvn = nullptr;
-    int32_t *tc = nullptr;
+    double *&tv = m->tab_v, *&tvt = m->tab_vt, *&tvn = m->tab_vn;   // kept: fgl_mesh_update_indexed_async reuses them
+    int32_t *&tc = m->corners;
+    m->nv = d->nv; m->nvt = d->nvt; m->nvn = d->nvn;
     cudaError_t e = dev_alloc(&m->staging, m->staging_elems);
     if (e == cudaSuccess) e = dev_alloc(&m->tpos, (size_t)count * 9);
     if (e == cudaSuccess) e = dev_alloc(&m->tnrm, (size_t)count * 9);
@@ -856,7 +834,6 @@ int fgl_mesh_create_indexed(fgl_ctx *c, const fgl_indexed_desc *d, fgl_mesh **ou
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // the caller may free its arrays
     }
-    dev_free(tv); dev_free(tvt); dev_free(tvn); dev_free(tc);
     if (e != cudaSuccess) {
         cudaGetLastError();
         fgl_mesh_destroy(m);
@@ -897,6 +874,7 @@ int fgl_mesh_destroy(fgl_mesh *m) {
     dev_free(m->tpos); dev_free(m->tnrm); dev_free(m->ttex); dev_free(m->tcol);
     dev_free(m->lpos); dev_free(m->lnrm); dev_free(m->ltex); dev_free(m->lcol);
     dev_free(m->staging);
+    dev_free(m->corners); dev_free(m->tab_v); dev_free(m->tab_vt); dev_free(m->tab_vn);
     if (m->has_events) { cudaEventDestroy(m->ev_uploaded); cudaEventDestroy(m->ev_drawn); }
     delete m;
     return FGL_OK;
@@ -1237,6 +1215,7 @@ int fgl_write_depth(fgl_ctx *c, const double *src) {
     std::lock_guard<std::mutex> lock(c->mu);
     fb_join(c);
     CK(c, cudaMemcpyAsync(c->depth, src, sizeof(double) * c->w * c->h, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemsetAsync(c->wb.dirty, 1, c->wb.ntiles, c->stream));  // any strip may hold drawn depth now
     CK(c, cudaStreamSynchronize(c->stream));
     return FGL_OK;
 }
@@ -1300,6 +1279,7 @@ int fgl_composite_unpack(fgl_ctx *c, const void *keys_dev) {
     std::lock_guard<std::mutex> lock(c->mu);
     fb_join(c);
     launch_composite_unpack(c->color, c->depth, static_cast<const unsigned long long *>(keys_dev), (size_t)c->w * c->h, c->stream);
+    cudaMemsetAsync(c->wb.dirty, 1, c->wb.ntiles, c->stream);
     CK(c, cudaGetLastError());
     return FGL_OK;
 }
@@ -1359,6 +1339,7 @@ int fgl_composite_peer(fgl_ctx *c, int rank, int nranks, void *const *color, voi
     fb_join(c);
     launch_composite_peer(reinterpret_cast<uint32_t *const *>(color), reinterpret_cast<double *const *>(depth), nranks,
                           px0, px1, c->stream);
+    cudaMemsetAsync(c->wb.dirty, 1, c->wb.ntiles, c->stream);  // (the peers write into this rank's buffers as well)
     CK(c, cudaGetLastError());
     return FGL_OK;
 }

@@ -657,6 +657,7 @@ k_rec_index(const __grid_constant__ WorkBuffers wb, uint32_t nblocks) {
 #define FGL_FRONT_FT 128
 #endif
 constexpr int FT = FGL_FRONT_FT;
+constexpr uint32_t FRONT_GROUP = 64;  // front-end blocks per group sum (wb.blk_base[g], added up by k_seg_index)
 constexpr unsigned long long CELL_SHIFT = 24, NREC_MASK = (1ull << CELL_SHIFT) - 1ull;
 static_assert(FT * 64 < (1 << CELL_SHIFT), "records of one block fit the low bits of its aggregate");
 static_assert((FT & (FT - 1)) == 0, "the item -> record search halves a power of two");
@@ -748,16 +749,13 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     __shared__ uint32_t s_scan32[2][FT / 32];
     uint32_t scan_parity = 0;
     __shared__ unsigned long long s_region;
-    __shared__ bool s_last;
     // fast blocks (no clipping / lines / wireframe): every warp compacts into a sub-region of its own
     __shared__ uint32_t s_celloff[FT];           // cells (rows x strip columns) of the records before this one
-    __shared__ uint32_t s_wcnt[FT / 32], s_wbase[FT / 32];  // segments stored by / first region offset of each warp
     __shared__ volatile uint32_t s_region_ready;
     if (threadIdx.x == 0) s_region_ready = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();  // k_seg_index may be scheduled while the last wave of this grid drains
     const uint32_t vb = blockIdx.x;
-    const uint32_t nblocks = (p.count + FT - 1) / FT;
     const uint32_t i = vb * FT + tid;
     const uint32_t prim = p.first + i;
 
@@ -891,19 +889,25 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         const uint32_t ipw = (((items + FT / 32 - 1) / (FT / 32)) + 31u) & ~31u;
         const uint32_t my0 = min((uint32_t)warp * ipw, items), my1 = min(my0 + ipw, items);
         uint32_t wbase = 0, wrun = 0;
+        // Item -> record without a search per item: the record of the warp's first item is found once (lo_base);
+        // inside a chunk of 32 consecutive items, lane j looks up where record lo_base + 1 + j begins, the lanes OR
+        // those boundaries into one mask, and an item's record is lo_base + the boundaries at or before it.
+        uint32_t lo_base = 0;
         if (my0 < my1) {
-            const uint32_t lo = locate(my0);
-            const SRec &r = s_rec[s_order[lo]];
-            const uint32_t cols = box_cols(p, r.x0, r.x1);
-            wbase = s_celloff[lo] + (my0 - s_rowoff[lo]) * cols;
+            lo_base = locate(my0);
+            const SRec &r = s_rec[s_order[lo_base]];
+            wbase = s_celloff[lo_base] + (my0 - s_rowoff[lo_base]) * box_cols(p, r.x0, r.x1);
         }
         bool have_region = false;
         for (uint32_t c0 = my0; c0 < my1; c0 += 32) {
             const uint32_t it = c0 + (uint32_t)lane;
+            const uint32_t rel = s_rowoff[min(lo_base + 1u + (uint32_t)lane, (uint32_t)FT)] - c0;  // >= 1
+            const uint32_t bmask = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+            const uint32_t lo = lo_base + (uint32_t)__popc(bmask & (0xffffffffu >> (31 - lane)));
+            lo_base += (uint32_t)__popc(bmask) + (__any_sync(0xffffffffu, rel == 32u) ? 1u : 0u);  // record of item c0 + 32
             uint32_t nseg = 0, ridx = 0;
             int y = 0;
             if (it < my1) {
-                const uint32_t lo = locate(it);
                 ridx = s_order[lo];
                 const SRec &r = s_rec[ridx];
                 y = row_base(p, r.x1, r.y0) + (int)(it - s_rowoff[lo]);
@@ -941,10 +945,22 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             }
             wrun += chunk_total;
         }
-        if (lane == 0) { s_wcnt[warp] = wrun; s_wbase[warp] = wbase; }
-        __syncthreads();
+        // Every warp publishes its own run and leaves: no barrier behind the walk (the block's warps used to wait
+        // here for the slowest of the four, then for thread 0's round trip to the block counter -- 15 % of the
+        // kernel's stall samples).  k_seg_index adds the runs up itself (group sums + the blocks of its group).
+        if (lane == 0) {
+            reinterpret_cast<uint32_t *>(wb.blk_wcnt + vb)[warp] = wrun;
+            reinterpret_cast<uint32_t *>(wb.blk_woff + vb)[warp] = wbase;
+            if (wrun) atomicAdd(&wb.blk_base[vb / FRONT_GROUP], (unsigned long long)wrun);
+            if (warp == 0) {
+                wb.blk_region[vb] = (uint32_t)min(my_region, 0xffffffffull);
+                if (nrec_blk) atomicAdd(&wb.counters->n_records, nrec_blk);
+            }
+        }
 #pragma unroll
-        for (int w = 0; w < FT / 32; w++) seg_run += s_wcnt[w];
+        for (int o = 16; o > 0; o >>= 1) covered += __shfl_down_sync(0xffffffffu, covered, o);
+        if (lane == 0 && covered) atomicAdd(&wb.counters->total_pixels, covered);  // TotalPixels, context.go:229
+        return;
     } else {
     for (uint32_t win0 = 0; win0 < nrec_blk; win0 += FT) {
         const uint32_t nw = min((uint32_t)FT, nrec_blk - win0);
@@ -1003,10 +1019,6 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             seg_run += chunk_total;
         }
     }
-    if (tid == 0) {  // one contiguous run from the front of the region
-        s_wcnt[0] = seg_run; s_wbase[0] = 0;
-        for (int w = 1; w < FT / 32; w++) { s_wcnt[w] = 0; s_wbase[w] = 0; }
-    }
     }
 
     // TotalPixels, context.go:229: every covered in-range pixel, before any depth test
@@ -1014,87 +1026,104 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     for (int o = 16; o > 0; o >>= 1) covered += __shfl_down_sync(0xffffffffu, covered, o);
     if (lane == 0 && covered) atomicAdd(&wb.counters->total_pixels, covered);
 
-    // ---- publish; the last block scans the aggregates ---------------------------------------------------
+    // ---- publish: one contiguous run from the front of the region ---------------------------------------------
     if (tid == 0) {
-        wb.blk_agg[vb] = ((unsigned long long)seg_run << 32) | nrec_blk;
-        wb.blk_region[vb] = (uint32_t)min(my_region, 0xffffffffull);
         static_assert(FT / 32 == 4, "blk_wcnt / blk_woff hold one entry per warp of a 128-thread block");
-        wb.blk_wcnt[vb] = make_uint4(s_wcnt[0], s_wcnt[1], s_wcnt[2], s_wcnt[3]);
-        wb.blk_woff[vb] = make_uint4(s_wbase[0], s_wbase[1], s_wbase[2], s_wbase[3]);
-        __threadfence();
-        s_last = atomicAdd(&wb.counters->blocks_done, 1u) == nblocks - 1u;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const uint32_t per = (nblocks + FT - 1) / FT;
-    const uint32_t b0 = min((uint32_t)tid * per, nblocks), b1 = min(b0 + per, nblocks);
-    unsigned long long sum = 0;  // segments << 32 | records (records of a draw < 2^30)
-    for (uint32_t b = b0; b < b1; b++) sum += __ldcg(&wb.blk_agg[b]);
-    unsigned long long incl2 = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl2, o);
-        if (lane >= o) incl2 += t;
-    }
-    if (lane == 31) s_scan[warp] = incl2;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long v = lane < FT / 32 ? s_scan[lane] : 0, vi = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, vi, o);
-            if (lane >= o) vi += t;
-        }
-        if (lane < FT / 32) s_scan[lane] = vi - v;
-        if (lane == FT / 32 - 1) s_scan[FT / 32] = vi;
-    }
-    __syncthreads();
-    unsigned long long run = s_scan[warp] + incl2 - sum;
-    for (uint32_t b = b0; b < b1; b++) {
-        wb.blk_base[b] = run >> 32;  // ordered position of the block's first segment
-        run += __ldcg(&wb.blk_agg[b]);
-    }
-    if (tid == 0) {
-        const unsigned long long tot = s_scan[FT / 32];
-        DrawCounters *c = wb.counters;
-        wb.tile_ctl->nheavy = 0; wb.tile_ctl->nlight = 0; wb.tile_ctl->head = 0;  // the busy-strip list of this draw
-        const unsigned long long cells_total = c->seg_cursor;  // every block has made its reservation
-        const uint32_t nsegs = (uint32_t)(tot >> 32);
-        c->n_records = (uint32_t)tot; c->need_records = 0;
-        c->n_rows = 0; c->need_rows = 0;
-        c->n_segs = nsegs;
-        c->need_segs = (unsigned int)min(cells_total, 0xfffffff0ull);
-        const unsigned nc = c->n_clip;
-        c->need_clip = nc;
-        unsigned ovf = 0;
-        if (cells_total > (unsigned long long)wb.cap_segs) ovf |= OVF_SEGS;
-        if (nc > wb.cap_clip) ovf |= OVF_CLIP;
-        if (ovf) atomicOr(&c->overflow, ovf);
+        wb.blk_wcnt[vb] = make_uint4(seg_run, 0u, 0u, 0u);
+        wb.blk_woff[vb] = make_uint4(0u, 0u, 0u, 0u);
+        wb.blk_region[vb] = (uint32_t)min(my_region, 0xffffffffull);
+        if (seg_run) atomicAdd(&wb.blk_base[vb / FRONT_GROUP], (unsigned long long)seg_run);
+        if (nrec_blk) atomicAdd(&wb.counters->n_records, nrec_blk);
     }
 }
 
-// Segments in primitive order for the stable sort: position blk_base[b] + (segments of the block's earlier warps)
-// + k  <-  slot blk_region[b] + blk_woff[b][w] + k.  One warp per (front-end block, warp run): a handful of loads
-// tell it where the run is, then it copies it with coalesced reads and writes, four independent loads in flight
-// per lane (no per-position search for the block).
-__global__ void __launch_bounds__(256)
+// Segments in primitive order for the stable sort: position (segments of all earlier blocks) + (segments of the
+// block's earlier warps) + k  <-  slot blk_region[b] + blk_woff[b][w] + k.  A CTA takes a contiguous range of
+// front-end blocks.  It first adds up what lies before its range -- the group sums k_front accumulated (one per
+// FRONT_GROUP blocks) plus the per-warp counts of the blocks between the group boundary and its range -- so k_front
+// needs neither a last-block scan nor a block counter; then one warp per (block, warp run) copies the run with
+// coalesced reads and writes, four independent loads in flight per lane.  CTA 0 also publishes the draw's totals
+// (segments, buffer needs, overflow) for the kernels behind it.
+constexpr int SI_THREADS = 256;
+__global__ void __launch_bounds__(SI_THREADS)
 k_seg_index(const __grid_constant__ WorkBuffers wb, uint32_t nent) {
+    __shared__ unsigned long long s_part[SI_THREADS / 32];
+    __shared__ uint32_t s_wtot[SI_THREADS / 32];
+    __shared__ uint32_t s_first[SI_THREADS];  // ordered position of the first segment of each block of the range
     pdl_wait();
     pdl_trigger();
-    const DrawCounters *ctr = wb.counters;
-    if (ctr->overflow) return;
-    const uint32_t n = min(ctr->n_segs, wb.cap_segs);
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5), ntasks = nent * 4u;
-    for (uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < ntasks; t += nwarps) {
-        const uint32_t b = t >> 2, w = t & 3u;
+    DrawCounters *ctr = wb.counters;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t ngroups = (nent + FRONT_GROUP - 1) / FRONT_GROUP;
+    // every block has made its reservation: the cursor is the sum of the upper bounds
+    const unsigned long long cells_total = ctr->seg_cursor;
+    const unsigned nclip = ctr->n_clip;
+    unsigned ovf = ctr->overflow;  // (k_front sets OVF_CLIP itself when the pool runs out)
+    if (cells_total > (unsigned long long)wb.cap_segs) ovf |= OVF_SEGS;
+    if (nclip > wb.cap_clip) ovf |= OVF_CLIP;
+    if (blockIdx.x == 0) {
+        // totals: all group sums
+        unsigned long long tot = 0;
+        for (uint32_t g = tid; g < ngroups; g += SI_THREADS) tot += wb.blk_base[g];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, o);
+        if (lane == 0) s_part[warp] = tot;
+        __syncthreads();
+        if (tid == 0) {
+            tot = 0;
+            for (int w = 0; w < SI_THREADS / 32; w++) tot += s_part[w];
+            wb.tile_ctl->nheavy = 0; wb.tile_ctl->nlight = 0; wb.tile_ctl->head = 0;  // the busy-strip list of this draw
+            ctr->need_records = 0; ctr->n_rows = 0; ctr->need_rows = 0;
+            ctr->n_segs = (unsigned int)min(tot, 0xfffffff0ull);
+            ctr->need_segs = (unsigned int)min(cells_total, 0xfffffff0ull);
+            ctr->need_clip = nclip;
+            if (ovf) atomicOr(&ctr->overflow, ovf);
+        }
+        __syncthreads();
+    }
+    if (ovf) return;
+    const uint32_t per = (nent + gridDim.x - 1) / gridDim.x;  // <= SI_THREADS (launch_seg_index)
+    const uint32_t b0 = min(blockIdx.x * per, nent), b1 = min(b0 + per, nent);
+    if (b0 >= b1) return;
+    // segments before block b0
+    const uint32_t g0 = b0 / FRONT_GROUP;
+    unsigned long long before = 0;
+    for (uint32_t g = tid; g < g0; g += SI_THREADS) before += wb.blk_base[g];
+    for (uint32_t b = g0 * FRONT_GROUP + tid; b < b0; b += SI_THREADS) {
+        const uint4 wc = wb.blk_wcnt[b];
+        before += (unsigned long long)wc.x + wc.y + wc.z + wc.w;
+    }
+    // ... and of each block of the range (per <= SI_THREADS: one block per thread, a block scan)
+    uint32_t mine = 0;
+    if (b0 + tid < b1) {
+        const uint4 wc = wb.blk_wcnt[b0 + tid];
+        mine = wc.x + wc.y + wc.z + wc.w;
+    }
+    const uint32_t incl = warp_incl_scan(mine);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_down_sync(0xffffffffu, before, o);
+    if (lane == 0) s_part[warp] = before;
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    unsigned long long base = 0;
+    uint32_t wprev = 0;
+#pragma unroll
+    for (int w = 0; w < SI_THREADS / 32; w++) {
+        base += s_part[w];
+        if (w < (int)warp) wprev += s_wtot[w];
+    }
+    if (tid < per) s_first[tid] = (uint32_t)min(base + wprev + incl - mine, 0xffffffffull);
+    __syncthreads();
+    const uint32_t n = wb.cap_segs;  // (without overflow every position is below the capacity: segments <= cells <= cap_segs)
+    const uint32_t ntasks = (b1 - b0) * 4u;
+    for (uint32_t t = warp; t < ntasks; t += SI_THREADS / 32) {
+        const uint32_t k_blk = t >> 2, b = b0 + k_blk, w = t & 3u;
         const uint4 wc = wb.blk_wcnt[b];
         const uint32_t cnt = w == 0 ? wc.x : (w == 1 ? wc.y : (w == 2 ? wc.z : wc.w));
         if (cnt == 0) continue;
         const uint4 wo = wb.blk_woff[b];
-        const uint32_t before = w == 0 ? 0u : (w == 1 ? wc.x : (w == 2 ? wc.x + wc.y : wc.x + wc.y + wc.z));
-        const uint32_t pos0 = (uint32_t)wb.blk_base[b] + before;
+        const uint32_t before_w = w == 0 ? 0u : (w == 1 ? wc.x : (w == 2 ? wc.x + wc.y : wc.x + wc.y + wc.z));
+        const uint32_t pos0 = s_first[k_blk] + before_w;
         const uint32_t slot0 = wb.blk_region[b] + (w == 0 ? wo.x : (w == 1 ? wo.y : (w == 2 ? wo.z : wo.w)));
         for (uint32_t k0 = 0; k0 < cnt; k0 += 128u) {
             uint32_t key[4];
@@ -1123,7 +1152,9 @@ int launch_front(const DrawParams &p, const WorkBuffers &wb, bool counters_clean
 }
 int launch_seg_index(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st) {
     const uint32_t blocks = (p.count + FT - 1) / FT;
-    launch_pdl(k_seg_index, 148 * 8, 256, 0, st, wb, blocks);
+    // a CTA scans its range of front-end blocks with one block per thread: at least blocks / SI_THREADS CTAs
+    const uint32_t grid = max(min(blocks, wb.nsm * 8u), (blocks + SI_THREADS - 1) / SI_THREADS);
+    launch_pdl(k_seg_index, grid, SI_THREADS, 0, st, wb, blocks);
     return 1;
 }
 

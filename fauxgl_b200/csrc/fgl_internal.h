@@ -174,6 +174,8 @@ struct WorkBuffers {
     TileCtl *tile_ctl;        // device
     uint32_t *vis_seg;        // [ntiles*TILE_W] deferred shading: per pixel of a busy strip, the segment (index into
                               //                 segv) whose fragment won, or 0xffffffff (allocated on the first deferred draw)
+    uint8_t *dirty;           // [ntiles] 1: some pixel of the strip had its depth written since the last depth clear (the
+                              //          sparse sort-last composite only exchanges such strips, fgl_comm.cu)
     unsigned long long *tile_clock;  // [ntiles][2] (cycles, smid<<32|segments) of the last k_strip launch; null unless FGL_TILE_CLOCK=1
     uint32_t *scan_tmp;       // block sums for scans / radix histograms
     DrawCounters *counters;   // device
@@ -290,9 +292,9 @@ int launch_mesh_bounds(const double *pos, uint32_t n, int nverts, unsigned long 
 int launch_depth_image(const double *depth, size_t npix, uint16_t *out, unsigned long long *scratch, cudaStream_t st);
 int launch_resolve(const uint32_t *src, int sw, int sh, uint32_t *dst, int factor, cudaStream_t st);
 int launch_composite_pack(const uint32_t *color, const double *depth, unsigned long long *keys, size_t npix,
-                          cudaStream_t st);
+                          cudaStream_t st, bool bias = true);
 int launch_composite_unpack(uint32_t *color, double *depth, const unsigned long long *keys, size_t npix,
-                            cudaStream_t st);
+                            cudaStream_t st, bool bias = true);
 int launch_composite_min(unsigned long long *inout, const unsigned long long *other, size_t n, cudaStream_t st);
 // `ops` 64-bit atomicMin on pseudo-random words of buf[0..words) (fgl_probe_atomic_rate)
 int launch_atomic_probe(unsigned long long *buf, size_t words, unsigned long long ops, cudaStream_t st);

@@ -179,17 +179,17 @@ __device__ __forceinline__ uint32_t depth32(double z) {
     return (uint32_t)(z * 4294967295.0);
 }
 __global__ void k_composite_pack(const uint32_t *__restrict__ color, const double *__restrict__ depth,
-                                 unsigned long long *__restrict__ keys, size_t npix) {
+                                 unsigned long long *__restrict__ keys, size_t npix, unsigned long long bias) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t c = color[i];
         const uint32_t be = ((c & 0xff) << 24) | (((c >> 8) & 0xff) << 16) | (((c >> 16) & 0xff) << 8) | (c >> 24);
-        keys[i] = (((unsigned long long)depth32(depth[i]) << 32) | be) ^ 0x8000000000000000ull;
+        keys[i] = (((unsigned long long)depth32(depth[i]) << 32) | be) ^ bias;
     }
 }
 __global__ void k_composite_unpack(uint32_t *__restrict__ color, double *__restrict__ depth,
-                                   const unsigned long long *__restrict__ keys, size_t npix) {
+                                   const unsigned long long *__restrict__ keys, size_t npix, unsigned long long bias) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
-        const unsigned long long k = keys[i] ^ 0x8000000000000000ull;
+        const unsigned long long k = keys[i] ^ bias;
         const uint32_t be = (uint32_t)k, d32 = (uint32_t)(k >> 32);
         color[i] = (be >> 24) | (((be >> 16) & 0xff) << 8) | (((be >> 8) & 0xff) << 16) | ((be & 0xff) << 24);
         depth[i] = d32 == 0xFFFFFFFFu ? 1.7976931348623157e308 : (double)d32 / 4294967295.0;
@@ -201,14 +201,15 @@ __global__ void k_composite_min(long long *__restrict__ inout, const long long *
         inout[i] = b < a ? b : a;
     }
 }
+// bias: keys ^ 2^63, so that a SIGNED 64-bit min (torch int64, gloo) orders them; unsigned collectives (ncclUint64) take them as they are
 int launch_composite_pack(const uint32_t *color, const double *depth, unsigned long long *keys, size_t npix,
-                          cudaStream_t st) {
-    k_composite_pack<<<148 * 8, 256, 0, st>>>(color, depth, keys, npix);
+                          cudaStream_t st, bool bias) {
+    k_composite_pack<<<148 * 8, 256, 0, st>>>(color, depth, keys, npix, bias ? 0x8000000000000000ull : 0ull);
     return 1;
 }
 int launch_composite_unpack(uint32_t *color, double *depth, const unsigned long long *keys, size_t npix,
-                            cudaStream_t st) {
-    k_composite_unpack<<<148 * 8, 256, 0, st>>>(color, depth, keys, npix);
+                            cudaStream_t st, bool bias) {
+    k_composite_unpack<<<148 * 8, 256, 0, st>>>(color, depth, keys, npix, bias ? 0x8000000000000000ull : 0ull);
     return 1;
 }
 // ---- peer-memory composite: compute + exchange in ONE kernel over NVLink ---------------------------------

@@ -458,6 +458,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                         const int i = lane + 32 * h;
                         if (i < tw) gdepth[grow + i] = t.depth[i];
                     }
+                    if (lane == 0) wb.dirty[strip] = 1;
                 }
             }
             if (wb.tile_clock && threadIdx.x == 0) {  // (s_nseg is complete: the last round ended with a barrier)
@@ -642,6 +643,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                 const int i = lane + 32 * h;
                 if (i < tw) gdepth[grow + i] = sm.depth[i];
             }
+            if (lane == 0) wb.dirty[strip] = 1;
         }
         if (wb.tile_clock && lane == 0) {
             unsigned smid;

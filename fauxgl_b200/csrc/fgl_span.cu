@@ -169,10 +169,15 @@ constexpr int TR_THREADS = 1024;
 // predecessor; only those few positions look 95 keys ahead for the heavy test.
 __global__ void __launch_bounds__(TR_THREADS)
 k_tile_ranges(const uint32_t *__restrict__ keys, DrawCounters *__restrict__ ctr, uint32_t n_max,
-              uint2 *__restrict__ busy_list, uint32_t ntiles, TileCtl *ctl) {
+              uint2 *__restrict__ busy_list, uint32_t ntiles, TileCtl *ctl, unsigned long long *__restrict__ group_sums,
+              uint32_t ngroups) {
     __shared__ uint32_t s_cnt[2], s_base[2], s_fill[2];
     pdl_wait();
     pdl_trigger();
+    // the group sums of the fused front end (k_front adds to them, k_seg_index has read them) are left zeroed for
+    // the next draw -- also when this one overflowed and is going to be re-issued
+    if (blockIdx.x == 0)
+        for (uint32_t g = threadIdx.x; g < ngroups; g += TR_THREADS) group_sums[g] = 0ull;
     if (ctr->overflow) return;  // the draw is going to be re-issued: its keys are incomplete
     const uint32_t n = min(ctr->n_segs, n_max);
     const uint32_t lane = threadIdx.x & 31;
@@ -279,7 +284,7 @@ int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cuda
     while ((1u << bits) < wb.ntiles) bits++;
     launches += launch_sort_pairs(wb.seg_key, wb.seg_val, &c->n_segs, wb.cap_segs, bits, wb.scan_tmp, sorted_buf, st);
     launch_pdl(k_tile_ranges, 148, TR_THREADS, 0, st, (const uint32_t *)wb.seg_key[*sorted_buf], c, wb.cap_segs, wb.busy_list,
-               wb.ntiles, wb.tile_ctl);
+               wb.ntiles, wb.tile_ctl, wb.blk_base, wb.cap_prims / (128u * 64u) + 2u);
     launches++;
     return launches;
 }

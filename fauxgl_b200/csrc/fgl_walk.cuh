@@ -171,9 +171,12 @@ __device__ __forceinline__ bool any_neg3(double b0, double b1, double b2) {
     return m != 0;
 }
 
-// The general walker as an out-of-line call that only reports the first segment (rows that alias into neighbours).
-static __device__ __noinline__ uint32_t walk_row_general(const DrawParams &p, const EdgeSetup e, int y, double w00, double w01,
-                                                  double w02, ParkedSeg *first, unsigned long long *covered) {
+// The general walker as an out-of-line call that only reports the first segment: rows of boxes that leave the
+// framebuffer sideways (they may alias into neighbouring rows).  Replays the per-row adds from y0 itself.
+static __device__ __noinline__ uint32_t walk_row_general(const DrawParams &p, const EdgeSetup e, int y0, int y, double w00,
+                                                         double w01, double w02, ParkedSeg *first,
+                                                         unsigned long long *covered) {
+    for (int yy = y0; yy < y; yy++) { w00 += e.b12; w01 += e.b20; w02 += e.b01; }  // context.go:275-277
     ParkedSeg f;
     f.w0 = f.w1 = f.w2 = 0; f.x = 0; f.cnt = 0; f.key = 0; f.wrap = 0;
     uint32_t k = 0;
@@ -192,6 +195,18 @@ static __device__ __noinline__ uint32_t walk_row_general(const DrawParams &p, co
 template <class R>
 __device__ __forceinline__ uint32_t walk_row_count(const DrawParams &p, const R &r, int y, ParkedSeg &first,
                                                    unsigned long long *covered) {
+    // A box that leaves the framebuffer sideways: its rows may start left of the pixels the reference keeps, or
+    // alias into neighbouring rows (row_x_range) -- the general walker handles both, out of line (rare: fat lines
+    // at the screen border), so that its state stays off this path's registers.  Every other box lies in
+    // 0 <= x0 <= x1 < width, its walked rows in [0, height): all its pixels are kept where they are.
+    if ((unsigned)r.x0 >= (unsigned)p.width || (unsigned)r.x1 >= (unsigned)p.width) {
+        ParkedSeg tmp;
+        unsigned long long cov = 0;
+        const uint32_t ns = walk_row_general(p, edge_setup(r), r.y0, y, r.w00, r.w01, r.w02, &tmp, &cov);
+        first = tmp;
+        *covered += cov;
+        return ns;
+    }
     const double a01 = r.s1y - r.s0y, b01 = r.s0x - r.s1x;  // context.go:167-172
     const double a12 = r.s2y - r.s1y, b12 = r.s1x - r.s2x;
     const double a20 = r.s0y - r.s2y, b20 = r.s2x - r.s0x;
@@ -208,21 +223,9 @@ __device__ __forceinline__ uint32_t walk_row_count(const DrawParams &p, const R 
     if (d < 0) d = 0;
     double w0 = w00 + a12 * d, w1 = w01 + a20 * d, w2 = w02 + a01 * d;
     // x0 + int(d) of the clamped d (context.go:207); beyond 2^40 the row starts right of any bounding box
-    long long xl = (long long)r.x0 + (di < 0 ? 0ll : (di > (1ll << 40) ? (1ll << 40) : di));
-    long long xlo, xhi;
-    row_x_range(p, y, xlo, xhi);
-    const long long xe64 = min((long long)r.x1, xhi);
+    const long long xl = (long long)r.x0 + (di < 0 ? 0ll : (di > (1ll << 40) ? (1ll << 40) : di));
+    const long long xe64 = (long long)r.x1;
     if (xl > xe64) return 0;
-    // A row that starts in front of the pixels the reference can keep, or reaches beyond the right edge, may alias
-    // into neighbouring rows (row_x_range): the general walker cuts it by the rows it lands in.
-    if (xl < max(xlo, 0ll) || xe64 >= (long long)p.width) {  // rare: out of line, its state stays off the hot path's registers
-        ParkedSeg tmp;
-        unsigned long long cov = 0;
-        const uint32_t ns = walk_row_general(p, edge_setup(r), y, w00, w01, w02, &tmp, &cov);
-        first = tmp;
-        *covered += cov;
-        return ns;
-    }
     const int xe = (int)xe64;
     int x = (int)xl;
     const double ra = r.ra;

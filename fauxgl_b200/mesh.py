@@ -104,6 +104,21 @@ class Mesh:
     def num_lines(self) -> int:
         return len(self.lposition)
 
+    def indexed(self):
+        """(v [n][3], vn [n][3], corners [T][3][3] int32): the triangle soup as shared-vertex tables, the form
+        fgl_mesh_create_indexed / fgl_mesh_update_indexed_async take (obj.go:19-79 parses such tables from a file).
+        Two corners share an entry when position AND normal are bit-identical, so expanding the tables gives the
+        soup back exactly.  The vt index of every corner is 0 (pass a single zero row as the vt table)."""
+        T = self.num_triangles
+        rec = np.ascontiguousarray(np.concatenate([self.position.reshape(T * 3, 3), self.normal.reshape(T * 3, 3)], axis=1))
+        key = rec.view(np.dtype((np.void, rec.dtype.itemsize * 6))).ravel()
+        _, first, inverse = np.unique(key, return_index=True, return_inverse=True)
+        table = rec[first]
+        corners = np.zeros((T, 3, 3), dtype=np.int32)
+        corners[:, :, 0] = inverse.reshape(T, 3)
+        corners[:, :, 2] = inverse.reshape(T, 3)
+        return np.ascontiguousarray(table[:, :3]), np.ascontiguousarray(table[:, 3:]), corners
+
     def Invalidate(self):
         """Call after poking the arrays directly (the reference lets users write
         ``mesh.Triangles[i].V1.Color = ...``; here that needs a re-upload)."""

@@ -16,8 +16,15 @@ Two ways the path shards:
    (smaller colour wins instead of the later triangle) and to the 32-bit depth
    quantisation; tests report the count.
 
-The reduction itself is ``torch.distributed.all_reduce(MIN)`` on int64 -- NCCL
-over NVLink/NVSwitch on the GPUs, gloo in the CPU tests.
+Three ways to run the reduction, all collective (every rank calls once per frame):
+
+* ``NcclComposite`` -- inside the library (fgl_comm_init / fgl_composite): stripe
+  reduce-scatter of the keys with ncclMin on ncclUint64, then a gather to the
+  presenting rank or an all-gather.  A Go host needs nothing else.
+* ``PeerGroup`` -- inside the library (fgl_peer_*): exact float64 depth, sparse (only
+  strips a rank has drawn), P2P loads/stores in one kernel per rank, device-side flags.
+* ``composite_min`` -- ``torch.distributed.all_reduce(MIN)`` on the biased int64
+  keys: the plain baseline (gloo in the CPU tests).
 """
 from __future__ import annotations
 
@@ -51,53 +58,120 @@ def composite_min(keys, group=None):
     return keys
 
 
-class PeerComposite:
-    """Sort-last composite over peer memory: ONE kernel per rank does the depth compare and the exchange
-    with P2P loads/stores through NVLink (fgl_composite_peer) instead of pack -> NCCL all-reduce -> unpack.
-    It keeps the float64 depth and breaks ties towards the higher rank (the later triangle range), so the
-    result equals a single-GPU render bit for bit in the order-independent state.
+def triangle_blocks(ntriangles: int, rank: int, world: int, block: int = 4096):
+    """Indices of the triangles of rank `rank` when blocks of `block` consecutive triangles are dealt
+    round-robin: the same total work as contiguous ranges, but every rank gets a share of every part of the
+    mesh (contiguous latitude bands leave the ranks that hold the far side of a closed surface idle).  The
+    composite does not care which rank drew a triangle (order-independent state)."""
+    import numpy as np
+    idx = np.arange(ntriangles, dtype=np.int64)
+    return idx[(idx // block) % world == rank]
 
-    Buffers are shared through CUDA IPC handles exchanged once with ``all_gather_object``; host barriers
-    fence the kernel (all ranks drawn before anyone reads; all composited before anyone draws again)."""
+
+class NcclComposite:
+    """fgl_comm_init / fgl_composite: the packed-key min-reduce with NCCL inside the library.  The unique id is
+    created on rank 0 and broadcast with torch.distributed (any transport would do)."""
 
     def __init__(self, ctx, rank: int, world: int, group=None):
+        import ctypes as C
         import torch.distributed as dist
-        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
-        mine = ctx.IpcExport()
-        handles = [None] * world
+        from .context import COMM_ID_BYTES, _check, capi
+        self.ctx, self.rank, self.world = ctx, rank, world
+        ident = [None]
+        if rank == 0:
+            buf = C.create_string_buffer(COMM_ID_BYTES)
+            _check(capi().fgl_comm_unique_id(buf))
+            ident[0] = buf.raw
         if world > 1:
-            dist.all_gather_object(handles, mine, group=group)
-        else:
-            handles[0] = mine
-        self.color, self.depth, self._opened = [], [], []
-        for r, (hc, hd) in enumerate(handles):
-            if r == rank:
-                self.color.append(ctx.color_ptr)
-                self.depth.append(ctx.depth_ptr)
-            else:
-                pc, pd = ctx.IpcOpen(hc, hd)
-                self._opened.append((pc, pd))
-                self.color.append(pc)
-                self.depth.append(pd)
+            dist.broadcast_object_list(ident, src=0, group=group)
+        self.handle = C.c_void_p()
+        _check(capi().fgl_comm_init(ctx._h, world, rank, ident[0], C.byref(self.handle)), ctx._h)
 
-    def _barrier(self):
-        import torch.distributed as dist
-        if self.world > 1:
-            dist.barrier(group=self.group)
+    def composite(self, root: int = 0):
+        """Enqueue pack -> reduce-scatter(min) -> gather to `root` (all-gather if root < 0) -> unpack."""
+        from .context import _check, capi
+        _check(capi().fgl_composite(self.ctx._h, self.handle, int(root)), self.ctx._h)
 
-    def composite(self):
-        """Call after this rank's draws of the frame; returns when every rank holds the full frame."""
-        info = self.ctx.Sync()               # (RasterizeInfo of this rank's async draws, if any)
-        self._barrier()                      # every rank's buffers are final
-        self.ctx.CompositePeer(self.rank, self.color, self.depth)
-        self.ctx.Sync()
-        self._barrier()                      # every stripe has been written everywhere
-        return info
+    def stage_times(self):
+        """{pack_ms, reduce_scatter_ms, gather_ms, unpack_ms} per composite issued while profiling was on."""
+        import ctypes as C
+        from .context import _check, capi
+        ms, n = (C.c_float * 4)(), C.c_uint32(0)
+        _check(capi().fgl_comm_stage_times(self.ctx._h, self.handle, ms, C.byref(n)), self.ctx._h)
+        k = max(int(n.value), 1)
+        return {"pack_ms": ms[0] / k, "reduce_scatter_ms": ms[1] / k, "gather_ms": ms[2] / k, "unpack_ms": ms[3] / k,
+                "composites": int(n.value)}
 
     def close(self):
-        for pc, pd in self._opened:
-            self.ctx.IpcClose(pc, pd)
-        self._opened = []
+        from .context import capi
+        if self.handle:
+            self.ctx.Sync()
+            capi().fgl_comm_destroy(self.handle)
+            self.handle = None
+
+
+class PeerGroup:
+    """fgl_peer_group: the exact, sparse, fused composite over peer memory.  ``records`` (one fgl_peer_export
+    record per rank, in rank order) are exchanged with ``all_gather_object`` when not given -- pass them
+    explicitly for ranks that live in one process (``PeerGroup.local``)."""
+
+    def __init__(self, ctx, rank: int, world: int, group=None, records=None):
+        import ctypes as C
+        from .context import _check, capi
+        self.ctx, self.rank, self.world = ctx, rank, world
+        if records is None:
+            import torch.distributed as dist
+            mine = ctx.PeerExport()
+            records = [None] * world
+            if world > 1:
+                dist.all_gather_object(records, mine, group=group)
+            else:
+                records[0] = mine
+        blob = b"".join(records)
+        self.handle = C.c_void_p()
+        _check(capi().fgl_peer_group_create(ctx._h, rank, world, blob, C.byref(self.handle)), ctx._h)
+
+    @classmethod
+    def local(cls, ctxs):
+        """One group object per context for ranks that are contexts of THIS process (any mix of devices)."""
+        records = [c.PeerExport() for c in ctxs]
+        return [cls(c, r, len(ctxs), records=records) for r, c in enumerate(ctxs)]
+
+    def composite(self, root: int = -1):
+        """Enqueue signal -> wait -> sparse composite -> signal -> wait on the context's stream (no host sync).
+        Afterwards rank `root` (every rank if root < 0) holds the frame."""
+        from .context import _check, capi
+        _check(capi().fgl_peer_composite(self.ctx._h, self.handle, int(root)), self.ctx._h)
+
+    @staticmethod
+    def composite_local(groups, root: int = -1):
+        """Composite for ranks that are contexts of THIS process, submitted by this one thread: phase by phase over all
+        ranks (fgl_peer_composite_phase), so that no waiting kernel is ever submitted ahead of the signal it waits for."""
+        from .context import _check, capi
+        for phase in (1, 2, 3):
+            for g in groups:
+                _check(capi().fgl_peer_composite_phase(g.ctx._h, g.handle, int(root), phase), g.ctx._h)
+
+    def stage_times(self):
+        """{wait_all_drawn_ms, composite_ms, wait_all_done_ms} per composite issued while profiling was on."""
+        import ctypes as C
+        from .context import _check, capi
+        ms, n = (C.c_float * 4)(), C.c_uint32(0)
+        _check(capi().fgl_peer_stage_times(self.ctx._h, self.handle, ms, C.byref(n)), self.ctx._h)
+        k = max(int(n.value), 1)
+        return {"wait_all_drawn_ms": ms[0] / k, "composite_ms": ms[1] / k, "wait_all_done_ms": ms[2] / k,
+                "composites": int(n.value)}
+
+    def status(self):
+        """Wait for the stream; raises if a rank never arrived."""
+        from .context import _check, capi
+        _check(capi().fgl_peer_status(self.ctx._h, self.handle), self.ctx._h)
+
+    def close(self):
+        from .context import capi
+        if self.handle:
+            capi().fgl_peer_group_destroy(self.handle)
+            self.handle = None
 
 
 def sort_last_draw(ctx, mesh, keys, rank: int, world: int, group=None):

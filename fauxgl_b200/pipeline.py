@@ -56,3 +56,43 @@ class FramePipeline:
 
     def __len__(self):
         return len(self.inflight)
+
+
+class IndexedFramePipeline:
+    """The same pipeline for a mesh kept as shared-vertex tables (``Mesh.indexed()``): the corner indices stay on
+    the device, a frame uploads only its v / vn tables (fgl_mesh_update_indexed_async) -- 48 bytes per shared vertex
+    instead of 144 per triangle -- and the expansion to the device layout runs on the copy stream."""
+
+    def __init__(self, ctx: Context, v: np.ndarray, vn: np.ndarray, corners: np.ndarray, depth: int = 2):
+        assert depth >= 1
+        self.ctx = ctx
+        vt = np.zeros((1, 3), dtype=np.float64)
+        self.slots = [{"mesh": DeviceMesh.FromIndexed(ctx, v, vt, vn, corners),
+                       "image": pinned_empty((ctx.Height, ctx.Width, 4), np.uint8),
+                       "fence": Fence(ctx)} for _ in range(depth)]
+        ctx.DrawMesh(self.slots[0]["mesh"])   # one synchronous draw sizes the work buffers
+        self.inflight = deque()
+        self.next = 0
+
+    def submit(self, v: np.ndarray, vn: np.ndarray, clear_color=None, clear_depth: bool = True):
+        """``v`` / ``vn``: this frame's tables (float64 [n][3]; pinned for a real overlap), unchanged until collected."""
+        if len(self.inflight) == len(self.slots):
+            raise RuntimeError("pipeline full: collect() a frame first")
+        slot = self.slots[self.next]
+        self.next = (self.next + 1) % len(self.slots)
+        slot["mesh"].update_indexed_async(v=v, vn=vn)
+        if clear_depth:
+            self.ctx.ClearDepthBuffer()
+        if clear_color is not None:
+            self.ctx.ClearColorBufferWith(clear_color)
+        self.ctx.DrawMeshAsync(slot["mesh"])
+        self.ctx.FrameEnd(slot["image"], slot["fence"])
+        self.inflight.append(slot)
+
+    def collect(self):
+        slot = self.inflight.popleft()
+        info = slot["fence"].wait()
+        return slot["image"], info
+
+    def __len__(self):
+        return len(self.inflight)

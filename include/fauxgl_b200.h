@@ -170,6 +170,13 @@ typedef struct fgl_indexed_desc {
     uint64_t ntriangles;
 } fgl_indexed_desc;
 int fgl_mesh_create_indexed(fgl_ctx *ctx, const fgl_indexed_desc *desc, fgl_mesh **out);
+/* Re-pose an indexed mesh (a host loop like examples/animate.go:66, which transforms the mesh every frame): the
+ * corner indices stayed on the device, only the v / vt / vn tables given (NULL = unchanged; sizes as at creation;
+ * desc->corners is ignored) are copied again -- on the context's copy stream, like fgl_mesh_update_async, with the
+ * same hand-over to the draw stream -- and expanded into the planes there.  For the 871 306-triangle benchmark mesh
+ * (436 k shared vertices) that is 21 MB per frame instead of 125 MB of expanded position + normal soup.  The host
+ * arrays (pinned memory for a real overlap) must stay unchanged until fgl_mesh_upload_wait returns. */
+int fgl_mesh_update_indexed_async(fgl_ctx *ctx, fgl_mesh *mesh, const fgl_indexed_desc *desc);
 /* Mesh.SmoothNormals, mesh.go:105-120, on the device: every triangle corner receives the normalised sum of the
  * normals of all corners at exactly the same position.  The sums are taken in the reference's order (triangle
  * index, then V1, V2, V3, starting from the zero vector), so the result is bit-identical: corners are grouped by a
@@ -307,6 +314,56 @@ int fgl_ipc_export(fgl_ctx *ctx, void *color_handle, void *depth_handle);
 int fgl_ipc_open(fgl_ctx *ctx, const void *color_handle, const void *depth_handle, void **color_ptr, void **depth_ptr);
 int fgl_ipc_close(fgl_ctx *ctx, void *color_ptr, void *depth_ptr);
 int fgl_composite_peer(fgl_ctx *ctx, int rank, int nranks, void *const *color, void *const *depth);
+
+/* ---- Sort-last composite inside the library ------------------------------------------------------
+ * The reference reduces the RasterizeInfo of its goroutines over a channel (context.go:393-410, 413-433) because
+ * they share one address space; ranks on different GPUs have to exchange pixels instead.  Everything below is
+ * enqueued on the context's stream and returns without waiting; read-backs, clears and draws issued afterwards are
+ * ordered behind it.  Collective: every rank of the group calls it once per frame, in the same order.
+ *
+ * (1) NCCL.  fgl_comm_unique_id: rank 0 obtains an id (FGL_COMM_ID_BYTES) and hands it to the other ranks by any
+ * means (torch.distributed, MPI, a file, a Go channel).  fgl_comm_init: every rank, with its context (collective;
+ * blocks until all ranks have joined).  fgl_composite: packs this rank's buffers into keys
+ * (depth32 << 32 | R<<24 | G<<16 | B<<8 | A), min-reduces them with ncclReduceScatter(ncclMin, ncclUint64) by screen
+ * stripe, and brings the stripes to rank `root` (grouped ncclSend/ncclRecv; only root's buffers then hold the frame)
+ * or, with root < 0, to every rank (ncclAllGather).  NCCL is loaded with dlopen (libnccl.so.2, or $FGL_NCCL_LIB) on
+ * first use; FGL_E_UNSUPPORTED if it is not installed.  Differences against a single-GPU render: depth ties (the
+ * smaller colour wins) and the 32-bit depth key; see fgl_peer_composite for the exact alternative. */
+#define FGL_COMM_ID_BYTES 128
+typedef struct fgl_comm fgl_comm;
+int fgl_comm_unique_id(void *id_out);
+int fgl_comm_init(fgl_ctx *ctx, int nranks, int rank, const void *id, fgl_comm **out);
+int fgl_comm_destroy(fgl_comm *comm);
+int fgl_composite(fgl_ctx *ctx, fgl_comm *comm, int root);
+/* Device time per stage of the composites issued while fgl_set_profiling was on, summed since the last call:
+ * ms[0] pack, ms[1] reduce-scatter, ms[2] gather / all-gather, ms[3] unpack; *composites = how many. */
+int fgl_comm_stage_times(fgl_ctx *ctx, fgl_comm *comm, float ms[4], uint32_t *composites);
+
+/* (2) Peer memory: exact (float64 depth, ties to the higher rank -- the later triangle range, the reference's `<=`
+ * rule -- so the result equals a single-GPU render bit for bit), sparse (only strips a rank has drawn into since its
+ * last depth clear are read from it) and synchronised on the device (flags in peer memory; no host barrier).
+ * fgl_peer_export fills a record of FGL_PEER_EXPORT_BYTES for this context (CUDA IPC handles of its colour, depth,
+ * dirty-strip and flag buffers); the host gathers the records of all ranks, in rank order, and passes them to
+ * fgl_peer_group_create on every rank.  Ranks may be processes (one per GPU) or contexts of one process (one host
+ * thread per GPU).  fgl_peer_composite(ctx, group, root): rank r composites the scanlines y = r (mod nranks) with ONE
+ * kernel of P2P loads and stores over NVLink and leaves the result in root's buffers (root >= 0) or in every rank's
+ * (root < 0).  fgl_peer_status waits for the stream and reports a rank that never arrived (10 s) as FGL_E_CUDA. */
+#define FGL_PEER_EXPORT_BYTES 512
+typedef struct fgl_peer_group fgl_peer_group;
+int fgl_peer_export(fgl_ctx *ctx, void *record);
+int fgl_peer_group_create(fgl_ctx *ctx, int rank, int nranks, const void *records, fgl_peer_group **out);
+int fgl_peer_group_destroy(fgl_peer_group *group);
+int fgl_peer_composite(fgl_ctx *ctx, fgl_peer_group *group, int root);
+/* The same in three steps, for ranks that share a DEVICE (several contexts of one process on one GPU, as in the
+ * single-GPU tests): a kernel that waits for a flag can occupy the hardware queue the kernel that sets the flag is
+ * submitted to, so the host has to submit phase 1 ("I have drawn") on every rank, then phase 2 (wait for all,
+ * composite, "I am done") on every rank, then phase 3 (wait for all) on every rank.  Ranks on different GPUs --
+ * processes or threads -- call fgl_peer_composite (= phase 0: all three at once). */
+int fgl_peer_composite_phase(fgl_ctx *ctx, fgl_peer_group *group, int root, int phase);
+int fgl_peer_status(fgl_ctx *ctx, fgl_peer_group *group);
+/* As fgl_comm_stage_times: ms[0] signal + wait until every rank has drawn (load imbalance shows up here), ms[1]
+ * bitmap gather + the composite kernel, ms[2] signal + wait until every rank has finished, ms[3] unused (0). */
+int fgl_peer_stage_times(fgl_ctx *ctx, fgl_peer_group *group, float ms[4], uint32_t *composites);
 
 /* Tuning aid: with FGL_TILE_CLOCK=1 in the environment when the context is created, the
  * tile kernel records, per screen tile, its SM cycles and (smid << 32 | segments in its bin);

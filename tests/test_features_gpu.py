@@ -50,6 +50,30 @@ def test_benchmark_mesh_ssaa_8k_and_resolve_bit_exact(m871k, oracle_lib, Context
     gctx.Close()
 
 
+@pytest.mark.timeout(900)
+def test_m10m_sphere_8k_bit_exact(oracle_lib, Context):
+    """BASELINE config 5 on ONE GPU: the 10 003 864-triangle sphere at 7680x4320 against the oracle.  The oracle runs
+    the reference's own threaded schedule (context.go:413-433 restated with pthreads), which in this
+    order-independent state (opaque, DepthBias 0, depth test on) gives the sequential depth and colour
+    (test_oracle_cpu.py::test_threaded_schedule_matches_sequential_when_order_free); TotalPixels is schedule
+    independent, UpdatedPixels is not and is not compared.  Bit-exact float64 depth and NRGBA8 colour."""
+    import os
+    from fauxgl_b200 import synth
+    mesh = synth.uv_sphere(2237, 2237)
+    assert mesh.num_triangles == 10003864
+    sc = scenes.dragon_scene(mesh, 7680, 4320)
+    octx = oracle_lib.OracleContext(sc.width, sc.height, threads=os.cpu_count() or 1)
+    oinfo = sc.run(octx)
+    gctx = Context(sc.width, sc.height)
+    gctx.upload_attributes = ("position", "normal")
+    ginfo = sc.run(gctx)
+    stats = compare_buffers(octx.ColorBuffer, octx.DepthBuffer, gctx.Image(), gctx.DepthBuffer)
+    print(stats, oinfo, ginfo)
+    assert stats["depth_mismatch"] == 0 and stats["color_mismatch"] == 0
+    assert ginfo[0][0] == oinfo[0][0] and ginfo[0][0] > 5_000_000
+    gctx.Close()
+
+
 @pytest.mark.parametrize("factor,w,h", [(2, 130, 70), (4, 256, 128), (3, 99, 60), (8, 64, 64), (1, 33, 17)])
 def test_resolve_matches_oracle(factor, w, h, oracle_lib, Context):
     rng = np.random.RandomState(factor)
