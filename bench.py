@@ -46,6 +46,12 @@ ALGO_BYTES_C2 = (T_TRIANGLES * 144 + (W1 * SSAA) * (H1 * SSAA) * 12
                  + (W1 * SSAA) * (H1 * SSAA) * 4 + W1 * H1 * 4)      # 664 604 064
 
 
+def log(msg: str):
+    """Progress on stderr (stdout carries the one JSON line)."""
+    sys.stderr.write("[bench %s] %s\n" % (os.environ.get("RANK", "0"), msg))
+    sys.stderr.flush()
+
+
 def load_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed summary of the
     latest `ncu --set full` capture (profiles/ncu_traffic.json; tools/ncu_summary.py writes the numbers)."""
@@ -163,7 +169,7 @@ def run_reference(args, rank):
                                    "goroutine schedule (no Go toolchain)" % len(times)},
         "e2e": {"value": value, "unit": "Mtri/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def bench_sort_last(args, rank, local_rank, world, barrier, max_over_ranks, use_dist):
@@ -179,6 +185,7 @@ def bench_sort_last(args, rank, local_rank, world, barrier, max_over_ranks, use_
     from fauxgl_b200 import multigpu, synth
     from fauxgl_b200.context import Context, DeviceMesh
     K = max(3, min(args.steps, 8))
+    log("sort-last: building the 10M-triangle sphere")
     nu = nv = 2237                                   # 2237 * (2*2237 - 2) = 10 003 864 triangles
     big = synth.uv_sphere(nu, nv)
     Tb = big.num_triangles
@@ -248,6 +255,7 @@ def bench_sort_last(args, rank, local_rank, world, barrier, max_over_ranks, use_
 
     runs = {}
     for partition in ("contiguous", "interleaved"):
+        log("sort-last: " + partition)
         if partition == "contiguous":
             first, count = multigpu.triangle_range(Tb, rank, world)
             part = type(big)(big.position[first:first + count], big.normal[first:first + count])
@@ -322,7 +330,27 @@ def bench_sort_last(args, rank, local_rank, world, barrier, max_over_ranks, use_
                            "interleaved": "blocks of 4096 consecutive triangles dealt round-robin"}}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries print there too (NCCL writes its version banner to stdout when
+    NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the run and the line goes to a
+    private duplicate of the original."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -418,6 +446,7 @@ def main():
         ctx.Close()
         return out
 
+    log("device-resident frames (value)")
     # `value`: no stage events between the kernels (they would serialise the programmatic dependent launches);
     # the per-stage times come from a second, shorter pass with the library's stage timers on.
     r1 = timed_frames(W1, H1, 0, K, Wm, False, probe=(rank == 0))
@@ -459,6 +488,7 @@ def main():
 
     # ---------------- 16x SSAA (7680x4320 + resolve) ----------------
     ssaa = None
+    log("8K + resolve")
     if not args.no_ssaa:
         K2 = max(3, min(K, 10))
         r2 = timed_frames(W1 * SSAA, H1 * SSAA, SSAA, K2, 3, False)
@@ -478,6 +508,7 @@ def main():
     # per stream, the longest interval counts.  No L2 flush is possible between concurrent frames; the working
     # set (mesh 125 MB + ~300 MB of segments per context) is several times the 126 MB L2.
     batch = None
+    log("animation batch")
     if not args.no_batch:
         from fauxgl_b200 import NewPhongShader, Rotate, V
         NCTX, NFRAMES = 4, 64
@@ -527,6 +558,7 @@ def main():
             c.Close()
 
     # ---------------- end to end through the public API with host buffers ----------------
+    log("end to end")
     Ke = max(3, min(K, 10))
     ctx = Context(W1, H1, local_rank)
     ctx.Shader = shader
@@ -672,11 +704,13 @@ def main():
 
     # ---------------- sort-last: 10 M-triangle sphere at 7680x4320 (BASELINE config 5) ----------------
     sort_last = None
+    log("sort-last")
     if not args.no_sort_last:
         sort_last = bench_sort_last(args, rank, local_rank, world, barrier, max_over_ranks, use_dist)
 
     # ---------------- CPU baseline beside it (rank 0, N == 1 only) ----------------
     cpu = None
+    log("cpu baseline")
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         times = cpu_reference_frames(mesh, 5, 1, cores)
@@ -701,7 +735,8 @@ def main():
             "raster_info": {"total_pixels": int(einfo.TotalPixels), "updated_pixels": int(einfo.UpdatedPixels),
                             "records": r1["records"], "pairs": r1["pairs"], "image_checksum": checksum},
         }
-        print(json.dumps(line))
+        emit(line)
+    log("done")
     if use_dist:
         dist.destroy_process_group()
 

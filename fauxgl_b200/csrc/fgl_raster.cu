@@ -676,18 +676,30 @@ k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     const uint32_t nbusy = wb.counters->overflow ? 0u : nheavy + wb.tile_ctl->nlight;
     const uint32_t tile_w = (uint32_t)p.tile_w, SPB = SHT / tile_w;  // strips per CTA pass
     const int pix = (int)(threadIdx.x % tile_w);
-    for (uint32_t q = blockIdx.x * SPB + threadIdx.x / tile_w; q < nbusy; q += gridDim.x * SPB) {
-        const uint32_t strip = busy_at(wb, nheavy, q).x;
-        const uint32_t sidx = wb.vis_seg[(size_t)strip * tile_w + pix];
-        if (sidx == NO_WINNER) continue;
-        const int x = (int)((strip % (uint32_t)p.tiles_x) * tile_w) + pix;
-        const int y = (int)(strip / (uint32_t)p.tiles_x);
+    // The loop is software-pipelined over its first two dependent loads: while strip q is shaded, the winner of the
+    // thread's next strip (q + stride) and the list entry of the one after it are in flight -- list entry -> winner
+    // -> segment record -> 18 attributes were four dependent memory round trips per pixel (long-scoreboard stall 9.7
+    // per issue, profiles/README.md).
+    const uint32_t stride = gridDim.x * SPB;
+    uint32_t q = blockIdx.x * SPB + threadIdx.x / tile_w;
+    auto strip_at = [&](uint32_t qq) { return qq < nbusy ? busy_at(wb, nheavy, qq).x : 0xffffffffu; };
+    auto winner_at = [&](uint32_t st_) { return st_ != 0xffffffffu ? wb.vis_seg[(size_t)st_ * tile_w + pix] : NO_WINNER; };
+    uint32_t strip = strip_at(q), strip1 = strip_at(q + stride);
+    uint32_t sidx = winner_at(strip);
+    for (; q < nbusy; q += stride) {
+        const uint32_t strip2 = strip_at(q + 2u * stride);   // in flight during this iteration
+        const uint32_t sidx1 = winner_at(strip1);            // its address arrived an iteration ago
+        const uint32_t cur_strip = strip, cur_sidx = sidx;
+        strip = strip1; strip1 = strip2; sidx = sidx1;
+        if (cur_sidx == NO_WINNER) continue;
+        const int x = (int)((cur_strip % (uint32_t)p.tiles_x) * tile_w) + pix;
+        const int y = (int)(cur_strip / (uint32_t)p.tiles_x);
         uint32_t *out = gcolor + (size_t)y * p.width + x;
         if (p.kind == FGL_SHADER_SOLID) {  // SolidColorShader.Fragment, shader.go:25-27: nothing to interpolate
             *out = c_nrgba(c4(p.color[0], p.color[1], p.color[2], p.color[3]));
             continue;
         }
-        const SegV *sp = wb.segv + sidx;
+        const SegV *sp = wb.segv + cur_sidx;
         const uint32_t src = sp->src, flags = sp->flags;
         double n[3][3], pos[3][3];  // all attribute loads are issued up front
         if (flags & REC_SRC_POOL) {
