@@ -220,24 +220,27 @@ def bench_sort_last(args, rank, local_rank, world, barrier, max_over_ranks, use_
         draw = sum(a.elapsed_time(b) for a, b in zip(s_ev, m_ev)) / steps
         return frame, draw, info
 
-    # ---- the single-GPU render of the whole mesh: the N = 1 anchor (timed on every rank-0) and the image to compare with
+    # ---- every rank keeps the whole mesh resident and draws a sub-range of it: re-balancing moves no data
+    dm_full = DeviceMesh(ctx, big, ("position", "normal"))
+    ctx.ClearDepthBuffer(); ctx.ClearColorBufferWith(bg_b)
+    full_info = ctx.DrawTriangles(dm_full)           # synchronous: sizes the work buffers, gives the RasterizeInfo
     ref_img = single = None
-    if rank == 0:
-        dm_full = DeviceMesh(ctx, big, ("position", "normal"))
+    if rank == 0:                                    # the single-GPU render of the whole mesh: the image to compare with
+        ref_img = ctx.Image().copy()
+        ref_depth = ctx.DepthBuffer
 
+    def stage_ms(st):
+        return {"geometry_ms": st.geometry_ms / st.draws, "spans_ms": st.spans_ms / st.draws,
+                "sort_ms": st.sort_ms / st.draws, "raster_ms": st.raster_ms / st.draws}
+    if world == 1:                                   # ... and the N = 1 anchor of the scaling curve
         def full_frame(mark):
             ctx.ClearDepthBuffer()
             ctx.ClearColorBufferWith(bg_b)
             ctx.DrawMeshAsync(dm_full)
             mark()
-        ctx.ClearDepthBuffer(); ctx.ClearColorBufferWith(bg_b)
-        full_info = ctx.DrawTriangles(dm_full)       # synchronous: sizes the work buffers, gives the RasterizeInfo
-        ref_img = ctx.Image().copy()
-        ref_depth = ctx.DepthBuffer
         for _ in range(2):
             full_frame(lambda: None)
         ctx.Sync()
-    if world == 1:
         fms, _, _ = timed(full_frame, K, ctx.Sync)
         ctx.SetProfiling(True)
         for _ in range(3):
@@ -245,35 +248,46 @@ def bench_sort_last(args, rank, local_rank, world, barrier, max_over_ranks, use_
         ctx.Sync()
         st = ctx.StageTimes()
         ctx.SetProfiling(False)
-        single = {"ms_per_frame": fms, "mtri_s": Tb / (fms / 1e3) / 1e6,
-                  "stages_ms": {"geometry_ms": st.geometry_ms / st.draws, "spans_ms": st.spans_ms / st.draws,
-                                "sort_ms": st.sort_ms / st.draws, "raster_ms": st.raster_ms / st.draws},
+        single = {"ms_per_frame": fms, "mtri_s": Tb / (fms / 1e3) / 1e6, "stages_ms": stage_ms(st),
                   "total_pixels": int(full_info.TotalPixels), "updated_pixels": int(full_info.UpdatedPixels)}
-    if rank == 0:
-        del dm_full
     barrier()
 
+    peer = multigpu.PeerGroup(ctx, rank, world)
+    nccl = multigpu.NcclComposite(ctx, rank, world)
     runs = {}
-    for partition in ("contiguous", "interleaved"):
+    for partition in ("contiguous", "balanced", "interleaved"):
         log("sort-last: " + partition)
-        if partition == "contiguous":
-            first, count = multigpu.triangle_range(Tb, rank, world)
-            part = type(big)(big.position[first:first + count], big.normal[first:first + count])
-        else:
+        dm, first, count = dm_full, 0, Tb
+        bounds = [r * Tb // world for r in range(world + 1)]
+        if partition == "interleaved":
             idx = multigpu.triangle_blocks(Tb, rank, world, 4096)
             part = type(big)(big.position[idx], big.normal[idx])
-        dm = DeviceMesh(ctx, part, ("position", "normal"))
-        del part
+            dm = DeviceMesh(ctx, part, ("position", "normal"))
+            first, count = 0, part.num_triangles
+            del part
+        elif partition == "balanced" and world > 1:
+            # feedback: draw, measure every rank's draw time, cut the cumulative cost into equal parts, repeat
+            for _round in range(6):
+                first, count = bounds[rank], bounds[rank + 1] - bounds[rank]
+                ctx.ClearDepthBuffer(); ctx.ClearColorBufferWith(bg_b)
+                ctx.DrawTriangles(dm, first, count)              # (sizes the work buffers for the new range)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(ext):
+                    e0.record(ext)
+                    for _ in range(3):
+                        ctx.ClearDepthBuffer(); ctx.ClearColorBufferWith(bg_b); ctx.DrawMeshAsync(dm, first, count)
+                    e1.record(ext)
+                ctx.Sync()
+                bounds = multigpu.rebalance_ranges(bounds, gather_floats(e0.elapsed_time(e1) / 3))
+        first, count = (bounds[rank], bounds[rank + 1] - bounds[rank]) if partition != "interleaved" else (first, count)
         ctx.ClearDepthBuffer(); ctx.ClearColorBufferWith(bg_b)
-        my_info = ctx.DrawTriangles(dm)              # synchronous: sizes the work buffers for this share
-        peer = multigpu.PeerGroup(ctx, rank, world)
-        nccl = multigpu.NcclComposite(ctx, rank, world)
+        my_info = ctx.DrawTriangles(dm, first, count)    # synchronous: sizes the work buffers for this share
         for method, comp, finish in (("peer", lambda: peer.composite(0), lambda: (ctx.Sync(), peer.status())[0]),
                                      ("nccl", lambda: nccl.composite(0), ctx.Sync)):
             def frame(mark, comp=comp):
                 ctx.ClearDepthBuffer()
                 ctx.ClearColorBufferWith(bg_b)
-                ctx.DrawMeshAsync(dm)
+                ctx.DrawMeshAsync(dm, first, count)
                 mark()
                 comp()
             for _ in range(2):
@@ -295,13 +309,13 @@ def bench_sort_last(args, rank, local_rank, world, barrier, max_over_ranks, use_
                 frame(lambda: None)
             finish()
             stages = (peer if method == "peer" else nccl).stage_times()
-            ctx.StageTimes()
+            dstages = stage_ms(ctx.StageTimes())
             ctx.SetProfiling(False)
             stages.pop("composites", None)
             runs["%s/%s" % (partition, method)] = {
                 "ms_per_frame": fms, "mtri_s": Tb / (fms / 1e3) / 1e6,
                 "draw_ms_max": max(draws), "draw_ms_min": min(draws), "draw_ms_per_rank": draws,
-                "composite_stages_ms_rank0": stages,
+                "draw_stages_ms_rank0": dstages, "composite_stages_ms_rank0": stages,
                 "mismatch_px": mism, "depth_mismatch_px": dmism,
                 "mismatch_frac": None if mism is None else mism / npix}
             if rank == 0:
@@ -310,10 +324,14 @@ def bench_sort_last(args, rank, local_rank, world, barrier, max_over_ranks, use_
                 assert dmism in (None, 0), (partition, method, dmism)
         totals = gather_floats(float(my_info.TotalPixels))
         runs[partition + "/total_pixels_per_rank"] = [int(v) for v in totals]
-        peer.close()
-        nccl.close()
-        del dm
+        if partition != "interleaved":
+            runs[partition + "/range_bounds"] = bounds
+        else:
+            del dm
         barrier()
+    peer.close()
+    nccl.close()
+    del dm_full
     ctx.Close()
     best = min((k for k in runs if "ms_per_frame" in (runs[k] if isinstance(runs[k], dict) else {})),
                key=lambda k: runs[k]["ms_per_frame"])
@@ -327,6 +345,8 @@ def bench_sort_last(args, rank, local_rank, world, barrier, max_over_ranks, use_
                         "nccl": "fgl_composite: packed keys (depth32<<32|rgba8), ncclReduceScatter(min, uint64) by stripe + "
                                 "ncclSend/Recv gather to rank 0, inside the library"},
             "partitions": {"contiguous": "rank r draws triangles [rT/N, (r+1)T/N)",
+                           "balanced": "contiguous ranges of equal measured draw time (six rounds of feedback: "
+                                       "multigpu.rebalance_ranges; every rank keeps the mesh resident, so moving a boundary moves no data)",
                            "interleaved": "blocks of 4096 consecutive triangles dealt round-robin"}}
 
 

@@ -68,6 +68,35 @@ def triangle_blocks(ntriangles: int, rank: int, world: int, block: int = 4096):
     return idx[(idx // block) % world == rank]
 
 
+def rebalance_ranges(bounds, times, damping: float = 0.8):
+    """Contiguous triangle ranges of equal measured COST instead of equal count.  ``bounds`` are the N+1 range
+    boundaries of the last frame, ``times[r]`` the time rank r took to draw [bounds[r], bounds[r+1]).  The cost
+    density is taken as constant inside each old range; the new boundaries cut the cumulative cost into N equal
+    parts (moved ``damping`` of the way, which keeps the iteration from oscillating).  A frame's cost is part
+    per-triangle (geometry) and part per-pixel (ranges that face the camera cover more pixels), so equal counts
+    leave the ranks up to 2x apart; a few frames of feedback bring them within a few percent."""
+    n = len(times)
+    assert len(bounds) == n + 1
+    total = float(sum(times))
+    if total <= 0:
+        return list(bounds)
+    new = [bounds[0]]
+    r, done = 0, 0.0        # walking through the old ranges: `done` = cost of the ranges before r
+    for k in range(1, n):
+        target = total * k / n
+        while r < n - 1 and done + times[r] < target:
+            done += times[r]
+            r += 1
+        width = bounds[r + 1] - bounds[r]
+        frac = 0.0 if times[r] <= 0 else (target - done) / times[r]
+        cut = bounds[r] + frac * width
+        old = bounds[k]
+        cut = old + damping * (cut - old)
+        new.append(int(min(max(round(cut), new[-1]), bounds[-1])))
+    new.append(bounds[-1])
+    return new
+
+
 class NcclComposite:
     """fgl_comm_init / fgl_composite: the packed-key min-reduce with NCCL inside the library.  The unique id is
     created on rank 0 and broadcast with torch.distributed (any transport would do)."""

@@ -111,3 +111,26 @@ def test_sort_last_composite_world2_gloo(tmp_path, oracle_lib):
     mismatch = int((want != k0).sum())
     print("sort-last composite mismatches vs single render:", mismatch, "of", want.size)
     assert mismatch <= max(1, int(1e-4 * want.size))   # depth ties / 32-bit quantisation only
+
+
+def test_rebalance_ranges_converges_to_equal_cost():
+    """multigpu.rebalance_ranges: feedback on measured per-rank times cuts the triangle index into contiguous ranges of
+    equal cost (the cost density along the index is not uniform: ranges that face the camera cover more pixels)."""
+    import numpy as np
+    from fauxgl_b200.multigpu import rebalance_ranges, triangle_blocks
+    dens = np.concatenate([np.full(3000, 1.0), np.full(4000, 3.0), np.full(3000, 0.5)])
+    for world in (2, 4, 8):
+        bounds = [r * len(dens) // world for r in range(world + 1)]
+        for _ in range(8):
+            times = [float(dens[bounds[i]:bounds[i + 1]].sum()) for i in range(world)]
+            bounds = rebalance_ranges(bounds, times)
+            assert bounds[0] == 0 and bounds[-1] == len(dens) and all(a <= b for a, b in zip(bounds, bounds[1:]))
+        times = [float(dens[bounds[i]:bounds[i + 1]].sum()) for i in range(world)]
+        assert max(times) <= 1.03 * (sum(times) / world), (world, bounds, times)
+    # degenerate inputs leave the ranges alone / valid
+    assert rebalance_ranges([0, 5, 10], [0.0, 0.0]) == [0, 5, 10]
+    assert rebalance_ranges([0, 10], [3.0]) == [0, 10]
+    # the round-robin block partition covers every triangle exactly once
+    T, world = 100003, 3
+    parts = [triangle_blocks(T, r, world, 4096) for r in range(world)]
+    assert sorted(np.concatenate(parts).tolist()) == list(range(T))
