@@ -132,6 +132,10 @@ ABI = [
     ("fgl_fence_wait", C.c_int, [_P, _P, C.POINTER(_Info)]),
     ("fgl_fence_destroy", C.c_int, [_P]),
     ("fgl_get_draw_stats", C.c_int, [_P, C.POINTER(DrawStats)]),
+    ("fgl_graph_begin", C.c_int, [_P]),
+    ("fgl_graph_end", C.c_int, [_P, C.POINTER(_P)]),
+    ("fgl_graph_launch", C.c_int, [_P, _P]),
+    ("fgl_graph_destroy", C.c_int, [_P]),
     ("fgl_set_profiling", C.c_int, [_P, C.c_int]),
     ("fgl_get_stage_times", C.c_int, [_P, C.POINTER(StageTimes)]),
     ("fgl_read_color", C.c_int, [_P, _P, C.c_size_t]),
@@ -223,6 +227,20 @@ class Fence:
         if self.handle:
             _check(capi().fgl_fence_wait(self.ctx._h, self.handle, C.byref(info)), self.ctx._h)
         return RasterizeInfo(info.total_pixels, info.updated_pixels)
+
+
+class FrameGraph:
+    """fgl_graph: a recorded frame (CUDA graph) of one context; ``launch()`` replays it with one call."""
+
+    def __init__(self, ctx: "Context", handle):
+        self.ctx, self.handle = ctx, handle
+        self._fin = weakref.finalize(self, capi().fgl_graph_destroy, handle)
+
+    def launch(self):
+        _check(capi().fgl_graph_launch(self.ctx._h, self.handle), self.ctx._h)
+
+    def Close(self):
+        self._fin()
 
 
 class DeviceTexture:
@@ -646,6 +664,15 @@ class Context:
         if fence._fin is None:
             fence._fin = weakref.finalize(fence, capi().fgl_fence_destroy, fence.handle)
         return fence
+
+    def GraphBegin(self):
+        """fgl_graph_begin: record the following clears / async draws / resolves instead of running them."""
+        _check(capi().fgl_graph_begin(self._h), self._h)
+
+    def GraphEnd(self) -> FrameGraph:
+        h = _P()
+        _check(capi().fgl_graph_end(self._h, C.byref(h)), self._h)
+        return FrameGraph(self, h)
 
     def SetProfiling(self, enabled: bool):
         _check(capi().fgl_set_profiling(self._h, int(enabled)), self._h)

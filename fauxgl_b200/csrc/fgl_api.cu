@@ -175,6 +175,13 @@ Caps grown(const fgl_ctx *c, const DrawCounters &hc) {
                 g(c->wb.cap_segs, hc.need_segs), g(c->wb.cap_clip, hc.need_clip)};
 }
 
+// Entry points that wait for the stream (or allocate / free buffers recorded launches may use) are errors while a
+// graph is being recorded: a synchronisation would invalidate the capture.
+#define NOT_WHILE_RECORDING(c, what)                                                                              \
+    do {                                                                                                          \
+        if ((c)->capturing) return fail(c, FGL_E_INVALID, what " waits for the device and cannot be recorded into a graph"); \
+    } while (0)
+
 int check_ctx(fgl_ctx *c) {
     if (!c) return fail(nullptr, FGL_E_INVALID, "null context");
     cudaError_t e = cudaSetDevice(c->device);
@@ -186,14 +193,14 @@ int check_ctx(fgl_ctx *c) {
 // draw stream used it, `release` lets the next streaming upload know when it may overwrite the buffers.
 void mesh_acquire(fgl_ctx *c, const fgl_mesh *cm) {
     fgl_mesh *m = const_cast<fgl_mesh *>(cm);
-    if (m->upload_pending) {
+    if (m->upload_pending && !c->capturing) {
         cudaStreamWaitEvent(c->stream, m->ev_uploaded, 0);
         m->upload_pending = false;
     }
 }
 void mesh_release(fgl_ctx *c, const fgl_mesh *cm) {
     fgl_mesh *m = const_cast<fgl_mesh *>(cm);
-    if (m->has_events) {
+    if (m->has_events && !c->capturing) {
         cudaEventRecord(m->ev_drawn, c->stream);
         m->drawn_recorded = true;
     }
@@ -374,6 +381,19 @@ int draw_common(fgl_ctx *c, const fgl_state *state, const fgl_shader *sh, const 
         }
         p.prim_info = c->prim_info;
     }
+    if (c->capturing) {
+        // a recorded frame replays fixed launches over fixed buffers: nothing may block, allocate or wait for an upload
+        if (!async) return fail(c, FGL_E_INVALID, "only the *_async draws can be recorded into a graph (a synchronous draw waits for its RasterizeInfo)");
+        if (mesh->upload_pending) return fail(c, FGL_E_INVALID, "fgl_mesh_upload_wait the mesh before recording a graph that draws it");
+        if (c->profiling) return fail(c, FGL_E_INVALID, "switch the stage timers off while recording a graph");
+        const WorkBuffers before = c->wb;
+        rc = initial_capacity(c, p);
+        if (rc) return rc;
+        if ((p.deferred && !c->wb.vis_seg) || before.segv != c->wb.segv || before.recs != c->wb.recs ||
+            before.row_first != c->wb.row_first || before.clip_pool != c->wb.clip_pool || before.blk_agg != c->wb.blk_agg)
+            return fail(c, FGL_E_INVALID, "the work buffers had to grow while recording: issue one synchronous draw of this mesh "
+                                          "first (it sizes them), then record again");
+    }
     if (p.deferred && !c->wb.vis_seg)  // winners of the deferred-shading path, strip-major
         CK(c, dev_alloc(&c->wb.vis_seg, (size_t)c->wb.ntiles * c->tile_w));
     rc = initial_capacity(c, p);
@@ -426,6 +446,79 @@ void api_fb_join(fgl_ctx *ctx) { fb_join(ctx); }
 }  // namespace fgl
 
 extern "C" {
+
+// ---- recorded frames (CUDA graphs) -----------------------------------------------------------------------------
+
+int fgl_graph_begin(fgl_ctx *c) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (c->capturing) return fail(c, FGL_E_INVALID, "already recording a graph on this context");
+    fb_join(c);  // (a clear issued before the recording belongs to the work before it)
+    // relaxed: the recorded calls may use cudaMalloc-free helper calls of other threads' contexts meanwhile
+    CK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    c->capturing = true;
+    c->counters_clean = false;  // the recorded frame zeroes the draw counters itself, whatever ran before a replay
+    return FGL_OK;
+}
+
+int fgl_graph_end(fgl_ctx *c, fgl_graph **out) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!out) return fail(c, FGL_E_INVALID, "null out pointer");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!c->capturing) return fail(c, FGL_E_INVALID, "fgl_graph_end without fgl_graph_begin");
+    fb_join(c);  // the clear stream joins the recording again
+    c->capturing = false;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    if (e != cudaSuccess || !g) {
+        cudaGetLastError();
+        c->counters_clean = false;
+        return fail(c, FGL_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    }
+    cudaGraphExec_t ex = nullptr;
+    e = cudaGraphInstantiate(&ex, g, 0);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaGraphDestroy(g);
+        c->counters_clean = false;
+        return fail(c, FGL_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    fgl_graph *gr = new (std::nothrow) fgl_graph();
+    if (!gr) { cudaGraphExecDestroy(ex); cudaGraphDestroy(g); return fail(c, FGL_E_OOM, "host allocation failed"); }
+    gr->device = c->device; gr->ctx = c; gr->graph = g; gr->exec = ex;
+    gr->has_draws = c->async_pending;   // (set by the recorded draws; nothing ran yet)
+    gr->counters_clean = c->counters_clean;
+    c->async_pending = false;           // the recording itself drew nothing
+    c->counters_clean = false;
+    *out = gr;
+    return FGL_OK;
+}
+
+int fgl_graph_launch(fgl_ctx *c, fgl_graph *g) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!g || g->ctx != c) return fail(c, FGL_E_INVALID, "graph belongs to another context");
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (c->capturing) return fail(c, FGL_E_INVALID, "cannot launch a graph while recording one");
+    fb_join(c);
+    CK(c, cudaGraphLaunch(g->exec, c->stream));
+    if (g->has_draws) c->async_pending = true;
+    c->counters_clean = g->counters_clean;
+    return FGL_OK;
+}
+
+int fgl_graph_destroy(fgl_graph *g) {
+    if (!g) return FGL_OK;
+    cudaSetDevice(g->device);
+    if (g->ctx && g->ctx->stream) cudaStreamSynchronize(g->ctx->stream);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return FGL_OK;
+}
 
 int fgl_abi_version(void) { return FGL_ABI_VERSION; }
 
@@ -489,8 +582,10 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     memset(&c->wb, 0, sizeof c->wb);
     memset(&c->stats, 0, sizeof c->stats);
     c->host_counters = nullptr; c->acc_dev = nullptr; c->async_pending = false; c->counters_clean = false;
+    c->capturing = false;
     c->prim_info = nullptr; c->prim_info_cap = 0; c->scratch = nullptr; c->gray16 = nullptr;
-    c->peer_flags = nullptr; c->peer_epoch = 0;
+    c->peer_flags = nullptr; c->peer_epoch = 0; c->clear_depth_value = 1.7976931348623157e308;
+    c->clear_color_value = 0u; c->clear_color_known = true;  // NewContext: transparent black
     c->profiling = false; c->prof_used = 0; c->prof_created = false;
     memset(&c->prof_acc, 0, sizeof c->prof_acc);
     const size_t npix = (size_t)width * height;
@@ -592,6 +687,7 @@ int fgl_clear_color(fgl_ctx *c, const uint8_t rgba[4]) {
     const uint32_t v = (uint32_t)rgba[0] | ((uint32_t)rgba[1] << 8) | ((uint32_t)rgba[2] << 16) | ((uint32_t)rgba[3] << 24);
     launch_clear_color(c->color, (size_t)c->w * c->h, v, fb_clear_begin(c));
     fb_clear_end(c);
+    c->clear_color_value = v; c->clear_color_known = true;
     CK(c, cudaGetLastError());
     return FGL_OK;
 }
@@ -602,6 +698,7 @@ int fgl_clear_depth(fgl_ctx *c, double value) {
     std::lock_guard<std::mutex> lock(c->mu);
     cudaStream_t cs = fb_clear_begin(c);
     cudaMemsetAsync(c->wb.dirty, 0, c->wb.ntiles, cs);  // no strip has drawn depth any more
+    c->clear_depth_value = value;
     launch_clear_depth(c->depth, (size_t)c->w * c->h, value, cs);
     fb_clear_end(c);
     CK(c, cudaGetLastError());
@@ -657,6 +754,7 @@ int fgl_mesh_create(fgl_ctx *c, const fgl_mesh_desc *d, fgl_mesh **out) {
     if ((d->ntriangles && !d->position) || (d->nlines && !d->lposition))
         return fail(c, FGL_E_INVALID, "position array missing");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_mesh_create");
     fgl_mesh *m = new (std::nothrow) fgl_mesh();
     if (!m) return fail(c, FGL_E_OOM, "host allocation failed");
     memset(m, 0, sizeof *m);
@@ -681,6 +779,7 @@ int fgl_mesh_update(fgl_ctx *c, fgl_mesh *m, const fgl_mesh_desc *d) {
                     (unsigned long long)d->ntriangles, (unsigned long long)d->nlines, (unsigned long long)m->nt,
                     (unsigned long long)m->nl);
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_mesh_update");
     mesh_acquire(c, m);
     return upload_all(c, m, d, false);
 }
@@ -694,6 +793,7 @@ int fgl_mesh_update_async(fgl_ctx *c, fgl_mesh *m, const fgl_mesh_desc *d) {
     if (d->ntriangles != m->nt || d->nlines != m->nl)
         return fail(c, FGL_E_INVALID, "fgl_mesh_update_async needs the same primitive counts");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_mesh_update_async");
     if (!m->has_events) {
         CK(c, cudaEventCreateWithFlags(&m->ev_uploaded, cudaEventDisableTiming));
         CK(c, cudaEventCreateWithFlags(&m->ev_drawn, cudaEventDisableTiming));
@@ -719,6 +819,7 @@ int fgl_mesh_update_indexed_async(fgl_ctx *c, fgl_mesh *m, const fgl_indexed_des
     if ((d->v && d->nv != m->nv) || (d->vt && d->nvt != m->nvt) || (d->vn && d->nvn != m->nvn))
         return fail(c, FGL_E_INVALID, "fgl_mesh_update_indexed_async needs tables of the sizes the mesh was created with");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_mesh_update_indexed_async");
     if (!m->has_events) {
         CK(c, cudaEventCreateWithFlags(&m->ev_uploaded, cudaEventDisableTiming));
         CK(c, cudaEventCreateWithFlags(&m->ev_drawn, cudaEventDisableTiming));
@@ -753,6 +854,7 @@ int fgl_mesh_create_stl(fgl_ctx *c, const uint8_t *records, uint64_t count, fgl_
     *out = nullptr;
     if (count > 0xfffffff0ull) return fail(c, FGL_E_INVALID, "mesh too large");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_mesh_create_stl");
     fgl_mesh *m = new (std::nothrow) fgl_mesh();
     if (!m) return fail(c, FGL_E_OOM, "host allocation failed");
     memset(m, 0, sizeof *m);
@@ -801,6 +903,7 @@ int fgl_mesh_create_indexed(fgl_ctx *c, const fgl_indexed_desc *d, fgl_mesh **ou
             return fail(c, FGL_E_INVALID, "corner %llu of the indexed mesh points outside its table", (unsigned long long)k);
     }
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_mesh_create_indexed");
     fgl_mesh *m = new (std::nothrow) fgl_mesh();
     if (!m) return fail(c, FGL_E_OOM, "host allocation failed");
     memset(m, 0, sizeof *m);
@@ -849,6 +952,7 @@ int fgl_mesh_bounds(fgl_ctx *c, const fgl_mesh *m, double mn[3], double mx[3]) {
     if (!m || !mn || !mx) return fail(c, FGL_E_INVALID, "null mesh/out pointer");
     if (m->device != c->device) return fail(c, FGL_E_INVALID, "mesh lives on another device");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_mesh_bounds");
     unsigned long long h[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
     mesh_acquire(c, m);
     CK(c, cudaMemcpyAsync(c->scratch, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
@@ -911,6 +1015,7 @@ static int smooth_normals_common(fgl_ctx *c, fgl_mesh *m, bool with_threshold, d
     if (m->nt == 0) return FGL_OK;
     if (m->nt > 0x55555555ull) return fail(c, FGL_E_INVALID, "mesh too large for 32-bit corner indices");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_mesh_smooth_normals");
     const uint32_t n = (uint32_t)m->nt, nc = 3u * n;
     uint32_t *key[2] = {nullptr, nullptr}, *val[2] = {nullptr, nullptr}, *tmp = nullptr;
     unsigned int *n_dev = nullptr;
@@ -967,6 +1072,7 @@ int fgl_mesh_read(fgl_ctx *c, const fgl_mesh *m, double *position, double *norma
     if (rc) return rc;
     if (!m) return fail(c, FGL_E_INVALID, "null mesh");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_mesh_read");
     mesh_acquire(c, m);
     rc = read_attr(c, m->tpos, position, m->nt, 3, 3);
     if (!rc) rc = read_attr(c, m->tnrm, normal, m->nt, 3, 3);
@@ -985,6 +1091,7 @@ int fgl_texture_create(fgl_ctx *c, const uint8_t *rgba8, int width, int height, 
         return fail(c, FGL_E_INVALID, "bad texture format %d", format);
     *out = nullptr;
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_texture_create");
     fgl_tex *t = new (std::nothrow) fgl_tex();
     if (!t) return fail(c, FGL_E_OOM, "host allocation failed");
     t->device = c->device; t->w = width; t->h = height; t->format = format; t->pixels = nullptr;
@@ -1041,6 +1148,7 @@ int fgl_sync(fgl_ctx *c, fgl_raster_info *info) {
     int rc = check_ctx(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_sync");
     if (info) { info->total_pixels = 0; info->updated_pixels = 0; }
     fb_join(c);
     if (c->async_pending) {
@@ -1069,6 +1177,7 @@ int fgl_frame_end(fgl_ctx *c, uint8_t *color_dst, size_t stride, fgl_fence **fen
     if (stride == 0) stride = (size_t)c->w * 4;
     if (stride < (size_t)c->w * 4) return fail(c, FGL_E_INVALID, "stride too small");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_frame_end");
     fgl_fence *f = *fence;
     if (!f) {
         f = new (std::nothrow) fgl_fence();
@@ -1136,6 +1245,7 @@ int fgl_set_profiling(fgl_ctx *c, int enabled) {
     int rc = check_ctx(c);
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_set_profiling");
     if (enabled && !c->prof_created) {
         for (int i = 0; i < PROF_RING; i++)
             for (int k = 0; k < PROF_EVENTS; k++) CK(c, cudaEventCreate(&c->prof[i].e[k]));
@@ -1166,6 +1276,7 @@ int fgl_read_color(fgl_ctx *c, uint8_t *dst, size_t stride) {
     if (stride == 0) stride = (size_t)c->w * 4;
     if (stride < (size_t)c->w * 4) return fail(c, FGL_E_INVALID, "stride too small");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_read_color");
     fb_join(c);
     CK(c, cudaMemcpy2DAsync(dst, stride, c->color, (size_t)c->w * 4, (size_t)c->w * 4, c->h, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
@@ -1176,6 +1287,7 @@ int fgl_read_depth(fgl_ctx *c, double *dst) {
     if (rc) return rc;
     if (!dst) return fail(c, FGL_E_INVALID, "null destination");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_read_depth");
     fb_join(c);
     CK(c, cudaMemcpyAsync(dst, c->depth, sizeof(double) * c->w * c->h, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
@@ -1186,6 +1298,7 @@ int fgl_depth_image(fgl_ctx *c, uint16_t *dst) {
     if (rc) return rc;
     if (!dst) return fail(c, FGL_E_INVALID, "null destination");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_depth_image");
     const size_t npix = (size_t)c->w * c->h;
     if (!c->gray16) CK(c, dev_alloc(&c->gray16, npix));
     fb_join(c);
@@ -1203,8 +1316,10 @@ int fgl_write_color(fgl_ctx *c, const uint8_t *src, size_t stride) {
     if (stride == 0) stride = (size_t)c->w * 4;
     if (stride < (size_t)c->w * 4) return fail(c, FGL_E_INVALID, "stride too small");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_write_color");
     fb_join(c);
     CK(c, cudaMemcpy2DAsync(c->color, (size_t)c->w * 4, src, stride, (size_t)c->w * 4, c->h, cudaMemcpyHostToDevice, c->stream));
+    c->clear_color_known = false;
     CK(c, cudaStreamSynchronize(c->stream));
     return FGL_OK;
 }
@@ -1213,9 +1328,11 @@ int fgl_write_depth(fgl_ctx *c, const double *src) {
     if (rc) return rc;
     if (!src) return fail(c, FGL_E_INVALID, "null source");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_write_depth");
     fb_join(c);
     CK(c, cudaMemcpyAsync(c->depth, src, sizeof(double) * c->w * c->h, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaMemsetAsync(c->wb.dirty, 1, c->wb.ntiles, c->stream));  // any strip may hold drawn depth now
+    c->clear_depth_value = __builtin_nan("");
     CK(c, cudaStreamSynchronize(c->stream));
     return FGL_OK;
 }
@@ -1250,6 +1367,7 @@ int fgl_read_resolved(fgl_ctx *c, uint8_t *dst) {
     if (!dst) return fail(c, FGL_E_INVALID, "null destination");
     if (!c->resolved) return fail(c, FGL_E_INVALID, "nothing resolved yet");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_read_resolved");
     CK(c, cudaMemcpyAsync(dst, c->resolved, (size_t)c->rw * c->rh * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return FGL_OK;
@@ -1361,6 +1479,7 @@ int fgl_probe_atomic_rate(fgl_ctx *c, uint64_t ops, double *ops_per_second) {
     if (rc) return rc;
     if (!ops_per_second || ops == 0) return fail(c, FGL_E_INVALID, "null result pointer / zero operations");
     std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_probe_atomic_rate");
     const size_t words = (size_t)c->w * c->h;
     unsigned long long *buf = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -207,13 +207,19 @@ __global__ void k_peer_gather_dirty(const PeerSet P, int nranks, uint32_t ntiles
 }
 
 // The sparse composite.  One warp per strip of the scanlines this rank owns (y = rank mod nranks).  Candidates: with
-// a presenting rank `root`, the peers whose bitmap has the strip, plus root itself; otherwise all ranks (every rank
-// receives the result, so every rank's own pixel takes part).  Per pixel: the candidates' float64 depths are loaded
-// (all loads issued before the first compare), the smallest wins -- on a tie the higher rank --, only the winner's
-// colour is fetched, and depth + colour go to the target(s) that do not already hold them.
+// a presenting rank `root`, the ranks whose bitmap has the strip -- a strip only root has drawn needs nothing, and an
+// undrawn strip of root's holds its clear value everywhere, which no drawn fragment of a peer can lose against
+// (it passed `z <= clear` on its own rank; all ranks clear with the same value), so root's buffer is not even read
+// there, and a pixel that still holds the clear depth AND the clear colour (`clear_z`, `clear_c`; NaN / unknown after
+// an upload: then everything is stored) is not stored -- root's own pixel is identical; with root < 0 all
+// ranks are candidates (every rank receives the result, so every rank's own pixel takes part).  Per pixel: the
+// candidates' float64 depths are loaded (all loads issued before the first compare), the smallest wins -- on a tie
+// the higher rank --, only the winner's colour is fetched, and depth + colour go to the target(s) that do not
+// already hold them.
 __global__ void __launch_bounds__(256)
 k_peer_composite(const PeerSet P, int rank, int nranks, int root, int width, int height, int tile_w, int tiles_x,
-                 const uint8_t *__restrict__ dirty_all, uint32_t dirty_stride) {
+                 const uint8_t *__restrict__ dirty_all, uint32_t dirty_stride, double clear_z, uint32_t clear_c,
+                 int clear_known) {
     const int lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * (blockDim.x >> 5), gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t my_rows = height > rank ? (uint32_t)((height - rank + nranks - 1) / nranks) : 0u;
@@ -225,9 +231,11 @@ k_peer_composite(const PeerSet P, int rank, int nranks, int root, int width, int
         // who has drawn into this strip
         const uint32_t drawn = __ballot_sync(0xffffffffu, lane < nranks && dirty_all[(size_t)lane * dirty_stride + strip] != 0);
         if (drawn == 0) continue;  // nobody: every rank keeps its own (cleared) pixels
+        if (root >= 0 && drawn == (1u << root)) continue;  // only the presenting rank: it already holds the result
         const uint32_t all = nranks >= 32 ? 0xffffffffu : ((1u << nranks) - 1u);
-        const uint32_t cand = root >= 0 ? (drawn | (1u << root)) : all;
+        const uint32_t cand = root >= 0 ? drawn : all;
         const uint32_t targets = root >= 0 ? (1u << root) : all;
+        const bool root_undrawn = root >= 0 && !((drawn >> root) & 1u);
         const int x0 = col * tile_w;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -251,6 +259,7 @@ k_peer_composite(const PeerSet P, int rank, int nranks, int root, int width, int
                 if (((targets >> r) & 1u) && r != win) need = true;
             if (!need) continue;
             const uint32_t c = __ldcv(P.color[win] + i);
+            if (root_undrawn && clear_known && best == clear_z && c == clear_c) continue;  // root's own cleared pixel is identical
 #pragma unroll
             for (int r = 0; r < FGL_MAX_PEERS; r++)
                 if (((targets >> r) & 1u) && r != win) {
@@ -561,7 +570,8 @@ int fgl_peer_composite_phase(fgl_ctx *c, fgl_peer_group *g, int root, int phase)
         }
         const int tiles_x = (c->w + c->tile_w - 1) / c->tile_w;
         fgl::k_peer_composite<<<c->wb.nsm * 8u, 256, 0, st>>>(g->set, g->rank, g->nranks, root, c->w, c->h, c->tile_w, tiles_x,
-                                                            g->dirty_all, g->dirty_stride);
+                                                            g->dirty_all, g->dirty_stride, c->clear_depth_value, c->clear_color_value,
+                                                            c->clear_color_known ? 1 : 0);
         if (tm) cudaEventRecord(tm->ev[2], st);
         fgl::k_peer_signal<<<1, 32, 0, st>>>(g->set, g->rank, g->nranks, fgl::FLAG_DONE, epoch);
     }

@@ -72,11 +72,15 @@ struct fgl_ctx {
     DrawCounters *host_counters;       // pinned
     DrawCounters *acc_dev;             // async accumulation (total/updated/overflow)
     bool async_pending;
+    bool capturing;                    // between fgl_graph_begin and fgl_graph_end: the stream records instead of running
     bool counters_clean;               // the last draw's k_shade zeroed the device-side draw counters
     unsigned long long *prim_info;     // per-primitive RasterizeInfo of fgl_draw_*_each, [prim_info_cap][2]
     uint64_t prim_info_cap;
     unsigned long long *scratch;       // 8 words: reductions of fgl_mesh_bounds / fgl_depth_image
     uint16_t *gray16;                  // DepthImage staging, allocated on first use
+    double clear_depth_value;          // what the last fgl_clear_depth wrote (NaN once the buffer was uploaded by the caller)
+    uint32_t clear_color_value;        // what the last fgl_clear_color wrote ...
+    bool clear_color_known;            // ... if nothing but draws has touched the colour buffer since
     unsigned long long *peer_flags;    // fgl_comm.cu: ready / done epochs written by the peers of a peer group (device)
     unsigned long long peer_epoch;     // last composite epoch this context took part in
     fgl_draw_stats stats;
@@ -86,6 +90,15 @@ struct fgl_ctx {
     int prof_used;          // slots recorded since the last drain
     bool prof_created;
     fgl_stage_times prof_acc;
+};
+
+struct fgl_graph {
+    int device;
+    fgl_ctx *ctx;
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    bool has_draws;        // launching it leaves RasterizeInfo to collect (fgl_sync / fgl_frame_end)
+    bool counters_clean;   // state of the draw counters after the recorded frame
 };
 
 namespace fgl {

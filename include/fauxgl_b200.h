@@ -246,6 +246,21 @@ int fgl_fence_wait(fgl_ctx *ctx, fgl_fence *fence, fgl_raster_info *info);
 int fgl_fence_destroy(fgl_fence *fence);
 int fgl_get_draw_stats(const fgl_ctx *ctx, fgl_draw_stats *out);
 
+/* Recorded frames.  A frame of an animation loop (examples/animate.go:43-67) issues the same calls every time --
+ * clears, DrawMesh, resolve -- and each costs ten-odd kernel launches from the host.  Between fgl_graph_begin and
+ * fgl_graph_end the context RECORDS the calls that only enqueue work (fgl_clear_color / fgl_clear_depth,
+ * fgl_draw_*_async, fgl_mesh_transform, fgl_resolve_device, the composites) into a CUDA graph instead of running
+ * them; fgl_graph_launch replays the whole frame with one call, after which fgl_sync / fgl_frame_end / the
+ * read-backs work as after the calls themselves (same kernels, same order: identical results).  The shader, the
+ * render state and the primitive range are part of the recording.  Calls that wait (synchronous draws,
+ * read-backs, fgl_sync) are errors while recording; the work buffers must already be large enough (draw the mesh
+ * once synchronously first).  A graph belongs to its context. */
+typedef struct fgl_graph fgl_graph;
+int fgl_graph_begin(fgl_ctx *ctx);
+int fgl_graph_end(fgl_ctx *ctx, fgl_graph **out);
+int fgl_graph_launch(fgl_ctx *ctx, fgl_graph *graph);
+int fgl_graph_destroy(fgl_graph *graph);
+
 /* Per-stage device timing (CUDA events on the context's stream).  While enabled,
  * every draw records events between its stages; fgl_get_stage_times waits for
  * the stream and returns the milliseconds accumulated since the last call and

@@ -442,3 +442,75 @@ def test_heavy_strips_per_primitive_info(kind, oracle_lib, Context):
     assert (ctx.Image() == o.ColorBuffer).all()
     assert (ctx.DepthBuffer.view(np.uint64) == o.DepthBuffer.view(np.uint64)).all()
     ctx.Close()
+
+
+@pytest.mark.parametrize("scene_name,resolve", [("bumpy_small", 2), ("shapes_multipass", 0), ("lines", 0)])
+def test_recorded_frame_replays_identically(scene_name, resolve, oracle_lib, Context):
+    """fgl_graph_*: a frame recorded into a CUDA graph (clears, async draws -- fused and split front ends, deferred and
+    inline shading, lines --, the resolve) and replayed gives the buffers, the RasterizeInfo and the resolved image of
+    the calls themselves, replay after replay, also when other work ran on the context in between."""
+    sc = scenes.SCENES[scene_name]()
+
+    class Recorder:
+        """Runs the scene script with DrawMesh / DrawTriangles / DrawLines turned into their async forms."""
+        def __init__(self, c):
+            self.__dict__["c"] = c
+
+        def __getattr__(self, k):
+            return getattr(self.c, k)
+
+        def __setattr__(self, k, v):
+            setattr(self.c, k, v)
+
+        def DrawMesh(self, m):
+            self.c.DrawMeshAsync(m)
+            return (0, 0)
+
+        def DrawTriangles(self, m, first=0, count=None):
+            self.c.DrawMeshAsync(self.c.device_mesh(m), first, self.c.device_mesh(m).num_triangles - first if count is None else count)
+            return (0, 0)
+
+        def DrawLines(self, m, first=0, count=None):
+            dm = self.c.device_mesh(m)
+            st, sh = self.c._state(), self.c._shader()
+            from fauxgl_b200.context import _check, capi
+            n = dm.num_lines - first if count is None else count
+            _check(capi().fgl_draw_lines_async(self.c._h, C.byref(st), C.byref(sh), dm.handle, first, n), self.c._h)
+            return (0, 0)
+    ref = Context(sc.width, sc.height)
+    rinfo = sc.run(ref)
+    want_c, want_d = ref.Image(), ref.DepthBuffer
+    want_r = ref.Resolve(resolve) if resolve else None
+    ctx = Context(sc.width, sc.height)
+    sc.run(ctx)                                  # a first, direct frame: uploads the meshes, sizes the work buffers
+    ctx2 = ctx                                   # the script mutates Wireframe / DepthBias / Cull ...: back to NewContext's state
+    ctx2.ReadDepth = ctx2.WriteDepth = ctx2.WriteColor = ctx2.AlphaBlend = True
+    ctx2.Wireframe, ctx2.FrontFace, ctx2.Cull, ctx2.LineWidth, ctx2.DepthBias = False, 2, 3, 2.0, 0.0
+    ctx2.ClearDepthBuffer()
+    ctx2.GraphBegin()
+    ctx2.ClearDepthBuffer()
+    sc.run(Recorder(ctx2))
+    if resolve:
+        ctx2.ResolveDevice(resolve)
+    graph = ctx2.GraphEnd()
+    total = sum(i[0] for i in rinfo), sum(i[1] for i in rinfo)
+    for rep in range(3):
+        graph.launch()
+        info = ctx2.Sync()
+        assert tuple(info) == total, (rep, info, total)
+        assert (ctx2.Image() == want_c).all() and (ctx2.DepthBuffer.view(np.uint64) == want_d.view(np.uint64)).all(), rep
+        if resolve:
+            out = np.empty_like(want_r)
+            from fauxgl_b200.context import _check, capi
+            _check(capi().fgl_read_resolved(ctx2._h, out.ctypes.data), ctx2._h)
+            assert (out == want_r).all()
+        if rep == 0:                              # unrelated direct work between two replays
+            ctx2.ClearColorBufferWith(scenes.HexColor("#123456"))
+            ctx2.ClearDepthBufferWith(0.25)
+    # what cannot be recorded says so
+    ctx2.GraphBegin()
+    with pytest.raises(Exception):
+        ctx2.Image()
+    ctx2.GraphEnd()
+    graph.Close()
+    ctx.Close(); ref.Close()
