@@ -26,6 +26,7 @@ from .shader import (SHADER_PHONG, SHADER_SOLID, SHADER_TEXTURE, ImageTexture, P
                      SolidColorShader, TextureShader)
 
 COMM_ID_BYTES, PEER_EXPORT_BYTES = 128, 512   # FGL_COMM_ID_BYTES, FGL_PEER_EXPORT_BYTES
+COMPOSITE_COLOR_ONLY = 1                       # FGL_COMPOSITE_COLOR_ONLY
 FaceCW, FaceCCW = 1, 2
 CullNone, CullFront, CullBack = 1, 2, 3
 
@@ -162,8 +163,8 @@ ABI = [
     ("fgl_peer_export", C.c_int, [_P, _P]),
     ("fgl_peer_group_create", C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(_P)]),
     ("fgl_peer_group_destroy", C.c_int, [_P]),
-    ("fgl_peer_composite", C.c_int, [_P, _P, C.c_int]),
-    ("fgl_peer_composite_phase", C.c_int, [_P, _P, C.c_int, C.c_int]),
+    ("fgl_peer_composite", C.c_int, [_P, _P, C.c_int, C.c_int]),
+    ("fgl_peer_composite_phase", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
     ("fgl_peer_status", C.c_int, [_P, _P]),
     ("fgl_debug_tile_cycles", C.c_int, [_P, _P, C.c_uint64]),
     ("fgl_probe_atomic_rate", C.c_int, [_P, C.c_uint64, C.POINTER(C.c_double)]),

@@ -219,7 +219,7 @@ __global__ void k_peer_gather_dirty(const PeerSet P, int nranks, uint32_t ntiles
 __global__ void __launch_bounds__(256)
 k_peer_composite(const PeerSet P, int rank, int nranks, int root, int width, int height, int tile_w, int tiles_x,
                  const uint8_t *__restrict__ dirty_all, uint32_t dirty_stride, double clear_z, uint32_t clear_c,
-                 int clear_known) {
+                 int clear_known, int color_only) {
     const int lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * (blockDim.x >> 5), gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t my_rows = height > rank ? (uint32_t)((height - rank + nranks - 1) / nranks) : 0u;
@@ -263,12 +263,12 @@ k_peer_composite(const PeerSet P, int rank, int nranks, int root, int width, int
 #pragma unroll
             for (int r = 0; r < FGL_MAX_PEERS; r++)
                 if (((targets >> r) & 1u) && r != win) {
-                    if (!((cand >> r) & 1u) || d[r] != best) P.depth[r][i] = best;
+                    if (!color_only && (!((cand >> r) & 1u) || d[r] != best)) P.depth[r][i] = best;
                     P.color[r][i] = c;
                 }
         }
         // the targets' buffers now hold drawn depth in this strip
-        if (lane < nranks && ((targets >> lane) & 1u) && !((drawn >> lane) & 1u)) P.dirty[lane][strip] = 1;
+        if (!color_only && lane < nranks && ((targets >> lane) & 1u) && !((drawn >> lane) & 1u)) P.dirty[lane][strip] = 1;
     }
 }
 
@@ -540,7 +540,7 @@ int fgl_peer_group_destroy(fgl_peer_group *g) {
 
 // phase 0: everything (ranks on different devices); 1: signal "drawn"; 2: wait for all, composite, signal "done";
 // 3: wait for all "done".
-int fgl_peer_composite_phase(fgl_ctx *c, fgl_peer_group *g, int root, int phase) {
+int fgl_peer_composite_phase(fgl_ctx *c, fgl_peer_group *g, int root, int flags, int phase) {
     int rc = api_check_ctx(c);
     if (rc) return rc;
     if (!g || g->ctx != c) return api_fail(c, FGL_E_INVALID, "peer group belongs to another context");
@@ -571,7 +571,7 @@ int fgl_peer_composite_phase(fgl_ctx *c, fgl_peer_group *g, int root, int phase)
         const int tiles_x = (c->w + c->tile_w - 1) / c->tile_w;
         fgl::k_peer_composite<<<c->wb.nsm * 8u, 256, 0, st>>>(g->set, g->rank, g->nranks, root, c->w, c->h, c->tile_w, tiles_x,
                                                             g->dirty_all, g->dirty_stride, c->clear_depth_value, c->clear_color_value,
-                                                            c->clear_color_known ? 1 : 0);
+                                                            c->clear_color_known ? 1 : 0, (flags & FGL_COMPOSITE_COLOR_ONLY) ? 1 : 0);
         if (tm) cudaEventRecord(tm->ev[2], st);
         fgl::k_peer_signal<<<1, 32, 0, st>>>(g->set, g->rank, g->nranks, fgl::FLAG_DONE, epoch);
     }
@@ -586,7 +586,7 @@ int fgl_peer_composite_phase(fgl_ctx *c, fgl_peer_group *g, int root, int phase)
     return FGL_OK;
 }
 
-int fgl_peer_composite(fgl_ctx *c, fgl_peer_group *g, int root) { return fgl_peer_composite_phase(c, g, root, 0); }
+int fgl_peer_composite(fgl_ctx *c, fgl_peer_group *g, int root, int flags) { return fgl_peer_composite_phase(c, g, root, flags, 0); }
 
 int fgl_peer_stage_times(fgl_ctx *c, fgl_peer_group *g, float ms[4], uint32_t *composites) {
     int rc = api_check_ctx(c);

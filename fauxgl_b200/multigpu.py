@@ -166,20 +166,21 @@ class PeerGroup:
         records = [c.PeerExport() for c in ctxs]
         return [cls(c, r, len(ctxs), records=records) for r, c in enumerate(ctxs)]
 
-    def composite(self, root: int = -1):
+    def composite(self, root: int = -1, color_only: bool = False):
         """Enqueue signal -> wait -> sparse composite -> signal -> wait on the context's stream (no host sync).
-        Afterwards rank `root` (every rank if root < 0) holds the frame."""
+        Afterwards rank `root` (every rank if root < 0) holds the frame; with ``color_only`` only its colours
+        (FGL_COMPOSITE_COLOR_ONLY: enough to present the frame, a third of the bytes)."""
         from .context import _check, capi
-        _check(capi().fgl_peer_composite(self.ctx._h, self.handle, int(root)), self.ctx._h)
+        _check(capi().fgl_peer_composite(self.ctx._h, self.handle, int(root), 1 if color_only else 0), self.ctx._h)
 
     @staticmethod
-    def composite_local(groups, root: int = -1):
+    def composite_local(groups, root: int = -1, color_only: bool = False):
         """Composite for ranks that are contexts of THIS process, submitted by this one thread: phase by phase over all
         ranks (fgl_peer_composite_phase), so that no waiting kernel is ever submitted ahead of the signal it waits for."""
         from .context import _check, capi
         for phase in (1, 2, 3):
             for g in groups:
-                _check(capi().fgl_peer_composite_phase(g.ctx._h, g.handle, int(root), phase), g.ctx._h)
+                _check(capi().fgl_peer_composite_phase(g.ctx._h, g.handle, int(root), 1 if color_only else 0, phase), g.ctx._h)
 
     def stage_times(self):
         """{wait_all_drawn_ms, composite_ms, wait_all_done_ms} per composite issued while profiling was on."""

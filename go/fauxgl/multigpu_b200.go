@@ -79,11 +79,20 @@ func (dc *Context) NewPeerGroup(rank int, records [][]byte) (*PeerGroup, error) 
 // Composite enqueues signal -> wait -> sparse composite -> signal -> wait on the
 // context's stream and returns at once.  Afterwards rank root holds the frame
 // (every rank if root < 0).  Collective: every rank calls it once per frame.
-func (g *PeerGroup) Composite(root int) error {
+func (g *PeerGroup) Composite(root int) error { return g.composite(root, 0) }
+
+// CompositeColors is Composite for a rank that only PRESENTS the frame: it receives
+// the winning colours but not the depths (FGL_COMPOSITE_COLOR_ONLY), a third of the
+// bytes; its depth buffer stays as it drew it.
+func (g *PeerGroup) CompositeColors(root int) error {
+	return g.composite(root, C.FGL_COMPOSITE_COLOR_ONLY)
+}
+
+func (g *PeerGroup) composite(root int, flags C.int) error {
 	g.dc.mu.Lock()
 	defer g.dc.mu.Unlock()
 	g.dc.hostOK = false
-	return lastError(g.dc.dev.h, C.fgl_peer_composite(g.dc.dev.h, g.h, C.int(root)))
+	return lastError(g.dc.dev.h, C.fgl_peer_composite(g.dc.dev.h, g.h, C.int(root), flags))
 }
 
 // Status waits for the stream and reports a rank that never arrived.

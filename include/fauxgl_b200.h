@@ -360,7 +360,7 @@ int fgl_comm_stage_times(fgl_ctx *ctx, fgl_comm *comm, float ms[4], uint32_t *co
  * fgl_peer_export fills a record of FGL_PEER_EXPORT_BYTES for this context (CUDA IPC handles of its colour, depth,
  * dirty-strip and flag buffers); the host gathers the records of all ranks, in rank order, and passes them to
  * fgl_peer_group_create on every rank.  Ranks may be processes (one per GPU) or contexts of one process (one host
- * thread per GPU).  fgl_peer_composite(ctx, group, root): rank r composites the scanlines y = r (mod nranks) with ONE
+ * thread per GPU).  fgl_peer_composite(ctx, group, root, flags): rank r composites the scanlines y = r (mod nranks) with ONE
  * kernel of P2P loads and stores over NVLink and leaves the result in root's buffers (root >= 0) or in every rank's
  * (root < 0).  fgl_peer_status waits for the stream and reports a rank that never arrived (10 s) as FGL_E_CUDA. */
 #define FGL_PEER_EXPORT_BYTES 512
@@ -368,13 +368,17 @@ typedef struct fgl_peer_group fgl_peer_group;
 int fgl_peer_export(fgl_ctx *ctx, void *record);
 int fgl_peer_group_create(fgl_ctx *ctx, int rank, int nranks, const void *records, fgl_peer_group **out);
 int fgl_peer_group_destroy(fgl_peer_group *group);
-int fgl_peer_composite(fgl_ctx *ctx, fgl_peer_group *group, int root);
+/* flags: FGL_COMPOSITE_COLOR_ONLY -- the target(s) receive the winning colours but not the depths: enough to PRESENT the
+ * frame (a third of the bytes into the presenting rank, whose NVLink ingress is what bounds the composite at 8 ranks),
+ * not to keep drawing into it (its depth buffer stays as the rank drew it). */
+#define FGL_COMPOSITE_COLOR_ONLY 1
+int fgl_peer_composite(fgl_ctx *ctx, fgl_peer_group *group, int root, int flags);
 /* The same in three steps, for ranks that share a DEVICE (several contexts of one process on one GPU, as in the
  * single-GPU tests): a kernel that waits for a flag can occupy the hardware queue the kernel that sets the flag is
  * submitted to, so the host has to submit phase 1 ("I have drawn") on every rank, then phase 2 (wait for all,
  * composite, "I am done") on every rank, then phase 3 (wait for all) on every rank.  Ranks on different GPUs --
  * processes or threads -- call fgl_peer_composite (= phase 0: all three at once). */
-int fgl_peer_composite_phase(fgl_ctx *ctx, fgl_peer_group *group, int root, int phase);
+int fgl_peer_composite_phase(fgl_ctx *ctx, fgl_peer_group *group, int root, int flags, int phase);
 int fgl_peer_status(fgl_ctx *ctx, fgl_peer_group *group);
 /* As fgl_comm_stage_times: ms[0] signal + wait until every rank has drawn (load imbalance shows up here), ms[1]
  * bitmap gather + the composite kernel, ms[2] signal + wait until every rank has finished, ms[3] unused (0). */

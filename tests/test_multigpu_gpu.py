@@ -283,6 +283,15 @@ def test_peer_group_in_process_is_exact(world, root, gpu_capi):
         for r in holders:
             assert (ctxs[r].Image() == want_c).all(), (world, root, r)
             assert (ctxs[r].DepthBuffer.view(np.uint64) == want_d.view(np.uint64)).all(), (world, root, r)
+    # colours only (FGL_COMPOSITE_COLOR_ONLY): the holders get the frame's colours, their depth stays as they drew it
+    _render_ranges(sc, mesh, ctxs, ranges)
+    own_depth = [c.DepthBuffer for c in ctxs]
+    multigpu.PeerGroup.composite_local(groups, root, color_only=True)
+    for g in groups:
+        g.status()
+    for r in (range(world) if root < 0 else [root]):
+        assert (ctxs[r].Image() == want_c).all(), (world, root, r)
+        assert (ctxs[r].DepthBuffer.view(np.uint64) == own_depth[r].view(np.uint64)).all()
     for g in groups:
         g.close()
     for c in ctxs + [full]:
