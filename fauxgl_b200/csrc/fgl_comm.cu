@@ -237,34 +237,56 @@ k_peer_composite(const PeerSet P, int rank, int nranks, int root, int width, int
         const uint32_t targets = root >= 0 ? (1u << root) : all;
         const bool root_undrawn = root >= 0 && !((drawn >> root) & 1u);
         const int x0 = col * tile_w;
+        // Both pixels of the lane at once, and every load issued before its first use: a strip costs two dependent
+        // round trips over NVLink (depths, then the winner's colour) -- one when a single rank drew it, because the
+        // winner is then known without comparing.
+        size_t idx[2];
+        bool live[2];
+        double d[2][FGL_MAX_PEERS];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            if (h >= ppl) break;
             const int x = x0 + lane + 32 * h;
-            if (x >= width) continue;
-            const size_t i = (size_t)y * width + x;
-            double d[FGL_MAX_PEERS];
+            live[h] = h < ppl && x < width;
+            idx[h] = (size_t)y * width + (live[h] ? x : x0);
+        }
+        const bool single = (cand & (cand - 1u)) == 0u;
+        const int only = __ffs(cand) - 1;
+        uint32_t cpre[2] = {0u, 0u};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (!live[h]) continue;
 #pragma unroll
             for (int r = 0; r < FGL_MAX_PEERS; r++)
-                if ((cand >> r) & 1u) d[r] = __ldcv(P.depth[r] + i);
-            double best = 0;
-            int win = -1;
+                if ((cand >> r) & 1u) d[h][r] = __ldcv(P.depth[r] + idx[h]);
+            if (single) cpre[h] = __ldcv(P.color[only] + idx[h]);
+        }
+        double best[2] = {0, 0};
+        int win[2] = {-1, -1};
+        bool need[2] = {false, false};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (!live[h]) continue;
 #pragma unroll
             for (int r = 0; r < FGL_MAX_PEERS; r++)
-                if (((cand >> r) & 1u) && (win < 0 || d[r] <= best)) { best = d[r]; win = r; }
+                if (((cand >> r) & 1u) && (win[h] < 0 || d[h][r] <= best[h])) { best[h] = d[h][r]; win[h] = r; }
             // (a target that is the winner, or that ties with a LOWER-ranked winner, already holds the result)
-            bool need = false;
 #pragma unroll
             for (int r = 0; r < FGL_MAX_PEERS; r++)
-                if (((targets >> r) & 1u) && r != win) need = true;
-            if (!need) continue;
-            const uint32_t c = __ldcv(P.color[win] + i);
-            if (root_undrawn && clear_known && best == clear_z && c == clear_c) continue;  // root's own cleared pixel is identical
+                if (((targets >> r) & 1u) && r != win[h]) need[h] = true;
+        }
+        uint32_t cwin[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) cwin[h] = (need[h] && !single) ? __ldcv(P.color[win[h]] + idx[h]) : cpre[h];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (!need[h]) continue;
+            const uint32_t c = cwin[h];
+            if (root_undrawn && clear_known && best[h] == clear_z && c == clear_c) continue;  // root's own cleared pixel is identical
 #pragma unroll
             for (int r = 0; r < FGL_MAX_PEERS; r++)
-                if (((targets >> r) & 1u) && r != win) {
-                    if (!color_only && (!((cand >> r) & 1u) || d[r] != best)) P.depth[r][i] = best;
-                    P.color[r][i] = c;
+                if (((targets >> r) & 1u) && r != win[h]) {
+                    if (!color_only && (!((cand >> r) & 1u) || d[h][r] != best[h])) P.depth[r][idx[h]] = best[h];
+                    P.color[r][idx[h]] = c;
                 }
         }
         // the targets' buffers now hold drawn depth in this strip

@@ -1,0 +1,113 @@
+"""Randomised parity: small random scenes -- triangles and lines partly outside the view volume (clipping on every
+plane), random vertex colours with alpha, random render state (cull / front face / wireframe / line width / depth
+bias / blend / read-write flags), every shader kind with 8-bit, premultiplying and 16-bit textures, ragged
+framebuffer sizes, several draws on top of each other -- rendered by the oracle and by the device, compared bit for
+bit (float64 depth, NRGBA8 colour, RasterizeInfo).  Seeds are fixed: a failure names its seed."""
+import numpy as np
+import pytest
+
+from fauxgl_b200 import (Color, LookAt, Mesh, NewImageTexture, NewLineMesh, NewPhongShader, NewSolidColorShader,
+                         NewTextureShader, NewTriangleMesh, Orthographic, V)
+from fauxgl_b200.shader import TEX_NRGBA, TEX_RGBA, TEX_RGBA64
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_texture(rng):
+    h, w = int(rng.randint(2, 40)), int(rng.randint(2, 40))
+    kind = rng.randint(3)
+    if kind == 2:
+        px = rng.randint(0, 65536, (h, w, 4)).astype(np.uint16)
+        px[..., :3] = np.minimum(px[..., :3], px[..., 3:4])       # premultiplied, as Color.RGBA() returns
+        return NewImageTexture(px, TEX_RGBA64)
+    px = rng.randint(0, 256, (h, w, 4)).astype(np.uint8)
+    if kind == 0:
+        px[..., 3] = 255
+    return NewImageTexture(px, TEX_RGBA if kind == 0 else TEX_NRGBA)
+
+
+def _random_mesh(rng, ntri, nline):
+    spread = rng.choice([0.6, 1.2, 2.5])                         # 2.5: most primitives cross the view volume
+    centres = (rng.rand(ntri, 1, 3) * 2 - 1) * spread
+    size = rng.choice([0.02, 0.2, 1.0])
+    pos = centres + (rng.rand(ntri, 3, 3) * 2 - 1) * size
+    nrm = rng.rand(ntri, 3, 3) * 2 - 1
+    nrm[rng.rand(ntri) < 0.2] = 0.0                              # zero normals (FixNormals in the clipper)
+    tex = rng.rand(ntri, 3, 3) * rng.choice([1.0, 3.0]) - rng.choice([0.0, 1.0])
+    mesh = NewTriangleMesh(pos, normal=nrm, texture=tex) if ntri else Mesh()
+    if ntri:
+        mesh.color[:, :, :3] = rng.rand(ntri, 3, 3)
+        mesh.color[:, :, 3] = np.where(rng.rand(ntri, 3) < 0.5, 1.0, rng.rand(ntri, 3))
+    if nline:
+        lp = (rng.rand(nline, 2, 3) * 2 - 1) * spread * 1.5
+        lines = NewLineMesh(lp)
+        lines.lcolor[:, :, :3] = rng.rand(nline, 2, 3)
+        lines.lcolor[:, :, 3] = np.where(rng.rand(nline, 2) < 0.5, 1.0, rng.rand(nline, 2))
+        lines.ltexture[:, :, :2] = rng.rand(nline, 2, 2)
+        mesh.Add(lines)
+    return mesh
+
+
+def _script(seed):
+    rng = np.random.RandomState(seed)
+    W, H = int(rng.randint(3, 300)), int(rng.randint(3, 200))
+    if rng.rand() < 0.5:
+        eye = V(*(rng.rand(3) * 4 - 2 + np.array([0, 0, 3.0])))
+        matrix = LookAt(eye, V(0, 0, 0), V(0, 1, 0)).Perspective(float(rng.uniform(20, 90)), W / H, float(rng.uniform(0.3, 2)), 20)
+    else:
+        eye = V(0, 0, 5)
+        matrix = Orthographic(-1, 1, -1, 1, -2, 2)
+    draws = []
+    for _ in range(int(rng.randint(1, 4))):
+        mesh = _random_mesh(rng, int(rng.choice([0, 5, 60, 300])), int(rng.choice([0, 0, 8, 40])))
+        kind = rng.randint(4)
+        tex = _random_texture(rng)
+        if kind == 0:
+            shader = NewSolidColorShader(matrix, Color(*rng.rand(3), float(rng.choice([1.0, 0.5, 0.0]))))
+        elif kind == 1:
+            shader = NewTextureShader(matrix, tex)
+        else:
+            shader = NewPhongShader(matrix, V(*(rng.rand(3) * 2 - 1)), eye)
+            mode = rng.randint(3)
+            if mode == 0:
+                shader.ObjectColor = Color(*rng.rand(3), float(rng.choice([1.0, 0.65])))
+            elif mode == 1:
+                shader.Texture = tex
+            shader.SpecularPower = float(rng.choice([0, 1, 7, 32]))
+        state = {"ReadDepth": rng.rand() < 0.85, "WriteDepth": rng.rand() < 0.85, "WriteColor": rng.rand() < 0.9,
+                 "AlphaBlend": rng.rand() < 0.7, "Wireframe": rng.rand() < 0.25, "FrontFace": int(rng.choice([1, 2])),
+                 "Cull": int(rng.choice([1, 2, 3])), "LineWidth": float(rng.choice([0.5, 1.0, 2.0, 5.5])),
+                 "DepthBias": float(rng.choice([0.0, 0.0, -1e-4, 1e-3]))}
+        draws.append((mesh, shader, state))
+    clear = Color(*rng.rand(4)) if rng.rand() < 0.7 else None
+    return W, H, clear, draws
+
+
+def _run(ctx, clear, draws):
+    infos = []
+    if clear is not None:
+        ctx.ClearColorBufferWith(clear)
+    for mesh, shader, state in draws:
+        ctx.Shader = shader
+        for k, v in state.items():
+            setattr(ctx, k, v)
+        infos.append(tuple(ctx.DrawMesh(mesh)))
+    return infos
+
+
+@pytest.mark.parametrize("front", ["fused", "split"])
+@pytest.mark.parametrize("block", range(6))
+def test_random_scenes_match_oracle(block, front, oracle_lib, gpu_capi, monkeypatch):
+    from fauxgl_b200.context import Context
+    monkeypatch.setenv("FGL_FRONT", front)
+    for seed in range(block * 8, block * 8 + 8):
+        W, H, clear, draws = _script(seed)
+        octx = oracle_lib.OracleContext(W, H)
+        oinfo = _run(octx, clear, draws)
+        gctx = Context(W, H)
+        ginfo = _run(gctx, clear, draws)
+        gd, gc = gctx.DepthBuffer, gctx.Image()
+        dm = int((gd.view(np.uint64) != octx.DepthBuffer.view(np.uint64)).sum())
+        cm = int((gc != octx.ColorBuffer).any(axis=-1).sum())
+        gctx.Close()
+        assert ginfo == oinfo and dm == 0 and cm == 0, (seed, front, W, H, ginfo, oinfo, dm, cm)
