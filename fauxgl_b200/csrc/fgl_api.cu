@@ -1500,7 +1500,7 @@ int fgl_probe_atomic_rate(fgl_ctx *c, uint64_t ops, double *ops_per_second) {
     if (e1) cudaEventDestroy(e1);
     dev_free(buf);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(c, FGL_E_CUDA, "atomic probe: %s", cudaGetErrorString(e)); }
-    const unsigned long long threads = 148ull * 8ull * 256ull;
+    const unsigned long long threads = (unsigned long long)GRID_WAVE * 256ull;
     const unsigned long long done = (ops + threads - 1) / threads * threads;
     *ops_per_second = ms > 0 ? (double)done / ((double)ms * 1e-3) : 0.0;
     return FGL_OK;

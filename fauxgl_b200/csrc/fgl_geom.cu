@@ -59,7 +59,7 @@ __global__ void k_mesh_transform(double *__restrict__ pos, double *__restrict__ 
 
 static int grid_for(size_t total, int threads) {
     size_t b = (total + threads - 1) / threads;
-    size_t cap = 148 * 16;
+    size_t cap = GRID_WAVE * 2;
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 int launch_mesh_ingest(const double *aos, double *planes, uint32_t n, int nverts, int ncomp_in, int ncomp_out,
@@ -112,15 +112,35 @@ FGL_DI uint32_t box_cols(const DrawParams &p, int32_t x0, int32_t x1) {
 }
 
 // Integer bounding box of a screen triangle, context.go:155-160, and its on-screen scanlines.
-struct BBox { int32_t x0, x1, y0, y1; bool visible; uint32_t rows, cols; };  // cols: strips a row can touch
+struct BBox { int32_t x0, x1, y0, y1; bool visible; uint32_t rows, cols; bool origin; };  // cols: strips a row can touch
 FGL_DI BBox compute_bbox(const DrawParams &p, V3 s0, V3 s1, V3 s2) {
     BBox b;
     const double mnx = go_min(s0.x, go_min(s1.x, s2.x)), mny = go_min(s0.y, go_min(s1.y, s2.y));
     const double mxx = go_max(s0.x, go_max(s1.x, s2.x)), mxy = go_max(s0.y, go_max(s1.y, s2.y));
-    b.x0 = sat_i32(go_int(floor(mnx)));
-    b.x1 = sat_i32(go_int(ceil(mxx)));
-    b.y0 = sat_i32(go_int(floor(mny)));
-    b.y1 = sat_i32(go_int(ceil(mxy)));
+    const long long ix0 = go_int(floor(mnx)), ix1 = go_int(ceil(mxx)), iy0 = go_int(floor(mny)), iy1 = go_int(ceil(mxy));
+    b.x0 = sat_i32(ix0);
+    b.x1 = sat_i32(ix1);
+    b.y0 = sat_i32(iy0);
+    b.y1 = sat_i32(iy1);
+    b.origin = false;
+    {
+        // All four bounds the "integer indefinite" value int(NaN) = -2^63: every screen coordinate is NaN -- what a
+        // degenerate triangle (two equal vertices) becomes in ClipTriangle, whose Barycentric divides 0 by 0; the cull
+        // test `a <= 0` is false for NaN, so it is drawn under every Cull mode.  The reference's loops then visit
+        // exactly one "pixel", (x, y) = (-2^63, -2^63), and Go's wrapping arithmetic gives it the index
+        // -2^63 * W - 2^63 = 0 when W is odd (-2^63, skipped, when W is even): pixel (0, 0) is counted in TotalPixels
+        // and, with ReadDepth off, gets a NaN depth.  Reproduced as a one-pixel box at the origin whose edge values
+        // are set up at (-2^63 + .5, -2^63 + .5) and whose segment is marked as aliased (its own x is off screen).
+        const long long IND = (long long)0x8000000000000000ull;
+        if (ix0 == IND && ix1 == IND && iy0 == IND && iy1 == IND) {
+            b.x0 = b.x1 = b.y0 = b.y1 = 0;
+            b.visible = (p.width & 1) && !p.state.x_guard;
+            b.origin = b.visible;
+            b.rows = b.visible ? 1u : 0u;
+            b.cols = b.rows;
+            return b;
+        }
+    }
     // The forward-differencing chains are replayed from (x0, y0); a box that starts
     // millions of pixels off screen (infinite/overflowing coordinates -- the reference
     // itself would spin for 2^63 iterations on those) is dropped instead of walked.
@@ -160,7 +180,7 @@ FGL_DI void write_record(const WorkBuffers *wb, uint32_t r, uint32_t row_off, co
     rec.s[3] = s1.x; rec.s[4] = s1.y; rec.s[5] = s1.z;
     rec.s[6] = s2.x; rec.s[7] = s2.y; rec.s[8] = s2.z;
     // per-triangle setup of Context.rasterize, context.go:163-181
-    const V3 pc = v3((double)b.x0 + 0.5, (double)b.y0 + 0.5, 0);
+    const V3 pc = b.origin ? v3(-9223372036854775808.0, -9223372036854775808.0, 0) : v3((double)b.x0 + 0.5, (double)b.y0 + 0.5, 0);
     rec.w00 = edge_fn(s1, s2, pc);
     rec.w01 = edge_fn(s2, s0, pc);
     rec.w02 = edge_fn(s0, s1, pc);
@@ -168,7 +188,7 @@ FGL_DI void write_record(const WorkBuffers *wb, uint32_t r, uint32_t row_off, co
     rec.ra = 1 / edge_fn(s0, s1, s2);
     rec.r0 = 1 / w0; rec.r1 = 1 / w1; rec.r2 = 1 / w2;
     rec.ra12 = 1 / a12; rec.ra20 = 1 / a20; rec.ra01 = 1 / a01;
-    rec.src = src; rec.flags = flags;
+    rec.src = src; rec.flags = flags | (b.origin ? REC_WRAP : 0u);
     rec.x0 = b.x0; rec.x1 = b.x1; rec.y0 = b.y0; rec.y1 = b.y1;
     wb->recs[r] = rec;
     wb->rec_local_row[r] = row_off;
@@ -678,7 +698,7 @@ FGL_DI void fill_srec(SRec &r, const BBox &b, V3 s0, V3 s1, V3 s2, double w0, do
                       uint32_t flags) {
     r.s0x = s0.x; r.s0y = s0.y; r.s1x = s1.x; r.s1y = s1.y; r.s2x = s2.x; r.s2y = s2.y;
     r.z0 = s0.z; r.z1 = s1.z; r.z2 = s2.z;
-    const V3 pc = v3((double)b.x0 + 0.5, (double)b.y0 + 0.5, 0);
+    const V3 pc = b.origin ? v3(-9223372036854775808.0, -9223372036854775808.0, 0) : v3((double)b.x0 + 0.5, (double)b.y0 + 0.5, 0);
     r.w00 = edge_fn(s1, s2, pc);
     r.w01 = edge_fn(s2, s0, pc);
     r.w02 = edge_fn(s0, s1, pc);
@@ -687,7 +707,7 @@ FGL_DI void fill_srec(SRec &r, const BBox &b, V3 s0, V3 s1, V3 s2, double w0, do
     r.r0 = 1 / w0; r.r1 = 1 / w1; r.r2 = 1 / w2;
     r.ra12 = 1 / a12; r.ra20 = 1 / a20; r.ra01 = 1 / a01;
     r.x0 = b.x0; r.x1 = b.x1; r.y0 = b.y0; r.rows = b.rows;
-    r.src = src; r.flags = flags;
+    r.src = src; r.flags = flags | (b.origin ? REC_WRAP : 0u);
 }
 
 // Emits the records of one primitive whose block-local index falls into the window [win0, win1).
@@ -1177,7 +1197,7 @@ int launch_geometry(const DrawParams &p, const WorkBuffers &wb, bool counters_cl
     // counters + look-back state of this draw (stream-ordered before the kernel)
     if (!counters_clean) cudaMemsetAsync(wb.counters, 0, sizeof(DrawCounters), st);
     k_geometry<<<blocks, GT, 0, st>>>(p, wb);
-    k_rec_index<<<blocks < 148u * 8u ? blocks : 148u * 8u, GT, 0, st>>>(wb, blocks);
+    k_rec_index<<<blocks < GRID_WAVE ? blocks : GRID_WAVE, GT, 0, st>>>(wb, blocks);
     return 2;
 }
 

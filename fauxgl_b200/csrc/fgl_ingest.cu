@@ -74,7 +74,7 @@ k_stl_ingest(const uint8_t *__restrict__ rec, double *__restrict__ pos, double *
 int launch_stl_ingest(const uint8_t *records, double *pos, double *nrm, uint32_t n, cudaStream_t st) {
     if (n == 0) return 0;
     const uint32_t blocks = (n + STL_T - 1) / STL_T;
-    k_stl_ingest<<<blocks < 148u * 8u ? blocks : 148u * 8u, STL_T, 0, st>>>(records, pos, nrm, n);
+    k_stl_ingest<<<blocks < GRID_WAVE ? blocks : GRID_WAVE, STL_T, 0, st>>>(records, pos, nrm, n);
     return 1;
 }
 
@@ -105,7 +105,7 @@ __global__ void k_mesh_bounds(const double *__restrict__ pos, uint32_t n, int nv
 int launch_mesh_bounds(const double *pos, uint32_t n, int nverts, unsigned long long *bounds, cudaStream_t st) {
     if (n == 0) return 0;
     const uint32_t blocks = (n + 255) / 256;
-    k_mesh_bounds<<<blocks < 148u * 8u ? blocks : 148u * 8u, 256, 0, st>>>(pos, n, nverts, bounds);
+    k_mesh_bounds<<<blocks < GRID_WAVE ? blocks : GRID_WAVE, 256, 0, st>>>(pos, n, nverts, bounds);
     return 1;
 }
 
@@ -142,8 +142,8 @@ __global__ void k_depth_gray16(const double *__restrict__ depth, size_t npix, co
 int launch_depth_image(const double *depth, size_t npix, uint16_t *out, unsigned long long *scratch, cudaStream_t st) {
     static const unsigned long long init[2] = {~0ull, 0ull};
     cudaMemcpyAsync(scratch, init, sizeof init, cudaMemcpyHostToDevice, st);
-    k_depth_range<<<148 * 8, 256, 0, st>>>(depth, npix, scratch);
-    k_depth_gray16<<<148 * 8, 256, 0, st>>>(depth, npix, scratch, out);
+    k_depth_range<<<GRID_WAVE, 256, 0, st>>>(depth, npix, scratch);
+    k_depth_gray16<<<GRID_WAVE, 256, 0, st>>>(depth, npix, scratch, out);
     return 2;
 }
 
@@ -184,7 +184,7 @@ int launch_indexed_ingest(const double *v, const double *vt, const double *vn, c
                           double *nrm, double *tex, uint32_t n, cudaStream_t st) {
     if (n == 0) return 0;
     const uint32_t blocks = (n + 255) / 256;
-    k_indexed_ingest<<<blocks < 148u * 8u ? blocks : 148u * 8u, 256, 0, st>>>(v, vt, vn, corners, pos, nrm, tex, n);
+    k_indexed_ingest<<<blocks < GRID_WAVE ? blocks : GRID_WAVE, 256, 0, st>>>(v, vt, vn, corners, pos, nrm, tex, n);
     return 1;
 }
 
@@ -286,18 +286,18 @@ k_smooth_threshold(const uint32_t *__restrict__ keys, const uint32_t *__restrict
 int launch_smooth_threshold(const uint32_t *keys, const uint32_t *vals, const double *pos, const double *nrm_in,
                             double *nrm_out, uint32_t n, double threshold, cudaStream_t st) {
     if (n == 0) return 0;
-    k_smooth_threshold<<<148 * 8, 256, 0, st>>>(keys, vals, pos, nrm_in, nrm_out, n, threshold);
+    k_smooth_threshold<<<GRID_WAVE, 256, 0, st>>>(keys, vals, pos, nrm_in, nrm_out, n, threshold);
     return 1;
 }
 int launch_corner_hash(const double *pos, uint32_t n, uint32_t *keys, uint32_t *vals, cudaStream_t st) {
     if (n == 0) return 0;
-    k_corner_hash<<<148 * 8, 256, 0, st>>>(pos, n, keys, vals);
+    k_corner_hash<<<GRID_WAVE, 256, 0, st>>>(pos, n, keys, vals);
     return 1;
 }
 int launch_smooth_groups(const uint32_t *keys, const uint32_t *vals, const double *pos, double *nrm, uint32_t n,
                          cudaStream_t st) {
     if (n == 0) return 0;
-    k_smooth_groups<<<148 * 8, 256, 0, st>>>(keys, vals, pos, nrm, n);
+    k_smooth_groups<<<GRID_WAVE, 256, 0, st>>>(keys, vals, pos, nrm, n);
     return 1;
 }
 

@@ -9,6 +9,11 @@
 
 namespace fgl {
 
+// The library is written for B200 (sm_100a, 148 SMs): grid-stride kernels are launched with one wave of 8 CTAs per SM.
+// (Correct on any device -- the loops cover the data whatever the grid -- but sized for this one.)
+constexpr unsigned B200_SMS = 148u;
+constexpr unsigned GRID_WAVE = B200_SMS * 8u;
+
 // ---- screen strips ------------------------------------------------------------
 // The framebuffer is binned into strips of 64 x 1 pixels.  The reference walks each scanline
 // left to right with forward differencing (context.go:207-213); a covered run is cut into one

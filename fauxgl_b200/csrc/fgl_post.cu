@@ -20,11 +20,11 @@ __global__ void k_clear_depth(double2 *__restrict__ depth2, double *__restrict__
     if (blockIdx.x == 0 && threadIdx.x == 0 && (npix & 1)) depth[npix - 1] = value;
 }
 int launch_clear_color(uint32_t *color, size_t npix, uint32_t rgba, cudaStream_t st) {
-    k_clear_color<<<148 * 8, 256, 0, st>>>(reinterpret_cast<uint4 *>(color), color, npix, rgba);
+    k_clear_color<<<GRID_WAVE, 256, 0, st>>>(reinterpret_cast<uint4 *>(color), color, npix, rgba);
     return 1;
 }
 int launch_clear_depth(double *depth, size_t npix, double v, cudaStream_t st) {
-    k_clear_depth<<<148 * 8, 256, 0, st>>>(reinterpret_cast<double2 *>(depth), depth, npix, v);
+    k_clear_depth<<<GRID_WAVE, 256, 0, st>>>(reinterpret_cast<double2 *>(depth), depth, npix, v);
     return 1;
 }
 
@@ -204,12 +204,12 @@ __global__ void k_composite_min(long long *__restrict__ inout, const long long *
 // bias: keys ^ 2^63, so that a SIGNED 64-bit min (torch int64, gloo) orders them; unsigned collectives (ncclUint64) take them as they are
 int launch_composite_pack(const uint32_t *color, const double *depth, unsigned long long *keys, size_t npix,
                           cudaStream_t st, bool bias) {
-    k_composite_pack<<<148 * 8, 256, 0, st>>>(color, depth, keys, npix, bias ? 0x8000000000000000ull : 0ull);
+    k_composite_pack<<<GRID_WAVE, 256, 0, st>>>(color, depth, keys, npix, bias ? 0x8000000000000000ull : 0ull);
     return 1;
 }
 int launch_composite_unpack(uint32_t *color, double *depth, const unsigned long long *keys, size_t npix,
                             cudaStream_t st, bool bias) {
-    k_composite_unpack<<<148 * 8, 256, 0, st>>>(color, depth, keys, npix, bias ? 0x8000000000000000ull : 0ull);
+    k_composite_unpack<<<GRID_WAVE, 256, 0, st>>>(color, depth, keys, npix, bias ? 0x8000000000000000ull : 0ull);
     return 1;
 }
 // ---- peer-memory composite: compute + exchange in ONE kernel over NVLink ---------------------------------
@@ -251,12 +251,12 @@ int launch_composite_peer(uint32_t *const *color, double *const *depth, int nran
         P.color[r] = r < nranks ? color[r] : nullptr;
         P.depth[r] = r < nranks ? depth[r] : nullptr;
     }
-    if (px1 > px0) k_composite_peer<<<148 * 8, 256, 0, st>>>(P, nranks, px0, px1);
+    if (px1 > px0) k_composite_peer<<<GRID_WAVE, 256, 0, st>>>(P, nranks, px0, px1);
     return 1;
 }
 
 int launch_composite_min(unsigned long long *inout, const unsigned long long *other, size_t n, cudaStream_t st) {
-    k_composite_min<<<148 * 8, 256, 0, st>>>(reinterpret_cast<long long *>(inout),
+    k_composite_min<<<GRID_WAVE, 256, 0, st>>>(reinterpret_cast<long long *>(inout),
                                             reinterpret_cast<const long long *>(other), n);
     return 1;
 }
@@ -275,8 +275,8 @@ k_atomic_probe(unsigned long long *__restrict__ buf, size_t words, unsigned long
     }
 }
 int launch_atomic_probe(unsigned long long *buf, size_t words, unsigned long long ops, cudaStream_t st) {
-    const unsigned threads = 148u * 8u * 256u;
-    k_atomic_probe<<<148 * 8, 256, 0, st>>>(buf, words, (ops + threads - 1) / threads);
+    const unsigned threads = GRID_WAVE * 256u;
+    k_atomic_probe<<<GRID_WAVE, 256, 0, st>>>(buf, words, (ops + threads - 1) / threads);
     return 1;
 }
 

@@ -18,7 +18,7 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr int RADIX_BINS_HOST = 1024;
-constexpr int RADIX_GRID = 148;
+constexpr int RADIX_GRID = (int)B200_SMS;
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_reduce(const uint32_t *__restrict__ in, uint32_t n_max, const unsigned int *__restrict__ n_dev,

@@ -23,7 +23,7 @@
 namespace fgl {
 
 constexpr int ST = 256;            // threads per CTA == (record, scanline) items per virtual block
-constexpr int SPAN_GRID = 148 * 8;  // persistent grid: virtual blocks are strided over it
+constexpr int SPAN_GRID = (int)GRID_WAVE;  // persistent grid: virtual blocks are strided over it
 
 // The fields of Rec the row walker needs.
 struct RowSetup {
@@ -283,7 +283,7 @@ int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cuda
     int bits = 1;
     while ((1u << bits) < wb.ntiles) bits++;
     launches += launch_sort_pairs(wb.seg_key, wb.seg_val, &c->n_segs, wb.cap_segs, bits, wb.scan_tmp, sorted_buf, st);
-    launch_pdl(k_tile_ranges, 148, TR_THREADS, 0, st, (const uint32_t *)wb.seg_key[*sorted_buf], c, wb.cap_segs, wb.busy_list,
+    launch_pdl(k_tile_ranges, B200_SMS, TR_THREADS, 0, st, (const uint32_t *)wb.seg_key[*sorted_buf], c, wb.cap_segs, wb.busy_list,
                wb.ntiles, wb.tile_ctl, wb.blk_base, wb.cap_prims / (128u * 64u) + 2u);
     launches++;
     return launches;

@@ -497,7 +497,10 @@ static oinfo rasterize(const Draw *dr, const Vertex *v0, const Vertex *v1, const
                 continue;
             }
             was_inside = 1;
-            int64_t i = y * W + x;
+            /* Go integer arithmetic wraps: a triangle whose screen coordinates are all NaN (a degenerate triangle
+             * that went through ClipTriangle: Barycentric divides 0 by 0) has x0 = x1 = y0 = y1 = int(NaN) =
+             * -2^63, and its one "pixel" gets the index -2^63 * W - 2^63, which is 0 when W is odd. */
+            int64_t i = (int64_t)((uint64_t)y * (uint64_t)W + (uint64_t)x);
             if (i < 0 || i >= len) continue;                                        /* :224 */
             if (dc->x_guard && (x < 0 || x >= W)) continue;    /* adopted rule */
             info.total_pixels++;

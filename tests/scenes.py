@@ -442,6 +442,33 @@ def tiny_framebuffer():
     return Scene(5, 3, run)
 
 
+def degenerate_clipped():
+    """Degenerate triangles (two equal vertices) that need clipping: ClipTriangle's Barycentric divides 0 by 0, every
+    attribute of the fan triangles -- Output included -- is NaN, `a <= 0` is false for NaN so they are drawn under
+    every Cull mode, the integer bounding box is int(NaN) = -2^63 on all four sides, and the reference's loops visit
+    one "pixel" whose index -2^63 * W - 2^63 wraps to 0 when the width is odd: pixel (0, 0) is counted, and with
+    ReadDepth off it receives a NaN depth and (blend path) a NaN-derived colour."""
+    tri = np.array([[(-0.3, -1.2, 0.1), (-0.3, -1.2, 0.1), (0.2, -0.7, 0.1)],      # v1 == v2, crosses y = -1
+                    [(0.9, 0.1, 0.0), (1.4, 0.3, 0.0), (1.4, 0.3, 0.0)],            # v2 == v3, crosses x = 1
+                    [(-0.5, -0.5, 0.2), (0.5, -0.5, 0.2), (0.0, 0.6, 0.2)]],        # an ordinary one
+                   dtype=np.float64)
+    mesh = NewTriangleMesh(tri)
+    mesh.color[:, :, :] = np.array([0.8, 0.3, 0.2, 0.6])
+
+    def run(ctx):
+        ctx.ClearColorBufferWith(HexColor("#405060"))
+        matrix = Orthographic(-1, 1, -1, 1, -1, 1)
+        sh = NewPhongShader(matrix, V(0, 0, 1), V(0, 0, 5))
+        sh.ObjectColor = HexColor("#C0D0E0")
+        ctx.Shader = sh
+        infos = [ctx.DrawMesh(mesh)]                 # CullBack: the NaN triangles are drawn all the same
+        ctx.Shader = NewPhongShader(matrix, V(0, 0, 1), V(0, 0, 5))   # vertex colours, alpha 0.6: blend path
+        ctx.ReadDepth = False
+        infos.append(ctx.DrawMesh(mesh))
+        return infos
+    return Scene(171, 19, run)
+
+
 # ---- synthetic benchmark meshes at test size ---------------------------------------------------------------
 _BUMPY_CACHE: Dict[tuple, Mesh] = {}
 
@@ -492,6 +519,7 @@ SCENES: Dict[str, Callable[[], Scene]] = {
     "state_wireframe_solid": state_wireframe_solid,
     "edge_cases": edge_cases,
     "tiny_framebuffer": tiny_framebuffer,
+    "degenerate_clipped": degenerate_clipped,
     "bumpy_small": bumpy_small,
 }
 GOLDEN_SCENES = list(SCENES)

@@ -31,6 +31,13 @@ def _random_mesh(rng, ntri, nline):
     centres = (rng.rand(ntri, 1, 3) * 2 - 1) * spread
     size = rng.choice([0.02, 0.2, 1.0])
     pos = centres + (rng.rand(ntri, 3, 3) * 2 - 1) * size
+    if ntri:
+        pick = rng.rand(ntri)
+        pos[pick < 0.05, 1] = pos[pick < 0.05, 0]                      # degenerate: two equal vertices
+        snap = (pick > 0.05) & (pick < 0.15)
+        pos[snap] = np.round(pos[snap] * 8) / 8                       # vertices on a coarse lattice: shared edges, pixel-centre hits, ties
+        far = (pick > 0.15) & (pick < 0.18)
+        pos[far, 0] *= 40.0                                           # one vertex far outside: long clipped slivers
     nrm = rng.rand(ntri, 3, 3) * 2 - 1
     nrm[rng.rand(ntri) < 0.2] = 0.0                              # zero normals (FixNormals in the clipper)
     tex = rng.rand(ntri, 3, 3) * rng.choice([1.0, 3.0]) - rng.choice([0.0, 1.0])
@@ -80,7 +87,7 @@ def _script(seed):
                  "DepthBias": float(rng.choice([0.0, 0.0, -1e-4, 1e-3]))}
         draws.append((mesh, shader, state))
     clear = Color(*rng.rand(4)) if rng.rand() < 0.7 else None
-    return W, H, clear, draws
+    return W, H, clear, draws, bool(rng.rand() < 0.25)
 
 
 def _run(ctx, clear, draws):
@@ -95,16 +102,20 @@ def _run(ctx, clear, draws):
     return infos
 
 
-@pytest.mark.parametrize("front", ["fused", "split"])
-@pytest.mark.parametrize("block", range(6))
+@pytest.mark.parametrize("front", ["fused", "split", "auto64"])
+@pytest.mark.parametrize("block", range(16))
 def test_random_scenes_match_oracle(block, front, oracle_lib, gpu_capi, monkeypatch):
     from fauxgl_b200.context import Context
-    monkeypatch.setenv("FGL_FRONT", front)
+    if front == "auto64":
+        monkeypatch.setenv("FGL_STRIP_W", "64")                   # the library's own choice of front end, 64-pixel strips
+    else:
+        monkeypatch.setenv("FGL_FRONT", front)
     for seed in range(block * 8, block * 8 + 8):
-        W, H, clear, draws = _script(seed)
-        octx = oracle_lib.OracleContext(W, H)
+        W, H, clear, draws, x_guard = _script(seed)
+        octx = oracle_lib.OracleContext(W, H, x_guard=x_guard)
         oinfo = _run(octx, clear, draws)
         gctx = Context(W, H)
+        gctx.XGuard = x_guard
         ginfo = _run(gctx, clear, draws)
         gd, gc = gctx.DepthBuffer, gctx.Image()
         dm = int((gd.view(np.uint64) != octx.DepthBuffer.view(np.uint64)).sum())
