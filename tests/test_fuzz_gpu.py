@@ -122,3 +122,70 @@ def test_random_scenes_match_oracle(block, front, oracle_lib, gpu_capi, monkeypa
         cm = int((gc != octx.ColorBuffer).any(axis=-1).sum())
         gctx.Close()
         assert ginfo == oinfo and dm == 0 and cm == 0, (seed, front, W, H, ginfo, oinfo, dm, cm)
+
+
+def _edge_script(seed):
+    """Corner cases on purpose: framebuffers of a few pixels, line widths larger than the screen, vertices on and behind the
+    eye plane (w = 0, w < 0), texture coordinates exactly on texel and wrap boundaries, depth cleared to arbitrary values."""
+    rng = np.random.RandomState(10_000 + seed)
+    W, H = int(rng.choice([1, 2, 3, 5, 8, 33, 64, 65])), int(rng.choice([1, 2, 3, 7, 32, 33]))
+    eye = V(0, 0, float(rng.choice([0.0, 0.5, 2.0])))                 # 0.0: the eye sits inside the geometry
+    matrix = LookAt(eye, V(0, 0, -1), V(0, 1, 0)).Perspective(float(rng.choice([30, 90, 150])), W / H, float(rng.choice([0.01, 0.5])), 10)
+    draws = []
+    for _ in range(int(rng.randint(1, 4))):
+        ntri, nline = int(rng.choice([1, 20, 150])), int(rng.choice([0, 3, 20]))
+        pos = (rng.rand(ntri, 3, 3) * 2 - 1) * np.array([2.0, 2.0, 3.0])
+        pos[rng.rand(ntri) < 0.3, :, 2] = eye[2]                       # whole triangles in the eye plane: w = 0
+        tex = np.round(rng.rand(ntri, 3, 3) * 8) / 4 - 0.5                # u, v on multiples of 1/4 in [-0.5, 1.5]
+        mesh = NewTriangleMesh(pos, texture=tex)
+        mesh.color[:, :, :3] = rng.rand(ntri, 3, 3)
+        mesh.color[:, :, 3] = rng.choice([0.0, 0.5, 1.0], size=(ntri, 3))  # alpha 0 everywhere on a triangle: Discard if the colour is black
+        mesh.color[rng.rand(ntri) < 0.1] = 0.0
+        if nline:
+            lines = NewLineMesh((rng.rand(nline, 2, 3) * 2 - 1) * 3.0)
+            lines.lcolor[:, :, :] = rng.rand(nline, 2, 4)
+            mesh.Add(lines)
+        kind = rng.randint(3)
+        if kind == 0:
+            shader = NewSolidColorShader(matrix, Color(*rng.rand(3), float(rng.choice([1.0, 0.25]))))
+        elif kind == 1:
+            shader = NewTextureShader(matrix, _random_texture(rng))
+        else:
+            shader = NewPhongShader(matrix, V(0.3, 0.4, 1.0), eye)    # vertex colours (ObjectColor == Discard)
+            shader.SpecularPower = float(rng.choice([0, 2.5, 100]))   # 2.5: Go's Pow with a fractional exponent
+        state = {"ReadDepth": rng.rand() < 0.8, "WriteDepth": rng.rand() < 0.8, "WriteColor": True,
+                 "AlphaBlend": rng.rand() < 0.7, "Wireframe": rng.rand() < 0.3, "FrontFace": 2,
+                 "Cull": int(rng.choice([1, 3])), "LineWidth": float(rng.choice([0.0, 1.0, 9.0, 200.0])),
+                 "DepthBias": float(rng.choice([0.0, -1e-5]))}
+        draws.append((mesh, shader, state, float(rng.choice([np.finfo(np.float64).max, 1.0, 0.5]))))
+    return W, H, draws
+
+
+@pytest.mark.parametrize("block", range(8))
+def test_random_corner_cases_match_oracle(block, oracle_lib, gpu_capi):
+    """Same comparison, plus the per-primitive RasterizeInfo of every draw (fgl_draw_*_each vs a loop of DrawTriangle /
+    DrawLine in the oracle)."""
+    from fauxgl_b200.context import Context
+    for seed in range(block * 6, block * 6 + 6):
+        W, H, draws = _edge_script(seed)
+        octx, gctx = oracle_lib.OracleContext(W, H), Context(W, H)
+        for di, (mesh, shader, state, cleard) in enumerate(draws):
+            for c in (octx, gctx):
+                c.Shader = shader
+                for k, v in state.items():
+                    setattr(c, k, v)
+                if di % 2 == 1:
+                    c.ClearDepthBufferWith(cleard)
+            if di % 2 == 0:
+                oi, gi = tuple(octx.DrawMesh(mesh)), tuple(gctx.DrawMesh(mesh))
+                assert oi == gi, (seed, di, oi, gi)
+            else:
+                ot, gt = octx.DrawTrianglesEach(mesh), gctx.DrawTrianglesEach(mesh)
+                assert (ot == gt).all(), (seed, di, np.nonzero((ot != gt).any(axis=1))[0][:5])
+                if mesh.num_lines:
+                    ol, gl = octx.DrawLinesEach(mesh), gctx.DrawLinesEach(mesh)
+                    assert (ol == gl).all(), (seed, di, np.nonzero((ol != gl).any(axis=1))[0][:5])
+            dm = int((gctx.DepthBuffer.view(np.uint64) != octx.DepthBuffer.view(np.uint64)).sum())
+            cm = int((gctx.Image() != octx.ColorBuffer).any(axis=-1).sum())
+            assert dm == 0 and cm == 0, (seed, di, W, H, dm, cm)
+        gctx.Close()
