@@ -171,8 +171,13 @@ int ensure_work(fgl_ctx *c, const Caps &want) {
 
 Caps grown(const fgl_ctx *c, const DrawCounters &hc) {
     auto g = [](uint32_t cap, uint32_t need) { return std::max<uint64_t>(cap, (uint64_t)need + need / 4 + 1024); };
+    // The stages run in sequence and stop at the first buffer that is too small: when the records or the scanlines did
+    // not fit, the span stage never ran and the segment count behind it is a sum over unwritten memory (found with
+    // compute-sanitizer, whose fill pattern turned that sum into a 500 GB request) -- the segment need is only
+    // trusted when everything in front of it fitted; the next attempt reports it.
+    const bool segs_known = !(hc.overflow & (OVF_RECORDS | OVF_ROWS));
     return Caps{c->wb.cap_prims, g(c->wb.cap_records, hc.need_records), g(c->wb.cap_rows, hc.need_rows),
-                g(c->wb.cap_segs, hc.need_segs), g(c->wb.cap_clip, hc.need_clip)};
+                segs_known ? g(c->wb.cap_segs, hc.need_segs) : c->wb.cap_segs, g(c->wb.cap_clip, hc.need_clip)};
 }
 
 // Entry points that wait for the stream (or allocate / free buffers recorded launches may use) are errors while a
@@ -1195,9 +1200,13 @@ int fgl_frame_end(fgl_ctx *c, uint8_t *color_dst, size_t stride, fgl_fence **fen
         return fail(c, FGL_E_INVALID, "fence belongs to another device");
     }
     fb_join(c);
-    if (color_dst)
-        CK(c, cudaMemcpy2DAsync(color_dst, stride, c->color, (size_t)c->w * 4, (size_t)c->w * 4, c->h,
-                                cudaMemcpyDeviceToHost, c->stream));
+    if (color_dst) {
+        if (stride == (size_t)c->w * 4)  // tightly packed: one linear copy (the 2-D form goes row by row)
+            CK(c, cudaMemcpyAsync(color_dst, c->color, (size_t)c->w * 4 * c->h, cudaMemcpyDeviceToHost, c->stream));
+        else
+            CK(c, cudaMemcpy2DAsync(color_dst, stride, c->color, (size_t)c->w * 4, (size_t)c->w * 4, c->h,
+                                    cudaMemcpyDeviceToHost, c->stream));
+    }
     CK(c, cudaMemcpyAsync(f->counters, c->acc_dev, sizeof(DrawCounters), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaMemsetAsync(c->acc_dev, 0, sizeof(DrawCounters), c->stream));
     CK(c, cudaEventRecord(f->done, c->stream));
@@ -1278,7 +1287,10 @@ int fgl_read_color(fgl_ctx *c, uint8_t *dst, size_t stride) {
     std::lock_guard<std::mutex> lock(c->mu);
     NOT_WHILE_RECORDING(c, "fgl_read_color");
     fb_join(c);
-    CK(c, cudaMemcpy2DAsync(dst, stride, c->color, (size_t)c->w * 4, (size_t)c->w * 4, c->h, cudaMemcpyDeviceToHost, c->stream));
+    if (stride == (size_t)c->w * 4)
+        CK(c, cudaMemcpyAsync(dst, c->color, (size_t)c->w * 4 * c->h, cudaMemcpyDeviceToHost, c->stream));
+    else
+        CK(c, cudaMemcpy2DAsync(dst, stride, c->color, (size_t)c->w * 4, (size_t)c->w * 4, c->h, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return FGL_OK;
 }

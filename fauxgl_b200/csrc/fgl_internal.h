@@ -274,7 +274,7 @@ __device__ __forceinline__ void accumulate_counters(const DrawCounters *cur, Dra
     acc->overflow |= cur->overflow;
     acc->need_records = max(acc->need_records, cur->need_records);
     acc->need_rows = max(acc->need_rows, cur->need_rows);
-    acc->need_segs = max(acc->need_segs, cur->need_segs);
+    if (!(cur->overflow & (OVF_RECORDS | OVF_ROWS))) acc->need_segs = max(acc->need_segs, cur->need_segs);  // (else: not computed)
     acc->need_clip = max(acc->need_clip, cur->need_clip);
 }
 
