@@ -251,8 +251,9 @@ struct ScanSink {
 int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n_max, const unsigned int *n_dev,
                           uint32_t *tmp, const ScanSink &sink, cudaStream_t st);
 // stable LSD radix sort of (key,val) pairs on `bits` key bits; returns launches, *sorted_buf = buffer index
+// skip_if (nullable): the draw's overflow word -- the keys of an overflowed draw were never written, sort nothing
 int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsigned int *n_dev, uint32_t n_max,
-                      int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st);
+                      int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st, const unsigned int *skip_if = nullptr);
 
 // counters_clean: the previous draw's last kernel left the draw counters zeroed (no memset node needed)
 int launch_geometry(const DrawParams &p, const WorkBuffers &wb, bool counters_clean, cudaStream_t st);

@@ -22,8 +22,10 @@ constexpr int RADIX_GRID = (int)B200_SMS;
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_reduce(const uint32_t *__restrict__ in, uint32_t n_max, const unsigned int *__restrict__ n_dev,
-              uint32_t *__restrict__ tmp) {
-    const uint32_t n = n_dev ? min(*n_dev, n_max) : n_max;
+              uint32_t *__restrict__ tmp, const unsigned int *__restrict__ skip_if) {
+    // skip_if (the draw's overflow word): an earlier stage ran out of buffer and the producer of `in` never ran --
+    // the input is unwritten memory; scan nothing (the host regrows and re-issues the draw)
+    const uint32_t n = (skip_if && *skip_if) ? 0u : (n_dev ? min(*n_dev, n_max) : n_max);
     const uint32_t base = blockIdx.x * SCAN_TILE;
     uint32_t sum = 0;
     if (base < n) {
@@ -42,9 +44,10 @@ k_scan_reduce(const uint32_t *__restrict__ in, uint32_t n_max, const unsigned in
 // One block: exclusive scan of the block sums in place; total -> out[n].
 __global__ void __launch_bounds__(1024)
 k_scan_spine(uint32_t *__restrict__ tmp, uint32_t nblocks, uint32_t *__restrict__ out, uint32_t n_max,
-             const unsigned int *__restrict__ n_dev, const ScanSink sink) {
+             const unsigned int *__restrict__ n_dev, const ScanSink sink, const unsigned int *__restrict__ skip_if) {
     __shared__ uint32_t sm[1024 / 32 + 1];
     uint32_t carry = 0;
+    const bool skipped = skip_if && *skip_if;
     for (uint32_t base = 0; base < nblocks; base += 1024) {
         uint32_t i = base + threadIdx.x;
         uint32_t v = i < nblocks ? tmp[i] : 0;
@@ -54,7 +57,7 @@ k_scan_spine(uint32_t *__restrict__ tmp, uint32_t nblocks, uint32_t *__restrict_
         carry += total;
     }
     if (threadIdx.x == 0) {
-        out[n_dev ? min(*n_dev, n_max) : n_max] = carry;
+        out[skipped ? 0u : (n_dev ? min(*n_dev, n_max) : n_max)] = carry;
         if (sink.count) *sink.count = carry;
         if (sink.need) *sink.need = carry;
         if (sink.overflow && carry > sink.cap) *sink.overflow |= sink.bit;
@@ -68,8 +71,8 @@ k_scan_spine(uint32_t *__restrict__ tmp, uint32_t nblocks, uint32_t *__restrict_
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_down(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n_max,
-            const unsigned int *__restrict__ n_dev, const uint32_t *__restrict__ tmp) {
-    const uint32_t n = n_dev ? min(*n_dev, n_max) : n_max;
+            const unsigned int *__restrict__ n_dev, const uint32_t *__restrict__ tmp, const unsigned int *__restrict__ skip_if) {
+    const uint32_t n = (skip_if && *skip_if) ? 0u : (n_dev ? min(*n_dev, n_max) : n_max);
     const uint32_t base = blockIdx.x * SCAN_TILE;
     if (base >= n) return;
     // thread t owns SCAN_ITEMS consecutive items
@@ -101,9 +104,11 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n_max, con
                           uint32_t *tmp, const ScanSink &sink, cudaStream_t st) {
     uint32_t nblocks = (n_max + SCAN_TILE - 1) / SCAN_TILE;
     if (nblocks == 0) nblocks = 1;
-    k_scan_reduce<<<nblocks, SCAN_THREADS, 0, st>>>(in, n_max, n_dev, tmp);
-    k_scan_spine<<<1, 1024, 0, st>>>(tmp, nblocks, out, n_max, n_dev, sink);
-    k_scan_down<<<nblocks, SCAN_THREADS, 0, st>>>(in, out, n_max, n_dev, tmp);
+    // (the overflow word is sampled by all three kernels before the spine may set this scan's own bit in it: the
+    // reduce and the spine read it first thing, the down-sweep skips harmlessly when the spine has just set it)
+    k_scan_reduce<<<nblocks, SCAN_THREADS, 0, st>>>(in, n_max, n_dev, tmp, sink.overflow);
+    k_scan_spine<<<1, 1024, 0, st>>>(tmp, nblocks, out, n_max, n_dev, sink, sink.overflow);
+    k_scan_down<<<nblocks, SCAN_THREADS, 0, st>>>(in, out, n_max, n_dev, tmp, sink.overflow);
     return 3;
 }
 
@@ -138,14 +143,14 @@ __device__ __forceinline__ void radix_segment(uint32_t n, uint32_t &beg, uint32_
 template <int BITS>
 __global__ void __launch_bounds__(RADIX_THREADS)
 k_radix_hist(const uint32_t *__restrict__ keys, const unsigned int *__restrict__ n_dev, uint32_t n_max, int shift,
-             uint32_t *__restrict__ hist /*[grid][BINS]*/) {
+             uint32_t *__restrict__ hist /*[grid][BINS]*/, const unsigned int *__restrict__ skip_if) {
     constexpr int BINS = 1 << BITS;
     __shared__ uint32_t h[BINS];
     pdl_wait();
     pdl_trigger();
     for (int k = threadIdx.x; k < BINS; k += RADIX_THREADS) h[k] = 0;
     __syncthreads();
-    const uint32_t n = min(*n_dev, n_max);
+    const uint32_t n = (skip_if && *skip_if) ? 0u : min(*n_dev, n_max);  // (overflowed draw: the keys were never written)
     uint32_t beg, end;
     radix_segment(n, beg, end);
     for (uint32_t i = beg + threadIdx.x; i < end; i += RADIX_THREADS)
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(RADIX_THREADS)
 k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                 const unsigned int *__restrict__ n_dev, uint32_t n_max, int shift,
-                const uint32_t *__restrict__ hist /*[grid][BINS], raw counts*/) {
+                const uint32_t *__restrict__ hist /*[grid][BINS], raw counts*/, const unsigned int *__restrict__ skip_if) {
     constexpr int BINS = 1 << BITS;
     constexpr int DPT = (BINS + RADIX_THREADS - 1) / RADIX_THREADS;  // digits per thread in the bucket-base scan (1)
     pdl_wait();
@@ -194,7 +199,7 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
         if (threadIdx.x < BINS) cursor[d] = digit_base + before;
     }
     __syncthreads();
-    const uint32_t n = min(*n_dev, n_max);
+    const uint32_t n = (skip_if && *skip_if) ? 0u : min(*n_dev, n_max);
     uint32_t beg, end;
     radix_segment(n, beg, end);
     const uint32_t ltmask = (1u << lane) - 1u;
@@ -264,14 +269,14 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
 
 template <int BITS>
 static int radix_pass(uint32_t *const key[2], uint32_t *const val[2], int cur, const unsigned int *n_dev, uint32_t n_max,
-                      int shift, uint32_t *tmp, cudaStream_t st) {
+                      int shift, uint32_t *tmp, cudaStream_t st, const unsigned int *skip_if) {
     constexpr int BINS = 1 << BITS;
     const size_t smem = sizeof(uint32_t) * (size_t)BINS * (RADIX_WARPS + 1);
     // per device and cheap: set on every call (a process may drive several GPUs)
     cudaFuncSetAttribute(k_radix_scatter<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    launch_pdl(k_radix_hist<BITS>, RADIX_GRID, RADIX_THREADS, 0, st, key[cur], n_dev, n_max, shift, tmp);
+    launch_pdl(k_radix_hist<BITS>, RADIX_GRID, RADIX_THREADS, 0, st, key[cur], n_dev, n_max, shift, tmp, skip_if);
     launch_pdl(k_radix_scatter<BITS>, RADIX_GRID, RADIX_THREADS, smem, st, key[cur], val[cur], key[cur ^ 1], val[cur ^ 1],
-               n_dev, n_max, shift, tmp);
+               n_dev, n_max, shift, (const uint32_t *)tmp, skip_if);
     return 2;
 }
 
@@ -280,13 +285,13 @@ static int radix_pass(uint32_t *const key[2], uint32_t *const val[2], int cur, c
 // scanning 32 x 1024 counters per tile costs more than the third pass.  10-bit digits are used only when
 // they save a pass AND the sort is small enough to be latency-bound (a launch saved > work added).
 int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsigned int *n_dev, uint32_t n_max,
-                      int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st) {
+                      int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st, const unsigned int *skip_if) {
     int launches = 0, cur = 0;
     const int passes = (bits + 9) / 10;
     const bool narrow = passes * 8 >= bits || n_max > (1u << 18);
     for (int shift = 0; shift < bits; shift += narrow ? 8 : 10) {
-        launches += narrow ? radix_pass<8>(key, val, cur, n_dev, n_max, shift, tmp, st)
-                           : radix_pass<10>(key, val, cur, n_dev, n_max, shift, tmp, st);
+        launches += narrow ? radix_pass<8>(key, val, cur, n_dev, n_max, shift, tmp, st, skip_if)
+                           : radix_pass<10>(key, val, cur, n_dev, n_max, shift, tmp, st, skip_if);
         cur ^= 1;
     }
     *sorted_buf = cur;
