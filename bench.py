@@ -84,7 +84,7 @@ def scene_setup():
 
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread
-    every ~2 ms (nvidia-smi's 100 ms loop is coarser than a whole timed region here)."""
+    every ~0.5 ms (nvidia-smi's 100 ms loop is coarser than a whole timed region here)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
@@ -111,7 +111,7 @@ class ClockSampler:
                 self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
     def start(self):
         if self.h is None:

@@ -763,6 +763,15 @@ FGL_DI bool surely_culled(const DrawParams &p, const V4 *o) {
 #ifndef FGL_FRONT_PREFETCH
 #define FGL_FRONT_PREFETCH 0
 #endif
+#ifndef FGL_FRONT_COMPACT
+#define FGL_FRONT_COMPACT 1  // queue the scanlines that cover something and walk their runs with full warps (0: walk in place)
+#endif
+struct __align__(8) QEntry {  // a scanline whose run has been found: edge values at its first covered pixel
+    double w0, w1, w2;
+    int32_t x, y;
+    uint32_t ridx, _pad;
+};
+constexpr uint32_t QCAP = 64;  // ring entries per warp: up to 31 left over + 32 new
 __global__ void __launch_bounds__(FT, FGL_FRONT_MINB)
 k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
     __shared__ SRec s_rec[FT];
@@ -775,6 +784,9 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     // fast blocks (no clipping / lines / wireframe): every warp compacts into a sub-region of its own
     __shared__ uint32_t s_celloff[FT];           // cells (rows x strip columns) of the records before this one
     __shared__ volatile uint32_t s_region_ready;
+#if FGL_FRONT_COMPACT
+    __shared__ QEntry s_ring[FT / 32][QCAP];
+#endif
     if (threadIdx.x == 0) s_region_ready = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();  // k_seg_index may be scheduled while the last wave of this grid drains
@@ -933,6 +945,82 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             wbase = s_celloff[lo_base] + (my0 - s_rowoff[lo_base]) * box_cols(p, r.x0, r.x1);
         }
         bool have_region = false;
+#if FGL_FRONT_COMPACT
+        // Two thirds of the (record, scanline) items of sub-pixel triangles cover nothing, and the run loop and the
+        // 128-byte segment store behind them ran with a dozen of 32 lanes.  So the walk is split: every lane first
+        // FINDS the run of its item (replay, skip-ahead, the pixels left of the run), the items that have one are
+        // queued -- in item order -- in a small per-warp ring in shared memory, and whenever 32 are waiting a full
+        // warp walks their runs and stores their segments.  Slots are still handed out in item order (the ring is a
+        // FIFO), so the segment order is unchanged.
+        QEntry *const ring = s_ring[warp];
+        uint32_t qhead = 0, qn = 0;  // warp-uniform
+        auto drain = [&](uint32_t take) {  // the first `take` (<= 32) queued items
+            uint32_t nseg = 0, ridx = 0;
+            int y = 0;
+            if ((uint32_t)lane < take) {
+                const QEntry e = ring[(qhead + (uint32_t)lane) % QCAP];
+                ridx = e.ridx; y = e.y;
+                const SRec &r = s_rec[ridx];
+                const unsigned long long before = covered;
+                nseg = walk_row_run(p, r, y, e.w0, e.w1, e.w2, e.x, first, &covered);
+                if (p.prim_info && covered != before)  // per-primitive TotalPixels (fgl_draw_*_each)
+                    atomicAdd(&p.prim_info[2 * (size_t)src_primitive(wb, p, r.src, r.flags)], covered - before);
+            }
+            const uint32_t incl_w = warp_incl_scan(nseg);
+            const uint32_t ex = incl_w - nseg, batch_total = __shfl_sync(0xffffffffu, incl_w, 31);
+            if (!have_region) {
+                uint32_t ready;
+                do {
+                    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ready) : "r"(flag_addr) : "memory");
+                } while (ready == 0u);
+                region = *(volatile unsigned long long *)&s_region;
+                have_region = true;
+            }
+            if (nseg) {
+                const unsigned long long slot64 = region + wbase + wrun + ex;
+                const SRec &r = s_rec[ridx];
+                RecTail tail;
+                tail.r0 = r.r0; tail.r1 = r.r1; tail.r2 = r.r2; tail.src = r.src; tail.flags = r.flags;
+                if (slot64 + nseg <= (unsigned long long)wb.cap_segs) {
+                    const uint32_t slot = (uint32_t)slot64;
+                    if (nseg == 1) {
+                        wb.segv[slot] = make_segv(first.w0, first.w1, first.w2, r.ra, r.z0, r.z1, r.z2, r.s2y - r.s1y,
+                                                  r.s0y - r.s2y, r.s1y - r.s0y, tail, (uint16_t)first.x, (uint8_t)first.cnt, first.wrap);
+                        wb.seg_key[1][slot] = first.key;
+                    } else {  // the scanline crosses strip boundaries: walk it again, storing every segment
+                        unsigned long long dummy = 0;
+                        walk_row_segments<true>(p, r, y, first, &tail, wb.segv, wb.seg_key[1], slot, wb.cap_segs, &dummy);
+                    }
+                }
+            }
+            wrun += batch_total;
+            qhead = (qhead + take) % QCAP;
+            qn -= take;
+            __syncwarp();
+        };
+        for (uint32_t c0 = my0; c0 < my1; c0 += 32) {
+            const uint32_t it = c0 + (uint32_t)lane;
+            const uint32_t rel = s_rowoff[min(lo_base + 1u + (uint32_t)lane, (uint32_t)FT)] - c0;  // >= 1
+            const uint32_t bmask = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+            const uint32_t lo = lo_base + (uint32_t)__popc(bmask & (0xffffffffu >> (31 - lane)));
+            lo_base += (uint32_t)__popc(bmask) + (__any_sync(0xffffffffu, rel == 32u) ? 1u : 0u);  // record of item c0 + 32
+            bool found = false;
+            QEntry e;
+            e.w0 = e.w1 = e.w2 = 0; e.x = 0; e.y = 0; e.ridx = 0;
+            if (it < my1) {
+                e.ridx = s_order[lo];
+                const SRec &r = s_rec[e.ridx];
+                e.y = row_base(p, r.x1, r.y0) + (int)(it - s_rowoff[lo]);
+                found = walk_row_find(p, r, e.y, e.w0, e.w1, e.w2, e.x);
+            }
+            const uint32_t fm = __ballot_sync(0xffffffffu, found);
+            if (found) ring[(qhead + qn + (uint32_t)__popc(fm & ((1u << lane) - 1u))) % QCAP] = e;
+            qn += (uint32_t)__popc(fm);
+            __syncwarp();
+            if (qn >= 32u) drain(32u);
+        }
+        if (qn) drain(qn);
+#else
         for (uint32_t c0 = my0; c0 < my1; c0 += 32) {
             const uint32_t it = c0 + (uint32_t)lane;
             const uint32_t rel = s_rowoff[min(lo_base + 1u + (uint32_t)lane, (uint32_t)FT)] - c0;  // >= 1
@@ -979,6 +1067,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             }
             wrun += chunk_total;
         }
+#endif
         // Every warp publishes its own run and leaves: no barrier behind the walk (the block's warps used to wait
         // here for the slowest of the four, then for thread 0's round trip to the block counter -- 15 % of the
         // kernel's stall samples).  k_seg_index adds the runs up itself (group sums + the blocks of its group).

@@ -254,6 +254,72 @@ __device__ __forceinline__ uint32_t walk_row_count(const DrawParams &p, const R 
     return (uint32_t)(c1 - c0 + 1);
 }
 
+// The count walk in two halves, for the compacting front end (fgl_geom.cu, FGL_FRONT_COMPACT): walk_row_find runs the
+// chain up to the first covered pixel (row replay, skip-ahead, the pixels left of the run) and says whether there is
+// one; walk_row_run continues from there over the run.  Together they execute exactly the adds and tests of
+// walk_row_count.  A box that leaves the framebuffer sideways is reported as found with x = WALK_GENERAL: the second
+// half then calls the general walker for the whole row.
+constexpr int WALK_GENERAL = (int)0x80000000;
+template <class R>
+__device__ __forceinline__ bool walk_row_find(const DrawParams &p, const R &r, int y, double &w0, double &w1, double &w2, int &x) {
+    if ((unsigned)r.x0 >= (unsigned)p.width || (unsigned)r.x1 >= (unsigned)p.width) { x = WALK_GENERAL; w0 = w1 = w2 = 0; return true; }
+    const double a01 = r.s1y - r.s0y, b01 = r.s0x - r.s1x;  // context.go:167-172
+    const double a12 = r.s2y - r.s1y, b12 = r.s1x - r.s2x;
+    const double a20 = r.s0y - r.s2y, b20 = r.s2x - r.s0x;
+    double w00 = r.w00, w01 = r.w01, w02 = r.w02;
+    for (int yy = r.y0; yy < y; yy++) { w00 += b12; w01 += b20; w02 += b01; }  // context.go:275-277
+    double d = 0;  // skip-ahead, context.go:185-205
+    const double d0 = -w00 * r.ra12, d1 = -w01 * r.ra20, d2 = -w02 * r.ra01;
+    if (w00 < 0 && d0 > d) d = d0;
+    if (w01 < 0 && d1 > d) d = d1;
+    if (w02 < 0 && d2 > d) d = d2;
+    const long long di = go_int(d);
+    d = (double)di;
+    if (d < 0) d = 0;
+    w0 = w00 + a12 * d; w1 = w01 + a20 * d; w2 = w02 + a01 * d;
+    const long long xl = (long long)r.x0 + (di < 0 ? 0ll : (di > (1ll << 40) ? (1ll << 40) : di));
+    if (xl > (long long)r.x1) return false;
+    const int xe = r.x1;
+    x = (int)xl;
+    const double ra = r.ra;
+    const bool pos = ra > 0;  // exact early exit, see walk_row_core
+    const uint32_t dead = ((pos && a12 <= 0) ? 1u : 0u) | ((pos && a20 <= 0) ? 2u : 0u) | ((pos && a01 <= 0) ? 4u : 0u);
+    for (;;) {  // pixels left of the run (context.go:208-219 with wasInside == false)
+        const uint32_t out = neg_mask3(w0 * ra, w1 * ra, w2 * ra);
+        if (out == 0) return true;
+        if (out & dead) return false;
+        w0 += a12; w1 += a20; w2 += a01;  // context.go:211-213
+        if (++x > xe) return false;
+    }
+}
+// (w0, w1, w2, x): the first covered pixel found by walk_row_find.  Returns the segments of the row, the first in `first`.
+template <class R>
+__device__ __forceinline__ uint32_t walk_row_run(const DrawParams &p, const R &r, int y, double w0, double w1, double w2, int x,
+                                                 ParkedSeg &first, unsigned long long *covered) {
+    if (x == WALK_GENERAL) {
+        ParkedSeg tmp;
+        unsigned long long cov = 0;
+        const uint32_t ns = walk_row_general(p, edge_setup(r), r.y0, y, r.w00, r.w01, r.w02, &tmp, &cov);
+        first = tmp;
+        *covered += cov;
+        return ns;
+    }
+    const double a01 = r.s1y - r.s0y, a12 = r.s2y - r.s1y, a20 = r.s0y - r.s2y, ra = r.ra;
+    const int xe = r.x1;
+    first.w0 = w0; first.w1 = w1; first.w2 = w2; first.x = x; first.wrap = 0;
+    const int xs = x;
+    do {  // the run: up to the first outside pixel (context.go:216-218) or the end of the row
+        w0 += a12; w1 += a20; w2 += a01;
+        if (++x > xe) break;
+    } while (!any_neg3(w0 * ra, w1 * ra, w2 * ra));
+    const uint32_t n = (uint32_t)(x - xs);
+    *covered += n;
+    const int c0 = xs >> p.tile_shift, c1 = (x - 1) >> p.tile_shift;
+    first.cnt = min(n, (uint32_t)(((c0 + 1) << p.tile_shift) - xs));
+    first.key = (uint32_t)y * (uint32_t)p.tiles_x + (uint32_t)c0;
+    return (uint32_t)(c1 - c0 + 1);
+}
+
 // Walk row y of the triangle described by r (any struct with the fields s0x..s2y, w00..w02, ra, ra12, ra20,
 // ra01, z0..z2, x0, x1, y0): the per-row adds are replayed from y0 (context.go:275-277).
 //   WRITE == false: the first segment is returned in `first`, nothing is stored.
