@@ -764,7 +764,9 @@ FGL_DI bool surely_culled(const DrawParams &p, const V4 *o) {
 #define FGL_FRONT_PREFETCH 0
 #endif
 #ifndef FGL_FRONT_COMPACT
-#define FGL_FRONT_COMPACT 1  // queue the scanlines that cover something and walk their runs with full warps (0: walk in place)
+#define FGL_FRONT_COMPACT 0  // 1: queue the scanlines that cover something and walk their runs with full warps.  Measured
+                             // SLOWER (k_front 100.4 -> 112.7 us at 1080p, 301 -> 330 us at 8K): the ring traffic and the
+                             // 10 KB of shared memory cost more than the idle lanes it removes.  Kept as a tuning variant.
 #endif
 struct __align__(8) QEntry {  // a scanline whose run has been found: edge values at its first covered pixel
     double w0, w1, w2;
