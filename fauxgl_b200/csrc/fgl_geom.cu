@@ -768,12 +768,14 @@ FGL_DI bool surely_culled(const DrawParams &p, const V4 *o) {
                              // SLOWER (k_front 100.4 -> 112.7 us at 1080p, 301 -> 330 us at 8K): the ring traffic and the
                              // 10 KB of shared memory cost more than the idle lanes it removes.  Kept as a tuning variant.
 #endif
+#if FGL_FRONT_COMPACT
 struct __align__(8) QEntry {  // a scanline whose run has been found: edge values at its first covered pixel
     double w0, w1, w2;
     int32_t x, y;
     uint32_t ridx, _pad;
 };
 constexpr uint32_t QCAP = 64;  // ring entries per warp: up to 31 left over + 32 new
+#endif
 __global__ void __launch_bounds__(FT, FGL_FRONT_MINB)
 k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffers wb) {
     __shared__ SRec s_rec[FT];
