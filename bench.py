@@ -436,6 +436,8 @@ def main():
             if resolve:
                 ctx.ResolveDevice(resolve)
         ctx.DrawMesh(dm)          # one synchronous draw sizes the work buffers (async draws cannot regrow)
+        if resolve:
+            ctx.ResolveDevice(resolve)   # (allocates the resolve target: nothing may be allocated while recording)
         direct = frame
         recorded = None
         if graph and not profile:

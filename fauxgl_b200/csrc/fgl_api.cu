@@ -110,8 +110,18 @@ void free_work(WorkBuffers &wb) {
 
 struct Caps { uint64_t prims, records, rows, segs, clip; };
 
-// (Re)allocate work buffers so that they hold at least the given capacities.
+int ensure_work_impl(fgl_ctx *c, const Caps &want);
+// (Re)allocate work buffers so that they hold at least the given capacities; a reallocation invalidates recorded graphs.
 int ensure_work(fgl_ctx *c, const Caps &want) {
+    const WorkBuffers before = c->wb;
+    const int rc = ensure_work_impl(c, want);
+    const WorkBuffers &wb = c->wb;
+    if (before.segv != wb.segv || before.recs != wb.recs || before.row_first != wb.row_first || before.clip_pool != wb.clip_pool ||
+        before.blk_agg != wb.blk_agg || before.scan_tmp != wb.scan_tmp || before.seg_key[0] != wb.seg_key[0])
+        c->buffer_epoch++;
+    return rc;
+}
+int ensure_work_impl(fgl_ctx *c, const Caps &want) {
     WorkBuffers &wb = c->wb;
     const uint64_t LIM = 0xfffffff0ull;
     if (want.records >= (1ull << 30)) return fail(c, FGL_E_INVALID, "draw too large: more than 2^30 raster records");
@@ -493,7 +503,7 @@ int fgl_graph_end(fgl_ctx *c, fgl_graph **out) {
     }
     fgl_graph *gr = new (std::nothrow) fgl_graph();
     if (!gr) { cudaGraphExecDestroy(ex); cudaGraphDestroy(g); return fail(c, FGL_E_OOM, "host allocation failed"); }
-    gr->device = c->device; gr->ctx = c; gr->graph = g; gr->exec = ex;
+    gr->device = c->device; gr->ctx = c; gr->graph = g; gr->exec = ex; gr->buffer_epoch = c->buffer_epoch;
     gr->has_draws = c->async_pending;   // (set by the recorded draws; nothing ran yet)
     gr->counters_clean = c->counters_clean;
     c->async_pending = false;           // the recording itself drew nothing
@@ -508,6 +518,9 @@ int fgl_graph_launch(fgl_ctx *c, fgl_graph *g) {
     if (!g || g->ctx != c) return fail(c, FGL_E_INVALID, "graph belongs to another context");
     std::lock_guard<std::mutex> lock(c->mu);
     if (c->capturing) return fail(c, FGL_E_INVALID, "cannot launch a graph while recording one");
+    if (g->buffer_epoch != c->buffer_epoch)
+        return fail(c, FGL_E_INVALID, "the context's work or resolve buffers were reallocated after this graph was recorded "
+                                      "(a larger draw, another resolve size): record it again");
     fb_join(c);
     CK(c, cudaGraphLaunch(g->exec, c->stream));
     if (g->has_draws) c->async_pending = true;
@@ -587,7 +600,7 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     memset(&c->wb, 0, sizeof c->wb);
     memset(&c->stats, 0, sizeof c->stats);
     c->host_counters = nullptr; c->acc_dev = nullptr; c->async_pending = false; c->counters_clean = false;
-    c->capturing = false;
+    c->capturing = false; c->buffer_epoch = 0;
     c->prim_info = nullptr; c->prim_info_cap = 0; c->scratch = nullptr; c->gray16 = nullptr;
     c->peer_flags = nullptr; c->peer_epoch = 0; c->clear_depth_value = 1.7976931348623157e308;
     c->clear_color_value = 0u; c->clear_color_known = true;  // NewContext: transparent black
@@ -1360,6 +1373,8 @@ int fgl_resolve_device(fgl_ctx *c, int factor) {
     const int dw = c->w / factor, dh = c->h / factor;
     fb_join(c);
     if (dw != c->rw || dh != c->rh) {
+        if (c->capturing) return fail(c, FGL_E_INVALID, "resolve once with this factor before recording (its buffer is allocated on first use)");
+        c->buffer_epoch++;
         dev_free(c->resolved);
         CK(c, dev_alloc(&c->resolved, (size_t)dw * dh));
         c->rw = dw; c->rh = dh;

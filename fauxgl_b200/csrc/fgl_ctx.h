@@ -73,6 +73,7 @@ struct fgl_ctx {
     DrawCounters *acc_dev;             // async accumulation (total/updated/overflow)
     bool async_pending;
     bool capturing;                    // between fgl_graph_begin and fgl_graph_end: the stream records instead of running
+    unsigned long long buffer_epoch;   // bumped whenever a device buffer recorded launches may point at is reallocated
     bool counters_clean;               // the last draw's k_shade zeroed the device-side draw counters
     unsigned long long *prim_info;     // per-primitive RasterizeInfo of fgl_draw_*_each, [prim_info_cap][2]
     uint64_t prim_info_cap;
@@ -97,6 +98,7 @@ struct fgl_graph {
     fgl_ctx *ctx;
     cudaGraph_t graph;
     cudaGraphExec_t exec;
+    unsigned long long buffer_epoch;  // the context's buffer_epoch when it was recorded: a replay after a reallocation is refused
     bool has_draws;        // launching it leaves RasterizeInfo to collect (fgl_sync / fgl_frame_end)
     bool counters_clean;   // state of the draw counters after the recorded frame
 };

@@ -486,6 +486,8 @@ def test_recorded_frame_replays_identically(scene_name, resolve, oracle_lib, Con
     ctx2 = ctx                                   # the script mutates Wireframe / DepthBias / Cull ...: back to NewContext's state
     ctx2.ReadDepth = ctx2.WriteDepth = ctx2.WriteColor = ctx2.AlphaBlend = True
     ctx2.Wireframe, ctx2.FrontFace, ctx2.Cull, ctx2.LineWidth, ctx2.DepthBias = False, 2, 3, 2.0, 0.0
+    if resolve:
+        ctx2.ResolveDevice(resolve)               # its buffer is allocated on first use: not while recording
     ctx2.ClearDepthBuffer()
     ctx2.GraphBegin()
     ctx2.ClearDepthBuffer()
@@ -512,5 +514,10 @@ def test_recorded_frame_replays_identically(scene_name, resolve, oracle_lib, Con
     with pytest.raises(Exception):
         ctx2.Image()
     ctx2.GraphEnd()
+    # a recording is refused once the buffers it points at have been reallocated (here: another resolve size)
+    if resolve:
+        ctx2.ResolveDevice(1)
+        with pytest.raises(Exception):
+            graph.launch()
     graph.Close()
     ctx.Close(); ref.Close()
