@@ -16,7 +16,7 @@
 //     reference's `<=` rule), so the result equals the single-GPU frame bit for bit.  It is SPARSE: every context
 //     keeps a bitmap of the strips whose depth was written since the last depth clear (k_strip sets it), rank r
 //     composites the scanlines y = r (mod N) and only reads, from each peer, the strips that peer has drawn into --
-//     a 10 M-triangle sphere that covers a third of an 8K frame moves ~12 B per COVERED pixel instead of 8 B per
+//     a 10 M-triangle sphere that covers 59 % of an 8K frame moves ~12 B per COVERED pixel instead of 8 B per
 //     pixel of the frame per rank.  Ranks synchronise through flags in peer memory (release stores / acquire loads at
 //     system scope), not through host barriers: signal(ready) -> wait(all ready) -> composite -> signal(done) ->
 //     wait(all done), all enqueued on the context's stream.
