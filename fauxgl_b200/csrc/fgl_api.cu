@@ -609,6 +609,15 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     const size_t npix = (size_t)width * height;
     c->stream = nullptr; c->copy_stream = nullptr; c->fb_stream = nullptr;
     c->ev_fb_free = nullptr; c->ev_cleared = nullptr; c->clear_pending = false;
+    c->read_stream = nullptr; c->rb_next = 0;
+    for (int k = 0; k < 2; k++) {
+        c->rb_color[k] = nullptr; c->rb_counters[k] = nullptr; c->ev_rb_staged[k] = nullptr; c->ev_rb_done[k] = nullptr;
+        c->rb_done_recorded[k] = false;
+    }
+    {
+        const char *ro = getenv("FGL_READBACK_OVERLAP");  // tuning aid: 0 reads back on the draw stream, straight from the framebuffer
+        c->rb_overlap = !(ro && atoi(ro) == 0);
+    }
     {
         const char *pd = getenv("FGL_PDL");  // tuning aid: 0 launches every kernel fully serialised
         fgl::g_pdl = !(pd && atoi(pd) == 0);
@@ -673,6 +682,12 @@ int fgl_context_destroy(fgl_ctx *c) {
     cudaSetDevice(c->device);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->fb_stream) { cudaStreamSynchronize(c->fb_stream); cudaStreamDestroy(c->fb_stream); }
+    if (c->read_stream) { cudaStreamSynchronize(c->read_stream); cudaStreamDestroy(c->read_stream); }
+    for (int k = 0; k < 2; k++) {
+        if (c->ev_rb_staged[k]) cudaEventDestroy(c->ev_rb_staged[k]);
+        if (c->ev_rb_done[k]) cudaEventDestroy(c->ev_rb_done[k]);
+        dev_free(c->rb_color[k]); dev_free(c->rb_counters[k]);
+    }
     if (c->ev_fb_free) cudaEventDestroy(c->ev_fb_free);
     if (c->ev_cleared) cudaEventDestroy(c->ev_cleared);
     if (c->stream) cudaStreamSynchronize(c->stream);
@@ -1174,6 +1189,7 @@ int fgl_sync(fgl_ctx *c, fgl_raster_info *info) {
         CK(c, cudaMemsetAsync(c->acc_dev, 0, sizeof(DrawCounters), c->stream));
     }
     CK(c, cudaStreamSynchronize(c->stream));
+    if (c->read_stream) CK(c, cudaStreamSynchronize(c->read_stream));  // read-backs of earlier fgl_frame_end calls
     if (c->async_pending) {
         c->async_pending = false;
         const DrawCounters hc = *c->host_counters;
@@ -1213,16 +1229,50 @@ int fgl_frame_end(fgl_ctx *c, uint8_t *color_dst, size_t stride, fgl_fence **fen
         return fail(c, FGL_E_INVALID, "fence belongs to another device");
     }
     fb_join(c);
-    if (color_dst) {
-        if (stride == (size_t)c->w * 4)  // tightly packed: one linear copy (the 2-D form goes row by row)
-            CK(c, cudaMemcpyAsync(color_dst, c->color, (size_t)c->w * 4 * c->h, cudaMemcpyDeviceToHost, c->stream));
-        else
-            CK(c, cudaMemcpy2DAsync(color_dst, stride, c->color, (size_t)c->w * 4, (size_t)c->w * 4, c->h,
-                                    cudaMemcpyDeviceToHost, c->stream));
+    // Overlapped read-back: stage the frame on the device, send it to the host from the read stream.  The first use
+    // creates the stream, two staging slots and their events; if that fails the frame is read back on the draw stream.
+    const size_t row_bytes = (size_t)c->w * 4, fb_bytes = row_bytes * c->h;
+    int slot = -1;
+    if (c->rb_overlap) {
+        slot = c->rb_next;
+        cudaError_t e = cudaSuccess;
+        if (!c->read_stream) e = cudaStreamCreateWithFlags(&c->read_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess && !c->ev_rb_staged[slot]) e = cudaEventCreateWithFlags(&c->ev_rb_staged[slot], cudaEventDisableTiming);
+        if (e == cudaSuccess && !c->ev_rb_done[slot]) e = cudaEventCreateWithFlags(&c->ev_rb_done[slot], cudaEventDisableTiming);
+        if (e == cudaSuccess && !c->rb_counters[slot]) e = dev_alloc(&c->rb_counters[slot], 1);
+        if (e == cudaSuccess && color_dst && !c->rb_color[slot]) e = dev_alloc(&c->rb_color[slot], (size_t)c->w * c->h);
+        if (e != cudaSuccess) { cudaGetLastError(); slot = -1; c->rb_overlap = false; }
     }
-    CK(c, cudaMemcpyAsync(f->counters, c->acc_dev, sizeof(DrawCounters), cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaMemsetAsync(c->acc_dev, 0, sizeof(DrawCounters), c->stream));
-    CK(c, cudaEventRecord(f->done, c->stream));
+    if (slot >= 0) {
+        c->rb_next = slot ^ 1;
+        if (c->rb_done_recorded[slot]) CK(c, cudaStreamWaitEvent(c->stream, c->ev_rb_done[slot], 0));  // the slot's last transfer
+        if (color_dst) CK(c, cudaMemcpyAsync(c->rb_color[slot], c->color, fb_bytes, cudaMemcpyDeviceToDevice, c->stream));
+        CK(c, cudaMemcpyAsync(c->rb_counters[slot], c->acc_dev, sizeof(DrawCounters), cudaMemcpyDeviceToDevice, c->stream));
+        CK(c, cudaMemsetAsync(c->acc_dev, 0, sizeof(DrawCounters), c->stream));
+        CK(c, cudaEventRecord(c->ev_rb_staged[slot], c->stream));
+        CK(c, cudaStreamWaitEvent(c->read_stream, c->ev_rb_staged[slot], 0));
+        if (color_dst) {
+            if (stride == row_bytes)  // tightly packed: one linear copy (the 2-D form goes row by row)
+                CK(c, cudaMemcpyAsync(color_dst, c->rb_color[slot], fb_bytes, cudaMemcpyDeviceToHost, c->read_stream));
+            else
+                CK(c, cudaMemcpy2DAsync(color_dst, stride, c->rb_color[slot], row_bytes, row_bytes, c->h, cudaMemcpyDeviceToHost,
+                                        c->read_stream));
+        }
+        CK(c, cudaMemcpyAsync(f->counters, c->rb_counters[slot], sizeof(DrawCounters), cudaMemcpyDeviceToHost, c->read_stream));
+        CK(c, cudaEventRecord(c->ev_rb_done[slot], c->read_stream));
+        c->rb_done_recorded[slot] = true;
+        CK(c, cudaEventRecord(f->done, c->read_stream));
+    } else {
+        if (color_dst) {
+            if (stride == row_bytes)
+                CK(c, cudaMemcpyAsync(color_dst, c->color, fb_bytes, cudaMemcpyDeviceToHost, c->stream));
+            else
+                CK(c, cudaMemcpy2DAsync(color_dst, stride, c->color, row_bytes, row_bytes, c->h, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CK(c, cudaMemcpyAsync(f->counters, c->acc_dev, sizeof(DrawCounters), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaMemsetAsync(c->acc_dev, 0, sizeof(DrawCounters), c->stream));
+        CK(c, cudaEventRecord(f->done, c->stream));
+    }
     f->recorded = true;
     c->async_pending = false;
     return FGL_OK;

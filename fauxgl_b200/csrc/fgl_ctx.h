@@ -58,6 +58,15 @@ struct fgl_ctx {
     // Clears run on a stream of their own: the front end of the next draw touches no framebuffer, so the clear
     // of a frame overlaps its k_front instead of preceding it (fb_clear_begin / fb_clear_end / fb_join below).
     cudaStream_t fb_stream;
+    // Frame read-back (fgl_frame_end): the colour buffer and the frame's counters are copied into one of two staging
+    // slots on the draw stream (device to device, a few microseconds) and go to the host on a stream of their own, so
+    // that the PCIe transfer of frame k overlaps the draw of frame k + 1 instead of holding the framebuffer.
+    cudaStream_t read_stream;
+    uint32_t *rb_color[2];
+    DrawCounters *rb_counters[2];
+    cudaEvent_t ev_rb_staged[2], ev_rb_done[2];
+    bool rb_done_recorded[2], rb_overlap;
+    int rb_next;
     cudaEvent_t ev_fb_free, ev_cleared;
     bool clear_overlap, clear_pending;
     std::mutex mu;

@@ -170,6 +170,45 @@ FGL_DI double edge_fn(V3 a, V3 b, V3 c) {  // context.go:147-149
     return (b.x - c.x) * (a.y - c.y) - (b.y - c.y) * (a.x - c.x);
 }
 
+// Rows and columns of an on-screen box that provably keep no pixel (fused front end, fast path).  The reference
+// walks every row y of [floor(min y), ceil(max y)] and every column of [floor(min x), ceil(max x)]
+// (context.go:155-160, 184-221), although a pixel centre above, below or right of the triangle is never covered: the
+// last row and the last column never are, the first row half of the time -- for the one-to-two-pixel triangles of the
+// benchmark mesh 43 % of the (record, scanline) items.  Skipping them changes nothing only if the reference's
+// FLOATING-POINT test fails there as well, so a row is dropped when that is certain:
+//   exact arithmetic: T the top vertex, d_a, d_b the edges from T, q = p - T with q.y = delta > 0.  The edge
+//   functions u_a, u_b of those edges (positive inside) satisfy |d_b.y| u_a + |d_a.y| u_b = -2 |A| delta, hence
+//   min(u_a, u_b) <= -2 |A| delta / (|d_a.y| + |d_b.y|) <= -|A| delta / H,  H = max y - min y,  A = the area term
+//   edge_fn(s0, s1, s2): SOME edge function is that negative at EVERY pixel of the row (mirrored: bottom, right).
+//   rounding: the reference's values come from edge_fn at (x0 + .5, y0 + .5) and a chain of at most rows + cols + 2
+//   additions of values bounded by 2 B^2, B = the box size + 2: they differ from the exact ones by less than
+//   2^-50 B^2 (B + 8).  E below is 64 times that.
+// A row is dropped when |A| delta / H > 4 E (delta >= 4 E H / |A| + 1e-6, the constant covering the rounding of the
+// comparison itself for coordinates below 2^22); sign(w * ra) = sign(w) sign(ra) then holds without underflow
+// (|w| > E, |ra| >= 2^-48).  Slivers (|A| <= 4 E) and anything non-finite are left alone.  Returns the first row to
+// walk; may clear b.visible.
+FGL_DI int tighten_box(const DrawParams &p, BBox &b, V3 s0, V3 s1, V3 s2, double ra) {
+    const int ys = max(b.y0, 0);
+    if (!b.visible || b.origin || (unsigned)b.x0 >= (unsigned)p.width || (unsigned)b.x1 >= (unsigned)p.width) return b.y0;
+    const double mnx = go_min(s0.x, go_min(s1.x, s2.x)), mny = go_min(s0.y, go_min(s1.y, s2.y));
+    const double mxx = go_max(s0.x, go_max(s1.x, s2.x)), mxy = go_max(s0.y, go_max(s1.y, s2.y));
+    const double B = (double)max(b.x1 - b.x0, b.y1 - b.y0) + 2.0;
+    const double E = 0x1p-44 * B * B * (B + 8.0);
+    const double k = 4.0 * E * fabs(ra);  // 4 E / |A|
+    const double my = k * (mxy - mny) + 1e-6, mx = k * (mxx - mnx) + 1e-6;
+    if (!(k < 0.25) || !(my < 0.25) || !(mx < 0.25)) return ys;  // sliver / NaN: nothing is certain
+    const int ylast = (int)ceil(mxy + my - 0.5) - 1;    // rows y >= ylast + 1:  y + .5 >= max y + my
+    const int yfirst = (int)floor(mny - my - 0.5) + 1;  // rows y <= yfirst - 1: y + .5 <= min y - my
+    const int xlast = (int)ceil(mxx + mx - 0.5) - 1;    // columns x >= xlast + 1: x + .5 >= max x + mx
+    const int cy0 = max(ys, yfirst), cy1 = min(min(b.y1, p.height - 1), ylast);
+    const int cx1 = min(b.x1, xlast);
+    if (cy0 > cy1 || cx1 < b.x0) { b.visible = false; b.rows = b.cols = 0; return ys; }
+    b.x1 = cx1;
+    b.rows = (uint32_t)(cy1 - cy0 + 1);
+    b.cols = box_cols(p, b.x0, b.x1);
+    return cy0;
+}
+
 // Write one record at slot r; its scanlines start at row_off within the block's share of the
 // (record, scanline) item space of the span stage.
 FGL_DI void write_record(const WorkBuffers *wb, uint32_t r, uint32_t row_off, const BBox &b, V3 s0, V3 s1, V3 s2,
@@ -694,19 +733,24 @@ struct __align__(16) SRec {  // a raster record in shared memory: RowSetup + the
 static_assert(sizeof(SRec) == 176, "SRec layout");
 
 // Per-triangle setup of Context.rasterize, context.go:155-181 (the same arithmetic as write_record).
+// ystart > b.y0: the per-row adds of the rows in front of ystart (context.go:275-277) are executed here, once, and
+// the record's chain then starts at ystart -- the same additions in the same order as replaying them in every row.
 FGL_DI void fill_srec(SRec &r, const BBox &b, V3 s0, V3 s1, V3 s2, double w0, double w1, double w2, uint32_t src,
-                      uint32_t flags) {
+                      uint32_t flags, double ra, int ystart) {
     r.s0x = s0.x; r.s0y = s0.y; r.s1x = s1.x; r.s1y = s1.y; r.s2x = s2.x; r.s2y = s2.y;
     r.z0 = s0.z; r.z1 = s1.z; r.z2 = s2.z;
     const V3 pc = b.origin ? v3(-9223372036854775808.0, -9223372036854775808.0, 0) : v3((double)b.x0 + 0.5, (double)b.y0 + 0.5, 0);
-    r.w00 = edge_fn(s1, s2, pc);
-    r.w01 = edge_fn(s2, s0, pc);
-    r.w02 = edge_fn(s0, s1, pc);
+    double w00 = edge_fn(s1, s2, pc), w01 = edge_fn(s2, s0, pc), w02 = edge_fn(s0, s1, pc);
     const double a01 = s1.y - s0.y, a12 = s2.y - s1.y, a20 = s0.y - s2.y;
-    r.ra = 1 / edge_fn(s0, s1, s2);
+    if (ystart > b.y0) {
+        const double b01 = s0.x - s1.x, b12 = s1.x - s2.x, b20 = s2.x - s0.x;  // context.go:168-172
+        for (int yy = b.y0; yy < ystart; yy++) { w00 += b12; w01 += b20; w02 += b01; }
+    }
+    r.w00 = w00; r.w01 = w01; r.w02 = w02;
+    r.ra = ra;
     r.r0 = 1 / w0; r.r1 = 1 / w1; r.r2 = 1 / w2;
     r.ra12 = 1 / a12; r.ra20 = 1 / a20; r.ra01 = 1 / a01;
-    r.x0 = b.x0; r.x1 = b.x1; r.y0 = b.y0; r.rows = b.rows;
+    r.x0 = b.x0; r.x1 = b.x1; r.y0 = max(b.y0, ystart); r.rows = b.rows;
     r.src = src; r.flags = flags | (b.origin ? REC_WRAP : 0u);
 }
 
@@ -722,7 +766,8 @@ struct SmemEmit {
                        uint32_t flags) {
         const BBox b = compute_bbox(p, s0, s1, s2);
         if (!b.visible) return;
-        if (next >= win0 && next < win1) fill_srec(s_rec[next - win0], b, s0, s1, s2, w0, w1, w2, src, flags);
+        if (next >= win0 && next < win1)
+            fill_srec(s_rec[next - win0], b, s0, s1, s2, w0, w1, w2, src, flags, 1 / edge_fn(s0, s1, s2), b.y0);
         next++;
     }
     FGL_DI uint32_t pool_alloc(const FullVertex *v, uint32_t prim) {
@@ -760,6 +805,18 @@ FGL_DI bool surely_culled(const DrawParams &p, const V4 *o) {
 #ifndef FGL_FRONT_MINB
 #define FGL_FRONT_MINB 6
 #endif
+#ifndef FGL_FRONT_CLOCK
+#define FGL_FRONT_CLOCK 0  // tuning aid (variant build, FGL_TILE_CLOCK=1): cycles of warp 0 per phase of a fast block, summed
+                           // into the debug counters behind wb.tile_clock (tools/front_cycles.py)
+#endif
+#if FGL_FRONT_CLOCK
+#define FRONT_TICK(k) do { if (wb.tile_clock && tid == 0) { const long long t_ = clock64(); fc_dt[k] = t_ - fc_t; fc_t = t_; } } while (0)
+#else
+#define FRONT_TICK(k) do { } while (0)
+#endif
+#ifndef FGL_FRONT_TIGHT
+#define FGL_FRONT_TIGHT 1  // drop the rows / columns of a box that provably keep no pixel (tighten_box)
+#endif
 #ifndef FGL_FRONT_PREFETCH
 #define FGL_FRONT_PREFETCH 0
 #endif
@@ -793,6 +850,10 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
 #endif
     if (threadIdx.x == 0) s_region_ready = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if FGL_FRONT_CLOCK
+    long long fc_t = clock64(), fc_dt[6] = {0, 0, 0, 0, 0, 0};
+    const long long fc_t0 = fc_t;
+#endif
     pdl_trigger();  // k_seg_index may be scheduled while the last wave of this grid drains
     const uint32_t vb = blockIdx.x;
     const uint32_t i = vb * FT + tid;
@@ -849,12 +910,20 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                 if (!(p.state.cull != FGL_CULL_NONE && a <= 0)) {
                     const V3 s0 = m_mul_position(p.screen, ndc0), s1 = m_mul_position(p.screen, ndc1),
                              s2 = m_mul_position(p.screen, ndc2);
-                    const BBox bb = compute_bbox(p, s0, s1, s2);
+                    BBox bb = compute_bbox(p, s0, s1, s2);
                     if (bb.visible) {
-                        n = 1;
-                        cells = (unsigned long long)bb.rows * bb.cols;
-                        fill_srec(s_rec[tid], bb, s0, s1, s2, i0 == 0 ? o[0].w : o[2].w, o[1].w, i2 == 2 ? o[2].w : o[0].w,
-                                  prim, vmap3(i0, 1, i2));
+                        const double ra = 1 / edge_fn(s0, s1, s2);  // context.go:163
+#if FGL_FRONT_TIGHT
+                        const int ystart = tighten_box(p, bb, s0, s1, s2, ra);
+#else
+                        const int ystart = bb.y0;
+#endif
+                        if (bb.visible) {
+                            n = 1;
+                            cells = (unsigned long long)bb.rows * bb.cols;
+                            fill_srec(s_rec[tid], bb, s0, s1, s2, i0 == 0 ? o[0].w : o[2].w, o[1].w, i2 == 2 ? o[2].w : o[0].w,
+                                      prim, vmap3(i0, 1, i2), ra, ystart);
+                        }
                     }
                 }
             }
@@ -864,7 +933,9 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             count_general(p, prim, &n, &rows_unused, &cells);
         }
     }
+    FRONT_TICK(0);  // phase 1 of this thread
     const bool general = __syncthreads_or(slow && n > 0) != 0;  // also orders the s_rec writes
+    FRONT_TICK(1);  // waiting for the block's slowest thread
 
     // block-wide exclusive scan of (cells << CELL_SHIFT | records)
     const unsigned long long mine = (cells << CELL_SHIFT) | n;
@@ -949,6 +1020,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             wbase = s_celloff[lo_base] + (my0 - s_rowoff[lo_base]) * box_cols(p, r.x0, r.x1);
         }
         bool have_region = false;
+        FRONT_TICK(2);  // scans, item ranges, the first record lookup
 #if FGL_FRONT_COMPACT
         // Two thirds of the (record, scanline) items of sub-pixel triangles cover nothing, and the run loop and the
         // 128-byte segment store behind them ran with a dozen of 32 lanes.  So the walk is split: every lane first
@@ -1072,6 +1144,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             wrun += chunk_total;
         }
 #endif
+        FRONT_TICK(3);  // the walk of warp 0's items
         // Every warp publishes its own run and leaves: no barrier behind the walk (the block's warps used to wait
         // here for the slowest of the four, then for thread 0's round trip to the block counter -- 15 % of the
         // kernel's stall samples).  k_seg_index adds the runs up itself (group sums + the blocks of its group).
@@ -1087,6 +1160,18 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) covered += __shfl_down_sync(0xffffffffu, covered, o);
         if (lane == 0 && covered) atomicAdd(&wb.counters->total_pixels, covered);  // TotalPixels, context.go:229
+#if FGL_FRONT_CLOCK
+        if (wb.tile_clock && lane == 0) {
+            unsigned long long *dbg = wb.tile_clock + 2 * (size_t)wb.ntiles;
+            if (tid == 0) {
+                FRONT_TICK(4);
+                for (int k = 0; k < 5; k++) atomicAdd(&dbg[k], (unsigned long long)fc_dt[k]);
+                atomicAdd(&dbg[5], 1ull);
+            }
+            atomicAdd(&dbg[6], (unsigned long long)(clock64() - fc_t0));  // lifetime of every warp
+            atomicAdd(&dbg[7], 1ull);
+        }
+#endif
         return;
     } else {
     for (uint32_t win0 = 0; win0 < nrec_blk; win0 += FT) {
