@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfauxgl_b200.so")
-SOURCES = ["fgl_api.cu", "fgl_geom.cu", "fgl_scan_sort.cu", "fgl_span.cu", "fgl_raster.cu", "fgl_post.cu", "fgl_ingest.cu", "fgl_comm.cu"]
+SOURCES = ["fgl_api.cu", "fgl_geom.cu", "fgl_scan_sort.cu", "fgl_span.cu", "fgl_order.cu", "fgl_raster.cu", "fgl_post.cu", "fgl_ingest.cu", "fgl_comm.cu"]
 HEADERS = ["fgl_internal.h", "fgl_ctx.h", "fgl_math.cuh", "fgl_block.cuh", "fgl_shade.cuh", "fgl_walk.cuh", "../../include/fauxgl_b200.h"]
 
 NVCC_FLAGS = [

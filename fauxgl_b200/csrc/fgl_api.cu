@@ -328,12 +328,13 @@ int enqueue_draw(fgl_ctx *c, const DrawParams &p, bool async) {
     }
     if (p.prim_info) cudaMemsetAsync(p.prim_info, 0, sizeof(unsigned long long) * 2 * p.count, c->stream);
     int sorted = 0;
-    if (use_fused_front(c, p)) {
+    const bool fused = use_fused_front(c, p);
+    if (fused) {
         // large draws: geometry and spans in one kernel (the stage timers then read: geometry = k_front alone,
-        // spans = k_seg_index)
+        // spans = k_seg_index -- nothing when k_order does the listing, whose time is then all under `sort`)
         launches += launch_front(p, c->wb, c->counters_clean, c->stream);
         if (ps) cudaEventRecord(ps->e[1], c->stream);
-        launches += launch_seg_index(p, c->wb, c->stream);
+        if (!c->order_coop) launches += launch_seg_index(p, c->wb, c->stream);
         if (ps) cudaEventRecord(ps->e[2], c->stream);
     } else {
         launches += launch_geometry(p, c->wb, c->counters_clean, c->stream);
@@ -341,7 +342,8 @@ int enqueue_draw(fgl_ctx *c, const DrawParams &p, bool async) {
         launches += launch_spans(p, c->wb, &sorted, c->stream);
         if (ps) cudaEventRecord(ps->e[2], c->stream);
     }
-    launches += launch_bin(p, c->wb, &sorted, c->stream);
+    if (c->order_coop) launches += launch_order(p, c->wb, fused, &sorted, c->stream);
+    else launches += launch_bin(p, c->wb, &sorted, c->stream);
     if (ps) cudaEventRecord(ps->e[3], c->stream);
     fb_join(c);  // the front end and the binning ran beside a pending clear; the strips need the framebuffer
     bool accumulated = false;
@@ -649,6 +651,15 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     if (err == cudaSuccess) err = dev_alloc(&c->wb.dirty, (size_t)c->wb.ntiles + 16);
     if (err == cudaSuccess) err = cudaMemsetAsync(c->wb.dirty, 0, (size_t)c->wb.ntiles + 16, c->stream);
     if (err == cudaSuccess) err = dev_alloc(&c->wb.tile_ctl, 1);
+    if (err == cudaSuccess) err = cudaMemsetAsync(c->wb.tile_ctl, 0, sizeof(fgl::TileCtl), c->stream);  // (the barrier words of k_order)
+    {
+        // FGL_ORDER=coop: the order plumbing (k_seg_index + radix passes + k_tile_ranges) as ONE cooperative kernel with
+        // grid-wide barriers (fgl_order.cu).  Bit-identical, but measured SLOWER than the six separate launches (1080p:
+        // 59 vs 53 us, 8K: 203 vs 197 us; four contexts in flight: 0.217 vs 0.175 ms per frame, a gang-scheduled grid
+        // with one 1024-thread CTA per SM cannot overlap other streams): off by default, kept as a tuning variant.
+        const char *om = getenv("FGL_ORDER");
+        c->order_coop = om && strcmp(om, "coop") == 0 && fgl::order_supported(device, c->wb.nsm);
+    }
     if (err == cudaSuccess && getenv("FGL_TILE_CLOCK")) {  // tuning aid: per-tile cycle counts of k_tile
         err = dev_alloc(&c->wb.tile_clock, (size_t)c->wb.ntiles * 2 + 16);  // + 16 path counters of k_strip
         if (err == cudaSuccess) err = cudaMemset(c->wb.tile_clock, 0, sizeof(unsigned long long) * ((size_t)c->wb.ntiles * 2 + 16));
@@ -865,10 +876,17 @@ int fgl_mesh_update_indexed_async(fgl_ctx *c, fgl_mesh *m, const fgl_indexed_des
     if (d->v) CK(c, cudaMemcpyAsync(m->tab_v, d->v, sizeof(double) * 3 * m->nv, cudaMemcpyHostToDevice, st));
     if (d->vt) CK(c, cudaMemcpyAsync(m->tab_vt, d->vt, sizeof(double) * 3 * m->nvt, cudaMemcpyHostToDevice, st));
     if (d->vn) CK(c, cudaMemcpyAsync(m->tab_vn, d->vn, sizeof(double) * 3 * m->nvn, cudaMemcpyHostToDevice, st));
-    launch_indexed_ingest(m->tab_v, m->tab_vt, m->tab_vn, m->corners, m->tpos, m->tnrm, m->ttex, (uint32_t)m->nt, st);
+    CK(c, cudaEventRecord(m->ev_uploaded, st));  // (fgl_mesh_upload_wait: the host tables may be reused)
+    // The expansion runs on the DRAW stream, behind the upload and, the stream being in order, behind every draw that
+    // still reads the planes: the copy stream carries nothing but PCIe transfers, so the tables of the next frame (another
+    // mesh) follow this frame's without a gap.  The texture planes are rewritten only when vt was sent.
+    CK(c, cudaStreamWaitEvent(c->stream, m->ev_uploaded, 0));
+    launch_indexed_ingest(m->tab_v, m->tab_vt, m->tab_vn, m->corners, m->tpos, m->tnrm, d->vt ? m->ttex : nullptr, (uint32_t)m->nt,
+                          c->stream);
     CK(c, cudaGetLastError());
-    CK(c, cudaEventRecord(m->ev_uploaded, st));
-    m->upload_pending = true;
+    CK(c, cudaEventRecord(m->ev_drawn, c->stream));  // the tables and the planes are in use up to here
+    m->drawn_recorded = true;
+    m->upload_pending = false;
     return FGL_OK;
 }
 

@@ -53,6 +53,7 @@ struct fgl_ctx {
     int w, h;
     int tile_w;                        // strip width of this context: 32 or 64 (fgl_internal.h)
     int front_mode;                    // 0 auto, 1 fused front end always, 2 split stages always (FGL_FRONT)
+    bool order_coop;                   // the order plumbing as one cooperative kernel (fgl_order.cu); FGL_ORDER=split: separate kernels
     cudaStream_t stream;
     cudaStream_t copy_stream;          // H2D of streaming mesh uploads, overlapping the draw stream
     // Clears run on a stream of their own: the front end of the next draw touches no framebuffer, so the clear

@@ -112,12 +112,17 @@ FGL_DI uint32_t box_cols(const DrawParams &p, int32_t x0, int32_t x1) {
 }
 
 // Integer bounding box of a screen triangle, context.go:155-160, and its on-screen scanlines.
-struct BBox { int32_t x0, x1, y0, y1; bool visible; uint32_t rows, cols; bool origin; };  // cols: strips a row can touch
+struct BBox {
+    int32_t x0, x1, y0, y1; bool visible; uint32_t rows, cols; bool origin;  // cols: strips a row can touch
+    double mnx, mny, mxx, mxy, fy0, fx1, fy1;  // the extremes and their floor / ceil as float64 (tighten_box)
+};
 FGL_DI BBox compute_bbox(const DrawParams &p, V3 s0, V3 s1, V3 s2) {
     BBox b;
     const double mnx = go_min(s0.x, go_min(s1.x, s2.x)), mny = go_min(s0.y, go_min(s1.y, s2.y));
     const double mxx = go_max(s0.x, go_max(s1.x, s2.x)), mxy = go_max(s0.y, go_max(s1.y, s2.y));
-    const long long ix0 = go_int(floor(mnx)), ix1 = go_int(ceil(mxx)), iy0 = go_int(floor(mny)), iy1 = go_int(ceil(mxy));
+    b.mnx = mnx; b.mny = mny; b.mxx = mxx; b.mxy = mxy;
+    b.fy0 = floor(mny); b.fx1 = ceil(mxx); b.fy1 = ceil(mxy);
+    const long long ix0 = go_int(floor(mnx)), ix1 = go_int(b.fx1), iy0 = go_int(b.fy0), iy1 = go_int(b.fy1);
     b.x0 = sat_i32(ix0);
     b.x1 = sat_i32(ix1);
     b.y0 = sat_i32(iy0);
@@ -185,27 +190,29 @@ FGL_DI double edge_fn(V3 a, V3 b, V3 c) {  // context.go:147-149
 //   2^-50 B^2 (B + 8).  E below is 64 times that.
 // A row is dropped when |A| delta / H > 4 E (delta >= 4 E H / |A| + 1e-6, the constant covering the rounding of the
 // comparison itself for coordinates below 2^22); sign(w * ra) = sign(w) sign(ra) then holds without underflow
-// (|w| > E, |ra| >= 2^-48).  Slivers (|A| <= 4 E) and anything non-finite are left alone.  Returns the first row to
-// walk; may clear b.visible.
-FGL_DI int tighten_box(const DrawParams &p, BBox &b, V3 s0, V3 s1, V3 s2, double ra) {
-    const int ys = max(b.y0, 0);
+// (|w| > E, |ra| >= 2^-48).  Slivers (|A| <= 16 E) and anything non-finite are left alone.
+// Written without branches or float <-> integer conversions (the floor / ceil values of compute_bbox are reused), so
+// that it schedules between the seven divisions of the set-up.  Returns the first row to walk; may clear b.visible.
+FGL_DI int tighten_box(const DrawParams &p, BBox &b, double ra) {
     if (!b.visible || b.origin || (unsigned)b.x0 >= (unsigned)p.width || (unsigned)b.x1 >= (unsigned)p.width) return b.y0;
-    const double mnx = go_min(s0.x, go_min(s1.x, s2.x)), mny = go_min(s0.y, go_min(s1.y, s2.y));
-    const double mxx = go_max(s0.x, go_max(s1.x, s2.x)), mxy = go_max(s0.y, go_max(s1.y, s2.y));
-    const double B = (double)max(b.x1 - b.x0, b.y1 - b.y0) + 2.0;
+    const double hx = b.mxx - b.mnx, hy = b.mxy - b.mny;
+    const double B = fmax(hx, hy) + 4.0;   // >= max(x1 - x0, y1 - y0) + 2
     const double E = 0x1p-44 * B * B * (B + 8.0);
-    const double k = 4.0 * E * fabs(ra);  // 4 E / |A|
-    const double my = k * (mxy - mny) + 1e-6, mx = k * (mxx - mnx) + 1e-6;
-    if (!(k < 0.25) || !(my < 0.25) || !(mx < 0.25)) return ys;  // sliver / NaN: nothing is certain
-    const int ylast = (int)ceil(mxy + my - 0.5) - 1;    // rows y >= ylast + 1:  y + .5 >= max y + my
-    const int yfirst = (int)floor(mny - my - 0.5) + 1;  // rows y <= yfirst - 1: y + .5 <= min y - my
-    const int xlast = (int)ceil(mxx + mx - 0.5) - 1;    // columns x >= xlast + 1: x + .5 >= max x + mx
-    const int cy0 = max(ys, yfirst), cy1 = min(min(b.y1, p.height - 1), ylast);
-    const int cx1 = min(b.x1, xlast);
-    if (cy0 > cy1 || cx1 < b.x0) { b.visible = false; b.rows = b.cols = 0; return ys; }
-    b.x1 = cx1;
-    b.rows = (uint32_t)(cy1 - cy0 + 1);
-    b.cols = box_cols(p, b.x0, b.x1);
+    const double k = 4.0 * E * fabs(ra);   // 4 E / |A|
+    const double my = k * hy + 1e-6, mx = k * hx + 1e-6;
+    const bool sure = k < 0.25 && my < 0.25 && mx < 0.25;  // (false for NaN)
+    // first row y0 = floor(min y): dropped when y0 + .5 <= min y - my
+    const int drop_first = (sure && b.mny - b.fy0 >= 0.5 + my) ? 1 : 0;
+    // last row y1 = ceil(max y): y1 + .5 >= max y + my always (my < .25); the row before it when y1 - .5 >= max y + my
+    const int drop_last = sure ? ((b.fy1 - b.mxy >= 0.5 + my) ? 2 : 1) : 0;
+    const int drop_right = sure ? ((b.fx1 - b.mxx >= 0.5 + mx) ? 2 : 1) : 0;
+    const int cy0 = max(max(b.y0, 0), b.y0 + drop_first), cy1 = min(min(b.y1, p.height - 1), b.y1 - drop_last);
+    const int cx1 = b.x1 - drop_right;  // (b.x1 < width)
+    const bool keep = cy0 <= cy1 && cx1 >= b.x0;
+    b.visible = keep;
+    b.x1 = keep ? cx1 : b.x1;
+    b.rows = keep ? (uint32_t)(cy1 - cy0 + 1) : 0u;
+    b.cols = keep ? (uint32_t)((cx1 >> p.tile_shift) - (b.x0 >> p.tile_shift) + 1) : 0u;
     return cy0;
 }
 
@@ -712,11 +719,7 @@ k_rec_index(const __grid_constant__ WorkBuffers wb, uint32_t nblocks) {
 // known after the geometry phase) and fills it from the front in (primitive, scanline, column) order; regions
 // are in block-arrival order.  Every block publishes its exact segment count, the last block to finish scans
 // the counts, and k_seg_index lists the segments in primitive order for the stable sort by strip.
-#ifndef FGL_FRONT_FT
-#define FGL_FRONT_FT 128
-#endif
-constexpr int FT = FGL_FRONT_FT;
-constexpr uint32_t FRONT_GROUP = 64;  // front-end blocks per group sum (wb.blk_base[g], added up by k_seg_index)
+constexpr int FT = FRONT_FT;  // (fgl_internal.h, with FRONT_GROUP: front-end blocks per group sum)
 constexpr unsigned long long CELL_SHIFT = 24, NREC_MASK = (1ull << CELL_SHIFT) - 1ull;
 static_assert(FT * 64 < (1 << CELL_SHIFT), "records of one block fit the low bits of its aggregate");
 static_assert((FT & (FT - 1)) == 0, "the item -> record search halves a power of two");
@@ -735,21 +738,29 @@ static_assert(sizeof(SRec) == 176, "SRec layout");
 // Per-triangle setup of Context.rasterize, context.go:155-181 (the same arithmetic as write_record).
 // ystart > b.y0: the per-row adds of the rows in front of ystart (context.go:275-277) are executed here, once, and
 // the record's chain then starts at ystart -- the same additions in the same order as replaying them in every row.
-FGL_DI void fill_srec(SRec &r, const BBox &b, V3 s0, V3 s1, V3 s2, double w0, double w1, double w2, uint32_t src,
-                      uint32_t flags, double ra, int ystart) {
+struct SetupRcp { double ra, r0, r1, r2, ra12, ra20, ra01; };  // the seven divisions of context.go:163-181
+FGL_DI SetupRcp setup_rcp(V3 s0, V3 s1, V3 s2, double w0, double w1, double w2) {
+    SetupRcp q;
+    const double a01 = s1.y - s0.y, a12 = s2.y - s1.y, a20 = s0.y - s2.y;
+    q.ra = 1 / edge_fn(s0, s1, s2);
+    q.r0 = 1 / w0; q.r1 = 1 / w1; q.r2 = 1 / w2;
+    q.ra12 = 1 / a12; q.ra20 = 1 / a20; q.ra01 = 1 / a01;
+    return q;
+}
+FGL_DI void fill_srec(SRec &r, const BBox &b, V3 s0, V3 s1, V3 s2, uint32_t src, uint32_t flags, const SetupRcp &q,
+                      int ystart) {
     r.s0x = s0.x; r.s0y = s0.y; r.s1x = s1.x; r.s1y = s1.y; r.s2x = s2.x; r.s2y = s2.y;
     r.z0 = s0.z; r.z1 = s1.z; r.z2 = s2.z;
     const V3 pc = b.origin ? v3(-9223372036854775808.0, -9223372036854775808.0, 0) : v3((double)b.x0 + 0.5, (double)b.y0 + 0.5, 0);
     double w00 = edge_fn(s1, s2, pc), w01 = edge_fn(s2, s0, pc), w02 = edge_fn(s0, s1, pc);
-    const double a01 = s1.y - s0.y, a12 = s2.y - s1.y, a20 = s0.y - s2.y;
     if (ystart > b.y0) {
         const double b01 = s0.x - s1.x, b12 = s1.x - s2.x, b20 = s2.x - s0.x;  // context.go:168-172
         for (int yy = b.y0; yy < ystart; yy++) { w00 += b12; w01 += b20; w02 += b01; }
     }
     r.w00 = w00; r.w01 = w01; r.w02 = w02;
-    r.ra = ra;
-    r.r0 = 1 / w0; r.r1 = 1 / w1; r.r2 = 1 / w2;
-    r.ra12 = 1 / a12; r.ra20 = 1 / a20; r.ra01 = 1 / a01;
+    r.ra = q.ra;
+    r.r0 = q.r0; r.r1 = q.r1; r.r2 = q.r2;
+    r.ra12 = q.ra12; r.ra20 = q.ra20; r.ra01 = q.ra01;
     r.x0 = b.x0; r.x1 = b.x1; r.y0 = max(b.y0, ystart); r.rows = b.rows;
     r.src = src; r.flags = flags | (b.origin ? REC_WRAP : 0u);
 }
@@ -767,7 +778,7 @@ struct SmemEmit {
         const BBox b = compute_bbox(p, s0, s1, s2);
         if (!b.visible) return;
         if (next >= win0 && next < win1)
-            fill_srec(s_rec[next - win0], b, s0, s1, s2, w0, w1, w2, src, flags, 1 / edge_fn(s0, s1, s2), b.y0);
+            fill_srec(s_rec[next - win0], b, s0, s1, s2, src, flags, setup_rcp(s0, s1, s2, w0, w1, w2), b.y0);
         next++;
     }
     FGL_DI uint32_t pool_alloc(const FullVertex *v, uint32_t prim) {
@@ -838,7 +849,8 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     __shared__ SRec s_rec[FT];
     __shared__ uint32_t s_rowoff[FT + 1];
     __shared__ uint16_t s_order[FT];
-    __shared__ unsigned long long s_scan[FT / 32 + 1];
+    __shared__ unsigned long long s_scan[FT / 32];
+    __shared__ uint32_t s_scanr[FT / 32];
     __shared__ uint32_t s_scan32[2][FT / 32];
     uint32_t scan_parity = 0;
     __shared__ unsigned long long s_region;
@@ -874,7 +886,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     // Fast path: a triangle entirely inside the view volume, not in wireframe mode, yields at most one
     // record, set up straight into this thread's shared-memory slot.  Lines, wireframe and triangles
     // that need clipping are only counted here (out-of-line general path).
-    uint32_t n = 0;
+    uint32_t n = 0, frows = 0;  // frows: scanlines of this thread's fast-path record
     unsigned long long cells = 0;
     bool slow = false;
     if (i < p.count) {
@@ -912,17 +924,18 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                              s2 = m_mul_position(p.screen, ndc2);
                     BBox bb = compute_bbox(p, s0, s1, s2);
                     if (bb.visible) {
-                        const double ra = 1 / edge_fn(s0, s1, s2);  // context.go:163
+                        // the seven divisions of the set-up first: the tightening below schedules between them
+                        const SetupRcp q = setup_rcp(s0, s1, s2, i0 == 0 ? o[0].w : o[2].w, o[1].w, i2 == 2 ? o[2].w : o[0].w);
 #if FGL_FRONT_TIGHT
-                        const int ystart = tighten_box(p, bb, s0, s1, s2, ra);
+                        const int ystart = tighten_box(p, bb, q.ra);
 #else
                         const int ystart = bb.y0;
 #endif
                         if (bb.visible) {
                             n = 1;
+                            frows = bb.rows;
                             cells = (unsigned long long)bb.rows * bb.cols;
-                            fill_srec(s_rec[tid], bb, s0, s1, s2, i0 == 0 ? o[0].w : o[2].w, o[1].w, i2 == 2 ? o[2].w : o[0].w,
-                                      prim, vmap3(i0, 1, i2), ra, ystart);
+                            fill_srec(s_rec[tid], bb, s0, s1, s2, prim, vmap3(i0, 1, i2), q, ystart);
                         }
                     }
                 }
@@ -934,40 +947,45 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         }
     }
     FRONT_TICK(0);  // phase 1 of this thread
-    const bool general = __syncthreads_or(slow && n > 0) != 0;  // also orders the s_rec writes
-    FRONT_TICK(1);  // waiting for the block's slowest thread
-
-    // block-wide exclusive scan of (cells << CELL_SHIFT | records)
+    // Block-wide exclusive scans of (cells << CELL_SHIFT | records) and of the rows of the fast-path records, with ONE
+    // barrier: the one that tells whether the block needs the general path and orders the s_rec writes.  (Six barriers
+    // -- or-reduction, a two-level scan, the order table, a second scan for the rows -- used to separate the geometry
+    // from the walk: 4 000 of a block's 21 700 cycles, tools/front_cycles.py.)
     const unsigned long long mine = (cells << CELL_SHIFT) | n;
     unsigned long long incl = mine;
+    uint32_t rincl = frows;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        const uint32_t tr = __shfl_up_sync(0xffffffffu, rincl, o);
+        if (lane >= o) { incl += t; rincl += tr; }
     }
-    if (lane == 31) s_scan[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long v = lane < FT / 32 ? s_scan[lane] : 0, vi = v;
+    if (lane == 31) { s_scan[warp] = incl; s_scanr[warp] = rincl; }
+    const bool general = __syncthreads_or(slow && n > 0) != 0;
+    FRONT_TICK(1);  // waiting for the block's slowest thread
+    unsigned long long excl = incl - mine, block_total = 0;
+    uint32_t rexcl = rincl - frows, items_all = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, vi, o);
-            if (lane >= o) vi += t;
-        }
-        if (lane < FT / 32) s_scan[lane] = vi - v;
-        if (lane == FT / 32 - 1) s_scan[FT / 32] = vi;
+    for (int w = 0; w < FT / 32; w++) {
+        const unsigned long long t = s_scan[w];
+        const uint32_t tr = s_scanr[w];
+        if (w < warp) { excl += t; rexcl += tr; }
+        block_total += t; items_all += tr;
     }
-    __syncthreads();
-    const uint32_t rec_off = (uint32_t)((s_scan[warp] + incl - mine) & NREC_MASK);
-    const unsigned long long block_total = s_scan[FT / 32];
+    const uint32_t rec_off = (uint32_t)(excl & NREC_MASK);
     const uint32_t nrec_blk = (uint32_t)(block_total & NREC_MASK);
     // The reservation's round trip is not waited for here: thread 0 keeps the old cursor in a register and hands it
     // to the block just before the first compaction barrier below, a scan and a row walk later.
     unsigned long long my_region = 0;
     if (tid == 0 && nrec_blk) my_region = atomicAdd(&wb.counters->seg_cursor, block_total >> CELL_SHIFT);
-    if (!general && n == 1) {
-        s_order[rec_off] = (uint16_t)tid;
-        s_celloff[rec_off] = (uint32_t)((s_scan[warp] + incl - mine) >> CELL_SHIFT);
+    if (!general) {
+        if (n == 1) {  // compacted record rec_off: its thread, the cells and the (record, scanline) items before it
+            s_order[rec_off] = (uint16_t)tid;
+            s_celloff[rec_off] = (uint32_t)(excl >> CELL_SHIFT);
+            s_rowoff[rec_off] = rexcl;
+        }
+        if (tid >= (int)nrec_blk) s_rowoff[tid] = items_all;
+        if (tid == 0) s_rowoff[FT] = items_all;
     }
     __syncthreads();
     unsigned long long region = 0;
@@ -984,14 +1002,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         // with -- so the warps never wait for each other's counts (the block scan per 128 items and its barrier
         // were 9 % of the kernel's stall samples).  Inside the region the warps' runs are in primitive order but
         // not contiguous; k_seg_index closes the gaps (blk_wcnt / blk_woff).
-        uint32_t items;
-        {
-            const uint32_t rows = tid < (int)nrec_blk ? s_rec[s_order[tid]].rows : 0u;
-            const uint32_t ex = block_excl_scan1<FT>(rows, s_scan32, scan_parity, &items);
-            s_rowoff[tid] = ex;
-            if (tid == 0) s_rowoff[FT] = items;
-            __syncthreads();
-        }
+        const uint32_t items = items_all;
         // Hand the reservation to the block: a release store of the flag after the value, acquire loads in the
         // readers (message passing without a barrier -- compute-sanitizer's racecheck reports exactly this pair).
         // Warp 0 absorbs what is left of the atomic's round trip; the other warps look only after their first walk.
@@ -1000,12 +1011,13 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             s_region = my_region;
             asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(flag_addr), "r"(1u) : "memory");
         }
-        auto locate = [&](uint32_t it) {  // the last entry with s_rowoff[lo] <= it (entries >= nrec_blk hold `items`)
-            uint32_t lo = 0;
+        // the last entry with s_rowoff[lo] <= it (it < items, warp-uniform; entries >= nrec_blk hold `items`): the table
+        // is sorted and starts at 0, so lo = (entries <= it) - 1 -- four independent loads per lane and one reduction
+        auto locate = [&](uint32_t it) {
+            uint32_t cnt = 0;
 #pragma unroll
-            for (uint32_t step = FT / 2; step > 0; step >>= 1)
-                if (s_rowoff[lo + step] <= it) lo += step;
-            return lo;
+            for (int j = 0; j < FT / 32; j++) cnt += s_rowoff[lane + 32 * j] <= it ? 1u : 0u;
+            return __reduce_add_sync(0xffffffffu, cnt) - 1u;
         };
         const uint32_t ipw = (((items + FT / 32 - 1) / (FT / 32)) + 31u) & ~31u;
         const uint32_t my0 = min((uint32_t)warp * ipw, items), my1 = min(my0 + ipw, items);

@@ -162,7 +162,7 @@ k_indexed_ingest(const double *__restrict__ tv, const double *__restrict__ tvt, 
             const int32_t *c = corners + ((size_t)i * 3 + v) * 3;
             const double *a = tv + (size_t)c[0] * 3, *b = tvt + (size_t)c[1] * 3, *d = tvn + (size_t)c[2] * 3;
             p[v] = v3(a[0], a[1], a[2]);
-            uv[v][0] = b[0]; uv[v][1] = b[1];
+            uv[v][0] = tex ? b[0] : 0.0; uv[v][1] = tex ? b[1] : 0.0;
             nn[v] = v3(d[0], d[1], d[2]);
         }
         const V3 face = v_normalize(v_cross(v_sub(p[1], p[0]), v_sub(p[2], p[0])));
@@ -175,8 +175,10 @@ k_indexed_ingest(const double *__restrict__ tv, const double *__restrict__ tvt, 
             nrm[(size_t)(v * 3 + 0) * n + i] = nn[v].x;
             nrm[(size_t)(v * 3 + 1) * n + i] = nn[v].y;
             nrm[(size_t)(v * 3 + 2) * n + i] = nn[v].z;
-            tex[(size_t)(v * 2 + 0) * n + i] = uv[v][0];
-            tex[(size_t)(v * 2 + 1) * n + i] = uv[v][1];
+            if (tex) {  // (null: the texture planes are up to date)
+                tex[(size_t)(v * 2 + 0) * n + i] = uv[v][0];
+                tex[(size_t)(v * 2 + 1) * n + i] = uv[v][1];
+            }
         }
     }
 }

@@ -106,7 +106,15 @@ static_assert(sizeof(SegV) == 128, "SegV layout");
 struct TileCtl {
     uint32_t nheavy, nlight;  // busy_list[0 .. nheavy) = heavy strips, busy_list[ntiles-1 .. ntiles-nlight] = the others
     uint32_t head, _pad;
+    uint32_t bar_count, bar_gen;  // grid-wide barrier of k_order (fgl_order.cu): arrivals of the round, rounds completed
 };
+// Fused front end (fgl_geom.cu): primitives per k_front block, and blocks per group sum (wb.blk_base[g], added up by
+// k_seg_index / k_order).
+#ifndef FGL_FRONT_FT
+#define FGL_FRONT_FT 128
+#endif
+constexpr int FRONT_FT = FGL_FRONT_FT;
+constexpr uint32_t FRONT_GROUP = 64;
 #ifndef FGL_HEAVY_SEGS
 #define FGL_HEAVY_SEGS 96
 #endif
@@ -263,6 +271,10 @@ int launch_front(const DrawParams &p, const WorkBuffers &wb, bool counters_clean
 int launch_seg_index(const DrawParams &p, const WorkBuffers &wb, cudaStream_t st);
 int launch_spans(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
 int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cudaStream_t st);
+// launch_seg_index (fused front end) + launch_bin as ONE cooperative kernel with grid-wide barriers (fgl_order.cu);
+// order_supported: the device can run it (cooperative launch, one 1024-thread CTA per SM)
+bool order_supported(int device, uint32_t nsm);
+int launch_order(const DrawParams &p, const WorkBuffers &wb, bool fused, int *sorted_buf, cudaStream_t st);
 // acc (nullable): counters of the frame's async draws; *accumulated tells whether the draw's counters were added
 // to it by the last kernel (k_shade's last CTA) -- otherwise the caller launches k_accumulate
 int launch_raster(const DrawParams &p, const WorkBuffers &wb, int sorted_buf, uint32_t *color, double *depth,

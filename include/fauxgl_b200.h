@@ -172,8 +172,8 @@ typedef struct fgl_indexed_desc {
 int fgl_mesh_create_indexed(fgl_ctx *ctx, const fgl_indexed_desc *desc, fgl_mesh **out);
 /* Re-pose an indexed mesh (a host loop like examples/animate.go:66, which transforms the mesh every frame): the
  * corner indices stayed on the device, only the v / vt / vn tables given (NULL = unchanged; sizes as at creation;
- * desc->corners is ignored) are copied again -- on the context's copy stream, like fgl_mesh_update_async, with the
- * same hand-over to the draw stream -- and expanded into the planes there.  For the 871 306-triangle benchmark mesh
+ * desc->corners is ignored) are copied again on the context's copy stream, which carries nothing else, and expanded
+ * into the planes on the draw stream, in order behind the draws that still read them.  For the 871 306-triangle benchmark mesh
  * (436 k shared vertices) that is 21 MB per frame instead of 125 MB of expanded position + normal soup.  The host
  * arrays (pinned memory for a real overlap) must stay unchanged until fgl_mesh_upload_wait returns. */
 int fgl_mesh_update_indexed_async(fgl_ctx *ctx, fgl_mesh *mesh, const fgl_indexed_desc *desc);
