@@ -15,7 +15,7 @@
 
 using namespace fgl;
 
-namespace fgl { bool g_pdl = true; }
+namespace fgl { bool g_pdl = true; bool g_bin_buckets = true; }
 
 namespace {
 
@@ -623,6 +623,8 @@ int fgl_context_create(int width, int height, int device, fgl_ctx **out) {
     {
         const char *pd = getenv("FGL_PDL");  // tuning aid: 0 launches every kernel fully serialised
         fgl::g_pdl = !(pd && atoi(pd) == 0);
+        const char *bn = getenv("FGL_BIN");  // tuning aid: lsd = every radix pass global + k_tile_ranges (fgl_scan_sort.cu)
+        fgl::g_bin_buckets = !(bn && strcmp(bn, "lsd") == 0);
     }
     {
         const char *co = getenv("FGL_CLEAR_OVERLAP");  // tuning aid: 0 keeps the clears on the draw stream

@@ -1169,8 +1169,12 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                 if (nrec_blk) atomicAdd(&wb.counters->n_records, nrec_blk);
             }
         }
+        if (!__any_sync(0xffffffffu, (covered >> 27) != 0ull)) {  // (always, short of absurd rows) one 32-bit reduction
+            covered = (unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)covered);
+        } else {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) covered += __shfl_down_sync(0xffffffffu, covered, o);
+            for (int o = 16; o > 0; o >>= 1) covered += __shfl_down_sync(0xffffffffu, covered, o);
+        }
         if (lane == 0 && covered) atomicAdd(&wb.counters->total_pixels, covered);  // TotalPixels, context.go:229
 #if FGL_FRONT_CLOCK
         if (wb.tile_clock && lane == 0) {

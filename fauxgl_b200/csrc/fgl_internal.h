@@ -263,6 +263,13 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n_max, con
 int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsigned int *n_dev, uint32_t n_max,
                       int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st, const unsigned int *skip_if = nullptr);
 
+// Binning by strip for 8 < bits <= 16: one global radix pass on the top eight bits, then one CTA per bucket orders its
+// pairs by the remaining bits and lists its busy strips (fgl_scan_sort.cu).  g_bin_buckets: FGL_BIN=lsd turns it off.
+extern bool g_bin_buckets;
+int launch_bin_buckets(uint32_t *const key[2], uint32_t *const val[2], DrawCounters *ctr, uint32_t n_max, int bits,
+                       uint32_t *tmp, int *sorted_buf, uint2 *busy_list, uint32_t ntiles, TileCtl *ctl,
+                       unsigned long long *group_sums, uint32_t ngroups, cudaStream_t st);
+
 // counters_clean: the previous draw's last kernel left the draw counters zeroed (no memset node needed)
 int launch_geometry(const DrawParams &p, const WorkBuffers &wb, bool counters_clean, cudaStream_t st);
 // fused geometry + span stage of large draws: k_front, then k_seg_index leaves (seg_key[0], seg_val[0]) in

@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(RADIX_THREADS)
 k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                 const unsigned int *__restrict__ n_dev, uint32_t n_max, int shift,
-                const uint32_t *__restrict__ hist /*[grid][BINS], raw counts*/, const unsigned int *__restrict__ skip_if) {
+                const uint32_t *__restrict__ hist /*[grid][BINS], raw counts*/, const unsigned int *__restrict__ skip_if,
+                uint32_t *__restrict__ bucket_start /*[BINS + 1] or null: where each digit's run begins in the output*/) {
     constexpr int BINS = 1 << BITS;
     constexpr int DPT = (BINS + RADIX_THREADS - 1) / RADIX_THREADS;  // digits per thread in the bucket-base scan (1)
     pdl_wait();
@@ -218,6 +219,10 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
         uint32_t total;
         const uint32_t digit_base = block_excl_scan<RADIX_THREADS>(threadIdx.x < BINS ? row : 0u, s_scan, &total);
         if (threadIdx.x < BINS) cursor[d] = digit_base + before;
+        if (bucket_start && blockIdx.x == 0 && threadIdx.x < BINS) {
+            bucket_start[d] = digit_base;
+            if (d == BINS - 1) bucket_start[BINS] = total;
+        }
     }
     __syncthreads();
     const uint32_t n = (skip_if && *skip_if) ? 0u : min(*n_dev, n_max);
@@ -290,15 +295,183 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
 
 template <int BITS>
 static int radix_pass(uint32_t *const key[2], uint32_t *const val[2], int cur, const unsigned int *n_dev, uint32_t n_max,
-                      int shift, uint32_t *tmp, cudaStream_t st, const unsigned int *skip_if) {
+                      int shift, uint32_t *tmp, cudaStream_t st, const unsigned int *skip_if, uint32_t *bucket_start = nullptr) {
     constexpr int BINS = 1 << BITS;
     const size_t smem = sizeof(uint32_t) * (size_t)BINS * (RADIX_WARPS + 1);
     // per device and cheap: set on every call (a process may drive several GPUs)
     cudaFuncSetAttribute(k_radix_scatter<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     launch_pdl(k_radix_hist<BITS>, RADIX_GRID, RADIX_THREADS, 0, st, key[cur], n_dev, n_max, shift, tmp, skip_if);
     launch_pdl(k_radix_scatter<BITS>, RADIX_GRID, RADIX_THREADS, smem, st, key[cur], val[cur], key[cur ^ 1], val[cur ^ 1],
-               n_dev, n_max, shift, (const uint32_t *)tmp, skip_if);
+               n_dev, n_max, shift, (const uint32_t *)tmp, skip_if, bucket_start);
     return 2;
+}
+
+// ---- binning by strip: one global pass on the TOP digit, the rest inside the buckets -----------------------------
+// The strip id has up to 16 bits for framebuffers of up to 65 536 strips (1080p: 64 800): two LSD passes
+// (k_radix_hist + k_radix_scatter each) and k_tile_ranges -- five short, latency-bound launches over a few megabytes.
+// Only the first pass has to be global.  Done on the top eight bits it cuts the pairs into 256 buckets of consecutive
+// strips, each a contiguous run of the output in primitive order; what is left -- ordering a bucket by its low bits,
+// stable -- is local: ONE CTA per bucket counts its low digits in shared memory, derives the bases itself (no
+// [CTA][digit] table, nothing to wait for) and scatters with the same stable ranking.  The histogram IS the bucket's
+// bin table: digit d of bucket b is strip (b << low_bits | d), its bin starts at the digit's base and holds the
+// digit's count, so the busy-strip list (the job of k_tile_ranges) is written from it without another look at the
+// keys.  1080p: 5 launches -> 3.  A bucket is handled by one CTA, so this pays while buckets stay a few tiles long
+// (the bucket of a pole of the benchmark mesh: ~8 k pairs); with more than 16 key bits (8K: 19) the local part would
+// need two passes over buckets of up to 47 k pairs -- measured slower than three global passes (sort stage 262 vs
+// 165 us) -- and the LSD path is kept.
+__global__ void __launch_bounds__(RADIX_THREADS, 2)
+k_bucket_sort(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int low_bits,
+              const uint32_t *__restrict__ bucket_start, DrawCounters *ctr, uint2 *__restrict__ busy_list,
+              uint32_t ntiles, TileCtl *ctl, unsigned long long *__restrict__ group_sums, uint32_t ngroups) {
+    constexpr int BINS = 256;
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t *cursor = s_dyn;                                                     // [BINS]
+    uint32_t(*warp_cnt)[BINS] = reinterpret_cast<uint32_t(*)[BINS]>(s_dyn + BINS);  // [RADIX_WARPS][BINS]
+    __shared__ uint32_t s_scan[RADIX_WARPS + 1];
+    __shared__ uint32_t s_base[2];
+    pdl_wait();
+    pdl_trigger();
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // the group sums of the fused front end are left zeroed for the next draw (also when this one overflowed)
+    if (blockIdx.x == 0)
+        for (uint32_t g = tid; g < ngroups; g += RADIX_THREADS) group_sums[g] = 0ull;
+    if (ctr->overflow) return;  // the draw is going to be re-issued: its keys are incomplete
+    const uint32_t beg = bucket_start[blockIdx.x], end = bucket_start[blockIdx.x + 1];
+    if (beg >= end) return;
+    const uint32_t ltmask = (1u << lane) - 1u;
+    const uint32_t mask = (1u << low_bits) - 1u;  // low_bits <= 8
+    for (int k = tid; k < BINS; k += RADIX_THREADS) cursor[k] = 0;
+    __syncthreads();
+    // count; the first tile stays in registers
+    uint32_t key0r[RADIX_ITEMS], val0r[RADIX_ITEMS];
+    {
+        const uint32_t wbase = beg + warp * (32 * RADIX_ITEMS);
+#pragma unroll
+        for (int r = 0; r < RADIX_ITEMS; r++) {
+            const uint32_t i = wbase + r * 32 + lane;
+            key0r[r] = i < end ? keys_in[i] : 0u;
+            val0r[r] = i < end ? vals_in[i] : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < RADIX_ITEMS; r++) {
+            const uint32_t i = wbase + r * 32 + lane;
+            if (i < end) atomicAdd(&cursor[key0r[r] & mask], 1u);
+        }
+    }
+    for (uint32_t i = beg + RADIX_TILE + tid; i < end; i += RADIX_THREADS) atomicAdd(&cursor[keys_in[i] & mask], 1u);
+    __syncthreads();
+    {   // bases; and the bucket's busy strips straight from the histogram
+        uint32_t total;
+        const uint32_t c = tid < BINS ? cursor[tid] : 0u;
+        const uint32_t ex = block_excl_scan<RADIX_THREADS>(c, s_scan, &total);
+        if (tid < BINS) cursor[tid] = beg + ex;
+        uint32_t mh = 0, ml = 0;
+        if (warp < BINS / 32) {  // (the digits live in the first eight warps)
+            const bool heavy = c >= HEAVY_SEGS, light = c > 0u && !heavy;
+            mh = __ballot_sync(0xffffffffu, heavy);
+            ml = __ballot_sync(0xffffffffu, light);
+            if (lane == 0) { warp_cnt[0][warp] = (uint32_t)__popc(mh); warp_cnt[1][warp] = (uint32_t)__popc(ml); }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t nh = 0, nl = 0;
+            for (int w = 0; w < BINS / 32; w++) { nh += warp_cnt[0][w]; nl += warp_cnt[1][w]; }
+            s_base[0] = nh ? atomicAdd(&ctl->nheavy, nh) : 0u;
+            s_base[1] = nl ? atomicAdd(&ctl->nlight, nl) : 0u;
+        }
+        __syncthreads();
+        if (warp < BINS / 32 && c > 0u) {
+            const bool heavy = c >= HEAVY_SEGS;
+            uint32_t before = 0;
+            for (uint32_t w = 0; w < warp; w++) before += warp_cnt[heavy ? 0 : 1][w];
+            const uint32_t strip = (blockIdx.x << low_bits) | tid;
+            // (a sorted key array has at most ntiles bins; the bound keeps a corrupted one from writing outside the list)
+            if (heavy) {
+                const uint32_t ph = s_base[0] + before + (uint32_t)__popc(mh & ltmask);
+                if (ph < ntiles) busy_list[ph] = make_uint2(strip, beg + ex);
+            } else {
+                const uint32_t pl = s_base[1] + before + (uint32_t)__popc(ml & ltmask);
+                if (pl < ntiles) busy_list[ntiles - 1u - pl] = make_uint2(strip, beg + ex);
+            }
+        }
+        __syncthreads();  // (warp_cnt is reused below)
+    }
+    for (uint32_t base = beg; base < end; base += RADIX_TILE) {
+        for (int k = tid; k < RADIX_WARPS * BINS; k += RADIX_THREADS) (&warp_cnt[0][0])[k] = 0;
+        __syncthreads();
+        uint32_t key[RADIX_ITEMS], val[RADIX_ITEMS], rank[RADIX_ITEMS];
+        bool valid[RADIX_ITEMS];
+        const uint32_t wbase = base + warp * (32 * RADIX_ITEMS);
+#pragma unroll
+        for (int r = 0; r < RADIX_ITEMS; r++) {
+            const uint32_t i = wbase + r * 32 + lane;
+            valid[r] = i < end;
+            if (base == beg) { key[r] = key0r[r]; val[r] = val0r[r]; }
+            else {
+                key[r] = valid[r] ? keys_in[i] : 0u;
+                val[r] = valid[r] ? vals_in[i] : 0u;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RADIX_ITEMS; r++) {
+            const uint32_t d = key[r] & mask;
+            const uint32_t active = __ballot_sync(0xffffffffu, valid[r]);
+            rank[r] = 0;
+            if (valid[r]) {
+                uint32_t peers = active;  // lanes with the same digit, from one ballot per digit bit
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    const uint32_t m = __ballot_sync(active, (d >> b) & 1u);
+                    peers &= ((d >> b) & 1u) ? m : ~m;
+                }
+                const int leader = __ffs(peers) - 1;
+                uint32_t old = 0;
+                if ((int)lane == leader) { old = warp_cnt[warp][d]; warp_cnt[warp][d] = old + __popc(peers); }
+                old = __shfl_sync(peers, old, leader);
+                rank[r] = old + __popc(peers & ltmask);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        uint32_t run = 0;
+        if (tid < BINS) {
+#pragma unroll 8
+            for (int w = 0; w < RADIX_WARPS; w++) {
+                const uint32_t c = warp_cnt[w][tid];
+                warp_cnt[w][tid] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RADIX_ITEMS; r++) {
+            if (valid[r]) {
+                const uint32_t d = key[r] & mask;
+                const uint32_t pos = cursor[d] + warp_cnt[warp][d] + rank[r];
+                keys_out[pos] = key[r];
+                vals_out[pos] = val[r];
+            }
+        }
+        __syncthreads();
+        if (tid < BINS) cursor[tid] += run;
+        __syncthreads();
+    }
+}
+
+// Binning of a draw's segments by strip (8 < bits <= 16): the global pass on the top eight bits, then k_bucket_sort.
+// *sorted_buf = the buffer that holds the sorted pairs.  tmp: [RADIX_GRID][256] histogram + 257 bucket starts.
+int launch_bin_buckets(uint32_t *const key[2], uint32_t *const val[2], DrawCounters *ctr, uint32_t n_max, int bits,
+                       uint32_t *tmp, int *sorted_buf, uint2 *busy_list, uint32_t ntiles, TileCtl *ctl,
+                       unsigned long long *group_sums, uint32_t ngroups, cudaStream_t st) {
+    const int low_bits = bits - 8;
+    uint32_t *bucket_start = tmp + (size_t)RADIX_GRID * 256;
+    int launches = radix_pass<8>(key, val, 0, &ctr->n_segs, n_max, low_bits, tmp, st, &ctr->overflow, bucket_start);
+    const size_t smem = sizeof(uint32_t) * (size_t)256 * (RADIX_WARPS + 1);
+    cudaFuncSetAttribute(k_bucket_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    launch_pdl(k_bucket_sort, 256, RADIX_THREADS, smem, st, (const uint32_t *)key[1], (const uint32_t *)val[1], key[0], val[0],
+               low_bits, (const uint32_t *)bucket_start, ctr, busy_list, ntiles, ctl, group_sums, ngroups);
+    *sorted_buf = 0;
+    return launches + 1;
 }
 
 // Stable LSD radix sort of (key, val) on `bits` key bits.  8-bit digits: measured on the 8K benchmark frame
