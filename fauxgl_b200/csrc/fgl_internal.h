@@ -263,9 +263,11 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n_max, con
 int launch_sort_pairs(uint32_t *const key[2], uint32_t *const val[2], const unsigned int *n_dev, uint32_t n_max,
                       int bits, uint32_t *tmp, int *sorted_buf, cudaStream_t st, const unsigned int *skip_if = nullptr);
 
-// Binning by strip for 8 < bits <= 16: one global radix pass on the top eight bits, then one CTA per bucket orders its
-// pairs by the remaining bits and lists its busy strips (fgl_scan_sort.cu).  g_bin_buckets: FGL_BIN=lsd turns it off.
+// Binning by strip for 8 < bits <= 20: one global radix pass on the low eight bits, then one CTA per bucket groups its
+// pairs by the remaining bits and lists its busy strips (fgl_scan_sort.cu).  The bins come out grouped, not in
+// ascending strip order -- the back end only needs them contiguous.  g_bin_buckets: FGL_BIN=lsd turns it off.
 extern bool g_bin_buckets;
+bool bin_buckets_ok(int bits);
 int launch_bin_buckets(uint32_t *const key[2], uint32_t *const val[2], DrawCounters *ctr, uint32_t n_max, int bits,
                        uint32_t *tmp, int *sorted_buf, uint2 *busy_list, uint32_t ntiles, TileCtl *ctl,
                        unsigned long long *group_sums, uint32_t ngroups, cudaStream_t st);

@@ -306,27 +306,33 @@ static int radix_pass(uint32_t *const key[2], uint32_t *const val[2], int cur, c
     return 2;
 }
 
-// ---- binning by strip: one global pass on the TOP digit, the rest inside the buckets -----------------------------
-// The strip id has up to 16 bits for framebuffers of up to 65 536 strips (1080p: 64 800): two LSD passes
-// (k_radix_hist + k_radix_scatter each) and k_tile_ranges -- five short, latency-bound launches over a few megabytes.
-// Only the first pass has to be global.  Done on the top eight bits it cuts the pairs into 256 buckets of consecutive
-// strips, each a contiguous run of the output in primitive order; what is left -- ordering a bucket by its low bits,
-// stable -- is local: ONE CTA per bucket counts its low digits in shared memory, derives the bases itself (no
-// [CTA][digit] table, nothing to wait for) and scatters with the same stable ranking.  The histogram IS the bucket's
-// bin table: digit d of bucket b is strip (b << low_bits | d), its bin starts at the digit's base and holds the
-// digit's count, so the busy-strip list (the job of k_tile_ranges) is written from it without another look at the
-// keys.  1080p: 5 launches -> 3.  A bucket is handled by one CTA, so this pays while buckets stay a few tiles long
-// (the bucket of a pole of the benchmark mesh: ~8 k pairs); with more than 16 key bits (8K: 19) the local part would
-// need two passes over buckets of up to 47 k pairs -- measured slower than three global passes (sort stage 262 vs
-// 165 us) -- and the LSD path is kept.
+// ---- binning by strip: one global pass, the rest inside the buckets ---------------------------------------------
+// The strip id has 16 bits at 1080p and 19 at 8K: two or three LSD passes (k_radix_hist + k_radix_scatter each) and
+// k_tile_ranges -- five or seven short, latency-bound launches over a few megabytes.  Only ONE pass has to be global,
+// and the back end does not need the strips in ascending order at all: it needs every strip's segments contiguous,
+// in primitive order, and a list of where each such bin begins.  So the global pass is LSD's first -- on the LOW
+// eight bits -- which cuts the pairs into 256 buckets, each a contiguous run of the output in primitive order and,
+// because neighbouring strips fall into different buckets, all about the same size (the pile-up at a pole of the
+// benchmark mesh spreads over all of them; bucketing by the TOP bits was measured first: the pole's bucket alone
+// took 29 k cycles).  What is left -- grouping a bucket by the remaining high bits, stable -- is local: ONE CTA per
+// bucket, eight bits per local pass, ping-ponging through the two global buffers (L2-resident; a CTA reads only what
+// it wrote itself).  Inside the CTA the bucket is cut into 32 contiguous chunks, one per warp: a warp counts the digits
+// of its chunk into a row of its own, ONE sweep over the rows turns them into the absolute position of each
+// (warp, digit) run, and the warp goes over its chunk again placing the pairs -- two block barriers per pass whatever
+// the bucket's length; steps of 32 pairs in chunk order, ranks from one ballot per digit bit: stable.  The histogram
+// of the high bits IS the bucket's bin table (bin of high value h: strip h << 8 | bucket, starting at the exclusive
+// prefix, as long as its count), so the busy-strip list -- the job of k_tile_ranges -- is written from it without
+// another look at the keys.  1080p: 5 launches -> 3; 8K: 7 -> 3.  Up to 20 key bits (12 high bits: 16 KB of bins).
+constexpr int BUCKET_MAX_HI_BITS = 12;
 __global__ void __launch_bounds__(RADIX_THREADS, 2)
-k_bucket_sort(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int low_bits,
+k_bucket_sort(uint32_t *key0, uint32_t *val0, uint32_t *key1, uint32_t *val1, int hi_bits,
               const uint32_t *__restrict__ bucket_start, DrawCounters *ctr, uint2 *__restrict__ busy_list,
               uint32_t ntiles, TileCtl *ctl, unsigned long long *__restrict__ group_sums, uint32_t ngroups) {
     constexpr int BINS = 256;
     extern __shared__ uint32_t s_dyn[];
-    uint32_t *cursor = s_dyn;                                                     // [BINS]
+    uint32_t *s_list = s_dyn;                                                     // [2][8] busy strips per warp of digits
     uint32_t(*warp_cnt)[BINS] = reinterpret_cast<uint32_t(*)[BINS]>(s_dyn + BINS);  // [RADIX_WARPS][BINS]
+    uint32_t *hfull = s_dyn + BINS * (RADIX_WARPS + 1);                           // [1 << hi_bits], two local passes only
     __shared__ uint32_t s_scan[RADIX_WARPS + 1];
     __shared__ uint32_t s_base[2];
     pdl_wait();
@@ -339,140 +345,175 @@ k_bucket_sort(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_o
     const uint32_t beg = bucket_start[blockIdx.x], end = bucket_start[blockIdx.x + 1];
     if (beg >= end) return;
     const uint32_t ltmask = (1u << lane) - 1u;
-    const uint32_t mask = (1u << low_bits) - 1u;  // low_bits <= 8
-    for (int k = tid; k < BINS; k += RADIX_THREADS) cursor[k] = 0;
-    __syncthreads();
-    // count; the first tile stays in registers
-    uint32_t key0r[RADIX_ITEMS], val0r[RADIX_ITEMS];
-    {
-        const uint32_t wbase = beg + warp * (32 * RADIX_ITEMS);
+    const uint32_t chunk = (((end - beg + RADIX_WARPS - 1) / RADIX_WARPS) + 31u) & ~31u;
+    const uint32_t cbeg = min(beg + warp * chunk, end), cend = min(cbeg + chunk, end);
+    const int passes = (hi_bits + 7) / 8;
+    const uint32_t nfull = 1u << hi_bits;
+    // lanes with the same digit as this one, among the valid lanes of the step
+    auto same_digit = [&](uint32_t d, uint32_t active) {
+        uint32_t peers = active;
 #pragma unroll
-        for (int r = 0; r < RADIX_ITEMS; r++) {
-            const uint32_t i = wbase + r * 32 + lane;
-            key0r[r] = i < end ? keys_in[i] : 0u;
-            val0r[r] = i < end ? vals_in[i] : 0u;
+        for (int b = 0; b < 8; b++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+            peers &= ((d >> b) & 1u) ? m : ~m;
         }
-#pragma unroll
-        for (int r = 0; r < RADIX_ITEMS; r++) {
-            const uint32_t i = wbase + r * 32 + lane;
-            if (i < end) atomicAdd(&cursor[key0r[r] & mask], 1u);
-        }
+        return peers;
+    };
+    if (passes > 1) {
+        for (uint32_t k = tid; k < nfull; k += RADIX_THREADS) hfull[k] = 0;
+        __syncthreads();
     }
-    for (uint32_t i = beg + RADIX_TILE + tid; i < end; i += RADIX_THREADS) atomicAdd(&cursor[keys_in[i] & mask], 1u);
-    __syncthreads();
-    {   // bases; and the bucket's busy strips straight from the histogram
-        uint32_t total;
-        const uint32_t c = tid < BINS ? cursor[tid] : 0u;
-        const uint32_t ex = block_excl_scan<RADIX_THREADS>(c, s_scan, &total);
-        if (tid < BINS) cursor[tid] = beg + ex;
-        uint32_t mh = 0, ml = 0;
-        if (warp < BINS / 32) {  // (the digits live in the first eight warps)
-            const bool heavy = c >= HEAVY_SEGS, light = c > 0u && !heavy;
-            mh = __ballot_sync(0xffffffffu, heavy);
-            ml = __ballot_sync(0xffffffffu, light);
-            if (lane == 0) { warp_cnt[0][warp] = (uint32_t)__popc(mh); warp_cnt[1][warp] = (uint32_t)__popc(ml); }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t nh = 0, nl = 0;
-            for (int w = 0; w < BINS / 32; w++) { nh += warp_cnt[0][w]; nl += warp_cnt[1][w]; }
-            s_base[0] = nh ? atomicAdd(&ctl->nheavy, nh) : 0u;
-            s_base[1] = nl ? atomicAdd(&ctl->nlight, nl) : 0u;
-        }
-        __syncthreads();
-        if (warp < BINS / 32 && c > 0u) {
-            const bool heavy = c >= HEAVY_SEGS;
-            uint32_t before = 0;
-            for (uint32_t w = 0; w < warp; w++) before += warp_cnt[heavy ? 0 : 1][w];
-            const uint32_t strip = (blockIdx.x << low_bits) | tid;
-            // (a sorted key array has at most ntiles bins; the bound keeps a corrupted one from writing outside the list)
-            if (heavy) {
-                const uint32_t ph = s_base[0] + before + (uint32_t)__popc(mh & ltmask);
-                if (ph < ntiles) busy_list[ph] = make_uint2(strip, beg + ex);
-            } else {
-                const uint32_t pl = s_base[1] + before + (uint32_t)__popc(ml & ltmask);
-                if (pl < ntiles) busy_list[ntiles - 1u - pl] = make_uint2(strip, beg + ex);
+    for (int pass = 0; pass < passes; pass++) {
+        const int shift = 8 + 8 * pass;
+        const uint32_t mask = (hi_bits - 8 * pass >= 8) ? 255u : ((1u << (hi_bits - 8 * pass)) - 1u);
+        const uint32_t *keys_in = (pass & 1) ? key0 : key1, *vals_in = (pass & 1) ? val0 : val1;  // (the global pass wrote buffer 1)
+        uint32_t *keys_out = (pass & 1) ? key1 : key0, *vals_out = (pass & 1) ? val1 : val0;
+        // ---- count: warp_cnt[warp][d] = pairs of this warp's chunk with digit d
+#pragma unroll
+        for (int k = 0; k < BINS / 32; k++) warp_cnt[warp][lane + 32 * k] = 0;
+        __syncwarp();
+        {
+            uint32_t nk = cbeg + lane < cend ? keys_in[cbeg + lane] : 0u;
+            for (uint32_t i = cbeg; i < cend; i += 32) {
+                const uint32_t k = nk;
+                const bool valid = i + lane < cend;
+                if (i + 32 < cend) nk = i + 32 + lane < cend ? keys_in[i + 32 + lane] : 0u;  // next step's keys are in flight
+                const uint32_t d = (k >> shift) & mask;
+                const uint32_t active = __ballot_sync(0xffffffffu, valid);
+                const uint32_t peers = same_digit(d, active);
+                if (valid && (peers & ltmask) == 0u) warp_cnt[warp][d] += (uint32_t)__popc(peers);  // the first lane of each digit
+                if (passes > 1 && pass == 0 && valid) atomicAdd(&hfull[(k >> 8) & (nfull - 1u)], 1u);
+                __syncwarp();
             }
         }
-        __syncthreads();  // (warp_cnt is reused below)
-    }
-    for (uint32_t base = beg; base < end; base += RADIX_TILE) {
-        for (int k = tid; k < RADIX_WARPS * BINS; k += RADIX_THREADS) (&warp_cnt[0][0])[k] = 0;
         __syncthreads();
-        uint32_t key[RADIX_ITEMS], val[RADIX_ITEMS], rank[RADIX_ITEMS];
-        bool valid[RADIX_ITEMS];
-        const uint32_t wbase = base + warp * (32 * RADIX_ITEMS);
-#pragma unroll
-        for (int r = 0; r < RADIX_ITEMS; r++) {
-            const uint32_t i = wbase + r * 32 + lane;
-            valid[r] = i < end;
-            if (base == beg) { key[r] = key0r[r]; val[r] = val0r[r]; }
-            else {
-                key[r] = valid[r] ? keys_in[i] : 0u;
-                val[r] = valid[r] ? vals_in[i] : 0u;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < RADIX_ITEMS; r++) {
-            const uint32_t d = key[r] & mask;
-            const uint32_t active = __ballot_sync(0xffffffffu, valid[r]);
-            rank[r] = 0;
-            if (valid[r]) {
-                uint32_t peers = active;  // lanes with the same digit, from one ballot per digit bit
-#pragma unroll
-                for (int b = 0; b < 8; b++) {
-                    const uint32_t m = __ballot_sync(active, (d >> b) & 1u);
-                    peers &= ((d >> b) & 1u) ? m : ~m;
-                }
-                const int leader = __ffs(peers) - 1;
-                uint32_t old = 0;
-                if ((int)lane == leader) { old = warp_cnt[warp][d]; warp_cnt[warp][d] = old + __popc(peers); }
-                old = __shfl_sync(peers, old, leader);
-                rank[r] = old + __popc(peers & ltmask);
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-        uint32_t run = 0;
-        if (tid < BINS) {
+        // ---- bases: digit totals, digit bases, the absolute position of every (warp, digit) run
+        {
+            uint32_t c = 0;
+            if (tid < BINS) {
 #pragma unroll 8
-            for (int w = 0; w < RADIX_WARPS; w++) {
-                const uint32_t c = warp_cnt[w][tid];
-                warp_cnt[w][tid] = run;
-                run += c;
+                for (int w = 0; w < RADIX_WARPS; w++) {
+                    const uint32_t v = warp_cnt[w][tid];
+                    warp_cnt[w][tid] = c;
+                    c += v;
+                }
+            }
+            uint32_t total;
+            const uint32_t ex = block_excl_scan<RADIX_THREADS>(c, s_scan, &total);
+            uint32_t mh = 0, ml = 0;
+            if (warp < BINS / 32) {  // (the digits live in the first eight warps)
+                const uint32_t base = beg + ex;
+#pragma unroll 8
+                for (int w = 0; w < RADIX_WARPS; w++) warp_cnt[w][tid] += base;
+                if (passes == 1) {  // the digit totals are the bucket's bins
+                    const bool heavy = c >= HEAVY_SEGS, light = c > 0u && !heavy;
+                    mh = __ballot_sync(0xffffffffu, heavy);
+                    ml = __ballot_sync(0xffffffffu, light);
+                    if (lane == 0) { s_list[warp] = (uint32_t)__popc(mh); s_list[8 + warp] = (uint32_t)__popc(ml); }
+                }
+            }
+            __syncthreads();
+            if (passes == 1) {
+                if (tid == 0) {
+                    uint32_t nh = 0, nl = 0;
+                    for (int w = 0; w < BINS / 32; w++) { nh += s_list[w]; nl += s_list[8 + w]; }
+                    s_base[0] = nh ? atomicAdd(&ctl->nheavy, nh) : 0u;
+                    s_base[1] = nl ? atomicAdd(&ctl->nlight, nl) : 0u;
+                }
+                __syncthreads();
+                if (warp < BINS / 32 && c > 0u) {
+                    const bool heavy = c >= HEAVY_SEGS;
+                    uint32_t before = 0;
+                    for (uint32_t w = 0; w < warp; w++) before += s_list[(heavy ? 0 : 8) + w];
+                    const uint32_t strip = (tid << 8) | blockIdx.x;
+                    // (at most ntiles bins; the bound keeps a corrupted key array from writing outside the list)
+                    if (heavy) {
+                        const uint32_t ph = s_base[0] + before + (uint32_t)__popc(mh & ltmask);
+                        if (ph < ntiles) busy_list[ph] = make_uint2(strip, beg + ex);
+                    } else {
+                        const uint32_t pl = s_base[1] + before + (uint32_t)__popc(ml & ltmask);
+                        if (pl < ntiles) busy_list[ntiles - 1u - pl] = make_uint2(strip, beg + ex);
+                    }
+                }
             }
         }
-        __syncthreads();
+        // ---- place: the same steps again, every pair to the running position of its (warp, digit) run
+        {
+            uint32_t nk = cbeg + lane < cend ? keys_in[cbeg + lane] : 0u, nv = cbeg + lane < cend ? vals_in[cbeg + lane] : 0u;
+            for (uint32_t i = cbeg; i < cend; i += 32) {
+                const uint32_t k = nk, v = nv;
+                const bool valid = i + lane < cend;
+                if (i + 32 < cend) {
+                    nk = i + 32 + lane < cend ? keys_in[i + 32 + lane] : 0u;
+                    nv = i + 32 + lane < cend ? vals_in[i + 32 + lane] : 0u;
+                }
+                const uint32_t d = (k >> shift) & mask;
+                const uint32_t active = __ballot_sync(0xffffffffu, valid);
+                const uint32_t peers = same_digit(d, active);
+                if (valid) {
+                    const uint32_t pos = warp_cnt[warp][d] + (uint32_t)__popc(peers & ltmask);
+                    keys_out[pos] = k;
+                    vals_out[pos] = v;
+                }
+                __syncwarp();
+                if (valid && (peers & ltmask) == 0u) warp_cnt[warp][d] += (uint32_t)__popc(peers);
+                __syncwarp();
+            }
+        }
+        __syncthreads();  // the next pass reads what other warps of this CTA have just stored
+    }
+    if (passes > 1) {
+        // ---- the bucket's bins from the histogram of all high bits: thread t owns nfull / 1024 consecutive bins
+        const uint32_t per = nfull / RADIX_THREADS;  // 1, 2 or 4 (9 <= hi_bits <= 12: nfull >= 512; below 1024 threads idle)
+        const uint32_t per1 = per ? per : 1u;
+        const uint32_t j0 = tid * per1;
+        uint32_t cnt[4] = {0, 0, 0, 0}, sum = 0, nh = 0, nl = 0;
 #pragma unroll
-        for (int r = 0; r < RADIX_ITEMS; r++) {
-            if (valid[r]) {
-                const uint32_t d = key[r] & mask;
-                const uint32_t pos = cursor[d] + warp_cnt[warp][d] + rank[r];
-                keys_out[pos] = key[r];
-                vals_out[pos] = val[r];
+        for (uint32_t u = 0; u < 4; u++) {
+            if (u < per1 && j0 + u < nfull) {
+                cnt[u] = hfull[j0 + u];
+                sum += cnt[u];
+                if (cnt[u] >= HEAVY_SEGS) nh++; else if (cnt[u]) nl++;
             }
         }
+        uint32_t total, tot_list;
+        uint32_t pos = beg + block_excl_scan<RADIX_THREADS>(sum, s_scan, &total);
+        const uint32_t lex = block_excl_scan<RADIX_THREADS>((nh << 16) | nl, s_scan, &tot_list);  // (<= 4096 bins: no carry)
+        if (tid == 0) {
+            s_base[0] = (tot_list >> 16) ? atomicAdd(&ctl->nheavy, tot_list >> 16) : 0u;
+            s_base[1] = (tot_list & 0xffffu) ? atomicAdd(&ctl->nlight, tot_list & 0xffffu) : 0u;
+        }
         __syncthreads();
-        if (tid < BINS) cursor[tid] += run;
-        __syncthreads();
+        uint32_t ph = s_base[0] + (lex >> 16), pl = s_base[1] + (lex & 0xffffu);
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) {
+            if (u < per1 && j0 + u < nfull && cnt[u]) {
+                const uint32_t strip = ((j0 + u) << 8) | blockIdx.x;
+                if (cnt[u] >= HEAVY_SEGS) { if (ph < ntiles) busy_list[ph] = make_uint2(strip, pos); ph++; }
+                else { if (pl < ntiles) busy_list[ntiles - 1u - pl] = make_uint2(strip, pos); pl++; }
+                pos += cnt[u];
+            }
+        }
     }
 }
 
-// Binning of a draw's segments by strip (8 < bits <= 16): the global pass on the top eight bits, then k_bucket_sort.
-// *sorted_buf = the buffer that holds the sorted pairs.  tmp: [RADIX_GRID][256] histogram + 257 bucket starts.
+// Binning of a draw's segments by strip (8 < bits <= 20): the global pass on the low eight bits, then k_bucket_sort.
+// *sorted_buf = the buffer that holds the binned pairs.  tmp: [RADIX_GRID][256] histogram + 257 bucket starts.
 int launch_bin_buckets(uint32_t *const key[2], uint32_t *const val[2], DrawCounters *ctr, uint32_t n_max, int bits,
                        uint32_t *tmp, int *sorted_buf, uint2 *busy_list, uint32_t ntiles, TileCtl *ctl,
                        unsigned long long *group_sums, uint32_t ngroups, cudaStream_t st) {
-    const int low_bits = bits - 8;
+    const int hi_bits = bits - 8;
     uint32_t *bucket_start = tmp + (size_t)RADIX_GRID * 256;
-    int launches = radix_pass<8>(key, val, 0, &ctr->n_segs, n_max, low_bits, tmp, st, &ctr->overflow, bucket_start);
-    const size_t smem = sizeof(uint32_t) * (size_t)256 * (RADIX_WARPS + 1);
-    cudaFuncSetAttribute(k_bucket_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    launch_pdl(k_bucket_sort, 256, RADIX_THREADS, smem, st, (const uint32_t *)key[1], (const uint32_t *)val[1], key[0], val[0],
-               low_bits, (const uint32_t *)bucket_start, ctr, busy_list, ntiles, ctl, group_sums, ngroups);
-    *sorted_buf = 0;
+    int launches = radix_pass<8>(key, val, 0, &ctr->n_segs, n_max, 0, tmp, st, &ctr->overflow, bucket_start);
+    const int passes = (hi_bits + 7) / 8;
+    const size_t smem = sizeof(uint32_t) * ((size_t)256 * (RADIX_WARPS + 1) + (passes > 1 ? ((size_t)1 << hi_bits) : 0));
+    cudaFuncSetAttribute(k_bucket_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * (256 * (RADIX_WARPS + 1) + (1 << BUCKET_MAX_HI_BITS))));
+    launch_pdl(k_bucket_sort, 256, RADIX_THREADS, smem, st, key[0], val[0], key[1], val[1], hi_bits,
+               (const uint32_t *)bucket_start, ctr, busy_list, ntiles, ctl, group_sums, ngroups);
+    *sorted_buf = (1 + passes) & 1;
     return launches + 1;
 }
+bool bin_buckets_ok(int bits) { return bits > 8 && bits - 8 <= BUCKET_MAX_HI_BITS; }
 
 // Stable LSD radix sort of (key, val) on `bits` key bits.  8-bit digits: measured on the 8K benchmark frame
 // (3.3 M pairs, 19 key bits) three 8-bit passes take 3 x 43 us, two 10-bit passes 2 x 76 us -- clearing and

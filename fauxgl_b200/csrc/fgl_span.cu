@@ -282,7 +282,7 @@ int launch_bin(const DrawParams &p, const WorkBuffers &wb, int *sorted_buf, cuda
     // stable sort of the segment indices by tile id
     int bits = 1;
     while ((1u << bits) < wb.ntiles) bits++;
-    if (g_bin_buckets && bits > 8 && bits <= 16)
+    if (g_bin_buckets && bin_buckets_ok(bits))
         return launch_bin_buckets(wb.seg_key, wb.seg_val, c, wb.cap_segs, bits, wb.scan_tmp, sorted_buf, wb.busy_list, wb.ntiles,
                                   wb.tile_ctl, wb.blk_base, wb.cap_prims / (128u * 64u) + 2u, st);
     launches += launch_sort_pairs(wb.seg_key, wb.seg_val, &c->n_segs, wb.cap_segs, bits, wb.scan_tmp, sorted_buf, st, &c->overflow);
