@@ -64,6 +64,24 @@ def test_scene_matches_oracle_for_both_strip_widths(name, strip_w, oracle_lib, g
     assert stats["gpu_info"] == stats["oracle_info"], stats
 
 
+@pytest.mark.parametrize("switch", ["FGL_BIN=lsd", "FGL_ORDER=coop", "FGL_READBACK_OVERLAP=0"])
+@pytest.mark.parametrize("name", ["hello", "bowser_close", "shapes_multipass", "lines", "edge_cases", "bumpy_small",
+                                  "offscreen_lines_tiny", "degenerate_clipped"])
+def test_scene_matches_oracle_under_order_variants(name, switch, oracle_lib, gpu_capi, monkeypatch):
+    """The binning of segments by strip has three implementations: a global radix pass on the low byte followed by
+    one CTA per bucket (the default), every radix pass global + k_tile_ranges (FGL_BIN=lsd; also the path of
+    framebuffers with more than 2^20 strips), and everything between k_front and k_strip as one cooperative kernel
+    (FGL_ORDER=coop, measured slower, kept as a tuning variant).  All must give the same frame."""
+    from fauxgl_b200.context import Context
+    if name not in scenes.SCENES:
+        pytest.skip("scene not in this tree")
+    k, v = switch.split("=")
+    monkeypatch.setenv(k, v)
+    stats = run_both(scenes.SCENES[name](), oracle_lib, Context)
+    assert stats["depth_mismatch"] == 0 and stats["color_mismatch"] == 0, stats
+    assert stats["gpu_info"] == stats["oracle_info"], stats
+
+
 def test_config4_capsule_texture_png_full_scale(oracle_lib, gpu_capi):
     """BASELINE config 4 at the size examples/capsule.go:11-14 renders (1024 x 1024, 4x supersampled): capsule.obj +
     the reference's 4096^2 texture.png through TextureShader, the translucent pass and the wireframe + DepthBias
