@@ -731,6 +731,7 @@ def main():
         dev = torch.device("cuda", local_rank)
         dv = [torch.empty_like(pin_v, device=dev), torch.empty_like(pin_vn, device=dev)]
         dimg = torch.empty(H1 * W1 * 4, dtype=torch.uint8, device=dev)
+        himg = torch.empty(H1 * W1 * 4, dtype=torch.uint8, pin_memory=True)
         s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
         def both():
@@ -738,7 +739,7 @@ def main():
                 dv[0].copy_(pin_v, non_blocking=True)
                 dv[1].copy_(pin_vn, non_blocking=True)
             with torch.cuda.stream(s_dn):
-                pin_img.view(-1).copy_(dimg, non_blocking=True)
+                himg.copy_(dimg, non_blocking=True)
         both()
         torch.cuda.synchronize()
         t = time.perf_counter()

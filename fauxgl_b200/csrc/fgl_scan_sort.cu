@@ -324,6 +324,9 @@ static int radix_pass(uint32_t *const key[2], uint32_t *const val[2], int cur, c
 // prefix, as long as its count), so the busy-strip list -- the job of k_tile_ranges -- is written from it without
 // another look at the keys.  1080p: 5 launches -> 3; 8K: 7 -> 3.  Up to 20 key bits (12 high bits: 16 KB of bins).
 constexpr int BUCKET_MAX_HI_BITS = 12;
+#ifndef FGL_BUCKET_MATCH
+#define FGL_BUCKET_MATCH 1  // place phase: peers by MATCH.ANY (1) or by one ballot per digit bit (0)
+#endif
 __global__ void __launch_bounds__(RADIX_THREADS, 2)
 k_bucket_sort(uint32_t *key0, uint32_t *val0, uint32_t *key1, uint32_t *val1, int hi_bits,
               const uint32_t *__restrict__ bucket_start, DrawCounters *ctr, uint2 *__restrict__ busy_list,
@@ -349,16 +352,17 @@ k_bucket_sort(uint32_t *key0, uint32_t *val0, uint32_t *key1, uint32_t *val1, in
     const uint32_t cbeg = min(beg + warp * chunk, end), cend = min(cbeg + chunk, end);
     const int passes = (hi_bits + 7) / 8;
     const uint32_t nfull = 1u << hi_bits;
-    // lanes with the same digit as this one, among the valid lanes of the step
-    auto same_digit = [&](uint32_t d, uint32_t active) {
+    // lanes with the same digit as this one, among the valid lanes of the step (ballot variant, FGL_BUCKET_MATCH=0)
+    auto same_digit_of = [&](uint32_t d, uint32_t active) {
         uint32_t peers = active;
 #pragma unroll
         for (int b = 0; b < 8; b++) {
-            const uint32_t m = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+            const uint32_t m = __ballot_sync(active, (d >> b) & 1u);
             peers &= ((d >> b) & 1u) ? m : ~m;
         }
         return peers;
     };
+    (void)same_digit_of;
     if (passes > 1) {
         for (uint32_t k = tid; k < nfull; k += RADIX_THREADS) hfull[k] = 0;
         __syncthreads();
@@ -379,11 +383,10 @@ k_bucket_sort(uint32_t *key0, uint32_t *val0, uint32_t *key1, uint32_t *val1, in
                 const bool valid = i + lane < cend;
                 if (i + 32 < cend) nk = i + 32 + lane < cend ? keys_in[i + 32 + lane] : 0u;  // next step's keys are in flight
                 const uint32_t d = (k >> shift) & mask;
-                const uint32_t active = __ballot_sync(0xffffffffu, valid);
-                const uint32_t peers = same_digit(d, active);
-                if (valid && (peers & ltmask) == 0u) warp_cnt[warp][d] += (uint32_t)__popc(peers);  // the first lane of each digit
+                // (one shared-memory atomic per pair: this kernel is issue-bound -- 64 resident warps per SM -- and the
+                // ballot ranking of the place phase costs 40 issue slots per step; the count does not need the ranks)
+                if (valid) atomicAdd(&warp_cnt[warp][d], 1u);
                 if (passes > 1 && pass == 0 && valid) atomicAdd(&hfull[(k >> 8) & (nfull - 1u)], 1u);
-                __syncwarp();
             }
         }
         __syncthreads();
@@ -449,8 +452,13 @@ k_bucket_sort(uint32_t *key0, uint32_t *val0, uint32_t *key1, uint32_t *val1, in
                 }
                 const uint32_t d = (k >> shift) & mask;
                 const uint32_t active = __ballot_sync(0xffffffffu, valid);
-                const uint32_t peers = same_digit(d, active);
+                uint32_t peers = 0;
                 if (valid) {
+#if FGL_BUCKET_MATCH
+                    peers = __match_any_sync(active, d);  // lanes of the step with the same digit: one issue slot
+#else
+                    peers = same_digit_of(d, active);
+#endif
                     const uint32_t pos = warp_cnt[warp][d] + (uint32_t)__popc(peers & ltmask);
                     keys_out[pos] = k;
                     vals_out[pos] = v;
