@@ -293,14 +293,135 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     }
 }
 
+// The 8-bit scatter in the shape that paid off in k_bucket_sort (below): the CTA's contiguous range is cut into 32
+// contiguous chunks, one per warp; a warp counts its chunk's digits into a row of its own (one shared-memory atomic per
+// pair), one sweep turns the rows into the absolute position of every (warp, digit) run -- digit base over all CTAs +
+// this digit in the CTAs before this one (the [CTA][digit] table of k_radix_hist) + this digit in the warps before --
+// and the warp places its pairs in steps of 32, ranks from MATCH.ANY: two block barriers per CTA whatever the range
+// (the tile loop above has six and a 32 x 256 counter sweep per 4096 pairs), and two CTAs per SM.  Stable for the same
+// reason: chunks are contiguous and in order, steps go through a chunk in order, lanes in order.
+#ifndef FGL_RADIX_CHUNKED
+#define FGL_RADIX_CHUNKED 1
+#endif
+__global__ void __launch_bounds__(RADIX_THREADS, 2)
+k_radix_scatter_chunked(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                        uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                        const unsigned int *__restrict__ n_dev, uint32_t n_max, int shift,
+                        const uint32_t *__restrict__ hist /*[grid][256], raw counts*/, const unsigned int *__restrict__ skip_if,
+                        uint32_t *__restrict__ bucket_start /*[257] or null*/) {
+    constexpr int BINS = 256;
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t(*part)[BINS] = reinterpret_cast<uint32_t(*)[BINS]>(s_dyn);                       // [8][BINS] partial sums
+    uint32_t(*warp_cnt)[BINS] = reinterpret_cast<uint32_t(*)[BINS]>(s_dyn + 8 * BINS);        // [RADIX_WARPS][BINS]
+    __shared__ uint32_t s_scan[RADIX_WARPS + 1];
+    pdl_wait();
+    pdl_trigger();
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n = (skip_if && *skip_if) ? 0u : min(*n_dev, n_max);
+    uint32_t beg, end;
+    radix_segment(n, beg, end);
+    const uint32_t ltmask = (1u << lane) - 1u;
+    const uint32_t chunk = (((end - beg + RADIX_WARPS - 1) / RADIX_WARPS) + 31u) & ~31u;
+    const uint32_t cbeg = min(beg + warp * chunk, end), cend = min(cbeg + chunk, end);
+    // ---- count (this warp's chunk) ...
+#pragma unroll
+    for (int k = 0; k < BINS / 32; k++) warp_cnt[warp][lane + 32 * k] = 0;
+    __syncwarp();
+    {
+        uint32_t nk = cbeg + lane < cend ? keys_in[cbeg + lane] : 0u;
+        for (uint32_t i = cbeg; i < cend; i += 32) {
+            const uint32_t k = nk;
+            const bool valid = i + lane < cend;
+            if (i + 32 < cend) nk = i + 32 + lane < cend ? keys_in[i + 32 + lane] : 0u;  // next step's keys are in flight
+            if (valid) atomicAdd(&warp_cnt[warp][(k >> shift) & (BINS - 1)], 1u);
+        }
+    }
+    // ---- ... and the [CTA][digit] table: four threads per digit, batches of independent loads
+    {
+        constexpr uint32_t Q = RADIX_THREADS / BINS, BATCH = 10;
+        const uint32_t d = tid & (BINS - 1), q = tid / BINS;
+        uint32_t row = 0, before = 0;
+        for (uint32_t b0 = q; b0 < gridDim.x; b0 += Q * BATCH) {
+            uint32_t v[BATCH];
+#pragma unroll
+            for (uint32_t k = 0; k < BATCH; k++) {
+                const uint32_t b = b0 + k * Q;
+                v[k] = b < gridDim.x ? __ldcg(&hist[b * BINS + d]) : 0u;
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < BATCH; k++) {
+                row += v[k];
+                if (b0 + k * Q < blockIdx.x) before += v[k];
+            }
+        }
+        part[q][d] = row;
+        part[Q + q][d] = before;
+    }
+    __syncthreads();
+    {
+        uint32_t row = 0, before = 0;
+        if (tid < BINS) {
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) { row += part[k][tid]; before += part[4 + k][tid]; }
+        }
+        uint32_t total;
+        const uint32_t digit_base = block_excl_scan<RADIX_THREADS>(tid < BINS ? row : 0u, s_scan, &total);
+        if (tid < BINS) {
+            uint32_t c = digit_base + before;
+#pragma unroll 8
+            for (int w = 0; w < RADIX_WARPS; w++) {
+                const uint32_t v = warp_cnt[w][tid];
+                warp_cnt[w][tid] = c;
+                c += v;
+            }
+            if (bucket_start && blockIdx.x == 0) {
+                bucket_start[tid] = digit_base;
+                if (tid == BINS - 1) bucket_start[BINS] = total;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- place
+    {
+        uint32_t nk = cbeg + lane < cend ? keys_in[cbeg + lane] : 0u, nv = cbeg + lane < cend ? vals_in[cbeg + lane] : 0u;
+        for (uint32_t i = cbeg; i < cend; i += 32) {
+            const uint32_t k = nk, v = nv;
+            const bool valid = i + lane < cend;
+            if (i + 32 < cend) {
+                nk = i + 32 + lane < cend ? keys_in[i + 32 + lane] : 0u;
+                nv = i + 32 + lane < cend ? vals_in[i + 32 + lane] : 0u;
+            }
+            const uint32_t d = (k >> shift) & (BINS - 1);
+            const uint32_t active = __ballot_sync(0xffffffffu, valid);
+            uint32_t peers = 0;
+            if (valid) {
+                peers = __match_any_sync(active, d);
+                const uint32_t pos = warp_cnt[warp][d] + (uint32_t)__popc(peers & ltmask);
+                keys_out[pos] = k;
+                vals_out[pos] = v;
+            }
+            __syncwarp();
+            if (valid && (peers & ltmask) == 0u) warp_cnt[warp][d] += (uint32_t)__popc(peers);
+            __syncwarp();
+        }
+    }
+}
+
 template <int BITS>
 static int radix_pass(uint32_t *const key[2], uint32_t *const val[2], int cur, const unsigned int *n_dev, uint32_t n_max,
                       int shift, uint32_t *tmp, cudaStream_t st, const unsigned int *skip_if, uint32_t *bucket_start = nullptr) {
     constexpr int BINS = 1 << BITS;
+    launch_pdl(k_radix_hist<BITS>, RADIX_GRID, RADIX_THREADS, 0, st, key[cur], n_dev, n_max, shift, tmp, skip_if);
+    if (BITS == 8 && FGL_RADIX_CHUNKED) {
+        const size_t smem = sizeof(uint32_t) * (size_t)256 * (RADIX_WARPS + 8);
+        cudaFuncSetAttribute(k_radix_scatter_chunked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        launch_pdl(k_radix_scatter_chunked, RADIX_GRID, RADIX_THREADS, smem, st, key[cur], val[cur], key[cur ^ 1], val[cur ^ 1],
+                   n_dev, n_max, shift, (const uint32_t *)tmp, skip_if, bucket_start);
+        return 2;
+    }
     const size_t smem = sizeof(uint32_t) * (size_t)BINS * (RADIX_WARPS + 1);
     // per device and cheap: set on every call (a process may drive several GPUs)
     cudaFuncSetAttribute(k_radix_scatter<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    launch_pdl(k_radix_hist<BITS>, RADIX_GRID, RADIX_THREADS, 0, st, key[cur], n_dev, n_max, shift, tmp, skip_if);
     launch_pdl(k_radix_scatter<BITS>, RADIX_GRID, RADIX_THREADS, smem, st, key[cur], val[cur], key[cur ^ 1], val[cur ^ 1],
                n_dev, n_max, shift, (const uint32_t *)tmp, skip_if, bucket_start);
     return 2;
