@@ -12,6 +12,26 @@ import subprocess
 import sys
 
 
+import os
+import re
+
+
+def _marks():
+    """Line numbers of the phase boundaries in the current fgl_geom.cu (the FRONT_TICK markers of k_front)."""
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fauxgl_b200", "csrc", "fgl_geom.cu")
+    m = {}
+    for i, l in enumerate(open(src), 1):
+        if re.match(r"k_front\(const __grid_constant__", l):
+            m["kernel"] = i
+        for k in ("FRONT_TICK(0)", "FRONT_TICK(2)"):
+            if k in l and "define" not in l:
+                m.setdefault(k, i)
+    return m["kernel"], m["FRONT_TICK(0)"], m["FRONT_TICK(2)"]
+
+
+L_KERNEL, L_PHASE1_END, L_WALK = _marks()
+
+
 def bucket(fname, line):
     if fname == "fgl_walk.cuh":
         return "phase 2: row walker (replay, skip-ahead, run loops)"
@@ -20,13 +40,13 @@ def bucket(fname, line):
     if fname == "fgl_block.cuh":
         return "block / warp scans"
     if fname == "fgl_geom.cu":
-        if line < 760:
+        if line < L_KERNEL:
             return "phase 1: bbox, per-triangle setup, cull filter (helpers above k_front)"
-        if line <= 860:
+        if line <= L_PHASE1_END:
             return "phase 1: k_front body (loads, NDC divisions, area, screen transform)"
-        if line <= 925:
-            return "phase 2: item ranges, record lookup, region hand-over"
-        return "phase 2: walk loop body, SegV stores, publish"
+        if line <= L_WALK:
+            return "scans, item ranges, first record lookup, region hand-over"
+        return "phase 2: walk loop body (item -> record, SegV stores), publish"
     return "other (" + fname + ")"
 
 
