@@ -133,10 +133,16 @@ constexpr int RADIX_WARPS = RADIX_THREADS / 32;
 constexpr int RADIX_ITEMS = 4;
 constexpr int RADIX_TILE = RADIX_THREADS * RADIX_ITEMS;
 
-__device__ __forceinline__ void radix_segment(uint32_t n, uint32_t &beg, uint32_t &end) {
+#ifndef FGL_RADIX_CGRID
+#define FGL_RADIX_CGRID 1  // CTAs per SM of the chunked 8-bit pass (k_radix_hist + k_radix_scatter_chunked); 2 measured slower
+                           // (sort stage 34.9 vs 28.6 us at 1080p, 110.9 vs 108.2 us at 8K: twice the [CTA][digit] rows to add up)
+#endif
+constexpr int RADIX_GRID_CHUNKED = RADIX_GRID * FGL_RADIX_CGRID;
+constexpr uint32_t RADIX_GRAN_CHUNKED = 1024;  // the chunked scatter takes any contiguous split: 32 warps x 32 pairs
+__device__ __forceinline__ void radix_segment(uint32_t n, uint32_t &beg, uint32_t &end, uint32_t gran = RADIX_TILE) {
     // contiguous segment of block b; a multiple of the tile so that tiles stay aligned
     uint32_t per = (n + gridDim.x - 1) / gridDim.x;
-    per = (per + RADIX_TILE - 1) / RADIX_TILE * RADIX_TILE;
+    per = (per + gran - 1) / gran * gran;
     uint64_t b = (uint64_t)blockIdx.x * per;
     beg = b < n ? (uint32_t)b : n;
     uint64_t e = b + per;
@@ -146,7 +152,7 @@ __device__ __forceinline__ void radix_segment(uint32_t n, uint32_t &beg, uint32_
 template <int BITS>
 __global__ void __launch_bounds__(RADIX_THREADS)
 k_radix_hist(const uint32_t *__restrict__ keys, const unsigned int *__restrict__ n_dev, uint32_t n_max, int shift,
-             uint32_t *__restrict__ hist /*[grid][BINS]*/, const unsigned int *__restrict__ skip_if) {
+             uint32_t *__restrict__ hist /*[grid][BINS]*/, const unsigned int *__restrict__ skip_if, uint32_t gran) {
     constexpr int BINS = 1 << BITS;
     __shared__ uint32_t h[BINS];
     pdl_wait();
@@ -155,7 +161,7 @@ k_radix_hist(const uint32_t *__restrict__ keys, const unsigned int *__restrict__
     __syncthreads();
     const uint32_t n = (skip_if && *skip_if) ? 0u : min(*n_dev, n_max);  // (overflowed draw: the keys were never written)
     uint32_t beg, end;
-    radix_segment(n, beg, end);
+    radix_segment(n, beg, end, gran);
     for (uint32_t i = beg + threadIdx.x; i < end; i += RADIX_THREADS)
         atomicAdd(&h[(keys[i] >> shift) & (BINS - 1)], 1u);
     __syncthreads();
@@ -319,7 +325,7 @@ k_radix_scatter_chunked(const uint32_t *__restrict__ keys_in, const uint32_t *__
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t n = (skip_if && *skip_if) ? 0u : min(*n_dev, n_max);
     uint32_t beg, end;
-    radix_segment(n, beg, end);
+    radix_segment(n, beg, end, RADIX_GRAN_CHUNKED);
     const uint32_t ltmask = (1u << lane) - 1u;
     const uint32_t chunk = (((end - beg + RADIX_WARPS - 1) / RADIX_WARPS) + 31u) & ~31u;
     const uint32_t cbeg = min(beg + warp * chunk, end), cend = min(cbeg + chunk, end);
@@ -411,14 +417,16 @@ template <int BITS>
 static int radix_pass(uint32_t *const key[2], uint32_t *const val[2], int cur, const unsigned int *n_dev, uint32_t n_max,
                       int shift, uint32_t *tmp, cudaStream_t st, const unsigned int *skip_if, uint32_t *bucket_start = nullptr) {
     constexpr int BINS = 1 << BITS;
-    launch_pdl(k_radix_hist<BITS>, RADIX_GRID, RADIX_THREADS, 0, st, key[cur], n_dev, n_max, shift, tmp, skip_if);
     if (BITS == 8 && FGL_RADIX_CHUNKED) {
         const size_t smem = sizeof(uint32_t) * (size_t)256 * (RADIX_WARPS + 8);
         cudaFuncSetAttribute(k_radix_scatter_chunked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        launch_pdl(k_radix_scatter_chunked, RADIX_GRID, RADIX_THREADS, smem, st, key[cur], val[cur], key[cur ^ 1], val[cur ^ 1],
-                   n_dev, n_max, shift, (const uint32_t *)tmp, skip_if, bucket_start);
+        launch_pdl(k_radix_hist<BITS>, RADIX_GRID_CHUNKED, RADIX_THREADS, 0, st, key[cur], n_dev, n_max, shift, tmp, skip_if,
+                   RADIX_GRAN_CHUNKED);
+        launch_pdl(k_radix_scatter_chunked, RADIX_GRID_CHUNKED, RADIX_THREADS, smem, st, key[cur], val[cur], key[cur ^ 1],
+                   val[cur ^ 1], n_dev, n_max, shift, (const uint32_t *)tmp, skip_if, bucket_start);
         return 2;
     }
+    launch_pdl(k_radix_hist<BITS>, RADIX_GRID, RADIX_THREADS, 0, st, key[cur], n_dev, n_max, shift, tmp, skip_if, (uint32_t)RADIX_TILE);
     const size_t smem = sizeof(uint32_t) * (size_t)BINS * (RADIX_WARPS + 1);
     // per device and cheap: set on every call (a process may drive several GPUs)
     cudaFuncSetAttribute(k_radix_scatter<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -627,12 +635,12 @@ k_bucket_sort(uint32_t *key0, uint32_t *val0, uint32_t *key1, uint32_t *val1, in
 }
 
 // Binning of a draw's segments by strip (8 < bits <= 20): the global pass on the low eight bits, then k_bucket_sort.
-// *sorted_buf = the buffer that holds the binned pairs.  tmp: [RADIX_GRID][256] histogram + 257 bucket starts.
+// *sorted_buf = the buffer that holds the binned pairs.  tmp: [RADIX_GRID_CHUNKED][256] histogram + 257 bucket starts.
 int launch_bin_buckets(uint32_t *const key[2], uint32_t *const val[2], DrawCounters *ctr, uint32_t n_max, int bits,
                        uint32_t *tmp, int *sorted_buf, uint2 *busy_list, uint32_t ntiles, TileCtl *ctl,
                        unsigned long long *group_sums, uint32_t ngroups, cudaStream_t st) {
     const int hi_bits = bits - 8;
-    uint32_t *bucket_start = tmp + (size_t)RADIX_GRID * 256;
+    uint32_t *bucket_start = tmp + (size_t)RADIX_GRID_CHUNKED * 256;
     int launches = radix_pass<8>(key, val, 0, &ctr->n_segs, n_max, 0, tmp, st, &ctr->overflow, bucket_start);
     const int passes = (hi_bits + 7) / 8;
     const size_t smem = sizeof(uint32_t) * ((size_t)256 * (RADIX_WARPS + 1) + (passes > 1 ? ((size_t)1 << hi_bits) : 0));
