@@ -185,7 +185,7 @@ struct WorkBuffers {
                               //             heavy ones from the front, the rest from the back
     uint32_t nsm;             // SMs of the device
     TileCtl *tile_ctl;        // device
-    uint32_t *vis_seg;        // [ntiles*TILE_W] deferred shading: per pixel of a busy strip, the segment (index into
+    uint32_t *vis_seg;        // [ntiles*TILE_W] deferred shading, indexed by busy-LIST position: per pixel of a busy strip, the segment (index into
                               //                 segv) whose fragment won, or 0xffffffff (allocated on the first deferred draw)
     uint8_t *dirty;           // [ntiles] 1: some pixel of the strip had its depth written since the last depth clear (the
                               //          sparse sort-last composite only exchanges such strips, fgl_comm.cu)

@@ -451,7 +451,7 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             if (warp == 0) {
                 const bool touched = __any_sync(0xffffffffu, my_updated != updated_at_start);
                 if (st.write_color)
-                    for (int h = 0; h < strip_h; h++) wb.vis_seg[(size_t)strip * tile_w + lane + 32 * h] = t.winseg[lane + 32 * h];
+                    for (int h = 0; h < strip_h; h++) wb.vis_seg[(size_t)hq * tile_w + lane + 32 * h] = t.winseg[lane + 32 * h];
                 if (touched && st.write_depth) {
 #pragma unroll
                     for (int h = 0; h < strip_h; h++) {
@@ -625,8 +625,8 @@ k_strip(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
         // ---- write the strip back ---------------------------------------------------------------
         const bool touched = __any_sync(0xffffffffu, my_updated != updated_at_start);
         if constexpr (DEFERRED) {
-            if (st.write_color) {  // k_shade reads the winners of every busy strip
-                for (int h = 0; h < strip_h; h++) wb.vis_seg[(size_t)strip * tile_w + lane + 32 * h] = sm.winseg[lane + 32 * h];
+            if (st.write_color) {  // k_shade reads the winners of every busy strip, by LIST position (it does not wait for the entry)
+                for (int h = 0; h < strip_h; h++) wb.vis_seg[(size_t)q * tile_w + lane + 32 * h] = sm.winseg[lane + 32 * h];
             }
         } else {
             if (touched && st.write_color) {
@@ -676,21 +676,18 @@ k_shade(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
     const uint32_t nbusy = wb.counters->overflow ? 0u : nheavy + wb.tile_ctl->nlight;
     const uint32_t tile_w = (uint32_t)p.tile_w, SPB = SHT / tile_w;  // strips per CTA pass
     const int pix = (int)(threadIdx.x % tile_w);
-    // The loop is software-pipelined over its first two dependent loads: while strip q is shaded, the winner of the
-    // thread's next strip (q + stride) and the list entry of the one after it are in flight -- list entry -> winner
-    // -> segment record -> 18 attributes were four dependent memory round trips per pixel (long-scoreboard stall 9.7
-    // per issue, profiles/README.md).
+    // list entry -> winner -> segment record -> 18 attributes were four dependent memory round trips per pixel
+    // (long-scoreboard stall 9.7 per issue, profiles/README.md).  The winners are stored by LIST position (k_strip
+    // knows it), so the entry and the winner are loaded side by side, and both are in flight one strip ahead.
     const uint32_t stride = gridDim.x * SPB;
     uint32_t q = blockIdx.x * SPB + threadIdx.x / tile_w;
     auto strip_at = [&](uint32_t qq) { return qq < nbusy ? busy_at(wb, nheavy, qq).x : 0xffffffffu; };
-    auto winner_at = [&](uint32_t st_) { return st_ != 0xffffffffu ? wb.vis_seg[(size_t)st_ * tile_w + pix] : NO_WINNER; };
-    uint32_t strip = strip_at(q), strip1 = strip_at(q + stride);
-    uint32_t sidx = winner_at(strip);
+    auto winner_at = [&](uint32_t qq) { return qq < nbusy ? wb.vis_seg[(size_t)qq * tile_w + pix] : NO_WINNER; };
+    uint32_t strip = strip_at(q), sidx = winner_at(q);
     for (; q < nbusy; q += stride) {
-        const uint32_t strip2 = strip_at(q + 2u * stride);   // in flight during this iteration
-        const uint32_t sidx1 = winner_at(strip1);            // its address arrived an iteration ago
+        const uint32_t strip1 = strip_at(q + stride), sidx1 = winner_at(q + stride);  // in flight during this iteration
         const uint32_t cur_strip = strip, cur_sidx = sidx;
-        strip = strip1; strip1 = strip2; sidx = sidx1;
+        strip = strip1; sidx = sidx1;
         if (cur_sidx == NO_WINNER) continue;
         const int x = (int)((cur_strip % (uint32_t)p.tiles_x) * tile_w) + pix;
         const int y = (int)(cur_strip / (uint32_t)p.tiles_x);
