@@ -58,7 +58,8 @@ namespace fgl {
 #define FGL_STRIP_MINB 2
 #endif
 #ifndef FGL_HEAVY_SKIP
-#define FGL_HEAVY_SKIP 3  // rounds a warp sits out after a heavy strip (strip stage at 1080p: 74 / 68 / 64 us for 0 / 2 / 3)
+#define FGL_HEAVY_SKIP 4  // rounds a warp sits out after a heavy strip (strip stage at 1080p: 74 / 68 / 64 us for 0 / 2 / 3 in round 1;
+                          // raster stage 62.6 / 61.4 / 61.6 / 63.4 / 62.6 us for 3 / 4 / 5 / 6 / 8 on the final build of round 2)
 #endif
 constexpr uint32_t HEAVY_SKIP = FGL_HEAVY_SKIP;
 #ifndef FGL_COOP_FACTOR
