@@ -182,15 +182,17 @@ FGL_DI double edge_fn(V3 a, V3 b, V3 c) {  // context.go:147-149
 // benchmark mesh 43 % of the (record, scanline) items.  Skipping them changes nothing only if the reference's
 // FLOATING-POINT test fails there as well, so a row is dropped when that is certain:
 //   exact arithmetic: T the top vertex, d_a, d_b the edges from T, q = p - T with q.y = delta > 0.  The edge
-//   functions u_a, u_b of those edges (positive inside) satisfy |d_b.y| u_a + |d_a.y| u_b = -2 |A| delta, hence
-//   min(u_a, u_b) <= -2 |A| delta / (|d_a.y| + |d_b.y|) <= -|A| delta / H,  H = max y - min y,  A = the area term
-//   edge_fn(s0, s1, s2): SOME edge function is that negative at EVERY pixel of the row (mirrored: bottom, right).
+//   functions u_a = s cross(d_a, q), u_b = s cross(q, d_b) of those edges (s = the sign that makes them positive
+//   inside) satisfy |d_b.y| u_a + |d_a.y| u_b = -|cross(d_a, d_b)| delta = -|A| delta, A = the area term
+//   edge_fn(s0, s1, s2) (twice the triangle's area), hence
+//   min(u_a, u_b) <= -|A| delta / (|d_a.y| + |d_b.y|) <= -|A| delta / (2 H),  H = max y - min y:
+//   SOME edge function is that negative at EVERY pixel of the row (mirrored: bottom rows, right columns).
 //   rounding: the reference's values come from edge_fn at (x0 + .5, y0 + .5) and a chain of at most rows + cols + 2
 //   additions of values bounded by 2 B^2, B = the box size + 2: they differ from the exact ones by less than
 //   2^-50 B^2 (B + 8).  E below is 64 times that.
-// A row is dropped when |A| delta / H > 4 E (delta >= 4 E H / |A| + 1e-6, the constant covering the rounding of the
-// comparison itself for coordinates below 2^22); sign(w * ra) = sign(w) sign(ra) then holds without underflow
-// (|w| > E, |ra| >= 2^-48).  Slivers (|A| <= 16 E) and anything non-finite are left alone.
+// A row is dropped when delta >= 4 E H / |A| + 1e-6 (the constant covers the rounding of the comparison itself for
+// coordinates below 2^22), i.e. when that edge value is below -2 E, twice the rounding bound, itself 64-fold;
+// sign(w * ra) = sign(w) sign(ra) then holds without underflow (|w| > E, |ra| >= 2^-48).  Slivers (|A| <= 16 E) and anything non-finite are left alone.
 // Written without branches or float <-> integer conversions (the floor / ceil values of compute_bbox are reused), so
 // that it schedules between the seven divisions of the set-up.  Returns the first row to walk; may clear b.visible.
 FGL_DI int tighten_box(const DrawParams &p, BBox &b, double ra) {
