@@ -168,6 +168,7 @@ ABI = [
     ("fgl_peer_status", C.c_int, [_P, _P]),
     ("fgl_debug_tile_cycles", C.c_int, [_P, _P, C.c_uint64]),
     ("fgl_probe_atomic_rate", C.c_int, [_P, C.c_uint64, C.POINTER(C.c_double)]),
+    ("fgl_debug_div_check", C.c_int, [_P, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("fgl_stream", _P, [_P]),
     ("fgl_color_device_ptr", _P, [_P]),
     ("fgl_depth_device_ptr", _P, [_P]),
@@ -694,6 +695,13 @@ class Context:
         r = C.c_double(0)
         _check(capi().fgl_probe_atomic_rate(self._h, int(ops), C.byref(r)), self._h)
         return float(r.value)
+
+    def DivCheck(self, seed: int, pairs: int):
+        """(mismatches, fast-path results) of the device's branch-free division helpers against the operator
+        (fgl_debug_div_check, include/fauxgl_b200.h)."""
+        bad, fast = C.c_uint64(0), C.c_uint64(0)
+        _check(capi().fgl_debug_div_check(self._h, int(seed), int(pairs), C.byref(bad), C.byref(fast)), self._h)
+        return int(bad.value), int(fast.value)
 
     # -- SSAA resolve (resize.Resize(..., resize.Bilinear) in the examples) -------------
     def Resolve(self, factor: int) -> np.ndarray:

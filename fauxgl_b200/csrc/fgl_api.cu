@@ -1571,6 +1571,23 @@ int fgl_debug_tile_cycles(fgl_ctx *c, uint64_t *dst, uint64_t ntiles) {
     return FGL_OK;
 }
 
+int fgl_debug_div_check(fgl_ctx *c, uint64_t seed, uint64_t pairs, uint64_t *mismatches, uint64_t *fast_path) {
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!mismatches || !fast_path) return fail(c, FGL_E_INVALID, "null result pointer");
+    std::lock_guard<std::mutex> lock(c->mu);
+    NOT_WHILE_RECORDING(c, "fgl_debug_div_check");
+    CK(c, cudaMemsetAsync(c->scratch, 0, 2 * sizeof(unsigned long long), c->stream));
+    launch_div_check(seed, pairs, c->scratch, c->stream);
+    CK(c, cudaGetLastError());
+    unsigned long long h[2] = {0, 0};
+    CK(c, cudaMemcpyAsync(h, c->scratch, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    *mismatches = h[0];
+    *fast_path = h[1];
+    return FGL_OK;
+}
+
 int fgl_probe_atomic_rate(fgl_ctx *c, uint64_t ops, double *ops_per_second) {
     int rc = check_ctx(c);
     if (rc) return rc;

@@ -749,6 +749,44 @@ FGL_DI SetupRcp setup_rcp(V3 s0, V3 s1, V3 s2, double w0, double w1, double w2) 
     q.ra12 = 1 / a12; q.ra20 = 1 / a20; q.ra01 = 1 / a01;
     return q;
 }
+// The same seven reciprocals side by side (fgl_math.cuh: the fast path of the compiler's own expansion as
+// straight-line code, one range test for all; the operator itself when it fails -- a zero edge slope, say).
+#ifndef FGL_FRONT_FASTDIV
+#define FGL_FRONT_FASTDIV 1
+#endif
+FGL_DI SetupRcp setup_rcp_fast(V3 s0, V3 s1, V3 s2, double w0, double w1, double w2) {
+#if FGL_FRONT_FASTDIV
+    SetupRcp q;
+    const double a01 = s1.y - s0.y, a12 = s2.y - s1.y, a20 = s0.y - s2.y;
+    const double area = edge_fn(s0, s1, s2);
+    bool ok = true;
+    q.ra = rcp_fast(area, ok);
+    q.r0 = rcp_fast(w0, ok); q.r1 = rcp_fast(w1, ok); q.r2 = rcp_fast(w2, ok);
+    q.ra12 = rcp_fast(a12, ok); q.ra20 = rcp_fast(a20, ok); q.ra01 = rcp_fast(a01, ok);
+    if (!ok) {
+        q.ra = 1 / area;
+        q.r0 = 1 / w0; q.r1 = 1 / w1; q.r2 = 1 / w2;
+        q.ra12 = 1 / a12; q.ra20 = 1 / a20; q.ra01 = 1 / a01;
+    }
+    return q;
+#else
+    return setup_rcp(s0, s1, s2, w0, w1, w2);
+#endif
+}
+// Vector{X / W, Y / W, Z / W} of the three vertices (context.go:318-320): one reciprocal refinement per W.
+FGL_DI void ndc_divide(const V4 *o, V3 &n0, V3 &n1, V3 &n2) {
+#if FGL_FRONT_FASTDIV
+    bool ok = true;
+    const double y0 = div_refine(o[0].w), y1 = div_refine(o[1].w), y2 = div_refine(o[2].w);
+    n0 = v3(div_tail(o[0].x, o[0].w, y0, ok), div_tail(o[0].y, o[0].w, y0, ok), div_tail(o[0].z, o[0].w, y0, ok));
+    n1 = v3(div_tail(o[1].x, o[1].w, y1, ok), div_tail(o[1].y, o[1].w, y1, ok), div_tail(o[1].z, o[1].w, y1, ok));
+    n2 = v3(div_tail(o[2].x, o[2].w, y2, ok), div_tail(o[2].y, o[2].w, y2, ok), div_tail(o[2].z, o[2].w, y2, ok));
+    if (ok) return;
+#endif
+    n0 = v3(o[0].x / o[0].w, o[0].y / o[0].w, o[0].z / o[0].w);
+    n1 = v3(o[1].x / o[1].w, o[1].y / o[1].w, o[1].z / o[1].w);
+    n2 = v3(o[2].x / o[2].w, o[2].y / o[2].w, o[2].z / o[2].w);
+}
 FGL_DI void fill_srec(SRec &r, const BBox &b, V3 s0, V3 s1, V3 s2, uint32_t src, uint32_t flags, const SetupRcp &q,
                       int ystart) {
     r.s0x = s0.x; r.s0y = s0.y; r.s1x = s1.x; r.s1y = s1.y; r.s2x = s2.x; r.s2y = s2.y;
@@ -910,9 +948,8 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
             } else if (surely_culled(p, o)) {
                 // (n stays 0: the reference computes a signed area that is provably on the culled side)
             } else {  // drawClippedTriangle, context.go:316-341
-                V3 ndc0 = v3(o[0].x / o[0].w, o[0].y / o[0].w, o[0].z / o[0].w);
-                V3 ndc1 = v3(o[1].x / o[1].w, o[1].y / o[1].w, o[1].z / o[1].w);
-                V3 ndc2 = v3(o[2].x / o[2].w, o[2].y / o[2].w, o[2].z / o[2].w);
+                V3 ndc0, ndc1, ndc2;
+                ndc_divide(o, ndc0, ndc1, ndc2);
                 double a = (ndc1.x - ndc0.x) * (ndc2.y - ndc0.y) - (ndc2.x - ndc0.x) * (ndc1.y - ndc0.y);
                 uint32_t i0 = 0, i2 = 2;
                 if (a < 0) {
@@ -927,7 +964,7 @@ k_front(const __grid_constant__ DrawParams p, const __grid_constant__ WorkBuffer
                     BBox bb = compute_bbox(p, s0, s1, s2);
                     if (bb.visible) {
                         // the seven divisions of the set-up first: the tightening below schedules between them
-                        const SetupRcp q = setup_rcp(s0, s1, s2, i0 == 0 ? o[0].w : o[2].w, o[1].w, i2 == 2 ? o[2].w : o[0].w);
+                        const SetupRcp q = setup_rcp_fast(s0, s1, s2, i0 == 0 ? o[0].w : o[2].w, o[1].w, i2 == 2 ? o[2].w : o[0].w);
 #if FGL_FRONT_TIGHT
                         const int ystart = tighten_box(p, bb, q.ra);
 #else

@@ -325,6 +325,9 @@ int launch_composite_unpack(uint32_t *color, double *depth, const unsigned long 
 int launch_composite_min(unsigned long long *inout, const unsigned long long *other, size_t n, cudaStream_t st);
 // `ops` 64-bit atomicMin on pseudo-random words of buf[0..words) (fgl_probe_atomic_rate)
 int launch_atomic_probe(unsigned long long *buf, size_t words, unsigned long long ops, cudaStream_t st);
+// the division helpers of fgl_math.cuh against the operator over `pairs` generated operand pairs: out[0] += mismatches,
+// out[1] += results that took the helpers' fast path (fgl_debug_div_check)
+int launch_div_check(unsigned long long seed, unsigned long long pairs, unsigned long long *out, cudaStream_t st);
 int launch_composite_peer(uint32_t *const *color, double *const *depth, int nranks, size_t px0, size_t px1,
                           cudaStream_t st);
 

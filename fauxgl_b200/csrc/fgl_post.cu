@@ -1,6 +1,7 @@
 // fgl_post.cu -- framebuffer kernels around the draw: clears, the SSAA resolve
 // and the pack/unpack/min kernels of the sort-last depth composite.
 #include "fgl_internal.h"
+#include "fgl_math.cuh"
 
 namespace fgl {
 
@@ -274,6 +275,65 @@ k_atomic_probe(unsigned long long *__restrict__ buf, size_t words, unsigned long
         atomicMin(&buf[w], (x >> 1) | 1ull);
     }
 }
+// Self-check of the branch-free division helpers (fgl_math.cuh) against the operator: every thread draws operand pairs
+// from a counter-based generator -- raw 64-bit patterns (NaN, infinities, subnormals, zeros included), values of the
+// magnitudes the rasteriser sees, operands with tiny and huge exponents, exact zeros -- and compares, wherever the
+// helper's range test says "fast path", its bits with those of `a / b` and `1 / b`.  out[0] += mismatches,
+// out[1] += pairs that passed the test (so that a test that never passes does not go unnoticed).
+__global__ void __launch_bounds__(256)
+k_div_check(unsigned long long seed, unsigned long long per_thread, unsigned long long *out) {
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1ull);
+    auto next = [&]() {
+        x += 0x9E3779B97F4A7C15ull;
+        unsigned long long z = x;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    auto draw = [&](unsigned kind) {
+        const unsigned long long r = next();
+        const double u = (double)(r >> 11) * 0x1p-53;  // [0, 1)
+        const double sgn = (r & 1ull) ? -1.0 : 1.0;
+        switch (kind & 7u) {
+            case 0: return __longlong_as_double((long long)r);                       // any bit pattern
+            case 1: return sgn * (u * 4096.0);                                      // screen coordinates
+            case 2: return sgn * (u * 2.0);                                         // clip / NDC magnitudes
+            case 3: return sgn * (1.0 + u * 9.0);                                   // w between the planes
+            case 4: return sgn * u * 0x1p-1000;                                     // tiny
+            case 5: return sgn * (1.0 + u) * 0x1p+1000;                             // huge
+            case 6: return (r & 6ull) ? sgn * (double)(long long)(r >> 44) : sgn * 0.0;  // integers and zeros
+            default: return sgn * u * 0x1p-1060;                                    // subnormal
+        }
+    };
+    unsigned long long bad = 0, fast = 0;
+    for (unsigned long long k = 0; k < per_thread; k++) {
+        const unsigned long long sel = next();
+        const double a = draw((unsigned)sel), b = draw((unsigned)(sel >> 3));
+        bool ok = true;
+        const double q = div_tail(a, b, div_refine(b), ok);
+        if (ok) {
+            const double ref = a / b;
+            fast++;
+            if (__double_as_longlong(q) != __double_as_longlong(ref) && !(q != q && ref != ref)) bad++;
+        }
+        ok = true;
+        const double r1 = rcp_fast(b, ok);
+        if (ok) {
+            const double ref = 1 / b;
+            fast++;
+            if (__double_as_longlong(r1) != __double_as_longlong(ref) && !(r1 != r1 && ref != ref)) bad++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { bad += __shfl_down_sync(0xffffffffu, bad, o); fast += __shfl_down_sync(0xffffffffu, fast, o); }
+    if ((threadIdx.x & 31) == 0) { if (bad) atomicAdd(&out[0], bad); atomicAdd(&out[1], fast); }
+}
+int launch_div_check(unsigned long long seed, unsigned long long pairs, unsigned long long *out, cudaStream_t st) {
+    const unsigned threads = GRID_WAVE * 256u;
+    k_div_check<<<GRID_WAVE, 256, 0, st>>>(seed, (pairs + threads - 1) / threads, out);
+    return 1;
+}
+
 int launch_atomic_probe(unsigned long long *buf, size_t words, unsigned long long ops, cudaStream_t st) {
     const unsigned threads = GRID_WAVE * 256u;
     k_atomic_probe<<<GRID_WAVE, 256, 0, st>>>(buf, words, (ops + threads - 1) / threads);

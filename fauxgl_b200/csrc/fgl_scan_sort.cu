@@ -481,6 +481,7 @@ k_bucket_sort(uint32_t *key0, uint32_t *val0, uint32_t *key1, uint32_t *val1, in
     const uint32_t cbeg = min(beg + warp * chunk, end), cend = min(cbeg + chunk, end);
     const int passes = (hi_bits + 7) / 8;
     const uint32_t nfull = 1u << hi_bits;
+#if !FGL_BUCKET_MATCH
     // lanes with the same digit as this one, among the valid lanes of the step (ballot variant, FGL_BUCKET_MATCH=0)
     auto same_digit_of = [&](uint32_t d, uint32_t active) {
         uint32_t peers = active;
@@ -491,7 +492,7 @@ k_bucket_sort(uint32_t *key0, uint32_t *val0, uint32_t *key1, uint32_t *val1, in
         }
         return peers;
     };
-    (void)same_digit_of;
+#endif
     if (passes > 1) {
         for (uint32_t k = tid; k < nfull; k += RADIX_THREADS) hfull[k] = 0;
         __syncthreads();

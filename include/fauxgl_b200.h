@@ -389,6 +389,13 @@ int fgl_peer_stage_times(fgl_ctx *ctx, fgl_peer_group *group, float ms[4], uint3
  * dst receives 2*ntiles uint64 (ntiles = tiles_x * tiles_y of fgl_draw_stats). */
 int fgl_debug_tile_cycles(fgl_ctx *ctx, uint64_t *dst, uint64_t ntiles);
 
+/* Self-check of the device's branch-free float64 division (the fused front end divides with the fast path of the
+ * compiler's own expansion written as straight-line code, the refinement of a reciprocal shared by the quotients of one
+ * denominator; csrc/fgl_math.cuh): `pairs` generated operand pairs -- raw bit patterns, NaN, infinities, subnormals,
+ * zeros, rasteriser-sized values -- are divided both ways on the device; *mismatches receives the results that took
+ * the helpers' fast path and differ from `a / b` or `1 / b` in any bit (must be 0), *fast_path how many took it. */
+int fgl_debug_div_check(fgl_ctx *ctx, uint64_t seed, uint64_t pairs, uint64_t *mismatches, uint64_t *fast_path);
+
 /* Fragment-rate bound of the roofline: the reference resolves every fragment with a locked
  * read-modify-write of DepthBuffer[i] (context.go:245-273); the device primitive that could replace it one
  * fragment at a time is a 64-bit atomicMin on a packed (depth, colour) key.  This measures that primitive on the

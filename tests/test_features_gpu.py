@@ -521,3 +521,19 @@ def test_recorded_frame_replays_identically(scene_name, resolve, oracle_lib, Con
             graph.launch()
     graph.Close()
     ctx.Close(); ref.Close()
+
+
+def test_branch_free_division_matches_the_operator(gpu_capi):
+    """k_front divides with the fast path of ptxas's own div.rn.f64 / rcp.rn.f64 expansions written as straight-line
+    code (one reciprocal refinement per denominator, no branch between independent divisions) and falls back to the
+    operator when the expansion's range test fails.  Wherever it does not fall back, every bit must equal `a / b` and
+    `1 / b`: 2^27 operand pairs per seed -- raw bit patterns, NaN, infinities, subnormals, zeros, rasteriser-sized values."""
+    from fauxgl_b200.context import Context
+    ctx = Context(64, 64)
+    total_fast = 0
+    for seed in (1, 2, 0xfa0c61):
+        bad, fast = ctx.DivCheck(seed, 1 << 27)
+        assert bad == 0, (seed, bad, fast)
+        total_fast += fast
+    assert total_fast > (3 << 27) // 2   # most pairs take the fast path
+    ctx.Close()
