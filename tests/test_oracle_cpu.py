@@ -245,3 +245,92 @@ def test_draw_each_equals_one_primitive_draws(oracle_lib):
     assert (each == one).all()
     assert (a.ColorBuffer == b.ColorBuffer).all()
     assert each[:, 0].sum() > 1000 and (each[:, 1] <= each[:, 0]).all()
+
+
+def _tightened_box(s, W, H):
+    """fgl_geom.cu tighten_box restated (same formulas, same constants): the rows [cy0, cy1] and the last column cx1
+    the fused front end still walks for a screen triangle s[3][2], or None when it walks nothing / does not tighten."""
+    import math
+    mnx, mxx = float(s[:, 0].min()), float(s[:, 0].max())
+    mny, mxy = float(s[:, 1].min()), float(s[:, 1].max())
+    fx0, fx1, fy0, fy1 = math.floor(mnx), math.ceil(mxx), math.floor(mny), math.ceil(mxy)
+    if not (0 <= fx0 < W and 0 <= fx1 < W):
+        return "skip"   # boxes that leave the screen sideways are not tightened
+    # edge_fn(s0, s1, s2), context.go:147-149,163
+    area = (s[1, 0] - s[2, 0]) * (s[0, 1] - s[2, 1]) - (s[1, 1] - s[2, 1]) * (s[0, 0] - s[2, 0])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ra = np.float64(1.0) / np.float64(area)
+    hx, hy = mxx - mnx, mxy - mny
+    B = max(hx, hy) + 4.0
+    E = 2.0 ** -44 * B * B * (B + 8.0)
+    k = 4.0 * E * abs(float(ra))
+    my, mx = k * hy + 1e-6, k * hx + 1e-6
+    sure = k < 0.25 and my < 0.25 and mx < 0.25
+    drop_first = 1 if (sure and mny - fy0 >= 0.5 + my) else 0
+    drop_last = (2 if fy1 - mxy >= 0.5 + my else 1) if sure else 0
+    drop_right = (2 if fx1 - mxx >= 0.5 + mx else 1) if sure else 0
+    cy0, cy1 = max(max(fy0, 0), fy0 + drop_first), min(min(fy1, H - 1), fy1 - drop_last)
+    cx1 = fx1 - drop_right
+    walked_before = max(0, min(fy1, H - 1) - max(fy0, 0) + 1)
+    if cy0 > cy1 or cx1 < fx0:
+        return (None, walked_before)
+    return ((cy0, cy1, cx1), walked_before)
+
+
+def test_tightened_boxes_never_lose_a_fragment(oracle_lib):
+    """The fused front end does not walk the rows and columns of a triangle's box that its tighten_box proves empty
+    (DESIGN.md section 4).  The proof is checked here against the oracle, without a GPU: thousands of triangles --
+    sub-pixel, a few pixels, large, slivers, vertices on pixel centres and pixel edges -- are rasterised one at a time
+    by the reference's restated loop, and every pixel it covers must lie inside the tightened box."""
+    from fauxgl_b200 import Identity, NewSolidColorShader, NewTriangleMesh, HexColor
+    W, H = 64, 32   # powers of two: the NDC -> screen mapping below is exact for dyadic coordinates
+    rng = np.random.RandomState(2024)
+    octx = pyoracle.OracleContext(W, H)
+    octx.Shader = NewSolidColorShader(Identity(), HexColor("#ffffff"))
+    octx.Cull = 1          # CullNone
+    octx.ReadDepth = False  # every covered pixel writes its depth
+    CLEAR = np.finfo(np.float64).max
+    kept = dropped = tested = vanished = covered = 0
+    for it in range(4000):
+        kind = it % 5
+        c = np.array([rng.uniform(3, W - 3), rng.uniform(3, H - 3)])
+        if kind == 0:   # sub-pixel to two pixels
+            s = c + rng.uniform(-1.2, 1.2, (3, 2))
+        elif kind == 1:  # a few pixels
+            s = c + rng.uniform(-4, 4, (3, 2))
+        elif kind == 2:  # large
+            s = np.stack([rng.uniform(1, W - 2, 3), rng.uniform(1, H - 2, 3)], axis=1)
+        elif kind == 3:  # sliver: two vertices a hair apart
+            a = c + rng.uniform(-6, 6, 2)
+            s = np.stack([a, a + rng.uniform(-1e-3, 1e-3, 2), c + rng.uniform(-6, 6, 2)])
+        else:            # vertices on pixel centres, pixel edges and quarter positions
+            s = np.round((c + rng.uniform(-3, 3, (3, 2))) * 4) / 4
+        s = np.clip(s, 0.25, [W - 1.25, H - 1.25])
+        # positions whose screen transform (matrix.go:119-128 via MulPosition) gives s; recompute s from them exactly
+        ndc = np.stack([(s[:, 0] - W / 2) / (W / 2), (H / 2 - s[:, 1]) / (H / 2)], axis=1)
+        sx = (W / 2) * ndc[:, 0] + W / 2
+        sy = -(H / 2) * ndc[:, 1] + H / 2
+        s = np.stack([sx, sy], axis=1)
+        pos = np.zeros((1, 3, 3))
+        pos[0, :, :2] = ndc
+        pos[0, :, 2] = rng.uniform(-0.5, 0.5, 3)
+        box = _tightened_box(s, W, H)
+        if box == "skip":
+            continue
+        octx.ClearDepthBuffer()
+        octx.DrawTriangles(NewTriangleMesh(pos, normal=np.ones((1, 3, 3))))
+        ys, xs = np.nonzero(octx.DepthBuffer != CLEAR)
+        tested += 1
+        covered += len(ys)
+        rows, before = box
+        if rows is None:
+            assert len(ys) == 0, (it, s, ys, xs)
+            vanished += 1
+            dropped += before
+            continue
+        cy0, cy1, cx1 = rows
+        assert (ys >= cy0).all() and (ys <= cy1).all() and (xs <= cx1).all(), (it, s.tolist(), rows, ys.tolist(), xs.tolist())
+        kept += cy1 - cy0 + 1
+        dropped += before - (cy1 - cy0 + 1)
+    assert tested > 3500 and vanished > 50 and covered > 20000, (tested, vanished, covered)
+    assert dropped > 0.2 * (kept + dropped)   # the test is not vacuous: a good share of the rows is dropped
