@@ -240,3 +240,75 @@ def test_parse_obj_tables_and_fan_triangulation(tmp_path):
     # triangles wind CCW, CCW, CW
     assert (m.normal[2:4] == [0, 0, 1]).all() and (m.normal[4, :, 2] == -1).all() and (m.normal[4, :, :2] == 0).all()
     assert (m.normal[5, 2] == m.normal[5, 0]).all()                                 # corner 3 had no vn: face normal (0,0,1)
+
+
+def test_view_volume_reject_agrees_with_sutherland_hodgman():
+    """The front ends drop a triangle with a vertex outside the view volume when the rule of fgl_geom.cu
+    clips_to_nothing says the clipper would return nothing: planes in sutherlandHodgman's order, as long as all three
+    vertices are in front of a plane the polygon passes it unchanged, the first plane with all three behind it
+    empties it, a plane that cuts the triangle ends the test.  Restated here next to clipping.go:16-52 (pure Python,
+    the same float64 operations in the same order): whenever the rule fires the clipper's output is empty -- over random
+    clip-space triangles that hug and touch the planes (the `> 0` test is strict), and it fires often enough to matter."""
+    import random
+    PLANES = [((1, 0, 0, 1), (-1, 0, 0, 1)), ((-1, 0, 0, 1), (1, 0, 0, 1)), ((0, 1, 0, 1), (0, -1, 0, 1)),
+              ((0, -1, 0, 1), (0, 1, 0, 1)), ((0, 0, 1, 1), (0, 0, -1, 1)), ((0, 0, -1, 1), (0, 0, 1, 1))]
+
+    def sub(a, b): return tuple(x - y for x, y in zip(a, b))
+    def add(a, b): return tuple(x + y for x, y in zip(a, b))
+    def dot(a, b): return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3]
+    def in_front(pl, v): return dot(sub(v, pl[0]), pl[1]) > 0
+
+    def intersect(pl, v0, v1):
+        u, w = sub(v1, v0), sub(v0, pl[0])
+        d, n = dot(pl[1], u), -dot(pl[1], w)
+        t = n / d if d != 0 else float("nan") if n == 0 else float("inf") * (1 if n > 0 else -1)
+        return add(v0, tuple(x * t for x in u))
+
+    def clipper(points):
+        out = list(points)
+        for pl in PLANES:
+            inp, out = out, []
+            if not inp:
+                return []
+            s = inp[-1]
+            for e in inp:
+                if in_front(pl, e):
+                    if not in_front(pl, s):
+                        out.append(intersect(pl, s, e))
+                    out.append(e)
+                elif in_front(pl, s):
+                    out.append(intersect(pl, s, e))
+                s = e
+        return out
+
+    def rule(o):
+        for pl in PLANES:
+            f = [in_front(pl, v) for v in o]
+            if not any(f):
+                return True
+            if not all(f):
+                return False
+        return False
+
+    rnd = random.Random(7)
+    fired = 0
+    for it in range(60000):
+        w = [rnd.choice((1.0, 2.5, rnd.uniform(0.5, 9.0))) for _ in range(3)]
+        o = []
+        for k in range(3):
+            v = []
+            for _ in range(3):
+                mode = rnd.randrange(5)
+                if mode == 0:
+                    v.append(rnd.choice((-1.0, 1.0)) * w[k])                          # exactly on a plane
+                elif mode == 1:
+                    v.append(rnd.choice((-1.0, 1.0)) * w[k] * (1 + rnd.uniform(-1e-15, 1e-15)))  # an ulp or two off it
+                elif mode == 2:
+                    v.append(rnd.uniform(-1, 1) * w[k])                               # inside
+                else:
+                    v.append(rnd.uniform(1.0, 3.0) * w[k] * rnd.choice((-1.0, 1.0)))  # outside
+            o.append((v[0], v[1], v[2], w[k]))
+        if rule(o):
+            fired += 1
+            assert clipper(o) == [], (it, o)
+    assert fired > 3000, fired
