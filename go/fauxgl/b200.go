@@ -126,6 +126,15 @@ func (d *deviceContext) resolve(factor int, dst []uint8) error {
 	return lastError(d.h, C.fgl_resolve(d.h, C.int(factor), (*C.uint8_t)(unsafe.Pointer(&dst[0]))))
 }
 
+// divCheck runs the device's self-check of its branch-free float64 division
+// (fgl_debug_div_check): `pairs` generated operand pairs are divided with the
+// helpers of the fused front end and with the operator; mismatches must be 0.
+func (d *deviceContext) divCheck(seed, pairs uint64) (mismatches, fastPath uint64, err error) {
+	var bad, fast C.uint64_t
+	err = lastError(d.h, C.fgl_debug_div_check(d.h, C.uint64_t(seed), C.uint64_t(pairs), &bad, &fast))
+	return uint64(bad), uint64(fast), err
+}
+
 // newTexture uploads an ImageTexture.  *image.RGBA (what Go's PNG decoder yields
 // for 8-bit RGB) and *image.NRGBA (8-bit RGBA) are passed through as bytes;
 // MakeColor's RGBA() conversion for each is reproduced on the device
