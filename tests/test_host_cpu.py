@@ -312,3 +312,50 @@ def test_view_volume_reject_agrees_with_sutherland_hodgman():
             fired += 1
             assert clipper(o) == [], (it, o)
     assert fired > 3000, fired
+
+
+def test_select_form_of_go_max_min_equals_the_if_chain():
+    """fgl_math.cuh writes Go's math.Max / math.Min as nested selects (no branch on k_front's dependent chain).  The
+    select form and the if-chain that follows the Go source are restated here and compared bit for bit over every
+    pair of special values (signed zeros, infinities, NaN, subnormals) and random values."""
+    import math
+    import random
+    import struct
+    INF, NAN = float("inf"), struct.unpack("<d", struct.pack("<Q", 0x7ff8000000000001))[0]
+
+    def bits(x): return struct.unpack("<Q", struct.pack("<d", x))[0]
+    def sign(x): return math.copysign(1.0, x) < 0
+
+    def max_chain(x, y):   # math.Max, with the special cases in the order the device code had them
+        if x > y: return x
+        if y > x: return y
+        if x == y: return y if (x == 0 and sign(x)) else x
+        if x == INF or y == INF: return INF
+        return NAN
+
+    def max_select(x, y):
+        r_eq = y if sign(x) else x
+        r_nan = INF if (x == INF or y == INF) else NAN
+        return x if x > y else (y if y > x else (r_eq if x == y else r_nan))
+
+    def min_chain(x, y):
+        if x < y: return x
+        if y < x: return y
+        if x == y: return y if (x == 0 and not sign(x)) else x
+        if x == -INF or y == -INF: return -INF
+        return NAN
+
+    def min_select(x, y):
+        r_eq = x if sign(x) else y
+        r_nan = -INF if (x == -INF or y == -INF) else NAN
+        return x if x < y else (y if y < x else (r_eq if x == y else r_nan))
+
+    rnd = random.Random(3)
+    vals = [0.0, -0.0, 1.0, -1.0, INF, -INF, NAN, 5e-324, -5e-324, 1.5, -2.25, 1e308, -1e308]
+    vals += [rnd.uniform(-10, 10) for _ in range(40)]
+    for x in vals:
+        for y in vals:
+            a, b = max_chain(x, y), max_select(x, y)
+            assert bits(a) == bits(b) or (a != a and b != b), (x, y, a, b)
+            a, b = min_chain(x, y), min_select(x, y)
+            assert bits(a) == bits(b) or (a != a and b != b), (x, y, a, b)
